@@ -498,9 +498,17 @@ int ref_pairsite_de_pair(void *h, void *config_h, int64_t n, const int64_t *a, c
   try {
     const auto *p = static_cast<pred::EnergyChangePredictorPairSite *>(h);
     const auto &c = *static_cast<cfg::Config *>(config_h);
+    std::string err;
 #pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
-    for (int64_t k = 0; k < n; ++k)
-      out[k] = p->GetDeFromLatticeIdPair(c, {static_cast<size_t>(a[k]), static_cast<size_t>(b[k])});
+    for (int64_t k = 0; k < n; ++k) {
+      try {
+        out[k] = p->GetDeFromLatticeIdPair(c, {static_cast<size_t>(a[k]), static_cast<size_t>(b[k])});
+      } catch (const std::exception &e) {
+#pragma omp critical
+        err = e.what();
+      }
+    }
+    if (!err.empty()) throw std::runtime_error(err);
     return 0;
   } catch (const std::exception &e) { return fail(e); }
 }
@@ -509,9 +517,17 @@ int ref_pairsite_de_site(void *h, void *config_h, int64_t n, const int64_t *site
   try {
     const auto *p = static_cast<pred::EnergyChangePredictorPairSite *>(h);
     const auto &c = *static_cast<cfg::Config *>(config_h);
+    std::string err;
 #pragma omp parallel for num_threads(threads > 0 ? threads : 1) schedule(static)
-    for (int64_t k = 0; k < n; ++k)
-      out[k] = p->GetDeFromLatticeIdSite(c, static_cast<size_t>(site[k]), element_from_code(new_code[k]));
+    for (int64_t k = 0; k < n; ++k) {
+      try {
+        out[k] = p->GetDeFromLatticeIdSite(c, static_cast<size_t>(site[k]), element_from_code(new_code[k]));
+      } catch (const std::exception &e) {
+#pragma omp critical
+        err = e.what();
+      }
+    }
+    if (!err.empty()) throw std::runtime_error(err);
     return 0;
   } catch (const std::exception &e) { return fail(e); }
 }
