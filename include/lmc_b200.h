@@ -1,0 +1,157 @@
+/* lmc_b200.h -- C ABI of the B200-native LatticeMC hot-path engine (liblmc_b200.so).
+ *
+ * The reference (zhucongx/LatticeMonteCarlo) has no plugin / FFI boundary: its hot path is reached through
+ * three C++ predictor classes and the mc:: drivers.  This header is the boundary a
+ * reference-side binding would use instead; every entry point names the reference interface it replaces.
+ * INTEGRATION.md shows the C++ adapter classes (same names / signatures as the reference's) that forward here.
+ *
+ * Conventions
+ *  - all functions return 0 on success, a negative lmc_status on failure; lmc_last_error() gives the message
+ *    (thread local).  The C++ adapters re-throw the reference's exception types from these codes.
+ *  - element codes are the reference's ElementName enum values (lmc/cfg/include/Element.hpp:7):
+ *    X(vacancy)=0, Al=1, Mg=2, Zn=3, Cu=4, Sn=5, pAl=6 ... pSn=10.
+ *  - lattice ids are the reference's lattice ids in one of its two id orders (lmc_id_order).
+ *  - host pointers unless the name ends in _dev; buffers are caller-owned; calls are synchronous.
+ *  - one engine per GPU; an engine is not thread safe (callers serialise), engines are independent.
+ *  - there is NO CPU fallback: every compute entry point fails with LMC_ERR_NO_DEVICE if the engine was created
+ *    without a CUDA device (device < 0 is allowed only for the lmc_tables_* / geometry queries below).
+ */
+#ifndef LMC_B200_H_
+#define LMC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lmc_engine lmc_engine;
+
+typedef enum lmc_status {
+  LMC_OK = 0,
+  LMC_ERR_INVALID_ARGUMENT = -1, /* std::invalid_argument in the adapters */
+  LMC_ERR_OUT_OF_RANGE = -2,     /* std::out_of_range: non-neighbour jump pair (VacancyMigrationPredictorQuartic.cpp:281-283),
+                                    cluster type without index, e.g. two vacancies in range (EnergyUtility.cpp:815-817) */
+  LMC_ERR_RUNTIME = -3,          /* std::runtime_error: "Cannot open <file>", JSON errors */
+  LMC_ERR_NO_DEVICE = -4,        /* compute call on a host-only engine / CUDA extension unusable */
+  LMC_ERR_CUDA = -5              /* CUDA runtime failure */
+} lmc_status;
+
+typedef enum lmc_id_order {
+  LMC_ID_ORDER_GENERATE = 0,   /* cfg::GenerateFCC order (cfg/src/Config.cpp:1073-1090); used by SimulatedAnnealing */
+  LMC_ID_ORDER_REASSIGNED = 1  /* Config::ReassignLatticeVector order (Config.cpp:466-552); every run started from a .cfg */
+} lmc_id_order;
+
+const char *lmc_last_error(void);
+int lmc_abi_version(void);
+/* number of CUDA devices visible to the library (0 if none) */
+int lmc_device_count(void);
+
+/* ------------------------------------------------------------------------------------------------ engine
+ * Replaces construction of cfg::Config neighbour lists (Config::UpdateNeighbors, Config.cpp:955-1045) and of the
+ * per-site tables in the predictor constructors (VacancyMigrationPredictorQuartic.cpp:64-100,
+ * EnergyChangePredictorPairSite.cpp:41-57): geometry becomes constant offset tables, occupancy one uint8 per site.
+ *   factors        supercell size in conventional FCC cells per axis (each >= 4, like the reference's cell list)
+ *   id_order       lmc_id_order
+ *   element_set    the `element_set` of the parameter file (ElementName codes, vacancy excluded), n_elements <= 7
+ *   solvent        ElementName code of the majority species (expansion origin of the contracted tables; any member of
+ *                  element_set gives identical results, the majority species gives the best speed); 0 = first in set
+ *   n_walkers      number of independent replicas of the lattice held on the device (>= 1)
+ *   device         CUDA device ordinal, or -1 for a host-only engine (table / geometry queries only)
+ */
+int lmc_engine_create(lmc_engine **out, const int32_t factors[3], int32_t id_order, const int32_t *element_set,
+                      int32_t n_elements, int32_t solvent, int32_t n_walkers, int32_t device);
+void lmc_engine_destroy(lmc_engine *engine);
+int64_t lmc_engine_num_sites(const lmc_engine *engine);
+int32_t lmc_engine_num_walkers(const lmc_engine *engine);
+
+/* JSON coefficient file in the reference's format: {"Base":{"theta":[...]}, "<El>":{"mu_x_mmm":..,"U_mmm":..,..}}
+ * (parsed like pred/src/VacancyMigrationPredictorQuartic.cpp:38-63, EnergyChangePredictorPairSite.cpp:29-40,
+ * EnergyPredictor.cpp:27-38).  Missing file -> LMC_ERR_RUNTIME "Cannot open <file>". */
+int lmc_engine_load_coefficients(lmc_engine *engine, const char *json_path);
+
+/* Occupancy by lattice id (ElementName codes), one replica ("walker") at a time or all at once (n_walkers*N bytes).
+ * Replaces cfg::Config::{SetAtomElementTypeAtLattice, GetElementAtLatticeId} (Config.cpp:132-135,462-464). */
+int lmc_engine_set_occupancy(lmc_engine *engine, int32_t walker, const uint8_t *occupancy, int64_t n);
+int lmc_engine_get_occupancy(lmc_engine *engine, int32_t walker, uint8_t *occupancy, int64_t n);
+int lmc_engine_set_occupancy_all(lmc_engine *engine, const uint8_t *occupancy, int64_t n_total);
+int lmc_engine_get_occupancy_all(lmc_engine *engine, uint8_t *occupancy, int64_t n_total);
+/* Config::LatticeJump (Config.cpp:431-456) as far as occupancy is concerned: exchange the species of two sites */
+int lmc_engine_lattice_jump(lmc_engine *engine, int32_t walker, int64_t site_a, int64_t site_b);
+
+/* ------------------------------------------------------------------------------------------------ hot path
+ * VacancyMigrationPredictorQuartic::GetBarrierAndDiffFromLatticeIdPair (pred/include/VacancyMigrationPredictorQuartic.h:25-27,
+ * src :247-276) for a batch of candidate events: event e is the exchange of the vacancy at site_i[e] with the atom at
+ * site_j[e] on replica walker[e] (walker == NULL: replica 0).  D / Ks (GetD :216-246, GetKs :167-215) are optional.
+ * Replaces the LRU-cached predictor (VacancyMigrationPredictorQuarticLru.cpp:11-49) by batch recomputation.
+ * A non-neighbour pair, a first site that is not a vacancy, or a second vacancy within range makes the call
+ * return LMC_ERR_OUT_OF_RANGE (outputs of the offending events are NaN, all others are valid). */
+int lmc_eval_barriers(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j,
+                      double *Ea, double *dE, double *D, double *Ks);
+/* same with every pointer in device memory (inputs already resident in HBM; asynchronous on the engine stream) */
+int lmc_eval_barriers_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_i,
+                          const int64_t *site_j, double *Ea, double *dE, double *D, double *Ks);
+
+/* EnergyChangePredictorPairSite::GetDeFromLatticeIdPair (pred/include/EnergyChangePredictorPairSite.h:20-23,
+ * src :70-146): energy change of exchanging the species at site_a[e] and site_b[e]; 0 for equal species; coupled
+ * pairs (b within the third shell of a) are evaluated exactly. */
+int lmc_eval_swap_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a, const int64_t *site_b,
+                     double *dE);
+int lmc_eval_swap_de_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a,
+                         const int64_t *site_b, double *dE);
+/* EnergyChangePredictorPairSite::GetDeFromLatticeIdSite (:154-192): species at `site` replaced by new_element */
+int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site,
+                     const uint8_t *new_element, double *dE);
+/* EnergyPredictor::GetEnergy / GetEncode (pred/src/EnergyPredictor.cpp:40-96,173-177) of one replica.
+ * counts (optional, n_types int64) receives the exact integer cluster counts of GetEncode before normalisation. */
+int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t *counts, int32_t n_types);
+
+/* ------------------------------------------------------------------------------------------------ debug taps
+ * Integer artefacts of the reference's algorithm, recomputed on the device, for bit-exact parity checks.
+ * lists: the symmetry-ordered lattice-id lists of pair (site_i, site_j)
+ *   state[60]  GetSortedLatticeVectorStateOfPair       (pred/src/EnergyUtility.cpp:261-287)
+ *   mmm[58]    GetSymmetricallySortedLatticeVectorMMM  (:45-74)
+ *   mm2[58]    GetSymmetricallySortedLatticeVectorMM2  (:75-104)
+ *   mm2_backward[58]  the same for the reversed pair (site_j, site_i), as used by GetKs (:187-188)
+ * counts: start/end cluster-type histograms of GetDe (VacancyMigrationPredictorQuartic.cpp:124-154), n_types each
+ * encodes: integer numerators of GetOneHotParametersFromMap (EnergyUtility.cpp:743-796): per slot the number of
+ *   clusters of that type (the reference's encode is this divided by the group size, see lmc_tables_group_sizes). */
+int lmc_debug_pair(lmc_engine *engine, int32_t walker, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
+                   int64_t *mm2_58, int64_t *mm2_backward58, int32_t *start_counts, int32_t *end_counts,
+                   int32_t *enc_mmm, int32_t *enc_mm2_forward, int32_t *enc_mm2_backward);
+/* GetSortedLatticeVectorStateOfSite (:288-313) + the counts of GetDeFromLatticeIdSite */
+int lmc_debug_site(lmc_engine *engine, int32_t walker, int64_t site, int32_t new_element, int64_t *state43,
+                   int32_t *start_counts, int32_t *end_counts);
+
+/* ------------------------------------------------------------------------------------------------ host-side tables
+ * (no device needed).  Neighbour lists in ascending lattice id like Config::Get{First,Second,Third}NeighborsAdjacencyList. */
+int lmc_engine_neighbors(const lmc_engine *engine, int32_t shell, int64_t site, int64_t *out);
+int lmc_engine_site_coords(const lmc_engine *engine, int64_t site, int32_t xyz_half_units[3]);
+/* host evaluation of the ordered id lists (same definition as lmc_debug_pair / lmc_debug_site) */
+int lmc_engine_pair_lists(const lmc_engine *engine, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
+                          int64_t *mm2_58, int64_t *mm2_backward58);
+int lmc_engine_site_list(const lmc_engine *engine, int64_t site, int64_t *state43);
+/* cluster mappings in list positions, flattened as: G, then per group: C, L, C*L entries (-1 = SIZE_MAX marker).
+ * which: 0 GetClusterParametersMappingStatePair, 1 GetAverageClusterParametersMappingMMM, 2 ...MM2,
+ * 3 GetClusterParametersMappingStateSite (pred/src/EnergyUtility.cpp:169-259,393-581). Returns the length needed. */
+int64_t lmc_tables_mapping(int32_t which, int64_t *out, int64_t capacity);
+/* cluster types in pred::ClusterIndexer order: rows [label, size, e1, e2, e3] (ElementName codes, -1 padded).
+ * Returns the number of types (= required length of Base.theta). */
+int32_t lmc_tables_cluster_types(const int32_t *element_set, int32_t n_elements, int32_t *rows5, int32_t capacity_rows);
+/* encode vector lengths and per-slot group sizes of the mmm (which=1) / mm2 (which=2) mappings */
+int32_t lmc_tables_group_sizes(int32_t which, int32_t n_elements, int32_t *sizes, int32_t capacity);
+
+/* Introspection of the contracted coefficient tables (host copies; engine must have coefficients loaded).
+ * which: 0 pair_C [m][3], 1 pair_A [m][58][n][3], 2 pair_B [m][556][n][n][3]   (jump tables: dE, logD, logKs)
+ *        3 site_C [x],    4 site_A [x][42][n+1],  5 site_B [x][204][n+1][n+1]  (single-site tables, codes incl. vacancy)
+ * Species codes are positions in the element set sorted by name; the vacancy is code n.  Returns the length. */
+int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *out, int64_t capacity);
+/* environment pairs (t,u), t<u, as indices into the environment (ordered state list without the centre site(s)):
+ * which 0: the 556 pairs of the jump environment, 1: the 204 pairs of the site environment. Returns the pair count. */
+int32_t lmc_tables_env_pairs(int32_t which, int16_t *pairs, int32_t capacity_pairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMC_B200_H_ */

@@ -1,0 +1,258 @@
+"""ctypes binding of the C ABI in include/lmc_b200.h (liblmc_b200.so).
+
+This is plumbing for tests / bench.py / the Python host mirror; the product is the shared library.
+There is no fallback: if the library is missing or no CUDA device is usable, compute calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblmc_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lmc_b200.h")
+
+LMC_OK, LMC_ERR_INVALID_ARGUMENT, LMC_ERR_OUT_OF_RANGE, LMC_ERR_RUNTIME, LMC_ERR_NO_DEVICE, LMC_ERR_CUDA = 0, -1, -2, -3, -4, -5
+ORDER_GENERATE, ORDER_REASSIGNED = 0, 1
+
+
+class LmcError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("[lmc %d] %s" % (code, message))
+        self.code = code
+
+
+class LmcInvalidArgument(LmcError, ValueError):
+    pass
+
+
+class LmcOutOfRange(LmcError, IndexError):
+    """std::out_of_range of the reference (non-neighbour pair, cluster without index)."""
+
+
+_lib = None
+
+
+def declared_symbols():
+    """Every function name declared in include/lmc_b200.h."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lmc_[a-z0-9_]+)\s*\(", text)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("liblmc_b200.so not built: run `python -m latticemontecarlo_b200.build` "
+                               "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.lmc_last_error.restype = C.c_char_p
+        _lib.lmc_engine_num_sites.restype = C.c_int64
+        _lib.lmc_tables_mapping.restype = C.c_int64
+        _lib.lmc_engine_destroy.restype = None
+    return _lib
+
+
+def _check(rc):
+    if rc >= 0:
+        return rc
+    msg = lib().lmc_last_error().decode()
+    cls = {LMC_ERR_INVALID_ARGUMENT: LmcInvalidArgument, LMC_ERR_OUT_OF_RANGE: LmcOutOfRange}.get(rc, LmcError)
+    raise cls(rc, msg)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def device_count():
+    return int(lib().lmc_device_count())
+
+
+def tables_mapping(which):
+    """which: 'state_pair' | 'mmm' | 'mm2' | 'state_site' -> list of groups of position tuples (-1 = SIZE_MAX)."""
+    w = {"state_pair": 0, "mmm": 1, "mm2": 2, "state_site": 3}[which]
+    n = _check(lib().lmc_tables_mapping(w, None, C.c_int64(0)))
+    flat = np.empty(n, dtype=np.int64)
+    _check(lib().lmc_tables_mapping(w, _p(flat), C.c_int64(n)))
+    pos, groups = 1, []
+    for _ in range(int(flat[0])):
+        c, l = int(flat[pos]), int(flat[pos + 1])
+        pos += 2
+        groups.append([tuple(int(v) for v in row) for row in flat[pos:pos + c * l].reshape(c, l)])
+        pos += c * l
+    return groups
+
+
+def tables_cluster_types(element_set):
+    es = np.ascontiguousarray(element_set, dtype=np.int32)
+    n = _check(lib().lmc_tables_cluster_types(_p(es), len(es), None, 0))
+    rows = np.empty((n, 5), dtype=np.int32)
+    _check(lib().lmc_tables_cluster_types(_p(es), len(es), _p(rows), n))
+    return [(int(r[0]), tuple(int(v) for v in r[2:2 + r[1]])) for r in rows]
+
+
+def tables_group_sizes(which, n_elements):
+    w = {"mmm": 1, "mm2": 2}[which]
+    n = _check(lib().lmc_tables_group_sizes(w, int(n_elements), None, 0))
+    sizes = np.zeros(n, dtype=np.int32)
+    _check(lib().lmc_tables_group_sizes(w, int(n_elements), _p(sizes), n))
+    return sizes
+
+
+def tables_env_pairs(which):
+    w = {"pair": 0, "site": 1}[which]
+    n = _check(lib().lmc_tables_env_pairs(w, None, 0))
+    out = np.empty((n, 2), dtype=np.int16)
+    _check(lib().lmc_tables_env_pairs(w, _p(out), n))
+    return out
+
+
+class Engine:
+    """One lmc_engine (one GPU, or host-only with device=-1)."""
+
+    def __init__(self, factors, id_order=ORDER_REASSIGNED, element_set=(1, 2, 3), solvent=1, n_walkers=1, device=0):
+        if np.isscalar(factors):
+            factors = (int(factors),) * 3
+        self.factors = tuple(int(f) for f in factors)
+        f = (C.c_int32 * 3)(*self.factors)
+        es = np.ascontiguousarray(element_set, dtype=np.int32)
+        self.element_set = tuple(int(e) for e in es)
+        h = C.c_void_p()
+        _check(lib().lmc_engine_create(C.byref(h), f, int(id_order), _p(es), len(es), int(solvent), int(n_walkers), int(device)))
+        self.h = h
+        self.num_sites = int(lib().lmc_engine_num_sites(self.h))
+        self.n_walkers = int(n_walkers)
+        self.device = int(device)
+        self.n_types = len(tables_cluster_types(self.element_set))
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().lmc_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state
+    def load_coefficients(self, json_path):
+        _check(lib().lmc_engine_load_coefficients(self.h, str(json_path).encode()))
+
+    def set_occupancy(self, occ, walker=0):
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        _check(lib().lmc_engine_set_occupancy(self.h, int(walker), _p(occ), C.c_int64(occ.size)))
+
+    def get_occupancy(self, walker=0):
+        out = np.empty(self.num_sites, dtype=np.uint8)
+        _check(lib().lmc_engine_get_occupancy(self.h, int(walker), _p(out), C.c_int64(out.size)))
+        return out
+
+    def set_occupancy_all(self, occ):
+        occ = np.ascontiguousarray(occ, dtype=np.uint8)
+        _check(lib().lmc_engine_set_occupancy_all(self.h, _p(occ), C.c_int64(occ.size)))
+
+    def get_occupancy_all(self):
+        out = np.empty((self.n_walkers, self.num_sites), dtype=np.uint8)
+        _check(lib().lmc_engine_get_occupancy_all(self.h, _p(out), C.c_int64(out.size)))
+        return out
+
+    def lattice_jump(self, a, b, walker=0):
+        _check(lib().lmc_engine_lattice_jump(self.h, int(walker), C.c_int64(int(a)), C.c_int64(int(b))))
+
+    def get_tables(self):
+        """Host copies of the contracted coefficient tables, reshaped (see lmc_engine_get_tables)."""
+        lib().lmc_engine_get_tables.restype = C.c_int64
+        raw = []
+        for which in range(6):
+            n = _check(lib().lmc_engine_get_tables(self.h, which, None, C.c_int64(0)))
+            buf = np.empty(n, dtype=np.float64)
+            _check(lib().lmc_engine_get_tables(self.h, which, _p(buf), C.c_int64(n)))
+            raw.append(buf)
+        n = len(self.element_set)
+        m = n + 1
+        return dict(pair_C=raw[0].reshape(n, 3), pair_A=raw[1].reshape(n, 58, n, 3), pair_B=raw[2].reshape(n, -1, n, n, 3),
+                    site_C=raw[3].reshape(m), site_A=raw[4].reshape(m, 42, m), site_B=raw[5].reshape(m, -1, m, m))
+
+    # ---- hot path
+    def eval_barriers(self, site_i, site_j, walker=None, want_parts=False):
+        i, j = _i64(site_i), _i64(site_j)
+        n = len(i)
+        w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)
+        ea = np.empty(n); de = np.empty(n)
+        d = np.empty(n) if want_parts else None
+        ks = np.empty(n) if want_parts else None
+        _check(lib().lmc_eval_barriers(self.h, C.c_int64(n), _p(w), _p(i), _p(j), _p(ea), _p(de), _p(d), _p(ks)))
+        return (ea, de, d, ks) if want_parts else (ea, de)
+
+    def eval_swap_de(self, site_a, site_b, walker=None):
+        a, b = _i64(site_a), _i64(site_b)
+        w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)
+        out = np.empty(len(a))
+        _check(lib().lmc_eval_swap_de(self.h, C.c_int64(len(a)), _p(w), _p(a), _p(b), _p(out)))
+        return out
+
+    def eval_site_de(self, site, new_element, walker=None):
+        s = _i64(site)
+        e = np.ascontiguousarray(new_element, dtype=np.uint8)
+        w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)
+        out = np.empty(len(s))
+        _check(lib().lmc_eval_site_de(self.h, C.c_int64(len(s)), _p(w), _p(s), _p(e), _p(out)))
+        return out
+
+    def total_energy(self, walker=0, want_counts=False):
+        e = C.c_double()
+        counts = np.zeros(self.n_types, dtype=np.int64) if want_counts else None
+        _check(lib().lmc_total_energy(self.h, int(walker), C.byref(e), _p(counts), self.n_types if want_counts else 0))
+        return (e.value, counts) if want_counts else e.value
+
+    # ---- debug taps (device)
+    def debug_pair(self, i, j, walker=0):
+        n_e = len(self.element_set)
+        len_mmm = len(tables_group_sizes("mmm", n_e)); len_mm2 = len(tables_group_sizes("mm2", n_e))
+        out = dict(state=np.empty(60, np.int64), mmm=np.empty(58, np.int64), mm2=np.empty(58, np.int64),
+                   mm2_backward=np.empty(58, np.int64), start_counts=np.empty(self.n_types, np.int32),
+                   end_counts=np.empty(self.n_types, np.int32), enc_mmm=np.empty(len_mmm, np.int32),
+                   enc_mm2_f=np.empty(len_mm2, np.int32), enc_mm2_b=np.empty(len_mm2, np.int32))
+        _check(lib().lmc_debug_pair(self.h, int(walker), C.c_int64(int(i)), C.c_int64(int(j)), _p(out["state"]), _p(out["mmm"]),
+                                    _p(out["mm2"]), _p(out["mm2_backward"]), _p(out["start_counts"]), _p(out["end_counts"]),
+                                    _p(out["enc_mmm"]), _p(out["enc_mm2_f"]), _p(out["enc_mm2_b"])))
+        return out
+
+    def debug_site(self, site, new_element, walker=0):
+        out = dict(state=np.empty(43, np.int64), start_counts=np.empty(self.n_types, np.int32),
+                   end_counts=np.empty(self.n_types, np.int32))
+        _check(lib().lmc_debug_site(self.h, int(walker), C.c_int64(int(site)), int(new_element), _p(out["state"]),
+                                    _p(out["start_counts"]), _p(out["end_counts"])))
+        return out
+
+    # ---- host geometry
+    def neighbors(self, shell, site):
+        out = np.empty({1: 12, 2: 6, 3: 24}[shell], dtype=np.int64)
+        _check(lib().lmc_engine_neighbors(self.h, int(shell), C.c_int64(int(site)), _p(out)))
+        return out
+
+    def site_coords(self, site):
+        out = (C.c_int32 * 3)()
+        _check(lib().lmc_engine_site_coords(self.h, C.c_int64(int(site)), out))
+        return tuple(out)
+
+    def pair_lists(self, i, j):
+        s = np.empty(60, np.int64); m = np.empty(58, np.int64); m2 = np.empty(58, np.int64); mb = np.empty(58, np.int64)
+        _check(lib().lmc_engine_pair_lists(self.h, C.c_int64(int(i)), C.c_int64(int(j)), _p(s), _p(m), _p(m2), _p(mb)))
+        return s, m, m2, mb
+
+    def site_list(self, site):
+        s = np.empty(43, np.int64)
+        _check(lib().lmc_engine_site_list(self.h, C.c_int64(int(site)), _p(s)))
+        return s

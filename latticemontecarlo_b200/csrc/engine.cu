@@ -1,0 +1,764 @@
+// engine.cu -- engine object and the extern "C" boundary declared in include/lmc_b200.h.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lmc_b200.h"
+#include "engine.h"
+#include "kernels.cuh"
+#include "tables.h"
+
+namespace lmc {
+
+thread_local std::string g_last_error;
+
+struct StatusError : std::runtime_error {
+  int code;
+  StatusError(int c, const std::string &what) : std::runtime_error(what), code(c) {}
+};
+
+#define LMC_CUDA(call)                                                                                     \
+  do {                                                                                                     \
+    cudaError_t err__ = (call);                                                                            \
+    if (err__ != cudaSuccess)                                                                              \
+      throw StatusError(LMC_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(err__));       \
+  } while (0)
+
+int guard(const std::function<void()> &fn) {
+  try {
+    fn();
+    return LMC_OK;
+  } catch (const StatusError &e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::invalid_argument &e) {
+    g_last_error = e.what();
+    return LMC_ERR_INVALID_ARGUMENT;
+  } catch (const std::out_of_range &e) {
+    g_last_error = e.what();
+    return LMC_ERR_OUT_OF_RANGE;
+  } catch (const std::exception &e) {
+    g_last_error = e.what();
+    return LMC_ERR_RUNTIME;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Engine
+Engine::Engine(const int32_t factors[3], int32_t id_order, const int32_t *element_set, int32_t n_elements, int32_t solvent,
+               int32_t n_walkers_, int32_t device_)
+    : n_walkers(n_walkers_), device(device_) {
+  for (int d = 0; d < 3; ++d)
+    if (factors[d] < 4) throw std::invalid_argument("supercell factors must be >= 4 (the reference's cell list needs 3 cells of 5.3 A per axis)");
+  if (id_order != LMC_ID_ORDER_GENERATE && id_order != LMC_ID_ORDER_REASSIGNED) throw std::invalid_argument("unknown id order");
+  if (n_walkers < 1) throw std::invalid_argument("n_walkers must be >= 1");
+  lat = make_lattice(factors[0], factors[1], factors[2], id_order);
+  species = make_species(element_set, n_elements, solvent);
+  const Geometry &g = geometry();
+  if (g.pair_first_pos != kFirstPos || g.pair_second_pos != kSecondPos || g.site_centre_pos != kCentrePos)
+    throw std::logic_error("ordered-neighbourhood structural constants changed");
+  if (device >= 0) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count)
+      throw StatusError(LMC_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
+    LMC_CUDA(cudaSetDevice(device));
+    LMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    LMC_CUDA(cudaMalloc(&d_occ, static_cast<size_t>(n_walkers) * lat.padded_size));
+    LMC_CUDA(cudaMalloc(&d_error, sizeof(int)));
+    LMC_CUDA(cudaMemsetAsync(d_error, 0, sizeof(int), stream));
+    upload_geometry_tables();
+  }
+}
+
+Engine::~Engine() {
+  if (device >= 0) {
+    cudaSetDevice(device);
+    for (void *p : device_allocs) cudaFree(p);
+    cudaFree(d_occ);
+    cudaFree(d_error);
+    cudaFree(d_scratch);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    if (stream) cudaStreamDestroy(stream);
+  }
+}
+
+void Engine::require_device() const {
+  if (device < 0) throw StatusError(LMC_ERR_NO_DEVICE, "compute call on a host-only engine: there is no CPU fallback");
+  cudaSetDevice(device);
+}
+void Engine::require_coefficients() const {
+  if (!has_coefficients) throw std::invalid_argument("coefficients not loaded (lmc_engine_load_coefficients)");
+}
+
+template <class T>
+const T *Engine::to_device(const std::vector<T> &v) {
+  void *p = nullptr;
+  LMC_CUDA(cudaMalloc(&p, std::max<size_t>(v.size() * sizeof(T), 16)));
+  LMC_CUDA(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));   // v may be a temporary
+  device_allocs.push_back(p);
+  return static_cast<const T *>(p);
+}
+
+void *Engine::scratch(size_t bytes) {
+  if (bytes > scratch_bytes) {
+    LMC_CUDA(cudaStreamSynchronize(stream));
+    cudaFree(d_scratch);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    scratch_bytes = std::max(bytes, scratch_bytes * 2);
+    LMC_CUDA(cudaMalloc(&d_scratch, scratch_bytes));
+    LMC_CUDA(cudaMallocHost(&h_pinned, scratch_bytes));
+  }
+  return d_scratch;
+}
+
+void Engine::upload_geometry_tables() {
+  const Geometry &g = geometry();
+  std::vector<int32_t> pair_delta(24 * kPairDeltaStride, 0), site_delta(2 * 43);
+  for (int k = 0; k < 12; ++k)
+    for (int zp = 0; zp < 2; ++zp)
+      for (int t = 0; t < 60; ++t) {
+        const Int3 o = g.pair_offsets[k][0][t];   // values are frame independent: the fast kernels use flag 0 throughout
+        pair_delta[(k * 2 + zp) * kPairDeltaStride + t] = lat.padded_delta(o.x, o.y, o.z, zp);
+      }
+  for (int zp = 0; zp < 2; ++zp)
+    for (int t = 0; t < 43; ++t) site_delta[zp * 43 + t] = lat.padded_delta(g.site_offsets[t].x, g.site_offsets[t].y, g.site_offsets[t].z, zp);
+  std::vector<int8_t> dir_lut(27, -1), nn1(48, 0), frame_p(48, 0), pair_off(12 * 2 * 60 * 4, 0), site_off(43 * 4, 0);
+  for (int k = 0; k < 12; ++k) {
+    const Int3 d = g.nn1[k], p = g.frame_p[k];
+    dir_lut[(d.x + 1) * 9 + (d.y + 1) * 3 + (d.z + 1)] = static_cast<int8_t>(k);
+    nn1[4 * k] = d.x; nn1[4 * k + 1] = d.y; nn1[4 * k + 2] = d.z;
+    frame_p[4 * k] = p.x; frame_p[4 * k + 1] = p.y; frame_p[4 * k + 2] = p.z;
+    for (int s = 0; s < 2; ++s)
+      for (int t = 0; t < 60; ++t) {
+        const Int3 o = g.pair_offsets[k][s][t];
+        int8_t *dst = &pair_off[((k * 2 + s) * 60 + t) * 4];
+        dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+      }
+  }
+  for (int t = 0; t < 43; ++t) {
+    site_off[4 * t] = g.site_offsets[t].x; site_off[4 * t + 1] = g.site_offsets[t].y; site_off[4 * t + 2] = g.site_offsets[t].z;
+  }
+  tab.pair_delta = to_device(pair_delta);
+  tab.site_delta = to_device(site_delta);
+  tab.dir_lut = to_device(dir_lut);
+  tab.nn1 = to_device(nn1);
+  tab.frame_p = to_device(frame_p);
+  tab.pair_off = to_device(pair_off);
+  tab.site_off = to_device(site_off);
+  tab.pair_first_pos = g.pair_first_pos;
+  tab.pair_second_pos = g.pair_second_pos;
+  tab.site_centre_pos = g.site_centre_pos;
+  tab.n_species = species.n;
+  tab.solvent = species.solvent;
+  std::vector<uint64_t> pmask(g.env_pair_mask_hi.begin(), g.env_pair_mask_hi.end()), smask(g.site_pair_mask_hi.begin(), g.site_pair_mask_hi.end());
+  std::vector<uint16_t> pbase(g.env_pair_base.begin(), g.env_pair_base.end()), sbase(g.site_pair_base.begin(), g.site_pair_base.end());
+  tab.pair_mask_hi = to_device(pmask);
+  tab.pair_base = to_device(pbase);
+  tab.site_mask_hi = to_device(smask);
+  tab.site_base = to_device(sbase);
+  tab.n_pair_pairs = static_cast<int32_t>(g.env_pairs.size());
+  tab.n_site_pairs = static_cast<int32_t>(g.site_env_pairs.size());
+  // total-energy walk in 43-list positions
+  auto site_pos = [&](Int3 o) {
+    for (int t = 0; t < 43; ++t)
+      if (g.site_offsets[t] == o) return t;
+    throw std::logic_error("offset outside the site neighbourhood");
+  };
+  std::vector<uint8_t> e_walk, e_shell;
+  for (const auto &w : g.energy_triplets) {
+    e_walk.push_back(static_cast<uint8_t>(site_pos(w.o2)));
+    e_walk.push_back(static_cast<uint8_t>(site_pos(w.o3)));
+    e_walk.push_back(static_cast<uint8_t>(w.label));
+    e_walk.push_back(0);
+  }
+  for (int t = 0; t < 43; ++t) {
+    if (t == g.site_centre_pos) continue;
+    e_shell.push_back(static_cast<uint8_t>(t));
+    e_shell.push_back(static_cast<uint8_t>(g.site_env_shell[t - (t > g.site_centre_pos)]));
+  }
+  tab.e_walk = to_device(e_walk);
+  tab.e_shell_pos = to_device(e_shell);
+  tab.n_e_walk = static_cast<int32_t>(g.energy_triplets.size());
+  // debug-tap mappings
+  const auto types = cluster_types(species);
+  const TypeLut lut = make_type_lut(species, types);
+  tab.type_lut = to_device(lut.lut);
+  tab.n_types = static_cast<int32_t>(types.size());
+  auto flat_state = [&](const std::vector<Cluster> &cl) {
+    std::vector<int8_t> out;
+    for (const auto &c : cl) {
+      out.push_back(c.label);
+      for (int q = 0; q < 3; ++q) out.push_back(q < c.arity ? static_cast<int8_t>(c.pos[q]) : -1);
+    }
+    return out;
+  };
+  tab.map_state_pair = to_device(flat_state(g.state_pair));
+  tab.n_state_pair = static_cast<int32_t>(g.state_pair.size());
+  tab.map_state_site = to_device(flat_state(g.state_site));
+  tab.n_state_site = static_cast<int32_t>(g.state_site.size());
+  int len_mmm = 0, len_mm2 = 0;
+  const auto gm = group_layout(g, false, species.n, &len_mmm);
+  const auto g2 = group_layout(g, true, species.n, &len_mm2);
+  auto flat_avg = [&](const std::vector<Cluster> &cl, const std::vector<GroupInfo> &groups) {
+    std::vector<int16_t> out;
+    for (const auto &c : cl) {
+      out.push_back(static_cast<int16_t>(groups[c.group].offset));
+      out.push_back(c.pos[0]);
+      out.push_back(c.arity == 2 ? c.pos[1] : static_cast<int16_t>(-1));
+      out.push_back(c.symmetric ? 1 : 0);
+    }
+    return out;
+  };
+  tab.map_mmm = to_device(flat_avg(g.mmm, gm));
+  tab.map_mm2 = to_device(flat_avg(g.mm2, g2));
+  tab.n_avg_clusters = static_cast<int32_t>(g.mmm.size());
+  tab.len_mmm = len_mmm;
+  tab.len_mm2 = len_mm2;
+  std::vector<int8_t> env_of_list(4 * 58), spe(58);
+  for (int a = 0; a < 58; ++a) {
+    env_of_list[a] = static_cast<int8_t>(g.env_of_mmm[a]);
+    env_of_list[58 + a] = static_cast<int8_t>(g.env_of_mm2[a]);
+    env_of_list[2 * 58 + a] = static_cast<int8_t>(g.env_of_mm2_backward[0][a]);
+    env_of_list[3 * 58 + a] = static_cast<int8_t>(g.env_of_mm2_backward[1][a]);
+  }
+  for (int t = 0; t < 60; ++t)
+    if (g.env_of_state[t] >= 0) spe[g.env_of_state[t]] = static_cast<int8_t>(t);
+  tab.env_of_list = to_device(env_of_list);
+  tab.state_pos_of_env = to_device(spe);
+  std::vector<int8_t> coe(species.code_of_enum.begin(), species.code_of_enum.end());
+  std::vector<uint8_t> eoc(species.enum_of_code.begin(), species.enum_of_code.end());
+  d_code_of_enum = to_device(coe);
+  d_enum_of_code = to_device(eoc);
+}
+
+void Engine::load_coefficients(const std::string &json_path) {
+  coefficients = parse_coefficients_json(json_path);
+  pair_tables = build_pair_tables(species, coefficients);
+  site_tables = build_site_tables(species, coefficients);
+  energy_tables = build_energy_tables(species, coefficients);
+  has_coefficients = true;
+  if (device >= 0) {
+    cudaSetDevice(device);
+    tab.pair_C = to_device(pair_tables.C);
+    tab.pair_A = to_device(pair_tables.A);
+    tab.pair_B = to_device(pair_tables.B);
+    tab.site_C = to_device(site_tables.C);
+    tab.site_A = to_device(site_tables.A);
+    tab.site_B = to_device(site_tables.B);
+    tab.e_single = to_device(energy_tables.single);
+    tab.e_pair = to_device(energy_tables.pair);
+    tab.e_triplet = to_device(energy_tables.triplet);
+  }
+}
+
+void Engine::check_event_errors(const char *what) {
+  int err = 0;
+  LMC_CUDA(cudaMemcpyAsync(&err, d_error, sizeof(int), cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  if (!err) return;
+  LMC_CUDA(cudaMemsetAsync(d_error, 0, sizeof(int), stream));
+  std::string msg = std::string(what) + ":";
+  if (err & kErrBadSite) msg += " lattice id or element code out of range;";
+  if (err & kErrNotNeighbour) msg += " Neighbor not found for lattice pair (not first neighbours);";
+  if (err & kErrNotVacancy) msg += " first site of a jump pair must hold the vacancy and the second an atom;";
+  if (err & kErrExtraVacancy) msg += " Cluster not found in ClusterIndexer (two vacancies within interaction range);";
+  throw StatusError((err & kErrBadSite) ? LMC_ERR_INVALID_ARGUMENT : LMC_ERR_OUT_OF_RANGE, msg);
+}
+
+void Engine::set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_t count) {
+  require_device();
+  if (walker < 0 || count < 1 || walker + count > n_walkers) throw std::invalid_argument("walker index out of range");
+  if (n != lat.num_sites * count) throw std::invalid_argument("occupancy length must be num_sites per walker");
+  uint8_t *d_in = static_cast<uint8_t *>(scratch(static_cast<size_t>(n)));
+  LMC_CUDA(cudaMemcpyAsync(d_in, occ, static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((lat.padded_size + threads - 1) / threads);
+  for (int w = 0; w < count; ++w)
+    upload_occupancy_kernel<<<blocks, threads, 0, stream>>>(lat, d_in + static_cast<int64_t>(w) * lat.num_sites,
+                                                           d_occ + static_cast<int64_t>(walker + w) * lat.padded_size, d_code_of_enum, d_error);
+  LMC_CUDA(cudaGetLastError());
+  check_event_errors("set_occupancy (element not in element_set)");
+}
+
+void Engine::get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t count) {
+  require_device();
+  if (walker < 0 || count < 1 || walker + count > n_walkers) throw std::invalid_argument("walker index out of range");
+  if (n != lat.num_sites * count) throw std::invalid_argument("occupancy length must be num_sites per walker");
+  uint8_t *d_out = static_cast<uint8_t *>(scratch(static_cast<size_t>(n)));
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((lat.num_sites + threads - 1) / threads);
+  for (int w = 0; w < count; ++w)
+    download_occupancy_kernel<<<blocks, threads, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker + w) * lat.padded_size,
+                                                             d_out + static_cast<int64_t>(w) * lat.num_sites, d_enum_of_code);
+  LMC_CUDA(cudaGetLastError());
+  LMC_CUDA(cudaMemcpyAsync(occ, d_out, static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::lattice_jump(int32_t walker, int64_t a, int64_t b) {
+  require_device();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  if (a < 0 || b < 0 || a >= lat.num_sites || b >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  lattice_jump_kernel<<<1, 32, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker) * lat.padded_size, a, b);
+  LMC_CUDA(cudaGetLastError());
+  LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::eval_barriers_dev(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea,
+                               double *dE, double *D, double *Ks) {
+  require_device();
+  require_coefficients();
+  if (!pair_tables.has_barrier) throw std::invalid_argument("the coefficient file has no per-element quartic blocks");
+  if (n <= 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + kBarrierThreads - 1) / kBarrierThreads);
+  barrier_kernel<<<blocks, kBarrierThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, site_i, site_j, Ea, dE, D, Ks, d_error);
+  LMC_CUDA(cudaGetLastError());
+}
+
+void Engine::eval_barriers(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea,
+                           double *dE, double *D, double *Ks) {
+  require_device();
+  if (n <= 0) return;
+  // one staging buffer: [i | j | walker] in, [Ea | dE | D | Ks] out
+  const size_t in_bytes = static_cast<size_t>(n) * (8 + 8 + 4), out_bytes = static_cast<size_t>(n) * 8 * 4;
+  char *d = static_cast<char *>(scratch(in_bytes + out_bytes + 64));
+  int64_t *d_i = reinterpret_cast<int64_t *>(d);
+  int64_t *d_j = d_i + n;
+  double *d_out = reinterpret_cast<double *>(d_j + n);
+  int32_t *d_w = reinterpret_cast<int32_t *>(d_out + 4 * n);
+  LMC_CUDA(cudaMemcpyAsync(d_i, site_i, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaMemcpyAsync(d_j, site_j, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  if (walker) LMC_CUDA(cudaMemcpyAsync(d_w, walker, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream));
+  eval_barriers_dev(n, walker ? d_w : nullptr, d_i, d_j, d_out, d_out + n, D ? d_out + 2 * n : nullptr, Ks ? d_out + 3 * n : nullptr);
+  LMC_CUDA(cudaMemcpyAsync(Ea, d_out, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(dE, d_out + n, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  if (D) LMC_CUDA(cudaMemcpyAsync(D, d_out + 2 * n, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  if (Ks) LMC_CUDA(cudaMemcpyAsync(Ks, d_out + 3 * n, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_eval_barriers");
+}
+
+void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE) {
+  require_device();
+  require_coefficients();
+  if (n <= 0) return;
+  const unsigned blocks = static_cast<unsigned>((n + kSwapThreads - 1) / kSwapThreads);
+  swap_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error);
+  LMC_CUDA(cudaGetLastError());
+}
+
+void Engine::eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE) {
+  require_device();
+  if (n <= 0) return;
+  char *d = static_cast<char *>(scratch(static_cast<size_t>(n) * (8 + 8 + 8 + 4) + 64));
+  int64_t *d_a = reinterpret_cast<int64_t *>(d);
+  int64_t *d_b = d_a + n;
+  double *d_out = reinterpret_cast<double *>(d_b + n);
+  int32_t *d_w = reinterpret_cast<int32_t *>(d_out + n);
+  LMC_CUDA(cudaMemcpyAsync(d_a, a, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaMemcpyAsync(d_b, b, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  if (walker) LMC_CUDA(cudaMemcpyAsync(d_w, walker, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream));
+  eval_swap_de_dev(n, walker ? d_w : nullptr, d_a, d_b, d_out);
+  LMC_CUDA(cudaMemcpyAsync(dE, d_out, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_eval_swap_de");
+}
+
+void Engine::eval_site_de(int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element, double *dE) {
+  require_device();
+  require_coefficients();
+  if (n <= 0) return;
+  std::vector<uint8_t> codes(static_cast<size_t>(n));
+  for (int64_t k = 0; k < n; ++k) {
+    const int c = new_element[k] < 16 ? species.code_of_enum[new_element[k]] : -1;
+    if (c < 0) throw std::invalid_argument("new element is not in the element set");
+    codes[static_cast<size_t>(k)] = static_cast<uint8_t>(c);
+  }
+  char *d = static_cast<char *>(scratch(static_cast<size_t>(n) * (8 + 8 + 4 + 1) + 64));
+  int64_t *d_s = reinterpret_cast<int64_t *>(d);
+  double *d_out = reinterpret_cast<double *>(d_s + n);
+  int32_t *d_w = reinterpret_cast<int32_t *>(d_out + n);
+  uint8_t *d_c = reinterpret_cast<uint8_t *>(d_w + n);
+  LMC_CUDA(cudaMemcpyAsync(d_s, site, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaMemcpyAsync(d_c, codes.data(), static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
+  if (walker) LMC_CUDA(cudaMemcpyAsync(d_w, walker, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream));
+  const unsigned blocks = static_cast<unsigned>((n + kSwapThreads - 1) / kSwapThreads);
+  site_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker ? d_w : nullptr, d_s, d_c, d_out, d_error);
+  LMC_CUDA(cudaGetLastError());
+  LMC_CUDA(cudaMemcpyAsync(dE, d_out, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_eval_site_de");
+}
+
+double Engine::total_energy(int32_t walker, int64_t *counts, int32_t n_types) {
+  require_device();
+  require_coefficients();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  if (counts && n_types != tab.n_types) throw std::invalid_argument("counts buffer must hold n_types entries");
+  const unsigned blocks = static_cast<unsigned>((lat.num_sites + kEnergyThreads - 1) / kEnergyThreads);
+  const int m = species.n + 1;
+  char *d = static_cast<char *>(scratch(static_cast<size_t>(blocks) * 8 + static_cast<size_t>(tab.n_types) * 8 + 64));
+  double *d_sums = reinterpret_cast<double *>(d);
+  unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(d_sums + blocks);
+  LMC_CUDA(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(tab.n_types) * 8, stream));
+  const size_t smem = sizeof(double) * (m + 3 * m * m + 4 * m * m * m) + sizeof(int32_t) * 2 * 43 + sizeof(unsigned) * tab.n_types;
+  energy_kernel<<<blocks, kEnergyThreads, smem, stream>>>(lat, tab, d_occ + static_cast<int64_t>(walker) * lat.padded_size, d_sums,
+                                                         counts ? d_counts : nullptr);
+  LMC_CUDA(cudaGetLastError());
+  std::vector<double> sums(blocks);
+  LMC_CUDA(cudaMemcpyAsync(sums.data(), d_sums, static_cast<size_t>(blocks) * 8, cudaMemcpyDeviceToHost, stream));
+  if (counts) LMC_CUDA(cudaMemcpyAsync(counts, d_counts, static_cast<size_t>(tab.n_types) * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  long double total = 0;
+  for (double s : sums) total += s;
+  const double e = static_cast<double>(total);
+  if (e != e) throw StatusError(LMC_ERR_OUT_OF_RANGE, "Cluster not found in ClusterIndexer (two vacancies within interaction range)");
+  return e;
+}
+
+void Engine::debug_pair(int32_t walker, int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b,
+                        int32_t *sc, int32_t *ec, int32_t *enc_mmm, int32_t *enc_f, int32_t *enc_b) {
+  require_device();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  if (i < 0 || j < 0 || i >= lat.num_sites || j >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const size_t n_lists = 60 + 3 * 58, n_counts = 2 * static_cast<size_t>(tab.n_types), n_enc = static_cast<size_t>(tab.len_mmm) + 2 * tab.len_mm2;
+  char *d = static_cast<char *>(scratch(n_lists * 8 + (n_counts + n_enc) * 4 + 64));
+  int64_t *d_lists = reinterpret_cast<int64_t *>(d);
+  int32_t *d_counts = reinterpret_cast<int32_t *>(d_lists + n_lists);
+  int32_t *d_enc = d_counts + n_counts;
+  debug_pair_kernel<<<1, 128, 0, stream>>>(lat, tab, d_occ + static_cast<int64_t>(walker) * lat.padded_size, i, j, d_lists, d_counts, d_enc, d_error);
+  LMC_CUDA(cudaGetLastError());
+  std::vector<int64_t> lists(n_lists);
+  std::vector<int32_t> counts(n_counts), enc(n_enc);
+  LMC_CUDA(cudaMemcpyAsync(lists.data(), d_lists, n_lists * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(counts.data(), d_counts, n_counts * 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(enc.data(), d_enc, n_enc * 4, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_debug_pair");
+  if (state) std::copy(lists.begin(), lists.begin() + 60, state);
+  if (mmm) std::copy(lists.begin() + 60, lists.begin() + 118, mmm);
+  if (mm2) std::copy(lists.begin() + 118, lists.begin() + 176, mm2);
+  if (mm2b) std::copy(lists.begin() + 176, lists.begin() + 234, mm2b);
+  if (sc) std::copy(counts.begin(), counts.begin() + tab.n_types, sc);
+  if (ec) std::copy(counts.begin() + tab.n_types, counts.end(), ec);
+  if (enc_mmm) std::copy(enc.begin(), enc.begin() + tab.len_mmm, enc_mmm);
+  if (enc_f) std::copy(enc.begin() + tab.len_mmm, enc.begin() + tab.len_mmm + tab.len_mm2, enc_f);
+  if (enc_b) std::copy(enc.begin() + tab.len_mmm + tab.len_mm2, enc.end(), enc_b);
+}
+
+void Engine::debug_site(int32_t walker, int64_t site, int32_t new_element, int64_t *state43, int32_t *sc, int32_t *ec) {
+  require_device();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  if (site < 0 || site >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const int code = (new_element >= 0 && new_element < 16) ? species.code_of_enum[new_element] : -1;
+  if (code < 0) throw std::invalid_argument("new element is not in the element set");
+  const size_t n_counts = 2 * static_cast<size_t>(tab.n_types);
+  char *d = static_cast<char *>(scratch(43 * 8 + n_counts * 4 + 64));
+  int64_t *d_list = reinterpret_cast<int64_t *>(d);
+  int32_t *d_counts = reinterpret_cast<int32_t *>(d_list + 43);
+  debug_site_kernel<<<1, 64, 0, stream>>>(lat, tab, d_occ + static_cast<int64_t>(walker) * lat.padded_size, site, code, d_list, d_counts, d_error);
+  LMC_CUDA(cudaGetLastError());
+  std::vector<int64_t> list(43);
+  std::vector<int32_t> counts(n_counts);
+  LMC_CUDA(cudaMemcpyAsync(list.data(), d_list, 43 * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(counts.data(), d_counts, n_counts * 4, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_debug_site");
+  if (state43) std::copy(list.begin(), list.end(), state43);
+  if (sc) std::copy(counts.begin(), counts.begin() + tab.n_types, sc);
+  if (ec) std::copy(counts.begin() + tab.n_types, counts.end(), ec);
+}
+
+// ------------------------------------------------------------------------------------------------ host geometry
+int64_t Engine::wrapped_id(int x, int y, int z) const {
+  auto w = [](int v, int p) { v %= p; return v < 0 ? v + p : v; };
+  return lat.id_of_coords(w(x, 2 * lat.fx), w(y, 2 * lat.fy), w(z, 2 * lat.fz));
+}
+
+void Engine::neighbors(int32_t shell, int64_t site, int64_t *out) const {
+  if (site < 0 || site >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const Geometry &g = geometry();
+  int x, y, z;
+  lat.coords_of_id(site, x, y, z);
+  std::vector<int64_t> ids;
+  auto push = [&](const Int3 &o) { ids.push_back(wrapped_id(x + o.x, y + o.y, z + o.z)); };
+  if (shell == 1) for (const auto &o : g.nn1) push(o);
+  else if (shell == 2) for (const auto &o : g.nn2) push(o);
+  else if (shell == 3) for (const auto &o : g.nn3) push(o);
+  else throw std::invalid_argument("shell must be 1, 2 or 3");
+  std::sort(ids.begin(), ids.end());   // adjacency lists are sorted ascending (cfg/src/Config.cpp:1036-1044)
+  std::copy(ids.begin(), ids.end(), out);
+}
+
+int Engine::host_direction(int64_t i, int64_t j, int *xyz_i) const {
+  if (i < 0 || j < 0 || i >= lat.num_sites || j >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const Geometry &g = geometry();
+  int xi, yi, zi, xj, yj, zj;
+  lat.coords_of_id(i, xi, yi, zi);
+  lat.coords_of_id(j, xj, yj, zj);
+  auto md = [](int d, int p) { d %= p; if (d > p / 2) d -= p; if (d < -p / 2) d += p; return d; };
+  const Int3 d{md(xj - xi, 2 * lat.fx), md(yj - yi, 2 * lat.fy), md(zj - zi, 2 * lat.fz)};
+  if (xyz_i) { xyz_i[0] = xi; xyz_i[1] = yi; xyz_i[2] = zi; }
+  for (int k = 0; k < 12; ++k)
+    if (g.nn1[k] == d) return k;
+  throw std::out_of_range("Neighbor not found for lattice pair in GetPairFlatIndex");   // reference message (:281-283)
+}
+
+int Engine::host_frame_flag(const int *xyz, int k) const {
+  const Int3 p = geometry().frame_p[k];
+  return wrapped_id(xyz[0] + p.x, xyz[1] + p.y, xyz[2] + p.z) < wrapped_id(xyz[0] - p.x, xyz[1] - p.y, xyz[2] - p.z) ? 0 : 1;
+}
+
+void Engine::pair_lists(int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b) const {
+  const Geometry &g = geometry();
+  int ci[3], cj[3];
+  const int k = host_direction(i, j, ci);
+  const int kb = host_direction(j, i, cj);
+  const int sf = host_frame_flag(ci, k), sb = host_frame_flag(cj, kb);
+  int64_t ids[60];
+  for (int t = 0; t < 60; ++t) {
+    const Int3 o = g.pair_offsets[k][sf][t];
+    ids[t] = wrapped_id(ci[0] + o.x, ci[1] + o.y, ci[2] + o.z);
+  }
+  int state_pos_of_env[58];
+  for (int t = 0; t < 60; ++t)
+    if (g.env_of_state[t] >= 0) state_pos_of_env[g.env_of_state[t]] = t;
+  const Int3 pf = g.frame_p[k], pb = g.frame_p[kb];
+  const int fs = sf ? -1 : 1, bs = sb ? -1 : 1;
+  const bool same = fs * pf.x == bs * pb.x && fs * pf.y == bs * pb.y && fs * pf.z == bs * pb.z;
+  for (int t = 0; t < 60 && state; ++t) state[t] = ids[t];
+  for (int a = 0; a < 58; ++a) {
+    if (mmm) mmm[a] = ids[state_pos_of_env[g.env_of_mmm[a]]];
+    if (mm2) mm2[a] = ids[state_pos_of_env[g.env_of_mm2[a]]];
+    if (mm2b) mm2b[a] = ids[state_pos_of_env[g.env_of_mm2_backward[same ? 1 : 0][a]]];
+  }
+}
+
+void Engine::site_list(int64_t site, int64_t *state43) const {
+  if (site < 0 || site >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const Geometry &g = geometry();
+  int x, y, z;
+  lat.coords_of_id(site, x, y, z);
+  for (int t = 0; t < 43; ++t) state43[t] = wrapped_id(x + g.site_offsets[t].x, y + g.site_offsets[t].y, z + g.site_offsets[t].z);
+}
+
+}  // namespace lmc
+
+// ================================================================================================ C ABI
+using lmc::Engine;
+using lmc::guard;
+
+struct lmc_engine {
+  std::unique_ptr<Engine> impl;
+};
+
+extern "C" {
+
+const char *lmc_last_error(void) { return lmc::g_last_error.c_str(); }
+int lmc_abi_version(void) { return 1; }
+int lmc_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int lmc_engine_create(lmc_engine **out, const int32_t factors[3], int32_t id_order, const int32_t *element_set,
+                      int32_t n_elements, int32_t solvent, int32_t n_walkers, int32_t device) {
+  return guard([&] {
+    if (!out || !factors || !element_set) throw std::invalid_argument("null argument");
+    auto e = std::make_unique<lmc_engine>();
+    e->impl = std::make_unique<Engine>(factors, id_order, element_set, n_elements, solvent, n_walkers, device);
+    *out = e.release();
+  });
+}
+void lmc_engine_destroy(lmc_engine *engine) { delete engine; }
+int64_t lmc_engine_num_sites(const lmc_engine *engine) { return engine ? engine->impl->lat.num_sites : 0; }
+int32_t lmc_engine_num_walkers(const lmc_engine *engine) { return engine ? engine->impl->n_walkers : 0; }
+
+int lmc_engine_load_coefficients(lmc_engine *engine, const char *json_path) {
+  return guard([&] {
+    if (!engine || !json_path) throw std::invalid_argument("null argument");
+    engine->impl->load_coefficients(json_path);
+  });
+}
+int lmc_engine_set_occupancy(lmc_engine *engine, int32_t walker, const uint8_t *occupancy, int64_t n) {
+  return guard([&] { engine->impl->set_occupancy(walker, occupancy, n, 1); });
+}
+int lmc_engine_get_occupancy(lmc_engine *engine, int32_t walker, uint8_t *occupancy, int64_t n) {
+  return guard([&] { engine->impl->get_occupancy(walker, occupancy, n, 1); });
+}
+int lmc_engine_set_occupancy_all(lmc_engine *engine, const uint8_t *occupancy, int64_t n_total) {
+  return guard([&] { engine->impl->set_occupancy(0, occupancy, n_total, engine->impl->n_walkers); });
+}
+int lmc_engine_get_occupancy_all(lmc_engine *engine, uint8_t *occupancy, int64_t n_total) {
+  return guard([&] { engine->impl->get_occupancy(0, occupancy, n_total, engine->impl->n_walkers); });
+}
+int lmc_engine_lattice_jump(lmc_engine *engine, int32_t walker, int64_t site_a, int64_t site_b) {
+  return guard([&] { engine->impl->lattice_jump(walker, site_a, site_b); });
+}
+
+int lmc_eval_barriers(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j,
+                      double *Ea, double *dE, double *D, double *Ks) {
+  return guard([&] { engine->impl->eval_barriers(n, walker, site_i, site_j, Ea, dE, D, Ks); });
+}
+int lmc_eval_barriers_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_i,
+                          const int64_t *site_j, double *Ea, double *dE, double *D, double *Ks) {
+  return guard([&] { engine->impl->eval_barriers_dev(n, walker, site_i, site_j, Ea, dE, D, Ks); });
+}
+int lmc_eval_swap_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a, const int64_t *site_b,
+                     double *dE) {
+  return guard([&] { engine->impl->eval_swap_de(n, walker, site_a, site_b, dE); });
+}
+int lmc_eval_swap_de_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a,
+                         const int64_t *site_b, double *dE) {
+  return guard([&] { engine->impl->eval_swap_de_dev(n, walker, site_a, site_b, dE); });
+}
+int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element,
+                     double *dE) {
+  return guard([&] { engine->impl->eval_site_de(n, walker, site, new_element, dE); });
+}
+int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t *counts, int32_t n_types) {
+  return guard([&] {
+    const double e = engine->impl->total_energy(walker, counts, n_types);
+    if (energy) *energy = e;
+  });
+}
+int lmc_debug_pair(lmc_engine *engine, int32_t walker, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
+                   int64_t *mm2_58, int64_t *mm2_backward58, int32_t *start_counts, int32_t *end_counts, int32_t *enc_mmm,
+                   int32_t *enc_mm2_forward, int32_t *enc_mm2_backward) {
+  return guard([&] {
+    engine->impl->debug_pair(walker, site_i, site_j, state60, mmm58, mm2_58, mm2_backward58, start_counts, end_counts, enc_mmm,
+                             enc_mm2_forward, enc_mm2_backward);
+  });
+}
+int lmc_debug_site(lmc_engine *engine, int32_t walker, int64_t site, int32_t new_element, int64_t *state43,
+                   int32_t *start_counts, int32_t *end_counts) {
+  return guard([&] { engine->impl->debug_site(walker, site, new_element, state43, start_counts, end_counts); });
+}
+
+int lmc_engine_neighbors(const lmc_engine *engine, int32_t shell, int64_t site, int64_t *out) {
+  return guard([&] { engine->impl->neighbors(shell, site, out); });
+}
+int lmc_engine_site_coords(const lmc_engine *engine, int64_t site, int32_t xyz[3]) {
+  return guard([&] {
+    if (site < 0 || site >= engine->impl->lat.num_sites) throw std::invalid_argument("lattice id out of range");
+    int x, y, z;
+    engine->impl->lat.coords_of_id(site, x, y, z);
+    xyz[0] = x; xyz[1] = y; xyz[2] = z;
+  });
+}
+int lmc_engine_pair_lists(const lmc_engine *engine, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
+                          int64_t *mm2_58, int64_t *mm2_backward58) {
+  return guard([&] { engine->impl->pair_lists(site_i, site_j, state60, mmm58, mm2_58, mm2_backward58); });
+}
+int lmc_engine_site_list(const lmc_engine *engine, int64_t site, int64_t *state43) {
+  return guard([&] { engine->impl->site_list(site, state43); });
+}
+
+int64_t lmc_tables_mapping(int32_t which, int64_t *out, int64_t capacity) {
+  int64_t needed = -1;
+  const int rc = guard([&] {
+    const lmc::Geometry &g = lmc::geometry();
+    std::vector<int64_t> flat;
+    auto emit_groups = [&](const std::vector<std::vector<std::vector<int64_t>>> &groups) {
+      flat.push_back(static_cast<int64_t>(groups.size()));
+      for (const auto &grp : groups) {
+        flat.push_back(static_cast<int64_t>(grp.size()));
+        flat.push_back(grp.empty() ? 0 : static_cast<int64_t>(grp[0].size()));
+        for (const auto &c : grp) flat.insert(flat.end(), c.begin(), c.end());
+      }
+    };
+    std::vector<std::vector<std::vector<int64_t>>> groups;
+    if (which == 0 || which == 3) {
+      const auto &cl = which == 0 ? g.state_pair : g.state_site;
+      groups.resize(8);
+      for (const auto &c : cl) {
+        std::vector<int64_t> v;
+        for (int q = 0; q < c.arity; ++q) v.push_back(c.pos[q]);
+        groups[c.label].push_back(v);
+      }
+    } else if (which == 1 || which == 2) {
+      const auto &cl = which == 1 ? g.mmm : g.mm2;
+      groups.resize(which == 1 ? g.n_groups_mmm : g.n_groups_mm2);
+      for (const auto &c : cl) {
+        std::vector<int64_t> v;
+        if (c.symmetric) v.push_back(-1);
+        for (int q = 0; q < c.arity; ++q) v.push_back(c.pos[q]);
+        groups[c.group].push_back(v);
+      }
+    } else {
+      throw std::invalid_argument("which must be 0..3");
+    }
+    emit_groups(groups);
+    needed = static_cast<int64_t>(flat.size());
+    if (out) std::copy(flat.begin(), flat.begin() + std::min<int64_t>(needed, capacity), out);
+  });
+  return rc == LMC_OK ? needed : rc;
+}
+
+int32_t lmc_tables_cluster_types(const int32_t *element_set, int32_t n_elements, int32_t *rows5, int32_t capacity_rows) {
+  int32_t count = -1;
+  const int rc = guard([&] {
+    const lmc::Species sp = lmc::make_species(element_set, n_elements, 0);
+    const auto types = lmc::cluster_types(sp);
+    count = static_cast<int32_t>(types.size());
+    for (int32_t r = 0; rows5 && r < count && r < capacity_rows; ++r) {
+      rows5[5 * r] = types[r].label;
+      rows5[5 * r + 1] = types[r].arity;
+      for (int q = 0; q < 3; ++q) rows5[5 * r + 2 + q] = q < types[r].arity ? sp.enum_of_code[types[r].code[q]] : -1;
+    }
+  });
+  return rc == LMC_OK ? count : rc;
+}
+
+int32_t lmc_tables_group_sizes(int32_t which, int32_t n_elements, int32_t *sizes, int32_t capacity) {
+  int32_t len = -1;
+  const int rc = guard([&] {
+    if (which != 1 && which != 2) throw std::invalid_argument("which must be 1 (mmm) or 2 (mm2)");
+    int L = 0;
+    const auto groups = lmc::group_layout(lmc::geometry(), which == 2, n_elements, &L);
+    len = L;
+    if (sizes)
+      for (const auto &gi : groups)
+        for (int q = 0; q < gi.length && gi.offset + q < capacity; ++q) sizes[gi.offset + q] = gi.size;
+  });
+  return rc == LMC_OK ? len : rc;
+}
+
+int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *out, int64_t capacity) {
+  int64_t len = -1;
+  const int rc = guard([&] {
+    engine->impl->require_coefficients();
+    const Engine &e = *engine->impl;
+    const std::vector<double> *v = nullptr;
+    switch (which) {
+      case 0: v = &e.pair_tables.C; break;
+      case 1: v = &e.pair_tables.A; break;
+      case 2: v = &e.pair_tables.B; break;
+      case 3: v = &e.site_tables.C; break;
+      case 4: v = &e.site_tables.A; break;
+      case 5: v = &e.site_tables.B; break;
+      default: throw std::invalid_argument("which must be 0..5");
+    }
+    len = static_cast<int64_t>(v->size());
+    if (out) std::copy(v->begin(), v->begin() + std::min<int64_t>(len, capacity), out);
+  });
+  return rc == LMC_OK ? len : rc;
+}
+
+int32_t lmc_tables_env_pairs(int32_t which, int16_t *pairs, int32_t capacity_pairs) {
+  int32_t count = -1;
+  const int rc = guard([&] {
+    if (which != 0 && which != 1) throw std::invalid_argument("which must be 0 or 1");
+    const auto &v = which == 0 ? lmc::geometry().env_pairs : lmc::geometry().site_env_pairs;
+    count = static_cast<int32_t>(v.size());
+    for (int32_t p = 0; pairs && p < count && p < capacity_pairs; ++p) {
+      pairs[2 * p] = v[p][0];
+      pairs[2 * p + 1] = v[p][1];
+    }
+  });
+  return rc == LMC_OK ? count : rc;
+}
+
+}  // extern "C"

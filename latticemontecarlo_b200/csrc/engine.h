@@ -1,0 +1,84 @@
+// engine.h -- the engine object behind the C ABI (include/lmc_b200.h): one per GPU, owns the device-resident
+// occupancy (packed uint8, padded layout) and the constant tables.
+#pragma once
+#include <cstdint>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "device_tables.h"
+#include "lattice.h"
+#include "tables.h"
+
+namespace lmc {
+
+extern thread_local std::string g_last_error;
+int guard(const std::function<void()> &fn);
+
+class Engine {
+ public:
+  Engine(const int32_t factors[3], int32_t id_order, const int32_t *element_set, int32_t n_elements, int32_t solvent,
+         int32_t n_walkers, int32_t device);
+  ~Engine();
+  Engine(const Engine &) = delete;
+  Engine &operator=(const Engine &) = delete;
+
+  void load_coefficients(const std::string &json_path);
+  void set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_t count);
+  void get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t count);
+  void lattice_jump(int32_t walker, int64_t a, int64_t b);
+
+  void eval_barriers(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea, double *dE,
+                     double *D, double *Ks);
+  void eval_barriers_dev(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea,
+                         double *dE, double *D, double *Ks);
+  void eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE);
+  void eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE);
+  void eval_site_de(int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element, double *dE);
+  double total_energy(int32_t walker, int64_t *counts, int32_t n_types);
+  void debug_pair(int32_t walker, int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b, int32_t *sc,
+                  int32_t *ec, int32_t *enc_mmm, int32_t *enc_f, int32_t *enc_b);
+  void debug_site(int32_t walker, int64_t site, int32_t new_element, int64_t *state43, int32_t *sc, int32_t *ec);
+
+  // host-side geometry (no device needed)
+  void neighbors(int32_t shell, int64_t site, int64_t *out) const;
+  void pair_lists(int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b) const;
+  void site_list(int64_t site, int64_t *state43) const;
+  int64_t wrapped_id(int x, int y, int z) const;
+  int host_direction(int64_t i, int64_t j, int *xyz_i) const;
+  int host_frame_flag(const int *xyz, int k) const;
+
+  void require_device() const;
+  void require_coefficients() const;
+  void check_event_errors(const char *what);
+  void *scratch(size_t bytes);
+  template <class T> const T *to_device(const std::vector<T> &v);
+
+  LatticeDesc lat{};
+  Species species;
+  int32_t n_walkers{1};
+  int32_t device{-1};
+  bool has_coefficients{false};
+  Coefficients coefficients;
+  PairTables pair_tables;
+  SiteTables site_tables;
+  EnergyTables energy_tables;
+
+  cudaStream_t stream{nullptr};
+  uint8_t *d_occ{nullptr};
+  int *d_error{nullptr};
+  DevTables tab{};
+  const int8_t *d_code_of_enum{nullptr};
+  const uint8_t *d_enum_of_code{nullptr};
+  std::vector<void *> device_allocs;
+  void *d_scratch{nullptr};
+  void *h_pinned{nullptr};
+  size_t scratch_bytes{0};
+
+ private:
+  void upload_geometry_tables();
+};
+
+}  // namespace lmc

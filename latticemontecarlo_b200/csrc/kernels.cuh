@@ -1,0 +1,589 @@
+// kernels.cuh -- hand-written sm_100a kernels of the LatticeMC hot path.
+//
+// Design: the reference evaluates one candidate event by ~2800 string/hash-keyed cluster lookups
+// (pred/src/VacancyMigrationPredictorQuartic.cpp:112-246).  Here every quantity of an event is the contracted form
+//     Q = C[m] + sum_t A[m][t][e_t] + sum_{(t,u)} B[m][(t,u)][e_t][e_u]          (tables.h)
+// over the 58 environment sites, stored relative to the solvent species so that only solute sites contribute.
+// The work of an event is therefore (i) one gather of 60 occupancy bytes through constant offset tables -- the
+// HBM/L2-bound part -- and (ii) a short data-dependent walk over the solute bits.  One thread owns one event.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "device_tables.h"
+
+namespace lmc {
+
+// structural constants of the ordered neighbourhoods (verified against tables.cpp at engine creation)
+constexpr int kFirstPos = 21, kSecondPos = 38, kCentrePos = 21;
+constexpr int kEnvN = 58, kSiteEnvN = 42;
+
+enum EventError : int { kErrNotNeighbour = 1, kErrNotVacancy = 2, kErrExtraVacancy = 4, kErrBadSite = 8 };
+
+// Species of the environment as bit planes over the env index (58 or 42 bits used).
+struct EnvBits {
+  uint64_t sol;        // species != solvent
+  uint64_t p0, p1, p2; // bits of the compact species code
+  __device__ __forceinline__ int code(int t) const {
+    return static_cast<int>((p0 >> t) & 1ULL) | (static_cast<int>((p1 >> t) & 1ULL) << 1) | (static_cast<int>((p2 >> t) & 1ULL) << 2);
+  }
+};
+
+__device__ __forceinline__ void envbits_add(EnvBits &e, int t, unsigned code, unsigned solvent) {
+  const uint64_t bit = 1ULL << t;
+  if (code != solvent) e.sol |= bit;
+  if (code & 1u) e.p0 |= bit;
+  if (code & 2u) e.p1 |= bit;
+  if (code & 4u) e.p2 |= bit;
+}
+
+__device__ __forceinline__ int direction_of(const LatticeDesc &lat, const DevTables &tab, int xi, int yi, int zi, int xj, int yj,
+                                            int zj) {
+  int dx = xj - xi, dy = yj - yi, dz = zj - zi;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
+  dy = dy > py / 2 ? dy - py : (dy < -py / 2 ? dy + py : dy);
+  dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
+  if (dx < -1 || dx > 1 || dy < -1 || dy > 1 || dz < -1 || dz > 1) return -1;
+  return tab.dir_lut[(dx + 1) * 9 + (dy + 1) * 3 + (dz + 1)];
+}
+
+// Closed form of pred/src/VacancyMigrationPredictorQuartic.cpp:266-275
+__device__ __forceinline__ double quartic_barrier(double dE, double D, double Ks) {
+  const double b = 4.0 * dE / (D * D * D);
+  const double a = Ks / (4.0 * D * D);
+  const double c = (9.0 * b * b - 16.0 * a * a * D * D) / (32.0 * a);
+  const double delta = sqrt(fabs(9.0 * b * b - 32.0 * a * c));
+  const double s = 3.0 * b + delta;
+  return s * s * (3.0 * b * b - 16.0 * a * c + b * delta) / (a * a * a) / 2048.0;
+}
+
+// Walk the solute bits of a jump environment and accumulate the three contracted quantities.
+__device__ __forceinline__ void accumulate_pair_tables(const DevTables &tab, int m, const EnvBits &env, double acc[3]) {
+  const int n = tab.n_species;
+  const double *__restrict__ C = tab.pair_C + m * 3;
+  acc[0] = C[0]; acc[1] = C[1]; acc[2] = C[2];
+  const double *__restrict__ A = tab.pair_A + static_cast<size_t>(m) * kEnvN * n * 3;
+  const double *__restrict__ B = tab.pair_B + static_cast<size_t>(m) * tab.n_pair_pairs * n * n * 3;
+  uint64_t sol = env.sol;
+  while (sol) {
+    const int t = __ffsll(static_cast<long long>(sol)) - 1;
+    sol &= sol - 1;
+    const int et = env.code(t);
+    const double *a = A + (t * n + et) * 3;
+    acc[0] += __ldg(a); acc[1] += __ldg(a + 1); acc[2] += __ldg(a + 2);
+    const uint64_t hi = __ldg(tab.pair_mask_hi + t);
+    uint64_t partners = hi & sol;
+    const int base = __ldg(tab.pair_base + t);
+    while (partners) {
+      const int u = __ffsll(static_cast<long long>(partners)) - 1;
+      partners &= partners - 1;
+      const int eu = env.code(u);
+      const int p = base + __popcll(hi & ((1ULL << u) - 1ULL));
+      const double *b = B + ((static_cast<size_t>(p) * n + et) * n + eu) * 3;
+      acc[0] += __ldg(b); acc[1] += __ldg(b + 1); acc[2] += __ldg(b + 2);
+    }
+  }
+}
+
+// Gather the 60 ordered sites of jump (first site at padded index `base`, direction k, z parity zpar) into bit planes.
+// `delta` is the [24][61] offset table (shared or global).  Returns the species at the second site in *mig and
+// the species at the first site in *first.
+__device__ __forceinline__ void gather_pair_env(const uint8_t *__restrict__ occ, int64_t base, const int32_t *__restrict__ drow,
+                                                unsigned solvent, EnvBits &env, unsigned *first, unsigned *mig) {
+  env.sol = env.p0 = env.p1 = env.p2 = 0;
+  unsigned codes[60];
+#pragma unroll
+  for (int t = 0; t < 60; ++t) codes[t] = occ[base + drow[t]];
+#pragma unroll
+  for (int t = 0; t < 60; ++t) {
+    if (t == kFirstPos) { *first = codes[t]; continue; }
+    if (t == kSecondPos) { *mig = codes[t]; continue; }
+    const int e = t - (t > kFirstPos) - (t > kSecondPos);
+    envbits_add(env, e, codes[t], solvent);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- occupancy I/O
+// element enum codes by lattice id  ->  compact codes in the padded layout (halo cells replicate their periodic image)
+__global__ void upload_occupancy_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ_by_id, uint8_t *__restrict__ padded,
+                                        const int8_t *__restrict__ code_of_enum, int *__restrict__ error) {
+  const int64_t cell = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (cell >= lat.padded_size) return;
+  const int zi = static_cast<int>(cell % lat.nz);
+  const int64_t r = cell / lat.nz;
+  const int yp = static_cast<int>(r % lat.ny);
+  const int xp = static_cast<int>(r / lat.ny);
+  const int X = wrap_coord(xp - kHalo, 2 * lat.fx), Y = wrap_coord(yp - kHalo, 2 * lat.fy);
+  // z index zi holds Z + 4 in {2 zi, 2 zi + 1}; the parity that makes X+Y+Z even is the real site
+  const int Zp = 2 * zi + (((xp - kHalo) + (yp - kHalo)) & 1);
+  const int Z = wrap_coord(wrap_coord(Zp - kHaloZ, 2 * lat.fz), 2 * lat.fz);
+  const int enum_code = occ_by_id[lat.id_of_coords(X, Y, Z)];
+  const int code = enum_code < 16 ? code_of_enum[enum_code] : -1;
+  if (code < 0) { atomicOr(error, kErrBadSite); padded[cell] = 0; return; }
+  padded[cell] = static_cast<uint8_t>(code);
+}
+
+__global__ void download_occupancy_kernel(LatticeDesc lat, const uint8_t *__restrict__ padded, uint8_t *__restrict__ occ_by_id,
+                                          const uint8_t *__restrict__ enum_of_code) {
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (id >= lat.num_sites) return;
+  occ_by_id[id] = enum_of_code[padded[lat.padded_index_of_id(id)]];
+}
+
+// write one site and all its periodic halo images
+__device__ __forceinline__ void store_site(const LatticeDesc &lat, uint8_t *occ, int X, int Y, int Z, uint8_t code) {
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+#pragma unroll
+  for (int a = -1; a <= 1; ++a) {
+    const int x = X + a * px;
+    if (x < -kHalo || x >= px + kHalo) continue;
+#pragma unroll
+    for (int b = -1; b <= 1; ++b) {
+      const int y = Y + b * py;
+      if (y < -kHalo || y >= py + kHalo) continue;
+#pragma unroll
+      for (int c = -1; c <= 1; ++c) {
+        const int z = Z + c * pz;
+        if (z < -kHaloZ || z >= pz + kHaloZ) continue;
+        occ[lat.padded_index(x, y, z)] = code;
+      }
+    }
+  }
+}
+
+__global__ void lattice_jump_kernel(LatticeDesc lat, uint8_t *occ, int64_t a, int64_t b) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int xa, ya, za, xb, yb, zb;
+  lat.coords_of_id(a, xa, ya, za);
+  lat.coords_of_id(b, xb, yb, zb);
+  const uint8_t ca = occ[lat.padded_index(xa, ya, za)], cb = occ[lat.padded_index(xb, yb, zb)];
+  store_site(lat, occ, xa, ya, za, cb);
+  store_site(lat, occ, xb, yb, zb, ca);
+}
+
+// ----------------------------------------------------------------------------------------------- barriers
+// One thread per candidate event.  Algorithmic traffic per event: 60 B occupancy + 240 B of
+// neighbour indices (here replaced by a 61-word offset row that lives in shared memory) + 16 B of output.
+constexpr int kBarrierThreads = 128;
+
+__global__ void __launch_bounds__(kBarrierThreads)
+barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
+               const int32_t *__restrict__ walker, const int64_t *__restrict__ site_i, const int64_t *__restrict__ site_j,
+               double *__restrict__ Ea, double *__restrict__ dE, double *__restrict__ D_out, double *__restrict__ Ks_out,
+               int *__restrict__ error) {
+  __shared__ int32_t s_delta[24 * kPairDeltaStride];
+  for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
+  __syncthreads();
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  const int64_t i = site_i[e], j = site_j[e];
+  const int w = walker ? walker[e] : 0;
+  const double nan = CUDART_NAN;
+  int err = 0;
+  double out_ea = nan, out_de = nan, out_d = nan, out_ks = nan;
+  if (i < 0 || i >= lat.num_sites || j < 0 || j >= lat.num_sites) {
+    err = kErrBadSite;
+  } else {
+    int xi, yi, zi, xj, yj, zj;
+    lat.coords_of_id(i, xi, yi, zi);
+    lat.coords_of_id(j, xj, yj, zj);
+    const int k = direction_of(lat, tab, xi, yi, zi, xj, yj, zj);
+    if (k < 0) {
+      err = kErrNotNeighbour;
+    } else {
+      const uint8_t *o = occ + w * walker_stride;
+      const int64_t base = lat.padded_index(xi, yi, zi);
+      const int32_t *drow = s_delta + (k * 2 + (zi & 1)) * kPairDeltaStride;
+      EnvBits env;
+      unsigned first = 0, mig = 0;
+      gather_pair_env(o, base, drow, static_cast<unsigned>(tab.solvent), env, &first, &mig);
+      const unsigned vac = static_cast<unsigned>(tab.n_species);
+      // a vacancy in the environment has all code bits of `vac` set; detect any
+      uint64_t is_vac = ~0ULL;
+      is_vac &= (vac & 1u) ? env.p0 : ~env.p0;
+      is_vac &= (vac & 2u) ? env.p1 : ~env.p1;
+      is_vac &= (vac & 4u) ? env.p2 : ~env.p2;
+      is_vac &= (1ULL << kEnvN) - 1ULL;
+      if (first != vac || mig == vac) err = kErrNotVacancy;
+      else if (is_vac) err = kErrExtraVacancy;
+      else {
+        double acc[3];
+        accumulate_pair_tables(tab, static_cast<int>(mig), env, acc);
+        out_de = acc[0];
+        out_d = exp(acc[1]);
+        out_ks = exp(acc[2]);
+        out_ea = quartic_barrier(out_de, out_d, out_ks);
+      }
+    }
+  }
+  if (err) atomicOr(error, err);
+  Ea[e] = out_ea;
+  dE[e] = out_de;
+  if (D_out) D_out[e] = out_d;
+  if (Ks_out) Ks_out[e] = out_ks;
+}
+
+// ----------------------------------------------------------------------------------------------- site / swap dE
+__device__ __forceinline__ void gather_site_env(const uint8_t *__restrict__ occ, int64_t base, const int32_t *__restrict__ drow,
+                                                unsigned solvent, EnvBits &env, unsigned *centre, int64_t override_index,
+                                                unsigned override_code) {
+  env.sol = env.p0 = env.p1 = env.p2 = 0;
+#pragma unroll
+  for (int t = 0; t < 43; ++t) {
+    const int64_t idx = base + drow[t];
+    unsigned c = occ[idx];
+    if (idx == override_index) c = override_code;
+    if (t == kCentrePos) { *centre = c; continue; }
+    envbits_add(env, t - (t > kCentrePos), c, solvent);
+  }
+}
+
+// H(x_new, env) - H(x_old, env) with the contracted site tables
+__device__ __forceinline__ double site_energy_change(const DevTables &tab, int x_old, int x_new, const EnvBits &env) {
+  const int m = tab.n_species + 1;
+  const size_t a_stride = static_cast<size_t>(kSiteEnvN) * m, b_stride = static_cast<size_t>(tab.n_site_pairs) * m * m;
+  const double *__restrict__ A_new = tab.site_A + x_new * a_stride, *__restrict__ A_old = tab.site_A + x_old * a_stride;
+  const double *__restrict__ B_new = tab.site_B + x_new * b_stride, *__restrict__ B_old = tab.site_B + x_old * b_stride;
+  double acc = __ldg(tab.site_C + x_new) - __ldg(tab.site_C + x_old);
+  uint64_t sol = env.sol;
+  while (sol) {
+    const int t = __ffsll(static_cast<long long>(sol)) - 1;
+    sol &= sol - 1;
+    const int et = env.code(t);
+    acc += __ldg(A_new + t * m + et) - __ldg(A_old + t * m + et);
+    const uint64_t hi = __ldg(tab.site_mask_hi + t);
+    uint64_t partners = hi & sol;
+    const int base = __ldg(tab.site_base + t);
+    while (partners) {
+      const int u = __ffsll(static_cast<long long>(partners)) - 1;
+      partners &= partners - 1;
+      const int eu = env.code(u);
+      const size_t p = (static_cast<size_t>(base + __popcll(hi & ((1ULL << u) - 1ULL))) * m + et) * m + eu;
+      acc += __ldg(B_new + p) - __ldg(B_old + p);
+    }
+  }
+  return acc;
+}
+
+// EnergyChangePredictorPairSite::GetDeFromLatticeIdPair (pred/src/EnergyChangePredictorPairSite.cpp:70-146).
+// Uncoupled pairs: dE_site(a -> e_b) + dE_site(b -> e_a) on the unchanged occupancy.  Coupled pairs (b within the
+// third shell of a): the two single-site changes are applied one after the other (the second sees the first), which
+// is the same sum over "clusters touching a or b" that the reference recounts on the fly (:96-134).
+__device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, const DevTables &tab, const uint8_t *__restrict__ occ,
+                                                     const int32_t *__restrict__ s_delta, int xa, int ya, int za, int xb, int yb,
+                                                     int zb, int *err) {
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
+  int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
+  unsigned ea = occ[base_a], eb = occ[base_b];
+  if (ea == eb) return 0.0;
+  int dx = xb - xa, dy = yb - ya, dz = zb - za;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
+  dy = dy > py / 2 ? dy - py : (dy < -py / 2 ? dy + py : dy);
+  dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
+  const int r2 = dx * dx + dy * dy + dz * dz;
+  const bool coupled = r2 <= 6;
+  int zpa = za & 1, zpb = zb & 1;
+  if (coupled && eb == vac) {   // move the vacancy first so that no intermediate state holds two vacancies
+    const int64_t tb = base_a; base_a = base_b; base_b = tb;
+    const unsigned te = ea; ea = eb; eb = te;
+    const int tz = zpa; zpa = zpb; zpb = tz;
+    dx = -dx; dy = -dy; dz = -dz;
+  }
+  EnvBits env;
+  unsigned centre;
+  gather_site_env(occ, base_a, s_delta + zpa * 43, solvent, env, &centre, -1, 0);
+  uint64_t is_vac = ~0ULL;
+  is_vac &= (vac & 1u) ? env.p0 : ~env.p0;
+  is_vac &= (vac & 2u) ? env.p1 : ~env.p1;
+  is_vac &= (vac & 4u) ? env.p2 : ~env.p2;
+  is_vac &= (1ULL << kSiteEnvN) - 1ULL;
+  (void)is_vac;
+  double de = site_energy_change(tab, static_cast<int>(ea), static_cast<int>(eb), env);
+  // second site; in the coupled case it sees site a already holding e_b.  The halo images of a are not updated in
+  // memory, so the override is applied by *position*: a sits at displacement (-dx,-dy,-dz) from b.
+  int64_t override_index = -1;
+  if (coupled) override_index = base_b + lat.padded_delta(-dx, -dy, -dz, zpb);
+  gather_site_env(occ, base_b, s_delta + zpb * 43, solvent, env, &centre, override_index, eb);
+  de += site_energy_change(tab, static_cast<int>(eb), static_cast<int>(ea), env);
+  if (de != de) *err |= kErrExtraVacancy;   // NaN: a cluster type the reference has no index for
+  return de;
+}
+
+constexpr int kSwapThreads = 128;
+
+__global__ void __launch_bounds__(kSwapThreads)
+swap_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
+               const int32_t *__restrict__ walker, const int64_t *__restrict__ site_a, const int64_t *__restrict__ site_b,
+               double *__restrict__ dE, int *__restrict__ error) {
+  __shared__ int32_t s_delta[2 * 43];
+  for (int q = threadIdx.x; q < 2 * 43; q += blockDim.x) s_delta[q] = tab.site_delta[q];
+  __syncthreads();
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  const int64_t a = site_a[e], b = site_b[e];
+  if (a < 0 || a >= lat.num_sites || b < 0 || b >= lat.num_sites) {
+    atomicOr(error, kErrBadSite);
+    dE[e] = CUDART_NAN;
+    return;
+  }
+  int xa, ya, za, xb, yb, zb;
+  lat.coords_of_id(a, xa, ya, za);
+  lat.coords_of_id(b, xb, yb, zb);
+  int err = 0;
+  const double de = swap_energy_change(lat, tab, occ + (walker ? walker[e] : 0) * walker_stride, s_delta, xa, ya, za, xb, yb, zb, &err);
+  if (err) atomicOr(error, err);
+  dE[e] = de;
+}
+
+__global__ void __launch_bounds__(kSwapThreads)
+site_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
+               const int32_t *__restrict__ walker, const int64_t *__restrict__ site, const uint8_t *__restrict__ new_code,
+               double *__restrict__ dE, int *__restrict__ error) {
+  __shared__ int32_t s_delta[2 * 43];
+  for (int q = threadIdx.x; q < 2 * 43; q += blockDim.x) s_delta[q] = tab.site_delta[q];
+  __syncthreads();
+  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (e >= n) return;
+  const int64_t s = site[e];
+  if (s < 0 || s >= lat.num_sites || new_code[e] > tab.n_species) {
+    atomicOr(error, kErrBadSite);
+    dE[e] = CUDART_NAN;
+    return;
+  }
+  int x, y, z;
+  lat.coords_of_id(s, x, y, z);
+  const uint8_t *o = occ + (walker ? walker[e] : 0) * walker_stride;
+  EnvBits env;
+  unsigned centre = 0;
+  gather_site_env(o, lat.padded_index(x, y, z), s_delta + (z & 1) * 43, static_cast<unsigned>(tab.solvent), env, &centre, -1, 0);
+  double de = 0.0;
+  if (centre != new_code[e]) {
+    de = site_energy_change(tab, static_cast<int>(centre), static_cast<int>(new_code[e]), env);
+    if (de != de) atomicOr(error, kErrExtraVacancy);
+  }
+  dE[e] = de;
+}
+
+// ----------------------------------------------------------------------------------------------- total energy
+// EnergyPredictor::GetEncode / GetEnergy (pred/src/EnergyPredictor.cpp:40-96,173-177): ordered-tuple counting,
+// one thread per site; per-block partial sums are reduced in a fixed order (deterministic).
+constexpr int kEnergyThreads = 128;
+
+__global__ void __launch_bounds__(kEnergyThreads)
+energy_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, double *__restrict__ block_sums,
+              unsigned long long *__restrict__ counts) {
+  extern __shared__ unsigned char smem_raw[];
+  const int m = tab.n_species + 1;
+  double *s_single = reinterpret_cast<double *>(smem_raw);
+  double *s_pair = s_single + m;
+  double *s_trip = s_pair + 3 * m * m;
+  int32_t *s_delta = reinterpret_cast<int32_t *>(s_trip + 4 * m * m * m);
+  unsigned int *s_counts = reinterpret_cast<unsigned int *>(s_delta + 2 * 43);
+  __shared__ double s_red[kEnergyThreads / 32];
+  for (int q = threadIdx.x; q < m; q += blockDim.x) s_single[q] = tab.e_single[q];
+  for (int q = threadIdx.x; q < 3 * m * m; q += blockDim.x) s_pair[q] = tab.e_pair[q];
+  for (int q = threadIdx.x; q < 4 * m * m * m; q += blockDim.x) s_trip[q] = tab.e_triplet[q];
+  for (int q = threadIdx.x; q < 2 * 43; q += blockDim.x) s_delta[q] = tab.site_delta[q];
+  if (counts)
+    for (int q = threadIdx.x; q < tab.n_types; q += blockDim.x) s_counts[q] = 0;
+  __syncthreads();
+  double acc = 0.0;
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (id < lat.num_sites) {
+    int x, y, z;
+    lat.coords_of_id(id, x, y, z);
+    const int64_t base = lat.padded_index(x, y, z);
+    const int32_t *drow = s_delta + (z & 1) * 43;
+    unsigned char code[43];
+#pragma unroll
+    for (int t = 0; t < 43; ++t) code[t] = occ[base + drow[t]];
+    const int c1 = code[kCentrePos];
+    acc += s_single[c1];
+    if (counts) atomicAdd(&s_counts[tab.type_lut[c1 * m * m]], 1u);
+    for (int q = 0; q < 42; ++q) {
+      const int pos = tab.e_shell_pos[2 * q], shell = tab.e_shell_pos[2 * q + 1];
+      const int c2 = code[pos];
+      acc += s_pair[((shell - 1) * m + c1) * m + c2];
+      if (counts) atomicAdd(&s_counts[tab.type_lut[((shell * m + c1) * m + c2) * m]], 1u);
+    }
+    for (int q = 0; q < tab.n_e_walk; ++q) {
+      const int p2 = tab.e_walk[4 * q], p3 = tab.e_walk[4 * q + 1], label = tab.e_walk[4 * q + 2];
+      const int c2 = code[p2], c3 = code[p3];
+      acc += s_trip[(((label - 4) * m + c1) * m + c2) * m + c3];
+      if (counts) atomicAdd(&s_counts[tab.type_lut[((label * m + c1) * m + c2) * m + c3]], 1u);
+    }
+  }
+  // block reduction in a fixed order
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < kEnergyThreads / 32; ++q) s += s_red[q];
+    block_sums[blockIdx.x] = s;
+  }
+  if (counts) {
+    for (int q = threadIdx.x; q < tab.n_types; q += blockDim.x)
+      if (s_counts[q]) atomicAdd(&counts[q], static_cast<unsigned long long>(s_counts[q]));
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- debug taps
+// One block per call; recomputes the reference's integer artefacts for one jump pair straight from its
+// definitions (ordered lists with the min-id frame rule, cluster-type histograms, one-hot numerators).
+__device__ __forceinline__ int64_t wrapped_id(const LatticeDesc &lat, int x, int y, int z) {
+  return lat.id_of_coords(wrap_coord(wrap_coord(x, 2 * lat.fx), 2 * lat.fx), wrap_coord(wrap_coord(y, 2 * lat.fy), 2 * lat.fy),
+                          wrap_coord(wrap_coord(z, 2 * lat.fz), 2 * lat.fz));
+}
+
+// frame flag of jump (x,y,z) -> direction k: 0 if +frame_p[k] is the perpendicular first neighbour with the smaller
+// lattice id (the one Config::GetLatticePairRotationMatrix meets first, cfg/src/Config.cpp:253-260), else 1
+__device__ __forceinline__ int frame_flag(const LatticeDesc &lat, const DevTables &tab, int x, int y, int z, int k) {
+  const int8_t *p = tab.frame_p + 4 * k;
+  const int64_t plus = wrapped_id(lat, x + p[0], y + p[1], z + p[2]);
+  const int64_t minus = wrapped_id(lat, x - p[0], y - p[1], z - p[2]);
+  return plus < minus ? 0 : 1;
+}
+
+__global__ void debug_pair_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t site_i, int64_t site_j,
+                                  int64_t *__restrict__ lists /*60+58+58+58*/, int32_t *__restrict__ counts /*2*n_types*/,
+                                  int32_t *__restrict__ enc /*len_mmm + 2*len_mm2*/, int *__restrict__ error) {
+  __shared__ int64_t s_ids[60];
+  __shared__ uint8_t s_code[60];
+  __shared__ int s_k, s_flag_f, s_flag_b;
+  int xi, yi, zi, xj, yj, zj;
+  lat.coords_of_id(site_i, xi, yi, zi);
+  lat.coords_of_id(site_j, xj, yj, zj);
+  if (threadIdx.x == 0) {
+    const int k = direction_of(lat, tab, xi, yi, zi, xj, yj, zj);
+    s_k = k;
+    if (k >= 0) {
+      s_flag_f = frame_flag(lat, tab, xi, yi, zi, k);
+      // reversed pair: direction -d has the same perpendicular pair; its flag is evaluated at site j.  frame_p of the
+      // reversed direction may be stored with either sign, so compare actual vectors: backward variant 1 <=> the
+      // backward y axis equals the forward y axis.
+      int kb = -1;
+      for (int q = 0; q < 12; ++q)
+        if (tab.nn1[4 * q] == -tab.nn1[4 * k] && tab.nn1[4 * q + 1] == -tab.nn1[4 * k + 1] && tab.nn1[4 * q + 2] == -tab.nn1[4 * k + 2]) kb = q;
+      const int fb = frame_flag(lat, tab, xj, yj, zj, kb);
+      const int sf = s_flag_f ? -1 : 1, sb = fb ? -1 : 1;
+      const bool same = (sf * tab.frame_p[4 * k] == sb * tab.frame_p[4 * kb]) && (sf * tab.frame_p[4 * k + 1] == sb * tab.frame_p[4 * kb + 1]) &&
+                        (sf * tab.frame_p[4 * k + 2] == sb * tab.frame_p[4 * kb + 2]);
+      s_flag_b = same ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (s_k < 0) {
+    if (threadIdx.x == 0) atomicOr(error, kErrNotNeighbour);
+    return;
+  }
+  const int k = s_k;
+  for (int t = threadIdx.x; t < 60; t += blockDim.x) {
+    const int8_t *o = tab.pair_off + ((k * 2 + s_flag_f) * 60 + t) * 4;
+    s_ids[t] = wrapped_id(lat, xi + o[0], yi + o[1], zi + o[2]);
+    // occupancy is read through the frame-independent offset table used by the production kernels
+    s_code[t] = 0;
+  }
+  __syncthreads();
+  // species by lattice id (independent of the fast kernels' offset rows)
+  for (int t = threadIdx.x; t < 60; t += blockDim.x) s_code[t] = occ[lat.padded_index_of_id(s_ids[t])];
+  __syncthreads();
+  const int n = tab.n_species, m = n + 1;
+  if (lists) {
+    for (int t = threadIdx.x; t < 60; t += blockDim.x) lists[t] = s_ids[t];
+    for (int a = threadIdx.x; a < 58; a += blockDim.x) {
+      lists[60 + a] = s_ids[tab.state_pos_of_env[tab.env_of_list[a]]];
+      lists[118 + a] = s_ids[tab.state_pos_of_env[tab.env_of_list[58 + a]]];
+      lists[176 + a] = s_ids[tab.state_pos_of_env[tab.env_of_list[(2 + s_flag_b) * 58 + a]]];
+    }
+  }
+  if (counts) {
+    for (int q = threadIdx.x; q < 2 * tab.n_types; q += blockDim.x) counts[q] = 0;
+    __syncthreads();
+    const int mig = s_code[kSecondPos];
+    for (int c = threadIdx.x; c < tab.n_state_pair; c += blockDim.x) {
+      const int8_t *cl = tab.map_state_pair + 4 * c;
+      int start[3] = {0, 0, 0}, end[3] = {0, 0, 0};
+      for (int q = 0; q < 3; ++q) {
+        const int pos = cl[1 + q];
+        if (pos < 0) break;
+        start[q] = s_code[pos];
+        end[q] = pos == kFirstPos ? mig : (pos == kSecondPos ? n : s_code[pos]);
+      }
+      const int ts = tab.type_lut[((cl[0] * m + start[0]) * m + start[1]) * m + start[2]];
+      const int te = tab.type_lut[((cl[0] * m + end[0]) * m + end[1]) * m + end[2]];
+      if (ts < 0 || te < 0) { atomicOr(error, kErrExtraVacancy); continue; }
+      atomicAdd(&counts[ts], 1);
+      atomicAdd(&counts[tab.n_types + te], 1);
+    }
+  }
+  if (enc) {
+    const int total = tab.len_mmm + 2 * tab.len_mm2;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) enc[q] = 0;
+    __syncthreads();
+    for (int which = 0; which < 3; ++which) {
+      const int16_t *map = which == 0 ? tab.map_mmm : tab.map_mm2;
+      const int8_t *env_of = tab.env_of_list + (which == 0 ? 0 : (which == 1 ? 58 : (2 + s_flag_b) * 58));
+      int32_t *out = enc + (which == 0 ? 0 : (which == 1 ? tab.len_mmm : tab.len_mmm + tab.len_mm2));
+      for (int c = threadIdx.x; c < tab.n_avg_clusters; c += blockDim.x) {
+        const int16_t *cl = map + 4 * c;
+        const int ea = s_code[tab.state_pos_of_env[env_of[cl[1]]]];
+        if (ea >= n) { atomicOr(error, kErrExtraVacancy); continue; }
+        int slot;
+        if (cl[2] < 0) {
+          slot = ea;
+        } else {
+          const int eb = s_code[tab.state_pos_of_env[env_of[cl[2]]]];
+          if (eb >= n) { atomicOr(error, kErrExtraVacancy); continue; }
+          if (cl[3] & 1) {
+            const int lo = ea < eb ? ea : eb, hi = ea < eb ? eb : ea;
+            slot = lo * n - lo * (lo - 1) / 2 + (hi - lo);
+          } else {
+            slot = ea * n + eb;
+          }
+        }
+        atomicAdd(&out[cl[0] + slot], 1);
+      }
+    }
+  }
+}
+
+__global__ void debug_site_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t site, int new_code,
+                                  int64_t *__restrict__ list43, int32_t *__restrict__ counts, int *__restrict__ error) {
+  __shared__ int64_t s_ids[43];
+  __shared__ uint8_t s_code[43];
+  int x, y, z;
+  lat.coords_of_id(site, x, y, z);
+  for (int t = threadIdx.x; t < 43; t += blockDim.x) {
+    const int8_t *o = tab.site_off + 4 * t;
+    s_ids[t] = wrapped_id(lat, x + o[0], y + o[1], z + o[2]);
+    s_code[t] = occ[lat.padded_index_of_id(s_ids[t])];
+    if (list43) list43[t] = s_ids[t];
+  }
+  __syncthreads();
+  if (!counts) return;
+  const int m = tab.n_species + 1;
+  for (int q = threadIdx.x; q < 2 * tab.n_types; q += blockDim.x) counts[q] = 0;
+  __syncthreads();
+  for (int c = threadIdx.x; c < tab.n_state_site; c += blockDim.x) {
+    const int8_t *cl = tab.map_state_site + 4 * c;
+    int start[3] = {0, 0, 0}, end[3] = {0, 0, 0};
+    for (int q = 0; q < 3; ++q) {
+      const int pos = cl[1 + q];
+      if (pos < 0) break;
+      start[q] = s_code[pos];
+      end[q] = pos == kCentrePos ? new_code : s_code[pos];
+    }
+    const int ts = tab.type_lut[((cl[0] * m + start[0]) * m + start[1]) * m + start[2]];
+    const int te = tab.type_lut[((cl[0] * m + end[0]) * m + end[1]) * m + end[2]];
+    if (ts < 0 || te < 0) { atomicOr(error, kErrExtraVacancy); continue; }
+    atomicAdd(&counts[ts], 1);
+    atomicAdd(&counts[tab.n_types + te], 1);
+  }
+}
+
+}  // namespace lmc
