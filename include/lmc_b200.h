@@ -107,6 +107,51 @@ int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const
  * counts (optional, n_types int64) receives the exact integer cluster counts of GetEncode before normalisation. */
 int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t *counts, int32_t n_types);
 
+/* ------------------------------------------------------------------------------------------------ measurement
+ * the engine's cudaStream_t (all engine work is enqueued on it; e.g. to record CUDA events around calls) */
+void *lmc_engine_cuda_stream(lmc_engine *engine);
+int lmc_engine_synchronize(lmc_engine *engine);
+/* device time (CUDA events on the engine stream) of the most recent hot-path kernel launch:
+ * barrier_kernel / swap_de_kernel / kmc_run_kernel / cmc_run_kernel.  Blocks until that kernel has finished. */
+double lmc_engine_last_kernel_ms(lmc_engine *engine);
+/* number of kernels this engine has launched so far */
+int64_t lmc_engine_launch_count(const lmc_engine *engine);
+
+/* ------------------------------------------------------------------------------------------------ KMC driver
+ * mc::KineticMcFirstOmp::Simulate (mc/src/KineticMcAbstract.cpp:140-188, mc/src/KineticMcFirstOmp.cpp:52-82) run for
+ * every replica ("walker") of the engine at once: per step the 12 jumps of the walker's vacancy are evaluated,
+ * ordered by ascending neighbour lattice id, rate_i = exp(-Ea_i/kT), dt = -ln(u1)/sum(rate)/1e13 * correction,
+ * the event is the first slot whose cumulative probability is >= u2, then time/energy/occupancy are updated.
+ * Walkers are independent (own occupancy, own temperature, own random stream).
+ */
+typedef struct lmc_kmc_params {
+  double temperature;              /* `temperature` of the parameter file; used for walkers when temperatures == NULL */
+  const double *temperatures;      /* optional per-walker temperatures [n_walkers] */
+  int32_t n_time_temperature;      /* `time_temperature_filename` table (pred/src/TimeTemperatureInterpolator.cpp): */
+  const double *tt_time;           /*   points sorted by time; 0 points = constant temperature */
+  const double *tt_temperature;
+  int32_t rate_corrector;          /* `rate_corrector` (pred/include/RateCorrector.hpp) */
+  uint64_t seed;                   /* Philox4x32-10 key; walker w uses key (seed ^ w), counter = its step number */
+} lmc_kmc_params;
+
+typedef struct lmc_kmc_trace {     /* optional per-step records, each [n_walkers][n_steps] (host), any may be NULL */
+  int64_t *from, *to;              /* vacancy lattice id before / after the step */
+  int32_t *slot;                   /* selected event index in the reference's event order */
+  double *dt, *Ea, *dE, *total_rate, *temperature;
+} lmc_kmc_trace;
+
+/* (re)initialise the per-walker KMC state from the current occupancy: locate the vacancy (Config::GetVacancyLatticeId),
+ * vacancy / solute concentrations for the rate corrector (KineticMcAbstract.cpp:35), time = energy = steps = 0.
+ * Fails with LMC_ERR_OUT_OF_RANGE unless every walker holds exactly one vacancy. */
+int lmc_kmc_reset(lmc_engine *engine);
+/* advance every walker by n_steps.  replay_u1 / replay_u2 (both or neither; host, [n_walkers][n_steps]) replace the
+ * Philox stream by caller-supplied uniforms: u1 -> residence time, u2 -> event selection, in the reference's draw order. */
+int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u1,
+                const double *replay_u2, const lmc_kmc_trace *trace);
+/* per-walker state after the last run (host arrays [n_walkers], any may be NULL): McAbstract::time_, energy_, steps_ */
+int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy,
+                      double *temperature);
+
 /* ------------------------------------------------------------------------------------------------ debug taps
  * Integer artefacts of the reference's algorithm, recomputed on the device, for bit-exact parity checks.
  * lists: the symmetry-ordered lattice-id lists of pair (site_i, site_j)

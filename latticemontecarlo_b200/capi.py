@@ -54,6 +54,10 @@ def lib():
         _lib.lmc_engine_num_sites.restype = C.c_int64
         _lib.lmc_tables_mapping.restype = C.c_int64
         _lib.lmc_engine_destroy.restype = None
+        _lib.lmc_engine_cuda_stream.restype = C.c_void_p
+        _lib.lmc_engine_last_kernel_ms.restype = C.c_double
+        _lib.lmc_engine_launch_count.restype = C.c_int64
+        _lib.lmc_engine_get_tables.restype = C.c_int64
     return _lib
 
 
@@ -114,6 +118,15 @@ def tables_env_pairs(which):
     out = np.empty((n, 2), dtype=np.int16)
     _check(lib().lmc_tables_env_pairs(w, _p(out), n))
     return out
+
+
+class KmcParams(C.Structure):
+    _fields_ = [("temperature", C.c_double), ("temperatures", C.c_void_p), ("n_time_temperature", C.c_int32),
+                ("tt_time", C.c_void_p), ("tt_temperature", C.c_void_p), ("rate_corrector", C.c_int32), ("seed", C.c_uint64)]
+
+
+class KmcTrace(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("from_", "to", "slot", "dt", "Ea", "dE", "total_rate", "temperature")]
 
 
 class Engine:
@@ -215,6 +228,72 @@ class Engine:
         counts = np.zeros(self.n_types, dtype=np.int64) if want_counts else None
         _check(lib().lmc_total_energy(self.h, int(walker), C.byref(e), _p(counts), self.n_types if want_counts else 0))
         return (e.value, counts) if want_counts else e.value
+
+    # ---- measurement
+    def cuda_stream(self):
+        return int(lib().lmc_engine_cuda_stream(self.h) or 0)
+
+    def synchronize(self):
+        _check(lib().lmc_engine_synchronize(self.h))
+
+    def last_kernel_ms(self):
+        return float(lib().lmc_engine_last_kernel_ms(self.h))
+
+    def launch_count(self):
+        return int(lib().lmc_engine_launch_count(self.h))
+
+    # ---- device-resident batches (inputs already in HBM): pointers are raw device addresses (e.g. tensor.data_ptr())
+    def eval_barriers_dev(self, n, walker_ptr, i_ptr, j_ptr, ea_ptr, de_ptr):
+        _check(lib().lmc_eval_barriers_dev(self.h, C.c_int64(int(n)), C.c_void_p(walker_ptr or None), C.c_void_p(i_ptr), C.c_void_p(j_ptr),
+                                           C.c_void_p(ea_ptr), C.c_void_p(de_ptr), None, None))
+
+    def eval_swap_de_dev(self, n, walker_ptr, a_ptr, b_ptr, de_ptr):
+        _check(lib().lmc_eval_swap_de_dev(self.h, C.c_int64(int(n)), C.c_void_p(walker_ptr or None), C.c_void_p(a_ptr), C.c_void_p(b_ptr),
+                                          C.c_void_p(de_ptr)))
+
+    # ---- KMC driver (mc::KineticMcFirstOmp semantics over all walkers)
+    def kmc_reset(self):
+        _check(lib().lmc_kmc_reset(self.h))
+
+    def kmc_run(self, n_steps, temperature=500.0, temperatures=None, time_temperature=None, rate_corrector=False, seed=0,
+                replay_u1=None, replay_u2=None, trace=False):
+        """Advance every walker by n_steps. Returns the trace dict (arrays [n_walkers, n_steps]) if trace else None."""
+        keep = []
+        prm = KmcParams()
+        prm.temperature = float(temperature)
+        if temperatures is not None:
+            t = np.ascontiguousarray(temperatures, dtype=np.float64); keep.append(t)
+            assert t.size == self.n_walkers
+            prm.temperatures = t.ctypes.data
+        if time_temperature is not None:
+            tt = np.ascontiguousarray(time_temperature, dtype=np.float64)
+            tt = tt[np.argsort(tt[:, 0], kind="stable")]
+            tt_t = np.ascontiguousarray(tt[:, 0]); tt_v = np.ascontiguousarray(tt[:, 1]); keep += [tt_t, tt_v]
+            prm.n_time_temperature = len(tt_t); prm.tt_time = tt_t.ctypes.data; prm.tt_temperature = tt_v.ctypes.data
+        prm.rate_corrector = int(bool(rate_corrector))
+        prm.seed = int(seed)
+        u1 = u2 = None
+        if replay_u1 is not None:
+            u1 = np.ascontiguousarray(replay_u1, dtype=np.float64).reshape(self.n_walkers, n_steps)
+            u2 = np.ascontiguousarray(replay_u2, dtype=np.float64).reshape(self.n_walkers, n_steps)
+        tr, out = None, None
+        if trace:
+            shape = (self.n_walkers, int(n_steps))
+            out = {"from": np.zeros(shape, np.int64), "to": np.zeros(shape, np.int64), "slot": np.zeros(shape, np.int32)}
+            for k in ("dt", "Ea", "dE", "total_rate", "temperature"):
+                out[k] = np.zeros(shape, np.float64)
+            tr = KmcTrace(out["from"].ctypes.data, out["to"].ctypes.data, out["slot"].ctypes.data, out["dt"].ctypes.data,
+                          out["Ea"].ctypes.data, out["dE"].ctypes.data, out["total_rate"].ctypes.data, out["temperature"].ctypes.data)
+        _check(lib().lmc_kmc_run(self.h, C.byref(prm), C.c_int64(int(n_steps)), _p(u1), _p(u2), C.byref(tr) if tr else None))
+        return out
+
+    def kmc_state(self):
+        n = self.n_walkers
+        out = dict(time=np.empty(n), energy=np.empty(n), steps=np.empty(n, np.int64), vacancy=np.empty(n, np.int64),
+                   temperature=np.empty(n))
+        _check(lib().lmc_kmc_get_state(self.h, _p(out["time"]), _p(out["energy"]), _p(out["steps"]), _p(out["vacancy"]),
+                                       _p(out["temperature"])))
+        return out
 
     # ---- debug taps (device)
     def debug_pair(self, i, j, walker=0):

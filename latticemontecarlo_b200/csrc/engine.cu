@@ -12,6 +12,7 @@
 #include "../../include/lmc_b200.h"
 #include "engine.h"
 #include "kernels.cuh"
+#include "kmc_kernels.cuh"
 #include "tables.h"
 
 namespace lmc {
@@ -70,6 +71,8 @@ Engine::Engine(const int32_t factors[3], int32_t id_order, const int32_t *elemen
     LMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     LMC_CUDA(cudaMalloc(&d_occ, static_cast<size_t>(n_walkers) * lat.padded_size));
     LMC_CUDA(cudaMalloc(&d_error, sizeof(int)));
+    LMC_CUDA(cudaEventCreate(&ev_begin));
+    LMC_CUDA(cudaEventCreate(&ev_end));
     LMC_CUDA(cudaMemsetAsync(d_error, 0, sizeof(int), stream));
     upload_geometry_tables();
   }
@@ -83,8 +86,27 @@ Engine::~Engine() {
     cudaFree(d_error);
     cudaFree(d_scratch);
     if (h_pinned) cudaFreeHost(h_pinned);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
     if (stream) cudaStreamDestroy(stream);
   }
+}
+
+void Engine::time_begin() { cudaEventRecord(ev_begin, stream); }
+void Engine::time_end() {
+  cudaEventRecord(ev_end, stream);
+  ++launch_count;
+  timing_pending = true;
+}
+double Engine::last_kernel_ms() {
+  if (!timing_pending) return last_ms;
+  require_device();
+  LMC_CUDA(cudaEventSynchronize(ev_end));
+  float ms = 0.f;
+  LMC_CUDA(cudaEventElapsedTime(&ms, ev_begin, ev_end));
+  last_ms = ms;
+  timing_pending = false;
+  return last_ms;
 }
 
 void Engine::require_device() const {
@@ -279,9 +301,13 @@ void Engine::set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_
   LMC_CUDA(cudaMemcpyAsync(d_in, occ, static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((lat.padded_size + threads - 1) / threads);
-  for (int w = 0; w < count; ++w)
-    upload_occupancy_kernel<<<blocks, threads, 0, stream>>>(lat, d_in + static_cast<int64_t>(w) * lat.num_sites,
-                                                           d_occ + static_cast<int64_t>(walker + w) * lat.padded_size, d_code_of_enum, d_error);
+  for (int w0 = 0; w0 < count; w0 += 32768) {   // gridDim.y limit is 65535
+    const unsigned ny = static_cast<unsigned>(std::min(32768, count - w0));
+    upload_occupancy_kernel<<<dim3(blocks, ny), threads, 0, stream>>>(lat, d_in + static_cast<int64_t>(w0) * lat.num_sites,
+                                                                     d_occ + static_cast<int64_t>(walker + w0) * lat.padded_size,
+                                                                     d_code_of_enum, d_error);
+    ++launch_count;
+  }
   LMC_CUDA(cudaGetLastError());
   check_event_errors("set_occupancy (element not in element_set)");
 }
@@ -293,9 +319,12 @@ void Engine::get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t coun
   uint8_t *d_out = static_cast<uint8_t *>(scratch(static_cast<size_t>(n)));
   const int threads = 256;
   const unsigned blocks = static_cast<unsigned>((lat.num_sites + threads - 1) / threads);
-  for (int w = 0; w < count; ++w)
-    download_occupancy_kernel<<<blocks, threads, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker + w) * lat.padded_size,
-                                                             d_out + static_cast<int64_t>(w) * lat.num_sites, d_enum_of_code);
+  for (int w0 = 0; w0 < count; w0 += 32768) {
+    const unsigned ny = static_cast<unsigned>(std::min(32768, count - w0));
+    download_occupancy_kernel<<<dim3(blocks, ny), threads, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker + w0) * lat.padded_size,
+                                                                       d_out + static_cast<int64_t>(w0) * lat.num_sites, d_enum_of_code);
+    ++launch_count;
+  }
   LMC_CUDA(cudaGetLastError());
   LMC_CUDA(cudaMemcpyAsync(occ, d_out, static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
@@ -317,7 +346,9 @@ void Engine::eval_barriers_dev(int64_t n, const int32_t *walker, const int64_t *
   if (!pair_tables.has_barrier) throw std::invalid_argument("the coefficient file has no per-element quartic blocks");
   if (n <= 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kBarrierThreads - 1) / kBarrierThreads);
+  time_begin();
   barrier_kernel<<<blocks, kBarrierThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, site_i, site_j, Ea, dE, D, Ks, d_error);
+  time_end();
   LMC_CUDA(cudaGetLastError());
 }
 
@@ -348,7 +379,9 @@ void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a
   require_coefficients();
   if (n <= 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kSwapThreads - 1) / kSwapThreads);
+  time_begin();
   swap_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error);
+  time_end();
   LMC_CUDA(cudaGetLastError());
 }
 
@@ -468,6 +501,123 @@ void Engine::debug_site(int32_t walker, int64_t site, int32_t new_element, int64
   if (state43) std::copy(list.begin(), list.end(), state43);
   if (sc) std::copy(counts.begin(), counts.begin() + tab.n_types, sc);
   if (ec) std::copy(counts.begin() + tab.n_types, counts.end(), ec);
+}
+
+// ------------------------------------------------------------------------------------------------ KMC driver
+namespace {
+template <class T>
+T *dev_alloc(size_t n) {
+  void *p = nullptr;
+  if (cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)) != cudaSuccess)
+    throw StatusError(LMC_ERR_CUDA, "cudaMalloc failed");
+  return static_cast<T *>(p);
+}
+}  // namespace
+
+void Engine::kmc_reset() {
+  require_device();
+  if (!d_kmc_vacancy) {
+    const size_t n = static_cast<size_t>(n_walkers);
+    d_kmc_vacancy = dev_alloc<int64_t>(n); d_kmc_steps = dev_alloc<int64_t>(n);
+    d_kmc_time = dev_alloc<double>(n); d_kmc_energy = dev_alloc<double>(n); d_kmc_temperature = dev_alloc<double>(n);
+    d_kmc_cvac = dev_alloc<double>(n); d_kmc_csol = dev_alloc<double>(n); d_kmc_error = dev_alloc<int32_t>(n);
+    for (void *p : {static_cast<void *>(d_kmc_vacancy), static_cast<void *>(d_kmc_steps), static_cast<void *>(d_kmc_time),
+                    static_cast<void *>(d_kmc_energy), static_cast<void *>(d_kmc_temperature), static_cast<void *>(d_kmc_cvac),
+                    static_cast<void *>(d_kmc_csol), static_cast<void *>(d_kmc_error)})
+      device_allocs.push_back(p);
+  }
+  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error};
+  const int al = species.code_of_enum[1];   // RateCorrector counts "not Al, not X" as solute (KineticMcAbstract.cpp:35)
+  kmc_init_kernel<<<static_cast<unsigned>(n_walkers), 256, 0, stream>>>(lat, d_occ, lat.padded_size, st, species.n, al, 1);
+  LMC_CUDA(cudaGetLastError());
+  std::vector<int32_t> err(static_cast<size_t>(n_walkers));
+  LMC_CUDA(cudaMemcpyAsync(err.data(), d_kmc_error, err.size() * 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  for (int w = 0; w < n_walkers; ++w)
+    if (err[static_cast<size_t>(w)]) throw std::out_of_range("vacancy not found (walker " + std::to_string(w) + " must hold exactly one vacancy)");
+  kmc_ready = true;
+}
+
+void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace) {
+  require_device();
+  require_coefficients();
+  if (!pair_tables.has_barrier) throw std::invalid_argument("the coefficient file has no per-element quartic blocks");
+  if (!kmc_ready) kmc_reset();
+  if ((u1 == nullptr) != (u2 == nullptr)) throw std::invalid_argument("replay needs both u1 and u2");
+  if (n_steps <= 0) return;
+  const size_t nw = static_cast<size_t>(n_walkers), total = nw * static_cast<size_t>(n_steps);
+  // temperatures
+  std::vector<double> temps(nw, params.temperature);
+  if (params.temperatures) std::copy(params.temperatures, params.temperatures + nw, temps.begin());
+  for (double t : temps)
+    if (!(t > 0.0) && params.n_time_temperature == 0) throw std::invalid_argument("temperature must be positive");
+  LMC_CUDA(cudaMemcpyAsync(d_kmc_temperature, temps.data(), nw * 8, cudaMemcpyHostToDevice, stream));
+  // staging: [tt_time | tt_temp | u1 | u2 | trace...]
+  const size_t n_tt = static_cast<size_t>(std::max(0, params.n_time_temperature));
+  const bool tracing = trace != nullptr;
+  size_t bytes = 2 * n_tt * 8 + 64;
+  if (u1) bytes += 2 * total * 8;
+  if (tracing) bytes += total * (8 + 8 + 4 + 5 * 8) + 64;
+  char *d = static_cast<char *>(scratch(bytes));
+  double *d_tt_time = reinterpret_cast<double *>(d), *d_tt_temp = d_tt_time + n_tt;
+  double *cursor = d_tt_temp + n_tt;
+  if (n_tt) {
+    LMC_CUDA(cudaMemcpyAsync(d_tt_time, params.tt_time, n_tt * 8, cudaMemcpyHostToDevice, stream));
+    LMC_CUDA(cudaMemcpyAsync(d_tt_temp, params.tt_temperature, n_tt * 8, cudaMemcpyHostToDevice, stream));
+  }
+  double *d_u1 = nullptr, *d_u2 = nullptr;
+  if (u1) {
+    d_u1 = cursor; d_u2 = d_u1 + total; cursor = d_u2 + total;
+    LMC_CUDA(cudaMemcpyAsync(d_u1, u1, total * 8, cudaMemcpyHostToDevice, stream));
+    LMC_CUDA(cudaMemcpyAsync(d_u2, u2, total * 8, cudaMemcpyHostToDevice, stream));
+  }
+  KmcTraceDev tr{};
+  if (tracing) {
+    tr.from = trace->from ? reinterpret_cast<int64_t *>(cursor) : nullptr; cursor += total;
+    tr.to = trace->to ? reinterpret_cast<int64_t *>(cursor) : nullptr; cursor += total;
+    tr.dt = trace->dt ? cursor : nullptr; cursor += total;
+    tr.Ea = trace->Ea ? cursor : nullptr; cursor += total;
+    tr.dE = trace->dE ? cursor : nullptr; cursor += total;
+    tr.total_rate = trace->total_rate ? cursor : nullptr; cursor += total;
+    tr.temperature = trace->temperature ? cursor : nullptr; cursor += total;
+    tr.slot = trace->slot ? reinterpret_cast<int32_t *>(cursor) : nullptr;
+  }
+  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error};
+  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed};
+  const int walkers_per_block = kKmcThreads / 16;
+  const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
+  time_begin();
+  kmc_run_kernel<<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+  time_end();
+  LMC_CUDA(cudaGetLastError());
+  if (tracing) {
+    auto back = [&](void *host, const void *dev, size_t elem) {
+      if (host && dev) LMC_CUDA(cudaMemcpyAsync(host, dev, total * elem, cudaMemcpyDeviceToHost, stream));
+    };
+    back(trace->from, tr.from, 8); back(trace->to, tr.to, 8); back(trace->slot, tr.slot, 4); back(trace->dt, tr.dt, 8);
+    back(trace->Ea, tr.Ea, 8); back(trace->dE, tr.dE, 8); back(trace->total_rate, tr.total_rate, 8);
+    back(trace->temperature, tr.temperature, 8);
+  }
+  std::vector<int32_t> err(nw);
+  LMC_CUDA(cudaMemcpyAsync(err.data(), d_kmc_error, nw * 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  for (size_t w = 0; w < nw; ++w)
+    if (err[w]) {
+      kmc_ready = false;
+      throw std::out_of_range("KMC walker " + std::to_string(w) + ": Cluster not found in ClusterIndexer (vacancy lost or second vacancy in range)");
+    }
+}
+
+void Engine::kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {
+  require_device();
+  if (!d_kmc_vacancy) throw std::invalid_argument("lmc_kmc_reset has not been called");
+  const size_t nw = static_cast<size_t>(n_walkers);
+  if (time) LMC_CUDA(cudaMemcpyAsync(time, d_kmc_time, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (energy) LMC_CUDA(cudaMemcpyAsync(energy, d_kmc_energy, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (steps) LMC_CUDA(cudaMemcpyAsync(steps, d_kmc_steps, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (vacancy) LMC_CUDA(cudaMemcpyAsync(vacancy, d_kmc_vacancy, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (temperature) LMC_CUDA(cudaMemcpyAsync(temperature, d_kmc_temperature, nw * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
 }
 
 // ------------------------------------------------------------------------------------------------ host geometry
@@ -623,6 +773,32 @@ int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t
     const double e = engine->impl->total_energy(walker, counts, n_types);
     if (energy) *energy = e;
   });
+}
+void *lmc_engine_cuda_stream(lmc_engine *engine) { return engine ? static_cast<void *>(engine->impl->stream) : nullptr; }
+int lmc_engine_synchronize(lmc_engine *engine) {
+  return guard([&] {
+    engine->impl->require_device();
+    if (cudaStreamSynchronize(engine->impl->stream) != cudaSuccess) throw std::runtime_error("cudaStreamSynchronize failed");
+  });
+}
+double lmc_engine_last_kernel_ms(lmc_engine *engine) {
+  double ms = -1.0;
+  guard([&] { ms = engine->impl->last_kernel_ms(); });
+  return ms;
+}
+int64_t lmc_engine_launch_count(const lmc_engine *engine) { return engine ? engine->impl->launch_count : 0; }
+int lmc_kmc_reset(lmc_engine *engine) {
+  return guard([&] { engine->impl->kmc_reset(); });
+}
+int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u1,
+                const double *replay_u2, const lmc_kmc_trace *trace) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    engine->impl->kmc_run(*params, n_steps, replay_u1, replay_u2, trace);
+  });
+}
+int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {
+  return guard([&] { engine->impl->kmc_get_state(time, energy, steps, vacancy, temperature); });
 }
 int lmc_debug_pair(lmc_engine *engine, int32_t walker, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
                    int64_t *mm2_58, int64_t *mm2_backward58, int32_t *start_counts, int32_t *end_counts, int32_t *enc_mmm,

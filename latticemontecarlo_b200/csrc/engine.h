@@ -12,6 +12,9 @@
 #include "lattice.h"
 #include "tables.h"
 
+struct lmc_kmc_params;
+struct lmc_kmc_trace;
+
 namespace lmc {
 
 extern thread_local std::string g_last_error;
@@ -42,6 +45,11 @@ class Engine {
                   int32_t *ec, int32_t *enc_mmm, int32_t *enc_f, int32_t *enc_b);
   void debug_site(int32_t walker, int64_t site, int32_t new_element, int64_t *state43, int32_t *sc, int32_t *ec);
 
+  // drivers
+  void kmc_reset();
+  void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace);
+  void kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature);
+
   // host-side geometry (no device needed)
   void neighbors(int32_t shell, int64_t site, int64_t *out) const;
   void pair_lists(int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b) const;
@@ -50,6 +58,9 @@ class Engine {
   int host_direction(int64_t i, int64_t j, int *xyz_i) const;
   int host_frame_flag(const int *xyz, int k) const;
 
+  void time_begin();
+  void time_end();
+  double last_kernel_ms();
   void require_device() const;
   void require_coefficients() const;
   void check_event_errors(const char *what);
@@ -76,6 +87,16 @@ class Engine {
   void *d_scratch{nullptr};
   void *h_pinned{nullptr};
   size_t scratch_bytes{0};
+  // KMC per-walker state (device)
+  int64_t *d_kmc_vacancy{nullptr}, *d_kmc_steps{nullptr};
+  double *d_kmc_time{nullptr}, *d_kmc_energy{nullptr}, *d_kmc_temperature{nullptr}, *d_kmc_cvac{nullptr}, *d_kmc_csol{nullptr};
+  int32_t *d_kmc_error{nullptr};
+  bool kmc_ready{false};
+  // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
+  cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
+  bool timing_pending{false};
+  double last_ms{0.0};
+  int64_t launch_count{0};
 
  private:
   void upload_geometry_tables();

@@ -90,7 +90,7 @@ __device__ __forceinline__ void accumulate_pair_tables(const DevTables &tab, int
 // Gather the 60 ordered sites of jump (first site at padded index `base`, direction k, z parity zpar) into bit planes.
 // `delta` is the [24][61] offset table (shared or global).  Returns the species at the second site in *mig and
 // the species at the first site in *first.
-__device__ __forceinline__ void gather_pair_env(const uint8_t *__restrict__ occ, int64_t base, const int32_t *__restrict__ drow,
+__device__ __forceinline__ void gather_pair_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
                                                 unsigned solvent, EnvBits &env, unsigned *first, unsigned *mig) {
   env.sol = env.p0 = env.p1 = env.p2 = 0;
   unsigned codes[60];
@@ -107,10 +107,13 @@ __device__ __forceinline__ void gather_pair_env(const uint8_t *__restrict__ occ,
 
 // ----------------------------------------------------------------------------------------------- occupancy I/O
 // element enum codes by lattice id  ->  compact codes in the padded layout (halo cells replicate their periodic image)
+// blockIdx.y = walker (both arrays are walker-major)
 __global__ void upload_occupancy_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ_by_id, uint8_t *__restrict__ padded,
                                         const int8_t *__restrict__ code_of_enum, int *__restrict__ error) {
   const int64_t cell = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (cell >= lat.padded_size) return;
+  occ_by_id += blockIdx.y * lat.num_sites;
+  padded += blockIdx.y * lat.padded_size;
   const int zi = static_cast<int>(cell % lat.nz);
   const int64_t r = cell / lat.nz;
   const int yp = static_cast<int>(r % lat.ny);
@@ -129,6 +132,8 @@ __global__ void download_occupancy_kernel(LatticeDesc lat, const uint8_t *__rest
                                           const uint8_t *__restrict__ enum_of_code) {
   const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (id >= lat.num_sites) return;
+  occ_by_id += blockIdx.y * lat.num_sites;
+  padded += blockIdx.y * lat.padded_size;
   occ_by_id[id] = enum_of_code[padded[lat.padded_index_of_id(id)]];
 }
 
@@ -226,7 +231,7 @@ barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
 }
 
 // ----------------------------------------------------------------------------------------------- site / swap dE
-__device__ __forceinline__ void gather_site_env(const uint8_t *__restrict__ occ, int64_t base, const int32_t *__restrict__ drow,
+__device__ __forceinline__ void gather_site_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
                                                 unsigned solvent, EnvBits &env, unsigned *centre, int64_t override_index,
                                                 unsigned override_code) {
   env.sol = env.p0 = env.p1 = env.p2 = 0;

@@ -1,0 +1,239 @@
+// kmc_kernels.cuh -- batched first-order kinetic Monte Carlo driver (mc::KineticMcFirstOmp semantics) over many
+// independent walkers.  Reference: mc/src/KineticMcAbstract.cpp:140-188 (OneStepSimulation / Simulate),
+// mc/src/KineticMcFirstOmp.cpp:52-82 (BuildEventList / CalculateTime), mc/src/JumpEvent.cpp:6-13.
+//
+// One half-warp owns one walker for the whole launch: lanes 0..11 evaluate the 12 candidate jumps of the walker's
+// vacancy (barrier kernel body), the 12 events are put in the reference's order (ascending neighbour lattice id),
+// Arrhenius rates, the cumulative-probability select and the residence-time update are done with half-warp
+// shuffles in exactly the reference's (sequential) floating point order, and the jump is written back to the
+// walker's occupancy.  Random numbers come from Philox4x32-10 (key = seed ^ walker, counter = step) or, in replay
+// mode, from host-supplied (u1, u2) streams so that the reference's event sequence can be reproduced.
+#pragma once
+#include "kernels.cuh"
+
+namespace lmc {
+
+constexpr double kBoltzmannEv = 8.617333262145e-5;   // cfg/include/Constants.hpp:31
+constexpr double kPrefactorHz = 1e13;                // Constants.hpp:32
+
+struct KmcState {            // per-walker arrays in device memory
+  int64_t *vacancy;          // lattice id of the vacancy
+  double *time, *energy;     // time_ / energy_ of McAbstract
+  int64_t *steps;            // steps_
+  double *temperature;       // temperature_ (constant per walker unless a T(t) table is given)
+  double *c_vacancy, *c_solute;   // RateCorrector inputs (pred/include/RateCorrector.hpp)
+  int32_t *error;            // sticky per-walker EventError bits
+};
+
+struct KmcParams {
+  int32_t n_tt;              // number of (time, temperature) points; 0 = constant temperature
+  const double *tt_time, *tt_temp;
+  int32_t rate_corrector;
+  uint64_t seed;
+};
+
+struct KmcTraceDev {         // optional per-step records, [walker][n_steps]; any pointer may be null
+  int64_t *from, *to;
+  int32_t *slot;
+  double *dt, *Ea, *dE, *total_rate, *temperature;
+};
+
+// ---- Philox4x32-10 (Salmon et al. 2011), counter = (c0,c1,0,0), key = (k0,k1)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  uint32_t c[4] = {c0, c1, 0u, 0u};
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+}
+// 53-bit uniforms like libstdc++'s generate_canonical<double,53> on a 64-bit engine: floor(x / 2^11) * 2^-53
+__device__ __forceinline__ double uniform53(uint32_t lo, uint32_t hi) {
+  const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
+  return static_cast<double>(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// pred::TimeTemperatureInterpolator::GetTemperature (pred/src/TimeTemperatureInterpolator.cpp:43-65)
+__device__ __forceinline__ double interpolate_temperature(const KmcParams &p, double time) {
+  int k = 0;                                   // lower_bound: first point with time_k >= time
+  while (k < p.n_tt && p.tt_time[k] < time) ++k;
+  if (k == p.n_tt) return p.tt_temp[p.n_tt - 1];
+  if (k == 0 && time <= p.tt_time[0]) return p.tt_temp[0];
+  const double x1 = p.tt_time[k], y1 = p.tt_temp[k], x0 = p.tt_time[k - 1], y0 = p.tt_temp[k - 1];
+  return y0 + ((time - x0) / (x1 - x0)) * (y1 - y0);
+}
+
+// pred::RateCorrector::GetTimeCorrectionFactor (pred/include/RateCorrector.hpp:17-24)
+__device__ __forceinline__ double rate_correction(double c_vac, double c_sol, double temperature) {
+  const double correct = 1.64 * exp(-(0.66 / kBoltzmannEv / temperature - 0.7));
+  return c_vac / correct / (1.0 - 13.0 * c_sol);
+}
+
+// One block per walker: locate the vacancy, count species (Config::GetVacancyLatticeId, GetVacancyConcentration,
+// GetSoluteConcentration(Al): cfg/src/Config.cpp:296-310,373-393), reset time / energy / steps.
+__global__ void kmc_init_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ, int64_t walker_stride, KmcState st,
+                                int vac_code, int al_code, int reset_clock) {
+  const int w = blockIdx.x;
+  const uint8_t *o = occ + w * walker_stride;
+  __shared__ unsigned long long s_vac_id;
+  __shared__ unsigned int s_nvac, s_nsol;
+  if (threadIdx.x == 0) { s_vac_id = ~0ULL; s_nvac = 0; s_nsol = 0; }
+  __syncthreads();
+  unsigned nvac = 0, nsol = 0;
+  unsigned long long first = ~0ULL;
+  for (int64_t id = threadIdx.x; id < lat.num_sites; id += blockDim.x) {
+    const int c = o[lat.padded_index_of_id(id)];
+    if (c == vac_code) { ++nvac; if (static_cast<unsigned long long>(id) < first) first = id; }
+    else if (c != al_code) ++nsol;
+  }
+  atomicAdd(&s_nvac, nvac);
+  atomicAdd(&s_nsol, nsol);
+  atomicMin(&s_vac_id, first);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    st.vacancy[w] = s_nvac ? static_cast<int64_t>(s_vac_id) : -1;
+    st.c_vacancy[w] = static_cast<double>(s_nvac) / static_cast<double>(lat.num_sites);
+    st.c_solute[w] = static_cast<double>(s_nsol) / static_cast<double>(lat.num_sites);
+    st.error[w] = s_nvac == 1 ? 0 : kErrNotVacancy;
+    if (reset_clock) { st.time[w] = 0.0; st.energy[w] = 0.0; st.steps[w] = 0; }
+  }
+}
+
+constexpr int kKmcThreads = 128;   // 8 walkers per block
+
+__global__ void __launch_bounds__(kKmcThreads)
+kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
+               int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
+  __shared__ int32_t s_delta[24 * kPairDeltaStride];
+  for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
+  __syncthreads();
+  const int lane = threadIdx.x & 15;
+  const int w = static_cast<int>((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4);
+  if (w >= n_walkers) return;
+  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+  uint8_t *o = occ + w * walker_stride;
+  if (st.error[w] != 0 || st.vacancy[w] < 0) return;
+
+  int X, Y, Z;
+  lat.coords_of_id(st.vacancy[w], X, Y, Z);
+  double time = st.time[w], energy = st.energy[w], temperature = st.temperature[w];
+  int64_t steps = st.steps[w];
+  const double c_vac = st.c_vacancy[w], c_sol = st.c_solute[w];
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac_code = static_cast<unsigned>(tab.n_species);
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  const bool active = lane < 12;
+  const int k = active ? lane : 0;
+  const int dxk = tab.nn1[4 * k], dyk = tab.nn1[4 * k + 1], dzk = tab.nn1[4 * k + 2];
+  int err = 0;
+
+  for (int64_t s = 0; s < n_steps; ++s) {
+    // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50)
+    if (prm.n_tt > 0) temperature = interpolate_temperature(prm, time);
+    const double beta = 1.0 / kBoltzmannEv / temperature;
+    // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
+    const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
+    const int64_t id_j = active ? lat.id_of_coords(xj, yj, zj) : INT64_MAX;
+    int slot = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) slot += (__shfl_sync(hmask, id_j, q, 16) < id_j) ? 1 : 0;
+    double ea = 0.0, de = 0.0, rate = 0.0;
+    unsigned mig = 0;
+    if (active) {
+      const int64_t base = lat.padded_index(X, Y, Z);
+      const int32_t *drow = s_delta + (k * 2 + (Z & 1)) * kPairDeltaStride;
+      EnvBits env;
+      unsigned first = 0;
+      gather_pair_env(o, base, drow, solvent, env, &first, &mig);
+      uint64_t is_vac = ~0ULL;
+      is_vac &= (vac_code & 1u) ? env.p0 : ~env.p0;
+      is_vac &= (vac_code & 2u) ? env.p1 : ~env.p1;
+      is_vac &= (vac_code & 4u) ? env.p2 : ~env.p2;
+      is_vac &= (1ULL << kEnvN) - 1ULL;
+      if (first != vac_code || mig == vac_code) err |= kErrNotVacancy;
+      else if (is_vac) err |= kErrExtraVacancy;
+      else {
+        double acc[3];
+        accumulate_pair_tables(tab, static_cast<int>(mig), env, acc);
+        de = acc[0];
+        ea = quartic_barrier(de, exp(acc[1]), exp(acc[2]));
+        rate = exp(-ea * beta);                      // JumpEvent.cpp:13
+      }
+    }
+    if (__any_sync(hmask, err != 0)) break;
+    // lane q now fetches the event whose slot is q
+    int src = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) src = (__shfl_sync(hmask, slot, q, 16) == lane) ? q : src;
+    const double rate_s = __shfl_sync(hmask, rate, src, 16);
+    // total rate and cumulative probabilities in slot order, sequentially (KineticMcFirstOmp.cpp:55-77)
+    double total = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) total += __shfl_sync(hmask, rate_s, q, 16);
+    double cumulative = 0.0, my_cumulative = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) {
+      cumulative += __shfl_sync(hmask, rate_s, q, 16) / total;
+      if (q == lane) my_cumulative = cumulative;
+    }
+    // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
+    double u1, u2;
+    if (replay_u1) {
+      u1 = replay_u1[static_cast<int64_t>(w) * n_steps + s];
+      u2 = replay_u2[static_cast<int64_t>(w) * n_steps + s];
+    } else {
+      uint32_t r[4];
+      philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
+                    static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r);
+      u1 = uniform53(r[0], r[1]) + (1.0 / 9007199254740992.0);   // (0, 1]: -log(u1) is finite
+      u2 = uniform53(r[2], r[3]);
+    }
+    const double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
+    const double dt = -log(u1) / total / kPrefactorHz * corr;
+    // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
+    const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> (threadIdx.x & 16)) & 0xFFFu;
+    const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
+    const int sel_lane = __shfl_sync(hmask, src, sel_slot, 16);
+    const double sel_ea = __shfl_sync(hmask, ea, sel_lane, 16), sel_de = __shfl_sync(hmask, de, sel_lane, 16);
+    const int nx = __shfl_sync(hmask, xj, sel_lane, 16), ny = __shfl_sync(hmask, yj, sel_lane, 16),
+              nz = __shfl_sync(hmask, zj, sel_lane, 16);
+    const unsigned sel_mig = __shfl_sync(hmask, mig, sel_lane, 16);
+    if (lane == 0) {
+      if (tr.from) tr.from[static_cast<int64_t>(w) * n_steps + s] = lat.id_of_coords(X, Y, Z);
+      if (tr.to) tr.to[static_cast<int64_t>(w) * n_steps + s] = lat.id_of_coords(nx, ny, nz);
+      if (tr.slot) tr.slot[static_cast<int64_t>(w) * n_steps + s] = sel_slot;
+      if (tr.dt) tr.dt[static_cast<int64_t>(w) * n_steps + s] = dt;
+      if (tr.Ea) tr.Ea[static_cast<int64_t>(w) * n_steps + s] = sel_ea;
+      if (tr.dE) tr.dE[static_cast<int64_t>(w) * n_steps + s] = sel_de;
+      if (tr.total_rate) tr.total_rate[static_cast<int64_t>(w) * n_steps + s] = total;
+      if (tr.temperature) tr.temperature[static_cast<int64_t>(w) * n_steps + s] = temperature;
+      // 7. Config::LatticeJump: the atom moves into the vacancy, the vacancy into the atom's site
+      store_site(lat, o, X, Y, Z, static_cast<uint8_t>(sel_mig));
+      store_site(lat, o, nx, ny, nz, static_cast<uint8_t>(vac_code));
+    }
+    time += dt;
+    energy += sel_de;
+    ++steps;
+    X = nx; Y = ny; Z = nz;
+    __syncwarp(hmask);
+  }
+  if (lane == 0) {
+    st.vacancy[w] = lat.id_of_coords(X, Y, Z);
+    st.time[w] = time;
+    st.energy[w] = energy;
+    st.steps[w] = steps;
+    st.temperature[w] = temperature;
+  }
+  const unsigned any_err = __ballot_sync(hmask, err != 0);
+  if (any_err && lane == 0) {
+    int e = 0;
+    (void)e;
+  }
+  if (err) atomicOr(&st.error[w], err);
+}
+
+}  // namespace lmc

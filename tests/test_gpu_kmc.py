@@ -1,0 +1,108 @@
+"""GPU suite: the batched KMC driver (lmc_kmc_run) against the reference's own KineticMcFirstOmp traces
+(golden, generated with a seeded std::mt19937_64) in replay mode -- north_star: "a replay mode that feeds the
+reference's random stream must reproduce its event sequence" -- plus determinism / chunking / multi-walker checks."""
+import numpy as np
+import pytest
+
+from latticemontecarlo_b200 import capi, synth
+from oracle import lmc_oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _engine(golden, tag, tmp_path, n_walkers=1):
+    order = capi.ORDER_REASSIGNED if int(golden[tag + "_factor"][1]) else capi.ORDER_GENERATE
+    e = capi.Engine(int(golden[tag + "_factor"][0]), id_order=order, n_walkers=n_walkers, device=0)
+    e.load_coefficients(H.golden_json(golden, tmp_path))
+    return e
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("run", ["kmc", "kmc_tt"])
+def test_replay_reproduces_reference_event_sequence(golden, tag, run, tmp_path):
+    e = _engine(golden, tag, tmp_path, n_walkers=3)
+    g = lambda k: golden["%s_%s_%s" % (tag, run, k)]
+    n = len(g("u1"))
+    for w in range(3):
+        e.set_occupancy(golden[tag + "_occ"], walker=w)
+    e.kmc_reset()
+    kw = dict(time_temperature=golden["tt_points"], rate_corrector=True) if run == "kmc_tt" else {}
+    u1 = np.tile(g("u1"), (3, 1)); u2 = np.tile(g("u2"), (3, 1))
+    tr = e.kmc_run(n, temperature=500.0, replay_u1=u1, replay_u2=u2, trace=True, **kw)
+    for w in range(3):
+        assert np.array_equal(tr["from"][w], g("from")) and np.array_equal(tr["to"][w], g("to"))
+        assert np.array_equal(tr["slot"][w], g("slot"))
+        assert np.max(np.abs(tr["Ea"][w] - g("Ea"))) < TOL and np.max(np.abs(tr["dE"][w] - g("dE"))) < TOL
+        assert np.allclose(tr["total_rate"][w], g("total_rate"), rtol=1e-9, atol=0)
+        assert np.allclose(tr["dt"][w], g("dt"), rtol=1e-9, atol=4e-16 * float(np.abs(g("time")).max()))
+        assert np.allclose(tr["temperature"][w], g("temperature"), rtol=1e-12, atol=0)
+        assert np.array_equal(e.get_occupancy(w), g("final_occ"))
+    st = e.kmc_state()
+    assert np.all(st["steps"] == n)
+    assert np.allclose(st["time"], g("time")[-1], rtol=1e-9) and np.max(np.abs(st["energy"] - g("energy")[-1])) < TOL
+    assert np.all(st["vacancy"] == g("to")[-1])
+
+
+def test_philox_runs_are_deterministic_and_chunkable(golden, tmp_path):
+    e = _engine(golden, "B", tmp_path, n_walkers=64)
+    occ = golden["B_occ"]
+
+    def run(chunks):
+        for w in range(64):
+            e.set_occupancy(occ, walker=w)
+        e.kmc_reset()
+        for c in chunks:
+            e.kmc_run(c, temperatures=np.linspace(400.0, 600.0, 64), seed=1234)
+        return e.kmc_state(), e.get_occupancy_all()
+
+    s1, o1 = run([200])
+    s2, o2 = run([200])
+    s3, o3 = run([50, 150])
+    assert np.array_equal(o1, o2) and np.array_equal(s1["time"], s2["time"]) and np.array_equal(s1["energy"], s2["energy"])
+    assert np.array_equal(o1, o3) and np.array_equal(s1["time"], s3["time"])          # counter = step number
+    assert len(set(s1["vacancy"].tolist())) > 8                                          # walkers decorrelate
+    assert np.all(s1["steps"] == 200) and np.all(s1["time"] > 0)
+    # every walker still holds exactly one vacancy and the composition is conserved
+    assert np.all((o1 == 0).sum(axis=1) == 1)
+    assert np.array_equal(np.sort(o1, axis=1), np.tile(np.sort(occ), (64, 1)))
+    # hotter walkers run faster clocks per step on average
+    assert s1["time"][:16].mean() > s1["time"][-16:].mean()
+
+
+def test_walkers_follow_oracle_with_device_random_numbers(coef_json):
+    """Philox mode: recompute each step's decision on the CPU oracle from the traced state (events are a function of
+    occupancy only, so the traced (from, to, Ea, dE, total_rate) of every step can be verified independently)."""
+    f = 5
+    occ = synth.random_alloy(f, 0.04, 0.04, seed=5)
+    cfg = O.Config.generate_fcc(f, occ)
+    cfg.reassign_lattice_vector()
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=2, device=0)
+    e.load_coefficients(coef_json)
+    for w in range(2):
+        e.set_occupancy(cfg.occ, walker=w)
+    e.kmc_reset()
+    tr = e.kmc_run(12, temperature=450.0, seed=99, trace=True)
+    quartic = O.VacancyMigrationPredictorQuartic(coef_json, cfg, H.CODES)
+    beta = 1.0 / O.K_BOLTZMANN / 450.0
+    for s in range(12):
+        vac = int(tr["from"][0, s])
+        assert cfg.occ[vac] == 0
+        nbrs = cfg.nn[0][vac]
+        ea, de = quartic.barrier_and_diff(cfg, np.full(12, vac), nbrs)
+        slot = int(tr["slot"][0, s])
+        assert int(nbrs[slot]) == int(tr["to"][0, s])
+        assert abs(ea[slot] - tr["Ea"][0, s]) < TOL and abs(de[slot] - tr["dE"][0, s]) < TOL
+        assert abs(np.exp(-ea * beta).sum() / tr["total_rate"][0, s] - 1) < 1e-10
+        assert tr["dt"][0, s] > 0
+        cfg.lattice_jump(vac, int(tr["to"][0, s]))
+    assert np.array_equal(e.get_occupancy(0), cfg.occ)
+
+
+def test_kmc_rejects_bad_walkers(golden, tmp_path):
+    e = _engine(golden, "A", tmp_path, n_walkers=2)
+    e.set_occupancy(golden["A_occ"], walker=0)
+    e.set_occupancy(golden["A_cmc_occ"], walker=1)         # no vacancy at all
+    with pytest.raises(capi.LmcOutOfRange):
+        e.kmc_reset()
