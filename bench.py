@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the LatticeMC hot path on B200 (contract: see the task's bench.py section).
+
+Metric (BASELINE.json): KMC vacancy hops/s (primary, walker-sharded, weak scaling) and CMC swap trials/s
+(secondary object "cmc") per box, next to the reference's own CPU path timed on this box's host cores.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [--gpus N] ...                the reference's CPU implementation (oracle/_ref)
+
+One "step" = one pass of the hot path over one batch: every walker of the rank advances `--hops` KMC steps
+(12 candidate barriers + Arrhenius rates + event select + residence time + jump per hop) in ONE kernel launch.
+Workload = BASELINE configs[2] shape: independent single-vacancy Al-2%Mg-2%Zn walkers on 8x8x8 FCC cells
+(2048 sites), T_w = 400..600 K, synthetic JSON coefficients; 8192 walkers per GPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_KMC_STEP = 3792 + 18   # 12 events x 316 B + state update
+BYTES_PER_EVENT = 316            # 60 B occupancy + 240 B neighbour indices + 16 B output
+BYTES_PER_TRIAL = 440            # CMC/SA swap trial
+FACTOR = 8                       # 8x8x8 cells = 2048 sites per walker
+P_MG = P_ZN = 0.02
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def walker_occupancy(first_walker, n_walkers, factor=FACTOR):
+    """Random Al-Mg-Zn alloy per walker (seed 42 + global walker index), one vacancy each, REASSIGNED id order."""
+    n = 4 * factor ** 3
+    out = np.empty((n_walkers, n), dtype=np.uint8)
+    for w in range(n_walkers):
+        u = np.random.default_rng(42 + first_walker + w).random(n)
+        row = out[w]
+        row[:] = 1
+        row[u < P_MG + P_ZN] = 3
+        row[u < P_MG] = 2
+        row[n // 2 + 3] = 0
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) >= 8 and r[4 + k].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def _ref_worker(args):
+    """One reference trajectory: mc::KineticMcFirstOmp::Simulate (LRU predictor, as shipped) on one walker, 1 OMP thread."""
+    seed, steps, json_path = args
+    from oracle import ref_lib as R
+    occ = walker_occupancy(seed, 1)[0]
+    # walker_occupancy is in REASSIGNED order; the reference config is built in GenerateFCC order then reassigned
+    from latticemontecarlo_b200 import synth
+    perm = synth.generate_to_reassigned_permutation(FACTOR)      # perm[new] = old
+    occ_gen = np.empty_like(occ)
+    occ_gen[perm] = occ
+    cfg = R.RefConfig.fcc(FACTOR, occ_gen, reassign=True)
+    t0 = time.perf_counter()
+    out = R.kmc_first_omp(cfg, json_path, temperature=400.0 + 200.0 * (seed % 8192) / 8191.0, maximum_steps=steps - 1,
+                          seed=seed + 1, threads=1, trace=False)
+    return out["seconds"], time.perf_counter() - t0
+
+
+def reference_kmc_throughput(json_path, steps_per_walker, n_procs, first_seed=0):
+    """Aggregate hops/s of n_procs independent reference trajectories running concurrently (one per host core)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(n_procs) as pool:
+        res = pool.map(_ref_worker, [(first_seed + p, steps_per_walker, json_path) for p in range(n_procs)])
+    wall = time.perf_counter() - t0
+    simulate_s = max(r[0] for r in res)          # slowest trajectory's time inside Simulate() (constructors excluded)
+    return n_procs * steps_per_walker / simulate_s, simulate_s, wall
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import ref_lib as R
+    from latticemontecarlo_b200 import synth
+    if not R.build():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblmc_ref.so missing and /root/reference absent"}))
+        return 0
+    cores = host_cores()
+    with tempfile.TemporaryDirectory() as d:
+        js = os.path.join(d, "quartic_coefficients.json")
+        synth.write_synthetic_json(js)
+        steps_per_walker = args.ref_hops
+        for _ in range(args.warmup if args.warmup < 2 else 1):     # one short warm-up pass (page-in, LRU is per process anyway)
+            reference_kmc_throughput(js, max(200, steps_per_walker // 10), cores)
+        rates, times = [], []
+        for k in range(args.steps):
+            rate, sim_s, _ = reference_kmc_throughput(js, steps_per_walker, cores, first_seed=1000 * k)
+            rates.append(rate)
+            times.append(sim_s)
+    value = sum(cores * steps_per_walker for _ in rates) / sum(times)
+    sample = "%d concurrent mc::KineticMcFirstOmp trajectories (LRU predictor as shipped, 1 OMP thread each) x %d hops, 8x8x8 cell" % (
+        cores, steps_per_walker)
+    line = {
+        "impl": "reference", "metric": "kmc_vacancy_hops_per_s", "value": value, "unit": "hops/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": value, "unit": "hops/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "hops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_gpus):
+    return {"workload": "BASELINE configs[2]: batched KMC, independent single-vacancy Al-2%Mg-2%Zn walkers on 8x8x8 FCC "
+                        "(2048 sites), T=400..600 K, walker-sharded, synthetic JSON coefficients (K=24/32)",
+            "walkers_per_gpu": args.walkers, "walkers_total": args.walkers * n_gpus, "hops_per_walker_per_step": args.hops,
+            "sites_per_walker": 4 * FACTOR ** 3, "l2": "flushed between timed steps (256 MiB write)",
+            "parallelism": "walker-sharded x%d, no data-path collective" % n_gpus}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    from latticemontecarlo_b200 import build as _build, capi, synth
+    _build.build()
+    if capi.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+    n_gpus = world
+    W, H = args.walkers, args.hops
+    n_sites = 4 * FACTOR ** 3
+    tmp = tempfile.TemporaryDirectory()
+    js = os.path.join(tmp.name, "quartic_coefficients.json")
+    synth.write_synthetic_json(js)
+    engine = capi.Engine(FACTOR, id_order=capi.ORDER_REASSIGNED, n_walkers=W, device=local_rank)
+    engine.load_coefficients(js)
+    occ_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
+    occ_np = occ_pinned.numpy()
+    occ_np[:] = walker_occupancy(rank * W, W)
+    out_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
+    temps = 400.0 + 200.0 * (rank * W + np.arange(W)) / max(1, W * n_gpus - 1)
+    stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    engine.set_occupancy_all(occ_np)
+    engine.kmc_reset()
+
+    def step_resident():
+        flush.fill_(1)                       # evict the walkers' occupancy from L2 between timed steps
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            engine.kmc_run(H, temperatures=temps, seed=20260101)
+            e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1), engine.last_kernel_ms()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    launches0 = engine.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        wall0 = time.perf_counter()
+        timings = [step_resident() for _ in range(args.steps)]
+        barrier()
+        wall = time.perf_counter() - wall0
+    launches = engine.launch_count() - launches0
+    step_ms = sum(t[0] for t in timings)
+    kernel_ms = sum(t[1] for t in timings)
+    if world > 1:
+        t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms, kernel_ms = float(t[0]), float(t[1])
+    hops_total = float(W) * H * args.steps * n_gpus
+    value = hops_total / (step_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers: H2D occupancy, reset, run, D2H state + occupancy
+    def step_e2e():
+        t0 = time.perf_counter()
+        engine.set_occupancy_all(occ_np)
+        engine.kmc_reset()
+        engine.kmc_run(H, temperatures=temps, seed=20260101)
+        st = engine.kmc_state()
+        capi._check(capi.lib().lmc_engine_get_occupancy_all(engine.h, out_pinned.numpy().ctypes.data_as(capi.C.c_void_p),
+                                                            capi.C.c_int64(W * n_sites)))
+        return time.perf_counter() - t0, st
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e2e_s = sum(step_e2e()[0] for _ in range(args.steps))
+    barrier()
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = hops_total / e2e_s
+
+    peak, peak_kind = measured_peaks()
+    achieved = (float(W) * H * args.steps * BYTES_PER_KMC_STEP) / (kernel_ms * 1e-3) / 1e9     # per GPU, dominant kernel
+    line = {
+        "metric": "kmc_vacancy_hops_per_s", "value": value, "unit": "hops/s", "n_gpus": n_gpus, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus),
+        "e2e": {"value": e2e_value, "unit": "hops/s", "h2d_bytes_per_step": int(W * n_sites + W * 8),
+                "d2h_bytes_per_step": int(W * n_sites + W * 44)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "kmc_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": int(W * H * BYTES_PER_KMC_STEP),
+                     "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
+                             "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"},
+        "wall_s_timed_region": wall,
+    }
+    if rank == 0:
+        line["clocks"] = clocks.summary()
+        line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(js)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def bench_barrier_eval(engine, torch, W, peak):
+    """Batched barrier evaluation with resident inputs: all 12 candidate events of every walker's vacancy."""
+    st = engine.kmc_state()
+    vac = st["vacancy"]
+    nbrs = np.stack([engine.neighbors(1, int(v)) for v in vac[:256]])
+    # neighbour ids for all walkers: translation by the vacancy differs per walker, so compute on the host once
+    all_nbrs = np.empty((W, 12), dtype=np.int64)
+    all_nbrs[:256] = nbrs
+    for w in range(256, W):
+        all_nbrs[w] = engine.neighbors(1, int(vac[w]))
+    n = W * 12
+    dev = torch.device("cuda")
+    d_w = torch.from_numpy(np.repeat(np.arange(W, dtype=np.int32), 12)).to(dev)
+    d_i = torch.from_numpy(np.repeat(vac, 12)).to(dev)
+    d_j = torch.from_numpy(all_nbrs.reshape(-1)).to(dev)
+    d_ea = torch.empty(n, dtype=torch.float64, device=dev)
+    d_de = torch.empty(n, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    times = []
+    for k in range(8):
+        engine.eval_barriers_dev(n, d_w.data_ptr(), d_i.data_ptr(), d_j.data_ptr(), d_ea.data_ptr(), d_de.data_ptr())
+        ms = engine.last_kernel_ms()
+        if k >= 3:
+            times.append(ms)
+    ms = sum(times) / len(times)
+    achieved = n * BYTES_PER_EVENT / (ms * 1e-3) / 1e9
+    return {"kernel": "barrier_kernel", "events": n, "ms": ms, "events_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
+            "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item())}
+
+
+def cpu_baseline(json_path):
+    """The reference's own KMC driver on this box's host cores, bounded sample (about 10-20 s of CPU work)."""
+    try:
+        from oracle import ref_lib as R
+        if not R.build():
+            return {"value": None, "unit": "hops/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref unavailable"}
+        cores = host_cores()
+        steps = 20000
+        rate, sim_s, wall = reference_kmc_throughput(json_path, steps, cores)
+        return {"value": rate, "unit": "hops/s", "cores": cores, "kind": "reference",
+                "sample": "%d concurrent mc::KineticMcFirstOmp trajectories (LRU on, 1 OMP thread each) x %d hops on the 8x8x8 "
+                          "workload; %.1f s inside Simulate(), %.1f s wall incl. predictor construction" % (cores, steps, sim_s, wall)}
+    except Exception as exc:  # the baseline must never take the GPU number down with it
+        return {"value": None, "unit": "hops/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--walkers", type=int, default=8192, help="walkers per GPU")
+    ap.add_argument("--hops", type=int, default=512, help="KMC steps per walker per bench step")
+    ap.add_argument("--ref-hops", type=int, default=4000, help="reference arm: hops per trajectory per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -21,22 +21,9 @@ constexpr int kEnvN = 58, kSiteEnvN = 42;
 
 enum EventError : int { kErrNotNeighbour = 1, kErrNotVacancy = 2, kErrExtraVacancy = 4, kErrBadSite = 8 };
 
-// Species of the environment as bit planes over the env index (58 or 42 bits used).
-struct EnvBits {
-  uint64_t sol;        // species != solvent
-  uint64_t p0, p1, p2; // bits of the compact species code
-  __device__ __forceinline__ int code(int t) const {
-    return static_cast<int>((p0 >> t) & 1ULL) | (static_cast<int>((p1 >> t) & 1ULL) << 1) | (static_cast<int>((p2 >> t) & 1ULL) << 2);
-  }
-};
-
-__device__ __forceinline__ void envbits_add(EnvBits &e, int t, unsigned code, unsigned solvent) {
-  const uint64_t bit = 1ULL << t;
-  if (code != solvent) e.sol |= bit;
-  if (code & 1u) e.p0 |= bit;
-  if (code & 2u) e.p1 |= bit;
-  if (code & 4u) e.p2 |= bit;
-}
+// The environment of an event is summarised by ONE bit mask over the env index: bit t set <=> the species at env
+// site t differs from the solvent.  Only those sites contribute to the contracted (delta-form) tables, and their
+// species codes are re-read from the occupancy when they are visited (an L1 hit; solute sites are rare).
 
 __device__ __forceinline__ int direction_of(const LatticeDesc &lat, const DevTables &tab, int xi, int yi, int zi, int xj, int yj,
                                             int zj) {
@@ -49,60 +36,73 @@ __device__ __forceinline__ int direction_of(const LatticeDesc &lat, const DevTab
   return tab.dir_lut[(dx + 1) * 9 + (dy + 1) * 3 + (dz + 1)];
 }
 
-// Closed form of pred/src/VacancyMigrationPredictorQuartic.cpp:266-275
-__device__ __forceinline__ double quartic_barrier(double dE, double D, double Ks) {
-  const double b = 4.0 * dE / (D * D * D);
-  const double a = Ks / (4.0 * D * D);
-  const double c = (9.0 * b * b - 16.0 * a * a * D * D) / (32.0 * a);
-  const double delta = sqrt(fabs(9.0 * b * b - 32.0 * a * c));
-  const double s = 3.0 * b + delta;
-  return s * s * (3.0 * b * b - 16.0 * a * c + b * delta) / (a * a * a) / 2048.0;
+// Closed form of pred/src/VacancyMigrationPredictorQuartic.cpp:266-275, algebraically reduced.  With
+//   b = 4 dE / D^3,  a = Ks / (4 D^2),  c = (9 b^2 - 16 a^2 D^2) / (32 a)   one has   9 b^2 - 32 a c = 16 a^2 D^2,
+// so delta = 4 a D, and with  E0 = Ks D^2  and  x = b / (a D) = 16 dE / E0  the barrier is
+//   Ea = E0 (3x + 4)^2 (8 + 4x - 1.5 x^2) / 8192        (dE = 0  =>  Ea = Ks D^2 / 64).
+// log_e0 = logKs + 2 logD comes straight from the contracted tables, so one exp and one division suffice.
+__device__ __forceinline__ double quartic_barrier_log(double dE, double log_e0) {
+  const double e0 = exp(log_e0);
+  const double x = 16.0 * dE / e0;
+  const double s = 3.0 * x + 4.0;
+  return e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
 }
 
-// Walk the solute bits of a jump environment and accumulate the three contracted quantities.
-__device__ __forceinline__ void accumulate_pair_tables(const DevTables &tab, int m, const EnvBits &env, double acc[3]) {
+// env index of a state-list position (the jump pair sits at positions 21 and 38)
+__host__ __device__ constexpr int env_of_pos(int t) { return t - (t > kFirstPos) - (t > kSecondPos); }
+__device__ __forceinline__ int pos_of_env(int e) { return e + (e >= kFirstPos) + (e >= kSecondPos - 1); }
+
+// Gather the 60 ordered sites of a jump (first site at padded index `base`; drow = offset row of its direction and
+// z parity) and return the solute mask over the 58 env sites plus the species at the two pair sites.
+__device__ __forceinline__ uint64_t gather_pair_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
+                                                    unsigned solvent, unsigned *first, unsigned *mig) {
+  unsigned codes[60];
+#pragma unroll
+  for (int t = 0; t < 60; ++t) codes[t] = occ[base + drow[t]];
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int t = 0; t < 60; ++t) {
+    if (t == kFirstPos || t == kSecondPos) continue;
+    const int e = env_of_pos(t);
+    if (e < 32) lo |= (codes[t] != solvent) ? (1u << e) : 0u;
+    else hi |= (codes[t] != solvent) ? (1u << (e - 32)) : 0u;
+  }
+  *first = codes[kFirstPos];
+  *mig = codes[kSecondPos];
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Walk the solute bits of a jump environment and accumulate the three contracted quantities (dE, logD, logKs).
+// Returns false if a vacancy sits in the environment (the reference has no cluster type for two vacancies).
+__device__ __forceinline__ bool accumulate_pair_tables(const DevTables &tab, int m, uint64_t sol, const uint8_t *occ, int64_t base,
+                                                       const int32_t *__restrict__ drow, double acc[3]) {
   const int n = tab.n_species;
   const double *__restrict__ C = tab.pair_C + m * 3;
-  acc[0] = C[0]; acc[1] = C[1]; acc[2] = C[2];
+  acc[0] = __ldg(C); acc[1] = __ldg(C + 1); acc[2] = __ldg(C + 2);
   const double *__restrict__ A = tab.pair_A + static_cast<size_t>(m) * kEnvN * n * 3;
   const double *__restrict__ B = tab.pair_B + static_cast<size_t>(m) * tab.n_pair_pairs * n * n * 3;
-  uint64_t sol = env.sol;
+  bool ok = true;
   while (sol) {
     const int t = __ffsll(static_cast<long long>(sol)) - 1;
     sol &= sol - 1;
-    const int et = env.code(t);
+    const int et = occ[base + drow[pos_of_env(t)]];
+    if (et >= n) { ok = false; continue; }
     const double *a = A + (t * n + et) * 3;
     acc[0] += __ldg(a); acc[1] += __ldg(a + 1); acc[2] += __ldg(a + 2);
     const uint64_t hi = __ldg(tab.pair_mask_hi + t);
     uint64_t partners = hi & sol;
-    const int base = __ldg(tab.pair_base + t);
+    const int pbase = __ldg(tab.pair_base + t);
     while (partners) {
       const int u = __ffsll(static_cast<long long>(partners)) - 1;
       partners &= partners - 1;
-      const int eu = env.code(u);
-      const int p = base + __popcll(hi & ((1ULL << u) - 1ULL));
+      const int eu = occ[base + drow[pos_of_env(u)]];
+      if (eu >= n) { ok = false; continue; }
+      const int p = pbase + __popcll(hi & ((1ULL << u) - 1ULL));
       const double *b = B + ((static_cast<size_t>(p) * n + et) * n + eu) * 3;
       acc[0] += __ldg(b); acc[1] += __ldg(b + 1); acc[2] += __ldg(b + 2);
     }
   }
-}
-
-// Gather the 60 ordered sites of jump (first site at padded index `base`, direction k, z parity zpar) into bit planes.
-// `delta` is the [24][61] offset table (shared or global).  Returns the species at the second site in *mig and
-// the species at the first site in *first.
-__device__ __forceinline__ void gather_pair_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
-                                                unsigned solvent, EnvBits &env, unsigned *first, unsigned *mig) {
-  env.sol = env.p0 = env.p1 = env.p2 = 0;
-  unsigned codes[60];
-#pragma unroll
-  for (int t = 0; t < 60; ++t) codes[t] = occ[base + drow[t]];
-#pragma unroll
-  for (int t = 0; t < 60; ++t) {
-    if (t == kFirstPos) { *first = codes[t]; continue; }
-    if (t == kSecondPos) { *mig = codes[t]; continue; }
-    const int e = t - (t > kFirstPos) - (t > kSecondPos);
-    envbits_add(env, e, codes[t], solvent);
-  }
+  return ok;
 }
 
 // ----------------------------------------------------------------------------------------------- occupancy I/O
@@ -140,19 +140,19 @@ __global__ void download_occupancy_kernel(LatticeDesc lat, const uint8_t *__rest
 // write one site and all its periodic halo images
 __device__ __forceinline__ void store_site(const LatticeDesc &lat, uint8_t *occ, int X, int Y, int Z, uint8_t code) {
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
-#pragma unroll
+  occ[lat.padded_index(X, Y, Z)] = code;
+  const bool edge = X < kHalo || X >= px - kHalo || Y < kHalo || Y >= py - kHalo || Z < kHaloZ || Z >= pz - kHaloZ;
+  if (!edge) return;                 // interior sites have no halo image
   for (int a = -1; a <= 1; ++a) {
     const int x = X + a * px;
     if (x < -kHalo || x >= px + kHalo) continue;
-#pragma unroll
     for (int b = -1; b <= 1; ++b) {
       const int y = Y + b * py;
       if (y < -kHalo || y >= py + kHalo) continue;
-#pragma unroll
       for (int c = -1; c <= 1; ++c) {
         const int z = Z + c * pz;
         if (z < -kHaloZ || z >= pz + kHaloZ) continue;
-        occ[lat.padded_index(x, y, z)] = code;
+        if (a | b | c) occ[lat.padded_index(x, y, z)] = code;
       }
     }
   }
@@ -201,25 +201,19 @@ barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
       const uint8_t *o = occ + w * walker_stride;
       const int64_t base = lat.padded_index(xi, yi, zi);
       const int32_t *drow = s_delta + (k * 2 + (zi & 1)) * kPairDeltaStride;
-      EnvBits env;
       unsigned first = 0, mig = 0;
-      gather_pair_env(o, base, drow, static_cast<unsigned>(tab.solvent), env, &first, &mig);
+      const uint64_t sol = gather_pair_env(o, base, drow, static_cast<unsigned>(tab.solvent), &first, &mig);
       const unsigned vac = static_cast<unsigned>(tab.n_species);
-      // a vacancy in the environment has all code bits of `vac` set; detect any
-      uint64_t is_vac = ~0ULL;
-      is_vac &= (vac & 1u) ? env.p0 : ~env.p0;
-      is_vac &= (vac & 2u) ? env.p1 : ~env.p1;
-      is_vac &= (vac & 4u) ? env.p2 : ~env.p2;
-      is_vac &= (1ULL << kEnvN) - 1ULL;
       if (first != vac || mig == vac) err = kErrNotVacancy;
-      else if (is_vac) err = kErrExtraVacancy;
       else {
         double acc[3];
-        accumulate_pair_tables(tab, static_cast<int>(mig), env, acc);
-        out_de = acc[0];
-        out_d = exp(acc[1]);
-        out_ks = exp(acc[2]);
-        out_ea = quartic_barrier(out_de, out_d, out_ks);
+        if (!accumulate_pair_tables(tab, static_cast<int>(mig), sol, o, base, drow, acc)) err = kErrExtraVacancy;
+        else {
+          out_de = acc[0];
+          out_ea = quartic_barrier_log(out_de, acc[2] + 2.0 * acc[1]);
+          if (D_out) out_d = exp(acc[1]);
+          if (Ks_out) out_ks = exp(acc[2]);
+        }
       }
     }
   }
@@ -231,41 +225,53 @@ barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
 }
 
 // ----------------------------------------------------------------------------------------------- site / swap dE
-__device__ __forceinline__ void gather_site_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
-                                                unsigned solvent, EnvBits &env, unsigned *centre, int64_t override_index,
-                                                unsigned override_code) {
-  env.sol = env.p0 = env.p1 = env.p2 = 0;
+// Site neighbourhood (43 ordered sites, centre at position 21): solute mask over the 42 env sites.  In the coupled
+// swap case one env site (`override_index`, a padded index) is to be seen with `override_code` instead of memory.
+__device__ __forceinline__ uint64_t gather_site_env(const uint8_t *occ, int64_t base, const int32_t *__restrict__ drow,
+                                                    unsigned solvent, unsigned *centre, int64_t override_index, unsigned override_code) {
+  unsigned codes[43];
+#pragma unroll
+  for (int t = 0; t < 43; ++t) codes[t] = occ[base + drow[t]];
+  uint32_t lo = 0, hi = 0;
 #pragma unroll
   for (int t = 0; t < 43; ++t) {
-    const int64_t idx = base + drow[t];
-    unsigned c = occ[idx];
-    if (idx == override_index) c = override_code;
-    if (t == kCentrePos) { *centre = c; continue; }
-    envbits_add(env, t - (t > kCentrePos), c, solvent);
+    if (t == kCentrePos) continue;
+    const int e = t - (t > kCentrePos);
+    unsigned c = codes[t];
+    if (base + drow[t] == override_index) c = override_code;
+    if (e < 32) lo |= (c != solvent) ? (1u << e) : 0u;
+    else hi |= (c != solvent) ? (1u << (e - 32)) : 0u;
   }
+  *centre = codes[kCentrePos];
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 
 // H(x_new, env) - H(x_old, env) with the contracted site tables
-__device__ __forceinline__ double site_energy_change(const DevTables &tab, int x_old, int x_new, const EnvBits &env) {
+__device__ __forceinline__ double site_energy_change(const DevTables &tab, int x_old, int x_new, uint64_t sol, const uint8_t *occ,
+                                                     int64_t base, const int32_t *__restrict__ drow, int64_t override_index,
+                                                     unsigned override_code) {
   const int m = tab.n_species + 1;
   const size_t a_stride = static_cast<size_t>(kSiteEnvN) * m, b_stride = static_cast<size_t>(tab.n_site_pairs) * m * m;
   const double *__restrict__ A_new = tab.site_A + x_new * a_stride, *__restrict__ A_old = tab.site_A + x_old * a_stride;
   const double *__restrict__ B_new = tab.site_B + x_new * b_stride, *__restrict__ B_old = tab.site_B + x_old * b_stride;
   double acc = __ldg(tab.site_C + x_new) - __ldg(tab.site_C + x_old);
-  uint64_t sol = env.sol;
+  auto code_at = [&](int e) -> int {
+    const int64_t idx = base + drow[e + (e >= kCentrePos)];
+    return idx == override_index ? static_cast<int>(override_code) : static_cast<int>(occ[idx]);
+  };
   while (sol) {
     const int t = __ffsll(static_cast<long long>(sol)) - 1;
     sol &= sol - 1;
-    const int et = env.code(t);
+    const int et = code_at(t);
     acc += __ldg(A_new + t * m + et) - __ldg(A_old + t * m + et);
     const uint64_t hi = __ldg(tab.site_mask_hi + t);
     uint64_t partners = hi & sol;
-    const int base = __ldg(tab.site_base + t);
+    const int pbase = __ldg(tab.site_base + t);
     while (partners) {
       const int u = __ffsll(static_cast<long long>(partners)) - 1;
       partners &= partners - 1;
-      const int eu = env.code(u);
-      const size_t p = (static_cast<size_t>(base + __popcll(hi & ((1ULL << u) - 1ULL))) * m + et) * m + eu;
+      const int eu = code_at(u);
+      const size_t p = (static_cast<size_t>(pbase + __popcll(hi & ((1ULL << u) - 1ULL))) * m + et) * m + eu;
       acc += __ldg(B_new + p) - __ldg(B_old + p);
     }
   }
@@ -280,6 +286,7 @@ __device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, con
                                                      const int32_t *__restrict__ s_delta, int xa, int ya, int za, int xb, int yb,
                                                      int zb, int *err) {
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
+  (void)vac;
   int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
   unsigned ea = occ[base_a], eb = occ[base_b];
   if (ea == eb) return 0.0;
@@ -297,22 +304,16 @@ __device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, con
     const int tz = zpa; zpa = zpb; zpb = tz;
     dx = -dx; dy = -dy; dz = -dz;
   }
-  EnvBits env;
   unsigned centre;
-  gather_site_env(occ, base_a, s_delta + zpa * 43, solvent, env, &centre, -1, 0);
-  uint64_t is_vac = ~0ULL;
-  is_vac &= (vac & 1u) ? env.p0 : ~env.p0;
-  is_vac &= (vac & 2u) ? env.p1 : ~env.p1;
-  is_vac &= (vac & 4u) ? env.p2 : ~env.p2;
-  is_vac &= (1ULL << kSiteEnvN) - 1ULL;
-  (void)is_vac;
-  double de = site_energy_change(tab, static_cast<int>(ea), static_cast<int>(eb), env);
+  const int32_t *row_a = s_delta + zpa * 43, *row_b = s_delta + zpb * 43;
+  uint64_t sol = gather_site_env(occ, base_a, row_a, solvent, &centre, -1, 0);
+  double de = site_energy_change(tab, static_cast<int>(ea), static_cast<int>(eb), sol, occ, base_a, row_a, -1, 0);
   // second site; in the coupled case it sees site a already holding e_b.  The halo images of a are not updated in
   // memory, so the override is applied by *position*: a sits at displacement (-dx,-dy,-dz) from b.
   int64_t override_index = -1;
   if (coupled) override_index = base_b + lat.padded_delta(-dx, -dy, -dz, zpb);
-  gather_site_env(occ, base_b, s_delta + zpb * 43, solvent, env, &centre, override_index, eb);
-  de += site_energy_change(tab, static_cast<int>(eb), static_cast<int>(ea), env);
+  sol = gather_site_env(occ, base_b, row_b, solvent, &centre, override_index, eb);
+  de += site_energy_change(tab, static_cast<int>(eb), static_cast<int>(ea), sol, occ, base_b, row_b, override_index, eb);
   if (de != de) *err |= kErrExtraVacancy;   // NaN: a cluster type the reference has no index for
   return de;
 }
@@ -361,12 +362,13 @@ site_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
   int x, y, z;
   lat.coords_of_id(s, x, y, z);
   const uint8_t *o = occ + (walker ? walker[e] : 0) * walker_stride;
-  EnvBits env;
   unsigned centre = 0;
-  gather_site_env(o, lat.padded_index(x, y, z), s_delta + (z & 1) * 43, static_cast<unsigned>(tab.solvent), env, &centre, -1, 0);
+  const int64_t base = lat.padded_index(x, y, z);
+  const int32_t *row = s_delta + (z & 1) * 43;
+  const uint64_t sol = gather_site_env(o, base, row, static_cast<unsigned>(tab.solvent), &centre, -1, 0);
   double de = 0.0;
   if (centre != new_code[e]) {
-    de = site_energy_change(tab, static_cast<int>(centre), static_cast<int>(new_code[e]), env);
+    de = site_energy_change(tab, static_cast<int>(centre), static_cast<int>(new_code[e]), sol, o, base, row, -1, 0);
     if (de != de) atomicOr(error, kErrExtraVacancy);
   }
   dE[e] = de;

@@ -146,22 +146,17 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     if (active) {
       const int64_t base = lat.padded_index(X, Y, Z);
       const int32_t *drow = s_delta + (k * 2 + (Z & 1)) * kPairDeltaStride;
-      EnvBits env;
       unsigned first = 0;
-      gather_pair_env(o, base, drow, solvent, env, &first, &mig);
-      uint64_t is_vac = ~0ULL;
-      is_vac &= (vac_code & 1u) ? env.p0 : ~env.p0;
-      is_vac &= (vac_code & 2u) ? env.p1 : ~env.p1;
-      is_vac &= (vac_code & 4u) ? env.p2 : ~env.p2;
-      is_vac &= (1ULL << kEnvN) - 1ULL;
+      const uint64_t sol = gather_pair_env(o, base, drow, solvent, &first, &mig);
       if (first != vac_code || mig == vac_code) err |= kErrNotVacancy;
-      else if (is_vac) err |= kErrExtraVacancy;
       else {
         double acc[3];
-        accumulate_pair_tables(tab, static_cast<int>(mig), env, acc);
-        de = acc[0];
-        ea = quartic_barrier(de, exp(acc[1]), exp(acc[2]));
-        rate = exp(-ea * beta);                      // JumpEvent.cpp:13
+        if (!accumulate_pair_tables(tab, static_cast<int>(mig), sol, o, base, drow, acc)) err |= kErrExtraVacancy;
+        else {
+          de = acc[0];
+          ea = quartic_barrier_log(de, acc[2] + 2.0 * acc[1]);
+          rate = exp(-ea * beta);                      // JumpEvent.cpp:13
+        }
       }
     }
     if (__any_sync(hmask, err != 0)) break;
@@ -174,10 +169,12 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     double total = 0.0;
 #pragma unroll
     for (int q = 0; q < 12; ++q) total += __shfl_sync(hmask, rate_s, q, 16);
+    // p_q = rate_q / total (one division per lane, same operands as the reference), then the running sum in order
+    const double prob_s = rate_s / total;
     double cumulative = 0.0, my_cumulative = 0.0;
 #pragma unroll
     for (int q = 0; q < 12; ++q) {
-      cumulative += __shfl_sync(hmask, rate_s, q, 16) / total;
+      cumulative += __shfl_sync(hmask, prob_s, q, 16);
       if (q == lane) my_cumulative = cumulative;
     }
     // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
@@ -227,11 +224,6 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     st.energy[w] = energy;
     st.steps[w] = steps;
     st.temperature[w] = temperature;
-  }
-  const unsigned any_err = __ballot_sync(hmask, err != 0);
-  if (any_err && lane == 0) {
-    int e = 0;
-    (void)e;
   }
   if (err) atomicOr(&st.error[w], err);
 }
