@@ -152,6 +152,36 @@ int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_step
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy,
                       double *temperature);
 
+/* ------------------------------------------------------------------------------------------------ CMC / SA driver
+ * mc::CanonicalMcOmp / CanonicalMcSerial::Simulate (mc/src/CanonicalMcOmp.cpp:40-92, CanonicalMcSerial.cpp:40-51) and
+ * mc::SimulatedAnnealing::Simulate (mc/src/SimulatedAnnealing.cpp:99-185) for every replica of the engine: random
+ * unlike-species pairs (CanonicalMcAbstract.cpp:43-51), swap dE (EnergyChangePredictorPairSite), Metropolis accept
+ * (CanonicalMcAbstract.cpp:86-101).  Like CanonicalMcOmp, trials are processed in batches of mutually
+ * non-interfering pairs (no trial site inside the 43-site neighbourhood of another trial's sites), evaluated in
+ * parallel and applied; rejected-by-interference proposals are redrawn, as in the reference.
+ */
+typedef struct lmc_cmc_params {
+  double temperature;              /* `temperature` (CMC) */
+  const double *temperatures;      /* optional per-replica temperatures [n_walkers] */
+  uint64_t seed;                   /* Philox4x32-10 key */
+  int32_t batch_size;              /* proposals per batch (power of two, 32..1024); 0 = chosen from the lattice size */
+} lmc_cmc_params;
+
+/* reset steps / energy / counters of every replica; with sa_maximum_steps > 0 the SimulatedAnnealing schedule is armed:
+ * T0 = sa_initial_temperature, T *= exp(-3/max) per trial, acceptance window 0.001 max, reheats (SimulatedAnnealing.h:42-68) */
+int lmc_cmc_reset(lmc_engine *engine, double sa_initial_temperature, uint64_t sa_maximum_steps);
+/* run until every replica has done at least n_trials more effective trials (device RNG) */
+int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
+/* replay mode on replica `walker`: the n trials (site_a, site_b, u) are applied in the given order with the reference's
+ * serial semantics (u is consumed only when dE >= 0).  Outputs (host, [n], optional): dE, energy and temperature before
+ * each trial, accept flags. */
+int lmc_cmc_replay(lmc_engine *engine, int32_t walker, const lmc_cmc_params *params, int64_t n, const int64_t *site_a,
+                   const int64_t *site_b, const double *u, double *dE, double *energy_before, double *temperature_before,
+                   uint8_t *accepted);
+/* per-replica state (host arrays [n_walkers], any may be NULL): energy_ (relative to the reset), steps_, accepted trials,
+ * current temperature (SA) */
+int lmc_cmc_get_state(lmc_engine *engine, double *energy, int64_t *steps, int64_t *accepted, double *temperature);
+
 /* ------------------------------------------------------------------------------------------------ debug taps
  * Integer artefacts of the reference's algorithm, recomputed on the device, for bit-exact parity checks.
  * lists: the symmetry-ordered lattice-id lists of pair (site_i, site_j)

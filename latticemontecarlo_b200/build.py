@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblmc_b200.so")
 SOURCES = ["engine.cu", "tables.cpp"]
-HEADERS = ["engine.h", "kernels.cuh", "kmc_kernels.cuh", "tables.h", "lattice.h", "device_tables.h", os.path.join("..", "..", "include", "lmc_b200.h")]
+HEADERS = ["engine.h", "kernels.cuh", "kmc_kernels.cuh", "cmc_kernels.cuh", "tables.h", "lattice.h", "device_tables.h", os.path.join("..", "..", "include", "lmc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]

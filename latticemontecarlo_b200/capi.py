@@ -129,6 +129,10 @@ class KmcTrace(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("from_", "to", "slot", "dt", "Ea", "dE", "total_rate", "temperature")]
 
 
+class CmcParams(C.Structure):
+    _fields_ = [("temperature", C.c_double), ("temperatures", C.c_void_p), ("seed", C.c_uint64), ("batch_size", C.c_int32)]
+
+
 class Engine:
     """One lmc_engine (one GPU, or host-only with device=-1)."""
 
@@ -293,6 +297,43 @@ class Engine:
                    temperature=np.empty(n))
         _check(lib().lmc_kmc_get_state(self.h, _p(out["time"]), _p(out["energy"]), _p(out["steps"]), _p(out["vacancy"]),
                                        _p(out["temperature"])))
+        return out
+
+    # ---- CMC / SA driver (mc::CanonicalMcOmp / SimulatedAnnealing semantics over all replicas)
+    def cmc_reset(self, sa_initial_temperature=0.0, sa_maximum_steps=0):
+        _check(lib().lmc_cmc_reset(self.h, C.c_double(sa_initial_temperature), C.c_uint64(int(sa_maximum_steps))))
+
+    def _cmc_params(self, temperature, temperatures, seed, batch_size, keep):
+        prm = CmcParams()
+        prm.temperature = float(temperature)
+        if temperatures is not None:
+            t = np.ascontiguousarray(temperatures, dtype=np.float64); keep.append(t)
+            prm.temperatures = t.ctypes.data
+        prm.seed = int(seed)
+        prm.batch_size = int(batch_size)
+        return prm
+
+    def cmc_run(self, n_trials, temperature=800.0, temperatures=None, seed=0, batch_size=0):
+        keep = []
+        prm = self._cmc_params(temperature, temperatures, seed, batch_size, keep)
+        _check(lib().lmc_cmc_run(self.h, C.byref(prm), C.c_int64(int(n_trials))))
+
+    def cmc_replay(self, site_a, site_b, u, temperature=800.0, walker=0, batch_size=0):
+        a, b = _i64(site_a), _i64(site_b)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        n = len(a)
+        out = dict(dE=np.empty(n), energy_before=np.empty(n), temperature_before=np.empty(n), accepted=np.empty(n, np.uint8))
+        keep = []
+        prm = self._cmc_params(temperature, None, 0, batch_size, keep)
+        _check(lib().lmc_cmc_replay(self.h, int(walker), C.byref(prm), C.c_int64(n), _p(a), _p(b), _p(u), _p(out["dE"]),
+                                    _p(out["energy_before"]), _p(out["temperature_before"]), _p(out["accepted"])))
+        out["accepted"] = out["accepted"].astype(bool)
+        return out
+
+    def cmc_state(self):
+        n = self.n_walkers
+        out = dict(energy=np.empty(n), steps=np.empty(n, np.int64), accepted=np.empty(n, np.int64), temperature=np.empty(n))
+        _check(lib().lmc_cmc_get_state(self.h, _p(out["energy"]), _p(out["steps"]), _p(out["accepted"]), _p(out["temperature"])))
         return out
 
     # ---- debug taps (device)

@@ -13,6 +13,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "kmc_kernels.cuh"
+#include "cmc_kernels.cuh"
 #include "tables.h"
 
 namespace lmc {
@@ -620,6 +621,137 @@ void Engine::kmc_get_state(double *time, double *energy, int64_t *steps, int64_t
   LMC_CUDA(cudaStreamSynchronize(stream));
 }
 
+// ------------------------------------------------------------------------------------------------ CMC / SA driver
+void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps) {
+  require_device();
+  const size_t nw = static_cast<size_t>(n_walkers);
+  if (!d_cmc_energy) {
+    d_cmc_energy = dev_alloc<double>(nw); d_cmc_temperature = dev_alloc<double>(nw);
+    d_cmc_steps = dev_alloc<unsigned long long>(nw); d_cmc_accepted = dev_alloc<unsigned long long>(nw);
+    d_cmc_proposals = dev_alloc<unsigned long long>(nw); d_cmc_epoch = dev_alloc<unsigned long long>(nw);
+    d_cmc_sa = dev_alloc<SaSchedule>(nw); d_cmc_error = dev_alloc<int32_t>(nw);
+    d_cmc_claims = dev_alloc<unsigned long long>(nw * static_cast<size_t>(lat.padded_size));
+    for (void *p : {static_cast<void *>(d_cmc_energy), static_cast<void *>(d_cmc_temperature), static_cast<void *>(d_cmc_steps),
+                    static_cast<void *>(d_cmc_accepted), static_cast<void *>(d_cmc_proposals), static_cast<void *>(d_cmc_epoch),
+                    d_cmc_sa, static_cast<void *>(d_cmc_error), static_cast<void *>(d_cmc_claims)})
+      device_allocs.push_back(p);
+  }
+  LMC_CUDA(cudaMemsetAsync(d_cmc_energy, 0, nw * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_steps, 0, nw * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_accepted, 0, nw * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_proposals, 0, nw * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_epoch, 0, nw * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_error, 0, nw * 4, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_claims, 0, nw * static_cast<size_t>(lat.padded_size) * 8, stream));
+  // SimulatedAnnealing constructor (mc/src/SimulatedAnnealing.cpp:53-56; ratios mc/include/SimulatedAnnealing.h:45-57)
+  SaSchedule sa{};
+  sa.enabled = sa_maximum_steps > 0 ? 1 : 0;
+  sa.temperature = sa_initial_temperature;
+  sa.maximum_steps = sa_maximum_steps;
+  sa.reheat_trigger_steps = std::max<unsigned long long>(1ULL, static_cast<unsigned long long>(static_cast<double>(sa_maximum_steps) * 0.05));
+  sa.reheat_cooldown_steps = std::max<unsigned long long>(1ULL, static_cast<unsigned long long>(static_cast<double>(sa_maximum_steps) * 0.10));
+  sa.window_size = std::max<unsigned long long>(1ULL, static_cast<unsigned long long>(static_cast<double>(sa_maximum_steps) * 0.001));
+  std::vector<SaSchedule> all(nw, sa);
+  LMC_CUDA(cudaMemcpyAsync(d_cmc_sa, all.data(), nw * sizeof(SaSchedule), cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  cmc_ready = true;
+}
+
+void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t replay_walker, int64_t n_replay, const int64_t *a,
+                     const int64_t *b, const double *u, double *dE, double *energy_before, double *temperature_before,
+                     uint8_t *accepted) {
+  require_device();
+  require_coefficients();
+  if (!cmc_ready) cmc_reset(0.0, 0);
+  const size_t nw = static_cast<size_t>(n_walkers);
+  std::vector<double> temps(nw, params.temperature);
+  if (params.temperatures) std::copy(params.temperatures, params.temperatures + nw, temps.begin());
+  LMC_CUDA(cudaMemcpyAsync(d_cmc_temperature, temps.data(), nw * 8, cudaMemcpyHostToDevice, stream));
+  int threads = params.batch_size;
+  if (threads <= 0) {
+    // the number of mutually non-interfering survivors peaks near N / (2 * 43 * 2) proposals per batch
+    threads = 32;
+    while (threads < kCmcMaxThreads && threads * 172 < lat.num_sites) threads *= 2;
+  }
+  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..1024");
+  CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
+  CmcReplay rp{};
+  const bool replaying = n_replay > 0;
+  unsigned long long target = 0;
+  int first_walker = 0, n_run = n_walkers;
+  if (replaying) {
+    if (replay_walker < 0 || replay_walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+    if (!a || !b || !u) throw std::invalid_argument("replay needs site_a, site_b and u");
+    const size_t n = static_cast<size_t>(n_replay);
+    char *d = static_cast<char *>(scratch(n * (8 + 8 + 8 + 8 + 8 + 8 + 1) + 64));
+    int64_t *d_a = reinterpret_cast<int64_t *>(d), *d_b = d_a + n;
+    double *d_u = reinterpret_cast<double *>(d_b + n), *d_de = d_u + n, *d_eb = d_de + n, *d_tb = d_eb + n;
+    uint8_t *d_acc = reinterpret_cast<uint8_t *>(d_tb + n);
+    LMC_CUDA(cudaMemcpyAsync(d_a, a, n * 8, cudaMemcpyHostToDevice, stream));
+    LMC_CUDA(cudaMemcpyAsync(d_b, b, n * 8, cudaMemcpyHostToDevice, stream));
+    LMC_CUDA(cudaMemcpyAsync(d_u, u, n * 8, cudaMemcpyHostToDevice, stream));
+    rp = CmcReplay{d_a, d_b, d_u, d_de, d_eb, d_tb, d_acc};
+    first_walker = replay_walker;
+    n_run = 1;
+    threads = std::min(threads, 256);
+  } else {
+    if (n_trials <= 0) return;
+    std::vector<unsigned long long> steps(nw);
+    LMC_CUDA(cudaMemcpyAsync(steps.data(), d_cmc_steps, nw * 8, cudaMemcpyDeviceToHost, stream));
+    LMC_CUDA(cudaStreamSynchronize(stream));
+    unsigned long long lo = steps[0];
+    for (auto s : steps) lo = std::min(lo, s);
+    target = lo + static_cast<unsigned long long>(n_trials);
+  }
+  // per-replica pointers are offset on the host for the single-replica replay launch
+  CmcState st_run = st;
+  if (replaying) {
+    st_run.energy += first_walker; st_run.steps += first_walker; st_run.accepted += first_walker; st_run.proposals += first_walker;
+    st_run.epoch += first_walker; st_run.sa += first_walker; st_run.error += first_walker;
+  }
+  time_begin();
+  cmc_run_kernel<<<static_cast<unsigned>(n_run), threads, static_cast<size_t>(threads) * sizeof(double), stream>>>(
+      lat, tab, d_occ + static_cast<int64_t>(first_walker) * lat.padded_size, lat.padded_size,
+      d_cmc_claims + static_cast<size_t>(first_walker) * lat.padded_size, st_run, d_cmc_temperature + first_walker, params.seed, target, rp,
+      static_cast<unsigned long long>(std::max<int64_t>(0, n_replay)));
+  time_end();
+  LMC_CUDA(cudaGetLastError());
+  if (replaying) {
+    const size_t n = static_cast<size_t>(n_replay);
+    if (dE) LMC_CUDA(cudaMemcpyAsync(dE, rp.dE, n * 8, cudaMemcpyDeviceToHost, stream));
+    if (energy_before) LMC_CUDA(cudaMemcpyAsync(energy_before, rp.energy_before, n * 8, cudaMemcpyDeviceToHost, stream));
+    if (temperature_before) LMC_CUDA(cudaMemcpyAsync(temperature_before, rp.temperature_before, n * 8, cudaMemcpyDeviceToHost, stream));
+    if (accepted) LMC_CUDA(cudaMemcpyAsync(accepted, rp.accepted, n, cudaMemcpyDeviceToHost, stream));
+  }
+  std::vector<int32_t> err(nw);
+  LMC_CUDA(cudaMemcpyAsync(err.data(), d_cmc_error, nw * 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  for (size_t w = 0; w < nw; ++w)
+    if (err[w]) {
+      cmc_ready = false;
+      if (err[w] & kErrBadSite) throw std::invalid_argument("CMC replica " + std::to_string(w) + ": lattice id out of range in the trial stream");
+      throw std::out_of_range("CMC replica " + std::to_string(w) + ": Cluster not found in ClusterIndexer (two vacancies within interaction range)");
+    }
+}
+
+void Engine::cmc_get_state(double *energy, int64_t *steps, int64_t *accepted, double *temperature) {
+  require_device();
+  if (!d_cmc_energy) throw std::invalid_argument("lmc_cmc_reset has not been called");
+  const size_t nw = static_cast<size_t>(n_walkers);
+  if (energy) LMC_CUDA(cudaMemcpyAsync(energy, d_cmc_energy, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (steps) LMC_CUDA(cudaMemcpyAsync(steps, d_cmc_steps, nw * 8, cudaMemcpyDeviceToHost, stream));
+  if (accepted) LMC_CUDA(cudaMemcpyAsync(accepted, d_cmc_accepted, nw * 8, cudaMemcpyDeviceToHost, stream));
+  std::vector<SaSchedule> sa(nw);
+  std::vector<double> temps(nw);
+  if (temperature) {
+    LMC_CUDA(cudaMemcpyAsync(sa.data(), d_cmc_sa, nw * sizeof(SaSchedule), cudaMemcpyDeviceToHost, stream));
+    LMC_CUDA(cudaMemcpyAsync(temps.data(), d_cmc_temperature, nw * 8, cudaMemcpyDeviceToHost, stream));
+  }
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  if (temperature)
+    for (size_t w = 0; w < nw; ++w) temperature[w] = sa[w].enabled ? sa[w].temperature : temps[w];
+}
+
 // ------------------------------------------------------------------------------------------------ host geometry
 int64_t Engine::wrapped_id(int x, int y, int z) const {
   auto w = [](int v, int p) { v %= p; return v < 0 ? v + p : v; };
@@ -799,6 +931,27 @@ int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_step
 }
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {
   return guard([&] { engine->impl->kmc_get_state(time, energy, steps, vacancy, temperature); });
+}
+int lmc_cmc_reset(lmc_engine *engine, double sa_initial_temperature, uint64_t sa_maximum_steps) {
+  return guard([&] { engine->impl->cmc_reset(sa_initial_temperature, sa_maximum_steps); });
+}
+int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    engine->impl->cmc_run(*params, n_trials, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+  });
+}
+int lmc_cmc_replay(lmc_engine *engine, int32_t walker, const lmc_cmc_params *params, int64_t n, const int64_t *site_a,
+                   const int64_t *site_b, const double *u, double *dE, double *energy_before, double *temperature_before,
+                   uint8_t *accepted) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    if (n <= 0) return;
+    engine->impl->cmc_run(*params, 0, walker, n, site_a, site_b, u, dE, energy_before, temperature_before, accepted);
+  });
+}
+int lmc_cmc_get_state(lmc_engine *engine, double *energy, int64_t *steps, int64_t *accepted, double *temperature) {
+  return guard([&] { engine->impl->cmc_get_state(energy, steps, accepted, temperature); });
 }
 int lmc_debug_pair(lmc_engine *engine, int32_t walker, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,
                    int64_t *mm2_58, int64_t *mm2_backward58, int32_t *start_counts, int32_t *end_counts, int32_t *enc_mmm,

@@ -14,6 +14,7 @@
 
 struct lmc_kmc_params;
 struct lmc_kmc_trace;
+struct lmc_cmc_params;
 
 namespace lmc {
 
@@ -49,6 +50,11 @@ class Engine {
   void kmc_reset();
   void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace);
   void kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature);
+
+  void cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps);
+  void cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t replay_walker, int64_t n_replay, const int64_t *a,
+               const int64_t *b, const double *u, double *dE, double *energy_before, double *temperature_before, uint8_t *accepted);
+  void cmc_get_state(double *energy, int64_t *steps, int64_t *accepted, double *temperature);
 
   // host-side geometry (no device needed)
   void neighbors(int32_t shell, int64_t site, int64_t *out) const;
@@ -92,6 +98,13 @@ class Engine {
   double *d_kmc_time{nullptr}, *d_kmc_energy{nullptr}, *d_kmc_temperature{nullptr}, *d_kmc_cvac{nullptr}, *d_kmc_csol{nullptr};
   int32_t *d_kmc_error{nullptr};
   bool kmc_ready{false};
+  // CMC / SA per-replica state (device)
+  double *d_cmc_energy{nullptr};
+  unsigned long long *d_cmc_steps{nullptr}, *d_cmc_accepted{nullptr}, *d_cmc_proposals{nullptr}, *d_cmc_epoch{nullptr}, *d_cmc_claims{nullptr};
+  void *d_cmc_sa{nullptr};
+  int32_t *d_cmc_error{nullptr};
+  double *d_cmc_temperature{nullptr};
+  bool cmc_ready{false};
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
   cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
   bool timing_pending{false};
