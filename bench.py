@@ -288,6 +288,8 @@ def run_ours(args):
         line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(js)
+        if not args.no_cmc:
+            line["cmc"] = bench_cmc(torch, local_rank, js, peak, n_gpus == 1 and not args.no_cpu_baseline)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -325,6 +327,72 @@ def bench_barrier_eval(engine, torch, W, peak):
             "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item())}
 
 
+def bench_cmc(torch, device, json_path, peak, with_cpu):
+    """Secondary metric: CMC swap trials/s.  (a) BASELINE configs[1]: one 40x40x40 (256k sites) Al-2%Mg-2%Zn lattice at
+    800 K, batches of mutually non-interfering trials in ONE persistent kernel launch per step; (b) the same driver over
+    148 independent replicas (one thread block each) -- temperatures shard with no communication."""
+    from latticemontecarlo_b200 import capi, synth
+    out = {"metric": "cmc_swap_trials_per_s", "unit": "trials/s", "bytes_per_trial": BYTES_PER_TRIAL}
+    for name, f, replicas, trials in (("single_lattice_40x40x40", 40, 1, 200000), ("replicas_148x_20x20x20", 20, 148, 20000)):
+        eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=replicas, device=device)
+        eng.load_coefficients(json_path)
+        occ = np.stack([synth.random_alloy(f, P_MG, P_ZN, seed=1000 + r, vacancy_site=None) for r in range(replicas)])
+        pinned = torch.empty(occ.shape, dtype=torch.uint8, pin_memory=True)
+        pinned.numpy()[:] = occ
+        temps = np.linspace(600.0, 1000.0, replicas) if replicas > 1 else np.array([800.0])
+        eng.set_occupancy_all(pinned.numpy())
+        eng.cmc_reset()
+        eng.cmc_run(trials // 4, temperatures=temps, seed=5)          # warm-up
+        kernel_ms, done = [], []
+        for _ in range(5):
+            s0 = eng.cmc_state()["steps"].sum()
+            eng.cmc_run(trials, temperatures=temps, seed=5)
+            kernel_ms.append(eng.last_kernel_ms())
+            done.append(int(eng.cmc_state()["steps"].sum() - s0))
+        rate = sum(done) / (sum(kernel_ms) * 1e-3)
+        t0 = time.perf_counter()
+        n_e2e = 0
+        for _ in range(3):
+            eng.set_occupancy_all(pinned.numpy())
+            eng.cmc_reset()
+            eng.cmc_run(trials, temperatures=temps, seed=5)
+            st = eng.cmc_state()
+            eng.get_occupancy_all()
+            n_e2e += int(st["steps"].sum())
+        e2e = n_e2e / (time.perf_counter() - t0)
+        achieved = rate * BYTES_PER_TRIAL / 1e9
+        out[name] = {"value": rate, "e2e": e2e, "replicas": replicas, "sites": 4 * f ** 3, "trials_per_launch": int(np.mean(done)),
+                     "kernel_ms": float(np.mean(kernel_ms)), "accept_ratio": float(st["accepted"].sum() / max(1, st["steps"].sum())),
+                     "roofline": {"kernel": "cmc_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                                  "frac": achieved / peak, "traffic": None}}
+        eng.close()
+    out["value"] = out["single_lattice_40x40x40"]["value"]
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline_cmc(json_path)
+    return out
+
+
+def cpu_baseline_cmc(json_path):
+    """mc::CanonicalMcOmp (batch = OMP thread count) on this box's host cores.  The per-trial cost does not depend on the
+    lattice size, so the sample uses a 20x20x20 cell (the reference's per-site tables for 256k sites take minutes to build)."""
+    try:
+        from oracle import ref_lib as R
+        from latticemontecarlo_b200 import synth
+        if not R.build():
+            return {"value": None, "unit": "trials/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref unavailable"}
+        cores = host_cores()
+        f = 20
+        occ = synth.random_alloy(f, P_MG, P_ZN, seed=1000, vacancy_site=None)
+        cfg = R.RefConfig.fcc(f, occ, reassign=False)
+        steps = 40000
+        res = R.cmc_omp(cfg, json_path, temperature=800.0, maximum_steps=steps, seed=3, threads=cores)
+        return {"value": res["steps"] / res["seconds"], "unit": "trials/s", "cores": cores, "kind": "reference",
+                "sample": "mc::CanonicalMcOmp, %d OMP threads, %d trials on a 20x20x20 Al-2%%Mg-2%%Zn cell at 800 K (%.1f s in Simulate())"
+                          % (cores, res["steps"], res["seconds"])}
+    except Exception as exc:
+        return {"value": None, "unit": "trials/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+
+
 def cpu_baseline(json_path):
     """The reference's own KMC driver on this box's host cores, bounded sample (about 10-20 s of CPU work)."""
     try:
@@ -351,6 +419,7 @@ def main():
     ap.add_argument("--hops", type=int, default=512, help="KMC steps per walker per bench step")
     ap.add_argument("--ref-hops", type=int, default=4000, help="reference arm: hops per trajectory per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cmc", action="store_true", help="skip the secondary CMC measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

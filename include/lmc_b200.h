@@ -164,7 +164,7 @@ typedef struct lmc_cmc_params {
   double temperature;              /* `temperature` (CMC) */
   const double *temperatures;      /* optional per-replica temperatures [n_walkers] */
   uint64_t seed;                   /* Philox4x32-10 key */
-  int32_t batch_size;              /* proposals per batch (power of two, 32..1024); 0 = chosen from the lattice size */
+  int32_t batch_size;              /* proposals per batch (power of two, 32..512); 0 = chosen from the lattice size */
 } lmc_cmc_params;
 
 /* reset steps / energy / counters of every replica; with sa_maximum_steps > 0 the SimulatedAnnealing schedule is armed:

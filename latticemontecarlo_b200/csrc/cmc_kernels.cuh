@@ -4,13 +4,14 @@
 // order), mc/src/CanonicalMcSerial.cpp:40-51, mc/src/SimulatedAnnealing.cpp:99-185 (schedule).
 //
 // One thread block owns one replica ("walker") for the whole launch and loops over batches:
-//   phase 1  every thread proposes one swap trial (two uniform lattice ids; Philox4x32-10, counter = trial number) and
-//            claims the 43-site neighbourhoods of both sites in a per-replica claim array (64-bit atomicMax of a
-//            tag = batch epoch | priority); this is CanonicalMcOmp's `unavailable_position_` set, built in parallel;
-//   phase 2  a trial survives if no higher-priority trial of the batch claimed one of its two sites (so no surviving
-//            trial reads a site another surviving trial may write: dE evaluated on the batch-start occupancy is the
-//            dE the serial chain would see); survivors evaluate dE (swap_energy_change), draw the Metropolis uniform,
-//            and apply their swap immediately.
+//   phase 1  every thread draws a few proposals (two uniform lattice ids each; Philox4x32-10) and keeps the first
+//            unlike-species pair; the live trials are compacted to the low thread ids (dense warps) and each marks its
+//            two sites in a per-replica mark array (atomicMax of epoch | priority);
+//   phase 2  each live trial gathers the 43-site neighbourhoods of its two sites -- species for dE and marks for the
+//            conflict test in the same pass.  A trial survives if no higher-priority trial of the batch marked a site
+//            of its neighbourhoods; this is CanonicalMcOmp's `unavailable_position_` rule evaluated in parallel.  No
+//            surviving trial reads a site another survivor may write, so dE evaluated on the batch-start occupancy is
+//            the dE the serial chain would see; survivors draw the Metropolis uniform and apply their swap at once.
 // Proposals whose two sites hold the same species, and proposals that lose the claim, are not trials (the reference
 // redraws them: CanonicalMcAbstract.cpp:45-50, CanonicalMcOmp.cpp:47-58), so they do not advance `steps`.
 //
@@ -19,9 +20,12 @@
 // energy and the annealing schedule are then applied strictly in order by one thread -- this reproduces
 // CanonicalMcSerial / SimulatedAnnealing traces exactly.
 #pragma once
+#include <cstdio>
+#include <cooperative_groups.h>
 #include "kmc_kernels.cuh"
 
 namespace lmc {
+namespace cg = cooperative_groups;
 
 struct SaSchedule {             // SimulatedAnnealing members (mc/include/SimulatedAnnealing.h:33-68)
   double temperature;
@@ -79,20 +83,12 @@ __device__ __forceinline__ void sa_update(SaSchedule &s, bool accepted, double e
   s.temperature *= cool_factor;
 }
 
-__device__ __forceinline__ uint64_t mul_hi_u64(uint64_t x, uint64_t n) { return __umul64hi(x, n); }
-
-// claim the 43-site neighbourhood of a site (cells addressed as base + offset row, i.e. possibly halo images)
-__device__ __forceinline__ void claim_site(unsigned long long *claim, int64_t base, const int32_t *__restrict__ drow, unsigned long long tag) {
-#pragma unroll 1
-  for (int t = 0; t < 43; ++t) atomicMax(claim + base + drow[t], tag);
-}
-
-// highest tag found on any periodic image of the site (interior cell + halo images)
-__device__ __forceinline__ unsigned long long strongest_claim(const LatticeDesc &lat, const unsigned long long *claim, int X, int Y, int Z) {
+// write a claim mark on a site and all its periodic halo images (the checkers read marks through base + offset)
+__device__ __forceinline__ void mark_site(const LatticeDesc &lat, unsigned int *marks, int X, int Y, int Z, unsigned int mark) {
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
-  unsigned long long best = claim[lat.padded_index(X, Y, Z)];
+  atomicMax(marks + lat.padded_index(X, Y, Z), mark);
   const bool edge = X < kHalo || X >= px - kHalo || Y < kHalo || Y >= py - kHalo || Z < kHaloZ || Z >= pz - kHaloZ;
-  if (!edge) return best;
+  if (!edge) return;
   for (int a = -1; a <= 1; ++a) {
     const int x = X + a * px;
     if (x < -kHalo || x >= px + kHalo) continue;
@@ -102,139 +98,359 @@ __device__ __forceinline__ unsigned long long strongest_claim(const LatticeDesc 
       for (int c = -1; c <= 1; ++c) {
         const int z = Z + c * pz;
         if (z < -kHaloZ || z >= pz + kHaloZ) continue;
-        const unsigned long long v = claim[lat.padded_index(x, y, z)];
-        best = v > best ? v : best;
+        if (a | b | c) atomicMax(marks + lat.padded_index(x, y, z), mark);
       }
     }
   }
-  return best;
 }
 
-constexpr int kCmcMaxThreads = 1024;
+// Tables of the single-site energy model staged in shared memory (a CMC replica is one thread block with few warps,
+// so the dependent table walk must not pay global-memory latency).  B stays in global memory if it does not fit.
+struct SiteTablesView {
+  const double *A, *B, *C;        // [x][42][m], [x][204][m][m], [x]
+  const uint64_t *mask_hi;        // [42]
+  const uint16_t *base;           // [42]
+  int m, n_pairs;
+};
+
+// 43-site gather of species AND claim marks.  Species codes are staged in shared memory (codes[t * stride], one
+// column per thread) for the table walk; returns the solute mask; *conflict is set if any site of the neighbourhood
+// carries a mark of this epoch with higher priority than `my_mark` (CanonicalMcOmp.cpp:47-72: a trial may not touch
+// the neighbourhood of an earlier trial of the batch).
+__device__ __forceinline__ uint64_t gather_site_env_marked(const uint8_t *occ, const unsigned int *marks, int64_t base,
+                                                           const int32_t *__restrict__ drow, unsigned solvent, uint8_t *codes, int stride,
+                                                           int64_t override_index, unsigned override_code, unsigned my_mark,
+                                                           bool *conflict) {
+  uint32_t lo = 0, hi = 0;
+  unsigned worst = 0;
+  // chunks of 11/11/11/10 sites: enough loads in flight to cover the latency, few enough live registers not to spill
+#pragma unroll
+  for (int t0 = 0; t0 < 43; t0 += 11) {
+    unsigned cd[11], mk[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) {
+      if (t0 + q >= 43) continue;
+      cd[q] = __ldcg(occ + base + drow[t0 + q]);         // the lattice is shared by the CTAs of a cluster: read at L2
+      mk[q] = __ldcg(marks + base + drow[t0 + q]);   // marks are written with atomics by other threads: bypass L1
+    }
+#pragma unroll
+    for (int q = 0; q < 11; ++q) {
+      const int t = t0 + q;
+      if (t >= 43) continue;
+      worst = mk[q] > worst ? mk[q] : worst;
+      unsigned c = cd[q];
+      if (base + drow[t] == override_index) c = override_code;
+      codes[t * stride] = static_cast<uint8_t>(c);
+      if (t == kCentrePos) continue;
+      const int e = t - (t > kCentrePos);
+      if (e < 32) lo |= (c != solvent) ? (1u << e) : 0u;
+      else hi |= (c != solvent) ? (1u << (e - 32)) : 0u;
+    }
+  }
+  // marks of older epochs are numerically smaller than any mark of the current epoch
+  if (worst > my_mark) *conflict = true;
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// H(x_new, env) - H(x_old, env) from staged codes and (shared-memory) tables
+__device__ __forceinline__ double site_energy_change_staged(const SiteTablesView &tv, int x_old, int x_new, uint64_t sol,
+                                                            const uint8_t *codes, int stride) {
+  const int m = tv.m;
+  const size_t a_stride = static_cast<size_t>(kSiteEnvN) * m, b_stride = static_cast<size_t>(tv.n_pairs) * m * m;
+  const double *A_new = tv.A + x_new * a_stride, *A_old = tv.A + x_old * a_stride;
+  const double *B_new = tv.B + x_new * b_stride, *B_old = tv.B + x_old * b_stride;
+  double acc = tv.C[x_new] - tv.C[x_old];
+  while (sol) {
+    const int t = __ffsll(static_cast<long long>(sol)) - 1;
+    sol &= sol - 1;
+    const int et = codes[(t + (t >= kCentrePos)) * stride];
+    acc += A_new[t * m + et] - A_old[t * m + et];
+    const uint64_t hi = tv.mask_hi[t];
+    uint64_t partners = hi & sol;
+    const int pbase = tv.base[t];
+    while (partners) {
+      const int u = __ffsll(static_cast<long long>(partners)) - 1;
+      partners &= partners - 1;
+      const int eu = codes[(u + (u >= kCentrePos)) * stride];
+      const size_t p = (static_cast<size_t>(pbase + __popcll(hi & ((1ULL << u) - 1ULL))) * m + et) * m + eu;
+      acc += B_new[p] - B_old[p];
+    }
+  }
+  return acc;
+}
+
+// swap_energy_change (kernels.cuh) with the claim check fused into its two gathers
+__device__ __forceinline__ double swap_energy_change_marked(const LatticeDesc &lat, const DevTables &tab, const SiteTablesView &tv,
+                                                            const uint8_t *occ, const unsigned int *marks,
+                                                            const int32_t *__restrict__ s_delta, uint8_t *codes, int stride, int xa,
+                                                            int ya, int za, int xb, int yb, int zb, unsigned my_mark,
+                                                            bool *conflict) {
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
+  int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
+  unsigned ea = __ldcg(occ + base_a), eb = __ldcg(occ + base_b);
+  int dx = xb - xa, dy = yb - ya, dz = zb - za;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
+  dy = dy > py / 2 ? dy - py : (dy < -py / 2 ? dy + py : dy);
+  dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
+  const bool coupled = dx * dx + dy * dy + dz * dz <= 6;
+  int zpa = za & 1, zpb = zb & 1;
+  if (coupled && eb == vac) {   // move the vacancy first so that no intermediate state holds two vacancies
+    const int64_t tb = base_a; base_a = base_b; base_b = tb;
+    const unsigned te = ea; ea = eb; eb = te;
+    const int tz = zpa; zpa = zpb; zpb = tz;
+    dx = -dx; dy = -dy; dz = -dz;
+  }
+  const int32_t *row_a = s_delta + zpa * 43, *row_b = s_delta + zpb * 43;
+  uint8_t *codes_b = codes + 43 * stride;
+  const uint64_t sol_a = gather_site_env_marked(occ, marks, base_a, row_a, solvent, codes, stride, -1, 0, my_mark, conflict);
+  const int64_t override_index = coupled ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
+  const uint64_t sol_b = gather_site_env_marked(occ, marks, base_b, row_b, solvent, codes_b, stride, override_index, eb, my_mark, conflict);
+  if (*conflict || ea == eb) return 0.0;
+  return site_energy_change_staged(tv, static_cast<int>(ea), static_cast<int>(eb), sol_a, codes, stride) +
+         site_energy_change_staged(tv, static_cast<int>(eb), static_cast<int>(ea), sol_b, codes_b, stride);
+}
+
+constexpr int kCmcMaxThreads = 512;
+constexpr int kCmcDraws = 8;          // proposals drawn per thread and batch; the first unlike-species pair is the thread's trial
+
+// species by lattice id (compact codes): lets a proposal test "same species?" with two byte loads
+__global__ void cmc_mirror_kernel(LatticeDesc lat, const uint8_t *__restrict__ padded, uint8_t *__restrict__ by_id) {
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (id >= lat.num_sites) return;
+  by_id[blockIdx.y * lat.num_sites + id] = padded[blockIdx.y * lat.padded_size + lat.padded_index_of_id(id)];
+}
+
+// One thread-block CLUSTER per replica: the CTAs of the cluster share the batch (proposals, marks, evaluation) so that the
+// scattered 43-site gathers of a batch are spread over several SMs' L1/LSU pipes; batch bookkeeping is replicated in every
+// CTA and kept identical by exchanging per-CTA partial sums through distributed shared memory after each batch.
+struct CmcPartial {
+  double sum;
+  unsigned int kept, accepted, live, first_conflict;
+  int err;
+};
 
 __global__ void __launch_bounds__(kCmcMaxThreads)
-cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, unsigned long long *claims, CmcState st,
-               const double *__restrict__ temperatures, uint64_t seed, unsigned long long target_steps, CmcReplay replay,
-               unsigned long long n_replay) {
+cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, uint8_t *mirror, unsigned int *marks_all,
+               CmcState st, const double *__restrict__ temperatures, uint64_t seed, unsigned long long target_steps, CmcReplay replay,
+               unsigned long long n_replay, int stage_b_table) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int n_cta = static_cast<int>(cluster.num_blocks()), rank = static_cast<int>(cluster.block_rank());
   __shared__ int32_t s_delta[2 * 43];
   __shared__ double s_warp_sum[kCmcMaxThreads / 32];
-  __shared__ unsigned int s_warp_cnt[kCmcMaxThreads / 32], s_warp_acc[kCmcMaxThreads / 32];
+  __shared__ unsigned int s_warp_cnt[kCmcMaxThreads / 32], s_warp_acc[kCmcMaxThreads / 32], s_warp_live[kCmcMaxThreads / 32];
   __shared__ unsigned int s_first_conflict;
+  __shared__ CmcPartial s_partial;
   __shared__ double s_energy, s_temperature;
   __shared__ unsigned long long s_steps, s_accepted, s_proposals, s_epoch, s_replay_pos;
   __shared__ SaSchedule s_sa;
-  extern __shared__ double s_replay_de[];          // replay mode: dE of the batch, blockDim.x doubles
+  __shared__ int32_t s_live_a[kCmcMaxThreads], s_live_b[kCmcMaxThreads];
+  extern __shared__ double s_dyn[];                // [replay dE: B*n_cta] [C: m] [A: m*42*m] [B: m*204*m*m, optional] [mask: 42] [base] [codes]
 
-  const int w = blockIdx.x;
+  const int w = blockIdx.x / n_cta;
   const int tid = threadIdx.x, B = blockDim.x;
   uint8_t *o = occ + w * walker_stride;
-  unsigned long long *claim = claims + static_cast<size_t>(w) * lat.padded_size;
+  uint8_t *by_id = mirror + static_cast<size_t>(w) * lat.num_sites;
+  unsigned int *marks = marks_all + static_cast<size_t>(w) * lat.padded_size;
   for (int q = tid; q < 2 * 43; q += B) s_delta[q] = tab.site_delta[q];
+  // ---- stage the site tables in shared memory
+  const int m = tab.n_species + 1;
+  double *s_replay_de = s_dyn;                      // rank 0 holds the dE of the whole replay window
+  double *s_C = s_replay_de + B * n_cta;
+  double *s_A = s_C + m;
+  const int a_len = m * kSiteEnvN * m, b_len = m * tab.n_site_pairs * m * m;
+  double *s_B = s_A + a_len;
+  uint64_t *s_mask = reinterpret_cast<uint64_t *>(s_B + (stage_b_table ? b_len : 0));
+  uint16_t *s_base = reinterpret_cast<uint16_t *>(s_mask + kSiteEnvN);
+  uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_base + 44);
+  for (int q = tid; q < m; q += B) s_C[q] = tab.site_C[q];
+  for (int q = tid; q < a_len; q += B) s_A[q] = tab.site_A[q];
+  if (stage_b_table)
+    for (int q = tid; q < b_len; q += B) s_B[q] = tab.site_B[q];
+  for (int q = tid; q < kSiteEnvN; q += B) { s_mask[q] = tab.site_mask_hi[q]; s_base[q] = tab.site_base[q]; }
+  const SiteTablesView tv{s_A, stage_b_table ? s_B : tab.site_B, s_C, s_mask, s_base, m, tab.n_site_pairs};
   if (tid == 0) {
     s_energy = st.energy[w]; s_steps = st.steps[w]; s_accepted = st.accepted[w]; s_proposals = st.proposals[w];
     s_epoch = st.epoch[w]; s_sa = st.sa[w]; s_replay_pos = 0;
     s_temperature = s_sa.enabled ? s_sa.temperature : temperatures[w];
   }
   __syncthreads();
+#ifdef LMC_CMC_PROFILE
+  __shared__ long long s_prof[8];
+  if (tid == 0) for (int q = 0; q < 8; ++q) s_prof[q] = 0;
+  long long t_prev = clock64();
+#define LMC_TICK(k) do { if (tid == 0) { const long long t_now = clock64(); s_prof[k] += t_now - t_prev; t_prev = t_now; } } while (0)
+#else
+#define LMC_TICK(k) do { } while (0)
+#endif
   const bool replaying = replay.a != nullptr;
-  const uint64_t n_sites = static_cast<uint64_t>(lat.num_sites);
+  const uint32_t n_sites = static_cast<uint32_t>(lat.num_sites);
   const double cool = s_sa.enabled ? exp(-3.0 / static_cast<double>(s_sa.maximum_steps > 0 ? s_sa.maximum_steps : 1ULL)) : 1.0;
+  const int gtid = rank * B + tid;                 // index of this thread within the replica's cluster
+  const int window = B * n_cta;                    // proposals (threads) per batch
   int err = 0;
 
   for (;;) {
-    // ---------------- batch bookkeeping (uniform across the block)
+    // ---------------- batch bookkeeping (identical in every CTA of the cluster)
     const unsigned long long steps0 = s_steps, epoch = s_epoch + 1, prop0 = s_proposals, rpos = s_replay_pos;
     const double t_batch = s_temperature, energy0 = s_energy;
     if (replaying ? (rpos >= n_replay) : (steps0 >= target_steps)) break;
     __syncthreads();
     if (tid == 0) s_first_conflict = 0xFFFFFFFFu;
-    // ---------------- phase 1: propose + claim
-    int64_t a = -1, b = -1;
-    uint32_t r[4] = {0, 0, 0, 0};
-    if (replaying) {
-      if (rpos + tid < n_replay) { a = replay.a[rpos + tid]; b = replay.b[rpos + tid]; }
-    } else {
-      const unsigned long long g = prop0 + tid;
-      philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(w),
-                    static_cast<uint32_t>(seed >> 32), r);
-      a = static_cast<int64_t>(mul_hi_u64((static_cast<uint64_t>(r[1]) << 32) | r[0], n_sites));
-      b = static_cast<int64_t>(mul_hi_u64((static_cast<uint64_t>(r[3]) << 32) | r[2], n_sites));
+    if ((epoch & 0xFFFFULL) == 0) {                 // 16-bit epoch wrapped: forget all marks
+      for (int64_t q = gtid; q < lat.padded_size; q += window) marks[q] = 0;
+      cluster.sync();
     }
-    bool live = a >= 0 && b >= 0 && a < lat.num_sites && b < lat.num_sites;
-    if (replaying && rpos + tid < n_replay && !live) err |= kErrBadSite;
+    const unsigned int epoch16 = static_cast<unsigned int>(epoch & 0xFFFFULL);
+    // ---------------- phase 1a: proposals (GenerateLatticeIdJumpPair: uniform ids, redrawn while the species are equal)
+    int32_t a = -1, b = -1;
+    if (replaying) {
+      // replay trials are dealt round-robin so that priorities (= positions in the stream) interleave over the CTAs
+      if (rpos + gtid < n_replay) {
+        const int64_t ra = replay.a[rpos + gtid], rb = replay.b[rpos + gtid];
+        if (ra < 0 || rb < 0 || ra >= lat.num_sites || rb >= lat.num_sites) err |= kErrBadSite;
+        else { a = static_cast<int32_t>(ra); b = static_cast<int32_t>(rb); }
+      }
+    } else {
+      uint32_t ida[kCmcDraws], idb[kCmcDraws];
+      uint8_t sa_[kCmcDraws], sb_[kCmcDraws];
+#pragma unroll
+      for (int d = 0; d < kCmcDraws; d += 2) {
+        uint32_t r[4];
+        const unsigned long long g = (prop0 + gtid) * (kCmcDraws / 2) + (d >> 1);
+        philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(w),
+                      static_cast<uint32_t>(seed >> 32), r);
+        ida[d] = __umulhi(r[0], n_sites); idb[d] = __umulhi(r[1], n_sites);
+        ida[d + 1] = __umulhi(r[2], n_sites); idb[d + 1] = __umulhi(r[3], n_sites);
+      }
+#pragma unroll
+      for (int d = 0; d < kCmcDraws; ++d) { sa_[d] = __ldcg(by_id + ida[d]); sb_[d] = __ldcg(by_id + idb[d]); }
+#pragma unroll
+      for (int d = kCmcDraws - 1; d >= 0; --d)
+        if (sa_[d] != sb_[d]) { a = static_cast<int32_t>(ida[d]); b = static_cast<int32_t>(idb[d]); }
+    }
+    LMC_TICK(0);
+    // ---------------- compaction of this CTA's live trials (deterministic: ballot + prefix over warps)
+    const bool has = a >= 0;
+    int n_live = 0, slot = -1;
+    if (replaying) {                                // keep stream order: no compaction, priority = stream position
+      n_live = B;
+      slot = tid;
+      s_live_a[tid] = a;
+      s_live_b[tid] = b;
+    } else {
+      const unsigned bal = __ballot_sync(0xffffffffu, has);
+      if ((tid & 31) == 0) s_warp_live[tid >> 5] = __popc(bal);
+      __syncthreads();
+      int my_off = 0;
+      for (int q = 0; q < (B + 31) / 32; ++q) {
+        if (q == (tid >> 5)) my_off = n_live;
+        n_live += s_warp_live[q];
+      }
+      if (has) {
+        slot = my_off + __popc(bal & ((1u << (tid & 31)) - 1u));
+        s_live_a[slot] = a;
+        s_live_b[slot] = b;
+      }
+    }
+    __syncthreads();
+    LMC_TICK(1);
+    // ---------------- phase 1b: thread i < n_live owns live trial i of this CTA; mark its two sites.
+    // priority: device RNG: (CTA rank, slot); replay: position in the stream
+    bool live = tid < n_live;
     int xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
-    int64_t base_a = 0, base_b = 0;
-    const unsigned long long tag = (epoch << 16) | static_cast<unsigned long long>(0xFFFF - tid);
+    const unsigned int prio = replaying ? static_cast<unsigned int>(gtid) : static_cast<unsigned int>(rank * B + tid);
+    const unsigned int my_mark = (epoch16 << 16) | (0xFFFFu - prio);
+    if (live) {
+      a = s_live_a[tid]; b = s_live_b[tid];
+      live = a >= 0;
+    }
     if (live) {
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
-      base_a = lat.padded_index(xa, ya, za);
-      base_b = lat.padded_index(xb, yb, zb);
-      if (!replaying && o[base_a] == o[base_b]) live = false;      // same species: not a trial (redrawn by the reference)
+      mark_site(lat, marks, xa, ya, za, my_mark);
+      mark_site(lat, marks, xb, yb, zb, my_mark);
     }
-    if (live) {
-      claim_site(claim, base_a, s_delta + (za & 1) * 43, tag);
-      claim_site(claim, base_b, s_delta + (zb & 1) * 43, tag);
-    }
-    __syncthreads();
-    // ---------------- phase 2: survivors
-    bool kept = false;
-    if (live) {
-      const unsigned long long ca = strongest_claim(lat, claim, xa, ya, za), cb = strongest_claim(lat, claim, xb, yb, zb);
-      kept = ca <= tag && cb <= tag;       // tags of this epoch from lower thread ids are larger; stale epochs are smaller
-      if (!kept && replaying) atomicMin(&s_first_conflict, static_cast<unsigned int>(tid));
-    }
-    __syncthreads();
-    if (replaying) {
-      // serial semantics: only the conflict-free prefix of the pending trials forms the batch
-      const unsigned int limit = s_first_conflict;
-      kept = live && static_cast<unsigned int>(tid) < limit;
-    }
+    cluster.sync();
+    LMC_TICK(2);
+    // ---------------- phase 2: conflict check fused with the dE gathers
+    bool conflict = false;
     double de = 0.0;
+    if (live) de = swap_energy_change_marked(lat, tab, tv, o, marks, s_delta, s_codes + tid, B, xa, ya, za, xb, yb, zb, my_mark, &conflict);
+    bool kept = live && !conflict;
+    LMC_TICK(3);
+    if (replaying) {
+      // serial semantics: only the conflict-free prefix of the window forms the batch; every CTA learns the position of
+      // the first conflict through distributed shared memory
+      if (live && conflict) atomicMin(&s_first_conflict, static_cast<unsigned int>(gtid));
+      __syncthreads();
+      if (tid == 0) s_partial.first_conflict = s_first_conflict;
+      cluster.sync();
+      unsigned int limit = 0xFFFFFFFFu;
+      for (int r = 0; r < n_cta; ++r) {
+        const unsigned int v = cluster.map_shared_rank(&s_partial, r)->first_conflict;
+        limit = v < limit ? v : limit;
+      }
+      kept = live && static_cast<unsigned int>(gtid) < limit;
+      if (kept) cluster.map_shared_rank(s_replay_de, 0)[gtid] = de;      // rank 0 applies the prefix serially
+      if (tid == 0) s_first_conflict = limit;
+    }
+    if (kept && de != de) err |= kErrExtraVacancy;
     bool accept = false;
-    if (kept) {
-      de = swap_energy_change(lat, tab, o, s_delta, xa, ya, za, xb, yb, zb, &err);
-      if (!replaying) {
-        // CanonicalMcAbstract::SelectEvent (:86-101): dE < 0 accepts, else u < exp(-dE beta); SA uses the temperature
-        // the trial would see after the geometric cooling of the trials before it in this batch
-        accept = de < 0.0;
-        if (!accept) {
-          uint32_t r2[4];
-          const unsigned long long g = prop0 + tid;
-          philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(w),
-                        static_cast<uint32_t>(seed >> 32) ^ 0x9E3779B9u, r2);
-          const double u = uniform53(r2[0], r2[1]);
-          const double beta = 1.0 / kBoltzmannEv / fmax(t_batch, 1e-12);
-          accept = u < exp(-de * beta);
-        }
-        if (accept) {
-          const uint8_t ea = o[base_a], eb = o[base_b];
-          store_site(lat, o, xa, ya, za, eb);
-          store_site(lat, o, xb, yb, zb, ea);
-        }
-      } else {
-        s_replay_de[tid] = de;
+    if (kept && !replaying) {
+      // CanonicalMcAbstract::SelectEvent (:86-101): dE < 0 accepts, else u < exp(-dE beta)
+      accept = de < 0.0;
+      if (!accept) {
+        uint32_t r2[4];
+        const unsigned long long g = prop0 + gtid;
+        philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(w),
+                      static_cast<uint32_t>(seed >> 32) ^ 0x9E3779B9u, r2);
+        const double beta = 1.0 / kBoltzmannEv / fmax(t_batch, 1e-12);
+        accept = uniform53(r2[0], r2[1]) < exp(-de * beta);
+      }
+      if (accept) {
+        const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
+        const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
+        store_site(lat, o, xa, ya, za, eb);
+        store_site(lat, o, xb, yb, zb, ea);
+        by_id[a] = eb;
+        by_id[b] = ea;
       }
     }
+    LMC_TICK(4);
     // ---------------- reductions (fixed order: deterministic)
     const unsigned kept_mask = __ballot_sync(0xffffffffu, kept), acc_mask = __ballot_sync(0xffffffffu, accept);
     double sum = accept ? de : 0.0;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
     if ((tid & 31) == 0) { s_warp_sum[tid >> 5] = sum; s_warp_cnt[tid >> 5] = __popc(kept_mask); s_warp_acc[tid >> 5] = __popc(acc_mask); }
-    __syncthreads();
+    const int block_err = __syncthreads_or(err != 0);
+    if (tid == 0) {
+      double e = 0.0;
+      unsigned int n_kept = 0, n_acc = 0;
+      for (int q = 0; q < (B + 31) / 32; ++q) { e += s_warp_sum[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
+      s_partial.sum = e; s_partial.kept = n_kept; s_partial.accepted = n_acc; s_partial.live = static_cast<unsigned int>(n_live);
+      s_partial.err = block_err;
+    }
+    cluster.sync();
+    int any_err = 0;
+    for (int r = 0; r < n_cta; ++r) any_err |= cluster.map_shared_rank(&s_partial, r)->err;   // uniform over the cluster
     if (tid == 0) {
       if (!replaying) {
         double e = 0.0;
         unsigned int n_kept = 0, n_acc = 0;
-        for (int q = 0; q < (B + 31) / 32; ++q) { e += s_warp_sum[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
+        for (int r = 0; r < n_cta; ++r) {                                  // rank order: every CTA computes the same totals
+          const CmcPartial *pp = cluster.map_shared_rank(&s_partial, r);
+          e += pp->sum; n_kept += pp->kept; n_acc += pp->accepted;
+        }
         s_energy = energy0 + e;
         s_steps = steps0 + n_kept;
         s_accepted += n_acc;
-        s_proposals = prop0 + B;
+        s_proposals = prop0 + window;
         if (s_sa.enabled && n_kept > 0) {
-          // batch-granular schedule: the per-trial geometric cooling is exact; acceptance-window and reheat logic see the
-          // batch as one block of trials (window sizes are >> batch sizes, SimulatedAnnealing.h:52-57)
+          // batch-granular schedule: all trials of a batch see the batch-start temperature; the geometric cooling of
+          // n_kept trials and the acceptance-window / reheat logic (SimulatedAnnealing.cpp:99-139) are applied per batch
+          // (window sizes are >> batch sizes, SimulatedAnnealing.h:52-57)
           SaSchedule sa = s_sa;
           sa.window_trials += n_kept;
           sa.window_accepts += n_acc;
@@ -254,27 +470,37 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
           s_temperature = sa.temperature;
         }
       } else {
-        // strictly serial accept / schedule over the conflict-free prefix
-        const unsigned int limit = s_first_conflict < static_cast<unsigned int>(B) ? s_first_conflict : static_cast<unsigned int>(B);
+        // strictly serial accept / schedule over the conflict-free prefix.  Every CTA runs the same loop on the same
+        // inputs (dE window of rank 0, host stream) so the replicated state stays identical; only rank 0 writes.
+        const double *de_window = cluster.map_shared_rank(s_replay_de, 0);
+        const unsigned long long remaining = n_replay - rpos;
+        unsigned int limit = s_first_conflict < static_cast<unsigned int>(window) ? s_first_conflict : static_cast<unsigned int>(window);
+        if (limit > remaining) limit = static_cast<unsigned int>(remaining);
         unsigned long long pos = rpos;
         double energy = energy0;
         unsigned long long step = steps0;
-        for (unsigned int q = 0; q < limit && pos < n_replay; ++q, ++pos) {
-          const double d = s_replay_de[q];
+        for (unsigned int q = 0; q < limit; ++q, ++pos) {
+          const double d = de_window[q];
           const double temp = s_sa.enabled ? s_sa.temperature : t_batch;
           const double beta = s_sa.enabled ? 1.0 / kBoltzmannEv / fmax(temp, 1e-12) : 1.0 / kBoltzmannEv / temp;
-          if (replay.dE) replay.dE[pos] = d;
-          if (replay.energy_before) replay.energy_before[pos] = energy;
-          if (replay.temperature_before) replay.temperature_before[pos] = temp;
           const bool acc = d < 0.0 || replay.u[pos] < exp(-d * beta);
-          if (replay.accepted) replay.accepted[pos] = acc ? 1 : 0;
+          if (rank == 0) {
+            if (replay.dE) replay.dE[pos] = d;
+            if (replay.energy_before) replay.energy_before[pos] = energy;
+            if (replay.temperature_before) replay.temperature_before[pos] = temp;
+            if (replay.accepted) replay.accepted[pos] = acc ? 1 : 0;
+          }
           if (acc) {
-            int x1, y1, z1, x2, y2, z2;
-            lat.coords_of_id(replay.a[pos], x1, y1, z1);
-            lat.coords_of_id(replay.b[pos], x2, y2, z2);
-            const uint8_t e1 = o[lat.padded_index(x1, y1, z1)], e2 = o[lat.padded_index(x2, y2, z2)];
-            store_site(lat, o, x1, y1, z1, e2);
-            store_site(lat, o, x2, y2, z2, e1);
+            if (rank == 0) {
+              int x1, y1, z1, x2, y2, z2;
+              lat.coords_of_id(replay.a[pos], x1, y1, z1);
+              lat.coords_of_id(replay.b[pos], x2, y2, z2);
+              const uint8_t e1 = __ldcg(o + lat.padded_index(x1, y1, z1)), e2 = __ldcg(o + lat.padded_index(x2, y2, z2));
+              store_site(lat, o, x1, y1, z1, e2);
+              store_site(lat, o, x2, y2, z2, e1);
+              by_id[replay.a[pos]] = e2;
+              by_id[replay.b[pos]] = e1;
+            }
             energy += d;
             ++s_accepted;
           }
@@ -283,16 +509,24 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         }
         s_energy = energy;
         s_steps = step;
-        s_replay_pos = pos;
+        s_replay_pos = limit == 0 ? n_replay : pos;   // limit == 0 cannot happen (trial 0 never conflicts); guards against livelock
         if (s_sa.enabled) s_temperature = s_sa.temperature;
-        if (limit == 0) s_replay_pos = n_replay;     // cannot happen (a trial never conflicts with itself); guards against livelock
       }
       s_epoch = epoch;
     }
-    __syncthreads();
-    if (__syncthreads_or(err != 0)) break;
+    // the next batch reads occupancy written by other CTAs in this one, and must not overwrite s_partial / the dE window
+    // before every CTA has read them
+    cluster.sync();
+    LMC_TICK(5);
+    if (any_err) break;
   }
-  if (tid == 0) {
+#ifdef LMC_CMC_PROFILE
+  if (tid == 0 && w == 0 && rank == 0)
+    printf("cmc profile (cycles): propose %lld compact %lld mark+sync %lld evaluate %lld accept %lld reduce+sync %lld | batches %llu ctas %d\n",
+           s_prof[0], s_prof[1], s_prof[2], s_prof[3], s_prof[4], s_prof[5], s_epoch - st.epoch[w], n_cta);
+#endif
+  cluster.sync();                                   // nobody may exit while others still read its shared memory
+  if (tid == 0 && rank == 0) {
     st.energy[w] = s_energy; st.steps[w] = s_steps; st.accepted[w] = s_accepted; st.proposals[w] = s_proposals;
     st.epoch[w] = s_epoch;
     if (s_sa.enabled) s_sa.temperature = s_temperature;

@@ -630,10 +630,12 @@ void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps)
     d_cmc_steps = dev_alloc<unsigned long long>(nw); d_cmc_accepted = dev_alloc<unsigned long long>(nw);
     d_cmc_proposals = dev_alloc<unsigned long long>(nw); d_cmc_epoch = dev_alloc<unsigned long long>(nw);
     d_cmc_sa = dev_alloc<SaSchedule>(nw); d_cmc_error = dev_alloc<int32_t>(nw);
-    d_cmc_claims = dev_alloc<unsigned long long>(nw * static_cast<size_t>(lat.padded_size));
+    if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the CMC driver addresses lattice ids with 32 bits (num_sites < 2^31)");
+    d_cmc_marks = dev_alloc<unsigned int>(nw * static_cast<size_t>(lat.padded_size));
+    d_cmc_mirror = dev_alloc<uint8_t>(nw * static_cast<size_t>(lat.num_sites));
     for (void *p : {static_cast<void *>(d_cmc_energy), static_cast<void *>(d_cmc_temperature), static_cast<void *>(d_cmc_steps),
                     static_cast<void *>(d_cmc_accepted), static_cast<void *>(d_cmc_proposals), static_cast<void *>(d_cmc_epoch),
-                    d_cmc_sa, static_cast<void *>(d_cmc_error), static_cast<void *>(d_cmc_claims)})
+                    d_cmc_sa, static_cast<void *>(d_cmc_error), static_cast<void *>(d_cmc_marks), static_cast<void *>(d_cmc_mirror)})
       device_allocs.push_back(p);
   }
   LMC_CUDA(cudaMemsetAsync(d_cmc_energy, 0, nw * 8, stream));
@@ -642,7 +644,17 @@ void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps)
   LMC_CUDA(cudaMemsetAsync(d_cmc_proposals, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_epoch, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_error, 0, nw * 4, stream));
-  LMC_CUDA(cudaMemsetAsync(d_cmc_claims, 0, nw * static_cast<size_t>(lat.padded_size) * 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_marks, 0, nw * static_cast<size_t>(lat.padded_size) * 4, stream));
+  {
+    const unsigned blocks = static_cast<unsigned>((lat.num_sites + 255) / 256);
+    for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
+      const unsigned ny = static_cast<unsigned>(std::min(32768, n_walkers - w0));
+      cmc_mirror_kernel<<<dim3(blocks, ny), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(w0) * lat.padded_size,
+                                                              d_cmc_mirror + static_cast<int64_t>(w0) * lat.num_sites);
+      ++launch_count;
+    }
+    LMC_CUDA(cudaGetLastError());
+  }
   // SimulatedAnnealing constructor (mc/src/SimulatedAnnealing.cpp:53-56; ratios mc/include/SimulatedAnnealing.h:45-57)
   SaSchedule sa{};
   sa.enabled = sa_maximum_steps > 0 ? 1 : 0;
@@ -669,11 +681,11 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
   LMC_CUDA(cudaMemcpyAsync(d_cmc_temperature, temps.data(), nw * 8, cudaMemcpyHostToDevice, stream));
   int threads = params.batch_size;
   if (threads <= 0) {
-    // the number of mutually non-interfering survivors peaks near N / (2 * 43 * 2) proposals per batch
+    // the number of mutually non-interfering survivors peaks near N / (2 * 43 * 2) live trials per batch
     threads = 32;
     while (threads < kCmcMaxThreads && threads * 172 < lat.num_sites) threads *= 2;
   }
-  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..1024");
+  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
   CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
   CmcReplay rp{};
   const bool replaying = n_replay > 0;
@@ -693,7 +705,7 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
     rp = CmcReplay{d_a, d_b, d_u, d_de, d_eb, d_tb, d_acc};
     first_walker = replay_walker;
     n_run = 1;
-    threads = std::min(threads, 256);
+    threads = std::min(threads, 128);
   } else {
     if (n_trials <= 0) return;
     std::vector<unsigned long long> steps(nw);
@@ -709,11 +721,42 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
     st_run.energy += first_walker; st_run.steps += first_walker; st_run.accepted += first_walker; st_run.proposals += first_walker;
     st_run.epoch += first_walker; st_run.sa += first_walker; st_run.error += first_walker;
   }
+  // cluster size: CTAs that share one replica's batch.  Many replicas -> 1; few replicas on a big lattice -> up to 8
+  int cluster = 1;
+  if (!replaying || true) {
+    int sms = 0;
+    LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    while (cluster < 8 && static_cast<int64_t>(n_run) * cluster * 2 <= sms && static_cast<int64_t>(threads) * cluster * 172 < lat.num_sites * 2) cluster *= 2;
+  }
+  if (params.batch_size <= 0 && cluster > 1) threads = std::max(128, threads / 2);
+  // dynamic shared memory: replay dE window, site tables, per-thread species staging (2 x 43 bytes per thread)
+  const int m = species.n + 1;
+  const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
+  const size_t fixed = (static_cast<size_t>(threads) * cluster + m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
+  int max_optin = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const int stage_b = (fixed + b_len * 8 + 16 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
+  const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
+  LMC_CUDA(cudaFuncSetAttribute(cmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(n_run * cluster));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   time_begin();
-  cmc_run_kernel<<<static_cast<unsigned>(n_run), threads, static_cast<size_t>(threads) * sizeof(double), stream>>>(
-      lat, tab, d_occ + static_cast<int64_t>(first_walker) * lat.padded_size, lat.padded_size,
-      d_cmc_claims + static_cast<size_t>(first_walker) * lat.padded_size, st_run, d_cmc_temperature + first_walker, params.seed, target, rp,
-      static_cast<unsigned long long>(std::max<int64_t>(0, n_replay)));
+  LMC_CUDA(cudaLaunchKernelEx(&cfg, cmc_run_kernel, lat, tab, d_occ + static_cast<int64_t>(first_walker) * lat.padded_size, lat.padded_size,
+                              d_cmc_mirror + static_cast<size_t>(first_walker) * lat.num_sites,
+                              d_cmc_marks + static_cast<size_t>(first_walker) * lat.padded_size, st_run,
+                              static_cast<const double *>(d_cmc_temperature + first_walker), static_cast<uint64_t>(params.seed),
+                              static_cast<unsigned long long>(target), rp,
+                              static_cast<unsigned long long>(std::max<int64_t>(0, n_replay)), stage_b));
   time_end();
   LMC_CUDA(cudaGetLastError());
   if (replaying) {

@@ -100,7 +100,9 @@ class Engine {
   bool kmc_ready{false};
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};
-  unsigned long long *d_cmc_steps{nullptr}, *d_cmc_accepted{nullptr}, *d_cmc_proposals{nullptr}, *d_cmc_epoch{nullptr}, *d_cmc_claims{nullptr};
+  unsigned long long *d_cmc_steps{nullptr}, *d_cmc_accepted{nullptr}, *d_cmc_proposals{nullptr}, *d_cmc_epoch{nullptr};
+  unsigned int *d_cmc_marks{nullptr};
+  uint8_t *d_cmc_mirror{nullptr};
   void *d_cmc_sa{nullptr};
   int32_t *d_cmc_error{nullptr};
   double *d_cmc_temperature{nullptr};
