@@ -186,7 +186,7 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    from latticemontecarlo_b200 import build as _build, capi, synth
+    from latticemontecarlo_b200 import build as _build, capi, sharding, synth
     _build.build()
     if capi.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
@@ -200,9 +200,10 @@ def run_ours(args):
     engine.load_coefficients(js)
     occ_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
     occ_np = occ_pinned.numpy()
-    occ_np[:] = walker_occupancy(rank * W, W)
+    first_walker, _ = sharding.shard_range(W * n_gpus, rank, n_gpus)        # weak scaling: W walkers on every rank
+    occ_np[:] = walker_occupancy(first_walker, W)
     out_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
-    temps = 400.0 + 200.0 * (rank * W + np.arange(W)) / max(1, W * n_gpus - 1)
+    temps = sharding.walker_temperatures(first_walker, W, W * n_gpus)
     stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -238,10 +239,7 @@ def run_ours(args):
     launches = engine.launch_count() - launches0
     step_ms = sum(t[0] for t in timings)
     kernel_ms = sum(t[1] for t in timings)
-    if world > 1:
-        t = torch.tensor([step_ms, kernel_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, kernel_ms = float(t[0]), float(t[1])
+    step_ms, kernel_ms = sharding.max_over_ranks([step_ms, kernel_ms], device="cuda")      # slowest rank defines the step
     hops_total = float(W) * H * args.steps * n_gpus
     value = hops_total / (step_ms * 1e-3)
 
@@ -261,10 +259,7 @@ def run_ours(args):
     barrier()
     e2e_s = sum(step_e2e()[0] for _ in range(args.steps))
     barrier()
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    e2e_s = sharding.max_over_ranks([e2e_s], device="cuda")[0]
     e2e_value = hops_total / e2e_s
 
     peak, peak_kind = measured_peaks()

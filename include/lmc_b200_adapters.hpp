@@ -1,0 +1,221 @@
+// lmc_b200_adapters.hpp -- C++ host-side mirror of the reference's predictor / driver interfaces over the C ABI.
+//
+// The reference (zhucongx/LatticeMonteCarlo) reaches its hot path through three predictor classes that are
+// const members of the mc:: drivers.  These adapters keep the same class names, constructor
+// arguments, method names, argument meaning and exception types, but forward to liblmc_b200.so:
+//
+//   pred::VacancyMigrationPredictorQuartic[Lru]::GetBarrierAndDiffFromLatticeIdPair   pred/include/VacancyMigrationPredictorQuartic.h:25-27
+//   pred::EnergyChangePredictorPairSite::GetDeFromLatticeIdPair / ...Site             pred/include/EnergyChangePredictorPairSite.h:20-25
+//   pred::EnergyPredictor::GetEnergy                                                   pred/include/EnergyPredictor.h:19-25
+//   mc::KineticMcFirstOmp / CanonicalMcOmp / SimulatedAnnealing ::Simulate             mc/include/*.h
+//
+// What differs, by design: the configuration lives on the device (lmc_b200::Config owns an lmc_engine and the
+// packed uint8 occupancy), batch entry points are added next to the scalar ones, and the LRU cache of
+// VacancyMigrationPredictorQuarticLru is replaced by batch recomputation (the class is kept as an alias).
+// Header-only; link with -llmc_b200.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "lmc_b200.h"
+
+namespace lmc_b200 {
+
+// ElementName values of the reference (lmc/cfg/include/Element.hpp:7)
+enum class ElementName : int32_t { X = 0, Al, Mg, Zn, Cu, Sn, pAl, pMg, pZn, pCu, pSn };
+
+inline void check(int rc) {
+  if (rc >= 0) return;
+  const std::string msg = lmc_last_error();
+  switch (rc) {
+    case LMC_ERR_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+    case LMC_ERR_OUT_OF_RANGE: throw std::out_of_range(msg);      // same type the reference throws (EnergyUtility.cpp:815-817)
+    default: throw std::runtime_error(msg);                        // "Cannot open <file>", CUDA errors, no device
+  }
+}
+
+namespace cfg {
+// Device-resident counterpart of cfg::Config (lmc/cfg/include/Config.h:14-112) for FCC supercells.
+class Config {
+ public:
+  Config(const std::array<size_t, 3> &factors, lmc_id_order order, const std::set<ElementName> &element_set, ElementName solvent,
+         int n_walkers = 1, int device = 0) {
+    const int32_t f[3] = {static_cast<int32_t>(factors[0]), static_cast<int32_t>(factors[1]), static_cast<int32_t>(factors[2])};
+    std::vector<int32_t> es;
+    for (auto e : element_set) es.push_back(static_cast<int32_t>(e));
+    lmc_engine *raw = nullptr;
+    check(lmc_engine_create(&raw, f, order, es.data(), static_cast<int32_t>(es.size()), static_cast<int32_t>(solvent), n_walkers, device));
+    engine_.reset(raw, lmc_engine_destroy);
+  }
+  [[nodiscard]] size_t GetNumAtoms() const { return static_cast<size_t>(lmc_engine_num_sites(engine_.get())); }
+  void SetOccupancy(const std::vector<uint8_t> &element_by_lattice_id, int walker = 0) {
+    check(lmc_engine_set_occupancy(engine_.get(), walker, element_by_lattice_id.data(), static_cast<int64_t>(element_by_lattice_id.size())));
+  }
+  [[nodiscard]] std::vector<uint8_t> GetOccupancy(int walker = 0) const {
+    std::vector<uint8_t> out(GetNumAtoms());
+    check(lmc_engine_get_occupancy(engine_.get(), walker, out.data(), static_cast<int64_t>(out.size())));
+    return out;
+  }
+  // Config::GetFirst/Second/ThirdNeighborsAdjacencyList()[lattice_id] (ascending ids)
+  [[nodiscard]] std::vector<size_t> GetNeighbors(int shell, size_t lattice_id) const {
+    int64_t buf[24];
+    check(lmc_engine_neighbors(engine_.get(), shell, static_cast<int64_t>(lattice_id), buf));
+    const int n = shell == 1 ? 12 : (shell == 2 ? 6 : 24);
+    return std::vector<size_t>(buf, buf + n);
+  }
+  void LatticeJump(const std::pair<size_t, size_t> &lattice_id_jump_pair, int walker = 0) {   // Config.cpp:431-456
+    check(lmc_engine_lattice_jump(engine_.get(), walker, static_cast<int64_t>(lattice_id_jump_pair.first),
+                                  static_cast<int64_t>(lattice_id_jump_pair.second)));
+  }
+  [[nodiscard]] lmc_engine *engine() const { return engine_.get(); }
+
+ private:
+  std::shared_ptr<lmc_engine> engine_;
+};
+}  // namespace cfg
+
+namespace pred {
+// One JSON file feeds all three predictors, exactly as in the reference (each of its constructors re-reads the file).
+inline void LoadCoefficients(const cfg::Config &reference_config, const std::string &predictor_filename) {
+  check(lmc_engine_load_coefficients(reference_config.engine(), predictor_filename.c_str()));
+}
+
+class VacancyMigrationPredictorQuartic {
+ public:
+  VacancyMigrationPredictorQuartic(const std::string &predictor_filename, const cfg::Config &reference_config,
+                                   const std::set<ElementName> & /*element_set: fixed by the Config*/) {
+    LoadCoefficients(reference_config, predictor_filename);
+  }
+  virtual ~VacancyMigrationPredictorQuartic() = default;
+  // {Ea, dE} of the vacancy at .first exchanging with the atom at .second
+  [[nodiscard]] virtual std::pair<double, double> GetBarrierAndDiffFromLatticeIdPair(
+      const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair, int walker = 0) const {
+    const int64_t i = static_cast<int64_t>(lattice_id_jump_pair.first), j = static_cast<int64_t>(lattice_id_jump_pair.second);
+    const int32_t w = walker;
+    double ea = 0, de = 0;
+    check(lmc_eval_barriers(config.engine(), 1, &w, &i, &j, &ea, &de, nullptr, nullptr));
+    return {ea, de};
+  }
+  // batch form: all candidate events of a step (or of many walkers) in one launch
+  void GetBarrierAndDiffFromLatticeIdPairs(const cfg::Config &config, const std::vector<int32_t> &walker, const std::vector<int64_t> &first,
+                                           const std::vector<int64_t> &second, std::vector<double> &Ea, std::vector<double> &dE) const {
+    Ea.resize(first.size());
+    dE.resize(first.size());
+    check(lmc_eval_barriers(config.engine(), static_cast<int64_t>(first.size()), walker.empty() ? nullptr : walker.data(), first.data(),
+                            second.data(), Ea.data(), dE.data(), nullptr, nullptr));
+  }
+};
+// The LRU cache (pred/src/VacancyMigrationPredictorQuarticLru.cpp) is replaced by batch recomputation; cache_size is accepted and ignored.
+class VacancyMigrationPredictorQuarticLru : public VacancyMigrationPredictorQuartic {
+ public:
+  VacancyMigrationPredictorQuarticLru(const std::string &predictor_filename, const cfg::Config &reference_config,
+                                      const std::set<ElementName> &element_set, size_t /*cache_size*/)
+      : VacancyMigrationPredictorQuartic(predictor_filename, reference_config, element_set) {}
+};
+
+class EnergyChangePredictorPairSite {
+ public:
+  EnergyChangePredictorPairSite(const std::string &predictor_filename, const cfg::Config &reference_config,
+                                const std::set<ElementName> &) {
+    LoadCoefficients(reference_config, predictor_filename);
+  }
+  [[nodiscard]] double GetDeFromLatticeIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair,
+                                              int walker = 0) const {
+    const int64_t a = static_cast<int64_t>(lattice_id_jump_pair.first), b = static_cast<int64_t>(lattice_id_jump_pair.second);
+    const int32_t w = walker;
+    double de = 0;
+    check(lmc_eval_swap_de(config.engine(), 1, &w, &a, &b, &de));
+    return de;
+  }
+  [[nodiscard]] double GetDeFromLatticeIdSite(const cfg::Config &config, size_t lattice_id, ElementName new_element, int walker = 0) const {
+    const int64_t s = static_cast<int64_t>(lattice_id);
+    const uint8_t e = static_cast<uint8_t>(new_element);
+    const int32_t w = walker;
+    double de = 0;
+    check(lmc_eval_site_de(config.engine(), 1, &w, &s, &e, &de));
+    return de;
+  }
+};
+
+class EnergyPredictor {
+ public:
+  EnergyPredictor(const std::string &predictor_filename, const cfg::Config &reference_config) {
+    LoadCoefficients(reference_config, predictor_filename);
+  }
+  [[nodiscard]] double GetEnergy(const cfg::Config &config, int walker = 0) const {
+    double e = 0;
+    check(lmc_total_energy(config.engine(), walker, &e, nullptr, 0));
+    return e;
+  }
+};
+}  // namespace pred
+
+namespace mc {
+// mc::KineticMcFirstOmp (mc/include/KineticMcFirstOmp.h) over all walkers of the Config.  Simulate() runs
+// maximum_steps + 1 iterations like the reference's `while (steps_ <= maximum_steps_)` (KineticMcAbstract.cpp:184-188).
+class KineticMcFirstOmp {
+ public:
+  KineticMcFirstOmp(cfg::Config config, unsigned long long maximum_steps, double temperature, const std::string &json_coefficients_filename,
+                    const std::vector<std::pair<double, double>> &time_temperature = {}, bool is_rate_corrector = false,
+                    uint64_t seed = 0)
+      : config_(std::move(config)), maximum_steps_(maximum_steps), temperature_(temperature), tt_(time_temperature),
+        rate_corrector_(is_rate_corrector), seed_(seed) {
+    pred::LoadCoefficients(config_, json_coefficients_filename);
+    check(lmc_kmc_reset(config_.engine()));
+  }
+  void Simulate() {
+    std::vector<double> t, v;
+    for (const auto &p : tt_) { t.push_back(p.first); v.push_back(p.second); }
+    lmc_kmc_params prm{};
+    prm.temperature = temperature_;
+    prm.n_time_temperature = static_cast<int32_t>(t.size());
+    prm.tt_time = t.data();
+    prm.tt_temperature = v.data();
+    prm.rate_corrector = rate_corrector_ ? 1 : 0;
+    prm.seed = seed_;
+    check(lmc_kmc_run(config_.engine(), &prm, static_cast<int64_t>(maximum_steps_ + 1), nullptr, nullptr, nullptr));
+  }
+  [[nodiscard]] const cfg::Config &GetConfig() const { return config_; }
+
+ private:
+  cfg::Config config_;
+  unsigned long long maximum_steps_;
+  double temperature_;
+  std::vector<std::pair<double, double>> tt_;
+  bool rate_corrector_;
+  uint64_t seed_;
+};
+
+// mc::CanonicalMcOmp (mc/include/CanonicalMcOmp.h); with initial_temperature > 0 and sa_maximum_steps > 0 it is
+// mc::SimulatedAnnealing's schedule (mc/include/SimulatedAnnealing.h:42-68).
+class CanonicalMcOmp {
+ public:
+  CanonicalMcOmp(cfg::Config config, unsigned long long maximum_steps, double temperature, const std::string &json_coefficients_filename,
+                 uint64_t seed = 0, bool simulated_annealing = false)
+      : config_(std::move(config)), maximum_steps_(maximum_steps), temperature_(temperature), seed_(seed) {
+    pred::LoadCoefficients(config_, json_coefficients_filename);
+    check(lmc_cmc_reset(config_.engine(), simulated_annealing ? temperature : 0.0, simulated_annealing ? maximum_steps : 0));
+  }
+  void Simulate() {
+    lmc_cmc_params prm{};
+    prm.temperature = temperature_;
+    prm.seed = seed_;
+    check(lmc_cmc_run(config_.engine(), &prm, static_cast<int64_t>(maximum_steps_ + 1)));
+  }
+  [[nodiscard]] const cfg::Config &GetConfig() const { return config_; }
+
+ private:
+  cfg::Config config_;
+  unsigned long long maximum_steps_;
+  double temperature_;
+  uint64_t seed_;
+};
+}  // namespace mc
+
+}  // namespace lmc_b200

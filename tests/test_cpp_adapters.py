@@ -1,0 +1,75 @@
+"""The C++ host-side mirror of the reference's interfaces (include/lmc_b200_adapters.hpp): it must compile and link
+against the C ABI on the CPU box, fail loudly without a device, and reproduce the Python/C-ABI numbers on the GPU."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from latticemontecarlo_b200 import build as _build, capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def demo(tmp_path_factory):
+    _build.build()
+    exe = str(tmp_path_factory.mktemp("demo") / "adapter_demo")
+    libdir = os.path.join(ROOT, "latticemontecarlo_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "adapter_demo.cpp"), "-L" + libdir, "-llmc_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                   check=True)
+    return exe
+
+
+def test_adapters_compile_and_fail_loudly_without_gpu(demo, coef_json):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present; the loud-failure path is for the CPU box")
+    res = subprocess.run([demo, coef_json], capture_output=True, text=True)
+    assert res.returncode == 1 and "not available" in res.stderr
+
+
+@pytest.mark.gpu
+def test_adapter_demo_matches_c_abi(demo, coef_json):
+    res = subprocess.run([demo, coef_json, "6"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    ea = np.array([float(m) for m in re.findall(r"Ea = ([-0-9.e+]+) eV", res.stdout)])
+    de = np.array([float(m) for m in re.findall(r"dE = ([-+0-9.e]+) eV", res.stdout)])
+    assert len(ea) == 12 and "std::out_of_range as in the reference" in res.stdout and "KMC: 1000 steps" in res.stdout
+    # the same occupancy through the Python binding: the demo draws it with std::mt19937_64(42), re-created here
+    f = 6
+    e = capi.Engine(f, device=0)
+    e.load_coefficients(coef_json)
+    occ = _mt19937_64_alloy(4 * f ** 3)
+    e.set_occupancy(occ)
+    vac = len(occ) // 2 + 3
+    ea2, de2 = e.eval_barriers(np.full(12, vac), e.neighbors(1, vac))
+    assert np.max(np.abs(ea - ea2)) < 1e-11 and np.max(np.abs(de - de2)) < 1e-11
+
+
+def _mt19937_64_alloy(n):
+    """std::mt19937_64(42) + uniform_real_distribution<double>(0,1): one 64-bit draw x, u = double(x) / 2^64
+    (libstdc++ generate_canonical)."""
+    nn, mm = 312, 156
+    mt = [0] * nn
+    mt[0] = 42
+    for i in range(1, nn):
+        mt[i] = (6364136223846793005 * (mt[i - 1] ^ (mt[i - 1] >> 62)) + i) & 0xFFFFFFFFFFFFFFFF
+    idx = nn
+    occ = np.ones(n, dtype=np.uint8)
+    for k in range(n):
+        if idx >= nn:
+            for i in range(nn):
+                x = (mt[i] & 0xFFFFFFFF80000000) | (mt[(i + 1) % nn] & 0x7FFFFFFF)
+                mt[i] = mt[(i + mm) % nn] ^ (x >> 1) ^ (0xB5026F5AA96619E9 if x & 1 else 0)
+            idx = 0
+        y = mt[idx]; idx += 1
+        y ^= (y >> 29) & 0x5555555555555555
+        y ^= (y << 17) & 0x71D67FFFEDA60000
+        y ^= (y << 37) & 0xFFF7EEE000000000
+        y ^= y >> 43
+        u = float(y) / 18446744073709551616.0
+        occ[k] = 2 if u < 0.02 else (3 if u < 0.04 else 1)
+    occ[n // 2 + 3] = 0
+    return occ

@@ -1,0 +1,47 @@
+"""CPU suite: the N>1 host logic (walker sharding, max-over-ranks timing, statistics gather) under torch.distributed
+with the gloo backend, world_size 2 -- the same code path bench.py runs over NCCL on the GPU box."""
+import os
+import socket
+
+import numpy as np
+import torch.multiprocessing as mp
+
+from latticemontecarlo_b200 import sharding
+
+
+def test_shard_ranges_partition_the_walkers():
+    for total in (1, 7, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            blocks = [sharding.shard_range(total, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == total
+            for (f0, c0), (f1, _) in zip(blocks, blocks[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+    t = np.concatenate([sharding.walker_temperatures(*sharding.shard_range(8192, r, 8), 8192) for r in range(8)])
+    assert np.allclose(t, 400.0 + 200.0 * np.arange(8192) / 8191.0)          # independent of the rank count
+
+
+def _worker(rank, world, port, total):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        first, count = sharding.shard_range(total, rank, world)
+        # every rank "measures" a different time; the reported one is the slowest rank's
+        assert sharding.max_over_ranks([10.0 + rank, 1.0 - rank]) == [10.0 + world - 1, 1.0]
+        assert sharding.sum_over_ranks([count]) == [float(total)]
+        stats = sharding.gather_walker_stats(np.arange(first, first + count, dtype=np.float64) * 2.0, total)
+        if rank == 0:
+            assert np.array_equal(stats, 2.0 * np.arange(total))
+        else:
+            assert stats is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_sharding():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port, 11), nprocs=2, join=True)
