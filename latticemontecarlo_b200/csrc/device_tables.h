@@ -18,11 +18,17 @@ struct DevTables {
   const int8_t *pair_off;        // [12][2][60][4] lattice offsets of the ordered pair neighbourhood (debug taps)
   const int8_t *site_off;        // [43][4]
   int32_t pair_first_pos, pair_second_pos, site_centre_pos;
+  // KMC box scan: the 7 x 7 x 4 padded cells around a vacancy that cover the neighbourhoods of all 12 jumps
+  const int32_t *box_delta;      // [2][196]      padded-layout offset of box cell c from the vacancy, row = z parity
+  const int8_t *box_envpos;      // [2][12][196]  env index (0..57) of box cell c in the neighbourhood of jump k; 58 / 59 =
+                                 //               first / second site of the pair; -1 = not part of that neighbourhood
   // chemistry
   int32_t n_species;             // species without vacancy; vacancy code == n_species
   int32_t solvent;               // compact code of the expansion origin
   // contracted jump tables (delta form): Q = C[m] + sum A[m][t][e] + sum B[m][p][a][b], 3 quantities each
   const double *pair_C, *pair_A, *pair_B;
+  // the same folded to the two numbers a barrier needs: (dE, log E0) with log E0 = logKs + 2 logD   [..][2]
+  const double *pair_C2, *pair_A2, *pair_B2;
   const uint64_t *pair_mask_hi;  // [58]
   const uint16_t *pair_base;     // [58]
   int32_t n_pair_pairs;          // 556

@@ -167,6 +167,30 @@ void Engine::upload_geometry_tables() {
   for (int t = 0; t < 43; ++t) {
     site_off[4 * t] = g.site_offsets[t].x; site_off[4 * t + 1] = g.site_offsets[t].y; site_off[4 * t + 2] = g.site_offsets[t].z;
   }
+  // KMC box tables
+  std::vector<int32_t> box_delta(2 * kBoxCells, 0);
+  std::vector<int8_t> box_envpos(2 * 12 * kBoxCells, -1);
+  for (int zp = 0; zp < 2; ++zp) {
+    const int dzi_min = zp == 0 ? -2 : -1;
+    for (int c = 0; c < kBoxCells; ++c) {
+      const int slot = c % 4, dy = (c / 4) % 7 - 3, dx = c / 28 - 3;
+      const int dzi = slot + dzi_min;
+      const int dz = 2 * dzi - zp + ((zp + dx + dy) & 1);
+      box_delta[zp * kBoxCells + c] = (dx * lat.ny + dy) * lat.nz + dzi;
+      if (lat.padded_delta(dx, dy, dz, zp) != box_delta[zp * kBoxCells + c]) throw std::logic_error("box cell geometry is inconsistent");
+      for (int k = 0; k < 12; ++k)
+        for (int t = 0; t < 60; ++t)
+          if (g.pair_offsets[k][0][t] == Int3{dx, dy, dz})
+            box_envpos[(zp * 12 + k) * kBoxCells + c] = static_cast<int8_t>(g.env_of_state[t] >= 0 ? g.env_of_state[t] : (g.env_of_state[t] == -1 ? 58 : 59));
+    }
+    for (int k = 0; k < 12; ++k) {   // every neighbourhood site must be inside the box
+      int found = 0;
+      for (int c = 0; c < kBoxCells; ++c) found += box_envpos[(zp * 12 + k) * kBoxCells + c] >= 0;
+      if (found != 60) throw std::logic_error("KMC box does not cover a jump neighbourhood");
+    }
+  }
+  tab.box_delta = to_device(box_delta);
+  tab.box_envpos = to_device(box_envpos);
   tab.pair_delta = to_device(pair_delta);
   tab.site_delta = to_device(site_delta);
   tab.dir_lut = to_device(dir_lut);
@@ -268,6 +292,17 @@ void Engine::load_coefficients(const std::string &json_path) {
   has_coefficients = true;
   if (device >= 0) {
     cudaSetDevice(device);
+    auto fold = [](const std::vector<double> &v) {      // [..][3] = (dE, logD, logKs)  ->  [..][2] = (dE, logKs + 2 logD)
+      std::vector<double> out(v.size() / 3 * 2);
+      for (size_t i = 0; i < v.size() / 3; ++i) {
+        out[2 * i] = v[3 * i];
+        out[2 * i + 1] = v[3 * i + 2] + 2.0 * v[3 * i + 1];
+      }
+      return out;
+    };
+    tab.pair_C2 = to_device(fold(pair_tables.C));
+    tab.pair_A2 = to_device(fold(pair_tables.A));
+    tab.pair_B2 = to_device(fold(pair_tables.B));
     tab.pair_C = to_device(pair_tables.C);
     tab.pair_A = to_device(pair_tables.A);
     tab.pair_B = to_device(pair_tables.B);
@@ -587,8 +622,11 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
+  if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the KMC driver orders events by 32-bit lattice ids (num_sites < 2^31)");
+  const size_t kmc_smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
+  LMC_CUDA(cudaFuncSetAttribute(kmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
   time_begin();
-  kmc_run_kernel<<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+  kmc_run_kernel<<<blocks, kKmcThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
   time_end();
   LMC_CUDA(cudaGetLastError());
   if (tracing) {

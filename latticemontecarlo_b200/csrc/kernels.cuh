@@ -18,6 +18,7 @@ namespace lmc {
 // structural constants of the ordered neighbourhoods (verified against tables.cpp at engine creation)
 constexpr int kFirstPos = 21, kSecondPos = 38, kCentrePos = 21;
 constexpr int kEnvN = 58, kSiteEnvN = 42;
+constexpr int kBoxCells = 7 * 7 * 4;   // KMC box scan: cells of the padded layout within 3 half-units of a vacancy
 
 enum EventError : int { kErrNotNeighbour = 1, kErrNotVacancy = 2, kErrExtraVacancy = 4, kErrBadSite = 8 };
 
@@ -137,25 +138,24 @@ __global__ void download_occupancy_kernel(LatticeDesc lat, const uint8_t *__rest
   occ_by_id[id] = enum_of_code[padded[lat.padded_index_of_id(id)]];
 }
 
-// write one site and all its periodic halo images
+// write one site and all its periodic halo images.  A coordinate within `halo` of a face has exactly one image along
+// that axis (periods are >= 8 half-units > 2 * halo), so there are at most 7 images: the non-empty subsets of the axes.
 __device__ __forceinline__ void store_site(const LatticeDesc &lat, uint8_t *occ, int X, int Y, int Z, uint8_t code) {
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
-  occ[lat.padded_index(X, Y, Z)] = code;
-  const bool edge = X < kHalo || X >= px - kHalo || Y < kHalo || Y >= py - kHalo || Z < kHaloZ || Z >= pz - kHaloZ;
-  if (!edge) return;                 // interior sites have no halo image
-  for (int a = -1; a <= 1; ++a) {
-    const int x = X + a * px;
-    if (x < -kHalo || x >= px + kHalo) continue;
-    for (int b = -1; b <= 1; ++b) {
-      const int y = Y + b * py;
-      if (y < -kHalo || y >= py + kHalo) continue;
-      for (int c = -1; c <= 1; ++c) {
-        const int z = Z + c * pz;
-        if (z < -kHaloZ || z >= pz + kHaloZ) continue;
-        if (a | b | c) occ[lat.padded_index(x, y, z)] = code;
-      }
-    }
-  }
+  const int64_t base = lat.padded_index(X, Y, Z);
+  occ[base] = code;
+  const int sx = X < kHalo ? px : (X >= px - kHalo ? -px : 0);
+  const int sy = Y < kHalo ? py : (Y >= py - kHalo ? -py : 0);
+  const int sz = Z < kHaloZ ? pz : (Z >= pz - kHaloZ ? -pz : 0);
+  if ((sx | sy | sz) == 0) return;                                      // interior site: no image
+  const int64_t ix = static_cast<int64_t>(sx) * lat.ny * lat.nz, iy = static_cast<int64_t>(sy) * lat.nz, iz = sz / 2;
+  if (sx) occ[base + ix] = code;
+  if (sy) occ[base + iy] = code;
+  if (sz) occ[base + iz] = code;
+  if (sx && sy) occ[base + ix + iy] = code;
+  if (sx && sz) occ[base + ix + iz] = code;
+  if (sy && sz) occ[base + iy + iz] = code;
+  if (sx && sy && sz) occ[base + ix + iy + iz] = code;
 }
 
 __global__ void lattice_jump_kernel(LatticeDesc lat, uint8_t *occ, int64_t a, int64_t b) {

@@ -105,17 +105,36 @@ __global__ void kmc_init_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ
 }
 
 constexpr int kKmcThreads = 128;   // 8 walkers per block
+constexpr int kKmcWalkersPerBlock = kKmcThreads / 16;
+constexpr int kBoxCentre = (3 * 7 + 3) * 4;   // + slot of dz = 0, which depends on the z parity (2 for even Z, 1 for odd Z)
 
-__global__ void __launch_bounds__(kKmcThreads)
+// The 12 jumps of one vacancy share a 7 x 7 x 7 half-unit box (196 padded cells).  Per step the half-warp scans the box
+// ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
+// event lane then maps that list into its own symmetry-ordered environment through a constant cell -> env-index table.
+__global__ void __launch_bounds__(kKmcThreads, 7)
 kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
-  __shared__ int32_t s_delta[24 * kPairDeltaStride];
-  for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
+  __shared__ int32_t s_box[2 * kBoxCells];
+  __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
+  __shared__ uint8_t s_list_cell[kKmcWalkersPerBlock][kBoxCells], s_list_code[kKmcWalkersPerBlock][kBoxCells];
+  __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
+  __shared__ double s_ord_rate[kKmcWalkersPerBlock][12];
+  __shared__ uint8_t s_ord_lane[kKmcWalkersPerBlock][12];
+  extern __shared__ double s_A2[];                 // [n][58][n][2]: the singlet table of every migrating species
+  __shared__ uint64_t s_mask_hi[kEnvN];
+  __shared__ uint16_t s_pbase[kEnvN];
+  __shared__ uint32_t s_ids[kKmcWalkersPerBlock][12];
+  for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
+  for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
+  for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
+  for (int q = threadIdx.x; q < 2 * 12 * kBoxCells; q += blockDim.x) s_envpos[q] = tab.box_envpos[q];
   __syncthreads();
   const int lane = threadIdx.x & 15;
+  const int wl = threadIdx.x >> 4;                 // walker slot within the block
   const int w = static_cast<int>((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4);
   if (w >= n_walkers) return;
-  const unsigned hmask = 0xFFFFu << (threadIdx.x & 16);
+  const int hshift = threadIdx.x & 16;
+  const unsigned hmask = 0xFFFFu << hshift;
   uint8_t *o = occ + w * walker_stride;
   if (st.error[w] != 0 || st.vacancy[w] < 0) return;
 
@@ -125,10 +144,18 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   int64_t steps = st.steps[w];
   const double c_vac = st.c_vacancy[w], c_sol = st.c_solute[w];
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac_code = static_cast<unsigned>(tab.n_species);
+  const int n_species = tab.n_species;
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
   const bool active = lane < 12;
   const int k = active ? lane : 0;
   const int dxk = tab.nn1[4 * k], dyk = tab.nn1[4 * k + 1], dzk = tab.nn1[4 * k + 2];
+  const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
+  double *ord_rate = s_ord_rate[wl];
+  uint8_t *ord_lane = s_ord_lane[wl];
+  uint8_t *list_cell = s_list_cell[wl], *list_code = s_list_code[wl], *my_codes = s_codes[threadIdx.x];
+  const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
+  uint32_t *ids = s_ids[wl];
+  const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
 
   for (int64_t s = 0; s < n_steps; ++s) {
@@ -137,44 +164,114 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const double beta = 1.0 / kBoltzmannEv / temperature;
     // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
     const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
-    const int64_t id_j = active ? lat.id_of_coords(xj, yj, zj) : INT64_MAX;
+    const uint32_t id_j = static_cast<uint32_t>(lat.id_of_coords(xj, yj, zj));       // num_sites < 2^31 (checked by the host)
+    if (active) ids[lane] = id_j;
+    __syncwarp(hmask);
     int slot = 0;
 #pragma unroll
-    for (int q = 0; q < 12; ++q) slot += (__shfl_sync(hmask, id_j, q, 16) < id_j) ? 1 : 0;
+    for (int q = 0; q < 12; ++q) slot += ids[q] < id_j ? 1 : 0;
+    // ---- box scan: the non-solvent cells around the vacancy, in cell order
+    const int zp = Z & 1;
+    const int64_t base = lat.padded_index(X, Y, Z);
+    const int32_t *box = s_box + zp * kBoxCells;
+    const int centre = kBoxCentre + (zp ? 1 : 2);
+    // each lane reads 13 (12) cells; its hits are kept as a bit mask + packed codes and compacted once at the end
+    unsigned hit_mask = 0;
+    unsigned long long hit_codes = 0;           // 4 bits per scanned cell
+#pragma unroll
+    for (int it = 0; it < (kBoxCells + 15) / 16; ++it) {
+      const int c = it * 16 + lane;
+      if (it * 16 + 15 < kBoxCells || c < kBoxCells) {
+        const unsigned code = o[base + box[c]];
+        if (c == centre) { if (code != vac_code) err |= kErrNotVacancy; }
+        else if (code != solvent) { hit_mask |= 1u << it; hit_codes |= static_cast<unsigned long long>(code) << (4 * it); }
+      }
+    }
+    // exclusive prefix of the per-lane hit counts over the half-warp
+    const int mine = __popc(hit_mask);
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+      const int v = __shfl_up_sync(hmask, incl, off, 16);
+      if (lane >= off) incl += v;
+    }
+    const int count = __shfl_sync(hmask, incl, 15, 16);
+    int pos = incl - mine;
+    while (hit_mask) {
+      const int it = __ffs(static_cast<int>(hit_mask)) - 1;
+      hit_mask &= hit_mask - 1;
+      list_cell[pos] = static_cast<uint8_t>(it * 16 + lane);
+      list_code[pos] = static_cast<uint8_t>((hit_codes >> (4 * it)) & 0xFULL);
+      ++pos;
+    }
+    __syncwarp(hmask);
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
     if (active) {
-      const int64_t base = lat.padded_index(X, Y, Z);
-      const int32_t *drow = s_delta + (k * 2 + (Z & 1)) * kPairDeltaStride;
-      unsigned first = 0;
-      const uint64_t sol = gather_pair_env(o, base, drow, solvent, &first, &mig);
-      if (first != vac_code || mig == vac_code) err |= kErrNotVacancy;
+      mig = o[base + (zp ? dmig1 : dmig0)];
+      if (mig == vac_code) err |= kErrNotVacancy;
       else {
-        double acc[3];
-        if (!accumulate_pair_tables(tab, static_cast<int>(mig), sol, o, base, drow, acc)) err |= kErrExtraVacancy;
+        // map the box list into this jump's environment: solute mask + species by env index
+        const int8_t *envpos = s_envpos + (zp * 12 + k) * kBoxCells;
+        uint64_t sol = 0;
+        for (int q = 0; q < count; ++q) {
+          const int t = envpos[list_cell[q]];
+          if (t >= 0 && t < kEnvN) {
+            sol |= 1ULL << t;
+            my_codes[t] = list_code[q];
+          }
+        }
+        // contracted tables: Q = C[m] + sum_t A[m][t][e_t] + sum_(t,u) B[m][(t,u)][e_t][e_u] over the solute sites
+        const int m = static_cast<int>(mig), n = n_species;
+        const double *__restrict__ C = tab.pair_C2 + m * 2;
+        double a0 = __ldg(C), a1 = __ldg(C + 1);                      // (dE, log E0)
+        const double2 *A = reinterpret_cast<const double2 *>(s_A2) + static_cast<size_t>(m) * kEnvN * n;
+        const double2 *__restrict__ B = B_all + static_cast<size_t>(m) * tab.n_pair_pairs * n * n;
+        bool ok = true;
+        while (sol) {
+          const int t = __ffsll(static_cast<long long>(sol)) - 1;
+          sol &= sol - 1;
+          const int et = my_codes[t];
+          if (et >= n) { ok = false; continue; }
+          const double2 a = A[t * n + et];
+          a0 += a.x; a1 += a.y;
+          const uint64_t hi = s_mask_hi[t];
+          uint64_t partners = hi & sol;
+          const int pbase = s_pbase[t];
+          while (partners) {
+            const int u = __ffsll(static_cast<long long>(partners)) - 1;
+            partners &= partners - 1;
+            const int eu = my_codes[u];
+            if (eu >= n) { ok = false; continue; }
+            const int p = pbase + __popcll(hi & ((1ULL << u) - 1ULL));
+            const double2 b = __ldg(B + (static_cast<size_t>(p) * n + et) * n + eu);
+            a0 += b.x; a1 += b.y;
+          }
+        }
+        if (!ok) err |= kErrExtraVacancy;
         else {
-          de = acc[0];
-          ea = quartic_barrier_log(de, acc[2] + 2.0 * acc[1]);
+          de = a0;
+          ea = quartic_barrier_log(de, a1);
           rate = exp(-ea * beta);                      // JumpEvent.cpp:13
         }
       }
     }
     if (__any_sync(hmask, err != 0)) break;
-    // lane q now fetches the event whose slot is q
-    int src = 0;
-#pragma unroll
-    for (int q = 0; q < 12; ++q) src = (__shfl_sync(hmask, slot, q, 16) == lane) ? q : src;
-    const double rate_s = __shfl_sync(hmask, rate, src, 16);
+    // events in the reference's order through shared memory: s_rate[slot] = rate, s_lane[slot] = lane
+    if (active) { ord_rate[slot] = rate; ord_lane[slot] = static_cast<uint8_t>(lane); }
+    __syncwarp(hmask);
     // total rate and cumulative probabilities in slot order, sequentially (KineticMcFirstOmp.cpp:55-77)
     double total = 0.0;
 #pragma unroll
-    for (int q = 0; q < 12; ++q) total += __shfl_sync(hmask, rate_s, q, 16);
-    // p_q = rate_q / total (one division per lane, same operands as the reference), then the running sum in order
-    const double prob_s = rate_s / total;
+    for (int q = 0; q < 12; ++q) total += ord_rate[q];
+    // p_q = rate_q / total, then the running sum in slot order (same operands and order as the reference)
+    __syncwarp(hmask);
+    if (active) ord_rate[lane] = ord_rate[lane] / total;        // lane q owns slot q from here on
+    __syncwarp(hmask);
     double cumulative = 0.0, my_cumulative = 0.0;
 #pragma unroll
     for (int q = 0; q < 12; ++q) {
-      cumulative += __shfl_sync(hmask, prob_s, q, 16);
+      cumulative += ord_rate[q];
       if (q == lane) my_cumulative = cumulative;
     }
     // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
@@ -192,22 +289,25 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
     const double dt = -log(u1) / total / kPrefactorHz * corr;
     // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
-    const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> (threadIdx.x & 16)) & 0xFFFu;
+    const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> hshift) & 0xFFFu;
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
-    const int sel_lane = __shfl_sync(hmask, src, sel_slot, 16);
+    const int sel_lane = ord_lane[sel_slot];
     const double sel_ea = __shfl_sync(hmask, ea, sel_lane, 16), sel_de = __shfl_sync(hmask, de, sel_lane, 16);
     const int nx = __shfl_sync(hmask, xj, sel_lane, 16), ny = __shfl_sync(hmask, yj, sel_lane, 16),
               nz = __shfl_sync(hmask, zj, sel_lane, 16);
     const unsigned sel_mig = __shfl_sync(hmask, mig, sel_lane, 16);
     if (lane == 0) {
-      if (tr.from) tr.from[static_cast<int64_t>(w) * n_steps + s] = lat.id_of_coords(X, Y, Z);
-      if (tr.to) tr.to[static_cast<int64_t>(w) * n_steps + s] = lat.id_of_coords(nx, ny, nz);
-      if (tr.slot) tr.slot[static_cast<int64_t>(w) * n_steps + s] = sel_slot;
-      if (tr.dt) tr.dt[static_cast<int64_t>(w) * n_steps + s] = dt;
-      if (tr.Ea) tr.Ea[static_cast<int64_t>(w) * n_steps + s] = sel_ea;
-      if (tr.dE) tr.dE[static_cast<int64_t>(w) * n_steps + s] = sel_de;
-      if (tr.total_rate) tr.total_rate[static_cast<int64_t>(w) * n_steps + s] = total;
-      if (tr.temperature) tr.temperature[static_cast<int64_t>(w) * n_steps + s] = temperature;
+      if (tracing) {
+        const int64_t at = static_cast<int64_t>(w) * n_steps + s;
+        if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
+        if (tr.to) tr.to[at] = lat.id_of_coords(nx, ny, nz);
+        if (tr.slot) tr.slot[at] = sel_slot;
+        if (tr.dt) tr.dt[at] = dt;
+        if (tr.Ea) tr.Ea[at] = sel_ea;
+        if (tr.dE) tr.dE[at] = sel_de;
+        if (tr.total_rate) tr.total_rate[at] = total;
+        if (tr.temperature) tr.temperature[at] = temperature;
+      }
       // 7. Config::LatticeJump: the atom moves into the vacancy, the vacancy into the atom's site
       store_site(lat, o, X, Y, Z, static_cast<uint8_t>(sel_mig));
       store_site(lat, o, nx, ny, nz, static_cast<uint8_t>(vac_code));
