@@ -106,7 +106,7 @@ __global__ void kmc_init_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ
 
 constexpr int kKmcThreads = 128;   // 8 walkers per block
 constexpr int kKmcWalkersPerBlock = kKmcThreads / 16;
-constexpr int kBoxCentre = (3 * 7 + 3) * 4;   // + slot of dz = 0, which depends on the z parity (2 for even Z, 1 for odd Z)
+constexpr int kBoxRows = 49;                  // (dx, dy) rows of the 7 x 7 x 4 box; the vacancy sits in row 24, slot 2 (even Z) or 1 (odd Z)
 
 // The 12 jumps of one vacancy share a 7 x 7 x 7 half-unit box (196 padded cells).  Per step the half-warp scans the box
 // ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
@@ -131,15 +131,18 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   __syncthreads();
   const int lane = threadIdx.x & 15;
   const int wl = threadIdx.x >> 4;                 // walker slot within the block
-  const int w = static_cast<int>((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4);
-  if (w >= n_walkers) return;
+  // Both half-warps of a warp run the same control flow (a dead walker keeps stepping without side effects), so every
+  // shuffle / ballot / syncwarp can use the full mask -- no MATCH.ANY convergence code in the loop.
+  const int w_raw = static_cast<int>((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 4);
+  const int w = w_raw < n_walkers ? w_raw : n_walkers - 1;
   const int hshift = threadIdx.x & 16;
-  const unsigned hmask = 0xFFFFu << hshift;
+  constexpr unsigned hmask = 0xFFFFFFFFu;
   uint8_t *o = occ + w * walker_stride;
-  if (st.error[w] != 0 || st.vacancy[w] < 0) return;
+  bool alive = w_raw < n_walkers && st.error[w] == 0 && st.vacancy[w] >= 0;
+  if (!__any_sync(hmask, alive)) return;
 
   int X, Y, Z;
-  lat.coords_of_id(st.vacancy[w], X, Y, Z);
+  lat.coords_of_id(st.vacancy[w] >= 0 ? st.vacancy[w] : 0, X, Y, Z);
   double time = st.time[w], energy = st.energy[w], temperature = st.temperature[w];
   int64_t steps = st.steps[w];
   const double c_vac = st.c_vacancy[w], c_sol = st.c_solute[w];
@@ -154,6 +157,9 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   uint8_t *ord_lane = s_ord_lane[wl];
   uint8_t *list_cell = s_list_cell[wl], *list_code = s_list_code[wl], *my_codes = s_codes[threadIdx.x];
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
+  const double2 *s_A2v = reinterpret_cast<const double2 *>(s_A2);
+  const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
+  const int b_stride = tab.n_pair_pairs * tab.n_species * tab.n_species;
   uint32_t *ids = s_ids[wl];
   const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
@@ -174,17 +180,30 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const int zp = Z & 1;
     const int64_t base = lat.padded_index(X, Y, Z);
     const int32_t *box = s_box + zp * kBoxCells;
-    const int centre = kBoxCentre + (zp ? 1 : 2);
-    // each lane reads 13 (12) cells; its hits are kept as a bit mask + packed codes and compacted once at the end
+    // each lane reads up to 4 rows of the box (4 consecutive bytes each: one address computation per row); hits are
+    // kept as a bit mask + packed codes (index = 4 * iteration + slot) and compacted once at the end
     unsigned hit_mask = 0;
     unsigned long long hit_codes = 0;           // 4 bits per scanned cell
+    const unsigned solvent4 = solvent * 0x01010101u;
+    const int centre_slot = zp ? 1 : 2;
 #pragma unroll
-    for (int it = 0; it < (kBoxCells + 15) / 16; ++it) {
-      const int c = it * 16 + lane;
-      if (it * 16 + 15 < kBoxCells || c < kBoxCells) {
-        const unsigned code = o[base + box[c]];
-        if (c == centre) { if (code != vac_code) err |= kErrNotVacancy; }
-        else if (code != solvent) { hit_mask |= 1u << it; hit_codes |= static_cast<unsigned long long>(code) << (4 * it); }
+    for (int it = 0; it < (kBoxRows + 15) / 16; ++it) {
+      const int row = it * 16 + lane;
+      if (it * 16 + 15 < kBoxRows || row < kBoxRows) {
+        const uint8_t *p = o + base + box[row * 4];
+        unsigned word = static_cast<unsigned>(p[0]) | (static_cast<unsigned>(p[1]) << 8) | (static_cast<unsigned>(p[2]) << 16) |
+                        (static_cast<unsigned>(p[3]) << 24);
+        if (row == kBoxRows / 2) {                                     // the row through the vacancy itself
+          if (((word >> (8 * centre_slot)) & 0xFFu) != vac_code) err |= kErrNotVacancy;
+          word = (word & ~(0xFFu << (8 * centre_slot))) | (solvent << (8 * centre_slot));
+        }
+        if (word != solvent4) {                                        // rare: at least one non-solvent cell in this row
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const unsigned code = (word >> (8 * sl)) & 0xFFu;
+            if (code != solvent) { hit_mask |= 1u << (4 * it + sl); hit_codes |= static_cast<unsigned long long>(code) << (4 * (4 * it + sl)); }
+          }
+        }
       }
     }
     // exclusive prefix of the per-lane hit counts over the half-warp
@@ -200,7 +219,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     while (hit_mask) {
       const int it = __ffs(static_cast<int>(hit_mask)) - 1;
       hit_mask &= hit_mask - 1;
-      list_cell[pos] = static_cast<uint8_t>(it * 16 + lane);
+      list_cell[pos] = static_cast<uint8_t>(((it >> 2) * 16 + lane) * 4 + (it & 3));       // cell = row * 4 + slot
       list_code[pos] = static_cast<uint8_t>((hit_codes >> (4 * it)) & 0xFULL);
       ++pos;
     }
@@ -225,28 +244,34 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         const int m = static_cast<int>(mig), n = n_species;
         const double *__restrict__ C = tab.pair_C2 + m * 2;
         double a0 = __ldg(C), a1 = __ldg(C + 1);                      // (dE, log E0)
-        const double2 *A = reinterpret_cast<const double2 *>(s_A2) + static_cast<size_t>(m) * kEnvN * n;
-        const double2 *__restrict__ B = B_all + static_cast<size_t>(m) * tab.n_pair_pairs * n * n;
+        const double2 *A = s_A2v + m * (kEnvN * n);                   // 32-bit index arithmetic throughout
+        const double2 *__restrict__ B = B_all + m * b_stride;
         bool ok = true;
-        while (sol) {
-          const int t = __ffsll(static_cast<long long>(sol)) - 1;
-          sol &= sol - 1;
+        // the solute mask is walked as two 32-bit words (single-instruction ffs / popc)
+        uint32_t w_lo = static_cast<uint32_t>(sol), w_hi = static_cast<uint32_t>(sol >> 32);
+        while (w_lo | w_hi) {
+          int t;
+          if (w_lo) { t = __ffs(static_cast<int>(w_lo)) - 1; w_lo &= w_lo - 1; }
+          else { t = 31 + __ffs(static_cast<int>(w_hi)); w_hi &= w_hi - 1; }
           const int et = my_codes[t];
           if (et >= n) { ok = false; continue; }
           const double2 a = A[t * n + et];
           a0 += a.x; a1 += a.y;
-          const uint64_t hi = s_mask_hi[t];
-          uint64_t partners = hi & sol;
-          const int pbase = s_pbase[t];
-          while (partners) {
-            const int u = __ffsll(static_cast<long long>(partners)) - 1;
-            partners &= partners - 1;
+          const uint2 hi = s_mask_hi2[t];
+          uint32_t p_lo = hi.x & w_lo, p_hi = hi.y & w_hi;             // partners u > t still to visit
+          if ((p_lo | p_hi) == 0) continue;
+          const int row = (s_pbase[t] * n + et) * n;
+          do {
+            int u;
+            if (p_lo) { u = __ffs(static_cast<int>(p_lo)) - 1; p_lo &= p_lo - 1; }
+            else { u = 31 + __ffs(static_cast<int>(p_hi)); p_hi &= p_hi - 1; }
             const int eu = my_codes[u];
             if (eu >= n) { ok = false; continue; }
-            const int p = pbase + __popcll(hi & ((1ULL << u) - 1ULL));
-            const double2 b = __ldg(B + (static_cast<size_t>(p) * n + et) * n + eu);
+            // index of pair (t,u) among the pairs of t = number of mask bits below u
+            const int rank = u < 32 ? __popc(hi.x & ((1u << u) - 1u)) : __popc(hi.x) + __popc(hi.y & ((1u << (u - 32)) - 1u));
+            const double2 b = __ldg(B + row + rank * (n * n) + eu);
             a0 += b.x; a1 += b.y;
-          }
+          } while (p_lo | p_hi);
         }
         if (!ok) err |= kErrExtraVacancy;
         else {
@@ -256,7 +281,8 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         }
       }
     }
-    if (__any_sync(hmask, err != 0)) break;
+    if ((__ballot_sync(hmask, err != 0) >> hshift) & 0xFFFFu) alive = false;    // this walker stops; its state is left untouched
+    if (!__any_sync(hmask, alive)) break;
     // events in the reference's order through shared memory: s_rate[slot] = rate, s_lane[slot] = lane
     if (active) { ord_rate[slot] = rate; ord_lane[slot] = static_cast<uint8_t>(lane); }
     __syncwarp(hmask);
@@ -268,12 +294,10 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     __syncwarp(hmask);
     if (active) ord_rate[lane] = ord_rate[lane] / total;        // lane q owns slot q from here on
     __syncwarp(hmask);
-    double cumulative = 0.0, my_cumulative = 0.0;
+    double my_cumulative = 0.0;                 // ((p0 + p1) + p2) + ... + p_lane: the reference's running sum at slot `lane`
 #pragma unroll
-    for (int q = 0; q < 12; ++q) {
-      cumulative += ord_rate[q];
-      if (q == lane) my_cumulative = cumulative;
-    }
+    for (int q = 0; q < 12; ++q)
+      if (q <= lane) my_cumulative += ord_rate[q];
     // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
     double u1, u2;
     if (replay_u1) {
@@ -296,7 +320,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const int nx = __shfl_sync(hmask, xj, sel_lane, 16), ny = __shfl_sync(hmask, yj, sel_lane, 16),
               nz = __shfl_sync(hmask, zj, sel_lane, 16);
     const unsigned sel_mig = __shfl_sync(hmask, mig, sel_lane, 16);
-    if (lane == 0) {
+    if (lane == 0 && alive) {
       if (tracing) {
         const int64_t at = static_cast<int64_t>(w) * n_steps + s;
         if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
@@ -312,20 +336,22 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       store_site(lat, o, X, Y, Z, static_cast<uint8_t>(sel_mig));
       store_site(lat, o, nx, ny, nz, static_cast<uint8_t>(vac_code));
     }
-    time += dt;
-    energy += sel_de;
-    ++steps;
-    X = nx; Y = ny; Z = nz;
+    if (alive) {
+      time += dt;
+      energy += sel_de;
+      ++steps;
+      X = nx; Y = ny; Z = nz;
+    }
     __syncwarp(hmask);
   }
-  if (lane == 0) {
+  if (lane == 0 && w_raw < n_walkers && (alive || err == 0) && st.error[w] == 0) {
     st.vacancy[w] = lat.id_of_coords(X, Y, Z);
     st.time[w] = time;
     st.energy[w] = energy;
     st.steps[w] = steps;
     st.temperature[w] = temperature;
   }
-  if (err) atomicOr(&st.error[w], err);
+  if (err && w_raw < n_walkers) atomicOr(&st.error[w], err);
 }
 
 }  // namespace lmc
