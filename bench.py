@@ -411,7 +411,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--walkers", type=int, default=8192, help="walkers per GPU")
-    ap.add_argument("--hops", type=int, default=512, help="KMC steps per walker per bench step")
+    ap.add_argument("--hops", type=int, default=2048, help="KMC steps per walker per bench step")
     ap.add_argument("--ref-hops", type=int, default=4000, help="reference arm: hops per trajectory per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cmc", action="store_true", help="skip the secondary CMC measurement")
