@@ -20,6 +20,22 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
 
 
+CLI_SRC = os.path.join(CSRC, "host", "lmc_cli.cpp")
+CLI_OUT = os.path.join(HERE, "lmc_b200.exe")
+
+
+def build_cli(force: bool = False) -> str:
+    """`lmc_b200.exe -p <param file>`: the reference's command-line surface (host C++ over the C ABI)."""
+    if not force and os.path.exists(CLI_OUT) and os.path.getmtime(CLI_OUT) > max(os.path.getmtime(CLI_SRC), os.path.getmtime(OUT)):
+        return CLI_OUT
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", CLI_SRC, "-L" + HERE, "-llmc_b200", "-lz", "-Wl,-rpath," + HERE, "-o", CLI_OUT]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building lmc_b200.exe")
+    return CLI_OUT
+
+
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
@@ -29,6 +45,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
+        build_cli()
         return OUT
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -37,6 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed building liblmc_b200.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    build_cli(force=True)
     return OUT
 
 

@@ -171,6 +171,18 @@ class TracedKmcFirstOmp : public mc::KineticMcFirstOmp {
   KmcTrace *trace_{nullptr};
 };
 
+// the driver exactly as shipped (Dump() writes kmc_log.txt and N.cfg.gz), only with a reproducible seed
+class SeededKmcFirstOmp : public mc::KineticMcFirstOmp {
+ public:
+  using mc::KineticMcFirstOmp::KineticMcFirstOmp;
+  void Reseed(uint64_t seed) { generator_.seed(seed); }
+};
+class SeededCmcSerial : public mc::CanonicalMcSerial {
+ public:
+  using mc::CanonicalMcSerial::CanonicalMcSerial;
+  void Reseed(uint64_t seed) { generator_.seed(seed); }
+};
+
 struct SwapTrace {
   int64_t cap{0}, n{0};
   int64_t *a{nullptr}, *b{nullptr};
@@ -691,6 +703,40 @@ double ref_sa(int factor, int solvent_code, const int *solute_codes, const int64
     if (final_energy) *final_energy = sa.energy();
     if (final_temperature) *final_temperature = sa.temperature();
     return t1 - t0;
+  } catch (const std::exception &e) { fail(e); return -1.0; }
+}
+
+// The drivers as shipped, logs and dumps included: after the call `workdir` holds kmc_log.txt / cmc_log.txt, 0.cfg.gz,
+// end.cfg.gz ... exactly as `lmc.exe -p` would have written them (gzip is a pass-through in the shim, so they are text).
+double ref_kmc_first_omp_with_logs(void *config_h, const char *json, const int *codes, int ncodes, const char *tt_file,
+                                   int rate_corrector, double temperature, uint64_t log_dump_steps, uint64_t config_dump_steps,
+                                   uint64_t maximum_steps, uint64_t seed, const char *workdir) {
+  try {
+    ScopedChdir cd(workdir);
+    ScopedQuietCout quiet;
+    omp_set_num_threads(1);
+    SeededKmcFirstOmp kmc(*static_cast<cfg::Config *>(config_h), log_dump_steps, config_dump_steps, maximum_steps, 0, 0, 0.0, 0.0,
+                          temperature, element_set_from_codes(codes, ncodes), json, tt_file ? tt_file : "", rate_corrector != 0,
+                          false, false);
+    kmc.Reseed(seed);
+    const double t0 = now_s();
+    kmc.Simulate();
+    return now_s() - t0;
+  } catch (const std::exception &e) { fail(e); return -1.0; }
+}
+double ref_cmc_serial_with_logs(void *config_h, const char *json, const int *codes, int ncodes, double temperature,
+                                uint64_t log_dump_steps, uint64_t config_dump_steps, uint64_t maximum_steps,
+                                uint64_t thermodynamic_averaging_steps, uint64_t seed, const char *workdir) {
+  try {
+    ScopedChdir cd(workdir);
+    ScopedQuietCout quiet;
+    omp_set_num_threads(1);
+    SeededCmcSerial cmc(*static_cast<cfg::Config *>(config_h), log_dump_steps, config_dump_steps, maximum_steps,
+                        thermodynamic_averaging_steps, 0, 0.0, temperature, element_set_from_codes(codes, ncodes), json);
+    cmc.Reseed(seed);
+    const double t0 = now_s();
+    cmc.Simulate();
+    return now_s() - t0;
   } catch (const std::exception &e) { fail(e); return -1.0; }
 }
 

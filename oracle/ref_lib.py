@@ -51,7 +51,8 @@ def lib():
             getattr(_lib, name).restype = C.c_void_p
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
             getattr(_lib, name).restype = C.c_int64
-        for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_sa", "ref_rate_correction"):
+        for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_sa", "ref_rate_correction",
+                     "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs"):
             getattr(_lib, name).restype = C.c_double
     return _lib
 
@@ -398,6 +399,32 @@ def simulated_annealing(factor, solvent, solute_counts: dict, occ, json_path, in
         raise RuntimeError(_err())
     return dict(seconds=sec, a=a, b=b, energy_before=eb, temperature_before=tb, u=u, final_occ=occ_out, energy0=e0.value,
                 final_energy=fe.value, final_temperature=ft.value)
+
+
+def kmc_first_omp_with_logs(config: RefConfig, json_path, workdir, elements=("Al", "Mg", "Zn"), temperature=500.0,
+                            maximum_steps=100, log_dump_steps=10, config_dump_steps=1000, seed=1, tt_file=None,
+                            rate_corrector=False):
+    """mc::KineticMcFirstOmp::Simulate() as shipped (logs + dumps written into workdir), seeded generator."""
+    _, p, n = _codes(elements)
+    sec = lib().ref_kmc_first_omp_with_logs(config.h, str(json_path).encode(), p, n, str(tt_file).encode() if tt_file else None,
+                                            int(bool(rate_corrector)), C.c_double(temperature), C.c_uint64(int(log_dump_steps)),
+                                            C.c_uint64(int(config_dump_steps)), C.c_uint64(int(maximum_steps)),
+                                            C.c_uint64(int(seed)), str(workdir).encode())
+    if sec < 0:
+        raise RuntimeError(_err())
+    return sec
+
+
+def cmc_serial_with_logs(config: RefConfig, json_path, workdir, elements=("Al", "Mg", "Zn"), temperature=800.0,
+                         maximum_steps=100, log_dump_steps=10, config_dump_steps=1000, thermodynamic_averaging_steps=0, seed=1):
+    _, p, n = _codes(elements)
+    sec = lib().ref_cmc_serial_with_logs(config.h, str(json_path).encode(), p, n, C.c_double(temperature),
+                                         C.c_uint64(int(log_dump_steps)), C.c_uint64(int(config_dump_steps)),
+                                         C.c_uint64(int(maximum_steps)), C.c_uint64(int(thermodynamic_averaging_steps)),
+                                         C.c_uint64(int(seed)), str(workdir).encode())
+    if sec < 0:
+        raise RuntimeError(_err())
+    return sec
 
 
 def uniform_real_stream(seed, n):

@@ -1,0 +1,52 @@
+"""Generate tests/golden/cli_v1/ from the reference itself (oracle/_ref): what `lmc.exe -p kmc_param.txt` with
+simulation_method KineticMcFirstOmp writes for a small seeded run -- kmc_log.txt, 0.cfg.gz, end.cfg.gz -- together with
+the start.cfg it read and the (u1, u2) stream its std::mt19937_64 delivered.  The coefficient file is the K=4/5 set of
+golden_v1.npz.   python tests/golden/make_golden_cli.py"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from latticemontecarlo_b200 import synth  # noqa: E402
+from oracle import ref_lib as R  # noqa: E402
+from tests import helpers as H  # noqa: E402
+
+STEPS, SEED, F = 60, 21, 4
+
+
+def main():
+    assert R.build()
+    out = os.path.join(ROOT, "tests", "golden", "cli_v1")
+    os.makedirs(out, exist_ok=True)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "golden_v1.npz"))
+    work = tempfile.mkdtemp()
+    js = H.golden_json(golden, work)
+    tt = os.path.join(work, "time_temperature.dat")
+    synth.write_time_temperature(tt, points=((0.0, 450.0), (2e-8, 500.0), (1e-6, 650.0)))
+    occ = synth.random_alloy(F, 0.03, 0.03, seed=104)
+    R.RefConfig.fcc(F, occ, reassign=False).write(os.path.join(work, "start.cfg"))
+    cfg = R.RefConfig.read(os.path.join(work, "start.cfg"), reassign=True)
+    trace = R.kmc_first_omp(cfg, js, temperature=500.0, maximum_steps=STEPS, seed=SEED, threads=1, tt_file=tt, rate_corrector=True)
+    R.kmc_first_omp_with_logs(cfg, js, work, temperature=500.0, maximum_steps=STEPS, log_dump_steps=5, config_dump_steps=25,
+                              seed=SEED, tt_file=tt, rate_corrector=True)
+    np.savetxt(os.path.join(out, "uniforms.txt"), np.stack([trace["u1"], trace["u2"]], axis=1), fmt="%.17g")
+    for name in ("start.cfg", "kmc_log.txt", "0.cfg.gz", "25.cfg.gz", "end.cfg.gz", "time_temperature.dat"):
+        dst = name.replace(".cfg.gz", ".cfg.txt")        # the shim's gzip is a pass-through: these are plain text
+        shutil.copy(os.path.join(work, name), os.path.join(out, dst))
+    with open(os.path.join(out, "kmc_param.txt"), "w") as f:
+        f.write("simulation_method KineticMcFirstOmp\njson_coefficients_filename coefficients.json\n"
+                "time_temperature_filename time_temperature.dat\nconfig_filename start.cfg\nlog_dump_steps 5\n"
+                "config_dump_steps 25\nmaximum_steps %d\nthermodynamic_averaging_steps 0\ntemperature 500\n"
+                "element_set Al Mg Zn\nrestart_steps 0\nrestart_energy 0\nrestart_time 0\nrate_corrector true\n"
+                "early_stop false\nsolute_disp false\n# extension of lmc_b200 (ignored by the reference):\n"
+                "replay_uniforms_filename uniforms.txt\n" % STEPS)
+    print(open(os.path.join(out, "kmc_log.txt")).read()[:600])
+    print(sorted(os.listdir(out)))
+
+
+if __name__ == "__main__":
+    main()
