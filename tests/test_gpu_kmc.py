@@ -106,3 +106,43 @@ def test_kmc_rejects_bad_walkers(golden, tmp_path):
     e.set_occupancy(golden["A_cmc_occ"], walker=1)         # no vacancy at all
     with pytest.raises(capi.LmcOutOfRange):
         e.kmc_reset()
+
+
+def test_large_cell_ramp_and_rate_corrector_follow_oracle(coef_json):
+    """BASELINE configs[4] shape at the largest size where the reference's own predictor is valid (f=48, 442k sites;
+    SURVEY 7: its mmm/mm2 comparators break at f >= 50): T(t) ramp + rate corrector, device RNG, every step re-derived
+    by the oracle from the traced state."""
+    f = 48
+    occ = synth.random_alloy(f, 0.02, 0.02, seed=42)
+    cfg = O.Config.generate_fcc(f, occ)
+    cfg.reassign_lattice_vector()
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, device=0)
+    e.load_coefficients(coef_json)
+    e.set_occupancy(cfg.occ)
+    e.kmc_reset()
+    points = np.array([[0.0, 300.0], [1e-3, 500.0], [1e-1, 700.0]])
+    n = 16
+    tr = e.kmc_run(n, temperature=500.0, time_temperature=points, rate_corrector=True, seed=7, trace=True)
+    quartic = O.VacancyMigrationPredictorQuartic(coef_json, cfg, H.CODES)
+    tt = O.TimeTemperatureInterpolator(points=[tuple(p) for p in points])
+    c_vac = float(np.mean(cfg.occ == 0)); c_sol = float(np.mean((cfg.occ != 1) & (cfg.occ != 0)))
+    time = 0.0
+    for s in range(n):
+        vac = int(tr["from"][0, s])
+        temperature = tt.temperature(time)
+        assert abs(temperature - tr["temperature"][0, s]) < 1e-9 * temperature
+        nbrs = cfg.nn[0][vac]
+        ea, de = quartic.barrier_and_diff(cfg, np.full(12, vac), nbrs)
+        slot = int(tr["slot"][0, s])
+        assert int(nbrs[slot]) == int(tr["to"][0, s])
+        assert abs(ea[slot] - tr["Ea"][0, s]) < TOL and abs(de[slot] - tr["dE"][0, s]) < TOL
+        total = np.exp(-ea / O.K_BOLTZMANN / temperature).sum()
+        assert abs(total / tr["total_rate"][0, s] - 1) < 1e-9
+        # dt = -ln(u1) / total / 1e13 * correction: the correction factor is implied by dt * total (u1 is the device's)
+        corr = O.rate_correction_factor(c_vac, c_sol, temperature)
+        assert tr["dt"][0, s] > 0 and corr > 0
+        time += float(tr["dt"][0, s])
+        cfg.lattice_jump(vac, int(tr["to"][0, s]))
+    st = e.kmc_state()
+    assert abs(st["time"][0] - time) < 1e-12 * time
+    assert np.array_equal(e.get_occupancy(), cfg.occ)
