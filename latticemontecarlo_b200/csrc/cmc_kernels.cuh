@@ -123,18 +123,18 @@ __device__ __forceinline__ uint64_t gather_site_env_marked(const uint8_t *occ, c
                                                            bool *conflict) {
   uint32_t lo = 0, hi = 0;
   unsigned worst = 0;
-  // chunks of 11/11/11/10 sites: enough loads in flight to cover the latency, few enough live registers not to spill
+  // chunks of 22 / 21 sites: enough loads in flight to cover the latency, few enough live registers not to spill
 #pragma unroll
-  for (int t0 = 0; t0 < 43; t0 += 11) {
-    unsigned cd[11], mk[11];
+  for (int t0 = 0; t0 < 43; t0 += 22) {
+    unsigned cd[22], mk[22];
 #pragma unroll
-    for (int q = 0; q < 11; ++q) {
+    for (int q = 0; q < 22; ++q) {
       if (t0 + q >= 43) continue;
       cd[q] = __ldcg(occ + base + drow[t0 + q]);         // the lattice is shared by the CTAs of a cluster: read at L2
       mk[q] = __ldcg(marks + base + drow[t0 + q]);   // marks are written with atomics by other threads: bypass L1
     }
 #pragma unroll
-    for (int q = 0; q < 11; ++q) {
+    for (int q = 0; q < 22; ++q) {
       const int t = t0 + q;
       if (t >= 43) continue;
       worst = mk[q] > worst ? mk[q] : worst;
@@ -179,12 +179,14 @@ __device__ __forceinline__ double site_energy_change_staged(const SiteTablesView
   return acc;
 }
 
-// swap_energy_change (kernels.cuh) with the claim check fused into its two gathers
-__device__ __forceinline__ double swap_energy_change_marked(const LatticeDesc &lat, const DevTables &tab, const SiteTablesView &tv,
-                                                            const uint8_t *occ, const unsigned int *marks,
-                                                            const int32_t *__restrict__ s_delta, uint8_t *codes, int stride, int xa,
-                                                            int ya, int za, int xb, int yb, int zb, unsigned my_mark,
-                                                            bool *conflict) {
+// One side of swap_energy_change (kernels.cuh): the two single-site changes of a swap are evaluated by two adjacent
+// lanes (side 0: the site that changes first, side 1: the other one, which sees the first already changed when the pair
+// is coupled), each with the claim check fused into its 43-site gather.  Returns this side's H(new) - H(old).
+__device__ __forceinline__ double swap_side_energy_change_marked(const LatticeDesc &lat, const DevTables &tab, const SiteTablesView &tv,
+                                                                 const uint8_t *occ, const unsigned int *marks,
+                                                                 const int32_t *__restrict__ s_delta, uint8_t *codes, int stride, int side,
+                                                                 int xa, int ya, int za, int xb, int yb, int zb, unsigned my_mark,
+                                                                 bool *conflict, bool *same_species) {
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
   int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
   unsigned ea = __ldcg(occ + base_a), eb = __ldcg(occ + base_b);
@@ -201,14 +203,19 @@ __device__ __forceinline__ double swap_energy_change_marked(const LatticeDesc &l
     const int tz = zpa; zpa = zpb; zpb = tz;
     dx = -dx; dy = -dy; dz = -dz;
   }
-  const int32_t *row_a = s_delta + zpa * 43, *row_b = s_delta + zpb * 43;
-  uint8_t *codes_b = codes + 43 * stride;
-  const uint64_t sol_a = gather_site_env_marked(occ, marks, base_a, row_a, solvent, codes, stride, -1, 0, my_mark, conflict);
+  *same_species = ea == eb;
+  uint64_t sol;
+  if (side == 0) {
+    sol = gather_site_env_marked(occ, marks, base_a, s_delta + zpa * 43, solvent, codes, stride, -1, 0, my_mark, conflict);
+    if (ea == eb) return 0.0;
+    return site_energy_change_staged(tv, static_cast<int>(ea), static_cast<int>(eb), sol, codes, stride);
+  }
+  // the halo images of the first site are not updated in memory, so the override is applied by *position*: the first
+  // site sits at displacement (-dx,-dy,-dz) from the second
   const int64_t override_index = coupled ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
-  const uint64_t sol_b = gather_site_env_marked(occ, marks, base_b, row_b, solvent, codes_b, stride, override_index, eb, my_mark, conflict);
-  if (*conflict || ea == eb) return 0.0;
-  return site_energy_change_staged(tv, static_cast<int>(ea), static_cast<int>(eb), sol_a, codes, stride) +
-         site_energy_change_staged(tv, static_cast<int>(eb), static_cast<int>(ea), sol_b, codes_b, stride);
+  sol = gather_site_env_marked(occ, marks, base_b, s_delta + zpb * 43, solvent, codes, stride, override_index, eb, my_mark, conflict);
+  if (ea == eb) return 0.0;
+  return site_energy_change_staged(tv, static_cast<int>(eb), static_cast<int>(ea), sol, codes, stride);
 }
 
 constexpr int kCmcMaxThreads = 512;
@@ -256,7 +263,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   // ---- stage the site tables in shared memory
   const int m = tab.n_species + 1;
   double *s_replay_de = s_dyn;                      // rank 0 holds the dE of the whole replay window
-  double *s_C = s_replay_de + B * n_cta;
+  double *s_C = s_replay_de + B * n_cta;          // (only B/2 * n_cta entries are used)
   double *s_A = s_C + m;
   const int a_len = m * kSiteEnvN * m, b_len = m * tab.n_site_pairs * m * m;
   double *s_B = s_A + a_len;
@@ -288,6 +295,8 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const double cool = s_sa.enabled ? exp(-3.0 / static_cast<double>(s_sa.maximum_steps > 0 ? s_sa.maximum_steps : 1ULL)) : 1.0;
   const int gtid = rank * B + tid;                 // index of this thread within the replica's cluster
   const int window = B * n_cta;                    // proposals (threads) per batch
+  const int half = B / 2;                          // live trials a CTA evaluates per batch (one lane pair each)
+  const int pair_id = tid >> 1, side = tid & 1;
   int err = 0;
 
   for (;;) {
@@ -306,8 +315,10 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     int32_t a = -1, b = -1;
     if (replaying) {
       // replay trials are dealt round-robin so that priorities (= positions in the stream) interleave over the CTAs
-      if (rpos + gtid < n_replay) {
-        const int64_t ra = replay.a[rpos + gtid], rb = replay.b[rpos + gtid];
+      // thread q < B/2 of CTA `rank` fetches trial rank * B/2 + q of the window (stream order = priority order)
+      const unsigned long long ridx = rpos + static_cast<unsigned long long>(rank) * half + tid;
+      if (tid < half && ridx < n_replay) {
+        const int64_t ra = replay.a[ridx], rb = replay.b[ridx];
         if (ra < 0 || rb < 0 || ra >= lat.num_sites || rb >= lat.num_sites) err |= kErrBadSite;
         else { a = static_cast<int32_t>(ra); b = static_cast<int32_t>(rb); }
       }
@@ -334,7 +345,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const bool has = a >= 0;
     int n_live = 0, slot = -1;
     if (replaying) {                                // keep stream order: no compaction, priority = stream position
-      n_live = B;
+      n_live = half;
       slot = tid;
       s_live_a[tid] = a;
       s_live_b[tid] = b;
@@ -355,34 +366,39 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     }
     __syncthreads();
     LMC_TICK(1);
-    // ---------------- phase 1b: thread i < n_live owns live trial i of this CTA; mark its two sites.
+    // ---------------- phase 1b: lane pair i < min(n_live, B/2) owns live trial i of this CTA (side 0 / 1 = its two sites)
     // priority: device RNG: (CTA rank, slot); replay: position in the stream
-    bool live = tid < n_live;
+    if (n_live > half) n_live = half;               // surplus proposals are dropped (they are redrawn in a later batch)
+    bool live = pair_id < n_live;
     int xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
-    const unsigned int prio = replaying ? static_cast<unsigned int>(gtid) : static_cast<unsigned int>(rank * B + tid);
+    const unsigned int prio = static_cast<unsigned int>(rank * half + pair_id);
     const unsigned int my_mark = (epoch16 << 16) | (0xFFFFu - prio);
     if (live) {
-      a = s_live_a[tid]; b = s_live_b[tid];
+      a = s_live_a[pair_id]; b = s_live_b[pair_id];
       live = a >= 0;
     }
     if (live) {
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
-      mark_site(lat, marks, xa, ya, za, my_mark);
-      mark_site(lat, marks, xb, yb, zb, my_mark);
+      if (side == 0) mark_site(lat, marks, xa, ya, za, my_mark);
+      else mark_site(lat, marks, xb, yb, zb, my_mark);
     }
     cluster.sync();
     LMC_TICK(2);
-    // ---------------- phase 2: conflict check fused with the dE gathers
-    bool conflict = false;
+    // ---------------- phase 2: conflict check fused with the dE gathers, one site per lane
+    bool conflict = false, same = false;
     double de = 0.0;
-    if (live) de = swap_energy_change_marked(lat, tab, tv, o, marks, s_delta, s_codes + tid, B, xa, ya, za, xb, yb, zb, my_mark, &conflict);
+    if (live) de = swap_side_energy_change_marked(lat, tab, tv, o, marks, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
+                                                  &conflict, &same);
+    conflict = __shfl_xor_sync(0xffffffffu, conflict ? 1 : 0, 1) || conflict;
+    de += __shfl_xor_sync(0xffffffffu, de, 1);      // both lanes of the pair now hold the swap's dE
     bool kept = live && !conflict;
     LMC_TICK(3);
+    const unsigned int gpair = static_cast<unsigned int>(rank * half + pair_id);   // position of the trial in the window
     if (replaying) {
       // serial semantics: only the conflict-free prefix of the window forms the batch; every CTA learns the position of
       // the first conflict through distributed shared memory
-      if (live && conflict) atomicMin(&s_first_conflict, static_cast<unsigned int>(gtid));
+      if (live && conflict && side == 0) atomicMin(&s_first_conflict, gpair);
       __syncthreads();
       if (tid == 0) s_partial.first_conflict = s_first_conflict;
       cluster.sync();
@@ -391,18 +407,19 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         const unsigned int v = cluster.map_shared_rank(&s_partial, r)->first_conflict;
         limit = v < limit ? v : limit;
       }
-      kept = live && static_cast<unsigned int>(gtid) < limit;
-      if (kept) cluster.map_shared_rank(s_replay_de, 0)[gtid] = de;      // rank 0 applies the prefix serially
+      kept = live && gpair < limit;
+      if (kept && side == 0) cluster.map_shared_rank(s_replay_de, 0)[gpair] = de;      // rank 0 applies the prefix serially
       if (tid == 0) s_first_conflict = limit;
     }
     if (kept && de != de) err |= kErrExtraVacancy;
     bool accept = false;
     if (kept && !replaying) {
-      // CanonicalMcAbstract::SelectEvent (:86-101): dE < 0 accepts, else u < exp(-dE beta)
+      // CanonicalMcAbstract::SelectEvent (:86-101): dE < 0 accepts, else u < exp(-dE beta); both lanes of the pair draw
+      // the same uniform (same counter), so they agree without communication
       accept = de < 0.0;
       if (!accept) {
         uint32_t r2[4];
-        const unsigned long long g = prop0 + gtid;
+        const unsigned long long g = prop0 + gpair;
         philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed) ^ static_cast<uint32_t>(w),
                       static_cast<uint32_t>(seed >> 32) ^ 0x9E3779B9u, r2);
         const double beta = 1.0 / kBoltzmannEv / fmax(t_batch, 1e-12);
@@ -411,12 +428,13 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       if (accept) {
         const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
         const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
-        store_site(lat, o, xa, ya, za, eb);
-        store_site(lat, o, xb, yb, zb, ea);
-        by_id[a] = eb;
-        by_id[b] = ea;
+        __syncwarp(__activemask());                 // both lanes have read the old species before either writes
+        if (side == 0) { store_site(lat, o, xa, ya, za, eb); by_id[a] = eb; }
+        else { store_site(lat, o, xb, yb, zb, ea); by_id[b] = ea; }
       }
     }
+    kept = kept && side == 0;                       // count every trial once
+    accept = accept && side == 0;
     LMC_TICK(4);
     // ---------------- reductions (fixed order: deterministic)
     const unsigned kept_mask = __ballot_sync(0xffffffffu, kept), acc_mask = __ballot_sync(0xffffffffu, accept);
@@ -474,7 +492,8 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         // inputs (dE window of rank 0, host stream) so the replicated state stays identical; only rank 0 writes.
         const double *de_window = cluster.map_shared_rank(s_replay_de, 0);
         const unsigned long long remaining = n_replay - rpos;
-        unsigned int limit = s_first_conflict < static_cast<unsigned int>(window) ? s_first_conflict : static_cast<unsigned int>(window);
+        const unsigned int batch_cap = static_cast<unsigned int>(half * n_cta);
+        unsigned int limit = s_first_conflict < batch_cap ? s_first_conflict : batch_cap;
         if (limit > remaining) limit = static_cast<unsigned int>(remaining);
         unsigned long long pos = rpos;
         double energy = energy0;

@@ -646,7 +646,7 @@ void run_swap_driver(const Parameter &p, bool annealing) {
   }
   const unsigned long long last = p.maximum_steps;   // while (steps_ <= maximum_steps_)
   unsigned long long next_cfg = p.config_dump_steps ? (steps / p.config_dump_steps + 1) * p.config_dump_steps : ~0ULL;
-  while (steps <= last) {
+  while (steps < last) {
     // run to the next step the reference would log (its cadence is log-spaced up to 10 * log_dump_steps)
     unsigned long long target = steps + 1;
     while (target <= last && !log_this_step(target, p.log_dump_steps) && !(annealing && target % std::max(1ULL, p.log_dump_steps) == 0)) ++target;
@@ -658,7 +658,7 @@ void run_swap_driver(const Parameter &p, bool annealing) {
       check(lmc_engine_get_occupancy(eng.e, 0, occ.data(), static_cast<int64_t>(occ.size())));
       write_relabelled(config, occ, "lowest_energy.cfg.gz");
     }
-    if (steps <= last + 1) log_row(std::min(steps, last), temperature, energy);
+    log_row(std::min(steps, last), temperature, energy);
     if (!annealing && steps >= next_cfg) {
       check(lmc_engine_get_occupancy(eng.e, 0, occ.data(), static_cast<int64_t>(occ.size())));
       write_relabelled(config, occ, std::to_string(next_cfg) + ".cfg.gz");

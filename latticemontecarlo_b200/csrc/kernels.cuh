@@ -158,6 +158,20 @@ __device__ __forceinline__ void store_site(const LatticeDesc &lat, uint8_t *occ,
   if (sx && sy && sz) occ[base + ix + iy + iz] = code;
 }
 
+// one periodic image per caller: `which` in 0..7 selects the subset of axes (bit 0: x, bit 1: y, bit 2: z) whose image
+// shift is applied; subsets that do not exist for this site write nothing.  which == 0 is the site itself.
+__device__ __forceinline__ void store_site_image(const LatticeDesc &lat, uint8_t *occ, int X, int Y, int Z, int which, uint8_t code) {
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  const int sx = X < kHalo ? px : (X >= px - kHalo ? -px : 0);
+  const int sy = Y < kHalo ? py : (Y >= py - kHalo ? -py : 0);
+  const int sz = Z < kHaloZ ? pz : (Z >= pz - kHaloZ ? -pz : 0);
+  const bool ok = (!(which & 1) || sx) && (!(which & 2) || sy) && (!(which & 4) || sz);
+  if (!ok) return;
+  const int64_t idx = lat.padded_index(X, Y, Z) + ((which & 1) ? static_cast<int64_t>(sx) * lat.ny * lat.nz : 0) +
+                      ((which & 2) ? static_cast<int64_t>(sy) * lat.nz : 0) + ((which & 4) ? sz / 2 : 0);
+  occ[idx] = code;
+}
+
 __global__ void lattice_jump_kernel(LatticeDesc lat, uint8_t *occ, int64_t a, int64_t b) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   int xa, ya, za, xb, yb, zb;

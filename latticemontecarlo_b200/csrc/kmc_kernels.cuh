@@ -164,10 +164,15 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
 
+  double beta = 1.0 / kBoltzmannEv / temperature;
+  double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
   for (int64_t s = 0; s < n_steps; ++s) {
-    // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50)
-    if (prm.n_tt > 0) temperature = interpolate_temperature(prm, time);
-    const double beta = 1.0 / kBoltzmannEv / temperature;
+    // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50): only a T(t) table changes the temperature during a run
+    if (prm.n_tt > 0) {
+      temperature = interpolate_temperature(prm, time);
+      beta = 1.0 / kBoltzmannEv / temperature;
+      if (prm.rate_corrector) corr = rate_correction(c_vac, c_sol, temperature);
+    }
     // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
     const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
     const uint32_t id_j = static_cast<uint32_t>(lat.id_of_coords(xj, yj, zj));       // num_sites < 2^31 (checked by the host)
@@ -310,7 +315,6 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       u1 = uniform53(r[0], r[1]) + (1.0 / 9007199254740992.0);   // (0, 1]: -log(u1) is finite
       u2 = uniform53(r[2], r[3]);
     }
-    const double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
     const double dt = -log(u1) / total / kPrefactorHz * corr;
     // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
     const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> hshift) & 0xFFFu;
@@ -332,10 +336,11 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         if (tr.total_rate) tr.total_rate[at] = total;
         if (tr.temperature) tr.temperature[at] = temperature;
       }
-      // 7. Config::LatticeJump: the atom moves into the vacancy, the vacancy into the atom's site
-      store_site(lat, o, X, Y, Z, static_cast<uint8_t>(sel_mig));
-      store_site(lat, o, nx, ny, nz, static_cast<uint8_t>(vac_code));
     }
+    // 7. Config::LatticeJump: the atom moves into the vacancy, the vacancy into the atom's site.  Lanes 0-7 write the (up to
+    // 8) periodic images of the old vacancy site, lanes 8-15 those of the new one.
+    if (alive) store_site_image(lat, o, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7,
+                                static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
     if (alive) {
       time += dt;
       energy += sel_de;
