@@ -247,7 +247,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   __shared__ double s_warp_sum[kCmcMaxThreads / 32];
   __shared__ unsigned int s_warp_cnt[kCmcMaxThreads / 32], s_warp_acc[kCmcMaxThreads / 32], s_warp_live[kCmcMaxThreads / 32];
   __shared__ unsigned int s_first_conflict;
-  __shared__ CmcPartial s_partial;
+  __shared__ CmcPartial s_partial2[2];            // double buffered by batch parity: a CTA may run one phase ahead
   __shared__ double s_energy, s_temperature;
   __shared__ unsigned long long s_steps, s_accepted, s_proposals, s_epoch, s_replay_pos;
   __shared__ SaSchedule s_sa;
@@ -302,6 +302,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   for (;;) {
     // ---------------- batch bookkeeping (identical in every CTA of the cluster)
     const unsigned long long steps0 = s_steps, epoch = s_epoch + 1, prop0 = s_proposals, rpos = s_replay_pos;
+    CmcPartial &s_partial = s_partial2[epoch & 1ULL];
     const double t_batch = s_temperature, energy0 = s_energy;
     if (replaying ? (rpos >= n_replay) : (steps0 >= target_steps)) break;
     __syncthreads();
@@ -533,9 +534,10 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       }
       s_epoch = epoch;
     }
-    // the next batch reads occupancy written by other CTAs in this one, and must not overwrite s_partial / the dE window
-    // before every CTA has read them
-    cluster.sync();
+    // No third barrier: the swaps of this batch were stored before the barrier above (visible to every CTA's next
+    // proposals), the partial sums are double buffered, and the dE window of a replay batch is only rewritten after the
+    // next batch's first barrier, which a CTA cannot pass before every CTA has finished reading here.
+    __syncthreads();
     LMC_TICK(5);
     if (any_err) break;
   }

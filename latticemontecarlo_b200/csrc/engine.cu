@@ -718,12 +718,6 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
   if (params.temperatures) std::copy(params.temperatures, params.temperatures + nw, temps.begin());
   LMC_CUDA(cudaMemcpyAsync(d_cmc_temperature, temps.data(), nw * 8, cudaMemcpyHostToDevice, stream));
   int threads = params.batch_size;
-  if (threads <= 0) {
-    // the number of mutually non-interfering survivors peaks near N / (2 * 43 * 2) live trials per batch
-    threads = 32;
-    while (threads < kCmcMaxThreads && threads * 172 < lat.num_sites) threads *= 2;
-  }
-  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
   CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
   CmcReplay rp{};
   const bool replaying = n_replay > 0;
@@ -743,7 +737,6 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
     rp = CmcReplay{d_a, d_b, d_u, d_de, d_eb, d_tb, d_acc};
     first_walker = replay_walker;
     n_run = 1;
-    threads = std::min(threads, 128);
   } else {
     if (n_trials <= 0) return;
     std::vector<unsigned long long> steps(nw);
@@ -759,35 +752,52 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
     st_run.energy += first_walker; st_run.steps += first_walker; st_run.accepted += first_walker; st_run.proposals += first_walker;
     st_run.epoch += first_walker; st_run.sa += first_walker; st_run.error += first_walker;
   }
-  // cluster size: CTAs that share one replica's batch.  Many replicas -> 1; few replicas on a big lattice -> up to 8
+  // Launch shape.  The number of mutually non-interfering trials of a batch peaks near N / (2 * 43 * 2) live trials; a
+  // trial occupies one lane pair, and the scattered gathers are L1-wavefront bound per SM, so a replica is spread over as
+  // many CTAs as the device allows (cluster of up to 16 on B200) with correspondingly small CTAs.
+  int sms = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   int cluster = 1;
-  if (!replaying || true) {
-    int sms = 0;
-    LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    while (cluster < 8 && static_cast<int64_t>(n_run) * cluster * 2 <= sms && static_cast<int64_t>(threads) * cluster * 172 < lat.num_sites * 2) cluster *= 2;
+  while (cluster < 16 && static_cast<int64_t>(n_run) * cluster * 2 <= sms) cluster *= 2;
+  if (threads <= 0) {
+    const int64_t want_pairs = std::max<int64_t>(16, lat.num_sites / 172);             // the non-interference optimum
+    threads = 64;
+    while (threads < kCmcMaxThreads && static_cast<int64_t>(threads) / 2 * cluster < want_pairs) threads *= 2;
+    while (cluster > 1 && static_cast<int64_t>(threads) / 2 * (cluster / 2) >= want_pairs) cluster /= 2;   // small lattices: fewer CTAs
   }
-  if (params.batch_size <= 0 && cluster > 1) threads = std::max(128, threads / 2);
+  if (replaying) threads = std::min(threads, 128);
+  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
   // dynamic shared memory: replay dE window, site tables, per-thread species staging (2 x 43 bytes per thread)
   const int m = species.n + 1;
   const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
-  const size_t fixed = (static_cast<size_t>(threads) * cluster + m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
   int max_optin = 0;
   LMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-  const int stage_b = (fixed + b_len * 8 + 16 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
-  const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
-  LMC_CUDA(cudaFuncSetAttribute(cmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  LMC_CUDA(cudaFuncSetAttribute(cmc_run_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(n_run * cluster));
-  cfg.blockDim = dim3(static_cast<unsigned>(threads));
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  int stage_b = 0;
+  for (;; cluster /= 2) {
+    const size_t fixed = (static_cast<size_t>(threads) * cluster + m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
+    stage_b = (fixed + b_len * 8 + 16 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
+    const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
+    LMC_CUDA(cudaFuncSetAttribute(cmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    cfg.gridDim = dim3(static_cast<unsigned>(n_run * cluster));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = static_cast<unsigned>(cluster);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // a cluster that cannot be co-scheduled on this device (GPC shape, MIG slice) is halved until it can
+    int active = 0;
+    const cudaError_t q = cudaOccupancyMaxActiveClusters(&active, cmc_run_kernel, &cfg);
+    if (q == cudaSuccess && active > 0) break;
+    (void)cudaGetLastError();
+    if (cluster == 1) { LMC_CUDA(q); throw std::runtime_error("cmc_run_kernel does not fit on this device"); }
+  }
   time_begin();
   LMC_CUDA(cudaLaunchKernelEx(&cfg, cmc_run_kernel, lat, tab, d_occ + static_cast<int64_t>(first_walker) * lat.padded_size, lat.padded_size,
                               d_cmc_mirror + static_cast<size_t>(first_walker) * lat.num_sites,
