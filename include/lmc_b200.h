@@ -148,6 +148,17 @@ int lmc_kmc_reset(lmc_engine *engine);
  * Philox stream by caller-supplied uniforms: u1 -> residence time, u2 -> event selection, in the reference's draw order. */
 int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u1,
                 const double *replay_u2, const lmc_kmc_trace *trace);
+/* Second-order ("chain") KMC: mc::KineticMcChainOmpi::Simulate (mc/src/KineticMcChainOmpi.cpp:56-152,
+ * mc/include/KineticMcAbstract.h:65-143; the method script/kmc_param.txt:1 selects).  Per step and walker, for each of
+ * the 12 neighbours i of the vacancy site k (the reference's 12 MPI ranks, ascending lattice id): the 12 jumps i -> l in
+ * the state "vacancy at i" (144 barrier evaluations), the event k -> i as the reverse of i -> k, the eight MpiData sums in
+ * rank order, the second-order residence time t_2 (an expectation: no uniform is consumed for it) and the second-order
+ * event probabilities that exclude an immediate return to the site the vacancy came from (previous_j_lattice_id_, which
+ * starts as first neighbour 0 of the vacancy and is kept per walker between calls; lmc_kmc_reset and lmc_kmc_run clear
+ * it).  One uniform per step: replay_u (host, [n_walkers][n_steps], optional) replaces the Philox stream.  The trace has
+ * the meaning of lmc_kmc_run's (Ea / dE of the chosen k -> i event, total_rate = total_rate_k_). */
+int lmc_kmc_chain_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u,
+                      const lmc_kmc_trace *trace);
 /* per-walker state after the last run (host arrays [n_walkers], any may be NULL): McAbstract::time_, energy_, steps_ */
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy,
                       double *temperature);

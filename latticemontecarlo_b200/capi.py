@@ -260,8 +260,9 @@ class Engine:
         _check(lib().lmc_kmc_reset(self.h))
 
     def kmc_run(self, n_steps, temperature=500.0, temperatures=None, time_temperature=None, rate_corrector=False, seed=0,
-                replay_u1=None, replay_u2=None, trace=False):
-        """Advance every walker by n_steps. Returns the trace dict (arrays [n_walkers, n_steps]) if trace else None."""
+                replay_u1=None, replay_u2=None, trace=False, second_order=False):
+        """Advance every walker by n_steps (first-order KMC; second_order=True: mc::KineticMcChainOmpi, one uniform per step
+        passed as replay_u2).  Returns the trace dict (arrays [n_walkers, n_steps]) if trace else None."""
         keep = []
         prm = KmcParams()
         prm.temperature = float(temperature)
@@ -279,6 +280,7 @@ class Engine:
         u1 = u2 = None
         if replay_u1 is not None:
             u1 = np.ascontiguousarray(replay_u1, dtype=np.float64).reshape(self.n_walkers, n_steps)
+        if replay_u2 is not None:
             u2 = np.ascontiguousarray(replay_u2, dtype=np.float64).reshape(self.n_walkers, n_steps)
         tr, out = None, None
         if trace:
@@ -288,8 +290,15 @@ class Engine:
                 out[k] = np.zeros(shape, np.float64)
             tr = KmcTrace(out["from"].ctypes.data, out["to"].ctypes.data, out["slot"].ctypes.data, out["dt"].ctypes.data,
                           out["Ea"].ctypes.data, out["dE"].ctypes.data, out["total_rate"].ctypes.data, out["temperature"].ctypes.data)
-        _check(lib().lmc_kmc_run(self.h, C.byref(prm), C.c_int64(int(n_steps)), _p(u1), _p(u2), C.byref(tr) if tr else None))
+        if second_order:
+            _check(lib().lmc_kmc_chain_run(self.h, C.byref(prm), C.c_int64(int(n_steps)), _p(u2), C.byref(tr) if tr else None))
+        else:
+            _check(lib().lmc_kmc_run(self.h, C.byref(prm), C.c_int64(int(n_steps)), _p(u1), _p(u2), C.byref(tr) if tr else None))
         return out
+
+    def kmc_chain_run(self, n_steps, replay_u=None, **kw):
+        """mc::KineticMcChainOmpi::Simulate over all walkers (lmc_kmc_chain_run)."""
+        return self.kmc_run(n_steps, replay_u2=replay_u, second_order=True, **kw)
 
     def kmc_state(self):
         n = self.n_walkers

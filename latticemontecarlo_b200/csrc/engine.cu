@@ -557,12 +557,13 @@ void Engine::kmc_reset() {
     d_kmc_vacancy = dev_alloc<int64_t>(n); d_kmc_steps = dev_alloc<int64_t>(n);
     d_kmc_time = dev_alloc<double>(n); d_kmc_energy = dev_alloc<double>(n); d_kmc_temperature = dev_alloc<double>(n);
     d_kmc_cvac = dev_alloc<double>(n); d_kmc_csol = dev_alloc<double>(n); d_kmc_error = dev_alloc<int32_t>(n);
+    d_kmc_previous = dev_alloc<int64_t>(n);
     for (void *p : {static_cast<void *>(d_kmc_vacancy), static_cast<void *>(d_kmc_steps), static_cast<void *>(d_kmc_time),
                     static_cast<void *>(d_kmc_energy), static_cast<void *>(d_kmc_temperature), static_cast<void *>(d_kmc_cvac),
-                    static_cast<void *>(d_kmc_csol), static_cast<void *>(d_kmc_error)})
+                    static_cast<void *>(d_kmc_csol), static_cast<void *>(d_kmc_error), static_cast<void *>(d_kmc_previous)})
       device_allocs.push_back(p);
   }
-  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error};
+  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error, d_kmc_previous};
   const int al = species.code_of_enum[1];   // RateCorrector counts "not Al, not X" as solute (KineticMcAbstract.cpp:35)
   kmc_init_kernel<<<static_cast<unsigned>(n_walkers), 256, 0, stream>>>(lat, d_occ, lat.padded_size, st, species.n, al, 1);
   LMC_CUDA(cudaGetLastError());
@@ -574,12 +575,14 @@ void Engine::kmc_reset() {
   kmc_ready = true;
 }
 
-void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace) {
+void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace,
+                     bool second_order) {
   require_device();
   require_coefficients();
   if (!pair_tables.has_barrier) throw std::invalid_argument("the coefficient file has no per-element quartic blocks");
   if (!kmc_ready) kmc_reset();
-  if ((u1 == nullptr) != (u2 == nullptr)) throw std::invalid_argument("replay needs both u1 and u2");
+  if (!second_order && (u1 == nullptr) != (u2 == nullptr)) throw std::invalid_argument("replay needs both u1 and u2");
+  if (second_order) u1 = u2;      // one uniform per step (SelectEvent); staged once below
   if (n_steps <= 0) return;
   const size_t nw = static_cast<size_t>(n_walkers), total = nw * static_cast<size_t>(n_steps);
   // temperatures
@@ -592,7 +595,7 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   const size_t n_tt = static_cast<size_t>(std::max(0, params.n_time_temperature));
   const bool tracing = trace != nullptr;
   size_t bytes = 2 * n_tt * 8 + 64;
-  if (u1) bytes += 2 * total * 8;
+  if (u2) bytes += 2 * total * 8;
   if (tracing) bytes += total * (8 + 8 + 4 + 5 * 8) + 64;
   char *d = static_cast<char *>(scratch(bytes));
   double *d_tt_time = reinterpret_cast<double *>(d), *d_tt_temp = d_tt_time + n_tt;
@@ -602,9 +605,9 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     LMC_CUDA(cudaMemcpyAsync(d_tt_temp, params.tt_temperature, n_tt * 8, cudaMemcpyHostToDevice, stream));
   }
   double *d_u1 = nullptr, *d_u2 = nullptr;
-  if (u1) {
+  if (u2) {
     d_u1 = cursor; d_u2 = d_u1 + total; cursor = d_u2 + total;
-    LMC_CUDA(cudaMemcpyAsync(d_u1, u1, total * 8, cudaMemcpyHostToDevice, stream));
+    if (!second_order) LMC_CUDA(cudaMemcpyAsync(d_u1, u1, total * 8, cudaMemcpyHostToDevice, stream));
     LMC_CUDA(cudaMemcpyAsync(d_u2, u2, total * 8, cudaMemcpyHostToDevice, stream));
   }
   KmcTraceDev tr{};
@@ -618,7 +621,7 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     tr.temperature = trace->temperature ? cursor : nullptr; cursor += total;
     tr.slot = trace->slot ? reinterpret_cast<int32_t *>(cursor) : nullptr;
   }
-  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error};
+  KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error, d_kmc_previous};
   KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
@@ -626,7 +629,13 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   const size_t kmc_smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
   LMC_CUDA(cudaFuncSetAttribute(kmc_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
   time_begin();
-  kmc_run_kernel<<<blocks, kKmcThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+  if (second_order) {
+    LMC_CUDA(cudaFuncSetAttribute(kmc_chain_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
+    kmc_chain_run_kernel<<<static_cast<unsigned>(n_walkers), kChainThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st,
+                                                                                               prm, n_steps, d_u2, tr);
+  } else {
+    kmc_run_kernel<<<blocks, kKmcThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+  }
   time_end();
   LMC_CUDA(cudaGetLastError());
   if (tracing) {
@@ -1017,7 +1026,14 @@ int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_step
                 const double *replay_u2, const lmc_kmc_trace *trace) {
   return guard([&] {
     if (!params) throw std::invalid_argument("null params");
-    engine->impl->kmc_run(*params, n_steps, replay_u1, replay_u2, trace);
+    engine->impl->kmc_run(*params, n_steps, replay_u1, replay_u2, trace, false);
+  });
+}
+int lmc_kmc_chain_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u,
+                      const lmc_kmc_trace *trace) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    engine->impl->kmc_run(*params, n_steps, nullptr, replay_u, trace, true);
   });
 }
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {

@@ -48,7 +48,8 @@ class Engine {
 
   // drivers
   void kmc_reset();
-  void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace);
+  void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace,
+               bool second_order);
   void kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature);
 
   void cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps);
@@ -97,6 +98,7 @@ class Engine {
   int64_t *d_kmc_vacancy{nullptr}, *d_kmc_steps{nullptr};
   double *d_kmc_time{nullptr}, *d_kmc_energy{nullptr}, *d_kmc_temperature{nullptr}, *d_kmc_cvac{nullptr}, *d_kmc_csol{nullptr};
   int32_t *d_kmc_error{nullptr};
+  int64_t *d_kmc_previous{nullptr};
   bool kmc_ready{false};
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};

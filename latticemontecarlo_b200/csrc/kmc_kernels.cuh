@@ -23,6 +23,7 @@ struct KmcState {            // per-walker arrays in device memory
   double *temperature;       // temperature_ (constant per walker unless a T(t) table is given)
   double *c_vacancy, *c_solute;   // RateCorrector inputs (pred/include/RateCorrector.hpp)
   int32_t *error;            // sticky per-walker EventError bits
+  int64_t *previous;         // second-order KMC: lattice id the vacancy came from (previous_j_lattice_id_); -1 = not set
 };
 
 struct KmcParams {
@@ -101,12 +102,164 @@ __global__ void kmc_init_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ
     st.c_solute[w] = static_cast<double>(s_nsol) / static_cast<double>(lat.num_sites);
     st.error[w] = s_nvac == 1 ? 0 : kErrNotVacancy;
     if (reset_clock) { st.time[w] = 0.0; st.energy[w] = 0.0; st.steps[w] = 0; }
+    st.previous[w] = -1;
   }
 }
+
 
 constexpr int kKmcThreads = 128;   // 8 walkers per block
 constexpr int kKmcWalkersPerBlock = kKmcThreads / 16;
 constexpr int kBoxRows = 49;                  // (dx, dy) rows of the 7 x 7 x 4 box; the vacancy sits in row 24, slot 2 (even Z) or 1 (odd Z)
+
+// Shared-memory tables and constants every event evaluation needs (set up once per block)
+struct KmcEvalContext {
+  const int32_t *s_box;            // [2][196]
+  const int8_t *s_envpos;          // [2][12][196]
+  const double2 *s_A2v;            // [n][58][n] (dE, log E0)
+  const uint2 *s_mask_hi2;         // [58]
+  const uint16_t *s_pbase;         // [58]
+  const double2 *B_all;            // global: [n][556][n][n]
+  const double *C2;                // global: [n][2]
+  int b_stride, n_species;
+  unsigned solvent, vac_code;
+};
+
+// The 12 jumps of the vacancy at (X, Y, Z) of occupancy `o`, one jump per lane (lanes 0..11 of a half-warp; all 16 lanes
+// take part in the scan).  The box around the vacancy is scanned ONCE: each lane reads up to 4 rows of 4 consecutive
+// bytes, hits (non-solvent cells) are kept as a bit mask + packed codes and compacted into the half-warp's list; every
+// event lane then maps that list into its own symmetry-ordered environment and contracts the folded (dE, log E0) tables.
+//
+// kHypothetical (second-order KMC, KineticMcChainOmpi.cpp:68-86): the configuration is read "as if" the vacancy had just
+// jumped here from the cell at absolute padded index `hypo_index`: the centre (which really holds the migrated atom) is
+// the vacancy, the cell at hypo_index holds `hypo_code`, and the jump in direction `hypo_dir` (back to where the vacancy
+// came from) moves that atom.  Nothing is written to memory.
+template <bool kHypothetical>
+__device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, const KmcEvalContext &ctx, const uint8_t *o, int X, int Y,
+                                                      int Z, int lane, bool active, int k, int32_t dmig0, int32_t dmig1,
+                                                      uint8_t *list_cell, uint8_t *list_code, uint8_t *my_codes, double beta,
+                                                      int64_t hypo_index, unsigned hypo_code, int hypo_dir, int &err, double &ea,
+                                                      double &de, double &rate, unsigned &mig) {
+  constexpr unsigned hmask = 0xFFFFFFFFu;
+  const unsigned solvent = ctx.solvent, vac_code = ctx.vac_code;
+  const int n_species = ctx.n_species;
+  const int32_t *s_box = ctx.s_box;
+  const int8_t *s_envpos = ctx.s_envpos;
+  const double2 *s_A2v = ctx.s_A2v;
+  const uint2 *s_mask_hi2 = ctx.s_mask_hi2;
+  const uint16_t *s_pbase = ctx.s_pbase;
+  const double2 *__restrict__ B_all = ctx.B_all;
+  const int b_stride = ctx.b_stride;
+  {
+    // ---- box scan: the non-solvent cells around the vacancy, in cell order
+    const int zp = Z & 1;
+    const int64_t base = lat.padded_index(X, Y, Z);
+    const int32_t *box = s_box + zp * kBoxCells;
+    // each lane reads up to 4 rows of the box (4 consecutive bytes each: one address computation per row); hits are
+    // kept as a bit mask + packed codes (index = 4 * iteration + slot) and compacted once at the end
+    unsigned hit_mask = 0;
+    unsigned long long hit_codes = 0;           // 4 bits per scanned cell
+    const unsigned solvent4 = solvent * 0x01010101u;
+    const int centre_slot = zp ? 1 : 2;
+#pragma unroll
+    for (int it = 0; it < (kBoxRows + 15) / 16; ++it) {
+      const int row = it * 16 + lane;
+      if (it * 16 + 15 < kBoxRows || row < kBoxRows) {
+        const uint8_t *p = o + base + box[row * 4];
+        unsigned word = static_cast<unsigned>(p[0]) | (static_cast<unsigned>(p[1]) << 8) | (static_cast<unsigned>(p[2]) << 16) |
+                        (static_cast<unsigned>(p[3]) << 24);
+        if (kHypothetical) {
+          const int64_t off = hypo_index - (base + box[row * 4]);      // the cell the vacancy came from holds the moved atom
+          if (off >= 0 && off < 4) word = (word & ~(0xFFu << (8 * static_cast<int>(off)))) | (hypo_code << (8 * static_cast<int>(off)));
+        }
+        if (row == kBoxRows / 2) {                                     // the row through the vacancy itself
+          if (!kHypothetical && ((word >> (8 * centre_slot)) & 0xFFu) != vac_code) err |= kErrNotVacancy;
+          word = (word & ~(0xFFu << (8 * centre_slot))) | (solvent << (8 * centre_slot));
+        }
+        if (word != solvent4) {                                        // rare: at least one non-solvent cell in this row
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            const unsigned code = (word >> (8 * sl)) & 0xFFu;
+            if (code != solvent) { hit_mask |= 1u << (4 * it + sl); hit_codes |= static_cast<unsigned long long>(code) << (4 * (4 * it + sl)); }
+          }
+        }
+      }
+    }
+    // exclusive prefix of the per-lane hit counts over the half-warp
+    const int mine = __popc(hit_mask);
+    int incl = mine;
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+      const int v = __shfl_up_sync(hmask, incl, off, 16);
+      if (lane >= off) incl += v;
+    }
+    const int count = __shfl_sync(hmask, incl, 15, 16);
+    int pos = incl - mine;
+    while (hit_mask) {
+      const int it = __ffs(static_cast<int>(hit_mask)) - 1;
+      hit_mask &= hit_mask - 1;
+      list_cell[pos] = static_cast<uint8_t>(((it >> 2) * 16 + lane) * 4 + (it & 3));       // cell = row * 4 + slot
+      list_code[pos] = static_cast<uint8_t>((hit_codes >> (4 * it)) & 0xFULL);
+      ++pos;
+    }
+    __syncwarp(hmask);
+    if (active) {
+      mig = o[base + (zp ? dmig1 : dmig0)];
+      if (kHypothetical && k == hypo_dir) mig = hypo_code;
+      if (mig == vac_code) err |= kErrNotVacancy;
+      else {
+        // map the box list into this jump's environment: solute mask + species by env index
+        const int8_t *envpos = s_envpos + (zp * 12 + k) * kBoxCells;
+        uint64_t sol = 0;
+        for (int q = 0; q < count; ++q) {
+          const int t = envpos[list_cell[q]];
+          if (t >= 0 && t < kEnvN) {
+            sol |= 1ULL << t;
+            my_codes[t] = list_code[q];
+          }
+        }
+        // contracted tables: Q = C[m] + sum_t A[m][t][e_t] + sum_(t,u) B[m][(t,u)][e_t][e_u] over the solute sites
+        const int m = static_cast<int>(mig), n = n_species;
+        const double *__restrict__ C = ctx.C2 + m * 2;
+        double a0 = __ldg(C), a1 = __ldg(C + 1);                      // (dE, log E0)
+        const double2 *A = s_A2v + m * (kEnvN * n);                   // 32-bit index arithmetic throughout
+        const double2 *__restrict__ B = B_all + m * b_stride;
+        bool ok = true;
+        // the solute mask is walked as two 32-bit words (single-instruction ffs / popc)
+        uint32_t w_lo = static_cast<uint32_t>(sol), w_hi = static_cast<uint32_t>(sol >> 32);
+        while (w_lo | w_hi) {
+          int t;
+          if (w_lo) { t = __ffs(static_cast<int>(w_lo)) - 1; w_lo &= w_lo - 1; }
+          else { t = 31 + __ffs(static_cast<int>(w_hi)); w_hi &= w_hi - 1; }
+          const int et = my_codes[t];
+          if (et >= n) { ok = false; continue; }
+          const double2 a = A[t * n + et];
+          a0 += a.x; a1 += a.y;
+          const uint2 hi = s_mask_hi2[t];
+          uint32_t p_lo = hi.x & w_lo, p_hi = hi.y & w_hi;             // partners u > t still to visit
+          if ((p_lo | p_hi) == 0) continue;
+          const int row = (s_pbase[t] * n + et) * n;
+          do {
+            int u;
+            if (p_lo) { u = __ffs(static_cast<int>(p_lo)) - 1; p_lo &= p_lo - 1; }
+            else { u = 31 + __ffs(static_cast<int>(p_hi)); p_hi &= p_hi - 1; }
+            const int eu = my_codes[u];
+            if (eu >= n) { ok = false; continue; }
+            // index of pair (t,u) among the pairs of t = number of mask bits below u
+            const int rank = u < 32 ? __popc(hi.x & ((1u << u) - 1u)) : __popc(hi.x) + __popc(hi.y & ((1u << (u - 32)) - 1u));
+            const double2 b = __ldg(B + row + rank * (n * n) + eu);
+            a0 += b.x; a1 += b.y;
+          } while (p_lo | p_hi);
+        }
+        if (!ok) err |= kErrExtraVacancy;
+        else {
+          de = a0;
+          ea = quartic_barrier_log(de, a1);
+          rate = exp(-ea * beta);                      // JumpEvent.cpp:13
+        }
+      }
+    }
+  }
+}
 
 // The 12 jumps of one vacancy share a 7 x 7 x 7 half-unit box (196 padded cells).  Per step the half-warp scans the box
 // ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
@@ -159,7 +312,8 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
   const double2 *s_A2v = reinterpret_cast<const double2 *>(s_A2);
   const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
-  const int b_stride = tab.n_pair_pairs * tab.n_species * tab.n_species;
+  const KmcEvalContext ctx{s_box, s_envpos, s_A2v, s_mask_hi2, s_pbase, B_all, tab.pair_C2,
+                           tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code};
   uint32_t *ids = s_ids[wl];
   const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
@@ -181,111 +335,10 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     int slot = 0;
 #pragma unroll
     for (int q = 0; q < 12; ++q) slot += ids[q] < id_j ? 1 : 0;
-    // ---- box scan: the non-solvent cells around the vacancy, in cell order
-    const int zp = Z & 1;
-    const int64_t base = lat.padded_index(X, Y, Z);
-    const int32_t *box = s_box + zp * kBoxCells;
-    // each lane reads up to 4 rows of the box (4 consecutive bytes each: one address computation per row); hits are
-    // kept as a bit mask + packed codes (index = 4 * iteration + slot) and compacted once at the end
-    unsigned hit_mask = 0;
-    unsigned long long hit_codes = 0;           // 4 bits per scanned cell
-    const unsigned solvent4 = solvent * 0x01010101u;
-    const int centre_slot = zp ? 1 : 2;
-#pragma unroll
-    for (int it = 0; it < (kBoxRows + 15) / 16; ++it) {
-      const int row = it * 16 + lane;
-      if (it * 16 + 15 < kBoxRows || row < kBoxRows) {
-        const uint8_t *p = o + base + box[row * 4];
-        unsigned word = static_cast<unsigned>(p[0]) | (static_cast<unsigned>(p[1]) << 8) | (static_cast<unsigned>(p[2]) << 16) |
-                        (static_cast<unsigned>(p[3]) << 24);
-        if (row == kBoxRows / 2) {                                     // the row through the vacancy itself
-          if (((word >> (8 * centre_slot)) & 0xFFu) != vac_code) err |= kErrNotVacancy;
-          word = (word & ~(0xFFu << (8 * centre_slot))) | (solvent << (8 * centre_slot));
-        }
-        if (word != solvent4) {                                        // rare: at least one non-solvent cell in this row
-#pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
-            const unsigned code = (word >> (8 * sl)) & 0xFFu;
-            if (code != solvent) { hit_mask |= 1u << (4 * it + sl); hit_codes |= static_cast<unsigned long long>(code) << (4 * (4 * it + sl)); }
-          }
-        }
-      }
-    }
-    // exclusive prefix of the per-lane hit counts over the half-warp
-    const int mine = __popc(hit_mask);
-    int incl = mine;
-#pragma unroll
-    for (int off = 1; off < 16; off <<= 1) {
-      const int v = __shfl_up_sync(hmask, incl, off, 16);
-      if (lane >= off) incl += v;
-    }
-    const int count = __shfl_sync(hmask, incl, 15, 16);
-    int pos = incl - mine;
-    while (hit_mask) {
-      const int it = __ffs(static_cast<int>(hit_mask)) - 1;
-      hit_mask &= hit_mask - 1;
-      list_cell[pos] = static_cast<uint8_t>(((it >> 2) * 16 + lane) * 4 + (it & 3));       // cell = row * 4 + slot
-      list_code[pos] = static_cast<uint8_t>((hit_codes >> (4 * it)) & 0xFULL);
-      ++pos;
-    }
-    __syncwarp(hmask);
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
-    if (active) {
-      mig = o[base + (zp ? dmig1 : dmig0)];
-      if (mig == vac_code) err |= kErrNotVacancy;
-      else {
-        // map the box list into this jump's environment: solute mask + species by env index
-        const int8_t *envpos = s_envpos + (zp * 12 + k) * kBoxCells;
-        uint64_t sol = 0;
-        for (int q = 0; q < count; ++q) {
-          const int t = envpos[list_cell[q]];
-          if (t >= 0 && t < kEnvN) {
-            sol |= 1ULL << t;
-            my_codes[t] = list_code[q];
-          }
-        }
-        // contracted tables: Q = C[m] + sum_t A[m][t][e_t] + sum_(t,u) B[m][(t,u)][e_t][e_u] over the solute sites
-        const int m = static_cast<int>(mig), n = n_species;
-        const double *__restrict__ C = tab.pair_C2 + m * 2;
-        double a0 = __ldg(C), a1 = __ldg(C + 1);                      // (dE, log E0)
-        const double2 *A = s_A2v + m * (kEnvN * n);                   // 32-bit index arithmetic throughout
-        const double2 *__restrict__ B = B_all + m * b_stride;
-        bool ok = true;
-        // the solute mask is walked as two 32-bit words (single-instruction ffs / popc)
-        uint32_t w_lo = static_cast<uint32_t>(sol), w_hi = static_cast<uint32_t>(sol >> 32);
-        while (w_lo | w_hi) {
-          int t;
-          if (w_lo) { t = __ffs(static_cast<int>(w_lo)) - 1; w_lo &= w_lo - 1; }
-          else { t = 31 + __ffs(static_cast<int>(w_hi)); w_hi &= w_hi - 1; }
-          const int et = my_codes[t];
-          if (et >= n) { ok = false; continue; }
-          const double2 a = A[t * n + et];
-          a0 += a.x; a1 += a.y;
-          const uint2 hi = s_mask_hi2[t];
-          uint32_t p_lo = hi.x & w_lo, p_hi = hi.y & w_hi;             // partners u > t still to visit
-          if ((p_lo | p_hi) == 0) continue;
-          const int row = (s_pbase[t] * n + et) * n;
-          do {
-            int u;
-            if (p_lo) { u = __ffs(static_cast<int>(p_lo)) - 1; p_lo &= p_lo - 1; }
-            else { u = 31 + __ffs(static_cast<int>(p_hi)); p_hi &= p_hi - 1; }
-            const int eu = my_codes[u];
-            if (eu >= n) { ok = false; continue; }
-            // index of pair (t,u) among the pairs of t = number of mask bits below u
-            const int rank = u < 32 ? __popc(hi.x & ((1u << u) - 1u)) : __popc(hi.x) + __popc(hi.y & ((1u << (u - 32)) - 1u));
-            const double2 b = __ldg(B + row + rank * (n * n) + eu);
-            a0 += b.x; a1 += b.y;
-          } while (p_lo | p_hi);
-        }
-        if (!ok) err |= kErrExtraVacancy;
-        else {
-          de = a0;
-          ea = quartic_barrier_log(de, a1);
-          rate = exp(-ea * beta);                      // JumpEvent.cpp:13
-        }
-      }
-    }
+    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list_cell, list_code, my_codes, beta, 0, 0u, -1,
+                                 err, ea, de, rate, mig);
     if ((__ballot_sync(hmask, err != 0) >> hshift) & 0xFFFFu) alive = false;    // this walker stops; its state is left untouched
     if (!__any_sync(hmask, alive)) break;
     // events in the reference's order through shared memory: s_rate[slot] = rate, s_lane[slot] = lane
@@ -355,8 +408,206 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     st.energy[w] = energy;
     st.steps[w] = steps;
     st.temperature[w] = temperature;
+    st.previous[w] = -1;        // a first-order run leaves no second-order history
   }
   if (err && w_raw < n_walkers) atomicOr(&st.error[w], err);
+}
+
+// ------------------------------------------------------------------------------------------------ second-order KMC
+// mc::KineticMcChainOmpi (mc/src/KineticMcChainOmpi.cpp:56-152, mc/include/KineticMcAbstract.h:65-143): the reference
+// spreads the 12 first neighbours i of the vacancy site k over 12 MPI ranks; rank r moves the vacancy to i, evaluates
+// the 12 jumps i -> l there (one of them is the jump back, whose reverse is the event k -> i), moves it back, and the
+// ranks combine eight sums (MpiData) into the second-order residence time t_2 and event probabilities that remove the
+// k <-> i flicker.  Here ONE BLOCK of 12 half-warps owns one walker: half-warp h plays rank "direction h" (lane = jump
+// i -> l), reads the moved configuration through the hypothetical view of kmc_scan_and_evaluate (no memory writes), and
+// the per-rank results meet in shared memory in the reference's rank order (ascending lattice id of i).  One uniform
+// per step (SelectEvent; the second-order time is an expectation, not a sample).
+constexpr int kChainThreads = 192;
+
+__global__ void __launch_bounds__(kChainThreads, 4)
+kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
+                     int64_t n_steps, const double *__restrict__ replay_u, KmcTraceDev tr) {
+  __shared__ int32_t s_box[2 * kBoxCells];
+  __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
+  __shared__ uint8_t s_list_cell[12][kBoxCells], s_list_code[12][kBoxCells];
+  __shared__ uint8_t s_codes[kChainThreads][kEnvN + 2];
+  __shared__ double s_ord_rate[12][12];
+  extern __shared__ double s_A2[];
+  __shared__ uint64_t s_mask_hi[kEnvN];
+  __shared__ uint16_t s_pbase[kEnvN];
+  __shared__ uint32_t s_ids[12][12];
+  // per-rank results in rank (slot) order
+  __shared__ double s_fwd[12], s_bwd[12], s_total_i[12], s_barrier[12], s_de[12];
+  __shared__ uint8_t s_dir[12], s_is_prev[12], s_mig[12];
+  for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
+  for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
+  for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
+  for (int q = threadIdx.x; q < 2 * 12 * kBoxCells; q += blockDim.x) s_envpos[q] = tab.box_envpos[q];
+  __syncthreads();
+  const int w = blockIdx.x;
+  if (w >= n_walkers || st.error[w] != 0 || st.vacancy[w] < 0) return;     // uniform over the block
+  const int lane = threadIdx.x & 15;
+  const int h = threadIdx.x >> 4;                  // rank of this half-warp = direction k -> i
+  const int hshift = threadIdx.x & 16;
+  constexpr unsigned hmask = 0xFFFFFFFFu;
+  uint8_t *o = occ + w * walker_stride;
+
+  int X, Y, Z;
+  lat.coords_of_id(st.vacancy[w], X, Y, Z);
+  double time = st.time[w], energy = st.energy[w], temperature = st.temperature[w];
+  int64_t steps = st.steps[w];
+  int64_t previous = st.previous[w];
+  const double c_vac = st.c_vacancy[w], c_sol = st.c_solute[w];
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac_code = static_cast<unsigned>(tab.n_species);
+  const int n_species = tab.n_species;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  const bool active = lane < 12;
+  const int k = active ? lane : 0;
+  const int dxk = tab.nn1[4 * k], dyk = tab.nn1[4 * k + 1], dzk = tab.nn1[4 * k + 2];            // lane's direction
+  const int dxh = tab.nn1[4 * h], dyh = tab.nn1[4 * h + 1], dzh = tab.nn1[4 * h + 2];            // half-warp's direction
+  const int back_dir = tab.dir_lut[(-dxh + 1) * 9 + (-dyh + 1) * 3 + (-dzh + 1)];                // the jump i -> k
+  const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
+  const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
+  const KmcEvalContext ctx{s_box, s_envpos, reinterpret_cast<const double2 *>(s_A2), reinterpret_cast<const uint2 *>(s_mask_hi), s_pbase,
+                           B_all, tab.pair_C2, tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code};
+  const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
+  int err = 0;
+
+  double beta = 1.0 / kBoltzmannEv / temperature;
+  double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    if (prm.n_tt > 0) {                            // UpdateTemperature (KineticMcAbstract.cpp:45-50)
+      temperature = interpolate_temperature(prm, time);
+      beta = 1.0 / kBoltzmannEv / temperature;
+      if (prm.rate_corrector) corr = rate_correction(c_vac, c_sol, temperature);
+    }
+    // ---- ranks: the 12 neighbours i of k in ascending lattice-id order
+    const int xn = wrap_coord(X + dxk, px), yn = wrap_coord(Y + dyk, py), zn = wrap_coord(Z + dzk, pz);
+    const uint32_t id_n = static_cast<uint32_t>(lat.id_of_coords(xn, yn, zn));   // lane's neighbour of k
+    const uint32_t id_i = __shfl_sync(hmask, id_n, h, 16);
+    const int rank = __popc((__ballot_sync(hmask, active && id_n < id_i) >> hshift) & 0xFFFu);
+    if (previous < 0) {                            // previous_j_ starts as first neighbour 0 of the vacancy (KineticMcAbstract.cpp:255)
+      uint32_t lo = active ? id_n : 0xFFFFFFFFu;
+#pragma unroll
+      for (int off = 8; off > 0; off >>= 1) lo = min(lo, __shfl_xor_sync(hmask, lo, off, 16));
+      previous = lo;
+    }
+    // ---- this rank's hypothetical state: vacancy at i, the atom of i at k
+    const int xi = wrap_coord(X + dxh, px), yi = wrap_coord(Y + dyh, py), zi = wrap_coord(Z + dzh, pz);
+    const int zpk = Z & 1, zpi = zi & 1;
+    const int64_t base_k = lat.padded_index(X, Y, Z), base_i = lat.padded_index(xi, yi, zi);
+    const unsigned mig_i = o[base_k + lat.padded_delta(dxh, dyh, dzh, zpk)];
+    if (mig_i == vac_code) err |= kErrNotVacancy;
+    if (lane == 0 && o[base_k] != vac_code) err |= kErrNotVacancy;
+    const int64_t hypo_index = base_i + lat.padded_delta(-dxh, -dyh, -dzh, zpi);
+    // event order of the jumps i -> l: ascending lattice id of l
+    const int xl = wrap_coord(xi + dxk, px), yl = wrap_coord(yi + dyk, py), zl = wrap_coord(zi + dzk, pz);
+    const uint32_t id_l = static_cast<uint32_t>(lat.id_of_coords(xl, yl, zl));
+    if (active) s_ids[h][lane] = id_l;
+    __syncwarp(hmask);
+    int slot = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) slot += s_ids[h][q] < id_l ? 1 : 0;
+    double ea = 0.0, de = 0.0, rate = 0.0;
+    unsigned mig = 0;
+    kmc_scan_and_evaluate<true>(lat, ctx, o, xi, yi, zi, lane, active, k, dmig0, dmig1, s_list_cell[h], s_list_code[h],
+                                s_codes[threadIdx.x], beta, hypo_index, mig_i, back_dir, err, ea, de, rate, mig);
+    // total_rate_i in event order (KineticMcChainOmpi.cpp:71-85)
+    if (active) s_ord_rate[h][slot] = rate;
+    __syncwarp(hmask);
+    double total_i = 0.0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) total_i += s_ord_rate[h][q];
+    // event k -> i = reverse of i -> k (JumpEvent::GetReverseJumpEvent, JumpEvent.cpp:55-58)
+    const double ea_ik = __shfl_sync(hmask, ea, back_dir, 16), de_ik = __shfl_sync(hmask, de, back_dir, 16);
+    if (lane == 0) {
+      const double barrier = ea_ik - de_ik, change = -de_ik;
+      s_barrier[rank] = barrier;
+      s_de[rank] = change;
+      s_fwd[rank] = exp(-barrier * beta);                      // forward_rate_ (JumpEvent.cpp:13)
+      s_bwd[rank] = exp((change - barrier) * beta);            // GetBackwardRate (:28-30)
+      s_total_i[rank] = total_i;
+      s_dir[rank] = static_cast<uint8_t>(h);
+      s_is_prev[rank] = static_cast<int64_t>(id_i) == previous ? 1 : 0;
+      s_mig[rank] = static_cast<uint8_t>(mig_i);
+    }
+    if (__syncthreads_or(err != 0)) break;                       // the walker stops; its state is left untouched
+    // ---- CalculateTime (KineticMcChainOmpi.cpp:93-151), replicated in every thread; sums in rank order
+    double total_k = 0.0;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) total_k += s_fwd[r];
+    const double t_1 = 1.0 / total_k / kPrefactorHz;
+    double beta_bar_k = 0.0, beta_k = 0.0, gamma_bar_k_j = 0.0, gamma_k_j = 0.0, beta_k_j = 0.0, alpha_k_j = 0.0, ts_num = 0.0, ts_j_num = 0.0;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      const double p_ki = s_fwd[r] / total_k, p_ik = s_bwd[r] / s_total_i[r];
+      const double bb = p_ki * p_ik, b = p_ki * (1 - p_ik);
+      const bool prev = s_is_prev[r] != 0;
+      const double t_i = 1.0 / s_total_i[r] / kPrefactorHz;
+      const double ts_term = (t_1 + t_i) * bb;
+      const double c2 = prev ? 0.0 : bb, c3 = prev ? 0.0 : b, c4 = prev ? b : 0.0, c5 = prev ? p_ki : 0.0, c7 = prev ? 0.0 : ts_term;
+      if (r == 0) { beta_bar_k = bb; beta_k = b; gamma_bar_k_j = c2; gamma_k_j = c3; beta_k_j = c4; alpha_k_j = c5; ts_num = ts_term; ts_j_num = c7; }
+      else { beta_bar_k += bb; beta_k += b; gamma_bar_k_j += c2; gamma_k_j += c3; beta_k_j += c4; alpha_k_j += c5; ts_num += ts_term; ts_j_num += c7; }
+    }
+    const double ts = ts_num / beta_bar_k, ts_j = ts_j_num / gamma_bar_k_j;
+    const double inv = 1 / (1 - alpha_k_j);
+    const double t_2 = inv * (gamma_k_j * t_1 + gamma_bar_k_j * (ts_j + t_1 + beta_bar_k / beta_k * ts));
+    // second-order probabilities, cumulative in rank order; first rank whose cumulative probability is not < u
+    double u;
+    if (replay_u) u = replay_u[static_cast<int64_t>(w) * n_steps + s];
+    else {
+      uint32_t r4[4];
+      philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
+                    static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r4);
+      u = uniform53(r4[2], r4[3]);
+    }
+    int sel = 11;
+    double cumulative = 0.0;
+    bool found = false;
+#pragma unroll
+    for (int r = 0; r < 12; ++r) {
+      const double p_ki = s_fwd[r] / total_k, p_ik = s_bwd[r] / s_total_i[r];
+      const double b = p_ki * (1 - p_ik);
+      cumulative += s_is_prev[r] ? inv * (gamma_bar_k_j / beta_k) * beta_k_j : inv * (1 + gamma_bar_k_j / beta_k) * b;
+      if (!found && !(cumulative < u)) { found = true; sel = r; }
+    }
+    const double dt = t_2 * corr;
+    const int sel_dir = s_dir[sel];
+    const double sel_ea = s_barrier[sel], sel_de = s_de[sel];
+    const unsigned sel_mig = s_mig[sel];
+    const int nx = wrap_coord(X + tab.nn1[4 * sel_dir], px), ny = wrap_coord(Y + tab.nn1[4 * sel_dir + 1], py),
+              nz = wrap_coord(Z + tab.nn1[4 * sel_dir + 2], pz);
+    if (threadIdx.x == 0 && tracing) {
+      const int64_t at = static_cast<int64_t>(w) * n_steps + s;
+      if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
+      if (tr.to) tr.to[at] = lat.id_of_coords(nx, ny, nz);
+      if (tr.slot) tr.slot[at] = sel;
+      if (tr.dt) tr.dt[at] = dt;
+      if (tr.Ea) tr.Ea[at] = sel_ea;
+      if (tr.dE) tr.dE[at] = sel_de;
+      if (tr.total_rate) tr.total_rate[at] = total_k;
+      if (tr.temperature) tr.temperature[at] = temperature;
+    }
+    // Config::LatticeJump: lanes 0-7 of the first half-warp write the images of the old vacancy site, lanes 8-15 the new one
+    if (threadIdx.x < 16)
+      store_site_image(lat, o, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7,
+                       static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
+    previous = lat.id_of_coords(X, Y, Z);          // KineticMcChainAbstract::OneStepSimulation (KineticMcAbstract.cpp:260-263)
+    time += dt;
+    energy += sel_de;
+    ++steps;
+    X = nx; Y = ny; Z = nz;
+    __syncthreads();                               // the jump is visible to every half-warp; shared results may be overwritten
+  }
+  if (err) atomicOr(&st.error[w], err);
+  else if (threadIdx.x == 0 && st.error[w] == 0) {
+    st.vacancy[w] = lat.id_of_coords(X, Y, Z);
+    st.time[w] = time;
+    st.energy[w] = energy;
+    st.steps[w] = steps;
+    st.temperature[w] = temperature;
+    st.previous[w] = previous;
+  }
 }
 
 }  // namespace lmc

@@ -852,6 +852,86 @@ def kmc_first(cfg, predictor, temperature, u1, u2, tt=None, rate_corrector=False
     return {k: np.asarray(v) for k, v in trace.items()}
 
 
+def kmc_chain(cfg, predictor, temperature, u, tt=None, rate_corrector=False):
+    """mc::KineticMcChainOmpi::Simulate (second-order KMC) with host-supplied uniforms (one per step).  Per step
+    (KineticMcAbstract.cpp:140-182,260-263; KineticMcChainOmpi.cpp:56-152), k = vacancy site, rank r handles the r-th first
+    neighbour i (ascending lattice ids):
+      BuildEventList: jump k->i, evaluate the 12 events i->l in that state, total_rate_i = sum exp(-Ea_il beta); the event
+        k->i is the REVERSE of i->k (barrier Ea_ik - dE_ik, change -dE_ik; JumpEvent.cpp:55-58); jump back;
+        total_rate_k = sum_r exp(-Ea_ki beta), p_ki = rate/total.
+      CalculateTime: p_ik = backward rate of (k->i) / total_rate_i; the eight sums of MpiData in rank order; t_2 and the
+        second-order probabilities (the branch depends on whether i is the site the vacancy came from).
+      SelectEvent: first slot with cumulative p >= u (last if none).  previous_j starts as first neighbour 0 of the initial
+        vacancy site (KineticMcAbstract.cpp:255).  cfg is modified in place."""
+    vac = int(np.nonzero(cfg.occ == 0)[0][0])
+    c_vac = float(np.mean(cfg.occ == 0))
+    c_sol = float(np.mean((cfg.occ != ELEMENT_CODES["Al"]) & (cfg.occ != 0)))
+    previous_j = int(cfg.nn[0][vac][0])
+    time, energy = 0.0, 0.0
+    beta = 1.0 / K_BOLTZMANN / temperature
+    trace = {k: [] for k in ("from", "to", "slot", "dt", "time", "energy", "Ea", "dE", "temperature", "total_rate")}
+    for s in range(len(u)):
+        if tt is not None:
+            temperature = tt.temperature(time)
+            beta = 1.0 / K_BOLTZMANN / temperature
+        k = vac
+        nbrs = [int(v) for v in cfg.nn[0][k]]
+        barrier_ki, de_ki, fwd, bwd, total_i = [], [], [], [], []
+        for i in nbrs:
+            cfg.lattice_jump(k, i)
+            ls = cfg.nn[0][i]
+            ea, de = predictor.barrier_and_diff(cfg, np.full(12, i), ls)
+            cfg.lattice_jump(i, k)
+            tot = 0.0
+            for q in range(12):
+                tot += math.exp(-float(ea[q]) * beta)
+            q = [int(v) for v in ls].index(k)
+            b_ki, d_ki = float(ea[q]) - float(de[q]), -float(de[q])            # GetReverseJumpEvent
+            barrier_ki.append(b_ki); de_ki.append(d_ki)
+            fwd.append(math.exp(-b_ki * beta))                                 # forward_rate_
+            bwd.append(math.exp((d_ki - b_ki) * beta))                         # GetBackwardRate
+            total_i.append(tot)
+        total_k = 0.0
+        for r in fwd:
+            total_k += r
+        t_1 = 1.0 / total_k / K_PREFACTOR
+        sums = [0.0] * 8
+        per_rank = []
+        for r in range(12):
+            p_ki = fwd[r] / total_k
+            p_ik = bwd[r] / total_i[r]
+            bb, b = p_ki * p_ik, p_ki * (1 - p_ik)
+            prev = nbrs[r] == previous_j
+            t_i = 1.0 / total_i[r] / K_PREFACTOR
+            contrib = (bb, b, 0.0 if prev else bb, 0.0 if prev else b, b if prev else 0.0, p_ki if prev else 0.0,
+                       (t_1 + t_i) * bb, 0.0 if prev else (t_1 + t_i) * bb)
+            for q in range(8):
+                sums[q] = contrib[q] if r == 0 else sums[q] + contrib[q]
+            per_rank.append((b, prev))
+        beta_bar_k, beta_k, gamma_bar_k_j, gamma_k_j, beta_k_j, alpha_k_j, ts_num, ts_j_num = sums
+        ts = ts_num / beta_bar_k
+        ts_j = ts_j_num / gamma_bar_k_j
+        inv = 1.0 / (1.0 - alpha_k_j)
+        t_2 = inv * (gamma_k_j * t_1 + gamma_bar_k_j * (ts_j + t_1 + beta_bar_k / beta_k * ts))
+        cumulative, acc = [], 0.0
+        for b, prev in per_rank:
+            acc += inv * (gamma_bar_k_j / beta_k) * beta_k_j if prev else inv * (1 + gamma_bar_k_j / beta_k) * b
+            cumulative.append(acc)
+        corr = rate_correction_factor(c_vac, c_sol, temperature) if rate_corrector else 1.0
+        dt = t_2 * corr
+        slot = next((q for q, cp in enumerate(cumulative) if not cp < u[s]), 11)
+        to = nbrs[slot]
+        time += dt
+        energy += de_ki[slot]
+        cfg.lattice_jump(k, to)
+        for key, val in (("from", k), ("to", to), ("slot", slot), ("dt", dt), ("time", time), ("energy", energy),
+                         ("Ea", barrier_ki[slot]), ("dE", de_ki[slot]), ("temperature", temperature), ("total_rate", total_k)):
+            trace[key].append(val)
+        previous_j = k
+        vac = to
+    return {k: np.asarray(v) for k, v in trace.items()}
+
+
 def metropolis_trials(cfg, predictor, a, b, u, temperature=None, sa_schedule=None):
     """CanonicalMcSerial::Simulate (mc/src/CanonicalMcSerial.cpp:40-51) / SimulatedAnnealing::Simulate
     (mc/src/SimulatedAnnealing.cpp:168-185) replayed on host-supplied trial pairs and uniforms: accept if dE < 0,

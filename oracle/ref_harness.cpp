@@ -20,6 +20,7 @@
 #include <set>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <unistd.h>
 #include <vector>
 
@@ -34,6 +35,7 @@
 #include "TimeTemperatureInterpolator.h"
 #include "RateCorrector.hpp"
 #include "KineticMcFirstOmp.h"
+#include "KineticMcChainOmpi.h"
 #include "CanonicalMcSerial.h"
 #include "CanonicalMcOmp.h"
 #include "SimulatedAnnealing.h"
@@ -149,6 +151,59 @@ class TracedKmcFirstOmp : public mc::KineticMcFirstOmp {
     const size_t to = vacancy_lattice_id_;
     if (trace_->u1) trace_->u1[k] = u1;
     if (trace_->u2) trace_->u2[k] = u2;
+    if (trace_->from) trace_->from[k] = static_cast<int64_t>(from);
+    if (trace_->to) trace_->to[k] = static_cast<int64_t>(to);
+    if (trace_->slot) {
+      const auto &nn = config_.GetFirstNeighborsAdjacencyList()[from];
+      int64_t s = -1;
+      for (size_t q = 0; q < nn.size(); ++q)
+        if (nn[q] == to) s = static_cast<int64_t>(q);
+      trace_->slot[k] = s;
+    }
+    if (trace_->dt) trace_->dt[k] = time_ - t0;
+    if (trace_->time) trace_->time[k] = time_;
+    if (trace_->energy) trace_->energy[k] = energy_;
+    if (trace_->Ea) trace_->Ea[k] = event_k_i_.GetForwardBarrier();
+    if (trace_->dE) trace_->dE[k] = event_k_i_.GetEnergyChange();
+    if (trace_->temperature) trace_->temperature[k] = temperature_;
+    if (trace_->total_rate) trace_->total_rate[k] = total_rate_k_;
+  }
+
+ private:
+  KmcTrace *trace_{nullptr};
+};
+
+// mc::KineticMcChainOmpi needs exactly 12 MPI ranks (KineticMcChainOmpi.cpp:37-42); the harness runs them as 12 threads
+// over the threads-as-ranks shim (shims/mpi.h).  Only rank 0's generator decides (SelectEvent broadcasts its choice,
+// KineticMcAbstract.cpp:116-120) and consumes ONE uniform per step (the second-order time is not sampled).
+class TracedKmcChainOmpi : public mc::KineticMcChainOmpi {
+ public:
+  using mc::KineticMcChainOmpi::KineticMcChainOmpi;
+  void Reseed(uint64_t seed) { generator_.seed(seed); }
+  void SetTrace(KmcTrace *t) { trace_ = t; }
+  const cfg::Config &config() const { return config_; }
+  double absolute_energy() const { return absolute_energy_; }
+  double energy() const { return energy_; }
+  double time() const { return time_; }
+  unsigned long long steps() const { return steps_; }
+
+ protected:
+  void Dump() const override {}
+  void OneStepSimulation() override {
+    if (!trace_ || trace_->n >= trace_->cap) {
+      mc::KineticMcChainAbstract::OneStepSimulation();
+      return;
+    }
+    auto g = generator_;
+    std::uniform_real_distribution<double> d(0.0, 1.0);
+    const double u = d(g);
+    const size_t from = vacancy_lattice_id_;
+    const double t0 = time_;
+    mc::KineticMcChainAbstract::OneStepSimulation();
+    const int64_t k = trace_->n++;
+    const size_t to = vacancy_lattice_id_;
+    if (trace_->u1) trace_->u1[k] = 0.0;
+    if (trace_->u2) trace_->u2[k] = u;
     if (trace_->from) trace_->from[k] = static_cast<int64_t>(from);
     if (trace_->to) trace_->to[k] = static_cast<int64_t>(to);
     if (trace_->slot) {
@@ -620,6 +675,60 @@ double ref_kmc_first_omp(void *config_h, const char *json, const int *codes, int
       summary4[3] = static_cast<double>(kmc.steps());
     }
     return t1 - t0;
+  } catch (const std::exception &e) { fail(e); return -1.0; }
+}
+
+// mc::KineticMcChainOmpi (mc/src/KineticMcChainOmpi.cpp:56-152, mc/src/KineticMcAbstract.cpp:140-188,260-263): the
+// second-order ("chain") KMC, 12 ranks run as 12 threads.  Trace semantics as ref_kmc_first_omp; u1 is unused (0),
+// u2 is the selecting uniform of rank 0, Ea/dE are those of the chosen k->i event, total_rate is total_rate_k_.
+double ref_kmc_chain_ompi(void *config_h, const char *json, const int *codes, int ncodes, const char *tt_file,
+                          int rate_corrector, double temperature, uint64_t maximum_steps, uint64_t seed,
+                          const char *workdir, int64_t trace_cap, double *u1, double *u2, int64_t *from, int64_t *to,
+                          int64_t *slot, double *dt, double *time, double *energy, double *Ea, double *dE,
+                          double *temp_trace, double *total_rate, uint8_t *final_occ, double *summary4) {
+  try {
+    ScopedChdir cd(workdir);
+    ScopedQuietCout quiet;
+    constexpr int kRanks = 12;
+    lmc_shim_mpi::World world(kRanks);
+    const auto element_set = element_set_from_codes(codes, ncodes);
+    const cfg::Config &start = *static_cast<cfg::Config *>(config_h);
+    std::vector<std::string> errors(kRanks);
+    double seconds = 0.0;
+    KmcTrace tr;
+    tr.cap = trace_cap; tr.u1 = u1; tr.u2 = u2; tr.from = from; tr.to = to; tr.slot = slot; tr.dt = dt; tr.time = time;
+    tr.energy = energy; tr.Ea = Ea; tr.dE = dE; tr.temperature = temp_trace; tr.total_rate = total_rate;
+    auto body = [&](int rank) {
+      lmc_shim_mpi::attach(&world, rank);
+      omp_set_num_threads(1);
+      try {
+        TracedKmcChainOmpi kmc(start, 1ULL << 62, 1ULL << 62, maximum_steps, 0, 0, 0.0, 0.0, temperature, element_set, json,
+                               tt_file ? tt_file : "", rate_corrector != 0, false, false);
+        kmc.Reseed(seed + static_cast<uint64_t>(rank));      // only rank 0's stream decides
+        if (rank == 0 && trace_cap > 0) kmc.SetTrace(&tr);
+        world.barrier();
+        const double t0 = now_s();
+        kmc.Simulate();
+        world.barrier();
+        if (rank == 0) {
+          seconds = now_s() - t0;
+          copy_occupancy(kmc.config(), final_occ);
+          if (summary4) {
+            summary4[0] = kmc.time(); summary4[1] = kmc.energy(); summary4[2] = kmc.absolute_energy();
+            summary4[3] = static_cast<double>(kmc.steps());
+          }
+        }
+      } catch (const std::exception &e) {
+        errors[static_cast<size_t>(rank)] = e.what();
+        std::cerr << "ref_kmc_chain_ompi rank " << rank << ": " << e.what() << std::endl;
+        std::abort();                                         // the other ranks would wait forever in a collective
+      }
+      lmc_shim_mpi::detach();
+    };
+    std::vector<std::thread> ranks;
+    for (int r = 0; r < kRanks; ++r) ranks.emplace_back(body, r);
+    for (auto &t : ranks) t.join();
+    return seconds;
   } catch (const std::exception &e) { fail(e); return -1.0; }
 }
 

@@ -52,7 +52,7 @@ def lib():
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
             getattr(_lib, name).restype = C.c_int64
         for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_sa", "ref_rate_correction",
-                     "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs"):
+                     "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs", "ref_kmc_chain_ompi"):
             getattr(_lib, name).restype = C.c_double
     return _lib
 
@@ -338,6 +338,33 @@ def kmc_first_omp(config: RefConfig, json_path, elements=("Al", "Mg", "Zn"), tem
                                       _p(t["to"]), _p(t["slot"]), _p(t["dt"]), _p(t["time"]), _p(t["energy"]),
                                       _p(t["Ea"]), _p(t["dE"]), _p(t["temperature"]), _p(t["total_rate"]), _p(occ),
                                       _p(summary))
+    if sec < 0:
+        raise RuntimeError(_err())
+    t.update(seconds=sec, final_occ=occ, final_time=summary[0], final_energy=summary[1], absolute_energy=summary[2],
+             steps=int(summary[3]))
+    return t
+
+
+def kmc_chain_ompi(config: RefConfig, json_path, elements=("Al", "Mg", "Zn"), temperature=500.0, maximum_steps=100,
+                   seed=1, tt_file=None, rate_corrector=False, trace=True):
+    """mc::KineticMcChainOmpi::Simulate() (second-order KMC) with its 12 MPI ranks run as 12 threads of this process and a
+    seeded rank-0 generator.  Trace as kmc_first_omp; u2 is the one uniform a step consumes (u1 is unused)."""
+    _, p, n = _codes(elements)
+    cap = int(maximum_steps) + 1 if trace else 0
+    f = lambda: np.zeros(cap, dtype=np.float64)
+    g = lambda: np.zeros(cap, dtype=np.int64)
+    t = dict(u1=f(), u2=f(), dt=f(), time=f(), energy=f(), Ea=f(), dE=f(), temperature=f(), total_rate=f())
+    t.update({"from": g(), "to": g(), "slot": g()})
+    occ = np.empty(config.num_sites, dtype=np.uint8)
+    summary = np.zeros(4, dtype=np.float64)
+    with tempfile.TemporaryDirectory() as d:
+        sec = lib().ref_kmc_chain_ompi(config.h, str(json_path).encode(), p, n,
+                                       str(tt_file).encode() if tt_file else None, int(bool(rate_corrector)),
+                                       C.c_double(temperature), C.c_uint64(int(maximum_steps)), C.c_uint64(int(seed)),
+                                       d.encode(), C.c_int64(cap), _p(t["u1"]), _p(t["u2"]), _p(t["from"]),
+                                       _p(t["to"]), _p(t["slot"]), _p(t["dt"]), _p(t["time"]), _p(t["energy"]),
+                                       _p(t["Ea"]), _p(t["dE"]), _p(t["temperature"]), _p(t["total_rate"]), _p(occ),
+                                       _p(summary))
     if sec < 0:
         raise RuntimeError(_err())
     t.update(seconds=sec, final_occ=occ, final_time=summary[0], final_energy=summary[1], absolute_energy=summary[2],

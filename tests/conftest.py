@@ -35,3 +35,10 @@ def golden():
     import numpy as np
     path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
     return np.load(path, allow_pickle=False)
+
+
+@pytest.fixture(scope="session")
+def golden_chain():
+    """Traces of the reference's second-order KMC (tests/golden/make_golden_chain.py)."""
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "golden_chain_v1.npz"), allow_pickle=False)

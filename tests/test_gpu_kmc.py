@@ -146,3 +146,54 @@ def test_large_cell_ramp_and_rate_corrector_follow_oracle(coef_json):
     st = e.kmc_state()
     assert abs(st["time"][0] - time) < 1e-12 * time
     assert np.array_equal(e.get_occupancy(), cfg.occ)
+
+
+# ------------------------------------------------------------------------------------------------ second-order KMC
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("run", ["chain", "chain_tt"])
+def test_chain_replay_reproduces_reference_event_sequence(golden, golden_chain, tag, run, tmp_path):
+    """lmc_kmc_chain_run against the traces of the reference's own mc::KineticMcChainOmpi (12 ranks), fed with the
+    selecting uniforms of its rank 0: same sites, same slots, same second-order residence times, same final occupancy."""
+    e = _engine(golden, tag, tmp_path, n_walkers=2)
+    g = lambda k: golden_chain["%s_%s_%s" % (tag, run, k)]
+    n = len(g("u2"))
+    for w in range(2):
+        e.set_occupancy(golden[tag + "_occ"], walker=w)
+    e.kmc_reset()
+    kw = dict(time_temperature=golden["tt_points"], rate_corrector=True) if run == "chain_tt" else {}
+    tr = e.kmc_chain_run(n, temperature=500.0, replay_u=np.tile(g("u2"), (2, 1)), trace=True, **kw)
+    for w in range(2):
+        assert np.array_equal(tr["from"][w], g("from")) and np.array_equal(tr["to"][w], g("to"))
+        assert np.array_equal(tr["slot"][w], g("slot"))
+        assert np.max(np.abs(tr["Ea"][w] - g("Ea"))) < TOL and np.max(np.abs(tr["dE"][w] - g("dE"))) < TOL
+        assert np.allclose(tr["total_rate"][w], g("total_rate"), rtol=1e-9, atol=0)
+        assert np.allclose(tr["dt"][w], g("dt"), rtol=1e-9, atol=4e-16 * float(np.abs(g("time")).max()))
+        assert np.allclose(tr["temperature"][w], g("temperature"), rtol=1e-12, atol=0)
+        assert np.array_equal(e.get_occupancy(w), g("final_occ"))
+    st = e.kmc_state()
+    assert np.all(st["steps"] == n)
+    assert np.allclose(st["time"], g("time")[-1], rtol=1e-9) and np.max(np.abs(st["energy"] - g("energy")[-1])) < TOL
+    assert np.all(st["vacancy"] == g("to")[-1])
+
+
+def test_chain_runs_are_chunkable_and_suppress_flicker(golden, tmp_path):
+    """Philox mode: chunked runs continue exactly (previous_j is carried between calls); and the point of the method:
+    immediate returns to the previous site are rarer than in first-order KMC on the same start state."""
+    e = _engine(golden, "B", tmp_path, n_walkers=32)
+    occ = golden["B_occ"]
+
+    def run(chunks, second_order=True):
+        for w in range(32):
+            e.set_occupancy(occ, walker=w)
+        e.kmc_reset()
+        trs = [e.kmc_run(c, temperature=450.0, seed=77, trace=True, second_order=second_order) for c in chunks]
+        return e.kmc_state(), e.get_occupancy_all(), {k: np.concatenate([t[k] for t in trs], axis=1) for k in ("from", "to")}
+
+    s1, o1, t1 = run([120])
+    s2, o2, t2 = run([40, 80])
+    assert np.array_equal(o1, o2) and np.array_equal(s1["time"], s2["time"]) and np.array_equal(t1["to"], t2["to"])
+    assert np.all((o1 == 0).sum(axis=1) == 1)
+    assert np.array_equal(np.sort(o1, axis=1), np.tile(np.sort(occ), (32, 1)))
+    _, _, tf = run([120], second_order=False)
+    back = lambda t: float(np.mean(t["to"][:, 1:] == t["from"][:, :-1]))
+    assert back(t1) < back(tf)

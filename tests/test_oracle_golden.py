@@ -142,6 +142,28 @@ def test_kmc_replay(golden, tag, run):
 
 
 @pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("run", ["chain", "chain_tt"])
+def test_kmc_chain_replay(golden, golden_chain, tag, run):
+    """Second-order KMC (mc::KineticMcChainOmpi): the reference's selecting uniforms reproduce its trajectory."""
+    co = H.golden_coefficients(golden)
+    cfg = H.oracle_config(golden, tag)
+    pred = O.VacancyMigrationPredictorQuartic(co, cfg, H.CODES)
+    n = 30                                                 # 144 numpy barrier evaluations per step: keep the CPU suite short
+    g = lambda k: golden_chain["%s_%s_%s" % (tag, run, k)][:n]
+    tt = O.TimeTemperatureInterpolator(points=[tuple(p) for p in golden["tt_points"]]) if run == "chain_tt" else None
+    tr = O.kmc_chain(cfg, pred, 500.0, g("u2"), tt=tt, rate_corrector=(run == "chain_tt"))
+    for k in ("from", "to", "slot"):
+        assert np.array_equal(tr[k], g(k)), k
+    for k in ("time", "total_rate"):
+        assert np.allclose(tr[k], g(k), rtol=1e-9, atol=0), k
+    assert np.allclose(tr["dt"], g("dt"), rtol=1e-9, atol=4e-16 * float(np.abs(g("time")).max()))
+    for k in ("energy", "Ea", "dE"):
+        assert np.max(np.abs(tr[k] - g(k))) < TOL, k
+    assert np.array_equal(tr["temperature"], g("temperature"))
+    # (the full 121-step trajectories incl. the final occupancy are replayed by the CUDA path in tests/test_gpu_kmc.py)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
 def test_cmc_replay(golden, tag):
     co = H.golden_coefficients(golden)
     cfg = H.oracle_config(golden, tag, golden[tag + "_cmc_occ"])
