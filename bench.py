@@ -295,6 +295,8 @@ def run_ours(args):
         line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(js)
+        if not args.no_chain:
+            line["chain"] = bench_chain(engine, W, temps, occ_pinned, peak, js, n_gpus == 1 and not args.no_cpu_baseline)
         if not args.no_cmc:
             line["cmc"] = bench_cmc(torch, local_rank, js, peak, n_gpus == 1 and not args.no_cpu_baseline)
         print(json.dumps(line))
@@ -332,6 +334,46 @@ def bench_barrier_eval(engine, torch, W, peak):
     achieved = n * BYTES_PER_EVENT / (ms * 1e-3) / 1e9
     return {"kernel": "barrier_kernel", "events": n, "ms": ms, "events_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
             "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item())}
+
+
+def bench_chain(engine, W, temps, occ_pinned, peak, json_path, with_cpu):
+    """Secondary metric: second-order KMC (mc::KineticMcChainOmpi, the method script/kmc_param.txt selects) on the same
+    walkers: 144 barrier evaluations per hop, one thread block (12 half-warps = the reference's 12 ranks) per walker."""
+    from latticemontecarlo_b200 import capi
+    hops = 256
+    n = int(occ_pinned.numel())
+    ms = []
+    for it in range(4):
+        capi._check(capi.lib().lmc_engine_set_occupancy_all(engine.h, occ_pinned.numpy().ctypes.data_as(capi.C.c_void_p), capi.C.c_int64(n)))
+        engine.kmc_reset()
+        engine.kmc_chain_run(hops, temperatures=temps, seed=20260101)
+        if it:
+            ms.append(engine.last_kernel_ms())
+    st = engine.kmc_state()
+    rate = W * hops / (sum(ms) / len(ms) * 1e-3)
+    achieved = rate * 12 * BYTES_PER_KMC_STEP / 1e9
+    out = {"metric": "kmc_chain_hops_per_s", "unit": "hops/s", "value": rate, "walkers": W, "hops_per_walker": hops,
+           "kernel_ms": sum(ms) / len(ms), "barrier_evaluations_per_hop": 144, "all_walkers_advanced": bool((st["steps"] == hops).all()),
+           "roofline": {"kernel": "kmc_chain_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "note": "12 x the first-order algorithmic bytes per hop (144 events)"}}
+    if with_cpu:
+        try:
+            from oracle import ref_lib as R
+            from latticemontecarlo_b200 import synth
+            occ = walker_occupancy(0, 1)[0]
+            perm = synth.generate_to_reassigned_permutation(FACTOR)
+            occ_gen = np.empty_like(occ)
+            occ_gen[perm] = occ
+            cfg = R.RefConfig.fcc(FACTOR, occ_gen, reassign=True)
+            steps = 3000
+            res = R.kmc_chain_ompi(cfg, json_path, temperature=500.0, maximum_steps=steps - 1, seed=1, trace=False)
+            out["cpu_baseline"] = {"value": steps / res["seconds"], "unit": "hops/s", "cores": min(12, host_cores()), "kind": "reference",
+                                   "sample": "one mc::KineticMcChainOmpi trajectory, its 12 MPI ranks as 12 threads of one process "
+                                             "(in-process MPI shim), %d hops on one 8x8x8 walker; %.1f s in Simulate()" % (steps, res["seconds"])}
+        except Exception as exc:
+            out["cpu_baseline"] = {"value": None, "unit": "hops/s", "cores": 0, "kind": "reference", "sample": "failed: %r" % (exc,)}
+    return out
 
 
 def bench_cmc(torch, device, json_path, peak, with_cpu):
@@ -428,6 +470,7 @@ def main():
     ap.add_argument("--ref-hops", type=int, default=4000, help="reference arm: hops per trajectory per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cmc", action="store_true", help="skip the secondary CMC measurement")
+    ap.add_argument("--no-chain", action="store_true", help="skip the secondary second-order KMC measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

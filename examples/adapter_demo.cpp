@@ -46,6 +46,10 @@ int main(int argc, char **argv) {
     int64_t steps = 0;
     check(lmc_kmc_get_state(kmc.GetConfig().engine(), &t, &e, &steps, nullptr, nullptr));
     std::printf("KMC: %lld steps, time %.6e s, energy %+.9f eV\n", static_cast<long long>(steps), t, e);
+    mc::KineticMcChainOmpi chain(config, 499, 500.0, argv[1]);      // second-order KMC continues from the same state
+    chain.Simulate();
+    check(lmc_kmc_get_state(chain.GetConfig().engine(), &t, &e, &steps, nullptr, nullptr));
+    std::printf("chain KMC: %lld steps, time %.6e s, energy %+.9f eV\n", static_cast<long long>(steps), t, e);
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -169,6 +169,7 @@ class KineticMcFirstOmp {
     pred::LoadCoefficients(config_, json_coefficients_filename);
     check(lmc_kmc_reset(config_.engine()));
   }
+  virtual ~KineticMcFirstOmp() = default;
   void Simulate() {
     std::vector<double> t, v;
     for (const auto &p : tt_) { t.push_back(p.first); v.push_back(p.second); }
@@ -179,9 +180,14 @@ class KineticMcFirstOmp {
     prm.tt_temperature = v.data();
     prm.rate_corrector = rate_corrector_ ? 1 : 0;
     prm.seed = seed_;
-    check(lmc_kmc_run(config_.engine(), &prm, static_cast<int64_t>(maximum_steps_ + 1), nullptr, nullptr, nullptr));
+    Run(prm, static_cast<int64_t>(maximum_steps_ + 1));
   }
   [[nodiscard]] const cfg::Config &GetConfig() const { return config_; }
+
+ protected:
+  virtual void Run(const lmc_kmc_params &prm, int64_t n_steps) {
+    check(lmc_kmc_run(config_.engine(), &prm, n_steps, nullptr, nullptr, nullptr));
+  }
 
  private:
   cfg::Config config_;
@@ -190,6 +196,18 @@ class KineticMcFirstOmp {
   std::vector<std::pair<double, double>> tt_;
   bool rate_corrector_;
   uint64_t seed_;
+};
+
+// mc::KineticMcChainOmpi (mc/include/KineticMcChainOmpi.h): second-order KMC; same constructor arguments, the 12 MPI ranks
+// of the reference become the 12 half-warps of one thread block per walker.
+class KineticMcChainOmpi : public KineticMcFirstOmp {
+ public:
+  using KineticMcFirstOmp::KineticMcFirstOmp;
+
+ protected:
+  void Run(const lmc_kmc_params &prm, int64_t n_steps) override {
+    check(lmc_kmc_chain_run(GetConfig().engine(), &prm, n_steps, nullptr, nullptr));
+  }
 };
 
 // mc::CanonicalMcOmp (mc/include/CanonicalMcOmp.h); with initial_temperature > 0 and sa_maximum_steps > 0 it is

@@ -2,14 +2,14 @@
 //
 // Mirrors (file:line under /root/reference/lmc/):
 //   api::Parameter::ReadParam            api/src/Parameter.cpp:23-130   key/value file, '#' comments, unknown keys ignored
-//   api::Run dispatch on simulation_method api/src/Home.cpp:97-125       KineticMcFirstOmp, CanonicalMcSerial/Omp, SimulatedAnnealing
+//   api::Run dispatch on simulation_method api/src/Home.cpp:97-125       KineticMcFirstOmp/Mpi, KineticMcChainOmpi, CanonicalMcSerial/Omp, SimulatedAnnealing
 //   Config::ReadConfig / WriteConfig      cfg/src/Config.cpp:554-710     .cfg (and .cfg.gz through zlib)
 //   KineticMcFirstAbstract::Dump          mc/src/KineticMcAbstract.cpp:59-104   kmc_log.txt, N.cfg.gz, end.cfg.gz
 //   CanonicalMcAbstract::Dump             mc/src/CanonicalMcAbstract.cpp:53-84  cmc_log.txt
 //   SimulatedAnnealing::Dump              mc/src/SimulatedAnnealing.cpp:81-97   sa_log.txt
 //   ThermodynamicAveraging                mc/src/ThermodynamicAveraging.cpp:5-39
 // The event loop itself runs on the GPU (lmc_kmc_run / lmc_cmc_run); this file only parses, logs and dumps.
-// KineticMcFirstMpi / KineticMcChainOmpi / Ansys / Reformat are not part of the accelerated path.
+// Ansys / Reformat are not part of the accelerated path.
 #include <zlib.h>
 
 #include <algorithm>
@@ -391,7 +391,7 @@ unsigned long long make_seed(const Parameter &p) {
 }
 
 // ------------------------------------------------------------------------------------------------ KineticMcFirstOmp
-void run_kmc(const Parameter &p) {
+void run_kmc(const Parameter &p, bool second_order) {
   if (!p.map_filename.empty()) throw std::runtime_error("map_filename input is not supported: start from a .cfg");
   HostConfig config = HostConfig::read(p.config_filename);
   std::cout << "Finish config reading. Start KMC." << std::endl;
@@ -413,7 +413,8 @@ void run_kmc(const Parameter &p) {
   if (!p.replay_uniforms_filename.empty()) {
     std::ifstream ifs(p.replay_uniforms_filename);
     if (!ifs) throw std::runtime_error("Cannot open " + p.replay_uniforms_filename);
-    for (double a, b; ifs >> a >> b;) { ru1.push_back(a); ru2.push_back(b); }
+    if (second_order) for (double a; ifs >> a;) ru2.push_back(a);               // one selecting uniform per step
+    else for (double a, b; ifs >> a >> b;) { ru1.push_back(a); ru2.push_back(b); }
   }
   const bool restarted = p.restart_steps > 0;
   bool skip_first_dump = restarted;
@@ -451,12 +452,15 @@ void run_kmc(const Parameter &p) {
     tr.from = from.data(); tr.to = to.data(); tr.slot = slot.data(); tr.dt = dt.data(); tr.Ea = Ea.data(); tr.dE = dE.data();
     tr.temperature = temp_trace.data();
     const double *u1 = nullptr, *u2 = nullptr;
-    if (!ru1.empty()) {
-      if (ru1.size() < done + chunk) throw std::runtime_error("replay_uniforms_filename holds too few rows");
-      u1 = ru1.data() + done;
+    if (!ru2.empty()) {
+      if (ru2.size() < done + chunk) throw std::runtime_error("replay_uniforms_filename holds too few rows");
+      u1 = second_order ? nullptr : ru1.data() + done;
       u2 = ru2.data() + done;
     }
-    check(lmc_kmc_run(eng.e, &prm, static_cast<int64_t>(chunk), u1, u2, &tr));
+    // KineticMcChainOmpi differs from KineticMcFirstOmp only in BuildEventList / CalculateTime (mc/src/KineticMcChainOmpi.cpp:56-152);
+    // Dump, IsEscaped and the state update are those of KineticMcFirstAbstract
+    if (second_order) check(lmc_kmc_chain_run(eng.e, &prm, static_cast<int64_t>(chunk), u2, &tr));
+    else check(lmc_kmc_run(eng.e, &prm, static_cast<int64_t>(chunk), u1, u2, &tr));
     // host replay of the chunk: IsEscaped, Dump, then the state update -- the order of OneStepSimulation (:140-182)
     for (unsigned long long s = 0; s < chunk; ++s) {
       temperature = temp_trace[s];
@@ -683,12 +687,14 @@ int main(int argc, char **argv) {
     p.read(p.parameters_filename);
     std::cout << "Parameters\nsimulation_method: " << p.method << std::endl;
     if (p.method == "KineticMcFirstOmp" || p.method == "KineticMcFirstMpi") {
-      run_kmc(p);   // the MPI variant only splits the same 12 events over 12 ranks (mc/src/KineticMcFirstMpi.cpp:46-76)
+      run_kmc(p, false);   // the MPI variant only splits the same 12 events over 12 ranks (mc/src/KineticMcFirstMpi.cpp:46-76)
+    } else if (p.method == "KineticMcChainOmpi") {
+      run_kmc(p, true);    // second-order KMC; the reference's 12 ranks are the 12 half-warps of one block
     } else if (p.method == "CanonicalMcSerial" || p.method == "CanonicalMcOmp") {
       run_swap_driver(p, false);
     } else if (p.method == "SimulatedAnnealing") {
       run_swap_driver(p, true);
-    } else if (p.method == "KineticMcChainOmpi" || p.method == "Ansys" || p.method == "Reformat") {
+    } else if (p.method == "Ansys" || p.method == "Reformat") {
       std::cout << "simulation_method " << p.method << " is outside the accelerated hot path of this engine" << std::endl;
       return 2;
     } else {

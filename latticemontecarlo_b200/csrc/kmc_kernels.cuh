@@ -439,6 +439,9 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
   // per-rank results in rank (slot) order
   __shared__ double s_fwd[12], s_bwd[12], s_total_i[12], s_barrier[12], s_de[12];
   __shared__ uint8_t s_dir[12], s_is_prev[12], s_mig[12];
+  __shared__ double s_terms[8][12];
+  __shared__ int s_sel_dir;
+  __shared__ double s_sel_dt, s_sel_de;
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
@@ -532,72 +535,89 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
       s_mig[rank] = static_cast<uint8_t>(mig_i);
     }
     if (__syncthreads_or(err != 0)) break;                       // the walker stops; its state is left untouched
-    // ---- CalculateTime (KineticMcChainOmpi.cpp:93-151), replicated in every thread; sums in rank order
-    double total_k = 0.0;
+    // ---- CalculateTime + SelectEvent (KineticMcChainOmpi.cpp:93-151, KineticMcAbstract.cpp:106-123) in the first
+    // half-warp: lane r owns rank r; every sum runs sequentially in rank order like the reference's reductions
+    if (threadIdx.x < 16) {
+      double total_k = 0.0;
 #pragma unroll
-    for (int r = 0; r < 12; ++r) total_k += s_fwd[r];
-    const double t_1 = 1.0 / total_k / kPrefactorHz;
-    double beta_bar_k = 0.0, beta_k = 0.0, gamma_bar_k_j = 0.0, gamma_k_j = 0.0, beta_k_j = 0.0, alpha_k_j = 0.0, ts_num = 0.0, ts_j_num = 0.0;
-#pragma unroll
-    for (int r = 0; r < 12; ++r) {
+      for (int r = 0; r < 12; ++r) total_k += s_fwd[r];
+      const double t_1 = 1.0 / total_k / kPrefactorHz;
+      const int r = active ? lane : 0;
       const double p_ki = s_fwd[r] / total_k, p_ik = s_bwd[r] / s_total_i[r];
       const double bb = p_ki * p_ik, b = p_ki * (1 - p_ik);
       const bool prev = s_is_prev[r] != 0;
       const double t_i = 1.0 / s_total_i[r] / kPrefactorHz;
       const double ts_term = (t_1 + t_i) * bb;
-      const double c2 = prev ? 0.0 : bb, c3 = prev ? 0.0 : b, c4 = prev ? b : 0.0, c5 = prev ? p_ki : 0.0, c7 = prev ? 0.0 : ts_term;
-      if (r == 0) { beta_bar_k = bb; beta_k = b; gamma_bar_k_j = c2; gamma_k_j = c3; beta_k_j = c4; alpha_k_j = c5; ts_num = ts_term; ts_j_num = c7; }
-      else { beta_bar_k += bb; beta_k += b; gamma_bar_k_j += c2; gamma_k_j += c3; beta_k_j += c4; alpha_k_j += c5; ts_num += ts_term; ts_j_num += c7; }
-    }
-    const double ts = ts_num / beta_bar_k, ts_j = ts_j_num / gamma_bar_k_j;
-    const double inv = 1 / (1 - alpha_k_j);
-    const double t_2 = inv * (gamma_k_j * t_1 + gamma_bar_k_j * (ts_j + t_1 + beta_bar_k / beta_k * ts));
-    // second-order probabilities, cumulative in rank order; first rank whose cumulative probability is not < u
-    double u;
-    if (replay_u) u = replay_u[static_cast<int64_t>(w) * n_steps + s];
-    else {
-      uint32_t r4[4];
-      philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
-                    static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r4);
-      u = uniform53(r4[2], r4[3]);
-    }
-    int sel = 11;
-    double cumulative = 0.0;
-    bool found = false;
+      if (active) {                                              // MpiData of rank r (KineticMcChainOmpi.cpp:104-113)
+        s_terms[0][r] = bb; s_terms[1][r] = b; s_terms[2][r] = prev ? 0.0 : bb; s_terms[3][r] = prev ? 0.0 : b;
+        s_terms[4][r] = prev ? b : 0.0; s_terms[5][r] = prev ? p_ki : 0.0; s_terms[6][r] = ts_term; s_terms[7][r] = prev ? 0.0 : ts_term;
+      }
+      __syncwarp(0xFFFFu);
+      double mine = 0.0;                                         // lane q < 8 reduces field q in rank order (DataSum)
+      if (lane < 8) {
+        mine = s_terms[lane][0];
 #pragma unroll
-    for (int r = 0; r < 12; ++r) {
-      const double p_ki = s_fwd[r] / total_k, p_ik = s_bwd[r] / s_total_i[r];
-      const double b = p_ki * (1 - p_ik);
-      cumulative += s_is_prev[r] ? inv * (gamma_bar_k_j / beta_k) * beta_k_j : inv * (1 + gamma_bar_k_j / beta_k) * b;
-      if (!found && !(cumulative < u)) { found = true; sel = r; }
-    }
-    const double dt = t_2 * corr;
-    const int sel_dir = s_dir[sel];
-    const double sel_ea = s_barrier[sel], sel_de = s_de[sel];
-    const unsigned sel_mig = s_mig[sel];
-    const int nx = wrap_coord(X + tab.nn1[4 * sel_dir], px), ny = wrap_coord(Y + tab.nn1[4 * sel_dir + 1], py),
-              nz = wrap_coord(Z + tab.nn1[4 * sel_dir + 2], pz);
-    if (threadIdx.x == 0 && tracing) {
-      const int64_t at = static_cast<int64_t>(w) * n_steps + s;
-      if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
-      if (tr.to) tr.to[at] = lat.id_of_coords(nx, ny, nz);
-      if (tr.slot) tr.slot[at] = sel;
-      if (tr.dt) tr.dt[at] = dt;
-      if (tr.Ea) tr.Ea[at] = sel_ea;
-      if (tr.dE) tr.dE[at] = sel_de;
-      if (tr.total_rate) tr.total_rate[at] = total_k;
-      if (tr.temperature) tr.temperature[at] = temperature;
-    }
-    // Config::LatticeJump: lanes 0-7 of the first half-warp write the images of the old vacancy site, lanes 8-15 the new one
-    if (threadIdx.x < 16)
+        for (int q = 1; q < 12; ++q) mine += s_terms[lane][q];
+      }
+      const double beta_bar_k = __shfl_sync(0xFFFFu, mine, 0, 16), beta_k = __shfl_sync(0xFFFFu, mine, 1, 16),
+                   gamma_bar_k_j = __shfl_sync(0xFFFFu, mine, 2, 16), gamma_k_j = __shfl_sync(0xFFFFu, mine, 3, 16),
+                   beta_k_j = __shfl_sync(0xFFFFu, mine, 4, 16), alpha_k_j = __shfl_sync(0xFFFFu, mine, 5, 16),
+                   ts_num = __shfl_sync(0xFFFFu, mine, 6, 16), ts_j_num = __shfl_sync(0xFFFFu, mine, 7, 16);
+      const double ts = ts_num / beta_bar_k, ts_j = ts_j_num / gamma_bar_k_j;
+      const double inv = 1 / (1 - alpha_k_j);
+      const double t_2 = inv * (gamma_k_j * t_1 + gamma_bar_k_j * (ts_j + t_1 + beta_bar_k / beta_k * ts));
+      // second-order probability of rank r, then the running sum in rank order
+      const double prob = prev ? inv * (gamma_bar_k_j / beta_k) * beta_k_j : inv * (1 + gamma_bar_k_j / beta_k) * b;
+      __syncwarp(0xFFFFu);
+      if (active) s_terms[0][r] = prob;
+      __syncwarp(0xFFFFu);
+      double cumulative = 0.0;
+#pragma unroll
+      for (int q = 0; q < 12; ++q)
+        if (q <= lane) cumulative += s_terms[0][q];
+      double u;
+      if (replay_u) u = replay_u[static_cast<int64_t>(w) * n_steps + s];
+      else {
+        uint32_t r4[4];
+        philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
+                      static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r4);
+        u = uniform53(r4[2], r4[3]);
+      }
+      const unsigned hit = __ballot_sync(0xFFFFu, active && !(cumulative < u)) & 0xFFFu;
+      const int sel = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
+      const int sel_dir = s_dir[sel];
+      const int nx = wrap_coord(X + tab.nn1[4 * sel_dir], px), ny = wrap_coord(Y + tab.nn1[4 * sel_dir + 1], py),
+                nz = wrap_coord(Z + tab.nn1[4 * sel_dir + 2], pz);
+      const double dt = t_2 * corr;
+      if (lane == 0) {
+        s_sel_dir = sel_dir;
+        s_sel_dt = dt;
+        s_sel_de = s_de[sel];
+        if (tracing) {
+          const int64_t at = static_cast<int64_t>(w) * n_steps + s;
+          if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
+          if (tr.to) tr.to[at] = lat.id_of_coords(nx, ny, nz);
+          if (tr.slot) tr.slot[at] = sel;
+          if (tr.dt) tr.dt[at] = dt;
+          if (tr.Ea) tr.Ea[at] = s_barrier[sel];
+          if (tr.dE) tr.dE[at] = s_de[sel];
+          if (tr.total_rate) tr.total_rate[at] = total_k;
+          if (tr.temperature) tr.temperature[at] = temperature;
+        }
+      }
+      // Config::LatticeJump: lanes 0-7 write the images of the old vacancy site, lanes 8-15 those of the new one
       store_site_image(lat, o, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7,
-                       static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
+                       static_cast<uint8_t>(lane < 8 ? s_mig[sel] : vac_code));
+    }
+    __syncthreads();                               // the selection and the jump are visible to every half-warp
+    const int sel_dir = s_sel_dir;
     previous = lat.id_of_coords(X, Y, Z);          // KineticMcChainAbstract::OneStepSimulation (KineticMcAbstract.cpp:260-263)
-    time += dt;
-    energy += sel_de;
+    time += s_sel_dt;
+    energy += s_sel_de;
     ++steps;
-    X = nx; Y = ny; Z = nz;
-    __syncthreads();                               // the jump is visible to every half-warp; shared results may be overwritten
+    X = wrap_coord(X + tab.nn1[4 * sel_dir], px);
+    Y = wrap_coord(Y + tab.nn1[4 * sel_dir + 1], py);
+    Z = wrap_coord(Z + tab.nn1[4 * sel_dir + 2], pz);
   }
   if (err) atomicOr(&st.error[w], err);
   else if (threadIdx.x == 0 && st.error[w] == 0) {

@@ -232,6 +232,11 @@ class SeededKmcFirstOmp : public mc::KineticMcFirstOmp {
   using mc::KineticMcFirstOmp::KineticMcFirstOmp;
   void Reseed(uint64_t seed) { generator_.seed(seed); }
 };
+class SeededKmcChainOmpi : public mc::KineticMcChainOmpi {
+ public:
+  using mc::KineticMcChainOmpi::KineticMcChainOmpi;
+  void Reseed(uint64_t seed) { generator_.seed(seed); }
+};
 class SeededCmcSerial : public mc::CanonicalMcSerial {
  public:
   using mc::CanonicalMcSerial::CanonicalMcSerial;
@@ -831,6 +836,42 @@ double ref_kmc_first_omp_with_logs(void *config_h, const char *json, const int *
     const double t0 = now_s();
     kmc.Simulate();
     return now_s() - t0;
+  } catch (const std::exception &e) { fail(e); return -1.0; }
+}
+// mc::KineticMcChainOmpi as shipped (rank 0 writes kmc_log.txt and the cfg dumps), 12 thread-ranks, seeded generators
+double ref_kmc_chain_ompi_with_logs(void *config_h, const char *json, const int *codes, int ncodes, const char *tt_file,
+                                    int rate_corrector, double temperature, uint64_t log_dump_steps, uint64_t config_dump_steps,
+                                    uint64_t maximum_steps, uint64_t seed, int solute_disp, const char *workdir) {
+  try {
+    ScopedChdir cd(workdir);
+    ScopedQuietCout quiet;
+    constexpr int kRanks = 12;
+    lmc_shim_mpi::World world(kRanks);
+    const auto element_set = element_set_from_codes(codes, ncodes);
+    const cfg::Config &start = *static_cast<cfg::Config *>(config_h);
+    double seconds = 0.0;
+    auto body = [&](int rank) {
+      lmc_shim_mpi::attach(&world, rank);
+      omp_set_num_threads(1);
+      try {
+        SeededKmcChainOmpi kmc(start, log_dump_steps, config_dump_steps, maximum_steps, 0, 0, 0.0, 0.0, temperature, element_set, json,
+                               tt_file ? tt_file : "", rate_corrector != 0, false, solute_disp != 0);
+        kmc.Reseed(seed + static_cast<uint64_t>(rank));
+        world.barrier();
+        const double t0 = now_s();
+        kmc.Simulate();
+        world.barrier();
+        if (rank == 0) seconds = now_s() - t0;
+      } catch (const std::exception &e) {
+        std::cerr << "ref_kmc_chain_ompi_with_logs rank " << rank << ": " << e.what() << std::endl;
+        std::abort();
+      }
+      lmc_shim_mpi::detach();
+    };
+    std::vector<std::thread> ranks;
+    for (int r = 0; r < kRanks; ++r) ranks.emplace_back(body, r);
+    for (auto &t : ranks) t.join();
+    return seconds;
   } catch (const std::exception &e) { fail(e); return -1.0; }
 }
 double ref_cmc_serial_with_logs(void *config_h, const char *json, const int *codes, int ncodes, double temperature,

@@ -52,7 +52,7 @@ def lib():
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
             getattr(_lib, name).restype = C.c_int64
         for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_sa", "ref_rate_correction",
-                     "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs", "ref_kmc_chain_ompi"):
+                     "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs", "ref_kmc_chain_ompi", "ref_kmc_chain_ompi_with_logs"):
             getattr(_lib, name).restype = C.c_double
     return _lib
 
@@ -437,6 +437,20 @@ def kmc_first_omp_with_logs(config: RefConfig, json_path, workdir, elements=("Al
                                             int(bool(rate_corrector)), C.c_double(temperature), C.c_uint64(int(log_dump_steps)),
                                             C.c_uint64(int(config_dump_steps)), C.c_uint64(int(maximum_steps)),
                                             C.c_uint64(int(seed)), str(workdir).encode())
+    if sec < 0:
+        raise RuntimeError(_err())
+    return sec
+
+
+def kmc_chain_ompi_with_logs(config: RefConfig, json_path, workdir, elements=("Al", "Mg", "Zn"), temperature=500.0,
+                             maximum_steps=100, log_dump_steps=10, config_dump_steps=1000, seed=1, tt_file=None,
+                             rate_corrector=False, solute_disp=False):
+    """mc::KineticMcChainOmpi::Simulate() as shipped (rank 0 writes logs + dumps into workdir), 12 thread-ranks, seeded."""
+    _, p, n = _codes(elements)
+    sec = lib().ref_kmc_chain_ompi_with_logs(config.h, str(json_path).encode(), p, n, str(tt_file).encode() if tt_file else None,
+                                             int(bool(rate_corrector)), C.c_double(temperature), C.c_uint64(int(log_dump_steps)),
+                                             C.c_uint64(int(config_dump_steps)), C.c_uint64(int(maximum_steps)),
+                                             C.c_uint64(int(seed)), int(bool(solute_disp)), str(workdir).encode())
     if sec < 0:
         raise RuntimeError(_err())
     return sec

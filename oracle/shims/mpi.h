@@ -5,10 +5,11 @@
 // the unmodified reference driver (mc::KineticMcChainOmpi / KineticMcFirstMpi need exactly 12 ranks).  The
 // collectives then exchange through the shared World; reductions are applied in rank order 0..N-1.
 #pragma once
-#include <condition_variable>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <vector>
 typedef int MPI_Comm;
 typedef int MPI_Datatype;
@@ -30,15 +31,19 @@ struct World {
   explicit World(int n) : size(n), slot(static_cast<size_t>(n), nullptr) {}
   int size;
   std::vector<const void *> slot;      // what each rank contributes to the collective in flight
-  std::mutex m;
-  std::condition_variable cv;
-  int waiting{0};
-  unsigned long generation{0};
+  // sense-reversing spin barrier (yields after a short spin): collectives of an intra-node MPI cost about a microsecond, a
+  // condition-variable barrier would add tens of microseconds per collective to the timed reference
+  std::atomic<int> waiting{0};
+  std::atomic<unsigned long> generation{0};
   void barrier() {
-    std::unique_lock<std::mutex> lk(m);
-    const unsigned long g = generation;
-    if (++waiting == size) { waiting = 0; ++generation; cv.notify_all(); }
-    else cv.wait(lk, [&] { return generation != g; });
+    const unsigned long g = generation.load(std::memory_order_acquire);
+    if (waiting.fetch_add(1, std::memory_order_acq_rel) + 1 == size) {
+      waiting.store(0, std::memory_order_relaxed);
+      generation.store(g + 1, std::memory_order_release);
+    } else {
+      for (int spin = 0; generation.load(std::memory_order_acquire) == g; ++spin)
+        if (spin > 2000) std::this_thread::yield();
+    }
   }
 };
 inline thread_local World *tl_world = nullptr;

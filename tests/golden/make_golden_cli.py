@@ -46,6 +46,32 @@ def main():
                 "replay_uniforms_filename uniforms.txt\n" % STEPS)
     print(open(os.path.join(out, "kmc_log.txt")).read()[:600])
     print(sorted(os.listdir(out)))
+    chain(golden, js, tt)
+
+
+def chain(golden, js, tt):
+    """The same start.cfg through mc::KineticMcChainOmpi (12 thread-ranks), the method script/kmc_param.txt selects, with
+    the solute centre-of-mass columns on -> tests/golden/cli_chain_v1/."""
+    out = os.path.join(ROOT, "tests", "golden", "cli_chain_v1")
+    os.makedirs(out, exist_ok=True)
+    work = tempfile.mkdtemp()
+    shutil.copy(os.path.join(ROOT, "tests", "golden", "cli_v1", "start.cfg"), os.path.join(work, "start.cfg"))
+    cfg = R.RefConfig.read(os.path.join(work, "start.cfg"), reassign=True)
+    trace = R.kmc_chain_ompi(cfg, js, temperature=500.0, maximum_steps=STEPS, seed=SEED + 1, tt_file=tt, rate_corrector=True)
+    R.kmc_chain_ompi_with_logs(cfg, js, work, temperature=500.0, maximum_steps=STEPS, log_dump_steps=5, config_dump_steps=25,
+                               seed=SEED + 1, tt_file=tt, rate_corrector=True, solute_disp=True)
+    np.savetxt(os.path.join(out, "uniforms.txt"), trace["u2"], fmt="%.17g")
+    for name in ("kmc_log.txt", "0.cfg.gz", "25.cfg.gz", "end.cfg.gz"):
+        shutil.copy(os.path.join(work, name), os.path.join(out, name.replace(".cfg.gz", ".cfg.txt")))
+    with open(os.path.join(out, "kmc_param.txt"), "w") as f:
+        f.write("simulation_method KineticMcChainOmpi\njson_coefficients_filename coefficients.json\n"
+                "time_temperature_filename time_temperature.dat\nconfig_filename start.cfg\nlog_dump_steps 5\n"
+                "config_dump_steps 25\nmaximum_steps %d\nthermodynamic_averaging_steps 0\ntemperature 500\n"
+                "element_set Al Mg Zn\nrestart_steps 0\nrestart_energy 0\nrestart_time 0\nrate_corrector true\n"
+                "early_stop false\nsolute_disp true\n# extension of lmc_b200 (ignored by the reference):\n"
+                "replay_uniforms_filename uniforms.txt\n" % STEPS)
+    print(open(os.path.join(out, "kmc_log.txt")).read()[:600])
+    print(sorted(os.listdir(out)))
 
 
 if __name__ == "__main__":

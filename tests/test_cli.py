@@ -63,6 +63,32 @@ def test_kmc_cli_reproduces_reference_log_and_dumps(exe, golden, tmp_path):
 
 
 @pytest.mark.gpu
+def test_chain_kmc_cli_reproduces_reference_log_and_dumps(exe, golden, tmp_path):
+    """simulation_method KineticMcChainOmpi (what script/kmc_param.txt selects), solute_disp on: the reference ran as 12
+    ranks, the engine as one block of 12 half-warps; same log rows (incl. the solute centre-of-mass columns) and dumps."""
+    gold = os.path.join(ROOT, "tests", "golden", "cli_chain_v1")
+    for name in ("kmc_param.txt", "uniforms.txt"):
+        shutil.copy(os.path.join(gold, name), tmp_path / name)
+    for name in ("start.cfg", "time_temperature.dat"):
+        shutil.copy(os.path.join(GOLD, name), tmp_path / name)
+    shutil.copy(H.golden_json(golden, tmp_path), tmp_path / "coefficients.json")
+    res = subprocess.run([exe, "-p", "kmc_param.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 0, res.stderr
+    head, mine = _rows((tmp_path / "kmc_log.txt").read_text())
+    head_ref, ref = _rows(open(os.path.join(gold, "kmc_log.txt")).read())
+    assert head == head_ref and len(mine) == len(ref)
+    for a, b in zip(mine, ref):
+        assert a[0] == b[0] and a[6] == b[6] and len(a) == len(b) == 13
+        va, vb = np.array([float(x) for x in a]), np.array([float(x) for x in b])
+        assert np.allclose(va[[1, 2]], vb[[1, 2]], rtol=1e-9, atol=0)         # second-order time, temperature
+        assert np.max(np.abs(va[3:6] - vb[3:6])) < 1e-9                        # energy, Ea, dE  (eV)
+        assert np.max(np.abs(va[7:13] - vb[7:13])) < 1e-9                      # vacancy position, solute centre of mass (A)
+    for name in ("0", "25", "end"):
+        got = gzip.open(tmp_path / (name + ".cfg.gz"), "rt").read()
+        assert got == open(os.path.join(gold, name + ".cfg.txt")).read(), name
+
+
+@pytest.mark.gpu
 def test_cmc_and_sa_cli_run_and_log(exe, golden, coef_json, tmp_path):
     """CanonicalMcOmp / SimulatedAnnealing through the CLI: log format, monotone step counter, energy bookkeeping
     against the total energy of the dumped configurations (re-read through the engine)."""

@@ -37,6 +37,7 @@ def test_adapter_demo_matches_c_abi(demo, coef_json):
     ea = np.array([float(m) for m in re.findall(r"Ea = ([-0-9.e+]+) eV", res.stdout)])
     de = np.array([float(m) for m in re.findall(r"dE = ([-+0-9.e]+) eV", res.stdout)])
     assert len(ea) == 12 and "std::out_of_range as in the reference" in res.stdout and "KMC: 1000 steps" in res.stdout
+    assert "chain KMC: 500 steps" in res.stdout
     # the same occupancy through the Python binding: the demo draws it with std::mt19937_64(42), re-created here
     f = 6
     e = capi.Engine(f, device=0)
