@@ -183,6 +183,23 @@ typedef struct lmc_cmc_params {
 int lmc_cmc_reset(lmc_engine *engine, double sa_initial_temperature, uint64_t sa_maximum_steps);
 /* run until every replica has done at least n_trials more effective trials (device RNG) */
 int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
+/* ONE large lattice on the whole GPU, and on several GPUs (BASELINE configs[3]).  Same Markov-chain rules as
+ * lmc_cmc_run, but the batch is spread over a persistent cooperative grid (one thread block per SM) instead of one
+ * thread-block cluster; requires an engine with n_walkers == 1.
+ *
+ * Multi-GPU (one process per GPU, same occupancy / coefficients / seed / reset on every rank): every rank keeps the whole
+ * lattice and draws the same proposals; the dE evaluation of a batch is sharded over the ranks, and kept / accept masks
+ * and partial sums are written directly into the peers' exchange buffers over NVLink inside the kernel.  The trajectory
+ * is bit-identical for every world size.  Set-up, collective over the ranks:
+ *   1. each rank: lmc_cmc_exchange_handle(engine, h)      -- 64-byte CUDA IPC handle of its exchange buffer
+ *   2. all-gather the handles (any transport; bench.py uses torch.distributed)
+ *   3. each rank: lmc_cmc_attach_peers(engine, rank, world, handles[world][64], grid_ctas)
+ *      grid_ctas = thread blocks per GPU, identical on all ranks (0 = this device's SM count; pass the minimum over ranks)
+ *   4. barrier, then every rank calls lmc_cmc_grid_run with identical arguments.
+ * A rank that waits longer than ~5 s for a peer gives up with LMC_ERR_RUNTIME instead of hanging the GPU. */
+int lmc_cmc_grid_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
+int lmc_cmc_exchange_handle(lmc_engine *engine, void *handle64);
+int lmc_cmc_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles, int32_t grid_ctas);
 /* replay mode on replica `walker`: the n trials (site_a, site_b, u) are applied in the given order with the reference's
  * serial semantics (u is consumed only when dE >= 0).  Outputs (host, [n], optional): dE, energy and temperature before
  * each trial, accept flags. */

@@ -327,6 +327,24 @@ class Engine:
         prm = self._cmc_params(temperature, temperatures, seed, batch_size, keep)
         _check(lib().lmc_cmc_run(self.h, C.byref(prm), C.c_int64(int(n_trials))))
 
+    def cmc_grid_run(self, n_trials, temperature=800.0, seed=0, batch_size=0):
+        """ONE lattice on the whole GPU (and, after cmc_attach_peers, on several GPUs): lmc_cmc_grid_run."""
+        keep = []
+        prm = self._cmc_params(temperature, None, seed, batch_size, keep)
+        _check(lib().lmc_cmc_grid_run(self.h, C.byref(prm), C.c_int64(int(n_trials))))
+
+    def cmc_exchange_handle(self):
+        """64-byte CUDA IPC handle of this engine's exchange buffer (to be all-gathered over the ranks)."""
+        buf = C.create_string_buffer(64)
+        _check(lib().lmc_cmc_exchange_handle(self.h, buf))
+        return buf.raw
+
+    def cmc_attach_peers(self, rank, world, handles, grid_ctas=0):
+        """handles: list of `world` 64-byte handles in rank order (entry `rank` is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * world
+        _check(lib().lmc_cmc_attach_peers(self.h, int(rank), int(world), blob, int(grid_ctas)))
+
     def cmc_replay(self, site_a, site_b, u, temperature=800.0, walker=0, batch_size=0):
         a, b = _i64(site_a), _i64(site_b)
         u = np.ascontiguousarray(u, dtype=np.float64)

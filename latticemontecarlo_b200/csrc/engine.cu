@@ -14,6 +14,7 @@
 #include "kernels.cuh"
 #include "kmc_kernels.cuh"
 #include "cmc_kernels.cuh"
+#include "cmc_grid_kernels.cuh"
 #include "tables.h"
 
 namespace lmc {
@@ -82,6 +83,8 @@ Engine::Engine(const int32_t factors[3], int32_t id_order, const int32_t *elemen
 Engine::~Engine() {
   if (device >= 0) {
     cudaSetDevice(device);
+    for (int r = 0; r < 8; ++r)
+      if (cmc_peer_xchg[r] && cmc_peer_xchg[r] != d_cmc_xchg) cudaIpcCloseMemHandle(cmc_peer_xchg[r]);
     for (void *p : device_allocs) cudaFree(p);
     cudaFree(d_occ);
     cudaFree(d_error);
@@ -668,6 +671,138 @@ void Engine::kmc_get_state(double *time, double *energy, int64_t *steps, int64_t
   LMC_CUDA(cudaStreamSynchronize(stream));
 }
 
+// ------------------------------------------------------------------------------------------------ grid / multi-GPU CMC
+void Engine::cmc_grid_prepare() {
+  require_device();
+  if (d_cmc_xchg) return;
+  d_cmc_xchg = dev_alloc<CmcExchange>(1);
+  d_cmc_grid_counter = dev_alloc<unsigned long long>(1);
+  d_cmc_sequence = dev_alloc<unsigned long long>(1);
+  d_cmc_abort = dev_alloc<int>(1);
+  for (void *p : {d_cmc_xchg, static_cast<void *>(d_cmc_grid_counter), static_cast<void *>(d_cmc_sequence), static_cast<void *>(d_cmc_abort)})
+    device_allocs.push_back(p);
+  LMC_CUDA(cudaMemsetAsync(d_cmc_xchg, 0, sizeof(CmcExchange), stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_sequence, 0, 8, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  cmc_peer_xchg[0] = d_cmc_xchg;
+}
+
+void Engine::cmc_exchange_handle(void *handle64) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  if (!handle64) throw std::invalid_argument("null handle buffer");
+  cmc_grid_prepare();
+  cudaIpcMemHandle_t h;
+  LMC_CUDA(cudaIpcGetMemHandle(&h, d_cmc_xchg));
+  std::memcpy(handle64, &h, 64);
+}
+
+void Engine::cmc_attach_peers(int32_t rank, int32_t world, const void *handles, int32_t grid_ctas) {
+  cmc_grid_prepare();
+  if (world < 1 || world > kGridMaxWorld || rank < 0 || rank >= world) throw std::invalid_argument("rank / world out of range (world <= 8)");
+  if (world > 1 && !handles) throw std::invalid_argument("null handles");
+  if (n_walkers != 1) throw std::invalid_argument("the multi-GPU CMC driver runs ONE replicated lattice (n_walkers == 1)");
+  for (int r = 0; r < 8; ++r) {
+    if (cmc_peer_xchg[r] && cmc_peer_xchg[r] != d_cmc_xchg) cudaIpcCloseMemHandle(cmc_peer_xchg[r]);
+    cmc_peer_xchg[r] = nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { cmc_peer_xchg[r] = d_cmc_xchg; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const char *>(handles) + 64 * r, 64);
+    void *mapped = nullptr;
+    LMC_CUDA(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+    cmc_peer_xchg[r] = mapped;
+  }
+  cmc_world = world;
+  cmc_rank = rank;
+  cmc_grid_ctas = grid_ctas;
+  // a fresh world starts a fresh flag sequence (collective: every rank attaches before any rank runs)
+  LMC_CUDA(cudaMemsetAsync(d_cmc_xchg, 0, sizeof(CmcExchange), stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_sequence, 0, 8, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
+  require_device();
+  require_coefficients();
+  if (n_walkers != 1) throw std::invalid_argument("lmc_cmc_grid_run drives ONE lattice with the whole GPU (n_walkers == 1)");
+  if (!cmc_ready) cmc_reset(0.0, 0);
+  cmc_grid_prepare();
+  if (n_trials <= 0) return;
+  const double temp = params.temperatures ? params.temperatures[0] : params.temperature;
+  LMC_CUDA(cudaMemcpyAsync(d_cmc_temperature, &temp, 8, cudaMemcpyHostToDevice, stream));
+  unsigned long long steps0 = 0;
+  LMC_CUDA(cudaMemcpyAsync(&steps0, d_cmc_steps, 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long target = steps0 + static_cast<unsigned long long>(n_trials);
+  int sms = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  int ctas = std::min(sms, kGridMaxCtas);
+  if (cmc_grid_ctas > 0) ctas = std::min(ctas, cmc_grid_ctas);
+  // threads per CTA: a trial is one lane pair; about N / 172 trials of a batch can be mutually non-interfering
+  int threads = params.batch_size;
+  if (threads <= 0) {
+    const int64_t want_pairs = std::max<int64_t>(16, lat.num_sites / 172);
+    threads = 64;
+    while (threads < kCmcMaxThreads && static_cast<int64_t>(threads) / 2 * ctas < want_pairs) threads *= 2;
+  }
+  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
+  if (static_cast<int64_t>(ctas) * (threads / 2) > 65535) throw std::invalid_argument("batch too large for 16-bit claim priorities");
+  const int m = species.n + 1;
+  const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
+  const size_t fixed = (m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
+  int max_optin = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  const int stage_b = (fixed + b_len * 8 + 24 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
+  const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
+  LMC_CUDA(cudaFuncSetAttribute(cmc_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmc_grid_kernel, threads, smem));
+  if (per_sm < 1) throw std::runtime_error("cmc_grid_kernel does not fit on an SM");
+  CmcGridParams gp{};
+  gp.world = cmc_world;
+  gp.rank = cmc_rank;
+  for (int r = 0; r < kGridMaxWorld; ++r) gp.xchg[r] = static_cast<CmcExchange *>(cmc_peer_xchg[r]);
+  gp.xchg[cmc_rank] = static_cast<CmcExchange *>(d_cmc_xchg);
+  gp.barrier_counter = d_cmc_grid_counter;
+  gp.abort_flag = d_cmc_abort;
+  gp.sequence = d_cmc_sequence;
+  int clock_khz = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device));
+  gp.spin_limit = static_cast<long long>(clock_khz) * 1000LL * 5LL;        // ~5 s: a lost peer ends the launch instead of hanging it
+  LMC_CUDA(cudaMemsetAsync(d_cmc_grid_counter, 0, 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_abort, 0, 4, stream));
+  CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of all CTAs: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  time_begin();
+  LMC_CUDA(cudaLaunchKernelEx(&cfg, cmc_grid_kernel, lat, tab, d_occ, d_cmc_mirror, d_cmc_marks, st, static_cast<const double *>(d_cmc_temperature),
+                              static_cast<uint64_t>(params.seed), target, gp, stage_b));
+  time_end();
+  LMC_CUDA(cudaGetLastError());
+  int32_t err = 0;
+  int aborted = 0;
+  LMC_CUDA(cudaMemcpyAsync(&err, d_cmc_error, 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(&aborted, d_cmc_abort, 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  if (aborted) {
+    cmc_ready = false;
+    throw std::runtime_error("CMC grid run: barrier / peer exchange timed out (a peer rank is missing or out of step)");
+  }
+  if (err) {
+    cmc_ready = false;
+    throw std::out_of_range("CMC: Cluster not found in ClusterIndexer (two vacancies within interaction range)");
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ CMC / SA driver
 void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps) {
   require_device();
@@ -1047,6 +1182,18 @@ int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_tria
     if (!params) throw std::invalid_argument("null params");
     engine->impl->cmc_run(*params, n_trials, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   });
+}
+int lmc_cmc_grid_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    engine->impl->cmc_grid_run(*params, n_trials);
+  });
+}
+int lmc_cmc_exchange_handle(lmc_engine *engine, void *handle64) {
+  return guard([&] { engine->impl->cmc_exchange_handle(handle64); });
+}
+int lmc_cmc_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles, int32_t grid_ctas) {
+  return guard([&] { engine->impl->cmc_attach_peers(rank, world, handles, grid_ctas); });
 }
 int lmc_cmc_replay(lmc_engine *engine, int32_t walker, const lmc_cmc_params *params, int64_t n, const int64_t *site_a,
                    const int64_t *site_b, const double *u, double *dE, double *energy_before, double *temperature_before,

@@ -56,6 +56,11 @@ class Engine {
   void cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t replay_walker, int64_t n_replay, const int64_t *a,
                const int64_t *b, const double *u, double *dE, double *energy_before, double *temperature_before, uint8_t *accepted);
   void cmc_get_state(double *energy, int64_t *steps, int64_t *accepted, double *temperature);
+  // whole-GPU / multi-GPU single-lattice driver (cmc_grid_kernels.cuh)
+  void cmc_grid_prepare();
+  void cmc_exchange_handle(void *handle64);
+  void cmc_attach_peers(int32_t rank, int32_t world, const void *handles, int32_t grid_ctas);
+  void cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials);
 
   // host-side geometry (no device needed)
   void neighbors(int32_t shell, int64_t site, int64_t *out) const;
@@ -109,6 +114,11 @@ class Engine {
   int32_t *d_cmc_error{nullptr};
   double *d_cmc_temperature{nullptr};
   bool cmc_ready{false};
+  void *d_cmc_xchg{nullptr};                       // CmcExchange (IPC-shareable)
+  void *cmc_peer_xchg[8]{};                        // peer mappings (cudaIpcOpenMemHandle), [rank] = own buffer
+  unsigned long long *d_cmc_grid_counter{nullptr}, *d_cmc_sequence{nullptr};
+  int *d_cmc_abort{nullptr};
+  int cmc_world{1}, cmc_rank{0}, cmc_grid_ctas{0};
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
   cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
   bool timing_pending{false};

@@ -62,3 +62,29 @@ def gather_walker_stats(local: np.ndarray, total: int, device=None):
     if rank != 0:
         return None
     return np.concatenate([out[r][:shard_range(total, r, world)[1]].cpu().numpy() for r in range(world)])
+
+
+def evaluation_owner(warp: int, world: int) -> int:
+    """Rank that evaluates warp-group `warp` of every thread block in the multi-GPU single-lattice CMC driver
+    (cmc_grid_kernels.cuh: `owner = warp % world == rank`)."""
+    return int(warp) % int(world)
+
+
+def attach_cmc_peers(engine, rank: int, world: int, sm_count: int | None = None):
+    """Collective set-up of the multi-GPU single-lattice CMC driver (include/lmc_b200.h, lmc_cmc_attach_peers): all-gather
+    the 64-byte CUDA IPC handles of the ranks' exchange buffers and the SM counts (the grid must be identical on every
+    rank), attach, barrier.  With world == 1 (or no process group) the engine is simply reset to a world of one."""
+    import torch.distributed as dist
+    handle = engine.cmc_exchange_handle()
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        engine.cmc_attach_peers(0, 1, [handle], 0)
+        return 0
+    if sm_count is None:
+        import torch
+        sm_count = torch.cuda.get_device_properties(engine.device).multi_processor_count
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (bytes(handle), int(sm_count)))
+    grid_ctas = min(g[1] for g in gathered)
+    engine.cmc_attach_peers(rank, world, [g[0] for g in gathered], grid_ctas)
+    dist.barrier()
+    return grid_ctas
