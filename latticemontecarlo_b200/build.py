@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblmc_b200.so")
 SOURCES = ["engine.cu", "tables.cpp"]
-HEADERS = ["engine.h", "kernels.cuh", "kmc_kernels.cuh", "cmc_kernels.cuh", "tables.h", "lattice.h", "device_tables.h", os.path.join("..", "..", "include", "lmc_b200.h")]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "lmc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
@@ -47,7 +47,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         build_cli()
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    extra = os.environ.get("LMC_NVCC_EXTRA", "").split()          # e.g. -DLMC_CMC_PROFILE for the clock64 phase profile
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -27,7 +27,7 @@ constexpr int kGridPartialDoubles = 4;                  // sum, kept, accepted, 
 
 // exchange buffer of one rank (device memory, IPC-shared with the peers)
 struct CmcExchange {
-  unsigned long long flags[kGridMaxWorld];                                        // flags[r] = last sequence number rank r finished writing
+  unsigned long long flags[kGridMaxWorld][kGridMaxCtas];                          // flags[r][c]: last sequence number CTA c of rank r finished writing
   unsigned int masks[2][kGridMaxCtas][kGridMaxWarps][2];                         // [parity][cta][warp]{kept, accept}
   double partials[2][kGridMaxWorld][kGridMaxCtas][kGridPartialDoubles];          // [parity][rank][cta]
 };
@@ -82,7 +82,7 @@ __device__ __forceinline__ void sa_update_batch(SaSchedule &sa, unsigned int n_k
 }
 
 __global__ void __launch_bounds__(kCmcMaxThreads)
-cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsigned int *marks, CmcState st, const double *__restrict__ temperatures,
+cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsigned int *cells, CmcState st, const double *__restrict__ temperatures,
                 uint64_t seed, unsigned long long target_steps, CmcGridParams gp, int stage_b_table) {
   const int n_cta = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   __shared__ int32_t s_delta[2 * 43];
@@ -93,6 +93,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   __shared__ SaSchedule s_sa;
   __shared__ int32_t s_live_a[kCmcMaxThreads], s_live_b[kCmcMaxThreads];
   __shared__ int s_flag_ok;
+  __shared__ unsigned int s_kept_mask[kGridMaxWarps], s_acc_mask[kGridMaxWarps];
   extern __shared__ double s_dyn[];                // [C: m] [A: m*42*m] [B: m*204*m*m, optional] [mask: 42] [base] [codes]
 
   const int tid = threadIdx.x, B = blockDim.x;
@@ -129,6 +130,15 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   unsigned long long bar_target = 0;
   int err = 0;
   bool healthy = true;
+#ifdef LMC_CMC_PROFILE
+  __shared__ long long s_gprof[8], s_eprof;
+  if (tid == 0) { for (int q = 0; q < 8; ++q) s_gprof[q] = 0; s_eprof = 0; }
+  long long tg_prev = clock64();
+  unsigned long long n_batches = 0;
+#define LMC_GTICK(k) do { if (tid == 0) { const long long t_now = clock64(); s_gprof[k] += t_now - tg_prev; tg_prev = t_now; } } while (0)
+#else
+#define LMC_GTICK(k) do { } while (0)
+#endif
 
   for (;;) {
     const unsigned long long steps0 = s_steps, epoch = s_epoch + 1, prop0 = s_proposals, seq = s_sequence + 1;
@@ -136,11 +146,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     const int parity = static_cast<int>(seq & 1ULL);
     if (steps0 >= target_steps) break;
     __syncthreads();
-    if ((epoch & 0xFFFFULL) == 0) {                 // 16-bit epoch wrapped: forget all marks
-      for (int64_t q = gtid; q < lat.padded_size; q += window) marks[q] = 0;
+    if ((epoch & 0xFFULL) == 0) {                   // 8-bit epoch wrapped: forget all marks (keep the species bytes)
+      for (int64_t q = gtid; q < lat.padded_size; q += window) cells[q] &= kCellSpeciesMask;
       if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     }
-    const unsigned int epoch16 = static_cast<unsigned int>(epoch & 0xFFFFULL);
+    const unsigned int epoch8 = static_cast<unsigned int>(epoch & 0xFFULL);
     // ---------------- proposals: identical on every rank (same counters), first unlike-species pair of 8 draws
     int32_t a = -1, b = -1;
     {
@@ -160,6 +170,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
       for (int d = kCmcDraws - 1; d >= 0; --d)
         if (sa_[d] != sb_[d]) { a = static_cast<int32_t>(ida[d]); b = static_cast<int32_t>(idb[d]); }
     }
+    LMC_GTICK(0);
     // ---------------- compaction of this CTA's live trials
     const bool has = a >= 0;
     int n_live = 0;
@@ -180,25 +191,34 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     }
     __syncthreads();
     if (n_live > half) n_live = half;               // surplus proposals are dropped (redrawn in a later batch)
+    LMC_GTICK(1);
     // ---------------- claims: every rank marks ALL live trials (lane pair i = trial i, one site per lane)
     bool live = pair_id < n_live;
     int xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
     const unsigned int gpair = static_cast<unsigned int>(cta * half + pair_id);   // position of the trial in the batch = priority
-    const unsigned int my_mark = (epoch16 << 16) | (0xFFFFu - gpair);
+    const unsigned int my_mark = (epoch8 << 16) | (0xFFFFu - gpair);      // 24 bits
     if (live) {
       a = s_live_a[pair_id]; b = s_live_b[pair_id];
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
-      if (side == 0) mark_site(lat, marks, xa, ya, za, my_mark);
-      else mark_site(lat, marks, xb, yb, zb, my_mark);
+      const int mx = side ? xb : xa, my = side ? yb : ya, mz = side ? zb : za;
+      const unsigned species = cells[lat.padded_index(mx, my, mz)] & kCellSpeciesMask;
+      mark_site(lat, cells, mx, my, mz, (my_mark << 8) | species);
     }
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
+    LMC_GTICK(2);
     // ---------------- evaluation: warp w belongs to rank (w mod world)
     const bool owner = (warp % world) == rank;
     bool conflict = false, same = false;
     double de = 0.0;
-    if (live && owner) de = swap_side_energy_change_marked(lat, tab, tv, o, marks, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
+#ifdef LMC_CMC_PROFILE
+    const long long te0 = clock64();
+#endif
+    if (live && owner) de = swap_side_energy_change_marked(lat, tab, tv, cells, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
                                                            &conflict, &same);
+#ifdef LMC_CMC_PROFILE
+    const long long te1 = clock64();
+#endif
     conflict = __shfl_xor_sync(0xffffffffu, conflict ? 1 : 0, 1) || conflict;
     de += __shfl_xor_sync(0xffffffffu, de, 1);
     bool kept = live && owner && !conflict;
@@ -225,34 +245,40 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
         s_warp_cnt[warp] = __popc(kept_mask & 0x55555555u);      // one lane per pair
         s_warp_acc[warp] = __popc(acc_mask & 0x55555555u);
       }
-      if (world > 1 && owner && (tid & 31) < world) {            // lane d publishes this group's masks in rank d's buffer
-        volatile unsigned int *dst = gp.xchg[tid & 31]->masks[parity][cta][warp];
-        dst[0] = kept_mask;
-        dst[1] = acc_mask;
-      }
+      if ((tid & 31) == 0) { s_kept_mask[warp] = kept_mask; s_acc_mask[warp] = acc_mask; }
     }
+#ifdef LMC_CMC_PROFILE
+    const long long te2 = clock64();
+    if (tid == 0) { s_gprof[7] += te1 - te0; s_eprof += te2 - te1; }
+#endif
     const int block_err = __syncthreads_or(err != 0);
-    if (tid < world) {                              // this CTA's partial, to every rank (own warps only; fixed order)
+    LMC_GTICK(3);
+    if (tid < world) {
+      // thread d ships this CTA's results to rank d: partial sums (own warps only; fixed order), the masks of the warp
+      // groups this rank evaluated, then -- after a system-scope fence -- the CTA's flag.  CTA c of rank d only waits for
+      // the CTAs c of the other ranks (it applies its own trials), so no grid barrier is needed for the exchange.
       double e = 0.0;
       unsigned int n_kept = 0, n_acc = 0;
       for (int q = 0; q < n_warps; ++q) { e += s_warp_sum[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
-      double *dst = gp.xchg[tid]->partials[parity][rank][cta];
-      volatile double *vd = dst;
+      CmcExchange *dst = gp.xchg[tid];
+      volatile double *vd = dst->partials[parity][rank][cta];
       vd[0] = e; vd[1] = static_cast<double>(n_kept); vd[2] = static_cast<double>(n_acc); vd[3] = static_cast<double>(block_err);
+      if (world > 1 && tid != rank) {
+        for (int q = rank; q < n_warps; q += world) {
+          volatile unsigned int *mk = dst->masks[parity][cta][q];
+          mk[0] = s_kept_mask[q];
+          mk[1] = s_acc_mask[q];
+        }
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned long long *>(&dst->flags[rank][cta]) = seq;
+      }
     }
     if (world > 1) {
-      // all of this rank's CTAs have written -> raise this rank's flag everywhere -> wait for every rank's flag
-      __threadfence_system();
-      if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
-      if (cta == 0 && tid < world) {
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&gp.xchg[tid]->flags[rank]) = seq;
-      }
       if (tid == 0) s_flag_ok = 1;
       __syncthreads();
-      if (tid < world) {
+      if (tid < world && tid != rank) {
         const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned long long *>(&mine->flags[tid]) < seq) {
+        while (*reinterpret_cast<volatile unsigned long long *>(&mine->flags[tid][cta]) < seq) {
           if (*reinterpret_cast<volatile int *>(gp.abort_flag) || clock64() - t0 > gp.spin_limit) {
             *reinterpret_cast<volatile int *>(gp.abort_flag) = 1;
             s_flag_ok = 0;
@@ -263,26 +289,44 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
       }
       __syncthreads();
       if (!s_flag_ok) { healthy = false; break; }
-      const volatile unsigned int *mk = mine->masks[parity][cta][warp];
-      if (!owner) { kept_mask = mk[0]; acc_mask = mk[1]; }
+      if (!owner) {
+        const volatile unsigned int *mk = mine->masks[parity][cta][warp];
+        kept_mask = mk[0]; acc_mask = mk[1];
+      }
     }
+    LMC_GTICK(4);
     // ---------------- apply every accepted swap of this CTA's trials (all ranks alike)
     if (live && ((acc_mask >> (tid & 31)) & 1u)) {
       const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
       const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
       __syncwarp(__activemask());                   // both lanes have read the old species before either writes
-      if (side == 0) { store_site(lat, o, xa, ya, za, eb); by_id[a] = eb; }
-      else { store_site(lat, o, xb, yb, zb, ea); by_id[b] = ea; }
+      if (side == 0) { store_site(lat, o, xa, ya, za, eb); store_site_cells(lat, cells, xa, ya, za, eb); by_id[a] = eb; }
+      else { store_site(lat, o, xb, yb, zb, ea); store_site_cells(lat, cells, xb, yb, zb, ea); by_id[b] = ea; }
     }
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
+    LMC_GTICK(5);
     // ---------------- totals: partials of all ranks and CTAs in one fixed order (identical in every CTA of every rank)
     int any_err = 0;
     if (warp == 0) {
       double e = 0.0, k = 0.0, ac = 0.0, er = 0.0;
       const int n_part = world * n_cta;
-      for (int q = tid; q < n_part; q += 32) {
-        const volatile double *src = mine->partials[parity][q / n_cta][q % n_cta];
-        e += src[0]; k += src[1]; ac += src[2]; er += src[3];
+      // L2 loads (the entries were written by other SMs / other GPUs before the barrier), eight entries in flight per lane
+      for (int q0 = tid; q0 < n_part; q0 += 32 * 8) {
+        double2 lo[8], hi[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int q = q0 + 32 * j;
+          if (q < n_part) {
+            const double2 *src = reinterpret_cast<const double2 *>(mine->partials[parity][q / n_cta][q % n_cta]);
+            lo[j] = __ldcg(src);
+            hi[j] = __ldcg(src + 1);
+          } else {
+            lo[j] = make_double2(0.0, 0.0);
+            hi[j] = make_double2(0.0, 0.0);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { e += lo[j].x; k += lo[j].y; ac += hi[j].x; er += hi[j].y; }
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
@@ -307,9 +351,21 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
       }
     }
     __syncthreads();
+    LMC_GTICK(6);
+#ifdef LMC_CMC_PROFILE
+    ++n_batches;
+#endif
     any_err = s_flag_ok == 0;
     if (any_err) { err |= kErrExtraVacancy; break; }
   }
+#ifdef LMC_CMC_PROFILE
+  if (tid == 0 && cta == 0)
+    printf("grid cmc profile rank %d (cycles/batch): propose %lld compact %lld mark+barrier %lld evaluate %lld exchange %lld apply+barrier %lld reduce %lld | "
+           "thread0: dE call %lld accept+reduce %lld | batches %llu ctas %d threads %d\n", rank, s_gprof[0] / (long long)max(1ULL, n_batches), s_gprof[1] / (long long)max(1ULL, n_batches),
+           s_gprof[2] / (long long)max(1ULL, n_batches), s_gprof[3] / (long long)max(1ULL, n_batches), s_gprof[4] / (long long)max(1ULL, n_batches),
+           s_gprof[5] / (long long)max(1ULL, n_batches), s_gprof[6] / (long long)max(1ULL, n_batches), s_gprof[7] / (long long)max(1ULL, n_batches),
+           s_eprof / (long long)max(1ULL, n_batches), n_batches, n_cta, B);
+#endif
   __syncthreads();
   if (cta == 0 && tid == 0) {
     st.energy[0] = s_energy; st.steps[0] = s_steps; st.accepted[0] = s_accepted; st.proposals[0] = s_proposals;

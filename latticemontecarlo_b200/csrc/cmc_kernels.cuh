@@ -83,7 +83,14 @@ __device__ __forceinline__ void sa_update(SaSchedule &s, bool accepted, double e
   s.temperature *= cool_factor;
 }
 
-// write a claim mark on a site and all its periodic halo images (the checkers read marks through base + offset)
+// CMC cell array: one 32-bit word per padded cell = claim mark (bits 31..8: batch epoch (8) | inverted priority (16)) over the
+// species code (bits 7..0), so that ONE load per neighbour delivers both the species for dE and the mark for the conflict
+// test.  The byte array `occ` stays the authoritative occupancy for every other entry point; both are written on accept.
+constexpr unsigned kCellSpeciesMask = 0xFFu;
+
+// write a claim on a site and all its periodic halo images (the checkers read cells through base + offset).
+// `mark` = (mark24 << 8) | species of that site: atomicMax replaces the word only if the mark is higher, and then writes
+// back the same species, so no compare-and-swap loop is needed.
 __device__ __forceinline__ void mark_site(const LatticeDesc &lat, unsigned int *marks, int X, int Y, int Z, unsigned int mark) {
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
   atomicMax(marks + lat.padded_index(X, Y, Z), mark);
@@ -104,6 +111,26 @@ __device__ __forceinline__ void mark_site(const LatticeDesc &lat, unsigned int *
   }
 }
 
+// species byte of a site and all its periodic halo images in the cell array (little endian: byte 0 of the word)
+__device__ __forceinline__ void store_site_cells(const LatticeDesc &lat, unsigned int *cells, int X, int Y, int Z, uint8_t code) {
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  const int64_t base = lat.padded_index(X, Y, Z);
+  auto put = [&](int64_t idx) { reinterpret_cast<uint8_t *>(cells + idx)[0] = code; };
+  put(base);
+  const int sx = X < kHalo ? px : (X >= px - kHalo ? -px : 0);
+  const int sy = Y < kHalo ? py : (Y >= py - kHalo ? -py : 0);
+  const int sz = Z < kHaloZ ? pz : (Z >= pz - kHaloZ ? -pz : 0);
+  if ((sx | sy | sz) == 0) return;
+  const int64_t ix = static_cast<int64_t>(sx) * lat.ny * lat.nz, iy = static_cast<int64_t>(sy) * lat.nz, iz = sz / 2;
+  if (sx) put(base + ix);
+  if (sy) put(base + iy);
+  if (sz) put(base + iz);
+  if (sx && sy) put(base + ix + iy);
+  if (sx && sz) put(base + ix + iz);
+  if (sy && sz) put(base + iy + iz);
+  if (sx && sy && sz) put(base + ix + iy + iz);
+}
+
 // Tables of the single-site energy model staged in shared memory (a CMC replica is one thread block with few warps,
 // so the dependent table walk must not pay global-memory latency).  B stays in global memory if it does not fit.
 struct SiteTablesView {
@@ -113,39 +140,31 @@ struct SiteTablesView {
   int m, n_pairs;
 };
 
-// 43-site gather of species AND claim marks.  Species codes are staged in shared memory (codes[t * stride], one
-// column per thread) for the table walk; returns the solute mask; *conflict is set if any site of the neighbourhood
-// carries a mark of this epoch with higher priority than `my_mark` (CanonicalMcOmp.cpp:47-72: a trial may not touch
-// the neighbourhood of an earlier trial of the batch).
-__device__ __forceinline__ uint64_t gather_site_env_marked(const uint8_t *occ, const unsigned int *marks, int64_t base,
-                                                           const int32_t *__restrict__ drow, unsigned solvent, uint8_t *codes, int stride,
-                                                           int64_t override_index, unsigned override_code, unsigned my_mark,
-                                                           bool *conflict) {
+// 43-site gather of species AND claim marks: one cell word per neighbour.  Species codes are staged in shared memory
+// (codes[t * stride], one column per thread) for the table walk; returns the solute mask; *conflict is set if any site
+// of the neighbourhood carries a mark of this epoch with higher priority than `my_mark` (CanonicalMcOmp.cpp:47-72: a
+// trial may not touch the neighbourhood of an earlier trial of the batch).
+__device__ __forceinline__ uint64_t gather_site_env_marked(const unsigned int *cells, int64_t base, const int32_t *__restrict__ drow,
+                                                           unsigned solvent, uint8_t *codes, int stride, int64_t override_index,
+                                                           unsigned override_code, unsigned my_mark, bool *conflict) {
   uint32_t lo = 0, hi = 0;
   unsigned worst = 0;
-  // chunks of 22 / 21 sites: enough loads in flight to cover the latency, few enough live registers not to spill
+  // plain (L1-cached) loads: the cells were last written before the preceding cluster / grid barrier, whose acquire
+  // invalidates this SM's L1; neighbouring sites share 32-byte sectors.  All 43 loads are in flight at once.
+  unsigned cell[43];
 #pragma unroll
-  for (int t0 = 0; t0 < 43; t0 += 22) {
-    unsigned cd[22], mk[22];
+  for (int t = 0; t < 43; ++t) cell[t] = cells[base + drow[t]];
 #pragma unroll
-    for (int q = 0; q < 22; ++q) {
-      if (t0 + q >= 43) continue;
-      cd[q] = __ldcg(occ + base + drow[t0 + q]);         // the lattice is shared by the CTAs of a cluster: read at L2
-      mk[q] = __ldcg(marks + base + drow[t0 + q]);   // marks are written with atomics by other threads: bypass L1
-    }
-#pragma unroll
-    for (int q = 0; q < 22; ++q) {
-      const int t = t0 + q;
-      if (t >= 43) continue;
-      worst = mk[q] > worst ? mk[q] : worst;
-      unsigned c = cd[q];
-      if (base + drow[t] == override_index) c = override_code;
-      codes[t * stride] = static_cast<uint8_t>(c);
-      if (t == kCentrePos) continue;
-      const int e = t - (t > kCentrePos);
-      if (e < 32) lo |= (c != solvent) ? (1u << e) : 0u;
-      else hi |= (c != solvent) ? (1u << (e - 32)) : 0u;
-    }
+  for (int t = 0; t < 43; ++t) {
+    const unsigned mk = cell[t] >> 8;
+    worst = mk > worst ? mk : worst;
+    unsigned c = cell[t] & kCellSpeciesMask;
+    if (base + drow[t] == override_index) c = override_code;
+    codes[t * stride] = static_cast<uint8_t>(c);
+    if (t == kCentrePos) continue;
+    const int e = t - (t > kCentrePos);
+    if (e < 32) lo |= (c != solvent) ? (1u << e) : 0u;
+    else hi |= (c != solvent) ? (1u << (e - 32)) : 0u;
   }
   // marks of older epochs are numerically smaller than any mark of the current epoch
   if (worst > my_mark) *conflict = true;
@@ -183,13 +202,13 @@ __device__ __forceinline__ double site_energy_change_staged(const SiteTablesView
 // lanes (side 0: the site that changes first, side 1: the other one, which sees the first already changed when the pair
 // is coupled), each with the claim check fused into its 43-site gather.  Returns this side's H(new) - H(old).
 __device__ __forceinline__ double swap_side_energy_change_marked(const LatticeDesc &lat, const DevTables &tab, const SiteTablesView &tv,
-                                                                 const uint8_t *occ, const unsigned int *marks,
+                                                                 const unsigned int *cells,
                                                                  const int32_t *__restrict__ s_delta, uint8_t *codes, int stride, int side,
                                                                  int xa, int ya, int za, int xb, int yb, int zb, unsigned my_mark,
                                                                  bool *conflict, bool *same_species) {
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
   int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
-  unsigned ea = __ldcg(occ + base_a), eb = __ldcg(occ + base_b);
+  unsigned ea = cells[base_a] & kCellSpeciesMask, eb = cells[base_b] & kCellSpeciesMask;
   int dx = xb - xa, dy = yb - ya, dz = zb - za;
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
   dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
@@ -204,18 +223,15 @@ __device__ __forceinline__ double swap_side_energy_change_marked(const LatticeDe
     dx = -dx; dy = -dy; dz = -dz;
   }
   *same_species = ea == eb;
-  uint64_t sol;
-  if (side == 0) {
-    sol = gather_site_env_marked(occ, marks, base_a, s_delta + zpa * 43, solvent, codes, stride, -1, 0, my_mark, conflict);
-    if (ea == eb) return 0.0;
-    return site_energy_change_staged(tv, static_cast<int>(ea), static_cast<int>(eb), sol, codes, stride);
-  }
-  // the halo images of the first site are not updated in memory, so the override is applied by *position*: the first
-  // site sits at displacement (-dx,-dy,-dz) from the second
-  const int64_t override_index = coupled ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
-  sol = gather_site_env_marked(occ, marks, base_b, s_delta + zpb * 43, solvent, codes, stride, override_index, eb, my_mark, conflict);
+  // both lanes of a pair run ONE instruction stream: the side only selects the operands (no divergent copies of the gather)
+  // side 1: the halo images of the first site are not updated in memory, so the override is applied by *position*: the
+  // first site sits at displacement (-dx,-dy,-dz) from the second
+  const int64_t base = side ? base_b : base_a;
+  const int zp = side ? zpb : zpa;
+  const int64_t override_index = (side && coupled) ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
+  const uint64_t sol = gather_site_env_marked(cells, base, s_delta + zp * 43, solvent, codes, stride, override_index, eb, my_mark, conflict);
   if (ea == eb) return 0.0;
-  return site_energy_change_staged(tv, static_cast<int>(eb), static_cast<int>(ea), sol, codes, stride);
+  return site_energy_change_staged(tv, static_cast<int>(side ? eb : ea), static_cast<int>(side ? ea : eb), sol, codes, stride);
 }
 
 constexpr int kCmcMaxThreads = 512;
@@ -228,6 +244,12 @@ __global__ void cmc_mirror_kernel(LatticeDesc lat, const uint8_t *__restrict__ p
   by_id[blockIdx.y * lat.num_sites + id] = padded[blockIdx.y * lat.padded_size + lat.padded_index_of_id(id)];
 }
 
+// cell array from the padded occupancy (all cells incl. the halo): species byte, no marks
+__global__ void cmc_cells_init_kernel(int64_t n, const uint8_t *__restrict__ padded, unsigned int *__restrict__ cells) {
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q < n) cells[q] = padded[q];
+}
+
 // One thread-block CLUSTER per replica: the CTAs of the cluster share the batch (proposals, marks, evaluation) so that the
 // scattered 43-site gathers of a batch are spread over several SMs' L1/LSU pipes; batch bookkeeping is replicated in every
 // CTA and kept identical by exchanging per-CTA partial sums through distributed shared memory after each batch.
@@ -238,7 +260,7 @@ struct CmcPartial {
 };
 
 __global__ void __launch_bounds__(kCmcMaxThreads)
-cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, uint8_t *mirror, unsigned int *marks_all,
+cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, uint8_t *mirror, unsigned int *cells_all,
                CmcState st, const double *__restrict__ temperatures, uint64_t seed, unsigned long long target_steps, CmcReplay replay,
                unsigned long long n_replay, int stage_b_table) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -258,7 +280,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const int tid = threadIdx.x, B = blockDim.x;
   uint8_t *o = occ + w * walker_stride;
   uint8_t *by_id = mirror + static_cast<size_t>(w) * lat.num_sites;
-  unsigned int *marks = marks_all + static_cast<size_t>(w) * lat.padded_size;
+  unsigned int *cells = cells_all + static_cast<size_t>(w) * lat.padded_size;
   for (int q = tid; q < 2 * 43; q += B) s_delta[q] = tab.site_delta[q];
   // ---- stage the site tables in shared memory
   const int m = tab.n_species + 1;
@@ -307,11 +329,11 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     if (replaying ? (rpos >= n_replay) : (steps0 >= target_steps)) break;
     __syncthreads();
     if (tid == 0) s_first_conflict = 0xFFFFFFFFu;
-    if ((epoch & 0xFFFFULL) == 0) {                 // 16-bit epoch wrapped: forget all marks
-      for (int64_t q = gtid; q < lat.padded_size; q += window) marks[q] = 0;
+    if ((epoch & 0xFFULL) == 0) {                   // 8-bit epoch wrapped: forget all marks (keep the species bytes)
+      for (int64_t q = gtid; q < lat.padded_size; q += window) cells[q] &= kCellSpeciesMask;
       cluster.sync();
     }
-    const unsigned int epoch16 = static_cast<unsigned int>(epoch & 0xFFFFULL);
+    const unsigned int epoch8 = static_cast<unsigned int>(epoch & 0xFFULL);
     // ---------------- phase 1a: proposals (GenerateLatticeIdJumpPair: uniform ids, redrawn while the species are equal)
     int32_t a = -1, b = -1;
     if (replaying) {
@@ -373,7 +395,7 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     bool live = pair_id < n_live;
     int xa = 0, ya = 0, za = 0, xb = 0, yb = 0, zb = 0;
     const unsigned int prio = static_cast<unsigned int>(rank * half + pair_id);
-    const unsigned int my_mark = (epoch16 << 16) | (0xFFFFu - prio);
+    const unsigned int my_mark = (epoch8 << 16) | (0xFFFFu - prio);       // 24 bits
     if (live) {
       a = s_live_a[pair_id]; b = s_live_b[pair_id];
       live = a >= 0;
@@ -381,15 +403,16 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     if (live) {
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
-      if (side == 0) mark_site(lat, marks, xa, ya, za, my_mark);
-      else mark_site(lat, marks, xb, yb, zb, my_mark);
+      const int mx = side ? xb : xa, my = side ? yb : ya, mz = side ? zb : za;
+      const unsigned species = cells[lat.padded_index(mx, my, mz)] & kCellSpeciesMask;
+      mark_site(lat, cells, mx, my, mz, (my_mark << 8) | species);
     }
     cluster.sync();
     LMC_TICK(2);
     // ---------------- phase 2: conflict check fused with the dE gathers, one site per lane
     bool conflict = false, same = false;
     double de = 0.0;
-    if (live) de = swap_side_energy_change_marked(lat, tab, tv, o, marks, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
+    if (live) de = swap_side_energy_change_marked(lat, tab, tv, cells, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
                                                   &conflict, &same);
     conflict = __shfl_xor_sync(0xffffffffu, conflict ? 1 : 0, 1) || conflict;
     de += __shfl_xor_sync(0xffffffffu, de, 1);      // both lanes of the pair now hold the swap's dE
@@ -430,8 +453,8 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
         const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
         __syncwarp(__activemask());                 // both lanes have read the old species before either writes
-        if (side == 0) { store_site(lat, o, xa, ya, za, eb); by_id[a] = eb; }
-        else { store_site(lat, o, xb, yb, zb, ea); by_id[b] = ea; }
+        if (side == 0) { store_site(lat, o, xa, ya, za, eb); store_site_cells(lat, cells, xa, ya, za, eb); by_id[a] = eb; }
+        else { store_site(lat, o, xb, yb, zb, ea); store_site_cells(lat, cells, xb, yb, zb, ea); by_id[b] = ea; }
       }
     }
     kept = kept && side == 0;                       // count every trial once
@@ -518,6 +541,8 @@ cmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
               const uint8_t e1 = __ldcg(o + lat.padded_index(x1, y1, z1)), e2 = __ldcg(o + lat.padded_index(x2, y2, z2));
               store_site(lat, o, x1, y1, z1, e2);
               store_site(lat, o, x2, y2, z2, e1);
+              store_site_cells(lat, cells, x1, y1, z1, e2);
+              store_site_cells(lat, cells, x2, y2, z2, e1);
               by_id[replay.a[pos]] = e2;
               by_id[replay.b[pos]] = e1;
             }

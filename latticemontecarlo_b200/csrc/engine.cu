@@ -336,6 +336,7 @@ void Engine::set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_
   require_device();
   if (walker < 0 || count < 1 || walker + count > n_walkers) throw std::invalid_argument("walker index out of range");
   if (n != lat.num_sites * count) throw std::invalid_argument("occupancy length must be num_sites per walker");
+  cmc_ready = false;                       // the CMC mirror / cell arrays are rebuilt by the next lmc_cmc_reset (or run)
   uint8_t *d_in = static_cast<uint8_t *>(scratch(static_cast<size_t>(n)));
   LMC_CUDA(cudaMemcpyAsync(d_in, occ, static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
   const int threads = 256;
@@ -373,6 +374,7 @@ void Engine::lattice_jump(int32_t walker, int64_t a, int64_t b) {
   require_device();
   if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
   if (a < 0 || b < 0 || a >= lat.num_sites || b >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  cmc_ready = false;
   lattice_jump_kernel<<<1, 32, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker) * lat.padded_size, a, b);
   LMC_CUDA(cudaGetLastError());
   LMC_CUDA(cudaStreamSynchronize(stream));
@@ -826,7 +828,6 @@ void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps)
   LMC_CUDA(cudaMemsetAsync(d_cmc_proposals, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_epoch, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_error, 0, nw * 4, stream));
-  LMC_CUDA(cudaMemsetAsync(d_cmc_marks, 0, nw * static_cast<size_t>(lat.padded_size) * 4, stream));
   {
     const unsigned blocks = static_cast<unsigned>((lat.num_sites + 255) / 256);
     for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
@@ -835,6 +836,10 @@ void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps)
                                                               d_cmc_mirror + static_cast<int64_t>(w0) * lat.num_sites);
       ++launch_count;
     }
+    // claim marks cleared, species bytes copied: the packed cell array of the CMC kernels
+    const int64_t n_cells = static_cast<int64_t>(n_walkers) * lat.padded_size;
+    cmc_cells_init_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, stream>>>(n_cells, d_occ, d_cmc_marks);
+    ++launch_count;
     LMC_CUDA(cudaGetLastError());
   }
   // SimulatedAnnealing constructor (mc/src/SimulatedAnnealing.cpp:53-56; ratios mc/include/SimulatedAnnealing.h:45-57)
