@@ -181,7 +181,8 @@ typedef struct lmc_cmc_params {
 /* reset steps / energy / counters of every replica; with sa_maximum_steps > 0 the SimulatedAnnealing schedule is armed:
  * T0 = sa_initial_temperature, T *= exp(-3/max) per trial, acceptance window 0.001 max, reheats (SimulatedAnnealing.h:42-68) */
 int lmc_cmc_reset(lmc_engine *engine, double sa_initial_temperature, uint64_t sa_maximum_steps);
-/* run until every replica has done at least n_trials more effective trials (device RNG) */
+/* run until every replica has done at least n_trials more effective trials (device RNG).  An engine with ONE replica of
+ * >= 32000 sites (or one attached to peers) is driven by the whole-GPU kernel of lmc_cmc_grid_run. */
 int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
 /* ONE large lattice on the whole GPU, and on several GPUs (BASELINE configs[3]).  Same Markov-chain rules as
  * lmc_cmc_run, but the batch is spread over a persistent cooperative grid (one thread block per SM) instead of one

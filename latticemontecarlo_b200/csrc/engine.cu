@@ -861,6 +861,12 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
                      uint8_t *accepted) {
   require_device();
   require_coefficients();
+  // one lattice: the whole GPU (cooperative grid) beats one cluster of <= 16 SMs from ~32k sites on; a world of several
+  // GPUs (lmc_cmc_attach_peers) always runs the grid kernel
+  if (n_replay <= 0 && n_walkers == 1 && (cmc_world > 1 || lat.num_sites >= 32000)) {
+    cmc_grid_run(params, n_trials);
+    return;
+  }
   if (!cmc_ready) cmc_reset(0.0, 0);
   const size_t nw = static_cast<size_t>(n_walkers);
   std::vector<double> temps(nw, params.temperature);

@@ -101,3 +101,37 @@ def test_batched_simulated_annealing_schedule(coef_json):
     assert 0.3 * base < st["temperature"][0] <= base * 1.1 ** 5 * (1 + 1e-9), (st["temperature"][0], base)
     assert abs((e.total_energy() - e0) - st["energy"][0]) < 5e-9
     assert st["energy"][0] < 0.0                                 # annealing lowers the energy of a random alloy
+
+
+def test_whole_gpu_single_lattice_driver(coef_json):
+    """lmc_cmc_grid_run (one lattice spread over a cooperative grid): energy bookkeeping == total-energy difference,
+    composition conserved, reproducible, chunkable; lmc_cmc_run dispatches to it for one large replica; the simulated
+    annealing schedule runs through it."""
+    f = 24
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=0)
+    e.load_coefficients(coef_json)
+    occ = synth.random_alloy(f, 0.05, 0.05, seed=21, vacancy_site=None)
+
+    def run(fn, chunks, **reset):
+        e.set_occupancy(occ)
+        e0 = e.total_energy()
+        e.cmc_reset(**reset)
+        for n in chunks:
+            fn(n, temperature=700.0, seed=3)
+        st = e.cmc_state()
+        final = e.get_occupancy(0)
+        assert abs((e.total_energy() - e0) - st["energy"][0]) < 5e-9
+        assert np.array_equal(np.sort(final), np.sort(occ))
+        return st, final
+
+    st1, o1 = run(e.cmc_grid_run, [30000])
+    st2, o2 = run(e.cmc_grid_run, [30000])
+    assert np.array_equal(o1, o2) and st1["energy"][0] == st2["energy"][0] and st1["steps"][0] == st2["steps"][0]
+    assert 30000 <= st1["steps"][0] < 30000 + 148 * 256 and 0.02 < st1["accepted"][0] / st1["steps"][0] < 0.9
+    st3, o3 = run(e.cmc_run, [30000])                                # 55k sites, one replica -> same kernel
+    assert np.array_equal(o1, o3) and st1["energy"][0] == st3["energy"][0]
+    st4, _ = run(e.cmc_grid_run, [40000], sa_initial_temperature=900.0, sa_maximum_steps=40000)
+    base = 900.0 * np.exp(-3.0 * st4["steps"][0] / 40000)
+    assert 0.3 * base < st4["temperature"][0] <= base * 1.1 ** 5 * (1 + 1e-9) and st4["energy"][0] < 0.0
+    with pytest.raises(capi.LmcInvalidArgument):
+        capi.Engine(6, n_walkers=2, device=0).cmc_grid_run(10)       # one lattice only

@@ -45,3 +45,14 @@ def test_two_rank_gloo_sharding():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, 11), nprocs=2, join=True)
+
+
+def test_evaluation_owner_partitions_the_warp_groups():
+    """Multi-GPU single-lattice CMC: every warp group of a thread block has exactly one evaluating rank, and the groups
+    are spread evenly (cmc_grid_kernels.cuh: owner = warp % world)."""
+    from latticemontecarlo_b200 import sharding
+    for world in (1, 2, 3, 4, 8):
+        owners = [sharding.evaluation_owner(w, world) for w in range(16)]
+        assert all(0 <= o < world for o in owners)
+        counts = [owners.count(r) for r in range(world)]
+        assert max(counts) - min(counts) <= 1
