@@ -25,12 +25,40 @@ constexpr int kGridMaxCtas = 160;                       // >= SM count of a B200
 constexpr int kGridMaxWarps = kCmcMaxThreads / 32;      // warps (= groups of 16 trials) per CTA
 constexpr int kGridPartialDoubles = 4;                  // sum, kept, accepted, error (as doubles: one 32-byte store)
 
-// exchange buffer of one rank (device memory, IPC-shared with the peers)
+// Exchange buffer of one rank (device memory, IPC-shared with the peers).  Everything travels as 16-byte "lines" in the
+// style of NCCL's LL protocol: two 32-bit payload words, each followed by a 32-bit flag (the low half of the batch sequence
+// number), written with ONE vector store.  8-byte halves arrive atomically, so a reader that sees both flags equal to the
+// sequence number it waits for has the payload: no fence, no separate flag, one NVLink traversal per message.  Lines are
+// double buffered by batch parity (a peer can be at most one batch ahead).
+struct CmcLine { unsigned int d0, f0, d1, f1; };
 struct CmcExchange {
-  unsigned long long flags[kGridMaxWorld][kGridMaxCtas];                          // flags[r][c]: last sequence number CTA c of rank r finished writing
-  unsigned int masks[2][kGridMaxCtas][kGridMaxWarps][2];                         // [parity][cta][warp]{kept, accept}
-  double partials[2][kGridMaxWorld][kGridMaxCtas][kGridPartialDoubles];          // [parity][rank][cta]
+  CmcLine masks[2][kGridMaxCtas][kGridMaxWarps];                       // [parity][cta][warp] {kept mask, accept mask}
+  CmcLine partials[2][kGridMaxWorld][kGridMaxCtas][2];                 // [parity][rank][cta] {sum lo, sum hi}, {kept, accepted | err << 31}
 };
+
+__device__ __forceinline__ void line_store(CmcLine *dst, unsigned d0, unsigned d1, unsigned flag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(d0), "r"(flag), "r"(d1), "r"(flag) : "memory");
+}
+// optimistic read at L2 (where local and peer writes land); not ordered against other loads, so many can be in flight.
+// A line whose flags do not match yet is re-read by line_wait.
+__device__ __forceinline__ uint4 line_load(const CmcLine *src) {      // {d0, f0, d1, f1}
+  return __ldcg(reinterpret_cast<const uint4 *>(src));
+}
+// spin until both flags of the line equal `flag`; false on timeout / abort
+__device__ __forceinline__ bool line_wait(const CmcLine *src, unsigned flag, unsigned &d0, unsigned &d1, int *abort_flag, long long spin_limit) {
+  const long long t0 = clock64();
+  for (;;) {
+    unsigned a, fa, b, fb;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(src) : "memory");
+    if (fa == flag && fb == flag) { d0 = a; d1 = b; return true; }
+    if (*reinterpret_cast<volatile int *>(abort_flag)) return false;
+    if (clock64() - t0 > spin_limit) { *reinterpret_cast<volatile int *>(abort_flag) = 1; return false; }
+  }
+}
+
+// batch energy totals are accumulated in 2^-44 eV fixed point: integer adds commute, so the total does not depend on the
+// order in which thread blocks (or GPUs) contribute -- every rank gets the bit-identical energy (resolution 5.7e-14 eV)
+constexpr double kEnergyFixedScale = 17592186044416.0;   // 2^44
 
 struct CmcGridParams {
   int world, rank;
@@ -38,6 +66,7 @@ struct CmcGridParams {
   unsigned long long *barrier_counter;    // local: monotonically increasing arrival counter (zeroed before the launch)
   int *abort_flag;                        // local: set when a spin loop times out (a peer died): every CTA leaves
   unsigned long long *sequence;           // local: exchange sequence number, never reset (flags compare against it)
+  unsigned long long *accum;              // local: [2][4] batch totals by parity {sum dE (fixed point), kept, accepted, errors}
   long long spin_limit;                   // clock64 ticks a spin loop may wait
 };
 
@@ -86,14 +115,15 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
                 uint64_t seed, unsigned long long target_steps, CmcGridParams gp, int stage_b_table) {
   const int n_cta = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   __shared__ int32_t s_delta[2 * 43];
-  __shared__ double s_warp_sum[kGridMaxWarps];
+  __shared__ long long s_warp_fixed[kGridMaxWarps];
   __shared__ unsigned int s_warp_cnt[kGridMaxWarps], s_warp_acc[kGridMaxWarps], s_warp_live[kGridMaxWarps];
   __shared__ double s_energy, s_temperature;
   __shared__ unsigned long long s_steps, s_accepted, s_proposals, s_epoch, s_sequence;
   __shared__ SaSchedule s_sa;
   __shared__ int32_t s_live_a[kCmcMaxThreads], s_live_b[kCmcMaxThreads];
   __shared__ int s_flag_ok;
-  __shared__ unsigned int s_kept_mask[kGridMaxWarps], s_acc_mask[kGridMaxWarps];
+  __shared__ long long s_part_e[kGridMaxWorld];
+  __shared__ unsigned int s_part_k[kGridMaxWorld], s_part_a[kGridMaxWorld];
   extern __shared__ double s_dyn[];                // [C: m] [A: m*42*m] [B: m*204*m*m, optional] [mask: 42] [base] [codes]
 
   const int tid = threadIdx.x, B = blockDim.x;
@@ -131,8 +161,8 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   int err = 0;
   bool healthy = true;
 #ifdef LMC_CMC_PROFILE
-  __shared__ long long s_gprof[8], s_eprof;
-  if (tid == 0) { for (int q = 0; q < 8; ++q) s_gprof[q] = 0; s_eprof = 0; }
+  __shared__ long long s_gprof[8], s_eprof, s_rprof[3];
+  if (tid == 0) { for (int q = 0; q < 8; ++q) s_gprof[q] = 0; s_eprof = 0; s_rprof[0] = s_rprof[1] = s_rprof[2] = 0; }
   long long tg_prev = clock64();
   unsigned long long n_batches = 0;
 #define LMC_GTICK(k) do { if (tid == 0) { const long long t_now = clock64(); s_gprof[k] += t_now - tg_prev; tg_prev = t_now; } } while (0)
@@ -144,6 +174,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     const unsigned long long steps0 = s_steps, epoch = s_epoch + 1, prop0 = s_proposals, seq = s_sequence + 1;
     const double t_batch = s_temperature, energy0 = s_energy;
     const int parity = static_cast<int>(seq & 1ULL);
+    const unsigned flag = static_cast<unsigned>(seq);            // never 0: the buffers start zeroed, seq starts at 1
     if (steps0 >= target_steps) break;
     __syncthreads();
     if ((epoch & 0xFFULL) == 0) {                   // 8-bit epoch wrapped: forget all marks (keep the species bytes)
@@ -241,11 +272,14 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
       if ((tid & 31) == 0) {
-        s_warp_sum[warp] = sum;
+        s_warp_fixed[warp] = __double2ll_rn(sum * kEnergyFixedScale);   // rounded per warp group = per unit of ownership:
+                                                                        // the integer total is the same for every world size
         s_warp_cnt[warp] = __popc(kept_mask & 0x55555555u);      // one lane per pair
         s_warp_acc[warp] = __popc(acc_mask & 0x55555555u);
       }
-      if ((tid & 31) == 0) { s_kept_mask[warp] = kept_mask; s_acc_mask[warp] = acc_mask; }
+      // the owner warp publishes its group's masks in every peer's buffer right away (lane d -> rank d)
+      if (world > 1 && owner && (tid & 31) < world && (tid & 31) != rank)
+        line_store(&gp.xchg[tid & 31]->masks[parity][cta][warp], kept_mask, acc_mask, flag);
     }
 #ifdef LMC_CMC_PROFILE
     const long long te2 = clock64();
@@ -254,44 +288,55 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     const int block_err = __syncthreads_or(err != 0);
     LMC_GTICK(3);
     if (tid < world) {
-      // thread d ships this CTA's results to rank d: partial sums (own warps only; fixed order), the masks of the warp
-      // groups this rank evaluated, then -- after a system-scope fence -- the CTA's flag.  CTA c of rank d only waits for
-      // the CTAs c of the other ranks (it applies its own trials), so no grid barrier is needed for the exchange.
-      double e = 0.0;
+      // this CTA's partial sums (own warps only; fixed order).  Thread d ships them to rank d as two lines.
+      long long e = 0;
       unsigned int n_kept = 0, n_acc = 0;
-      for (int q = 0; q < n_warps; ++q) { e += s_warp_sum[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
-      CmcExchange *dst = gp.xchg[tid];
-      volatile double *vd = dst->partials[parity][rank][cta];
-      vd[0] = e; vd[1] = static_cast<double>(n_kept); vd[2] = static_cast<double>(n_acc); vd[3] = static_cast<double>(block_err);
-      if (world > 1 && tid != rank) {
-        for (int q = rank; q < n_warps; q += world) {
-          volatile unsigned int *mk = dst->masks[parity][cta][q];
-          mk[0] = s_kept_mask[q];
-          mk[1] = s_acc_mask[q];
-        }
-        __threadfence_system();
-        *reinterpret_cast<volatile unsigned long long *>(&dst->flags[rank][cta]) = seq;
+      for (int q = 0; q < n_warps; ++q) { e += s_warp_fixed[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
+      if (tid == rank) { s_part_e[rank] = e; s_part_k[rank] = n_kept; s_part_a[rank] = n_acc | (block_err ? 0x80000000u : 0u); }
+      else {
+        CmcLine *dst = gp.xchg[tid]->partials[parity][rank][cta];
+        const unsigned long long bits = static_cast<unsigned long long>(e);
+        line_store(dst, static_cast<unsigned>(bits), static_cast<unsigned>(bits >> 32), flag);
+        line_store(dst + 1, n_kept, n_acc | (block_err ? 0x80000000u : 0u), flag);
       }
     }
-    if (world > 1) {
-      if (tid == 0) s_flag_ok = 1;
-      __syncthreads();
-      if (tid < world && tid != rank) {
-        const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned long long *>(&mine->flags[tid][cta]) < seq) {
-          if (*reinterpret_cast<volatile int *>(gp.abort_flag) || clock64() - t0 > gp.spin_limit) {
-            *reinterpret_cast<volatile int *>(gp.abort_flag) = 1;
-            s_flag_ok = 0;
-            break;
-          }
+    {
+      // a warp whose group was evaluated elsewhere waits for that rank's masks; threads d != rank of warp 0 wait for the
+      // partial sums of CTA c of rank d (CTA c only ever needs the CTAs c of its peers: no grid barrier in the exchange)
+      bool ok = true;
+      if (world > 1) {
+        if (!owner) {
+          unsigned k = 0, a2 = 0;
+          if ((tid & 31) == 0) ok = line_wait(&mine->masks[parity][cta][warp], flag, k, a2, gp.abort_flag, gp.spin_limit);
+          kept_mask = __shfl_sync(0xffffffffu, k, 0);
+          acc_mask = __shfl_sync(0xffffffffu, a2, 0);
         }
-        __threadfence_system();
+        if (tid < world && tid != rank) {
+          const CmcLine *src = mine->partials[parity][tid][cta];
+          unsigned lo = 0, hi = 0, nk = 0, na = 0;
+          ok = line_wait(src, flag, lo, hi, gp.abort_flag, gp.spin_limit) && ok;
+          ok = line_wait(src + 1, flag, nk, na, gp.abort_flag, gp.spin_limit) && ok;
+          s_part_e[tid] = static_cast<long long>((static_cast<unsigned long long>(hi) << 32) | lo);
+          s_part_k[tid] = nk;
+          s_part_a[tid] = na;
+        }
       }
-      __syncthreads();
-      if (!s_flag_ok) { healthy = false; break; }
-      if (!owner) {
-        const volatile unsigned int *mk = mine->masks[parity][cta][warp];
-        kept_mask = mk[0]; acc_mask = mk[1];
+      if (__syncthreads_or(!ok)) { healthy = false; break; }
+      if (tid == 0) {
+        // contributions of CTA c of every rank go into this rank's batch accumulators (before the closing grid barrier)
+        long long fixed = 0;
+        unsigned long long n_kept = 0, n_acc = 0, n_err = 0;
+        for (int r = 0; r < world; ++r) {
+          fixed += s_part_e[r];
+          n_kept += s_part_k[r];
+          n_acc += s_part_a[r] & 0x7FFFFFFFu;
+          n_err += s_part_a[r] >> 31;
+        }
+        unsigned long long *acc = gp.accum + 4 * parity;
+        if (fixed) atomicAdd(acc, static_cast<unsigned long long>(fixed));
+        if (n_kept) atomicAdd(acc + 1, n_kept);
+        if (n_acc) atomicAdd(acc + 2, n_acc);
+        if (n_err) atomicAdd(acc + 3, n_err);
       }
     }
     LMC_GTICK(4);
@@ -305,49 +350,30 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     }
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     LMC_GTICK(5);
-    // ---------------- totals: partials of all ranks and CTAs in one fixed order (identical in every CTA of every rank)
+    // ---------------- totals: one 32-byte read per CTA (the accumulators are complete after the grid barrier)
     int any_err = 0;
-    if (warp == 0) {
-      double e = 0.0, k = 0.0, ac = 0.0, er = 0.0;
-      const int n_part = world * n_cta;
-      // L2 loads (the entries were written by other SMs / other GPUs before the barrier), eight entries in flight per lane
-      for (int q0 = tid; q0 < n_part; q0 += 32 * 8) {
-        double2 lo[8], hi[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int q = q0 + 32 * j;
-          if (q < n_part) {
-            const double2 *src = reinterpret_cast<const double2 *>(mine->partials[parity][q / n_cta][q % n_cta]);
-            lo[j] = __ldcg(src);
-            hi[j] = __ldcg(src + 1);
-          } else {
-            lo[j] = make_double2(0.0, 0.0);
-            hi[j] = make_double2(0.0, 0.0);
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { e += lo[j].x; k += lo[j].y; ac += hi[j].x; er += hi[j].y; }
+    if (tid == 0) {
+      const ulonglong2 *acc = reinterpret_cast<const ulonglong2 *>(gp.accum + 4 * parity);
+      const ulonglong2 v0 = __ldcg(acc), v1 = __ldcg(acc + 1);
+      const double e = static_cast<double>(static_cast<long long>(v0.x)) / kEnergyFixedScale;
+      const unsigned int n_kept = static_cast<unsigned int>(v0.y), n_acc = static_cast<unsigned int>(v1.x);
+      s_energy = energy0 + e;
+      s_steps = steps0 + n_kept;
+      s_accepted += n_acc;
+      s_proposals = prop0 + window;
+      if (s_sa.enabled && n_kept > 0) {
+        SaSchedule sa = s_sa;
+        sa_update_batch(sa, n_kept, n_acc, s_energy, s_steps, cool);
+        s_sa = sa;
+        s_temperature = sa.temperature;
       }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        e += __shfl_xor_sync(0xffffffffu, e, off); k += __shfl_xor_sync(0xffffffffu, k, off);
-        ac += __shfl_xor_sync(0xffffffffu, ac, off); er += __shfl_xor_sync(0xffffffffu, er, off);
-      }
-      if (tid == 0) {
-        const unsigned int n_kept = static_cast<unsigned int>(k), n_acc = static_cast<unsigned int>(ac);
-        s_energy = energy0 + e;
-        s_steps = steps0 + n_kept;
-        s_accepted += n_acc;
-        s_proposals = prop0 + window;
-        if (s_sa.enabled && n_kept > 0) {
-          SaSchedule sa = s_sa;
-          sa_update_batch(sa, n_kept, n_acc, s_energy, s_steps, cool);
-          s_sa = sa;
-          s_temperature = sa.temperature;
-        }
-        s_epoch = epoch;
-        s_sequence = seq;
-        s_flag_ok = er != 0.0 ? 0 : 1;
+      s_epoch = epoch;
+      s_sequence = seq;
+      s_flag_ok = v1.y != 0ULL ? 0 : 1;
+      // the other parity's accumulators were last read one batch ago by CTAs that have all passed two barriers since
+      if (cta == 0) {
+        unsigned long long *next = gp.accum + 4 * (parity ^ 1);
+        next[0] = 0ULL; next[1] = 0ULL; next[2] = 0ULL; next[3] = 0ULL;
       }
     }
     __syncthreads();
@@ -361,10 +387,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
 #ifdef LMC_CMC_PROFILE
   if (tid == 0 && cta == 0)
     printf("grid cmc profile rank %d (cycles/batch): propose %lld compact %lld mark+barrier %lld evaluate %lld exchange %lld apply+barrier %lld reduce %lld | "
-           "thread0: dE call %lld accept+reduce %lld | batches %llu ctas %d threads %d\n", rank, s_gprof[0] / (long long)max(1ULL, n_batches), s_gprof[1] / (long long)max(1ULL, n_batches),
+           "thread0: dE call %lld accept+reduce %lld | reduce parts: loads %lld shuffles %lld update %lld | batches %llu ctas %d threads %d\n", rank, s_gprof[0] / (long long)max(1ULL, n_batches), s_gprof[1] / (long long)max(1ULL, n_batches),
            s_gprof[2] / (long long)max(1ULL, n_batches), s_gprof[3] / (long long)max(1ULL, n_batches), s_gprof[4] / (long long)max(1ULL, n_batches),
            s_gprof[5] / (long long)max(1ULL, n_batches), s_gprof[6] / (long long)max(1ULL, n_batches), s_gprof[7] / (long long)max(1ULL, n_batches),
-           s_eprof / (long long)max(1ULL, n_batches), n_batches, n_cta, B);
+           s_eprof / (long long)max(1ULL, n_batches), s_rprof[0] / (long long)max(1ULL, n_batches), s_rprof[1] / (long long)max(1ULL, n_batches),
+           s_rprof[2] / (long long)max(1ULL, n_batches), n_batches, n_cta, B);
 #endif
   __syncthreads();
   if (cta == 0 && tid == 0) {

@@ -681,7 +681,9 @@ void Engine::cmc_grid_prepare() {
   d_cmc_grid_counter = dev_alloc<unsigned long long>(1);
   d_cmc_sequence = dev_alloc<unsigned long long>(1);
   d_cmc_abort = dev_alloc<int>(1);
-  for (void *p : {d_cmc_xchg, static_cast<void *>(d_cmc_grid_counter), static_cast<void *>(d_cmc_sequence), static_cast<void *>(d_cmc_abort)})
+  d_cmc_accum = dev_alloc<unsigned long long>(8);
+  for (void *p : {d_cmc_xchg, static_cast<void *>(d_cmc_grid_counter), static_cast<void *>(d_cmc_sequence), static_cast<void *>(d_cmc_abort),
+                  static_cast<void *>(d_cmc_accum)})
     device_allocs.push_back(p);
   LMC_CUDA(cudaMemsetAsync(d_cmc_xchg, 0, sizeof(CmcExchange), stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_sequence, 0, 8, stream));
@@ -769,11 +771,13 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   gp.barrier_counter = d_cmc_grid_counter;
   gp.abort_flag = d_cmc_abort;
   gp.sequence = d_cmc_sequence;
+  gp.accum = d_cmc_accum;
   int clock_khz = 0;
   LMC_CUDA(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device));
   gp.spin_limit = static_cast<long long>(clock_khz) * 1000LL * 5LL;        // ~5 s: a lost peer ends the launch instead of hanging it
   LMC_CUDA(cudaMemsetAsync(d_cmc_grid_counter, 0, 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_abort, 0, 4, stream));
+  LMC_CUDA(cudaMemsetAsync(d_cmc_accum, 0, 64, stream));
   CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));

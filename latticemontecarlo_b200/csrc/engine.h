@@ -116,7 +116,7 @@ class Engine {
   bool cmc_ready{false};
   void *d_cmc_xchg{nullptr};                       // CmcExchange (IPC-shareable)
   void *cmc_peer_xchg[8]{};                        // peer mappings (cudaIpcOpenMemHandle), [rank] = own buffer
-  unsigned long long *d_cmc_grid_counter{nullptr}, *d_cmc_sequence{nullptr};
+  unsigned long long *d_cmc_grid_counter{nullptr}, *d_cmc_sequence{nullptr}, *d_cmc_accum{nullptr};
   int *d_cmc_abort{nullptr};
   int cmc_world{1}, cmc_rank{0}, cmc_grid_ctas{0};
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
