@@ -290,6 +290,9 @@ def run_ours(args):
                              "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"},
         "wall_s_timed_region": wall,
     }
+    cmc_multi = None
+    if world > 1 and not args.no_cmc:
+        cmc_multi = bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, js)      # collective: every rank takes part
     if rank == 0:
         line["clocks"] = clocks.summary()
         line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)
@@ -299,6 +302,8 @@ def run_ours(args):
             line["chain"] = bench_chain(engine, W, temps, occ_pinned, peak, js, n_gpus == 1 and not args.no_cpu_baseline)
         if not args.no_cmc:
             line["cmc"] = bench_cmc(torch, local_rank, js, peak, n_gpus == 1 and not args.no_cpu_baseline)
+            if cmc_multi is not None:
+                line["cmc"]["multi_gpu_single_lattice_100x100x100_sa"] = cmc_multi
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -382,7 +387,10 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
     148 independent replicas (one thread block each) -- temperatures shard with no communication."""
     from latticemontecarlo_b200 import capi, synth
     out = {"metric": "cmc_swap_trials_per_s", "unit": "trials/s", "bytes_per_trial": BYTES_PER_TRIAL}
-    for name, f, replicas, trials in (("single_lattice_40x40x40", 40, 1, 200000), ("replicas_148x_20x20x20", 20, 148, 20000)):
+    cases = (("single_lattice_40x40x40", 40, 1, 200000, None),                        # BASELINE configs[1]
+             ("single_lattice_100x100x100_sa", 100, 1, 2000000, (900.0, 40000000)),    # configs[3]: SimulatedAnnealing, 4M sites
+             ("replicas_148x_20x20x20", 20, 148, 20000, None))
+    for name, f, replicas, trials, sa in cases:
         eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=replicas, device=device)
         eng.load_coefficients(json_path)
         occ = np.stack([synth.random_alloy(f, P_MG, P_ZN, seed=1000 + r, vacancy_site=None) for r in range(replicas)])
@@ -390,7 +398,7 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
         pinned.numpy()[:] = occ
         temps = np.linspace(600.0, 1000.0, replicas) if replicas > 1 else np.array([800.0])
         eng.set_occupancy_all(pinned.numpy())
-        eng.cmc_reset()
+        eng.cmc_reset(*(sa or ()))
         eng.cmc_run(trials // 4, temperatures=temps, seed=5)          # warm-up
         kernel_ms, done = [], []
         for _ in range(5):
@@ -403,23 +411,58 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
         n_e2e = 0
         for _ in range(3):
             eng.set_occupancy_all(pinned.numpy())
-            eng.cmc_reset()
+            eng.cmc_reset(*(sa or ()))
             eng.cmc_run(trials, temperatures=temps, seed=5)
             st = eng.cmc_state()
             eng.get_occupancy_all()
             n_e2e += int(st["steps"].sum())
         e2e = n_e2e / (time.perf_counter() - t0)
         achieved = rate * BYTES_PER_TRIAL / 1e9
+        kernel = "cmc_grid_kernel" if replicas == 1 else "cmc_run_kernel"     # one lattice: whole-GPU cooperative kernel
         out[name] = {"value": rate, "e2e": e2e, "replicas": replicas, "sites": 4 * f ** 3, "trials_per_launch": int(np.mean(done)),
                      "kernel_ms": float(np.mean(kernel_ms)), "accept_ratio": float(st["accepted"].sum() / max(1, st["steps"].sum())),
-                     "roofline": {"kernel": "cmc_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "driver": "SimulatedAnnealing schedule" if sa else "CanonicalMc at fixed temperature",
+                     "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                   "frac": achieved / peak,
-                                  "traffic": recorded_traffic("cmc_run_kernel", replicas=replicas, factor=f, trials=trials)}}
+                                  "traffic": recorded_traffic(kernel, replicas=replicas, factor=f, trials=trials)}}
         eng.close()
     out["value"] = out["single_lattice_40x40x40"]["value"]
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline_cmc(json_path)
     return out
+
+
+def bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, json_path):
+    """BASELINE configs[3] over all GPUs of the job: ONE 4M-site lattice annealed by `world` ranks (replicated occupancy,
+    sharded dE evaluation, in-kernel peer-memory exchange: include/lmc_b200.h, lmc_cmc_attach_peers).  Every rank takes
+    part; the rate uses the slowest rank's kernel time; the ranks' final states must be identical."""
+    import hashlib
+    from latticemontecarlo_b200 import capi, sharding, synth
+    f, trials = 100, 2000000
+    eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=local_rank)
+    eng.load_coefficients(json_path)
+    occ = synth.random_alloy(f, P_MG, P_ZN, seed=1000, vacancy_site=None)
+    eng.set_occupancy(occ)
+    sharding.attach_cmc_peers(eng, rank, world)
+    eng.cmc_reset(900.0, 40000000)
+    dist.barrier(); torch.cuda.synchronize()
+    eng.cmc_grid_run(trials // 4, seed=5)
+    ms, done = [], []
+    for _ in range(5):
+        dist.barrier(); torch.cuda.synchronize()
+        s0 = int(eng.cmc_state()["steps"][0])
+        eng.cmc_grid_run(trials, seed=5)
+        ms.append(sharding.max_over_ranks([eng.last_kernel_ms()], device="cuda")[0])
+        done.append(int(eng.cmc_state()["steps"][0]) - s0)
+    st = eng.cmc_state()
+    digest = hashlib.sha256(eng.get_occupancy(0).tobytes()).hexdigest() + "%.17g" % st["energy"][0]
+    digests = [None] * world
+    dist.all_gather_object(digests, digest)
+    eng.close()
+    return {"value": sum(done) / (sum(ms) * 1e-3), "unit": "trials/s", "n_gpus": world, "sites": 4 * f ** 3, "scaling": "strong",
+            "driver": "SimulatedAnnealing schedule", "trials_per_launch": int(np.mean(done)), "kernel_ms": float(np.mean(ms)),
+            "ranks_identical": len(set(digests)) == 1,
+            "exchange": "kept/accept masks + partial sums as 16-byte flag-in-data lines written into peer memory inside cmc_grid_kernel"}
 
 
 def cpu_baseline_cmc(json_path):

@@ -9,6 +9,9 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include "../../include/lmc_b200.h"
 #include "engine.h"
 #include "kernels.cuh"
@@ -94,6 +97,16 @@ Engine::~Engine() {
     if (ev_end) cudaEventDestroy(ev_end);
     if (stream) cudaStreamDestroy(stream);
   }
+}
+
+// device attributes are queried once (cudaDevAttrClockRate alone costs about a millisecond per call)
+int Engine::device_attr(int attr) {
+  auto it = attr_cache.find(attr);
+  if (it != attr_cache.end()) return it->second;
+  int v = 0;
+  LMC_CUDA(cudaDeviceGetAttribute(&v, static_cast<cudaDeviceAttr>(attr), device));
+  attr_cache[attr] = v;
+  return v;
 }
 
 void Engine::time_begin() { cudaEventRecord(ev_begin, stream); }
@@ -727,6 +740,14 @@ void Engine::cmc_attach_peers(int32_t rank, int32_t world, const void *handles, 
 }
 
 void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
+  const bool dbg = std::getenv("LMC_DEBUG_TIMING") != nullptr;
+  auto t_dbg = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (!dbg) return;
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[cmc_grid_run] %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t_dbg).count());
+    t_dbg = now;
+  };
   require_device();
   require_coefficients();
   if (n_walkers != 1) throw std::invalid_argument("lmc_cmc_grid_run drives ONE lattice with the whole GPU (n_walkers == 1)");
@@ -739,8 +760,9 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   LMC_CUDA(cudaMemcpyAsync(&steps0, d_cmc_steps, 8, cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
   const unsigned long long target = steps0 + static_cast<unsigned long long>(n_trials);
+  tick("steps readback");
   int sms = 0;
-  LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  sms = device_attr(cudaDevAttrMultiProcessorCount);
   int ctas = std::min(sms, kGridMaxCtas);
   if (cmc_grid_ctas > 0) ctas = std::min(ctas, cmc_grid_ctas);
   // threads per CTA: a trial is one lane pair; about N / 172 trials of a batch can be mutually non-interfering
@@ -756,13 +778,17 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
   const size_t fixed = (m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
   int max_optin = 0;
-  LMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  max_optin = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin);
   const int stage_b = (fixed + b_len * 8 + 24 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
   const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
   LMC_CUDA(cudaFuncSetAttribute(cmc_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int per_sm = 0;
-  LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmc_grid_kernel, threads, smem));
-  if (per_sm < 1) throw std::runtime_error("cmc_grid_kernel does not fit on an SM");
+  if (cmc_grid_checked_threads != threads || cmc_grid_checked_smem != smem) {     // once per launch shape
+    int per_sm = 0;
+    LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmc_grid_kernel, threads, smem));
+    if (per_sm < 1) throw std::runtime_error("cmc_grid_kernel does not fit on an SM");
+    cmc_grid_checked_threads = threads;
+    cmc_grid_checked_smem = smem;
+  }
   CmcGridParams gp{};
   gp.world = cmc_world;
   gp.rank = cmc_rank;
@@ -773,7 +799,7 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   gp.sequence = d_cmc_sequence;
   gp.accum = d_cmc_accum;
   int clock_khz = 0;
-  LMC_CUDA(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, device));
+  clock_khz = device_attr(cudaDevAttrClockRate);
   gp.spin_limit = static_cast<long long>(clock_khz) * 1000LL * 5LL;        // ~5 s: a lost peer ends the launch instead of hanging it
   LMC_CUDA(cudaMemsetAsync(d_cmc_grid_counter, 0, 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_abort, 0, 4, stream));
@@ -789,16 +815,19 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  tick("setup");
   time_begin();
   LMC_CUDA(cudaLaunchKernelEx(&cfg, cmc_grid_kernel, lat, tab, d_occ, d_cmc_mirror, d_cmc_marks, st, static_cast<const double *>(d_cmc_temperature),
                               static_cast<uint64_t>(params.seed), target, gp, stage_b));
   time_end();
+  tick("launch");
   LMC_CUDA(cudaGetLastError());
   int32_t err = 0;
   int aborted = 0;
   LMC_CUDA(cudaMemcpyAsync(&err, d_cmc_error, 4, cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaMemcpyAsync(&aborted, d_cmc_abort, 4, cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
+  tick("kernel + sync");
   if (aborted) {
     cmc_ready = false;
     throw std::runtime_error("CMC grid run: barrier / peer exchange timed out (a peer rank is missing or out of step)");
@@ -915,7 +944,7 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
   // trial occupies one lane pair, and the scattered gathers are L1-wavefront bound per SM, so a replica is spread over as
   // many CTAs as the device allows (cluster of up to 16 on B200) with correspondingly small CTAs.
   int sms = 0;
-  LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  sms = device_attr(cudaDevAttrMultiProcessorCount);
   int cluster = 1;
   while (cluster < 16 && static_cast<int64_t>(n_run) * cluster * 2 <= sms) cluster *= 2;
   if (threads <= 0) {
@@ -930,7 +959,7 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
   const int m = species.n + 1;
   const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
   int max_optin = 0;
-  LMC_CUDA(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  max_optin = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin);
   LMC_CUDA(cudaFuncSetAttribute(cmc_run_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cudaLaunchAttribute attr[1];

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <functional>
 #include <string>
+#include <map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -119,6 +120,10 @@ class Engine {
   unsigned long long *d_cmc_grid_counter{nullptr}, *d_cmc_sequence{nullptr}, *d_cmc_accum{nullptr};
   int *d_cmc_abort{nullptr};
   int cmc_world{1}, cmc_rank{0}, cmc_grid_ctas{0};
+  int cmc_grid_checked_threads{0};
+  size_t cmc_grid_checked_smem{0};
+  std::map<int, int> attr_cache;
+  int device_attr(int attr);
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
   cudaEvent_t ev_begin{nullptr}, ev_end{nullptr};
   bool timing_pending{false};
