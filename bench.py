@@ -360,7 +360,7 @@ def bench_chain(engine, W, temps, occ_pinned, peak, json_path, with_cpu):
     out = {"metric": "kmc_chain_hops_per_s", "unit": "hops/s", "value": rate, "walkers": W, "hops_per_walker": hops,
            "kernel_ms": sum(ms) / len(ms), "barrier_evaluations_per_hop": 144, "all_walkers_advanced": bool((st["steps"] == hops).all()),
            "roofline": {"kernel": "kmc_chain_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": recorded_traffic("kmc_chain_run_kernel", walkers=W, hops=hops),
                         "note": "12 x the first-order algorithmic bytes per hop (144 events)"}}
     if with_cpu:
         try:
