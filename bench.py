@@ -337,8 +337,32 @@ def bench_barrier_eval(engine, torch, W, peak):
             times.append(ms)
     ms = sum(times) / len(times)
     achieved = n * BYTES_PER_EVENT / (ms * 1e-3) / 1e9
-    return {"kernel": "barrier_kernel", "events": n, "ms": ms, "events_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
-            "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item())}
+    out = {"kernel": "barrier_kernel", "events": n, "ms": ms, "events_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
+           "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item()),
+           "note": "arbitrary (vacancy, neighbour) events, one thread per event"}
+    # the event-list form (KineticMcFirstOmp::BuildEventList for a batch of vacancies): one box scan per vacancy.  Every
+    # walker holds one vacancy, so a large batch is built by listing each (walker, vacancy) item `reps` times.
+    reps = 16
+    d_v = torch.from_numpy(np.tile(vac, reps)).to(dev)
+    d_wv = torch.from_numpy(np.tile(np.arange(W, dtype=np.int32), reps)).to(dev)
+    d_nb = torch.empty(W * reps * 12, dtype=torch.int64, device=dev)
+    d_ea2 = torch.empty(W * reps * 12, dtype=torch.float64, device=dev)
+    d_de2 = torch.empty(W * reps * 12, dtype=torch.float64, device=dev)
+    times = []
+    for k in range(8):
+        engine.eval_vacancy_events_dev(W * reps, d_wv.data_ptr(), d_v.data_ptr(), d_nb.data_ptr(), d_ea2.data_ptr(), d_de2.data_ptr())
+        if k >= 3:
+            times.append(engine.last_kernel_ms())
+    ms2 = sum(times) / len(times)
+    n2 = W * reps * 12
+    # same events, same numbers (the list form is ordered by neighbour id: compare as sorted sets per vacancy)
+    same = bool(torch.allclose(torch.sort(d_ea2[:n].view(W, 12), dim=1).values, torch.sort(d_ea.view(W, 12), dim=1).values, rtol=0, atol=1e-12))
+    achieved2 = n2 * BYTES_PER_EVENT / (ms2 * 1e-3) / 1e9
+    out["event_lists"] = {"kernel": "vacancy_events_kernel", "events": n2, "ms": ms2, "events_per_s": n2 / (ms2 * 1e-3),
+                          "achieved_gbs": achieved2, "frac_of_hbm_peak": achieved2 / peak, "bytes_per_event": BYTES_PER_EVENT,
+                          "matches_barrier_kernel": same,
+                          "note": "12 events of each of %d (walker, vacancy) items per launch, half-warp per item, one box scan" % (W * reps)}
+    return out
 
 
 def bench_chain(engine, W, temps, occ_pinned, peak, json_path, with_cpu):

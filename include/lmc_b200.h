@@ -93,6 +93,18 @@ int lmc_eval_barriers(lmc_engine *engine, int64_t n, const int32_t *walker, cons
 int lmc_eval_barriers_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_i,
                           const int64_t *site_j, double *Ea, double *dE, double *D, double *Ks);
 
+/* The event list of a vacancy in one call: KineticMcFirstOmp::BuildEventList (mc/src/KineticMcFirstOmp.cpp:52-68) evaluates
+ * the 12 jumps (vacancy, first neighbour) of the current vacancy site; here for a batch of n vacancies (vacancy_site[q] on
+ * replica walker[q]; walker == NULL: replica 0).  Outputs are [n][12] in the reference's event order (ascending neighbour
+ * lattice id = Config::GetFirstNeighborsAdjacencyList order): the neighbour ids, Ea and dE.  The 12 jumps share one scan of
+ * the 7x7x7 half-unit box around the vacancy instead of 12 separate 60-site gathers (the fast path of the KMC drivers).
+ * Errors as lmc_eval_barriers (offending items are NaN). */
+int lmc_eval_vacancy_events(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site, int64_t *neighbour_site,
+                            double *Ea, double *dE);
+/* same with every pointer in device memory (asynchronous on the engine stream) */
+int lmc_eval_vacancy_events_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site,
+                                int64_t *neighbour_site, double *Ea, double *dE);
+
 /* EnergyChangePredictorPairSite::GetDeFromLatticeIdPair (pred/include/EnergyChangePredictorPairSite.h:20-23,
  * src :70-146): energy change of exchanging the species at site_a[e] and site_b[e]; 0 for equal species; coupled
  * pairs (b within the third shell of a) are evaluated exactly. */

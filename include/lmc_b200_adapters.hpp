@@ -110,6 +110,20 @@ class VacancyMigrationPredictorQuartic {
     check(lmc_eval_barriers(config.engine(), static_cast<int64_t>(first.size()), walker.empty() ? nullptr : walker.data(), first.data(),
                             second.data(), Ea.data(), dE.data(), nullptr, nullptr));
   }
+  // the whole event list of a vacancy (KineticMcFirstOmp::BuildEventList, mc/src/KineticMcFirstOmp.cpp:52-68): neighbour ids
+  // in adjacency order with their {Ea, dE}
+  void GetEventListOfVacancy(const cfg::Config &config, size_t vacancy_lattice_id, std::array<size_t, 12> &neighbour_lattice_ids,
+                             std::array<std::pair<double, double>, 12> &barrier_and_diff, int walker = 0) const {
+    const int64_t v = static_cast<int64_t>(vacancy_lattice_id);
+    const int32_t w = walker;
+    int64_t nb[12];
+    double ea[12], de[12];
+    check(lmc_eval_vacancy_events(config.engine(), 1, &w, &v, nb, ea, de));
+    for (int q = 0; q < 12; ++q) {
+      neighbour_lattice_ids[static_cast<size_t>(q)] = static_cast<size_t>(nb[q]);
+      barrier_and_diff[static_cast<size_t>(q)] = {ea[q], de[q]};
+    }
+  }
 };
 // The LRU cache (pred/src/VacancyMigrationPredictorQuarticLru.cpp) is replaced by batch recomputation; cache_size is accepted and ignored.
 class VacancyMigrationPredictorQuarticLru : public VacancyMigrationPredictorQuartic {

@@ -212,6 +212,19 @@ class Engine:
         _check(lib().lmc_eval_barriers(self.h, C.c_int64(n), _p(w), _p(i), _p(j), _p(ea), _p(de), _p(d), _p(ks)))
         return (ea, de, d, ks) if want_parts else (ea, de)
 
+    def eval_vacancy_events(self, vacancy_site, walker=None):
+        """All 12 jumps of each listed vacancy (KineticMcFirstOmp::BuildEventList order): (neighbour ids, Ea, dE), each [n, 12]."""
+        v = _i64(vacancy_site)
+        n = len(v)
+        w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)
+        nb = np.empty((n, 12), dtype=np.int64); ea = np.empty((n, 12)); de = np.empty((n, 12))
+        _check(lib().lmc_eval_vacancy_events(self.h, C.c_int64(n), _p(w), _p(v), _p(nb), _p(ea), _p(de)))
+        return nb, ea, de
+
+    def eval_vacancy_events_dev(self, n, walker_ptr, vacancy_ptr, neighbour_ptr, ea_ptr, de_ptr):
+        _check(lib().lmc_eval_vacancy_events_dev(self.h, C.c_int64(int(n)), C.c_void_p(walker_ptr or None), C.c_void_p(vacancy_ptr),
+                                                 C.c_void_p(neighbour_ptr), C.c_void_p(ea_ptr), C.c_void_p(de_ptr)))
+
     def eval_swap_de(self, site_a, site_b, walker=None):
         a, b = _i64(site_a), _i64(site_b)
         w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)

@@ -428,6 +428,41 @@ void Engine::eval_barriers(int64_t n, const int32_t *walker, const int64_t *site
   check_event_errors("lmc_eval_barriers");
 }
 
+void Engine::eval_vacancy_events_dev(int64_t n, const int32_t *walker, const int64_t *vacancy, int64_t *neighbour, double *Ea, double *dE) {
+  require_device();
+  require_coefficients();
+  if (!pair_tables.has_barrier) throw std::invalid_argument("the coefficient file has no per-element quartic blocks");
+  if (n <= 0) return;
+  if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("event lists are ordered by 32-bit lattice ids (num_sites < 2^31)");
+  const size_t smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
+  LMC_CUDA(cudaFuncSetAttribute(vacancy_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // enough blocks to fill the device, few enough that each stages the tables once for several items
+  const int64_t want = (n + kKmcWalkersPerBlock - 1) / kKmcWalkersPerBlock;
+  const unsigned blocks = static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(device_attr(cudaDevAttrMultiProcessorCount)) * 7)));
+  time_begin();
+  vacancy_events_kernel<<<blocks, kKmcThreads, smem, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, vacancy, neighbour, Ea, dE, d_error);
+  time_end();
+  LMC_CUDA(cudaGetLastError());
+}
+
+void Engine::eval_vacancy_events(int64_t n, const int32_t *walker, const int64_t *vacancy, int64_t *neighbour, double *Ea, double *dE) {
+  require_device();
+  if (n <= 0) return;
+  const size_t N = static_cast<size_t>(n);
+  char *d = static_cast<char *>(scratch(N * 8 + N * 12 * (8 + 8 + 8) + N * 4 + 64));
+  int64_t *d_v = reinterpret_cast<int64_t *>(d);
+  int64_t *d_nb = d_v + N;
+  double *d_ea = reinterpret_cast<double *>(d_nb + 12 * N), *d_de = d_ea + 12 * N;
+  int32_t *d_w = reinterpret_cast<int32_t *>(d_de + 12 * N);
+  LMC_CUDA(cudaMemcpyAsync(d_v, vacancy, N * 8, cudaMemcpyHostToDevice, stream));
+  if (walker) LMC_CUDA(cudaMemcpyAsync(d_w, walker, N * 4, cudaMemcpyHostToDevice, stream));
+  eval_vacancy_events_dev(n, walker ? d_w : nullptr, d_v, d_nb, d_ea, d_de);
+  if (neighbour) LMC_CUDA(cudaMemcpyAsync(neighbour, d_nb, N * 12 * 8, cudaMemcpyDeviceToHost, stream));
+  if (Ea) LMC_CUDA(cudaMemcpyAsync(Ea, d_ea, N * 12 * 8, cudaMemcpyDeviceToHost, stream));
+  if (dE) LMC_CUDA(cudaMemcpyAsync(dE, d_de, N * 12 * 8, cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_eval_vacancy_events");
+}
+
 void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE) {
   require_device();
   require_coefficients();
@@ -1198,6 +1233,17 @@ double lmc_engine_last_kernel_ms(lmc_engine *engine) {
   return ms;
 }
 int64_t lmc_engine_launch_count(const lmc_engine *engine) { return engine ? engine->impl->launch_count : 0; }
+int lmc_eval_vacancy_events(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site, int64_t *neighbour_site,
+                            double *Ea, double *dE) {
+  return guard([&] { engine->impl->eval_vacancy_events(n, walker, vacancy_site, neighbour_site, Ea, dE); });
+}
+int lmc_eval_vacancy_events_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site, int64_t *neighbour_site,
+                                double *Ea, double *dE) {
+  return guard([&] {
+    if (!vacancy_site || !neighbour_site || !Ea || !dE) throw std::invalid_argument("null device pointer");
+    engine->impl->eval_vacancy_events_dev(n, walker, vacancy_site, neighbour_site, Ea, dE);
+  });
+}
 int lmc_kmc_reset(lmc_engine *engine) {
   return guard([&] { engine->impl->kmc_reset(); });
 }

@@ -48,6 +48,8 @@ class Engine {
   void debug_site(int32_t walker, int64_t site, int32_t new_element, int64_t *state43, int32_t *sc, int32_t *ec);
 
   // drivers
+  void eval_vacancy_events(int64_t n, const int32_t *walker, const int64_t *vacancy, int64_t *neighbour, double *Ea, double *dE);
+  void eval_vacancy_events_dev(int64_t n, const int32_t *walker, const int64_t *vacancy, int64_t *neighbour, double *Ea, double *dE);
   void kmc_reset();
   void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace,
                bool second_order);

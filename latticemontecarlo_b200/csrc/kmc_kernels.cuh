@@ -413,6 +413,76 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   if (err && w_raw < n_walkers) atomicOr(&st.error[w], err);
 }
 
+// ------------------------------------------------------------------------------------------------ batched event lists
+// KineticMcFirstOmp::BuildEventList (mc/src/KineticMcFirstOmp.cpp:52-68) for many vacancies at once: item q is the vacancy
+// at lattice id vacancy[q] of replica walker[q]; a half-warp evaluates its 12 jumps with ONE scan of the surrounding box
+// (kmc_scan_and_evaluate) instead of 12 independent 60-site gathers.  Outputs per item, in the reference's event order
+// (ascending neighbour lattice id): neighbour id, Ea, dE.  Blocks loop over items so that the shared-memory tables are
+// staged once per block.
+__global__ void __launch_bounds__(kKmcThreads, 7)
+vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n_items,
+                      const int32_t *__restrict__ walker, const int64_t *__restrict__ vacancy, int64_t *__restrict__ neighbour,
+                      double *__restrict__ Ea, double *__restrict__ dE, int *error) {
+  __shared__ int32_t s_box[2 * kBoxCells];
+  __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
+  __shared__ uint8_t s_list_cell[kKmcWalkersPerBlock][kBoxCells], s_list_code[kKmcWalkersPerBlock][kBoxCells];
+  __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
+  extern __shared__ double s_A2[];
+  __shared__ uint64_t s_mask_hi[kEnvN];
+  __shared__ uint16_t s_pbase[kEnvN];
+  __shared__ uint32_t s_ids[kKmcWalkersPerBlock][12];
+  for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
+  for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
+  for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
+  for (int q = threadIdx.x; q < 2 * 12 * kBoxCells; q += blockDim.x) s_envpos[q] = tab.box_envpos[q];
+  __syncthreads();
+  const int lane = threadIdx.x & 15, wl = threadIdx.x >> 4;
+  constexpr unsigned hmask = 0xFFFFFFFFu;
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac_code = static_cast<unsigned>(tab.n_species);
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  const bool active = lane < 12;
+  const int k = active ? lane : 0;
+  const int dxk = tab.nn1[4 * k], dyk = tab.nn1[4 * k + 1], dzk = tab.nn1[4 * k + 2];
+  const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
+  const KmcEvalContext ctx{s_box, s_envpos, reinterpret_cast<const double2 *>(s_A2), reinterpret_cast<const uint2 *>(s_mask_hi), s_pbase,
+                           reinterpret_cast<const double2 *>(tab.pair_B2), tab.pair_C2, tab.n_pair_pairs * tab.n_species * tab.n_species,
+                           tab.n_species, solvent, vac_code};
+  const int64_t slots = static_cast<int64_t>(gridDim.x) * kKmcWalkersPerBlock;
+  const int64_t rounds = (n_items + slots - 1) / slots;          // every half-warp runs the same number of rounds (full-mask shuffles)
+  for (int64_t r = 0; r < rounds; ++r) {
+    const int64_t item_raw = r * slots + static_cast<int64_t>(blockIdx.x) * kKmcWalkersPerBlock + wl;
+    const bool real = item_raw < n_items;
+    const int64_t item = real ? item_raw : n_items - 1;
+    const int64_t vac_id = vacancy[item];
+    int err = 0;
+    const bool id_ok = vac_id >= 0 && vac_id < lat.num_sites;
+    if (!id_ok) err |= kErrBadSite;
+    const uint8_t *o = occ + (walker ? walker[item] : 0) * walker_stride;
+    int X, Y, Z;
+    lat.coords_of_id(id_ok ? vac_id : 0, X, Y, Z);
+    const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
+    const uint32_t id_j = static_cast<uint32_t>(lat.id_of_coords(xj, yj, zj));
+    if (active) s_ids[wl][lane] = id_j;
+    __syncwarp(hmask);
+    int slot = 0;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) slot += s_ids[wl][q] < id_j ? 1 : 0;
+    double ea = 0.0, de = 0.0, rate = 0.0;
+    unsigned mig = 0;
+    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, s_list_cell[wl], s_list_code[wl], s_codes[threadIdx.x], 0.0,
+                                 0, 0u, -1, err, ea, de, rate, mig);
+    const bool bad = ((__ballot_sync(hmask, err != 0) >> (threadIdx.x & 16)) & 0xFFFFu) != 0;     // any lane of this item
+    if (real && active) {
+      const int64_t at = item * 12 + slot;
+      neighbour[at] = id_j;
+      Ea[at] = bad ? nan("") : ea;
+      dE[at] = bad ? nan("") : de;
+    }
+    if (real && err) atomicOr(error, err);
+    __syncwarp(hmask);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ second-order KMC
 // mc::KineticMcChainOmpi (mc/src/KineticMcChainOmpi.cpp:56-152, mc/include/KineticMcAbstract.h:65-143): the reference
 // spreads the 12 first neighbours i of the vacancy site k over 12 MPI ranks; rank r moves the vacancy to i, evaluates

@@ -245,3 +245,34 @@ def test_full_size_identities(coef_json):
     ea2, de2 = e.eval_barriers(np.full(12, vac2), (nn + shift) % n, walker=np.ones(12, np.int32))
     order1, order2 = np.argsort(nn), np.argsort((nn + shift) % n)
     assert np.allclose(np.sort(ea), np.sort(ea2), rtol=0, atol=1e-12) and np.allclose(np.sort(de_v), np.sort(de2), rtol=0, atol=1e-12)
+
+
+def test_vacancy_event_lists_match_per_event_evaluation(golden, coef_json, tmp_path):
+    """lmc_eval_vacancy_events (one box scan per vacancy) against the golden Ea / dE of the reference for the same events,
+    in the reference's event order, and against lmc_eval_barriers on a many-walker engine."""
+    for tag in ("A", "B"):
+        order = capi.ORDER_REASSIGNED if int(golden[tag + "_factor"][1]) else capi.ORDER_GENERATE
+        e = capi.Engine(int(golden[tag + "_factor"][0]), id_order=order, n_walkers=1, device=0)
+        e.load_coefficients(H.golden_json(golden, tmp_path))
+        base = golden[tag + "_ev_base_occ"]
+        vacs = golden[tag + "_ev_vac"][::12]
+        for q, v in enumerate(vacs):
+            occ = base.copy(); occ[v] = 0
+            e.set_occupancy(occ)
+            nb, ea, de = e.eval_vacancy_events([int(v)])
+            sl = slice(12 * q, 12 * q + 12)
+            assert np.array_equal(nb[0], golden[tag + "_ev_j"][sl])                       # ascending neighbour ids = reference order
+            assert np.max(np.abs(ea[0] - golden[tag + "_ev_Ea"][sl])) < 1e-9 and np.max(np.abs(de[0] - golden[tag + "_ev_dE"][sl])) < 1e-9
+    f, W = 6, 40
+    e = capi.Engine(f, n_walkers=W, device=0)
+    e.load_coefficients(coef_json)
+    rng = np.random.default_rng(5)
+    vac = rng.integers(0, 4 * f ** 3, W)
+    for w in range(W):
+        e.set_occupancy(synth.random_alloy(f, 0.1, 0.1, seed=50 + w, vacancy_site=int(vac[w])), walker=w)
+    nb, ea, de = e.eval_vacancy_events(vac, walker=np.arange(W))
+    ea2, de2 = e.eval_barriers(np.repeat(vac, 12), nb.reshape(-1), walker=np.repeat(np.arange(W), 12))
+    assert np.array_equal(nb, np.stack([e.neighbors(1, int(v)) for v in vac]))
+    assert np.max(np.abs(ea.reshape(-1) - ea2)) < 1e-12 and np.max(np.abs(de.reshape(-1) - de2)) < 1e-12
+    with pytest.raises(capi.LmcOutOfRange):                                                   # not a vacancy there
+        e.eval_vacancy_events([int((vac[0] + 1) % (4 * f ** 3))], walker=[0])
