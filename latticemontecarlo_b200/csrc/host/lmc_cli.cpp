@@ -155,8 +155,14 @@ struct HostConfig {
   std::vector<Vec3> rel_of_lattice;                // lattice_vector_[l].relative_position_
   std::vector<std::array<int, 3>> map_shift;       // map_shift_list_[a]
   std::vector<int64_t> atom_to_lattice, lattice_to_atom;
+  lmc_id_order id_order{LMC_ID_ORDER_REASSIGNED};  // how lattice ids map to sites (a .cfg is reassigned; a map keeps lattice.txt's order)
   size_t n() const { return element_of_atom.size(); }
-  int64_t lattice_id(int X, int Y, int Z) const {   // ReassignLatticeVector order
+  int64_t lattice_id(int X, int Y, int Z) const {
+    if (id_order == LMC_ID_ORDER_GENERATE) {        // cfg::GenerateFCC order (Config.cpp:1073-1090): ((k fy + j) fx + i) 4 + basis site
+      const int b = (X & 1) ? ((Y & 1) ? 1 : 2) : ((Y & 1) ? 3 : 0);
+      return ((static_cast<int64_t>(Z >> 1) * factors[1] + (Y >> 1)) * factors[0] + (X >> 1)) * 4 + b;
+    }
+    // ReassignLatticeVector order
     return static_cast<int64_t>(X) * (2LL * factors[1] * factors[2]) + static_cast<int64_t>(Y) * factors[2] + (Z >> 1);
   }
   uint8_t element_at_lattice(int64_t l) const { return element_of_atom[static_cast<size_t>(lattice_to_atom[static_cast<size_t>(l)])]; }
@@ -264,6 +270,108 @@ struct HostConfig {
       c.rel_of_lattice[static_cast<size_t>(l)] = rel[a];
     }
     return c;
+  }
+  // Config::ReadMap (Config.cpp:814-885): lattice.txt (positions + neighbour lists, lattice-id order as written),
+  // element.txt (element of every atom id), map file (lattice id of every atom id).  No reassignment (Home.cpp:133-138):
+  // the ids of lattice.txt are kept, so the file must be in one of the two orders the engine knows (what
+  // Config::WriteLattice produces from a generated or a reassigned configuration); the neighbour columns are checked.
+  static HostConfig read_map(const std::string &lattice_filename, const std::string &element_filename, const std::string &map_filename) {
+    std::ifstream ifs_lattice(lattice_filename);
+    if (!ifs_lattice) throw std::runtime_error("Cannot open " + lattice_filename);
+    HostConfig c;
+    size_t num_atoms = 0;
+    ifs_lattice >> num_atoms;
+    ifs_lattice.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) ifs_lattice >> c.basis[i][j];
+    c.rel_of_lattice.resize(num_atoms);
+    std::vector<std::array<int64_t, 42>> neighbours(num_atoms);
+    for (size_t l = 0; l < num_atoms; ++l) {
+      ifs_lattice >> c.rel_of_lattice[l][0] >> c.rel_of_lattice[l][1] >> c.rel_of_lattice[l][2];
+      ifs_lattice.ignore(std::numeric_limits<std::streamsize>::max(), '#');
+      for (auto &v : neighbours[l]) ifs_lattice >> v;
+      if (!ifs_lattice) throw std::runtime_error("Unexpected end of " + lattice_filename);
+      ifs_lattice.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
+    }
+    c.detect_factors(num_atoms, lattice_filename);
+    // which id order?  compare every site's id under both orders with its line number
+    std::vector<std::array<int, 3>> xyz(num_atoms);
+    for (size_t l = 0; l < num_atoms; ++l) xyz[l] = c.grid_coordinates(c.rel_of_lattice[l], lattice_filename);
+    bool found = false;
+    for (lmc_id_order order : {LMC_ID_ORDER_REASSIGNED, LMC_ID_ORDER_GENERATE}) {
+      c.id_order = order;
+      bool ok = true;
+      for (size_t l = 0; l < num_atoms && ok; ++l) ok = c.lattice_id(xyz[l][0], xyz[l][1], xyz[l][2]) == static_cast<int64_t>(l);
+      if (ok) { found = true; break; }
+    }
+    if (!found) throw std::runtime_error(lattice_filename + ": lattice ids are neither in GenerateFCC nor in ReassignLatticeVector order");
+    // the first-neighbour column must be what this order implies (ascending ids of the 12 nearest sites)
+    for (size_t l = 0; l < num_atoms; l += std::max<size_t>(1, num_atoms / 64)) {
+      std::vector<int64_t> want;
+      static const int nn[12][3] = {{1, 1, 0}, {1, -1, 0}, {-1, 1, 0}, {-1, -1, 0}, {1, 0, 1}, {1, 0, -1}, {-1, 0, 1}, {-1, 0, -1},
+                                    {0, 1, 1}, {0, 1, -1}, {0, -1, 1}, {0, -1, -1}};
+      for (const auto &d : nn) {
+        int q[3];
+        for (int k = 0; k < 3; ++k) q[k] = ((xyz[l][k] + d[k]) % (2 * c.factors[k]) + 2 * c.factors[k]) % (2 * c.factors[k]);
+        want.push_back(c.lattice_id(q[0], q[1], q[2]));
+      }
+      std::sort(want.begin(), want.end());
+      if (!std::equal(want.begin(), want.end(), neighbours[l].begin()))
+        throw std::runtime_error(lattice_filename + ": neighbour list of lattice id " + std::to_string(l) + " does not match the FCC supercell");
+    }
+    std::ifstream ifs_element(element_filename);
+    if (!ifs_element) throw std::runtime_error("Cannot open " + element_filename);
+    c.element_of_atom.resize(num_atoms);
+    c.map_shift.assign(num_atoms, {0, 0, 0});
+    for (size_t a = 0; a < num_atoms; ++a) {
+      std::string type;
+      ifs_element >> type;
+      if (!ifs_element) throw std::runtime_error("Unexpected end of " + element_filename);
+      c.element_of_atom[a] = static_cast<uint8_t>(element_from_string(type));
+      ifs_element.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
+    }
+    std::ifstream ifs_map(map_filename);
+    if (!ifs_map) throw std::runtime_error("Cannot open " + map_filename);
+    c.atom_to_lattice.assign(num_atoms, -1);
+    c.lattice_to_atom.assign(num_atoms, -1);
+    for (size_t a = 0; a < num_atoms; ++a) {
+      long long l = -1;
+      ifs_map >> l;
+      if (!ifs_map) throw std::runtime_error("Unexpected end of " + map_filename);
+      if (l < 0 || static_cast<size_t>(l) >= num_atoms) throw std::runtime_error("Lattice id out of bounds in map file: " + std::to_string(l));
+      if (c.lattice_to_atom[static_cast<size_t>(l)] >= 0) throw std::runtime_error("Duplicate lattice id in map file: " + std::to_string(l));
+      c.lattice_to_atom[static_cast<size_t>(l)] = static_cast<int64_t>(a);
+      c.atom_to_lattice[a] = l;
+      ifs_map.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
+    }
+    return c;
+  }
+  // FCC supercell detection: factors from the basis lengths and the site count
+  void detect_factors(size_t num_atoms, const std::string &filename) {
+    double len[3], volume_cells = static_cast<double>(num_atoms) / 4.0, prod = 1.0;
+    for (int d = 0; d < 3; ++d) {
+      len[d] = std::sqrt(basis[d][0] * basis[d][0] + basis[d][1] * basis[d][1] + basis[d][2] * basis[d][2]);
+      prod *= len[d];
+    }
+    const double scale = std::cbrt(volume_cells / prod);
+    size_t check_sites = 4;
+    for (int d = 0; d < 3; ++d) {
+      factors[d] = static_cast<int32_t>(std::lround(len[d] * scale));
+      check_sites *= static_cast<size_t>(factors[d]);
+    }
+    if (check_sites != num_atoms) throw std::runtime_error(filename + ": not an FCC supercell (site count does not match the basis)");
+  }
+  // half-unit grid coordinates of a relative position
+  std::array<int, 3> grid_coordinates(const Vec3 &rel, const std::string &filename) const {
+    std::array<int, 3> xyz{};
+    for (int d = 0; d < 3; ++d) {
+      const double g = rel[d] * 2.0 * factors[d];
+      const long r = std::lround(g);
+      if (std::abs(g - static_cast<double>(r)) > 1e-3) throw std::runtime_error(filename + ": site off the FCC lattice");
+      xyz[static_cast<size_t>(d)] = static_cast<int>(((r % (2 * factors[d])) + 2 * factors[d]) % (2 * factors[d]));
+    }
+    if ((xyz[0] + xyz[1] + xyz[2]) & 1) throw std::runtime_error(filename + ": site on the wrong FCC sublattice");
+    return xyz;
   }
   // cfg::GenerateFCC (Config.cpp:1060-1095) relabelled like ReassignLatticeVector would: atom id = lattice id
   static HostConfig generate_fcc(size_t f, int element) {
@@ -392,13 +500,13 @@ unsigned long long make_seed(const Parameter &p) {
 
 // ------------------------------------------------------------------------------------------------ KineticMcFirstOmp
 void run_kmc(const Parameter &p, bool second_order) {
-  if (!p.map_filename.empty()) throw std::runtime_error("map_filename input is not supported: start from a .cfg");
-  HostConfig config = HostConfig::read(p.config_filename);
+  // api/src/Home.cpp:133-138: a map file replaces the .cfg (lattice.txt / element.txt are fixed names in the working directory)
+  HostConfig config = p.map_filename.empty() ? HostConfig::read(p.config_filename) : HostConfig::read_map("lattice.txt", "element.txt", p.map_filename);
   std::cout << "Finish config reading. Start KMC." << std::endl;
   const auto elements = element_codes(p.element_set);
   const int solvent = solvent_of(config);
   EngineHandle eng;
-  check(lmc_engine_create(&eng.e, config.factors, LMC_ID_ORDER_REASSIGNED, elements.data(), static_cast<int32_t>(elements.size()),
+  check(lmc_engine_create(&eng.e, config.factors, config.id_order, elements.data(), static_cast<int32_t>(elements.size()),
                           std::find(elements.begin(), elements.end(), solvent) != elements.end() ? solvent : 0, 1, p.device));
   check(lmc_engine_load_coefficients(eng.e, p.json_coefficients_filename.c_str()));
   const auto occ = config.occupancy();
@@ -546,14 +654,13 @@ void run_swap_driver(const Parameter &p, bool annealing) {
     elements.push_back(solvent);
     for (const auto &s : p.solute_element_set) elements.push_back(element_from_string(s));
   } else {
-    if (!p.map_filename.empty()) throw std::runtime_error("map_filename input is not supported: start from a .cfg");
-    config = HostConfig::read(p.config_filename);
+    config = p.map_filename.empty() ? HostConfig::read(p.config_filename) : HostConfig::read_map("lattice.txt", "element.txt", p.map_filename);
     std::cout << "Finish config reading. Start CMC." << std::endl;
     elements = element_codes(p.element_set);
     solvent = solvent_of(config);
   }
   EngineHandle eng;
-  check(lmc_engine_create(&eng.e, config.factors, LMC_ID_ORDER_REASSIGNED, elements.data(), static_cast<int32_t>(elements.size()),
+  check(lmc_engine_create(&eng.e, config.factors, config.id_order, elements.data(), static_cast<int32_t>(elements.size()),
                           std::find(elements.begin(), elements.end(), solvent) != elements.end() ? solvent : 0, 1, p.device));
   check(lmc_engine_load_coefficients(eng.e, p.json_coefficients_filename.c_str()));
   if (annealing) {

@@ -388,6 +388,22 @@ void *ref_config_read(const char *path, int reassign) {
     return new cfg::Config(std::move(config));
   } catch (const std::exception &e) { fail(e); return nullptr; }
 }
+// Config::ReadMap (cfg/src/Config.cpp:814-885): lattice.txt + element.txt + map file, lattice ids as written (no reassignment)
+void *ref_config_read_map(const char *lattice, const char *element, const char *map) {
+  try {
+    return new cfg::Config(cfg::Config::ReadMap(lattice, element, map));
+  } catch (const std::exception &e) { fail(e); return nullptr; }
+}
+// Config::WriteLattice / WriteElement / WriteMap (:887-922)
+int ref_config_write_map_files(void *h, const char *lattice, const char *element, const char *map) {
+  try {
+    auto *config = static_cast<cfg::Config *>(h);
+    config->WriteLattice(lattice);
+    config->WriteElement(element);
+    config->WriteMap(map);
+    return 0;
+  } catch (const std::exception &e) { return fail(e); }
+}
 void *ref_config_clone(void *h) { return new cfg::Config(*static_cast<cfg::Config *>(h)); }
 int ref_config_write(void *h, const char *path) {
   try { static_cast<cfg::Config *>(h)->WriteConfig(path); return 0; } catch (const std::exception &e) { return fail(e); }

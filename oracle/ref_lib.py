@@ -46,7 +46,7 @@ def lib():
             raise RuntimeError("oracle/_ref/liblmc_ref.so missing: run `make -C oracle` where /root/reference exists")
         _lib = C.CDLL(_SO)
         _lib.ref_last_error.restype = C.c_char_p
-        for name in ("ref_config_create", "ref_config_read", "ref_config_clone", "ref_quartic_create",
+        for name in ("ref_config_create", "ref_config_read", "ref_config_read_map", "ref_config_clone", "ref_quartic_create",
                      "ref_pairsite_create", "ref_energy_create"):
             getattr(_lib, name).restype = C.c_void_p
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
@@ -96,6 +96,15 @@ class RefConfig:
     @classmethod
     def read(cls, path, reassign=True):
         return cls(lib().ref_config_read(str(path).encode(), int(bool(reassign))))
+
+    @classmethod
+    def read_map(cls, lattice_path, element_path, map_path):
+        """Config::ReadMap: lattice ids as written in lattice.txt (no reassignment)."""
+        return cls(lib().ref_config_read_map(str(lattice_path).encode(), str(element_path).encode(), str(map_path).encode()))
+
+    def write_map_files(self, lattice_path, element_path, map_path):
+        if lib().ref_config_write_map_files(self.h, str(lattice_path).encode(), str(element_path).encode(), str(map_path).encode()) != 0:
+            raise RuntimeError(_err())
 
     def clone(self):
         return RefConfig(lib().ref_config_clone(self.h))

@@ -47,6 +47,32 @@ def main():
     print(open(os.path.join(out, "kmc_log.txt")).read()[:600])
     print(sorted(os.listdir(out)))
     chain(golden, js, tt)
+    from_map(js, tt)
+
+
+def from_map(js, tt):
+    """map_filename input (api/src/Home.cpp:133-138 -> Config::ReadMap): lattice.txt / element.txt / map.txt written by the
+    reference's own Config::WriteLattice / WriteElement / WriteMap from the GenerateFCC-ordered start configuration (ids are
+    NOT reassigned on this path) -> tests/golden/cli_map_v1/.  Only the file formats can be pinned: a reference run started
+    through ReadMap crashes in Config::LatticeJump / GetUnwrappedCartesianPositionOfLattice because ReadMap never allocates
+    map_shift_list_ (cfg/src/Config.cpp:814-885 vs :283,:448).  The test therefore checks the CLI against this repository's
+    C ABI in the same id order."""
+    out = os.path.join(ROOT, "tests", "golden", "cli_map_v1")
+    os.makedirs(out, exist_ok=True)
+    start = R.RefConfig.read(os.path.join(ROOT, "tests", "golden", "cli_v1", "start.cfg"), reassign=False)
+    start.write_map_files(os.path.join(out, "lattice.txt"), os.path.join(out, "element.txt"), os.path.join(out, "map.txt"))
+    back = R.RefConfig.read_map(os.path.join(out, "lattice.txt"), os.path.join(out, "element.txt"), os.path.join(out, "map.txt"))
+    assert np.array_equal(back.occupancy(), start.occupancy())
+    np.save(os.path.join(out, "occupancy_by_lattice_id.npy"), start.occupancy())
+    rng = np.random.default_rng(77)
+    np.savetxt(os.path.join(out, "uniforms.txt"), rng.random((STEPS + 1, 2)), fmt="%.17g")
+    with open(os.path.join(out, "kmc_param.txt"), "w") as f:
+        f.write("simulation_method KineticMcFirstOmp\njson_coefficients_filename coefficients.json\n"
+                "time_temperature_filename time_temperature.dat\nmap_filename map.txt\nlog_dump_steps 1\n"
+                "config_dump_steps 1000\nmaximum_steps %d\nthermodynamic_averaging_steps 0\ntemperature 500\n"
+                "element_set Al Mg Zn\nrestart_steps 0\nrestart_energy 0\nrestart_time 0\nrate_corrector true\n"
+                "early_stop false\nsolute_disp false\nreplay_uniforms_filename uniforms.txt\n" % STEPS)
+    print(sorted(os.listdir(out)))
 
 
 def chain(golden, js, tt):

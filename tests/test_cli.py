@@ -89,6 +89,47 @@ def test_chain_kmc_cli_reproduces_reference_log_and_dumps(exe, golden, tmp_path)
 
 
 @pytest.mark.gpu
+def test_kmc_cli_from_map_files(exe, golden, tmp_path):
+    """map_filename input (Config::ReadMap): lattice.txt / element.txt / map.txt as written by the reference
+    (tests/golden/cli_map_v1; GenerateFCC id order, kept as is).  The reference itself cannot run from this input (see
+    make_golden_cli.from_map), so the CLI's log is checked against the C ABI driven in the same id order with the same
+    uniforms; the cfg path's parity with the reference is covered by the tests above."""
+    gold = os.path.join(ROOT, "tests", "golden", "cli_map_v1")
+    for name in ("lattice.txt", "element.txt", "map.txt", "kmc_param.txt", "uniforms.txt"):
+        shutil.copy(os.path.join(gold, name), tmp_path / name)
+    shutil.copy(os.path.join(GOLD, "time_temperature.dat"), tmp_path / "time_temperature.dat")
+    js = H.golden_json(golden, tmp_path)
+    shutil.copy(js, tmp_path / "coefficients.json")
+    res = subprocess.run([exe, "-p", "kmc_param.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 0, res.stderr
+    _, rows = _rows((tmp_path / "kmc_log.txt").read_text())
+    occ = np.load(os.path.join(gold, "occupancy_by_lattice_id.npy"))
+    u = np.loadtxt(os.path.join(gold, "uniforms.txt"))
+    tt = np.loadtxt(os.path.join(GOLD, "time_temperature.dat"))
+    e = capi.Engine(4, id_order=capi.ORDER_GENERATE, device=0)
+    e.load_coefficients(js)
+    e.set_occupancy(occ)
+    e.kmc_reset()
+    n = len(u)
+    tr = e.kmc_run(n, temperature=500.0, time_temperature=tt, rate_corrector=True, replay_u1=u[:, 0], replay_u2=u[:, 1], trace=True)
+    assert len(rows) == n
+    time = np.concatenate([[0.0], np.cumsum(tr["dt"][0])])
+    energy = np.concatenate([[0.0], np.cumsum(tr["dE"][0])])
+    for s, r in enumerate(rows):
+        v = [float(x) for x in r]
+        assert int(v[0]) == s
+        assert np.isclose(v[1], time[s], rtol=1e-9, atol=0) and abs(v[3] - energy[s]) < 1e-9
+        assert abs(v[4] - tr["Ea"][0][s]) < 1e-9 and abs(v[5] - tr["dE"][0][s]) < 1e-9
+    # bad inputs fail like the reference's ReadMap (Config.cpp:819-879)
+    (tmp_path / "map.txt").write_text("0\n0\n")
+    res = subprocess.run([exe, "-p", "kmc_param.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 1 and "Duplicate lattice id in map file: 0" in res.stderr
+    os.remove(tmp_path / "lattice.txt")
+    res = subprocess.run([exe, "-p", "kmc_param.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 1 and "Cannot open lattice.txt" in res.stderr
+
+
+@pytest.mark.gpu
 def test_cmc_and_sa_cli_run_and_log(exe, golden, coef_json, tmp_path):
     """CanonicalMcOmp / SimulatedAnnealing through the CLI: log format, monotone step counter, energy bookkeeping
     against the total energy of the dumped configurations (re-read through the engine)."""
