@@ -299,6 +299,7 @@ def run_ours(args):
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(js)
         if not args.no_chain:
+            line["single_trajectory"] = bench_single_trajectory(local_rank, js)
             line["chain"] = bench_chain(engine, W, temps, occ_pinned, peak, js, n_gpus == 1 and not args.no_cpu_baseline)
         if not args.no_cmc:
             line["cmc"] = bench_cmc(torch, local_rank, js, peak, n_gpus == 1 and not args.no_cpu_baseline)
@@ -362,6 +363,32 @@ def bench_barrier_eval(engine, torch, W, peak):
                           "achieved_gbs": achieved2, "frac_of_hbm_peak": achieved2 / peak, "bytes_per_event": BYTES_PER_EVENT,
                           "matches_barrier_kernel": same,
                           "note": "12 events of each of %d (walker, vacancy) items per launch, half-warp per item, one box scan" % (W * reps)}
+    return out
+
+
+def bench_single_trajectory(device, json_path):
+    """BASELINE configs[0] / configs[4]: ONE vacancy trajectory (a step is a serial dependency, so this is a latency
+    number): 10^6-site Al-2%Mg-2%Zn supercell (f = 63), time-temperature ramp + rate corrector, first- and second-order KMC."""
+    from latticemontecarlo_b200 import capi, synth
+    f, steps = 63, 20000
+    eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=device)
+    eng.load_coefficients(json_path)
+    occ = synth.random_alloy(f, P_MG, P_ZN, seed=42, vacancy_site=4 * f ** 3 // 2 + 3)
+    tt = np.array([[0.0, 300.0], [1e-3, 500.0], [1e-1, 700.0]])
+    out = {"sites": 4 * f ** 3, "steps_per_launch": steps, "unit": "hops/s",
+           "workload": "single vacancy, %d sites, T(t) ramp 300-700 K + rate corrector" % (4 * f ** 3)}
+    for name, second_order in (("first_order", False), ("second_order_chain", True)):
+        eng.set_occupancy(occ)
+        eng.kmc_reset()
+        eng.kmc_run(2000, time_temperature=tt, rate_corrector=True, seed=7, second_order=second_order)
+        ms = []
+        for _ in range(3):
+            eng.kmc_run(steps, time_temperature=tt, rate_corrector=True, seed=7, second_order=second_order)
+            ms.append(eng.last_kernel_ms())
+        st = eng.kmc_state()
+        out[name] = {"value": steps / (min(ms) * 1e-3), "kernel_ms": min(ms), "us_per_step": min(ms) * 1e3 / steps,
+                     "time_reached_s": float(st["time"][0]), "temperature_reached_K": float(st["temperature"][0])}
+    eng.close()
     return out
 
 

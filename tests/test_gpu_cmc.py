@@ -135,3 +135,23 @@ def test_whole_gpu_single_lattice_driver(coef_json):
     assert 0.3 * base < st4["temperature"][0] <= base * 1.1 ** 5 * (1 + 1e-9) and st4["energy"][0] < 0.0
     with pytest.raises(capi.LmcInvalidArgument):
         capi.Engine(6, n_walkers=2, device=0).cmc_grid_run(10)       # one lattice only
+
+
+def test_full_size_lattices_bookkeeping(coef_json):
+    """BASELINE configs[1] (40^3, 256k sites) and configs[3] (100^3, 4M sites, simulated annealing) at full size through a
+    size-independent identity: the accumulated dE of the accepted swaps equals the total-energy difference, and the
+    composition is conserved."""
+    for f, trials, sa in ((40, 300000, {}), (100, 1500000, dict(sa_initial_temperature=900.0, sa_maximum_steps=6000000))):
+        e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=0)
+        e.load_coefficients(coef_json)
+        occ = synth.random_alloy(f, 0.02, 0.02, seed=1000, vacancy_site=None)
+        e.set_occupancy(occ)
+        e0 = e.total_energy()
+        e.cmc_reset(**sa)
+        e.cmc_run(trials, temperature=800.0, seed=11)
+        st = e.cmc_state()
+        final = e.get_occupancy(0)
+        assert st["steps"][0] >= trials and st["accepted"][0] > 0.05 * trials
+        assert abs((e.total_energy() - e0) - st["energy"][0]) < 1e-7 * max(1.0, abs(st["energy"][0]))
+        assert np.array_equal(np.bincount(final, minlength=4), np.bincount(occ, minlength=4))
+        e.close()
