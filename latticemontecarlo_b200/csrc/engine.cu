@@ -74,7 +74,7 @@ Engine::Engine(const int32_t factors[3], int32_t id_order, const int32_t *elemen
       throw StatusError(LMC_ERR_NO_DEVICE, "CUDA device " + std::to_string(device) + " not available");
     LMC_CUDA(cudaSetDevice(device));
     LMC_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-    LMC_CUDA(cudaMalloc(&d_occ, static_cast<size_t>(n_walkers) * lat.padded_size));
+    LMC_CUDA(cudaMalloc(&d_occ, static_cast<size_t>(n_walkers) * lat.padded_size + 16));   // +16: the KMC box scan reads aligned words
     LMC_CUDA(cudaMalloc(&d_error, sizeof(int)));
     LMC_CUDA(cudaEventCreate(&ev_begin));
     LMC_CUDA(cudaEventCreate(&ev_end));
@@ -183,23 +183,43 @@ void Engine::upload_geometry_tables() {
   for (int t = 0; t < 43; ++t) {
     site_off[4 * t] = g.site_offsets[t].x; site_off[4 * t + 1] = g.site_offsets[t].y; site_off[4 * t + 2] = g.site_offsets[t].z;
   }
-  // KMC box tables
+  // KMC box tables: the (dx, dy) rows of the 7 x 7 box that hold at least one neighbourhood site of some jump
+  auto cell_of = [&](int zp, int dx, int dy, int slot, int &dz) {
+    const int dzi = slot + (zp == 0 ? -2 : -1);
+    dz = 2 * dzi - zp + ((zp + dx + dy) & 1);
+    return (dx * lat.ny + dy) * lat.nz + dzi;
+  };
+  auto envpos_of = [&](int k, int dx, int dy, int dz) -> int {
+    for (int t = 0; t < 60; ++t)
+      if (g.pair_offsets[k][0][t] == Int3{dx, dy, dz}) return g.env_of_state[t] >= 0 ? g.env_of_state[t] : (g.env_of_state[t] == -1 ? 58 : 59);
+    return -1;
+  };
+  std::vector<std::pair<int, int>> rows;
+  for (int dx = -3; dx <= 3; ++dx)
+    for (int dy = -3; dy <= 3; ++dy) {
+      bool used = false;
+      for (int zp = 0; zp < 2; ++zp)
+        for (int slot = 0; slot < 4; ++slot) {
+          int dz;
+          cell_of(zp, dx, dy, slot, dz);
+          for (int k = 0; k < 12; ++k) used = used || envpos_of(k, dx, dy, dz) >= 0;
+        }
+      if (used) rows.emplace_back(dx, dy);
+    }
+  if (static_cast<int>(rows.size()) > kBoxRows) throw std::logic_error("KMC box has more rows than the scan covers");
+  if (rows.at(kBoxCentreRow) != std::make_pair(0, 0)) throw std::logic_error("KMC box centre row is not where the kernels expect it");
+  while (static_cast<int>(rows.size()) < kBoxRows) rows.emplace_back(3, 3);      // padding rows: scanned, never mapped (no site of any jump)
   std::vector<int32_t> box_delta(2 * kBoxCells, 0);
   std::vector<int8_t> box_envpos(2 * 12 * kBoxCells, -1);
   for (int zp = 0; zp < 2; ++zp) {
-    const int dzi_min = zp == 0 ? -2 : -1;
     for (int c = 0; c < kBoxCells; ++c) {
-      const int slot = c % 4, dy = (c / 4) % 7 - 3, dx = c / 28 - 3;
-      const int dzi = slot + dzi_min;
-      const int dz = 2 * dzi - zp + ((zp + dx + dy) & 1);
-      box_delta[zp * kBoxCells + c] = (dx * lat.ny + dy) * lat.nz + dzi;
+      const int slot = c % 4, dx = rows[static_cast<size_t>(c / 4)].first, dy = rows[static_cast<size_t>(c / 4)].second;
+      int dz;
+      box_delta[zp * kBoxCells + c] = cell_of(zp, dx, dy, slot, dz);
       if (lat.padded_delta(dx, dy, dz, zp) != box_delta[zp * kBoxCells + c]) throw std::logic_error("box cell geometry is inconsistent");
-      for (int k = 0; k < 12; ++k)
-        for (int t = 0; t < 60; ++t)
-          if (g.pair_offsets[k][0][t] == Int3{dx, dy, dz})
-            box_envpos[(zp * 12 + k) * kBoxCells + c] = static_cast<int8_t>(g.env_of_state[t] >= 0 ? g.env_of_state[t] : (g.env_of_state[t] == -1 ? 58 : 59));
+      for (int k = 0; k < 12; ++k) box_envpos[(zp * 12 + k) * kBoxCells + c] = static_cast<int8_t>(envpos_of(k, dx, dy, dz));
     }
-    for (int k = 0; k < 12; ++k) {   // every neighbourhood site must be inside the box
+    for (int k = 0; k < 12; ++k) {   // every neighbourhood site must be inside the box, exactly once
       int found = 0;
       for (int c = 0; c < kBoxCells; ++c) found += box_envpos[(zp * 12 + k) * kBoxCells + c] >= 0;
       if (found != 60) throw std::logic_error("KMC box does not cover a jump neighbourhood");

@@ -18,7 +18,10 @@ namespace lmc {
 // structural constants of the ordered neighbourhoods (verified against tables.cpp at engine creation)
 constexpr int kFirstPos = 21, kSecondPos = 38, kCentrePos = 21;
 constexpr int kEnvN = 58, kSiteEnvN = 42;
-constexpr int kBoxCells = 7 * 7 * 4;   // KMC box scan: cells of the padded layout within 3 half-units of a vacancy
+constexpr int kBoxRows = 48;            // KMC box scan: (dx, dy) rows of the 7 x 7 box around a vacancy that hold a neighbourhood site of
+                                        // some jump (the 4 corner rows hold none: 45 rows, padded to 3 x 16 for the half-warp scan)
+constexpr int kBoxCells = kBoxRows * 4; // 4 consecutive z slots (cells of the padded layout) per row
+constexpr int kBoxCentreRow = 22;       // position of the vacancy's own row (dx = dy = 0) among the kept rows
 
 enum EventError : int { kErrNotNeighbour = 1, kErrNotVacancy = 2, kErrExtraVacancy = 4, kErrBadSite = 8 };
 

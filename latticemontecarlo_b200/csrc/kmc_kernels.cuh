@@ -109,7 +109,7 @@ __global__ void kmc_init_kernel(LatticeDesc lat, const uint8_t *__restrict__ occ
 
 constexpr int kKmcThreads = 128;   // 8 walkers per block
 constexpr int kKmcWalkersPerBlock = kKmcThreads / 16;
-constexpr int kBoxRows = 49;                  // (dx, dy) rows of the 7 x 7 x 4 box; the vacancy sits in row 24, slot 2 (even Z) or 1 (odd Z)
+// the vacancy sits in row kBoxCentreRow of the box, slot 2 (even Z) or 1 (odd Z)
 
 // Shared-memory tables and constants every event evaluation needs (set up once per block)
 struct KmcEvalContext {
@@ -136,7 +136,7 @@ struct KmcEvalContext {
 template <bool kHypothetical>
 __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, const KmcEvalContext &ctx, const uint8_t *o, int X, int Y,
                                                       int Z, int lane, bool active, int k, int32_t dmig0, int32_t dmig1,
-                                                      uint8_t *list_cell, uint8_t *list_code, uint8_t *my_codes, double beta,
+                                                      uint16_t *list, uint8_t *my_codes, double beta,
                                                       int64_t hypo_index, unsigned hypo_code, int hypo_dir, int &err, double &ea,
                                                       double &de, double &rate, unsigned &mig) {
   constexpr unsigned hmask = 0xFFFFFFFFu;
@@ -161,17 +161,20 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
     const unsigned solvent4 = solvent * 0x01010101u;
     const int centre_slot = zp ? 1 : 2;
 #pragma unroll
-    for (int it = 0; it < (kBoxRows + 15) / 16; ++it) {
+    static_assert(kBoxRows % 16 == 0, "the half-warp scans 16 rows per iteration");
+    for (int it = 0; it < kBoxRows / 16; ++it) {
       const int row = it * 16 + lane;
-      if (it * 16 + 15 < kBoxRows || row < kBoxRows) {
-        const uint8_t *p = o + base + box[row * 4];
-        unsigned word = static_cast<unsigned>(p[0]) | (static_cast<unsigned>(p[1]) << 8) | (static_cast<unsigned>(p[2]) << 16) |
-                        (static_cast<unsigned>(p[3]) << 24);
+      {
+        // 4 consecutive bytes at arbitrary alignment: two aligned 32-bit loads + one funnel shift (the occupancy buffer
+        // carries 16 bytes of slack at its end for the second word)
+        const uintptr_t addr = reinterpret_cast<uintptr_t>(o + base + box[row * 4]);
+        const unsigned *aligned = reinterpret_cast<const unsigned *>(addr & ~static_cast<uintptr_t>(3));
+        unsigned word = __funnelshift_r(aligned[0], aligned[1], 8u * static_cast<unsigned>(addr & 3u));
         if (kHypothetical) {
           const int64_t off = hypo_index - (base + box[row * 4]);      // the cell the vacancy came from holds the moved atom
           if (off >= 0 && off < 4) word = (word & ~(0xFFu << (8 * static_cast<int>(off)))) | (hypo_code << (8 * static_cast<int>(off)));
         }
-        if (row == kBoxRows / 2) {                                     // the row through the vacancy itself
+        if (row == kBoxCentreRow) {                                    // the row through the vacancy itself
           if (!kHypothetical && ((word >> (8 * centre_slot)) & 0xFFu) != vac_code) err |= kErrNotVacancy;
           word = (word & ~(0xFFu << (8 * centre_slot))) | (solvent << (8 * centre_slot));
         }
@@ -197,8 +200,8 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
     while (hit_mask) {
       const int it = __ffs(static_cast<int>(hit_mask)) - 1;
       hit_mask &= hit_mask - 1;
-      list_cell[pos] = static_cast<uint8_t>(((it >> 2) * 16 + lane) * 4 + (it & 3));       // cell = row * 4 + slot
-      list_code[pos] = static_cast<uint8_t>((hit_codes >> (4 * it)) & 0xFULL);
+      // one 16-bit entry per non-solvent cell: cell index (row * 4 + slot) | species code << 8
+      list[pos] = static_cast<uint16_t>((((it >> 2) * 16 + lane) * 4 + (it & 3)) | (static_cast<unsigned>((hit_codes >> (4 * it)) & 0xFULL) << 8));
       ++pos;
     }
     __syncwarp(hmask);
@@ -211,10 +214,11 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
         const int8_t *envpos = s_envpos + (zp * 12 + k) * kBoxCells;
         uint64_t sol = 0;
         for (int q = 0; q < count; ++q) {
-          const int t = envpos[list_cell[q]];
+          const unsigned ent = list[q];
+          const int t = envpos[ent & 0xFFu];
           if (t >= 0 && t < kEnvN) {
             sol |= 1ULL << t;
-            my_codes[t] = list_code[q];
+            my_codes[t] = static_cast<uint8_t>(ent >> 8);
           }
         }
         // contracted tables: Q = C[m] + sum_t A[m][t][e_t] + sum_(t,u) B[m][(t,u)][e_t][e_u] over the solute sites
@@ -264,12 +268,12 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
 // The 12 jumps of one vacancy share a 7 x 7 x 7 half-unit box (196 padded cells).  Per step the half-warp scans the box
 // ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
 // event lane then maps that list into its own symmetry-ordered environment through a constant cell -> env-index table.
-__global__ void __launch_bounds__(kKmcThreads, 7)
+__global__ void __launch_bounds__(kKmcThreads, 8)
 kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
   __shared__ int32_t s_box[2 * kBoxCells];
   __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
-  __shared__ uint8_t s_list_cell[kKmcWalkersPerBlock][kBoxCells], s_list_code[kKmcWalkersPerBlock][kBoxCells];
+  __shared__ uint16_t s_list[kKmcWalkersPerBlock][kBoxCells];
   __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
   __shared__ double s_ord_rate[kKmcWalkersPerBlock][12];
   __shared__ uint8_t s_ord_lane[kKmcWalkersPerBlock][12];
@@ -308,7 +312,8 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
   double *ord_rate = s_ord_rate[wl];
   uint8_t *ord_lane = s_ord_lane[wl];
-  uint8_t *list_cell = s_list_cell[wl], *list_code = s_list_code[wl], *my_codes = s_codes[threadIdx.x];
+  uint16_t *list = s_list[wl];
+  uint8_t *my_codes = s_codes[threadIdx.x];
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
   const double2 *s_A2v = reinterpret_cast<const double2 *>(s_A2);
   const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
@@ -320,12 +325,13 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
 
   double beta = 1.0 / kBoltzmannEv / temperature;
   double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
+  double corr_over_prefactor = corr / kPrefactorHz;     // dt = -ln(u1) / total / 1e13 * corr with one division per step
   for (int64_t s = 0; s < n_steps; ++s) {
     // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50): only a T(t) table changes the temperature during a run
     if (prm.n_tt > 0) {
       temperature = interpolate_temperature(prm, time);
       beta = 1.0 / kBoltzmannEv / temperature;
-      if (prm.rate_corrector) corr = rate_correction(c_vac, c_sol, temperature);
+      if (prm.rate_corrector) { corr = rate_correction(c_vac, c_sol, temperature); corr_over_prefactor = corr / kPrefactorHz; }
     }
     // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
     const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
@@ -337,7 +343,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     for (int q = 0; q < 12; ++q) slot += ids[q] < id_j ? 1 : 0;
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
-    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list_cell, list_code, my_codes, beta, 0, 0u, -1,
+    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list, my_codes, beta, 0, 0u, -1,
                                  err, ea, de, rate, mig);
     if ((__ballot_sync(hmask, err != 0) >> hshift) & 0xFFFFu) alive = false;    // this walker stops; its state is left untouched
     if (!__any_sync(hmask, alive)) break;
@@ -368,7 +374,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       u1 = uniform53(r[0], r[1]) + (1.0 / 9007199254740992.0);   // (0, 1]: -log(u1) is finite
       u2 = uniform53(r[2], r[3]);
     }
-    const double dt = -log(u1) / total / kPrefactorHz * corr;
+    const double dt = -log(u1) / total * corr_over_prefactor;
     // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
     const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> hshift) & 0xFFFu;
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
@@ -425,7 +431,7 @@ vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict_
                       double *__restrict__ Ea, double *__restrict__ dE, int *error) {
   __shared__ int32_t s_box[2 * kBoxCells];
   __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
-  __shared__ uint8_t s_list_cell[kKmcWalkersPerBlock][kBoxCells], s_list_code[kKmcWalkersPerBlock][kBoxCells];
+  __shared__ uint16_t s_list[kKmcWalkersPerBlock][kBoxCells];
   __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
   extern __shared__ double s_A2[];
   __shared__ uint64_t s_mask_hi[kEnvN];
@@ -469,7 +475,7 @@ vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict_
     for (int q = 0; q < 12; ++q) slot += s_ids[wl][q] < id_j ? 1 : 0;
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
-    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, s_list_cell[wl], s_list_code[wl], s_codes[threadIdx.x], 0.0,
+    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, s_list[wl], s_codes[threadIdx.x], 0.0,
                                  0, 0u, -1, err, ea, de, rate, mig);
     const bool bad = ((__ballot_sync(hmask, err != 0) >> (threadIdx.x & 16)) & 0xFFFFu) != 0;     // any lane of this item
     if (real && active) {
@@ -499,7 +505,7 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
                      int64_t n_steps, const double *__restrict__ replay_u, KmcTraceDev tr) {
   __shared__ int32_t s_box[2 * kBoxCells];
   __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
-  __shared__ uint8_t s_list_cell[12][kBoxCells], s_list_code[12][kBoxCells];
+  __shared__ uint16_t s_list[12][kBoxCells];
   __shared__ uint8_t s_codes[kChainThreads][kEnvN + 2];
   __shared__ double s_ord_rate[12][12];
   extern __shared__ double s_A2[];
@@ -583,7 +589,7 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
     for (int q = 0; q < 12; ++q) slot += s_ids[h][q] < id_l ? 1 : 0;
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
-    kmc_scan_and_evaluate<true>(lat, ctx, o, xi, yi, zi, lane, active, k, dmig0, dmig1, s_list_cell[h], s_list_code[h],
+    kmc_scan_and_evaluate<true>(lat, ctx, o, xi, yi, zi, lane, active, k, dmig0, dmig1, s_list[h],
                                 s_codes[threadIdx.x], beta, hypo_index, mig_i, back_dir, err, ea, de, rate, mig);
     // total_rate_i in event order (KineticMcChainOmpi.cpp:71-85)
     if (active) s_ord_rate[h][slot] = rate;
