@@ -449,6 +449,8 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
         pinned.numpy()[:] = occ
         temps = np.linspace(600.0, 1000.0, replicas) if replicas > 1 else np.array([800.0])
         eng.set_occupancy_all(pinned.numpy())
+        if name == "single_lattice_40x40x40":
+            out["swap_de_eval"] = bench_swap_de_eval(torch, eng, 4 * f ** 3, peak)
         eng.cmc_reset(*(sa or ()))
         eng.cmc_run(trials // 4, temperatures=temps, seed=5)          # warm-up
         kernel_ms, done = [], []
@@ -481,6 +483,31 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline_cmc(json_path)
     return out
+
+
+def bench_swap_de_eval(torch, eng, n_sites, peak, n=1 << 22):
+    """Batched EnergyChangePredictorPairSite::GetDeFromLatticeIdPair with resident inputs: n uniformly random site pairs
+    of the 256k-site lattice (same-species pairs return 0 like the reference; ~42/N of the pairs are coupled)."""
+    rng = np.random.default_rng(11)
+    dev = torch.device("cuda")
+    d_a = torch.from_numpy(rng.integers(0, n_sites, n)).to(dev)
+    d_b = torch.from_numpy(rng.integers(0, n_sites, n)).to(dev)
+    d_de = torch.empty(n, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+    times = []
+    for k in range(8):
+        eng.eval_swap_de_dev(n, 0, d_a.data_ptr(), d_b.data_ptr(), d_de.data_ptr())
+        ms = eng.last_kernel_ms()
+        if k >= 3:
+            times.append(ms)
+    ms = sum(times) / len(times)
+    unlike = int((d_de != 0).sum().item())
+    achieved = n * BYTES_PER_TRIAL / (ms * 1e-3) / 1e9
+    return {"kernel": "swap_de_kernel", "pairs": n, "unlike_pairs": unlike, "ms": ms, "pairs_per_s": n / (ms * 1e-3),
+            "unlike_pairs_per_s": unlike / (ms * 1e-3), "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak,
+            "bytes_per_trial": BYTES_PER_TRIAL, "finite": bool(torch.isfinite(d_de).all().item()),
+            "note": "uniformly random pairs of one 40x40x40 lattice; same-species pairs (dE = 0 without a gather) are counted "
+                    "in pairs_per_s / achieved_gbs, unlike_pairs_per_s counts only the pairs that were evaluated"}
 
 
 def bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, json_path):

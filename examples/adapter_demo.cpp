@@ -1,7 +1,7 @@
 // adapter_demo.cpp -- the reference's call pattern (KineticMcFirstOmp::BuildEventList, mc/src/KineticMcFirstOmp.cpp:52-68)
 // written against the drop-in adapters: evaluate the 12 candidate jumps of the vacancy, then run the batched driver.
 //   g++ -std=c++17 -Iinclude examples/adapter_demo.cpp -Llatticemontecarlo_b200 -llmc_b200 -Wl,-rpath,$PWD/latticemontecarlo_b200
-//   ./a.out coefficients.json <factor>
+//   ./a.out coefficients.json <factor> [e0_coefficients.json]
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -39,6 +39,27 @@ int main(int argc, char **argv) {
       (void)predictor.GetBarrierAndDiffFromLatticeIdPair(config, {vacancy, vacancy + 7});   // not a first neighbour
     } catch (const std::out_of_range &e) {
       std::printf("std::out_of_range as in the reference: %s\n", e.what());
+    }
+    if (argc > 3) {
+      // the alternative predictors (VacancyMigrationPredictorE0Lru, EnergyChangePredictorPair / Site) on the same Config;
+      // the quartic predictor above stays valid: each barrier predictor puts its own model back on the engine when needed
+      const pred::VacancyMigrationPredictorE0Lru e0_predictor(argv[3], config, element_set, 100000);
+      const pred::EnergyChangePredictorPair pair_predictor(argv[3], config, element_set);
+      const pred::EnergyChangePredictorSite site_predictor(argv[3], config, element_set);
+      const auto neighbours = config.GetNeighbors(1, vacancy);
+      for (size_t j : neighbours) {
+        const auto [ea, de] = e0_predictor.GetBarrierAndDiffFromLatticeIdPair(config, {vacancy, j});
+        std::printf("E0 model %zu -> %zu  barrier %.12f  change %+.12f  pair-predictor %+.12f\n", vacancy, j, ea, de,
+                    pair_predictor.GetDeFromLatticeIdPair(config, {vacancy, j}));
+      }
+      std::printf("site %zu -> Mg: %+.12f\n", neighbours[0], site_predictor.GetDeFromLatticeIdSite(config, neighbours[0], ElementName::Mg));
+      try {
+        (void)pair_predictor.GetDeFromLatticeIdPair(config, {vacancy, config.GetNeighbors(2, vacancy)[0]});
+      } catch (const std::out_of_range &) {
+        std::printf("pair predictor: std::out_of_range for a second-neighbour pair\n");
+      }
+      const auto [ea_q, de_q] = predictor.GetBarrierAndDiffFromLatticeIdPair(config, {vacancy, neighbours[0]});   // quartic again
+      std::printf("quartic after E0: %.12f %+.12f\n", ea_q, de_q);
     }
     mc::KineticMcFirstOmp kmc(config, 999, 500.0, argv[1]);
     kmc.Simulate();

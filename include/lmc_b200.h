@@ -70,6 +70,20 @@ int32_t lmc_engine_num_walkers(const lmc_engine *engine);
  * (parsed like pred/src/VacancyMigrationPredictorQuartic.cpp:38-63, EnergyChangePredictorPairSite.cpp:29-40,
  * EnergyPredictor.cpp:27-38).  Missing file -> LMC_ERR_RUNTIME "Cannot open <file>". */
 int lmc_engine_load_coefficients(lmc_engine *engine, const char *json_path);
+/* The same with the barrier model named: the reference selects it by predictor class.
+ *   LMC_BARRIER_QUARTIC  pred::VacancyMigrationPredictorQuartic[Lru] (the model every live driver uses, KineticMcAbstract.h:50);
+ *                        keys mu_x_mmm sigma_x_mmm U_mmm mu_x_mm2 sigma_x_mm2 U_mm2 theta_D theta_Ks mu_D sigma_D mu_Ks sigma_Ks
+ *   LMC_BARRIER_E0       pred::VacancyMigrationPredictorE0[Lru] (pred/src/VacancyMigrationPredictorE0.cpp:9-160, JSON keys :30-37
+ *                        mu_x_mmm sigma_x_mmm U_mmm theta_e0 mu_e0 sigma_e0): dE as above, e0 = exp(mu_e0 + sigma_e0 theta_e0 . U_mmm x^),
+ *                        Ea = max(0, e0 + dE / 2) (:153-159).  lmc_eval_barriers then returns D = 1 and Ks = e0; the KMC drivers
+ *                        run on either model.
+ * "Base".theta (the dE part, also used by lmc_eval_swap_de / lmc_eval_site_de / lmc_total_energy, i.e. by
+ * pred::EnergyChangePredictorPairSite / Pair / Site and pred::EnergyPredictor) is read in both cases. */
+typedef enum lmc_barrier_model { LMC_BARRIER_QUARTIC = 0, LMC_BARRIER_E0 = 1 } lmc_barrier_model;
+int lmc_engine_load_coefficients_model(lmc_engine *engine, const char *json_path, int32_t model);
+/* the barrier model of the coefficients currently loaded (an engine holds ONE at a time), or -1 if the file had no
+ * per-element barrier blocks */
+int lmc_engine_barrier_model(const lmc_engine *engine);
 
 /* Occupancy by lattice id (ElementName codes), one replica ("walker") at a time or all at once (n_walkers*N bytes).
  * Replaces cfg::Config::{SetAtomElementTypeAtLattice, GetElementAtLatticeId} (Config.cpp:132-135,462-464). */
@@ -112,7 +126,14 @@ int lmc_eval_swap_de(lmc_engine *engine, int64_t n, const int32_t *walker, const
                      double *dE);
 int lmc_eval_swap_de_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a,
                          const int64_t *site_b, double *dE);
-/* EnergyChangePredictorPairSite::GetDeFromLatticeIdSite (:154-192): species at `site` replaced by new_element */
+/* EnergyChangePredictorPair::GetDeFromLatticeIdPair (pred/include/EnergyChangePredictorPair.h:22-25, src :69-122): the same
+ * exchange energy restricted to FIRST-NEIGHBOUR pairs, the only pairs that predictor holds a cluster list for: equal species
+ * give 0 (:71-75); an unlike pair that is not a first-neighbour pair returns LMC_ERR_OUT_OF_RANGE (the reference's
+ * unordered_map::at throws std::out_of_range, :83) with NaN in the offending outputs. */
+int lmc_eval_pair_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a, const int64_t *site_b,
+                     double *dE);
+/* EnergyChangePredictorPairSite::GetDeFromLatticeIdSite (:154-192) == EnergyChangePredictorSite::GetDeFromLatticeIdSite
+ * (pred/src/EnergyChangePredictorSite.cpp:56-98): species at `site` replaced by new_element */
 int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site,
                      const uint8_t *new_element, double *dE);
 /* EnergyPredictor::GetEnergy / GetEncode (pred/src/EnergyPredictor.cpp:40-96,173-177) of one replica.

@@ -7,6 +7,9 @@
 //   pred::VacancyMigrationPredictorQuartic[Lru]::GetBarrierAndDiffFromLatticeIdPair   pred/include/VacancyMigrationPredictorQuartic.h:25-27
 //   pred::EnergyChangePredictorPairSite::GetDeFromLatticeIdPair / ...Site             pred/include/EnergyChangePredictorPairSite.h:20-25
 //   pred::EnergyPredictor::GetEnergy                                                   pred/include/EnergyPredictor.h:19-25
+//   pred::VacancyMigrationPredictorE0[Lru]::GetBarrierAndDiffFromLatticeIdPair        pred/include/VacancyMigrationPredictorE0.h:26-31
+//   pred::EnergyChangePredictorPair::GetDeFromLatticeIdPair                            pred/include/EnergyChangePredictorPair.h:22-25
+//   pred::EnergyChangePredictorSite::GetDeFromLatticeIdSite                            pred/include/EnergyChangePredictorSite.h:22-25
 //   mc::KineticMcFirstOmp / CanonicalMcOmp / SimulatedAnnealing ::Simulate             mc/include/*.h
 //
 // What differs, by design: the configuration lives on the device (lmc_b200::Config owns an lmc_engine and the
@@ -82,20 +85,26 @@ class Config {
 
 namespace pred {
 // One JSON file feeds all three predictors, exactly as in the reference (each of its constructors re-reads the file).
-inline void LoadCoefficients(const cfg::Config &reference_config, const std::string &predictor_filename) {
-  check(lmc_engine_load_coefficients(reference_config.engine(), predictor_filename.c_str()));
+inline void LoadCoefficients(const cfg::Config &reference_config, const std::string &predictor_filename,
+                             lmc_barrier_model model = LMC_BARRIER_QUARTIC) {
+  check(lmc_engine_load_coefficients_model(reference_config.engine(), predictor_filename.c_str(), model));
+}
+// An engine holds the barrier tables of ONE model at a time.  A barrier predictor re-loads its file if another predictor
+// object has put a different model (or none) on the shared engine since, so two predictor objects on one Config stay correct.
+inline void EnsureBarrierModel(const cfg::Config &config, const std::string &predictor_filename, lmc_barrier_model model) {
+  if (lmc_engine_barrier_model(config.engine()) != static_cast<int>(model)) LoadCoefficients(config, predictor_filename, model);
 }
 
 class VacancyMigrationPredictorQuartic {
  public:
   VacancyMigrationPredictorQuartic(const std::string &predictor_filename, const cfg::Config &reference_config,
-                                   const std::set<ElementName> & /*element_set: fixed by the Config*/) {
-    LoadCoefficients(reference_config, predictor_filename);
-  }
+                                   const std::set<ElementName> & /*element_set: fixed by the Config*/)
+      : VacancyMigrationPredictorQuartic(predictor_filename, reference_config, LMC_BARRIER_QUARTIC) {}
   virtual ~VacancyMigrationPredictorQuartic() = default;
   // {Ea, dE} of the vacancy at .first exchanging with the atom at .second
   [[nodiscard]] virtual std::pair<double, double> GetBarrierAndDiffFromLatticeIdPair(
       const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair, int walker = 0) const {
+    EnsureBarrierModel(config, filename_, model_);
     const int64_t i = static_cast<int64_t>(lattice_id_jump_pair.first), j = static_cast<int64_t>(lattice_id_jump_pair.second);
     const int32_t w = walker;
     double ea = 0, de = 0;
@@ -105,6 +114,7 @@ class VacancyMigrationPredictorQuartic {
   // batch form: all candidate events of a step (or of many walkers) in one launch
   void GetBarrierAndDiffFromLatticeIdPairs(const cfg::Config &config, const std::vector<int32_t> &walker, const std::vector<int64_t> &first,
                                            const std::vector<int64_t> &second, std::vector<double> &Ea, std::vector<double> &dE) const {
+    EnsureBarrierModel(config, filename_, model_);
     Ea.resize(first.size());
     dE.resize(first.size());
     check(lmc_eval_barriers(config.engine(), static_cast<int64_t>(first.size()), walker.empty() ? nullptr : walker.data(), first.data(),
@@ -114,6 +124,7 @@ class VacancyMigrationPredictorQuartic {
   // in adjacency order with their {Ea, dE}
   void GetEventListOfVacancy(const cfg::Config &config, size_t vacancy_lattice_id, std::array<size_t, 12> &neighbour_lattice_ids,
                              std::array<std::pair<double, double>, 12> &barrier_and_diff, int walker = 0) const {
+    EnsureBarrierModel(config, filename_, model_);
     const int64_t v = static_cast<int64_t>(vacancy_lattice_id);
     const int32_t w = walker;
     int64_t nb[12];
@@ -124,6 +135,18 @@ class VacancyMigrationPredictorQuartic {
       barrier_and_diff[static_cast<size_t>(q)] = {ea[q], de[q]};
     }
   }
+
+ protected:
+  VacancyMigrationPredictorQuartic(const std::string &predictor_filename, const cfg::Config &reference_config, lmc_barrier_model model)
+      : filename_(predictor_filename), model_(model) {
+    LoadCoefficients(reference_config, predictor_filename, model);
+    if (lmc_engine_barrier_model(reference_config.engine()) != static_cast<int>(model))   // the reference's json .at() would throw
+      throw std::out_of_range("coefficient file " + predictor_filename + " has no element blocks for this barrier model");
+  }
+
+ private:
+  std::string filename_;
+  lmc_barrier_model model_;
 };
 // The LRU cache (pred/src/VacancyMigrationPredictorQuarticLru.cpp) is replaced by batch recomputation; cache_size is accepted and ignored.
 class VacancyMigrationPredictorQuarticLru : public VacancyMigrationPredictorQuartic {
@@ -131,6 +154,20 @@ class VacancyMigrationPredictorQuarticLru : public VacancyMigrationPredictorQuar
   VacancyMigrationPredictorQuarticLru(const std::string &predictor_filename, const cfg::Config &reference_config,
                                       const std::set<ElementName> &element_set, size_t /*cache_size*/)
       : VacancyMigrationPredictorQuartic(predictor_filename, reference_config, element_set) {}
+};
+
+// pred::VacancyMigrationPredictorE0 (pred/src/VacancyMigrationPredictorE0.cpp): same interface, coefficient keys
+// mu_x_mmm / sigma_x_mmm / U_mmm / theta_e0 / mu_e0 / sigma_e0, Ea = max(0, e0 + dE / 2).  Batch and event-list forms are inherited.
+class VacancyMigrationPredictorE0 : public VacancyMigrationPredictorQuartic {
+ public:
+  VacancyMigrationPredictorE0(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &)
+      : VacancyMigrationPredictorQuartic(predictor_filename, reference_config, LMC_BARRIER_E0) {}
+};
+class VacancyMigrationPredictorE0Lru : public VacancyMigrationPredictorE0 {       // cache replaced by batch recomputation
+ public:
+  VacancyMigrationPredictorE0Lru(const std::string &predictor_filename, const cfg::Config &reference_config,
+                                 const std::set<ElementName> &element_set, size_t /*cache_size*/)
+      : VacancyMigrationPredictorE0(predictor_filename, reference_config, element_set) {}
 };
 
 class EnergyChangePredictorPairSite {
@@ -146,6 +183,39 @@ class EnergyChangePredictorPairSite {
     double de = 0;
     check(lmc_eval_swap_de(config.engine(), 1, &w, &a, &b, &de));
     return de;
+  }
+  [[nodiscard]] double GetDeFromLatticeIdSite(const cfg::Config &config, size_t lattice_id, ElementName new_element, int walker = 0) const {
+    const int64_t s = static_cast<int64_t>(lattice_id);
+    const uint8_t e = static_cast<uint8_t>(new_element);
+    const int32_t w = walker;
+    double de = 0;
+    check(lmc_eval_site_de(config.engine(), 1, &w, &s, &e, &de));
+    return de;
+  }
+};
+
+// pred::EnergyChangePredictorPair (pred/src/EnergyChangePredictorPair.cpp:69-122): exchange energy of a FIRST-NEIGHBOUR pair;
+// equal species give 0, an unlike pair further apart throws std::out_of_range like the reference's unordered_map::at (:83).
+// NB these dE predictors read only "Base".theta; they re-use whatever barrier model is on the engine.
+class EnergyChangePredictorPair {
+ public:
+  EnergyChangePredictorPair(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &) {
+    if (lmc_engine_barrier_model(reference_config.engine()) < 0) LoadCoefficients(reference_config, predictor_filename);
+  }
+  [[nodiscard]] double GetDeFromLatticeIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair,
+                                              int walker = 0) const {
+    const int64_t a = static_cast<int64_t>(lattice_id_jump_pair.first), b = static_cast<int64_t>(lattice_id_jump_pair.second);
+    const int32_t w = walker;
+    double de = 0;
+    check(lmc_eval_pair_de(config.engine(), 1, &w, &a, &b, &de));
+    return de;
+  }
+};
+// pred::EnergyChangePredictorSite (pred/src/EnergyChangePredictorSite.cpp:56-98)
+class EnergyChangePredictorSite {
+ public:
+  EnergyChangePredictorSite(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &) {
+    if (lmc_engine_barrier_model(reference_config.engine()) < 0) LoadCoefficients(reference_config, predictor_filename);
   }
   [[nodiscard]] double GetDeFromLatticeIdSite(const cfg::Config &config, size_t lattice_id, ElementName new_element, int walker = 0) const {
     const int64_t s = static_cast<int64_t>(lattice_id);

@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lmc_b200.h")
 
 LMC_OK, LMC_ERR_INVALID_ARGUMENT, LMC_ERR_OUT_OF_RANGE, LMC_ERR_RUNTIME, LMC_ERR_NO_DEVICE, LMC_ERR_CUDA = 0, -1, -2, -3, -4, -5
 ORDER_GENERATE, ORDER_REASSIGNED = 0, 1
+BARRIER_QUARTIC, BARRIER_E0 = 0, 1
 
 
 class LmcError(RuntimeError):
@@ -163,8 +164,12 @@ class Engine:
             pass
 
     # ---- state
-    def load_coefficients(self, json_path):
-        _check(lib().lmc_engine_load_coefficients(self.h, str(json_path).encode()))
+    def load_coefficients(self, json_path, model=BARRIER_QUARTIC):
+        """model: BARRIER_QUARTIC (VacancyMigrationPredictorQuartic) or BARRIER_E0 (VacancyMigrationPredictorE0)."""
+        if model == BARRIER_QUARTIC:
+            _check(lib().lmc_engine_load_coefficients(self.h, str(json_path).encode()))
+        else:
+            _check(lib().lmc_engine_load_coefficients_model(self.h, str(json_path).encode(), C.c_int32(int(model))))
 
     def set_occupancy(self, occ, walker=0):
         occ = np.ascontiguousarray(occ, dtype=np.uint8)
@@ -231,6 +236,17 @@ class Engine:
         out = np.empty(len(a))
         _check(lib().lmc_eval_swap_de(self.h, C.c_int64(len(a)), _p(w), _p(a), _p(b), _p(out)))
         return out
+
+    def eval_pair_de(self, site_a, site_b, walker=None):
+        """EnergyChangePredictorPair semantics: first-neighbour pairs only (LmcOutOfRange otherwise)."""
+        a, b = _i64(site_a), _i64(site_b)
+        w = None if walker is None else np.ascontiguousarray(walker, dtype=np.int32)
+        out = np.empty(len(a), dtype=np.float64)
+        _check(lib().lmc_eval_pair_de(self.h, C.c_int64(len(a)), _p(w), _p(a), _p(b), _p(out)))
+        return out
+
+    def barrier_model(self):
+        return int(lib().lmc_engine_barrier_model(self.h))
 
     def eval_site_de(self, site, new_element, walker=None):
         s = _i64(site)

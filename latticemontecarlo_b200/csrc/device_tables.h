@@ -29,6 +29,7 @@ struct DevTables {
   const double *pair_C, *pair_A, *pair_B;
   // the same folded to the two numbers a barrier needs: (dE, log E0) with log E0 = logKs + 2 logD   [..][2]
   const double *pair_C2, *pair_A2, *pair_B2;
+  int32_t barrier_model;         // 0: quartic closed form Ea(dE, E0 = Ks D^2); 1: E0 model, Ea = max(0, e0 + dE/2), log e0 in slot 2
   const uint64_t *pair_mask_hi;  // [58]
   const uint16_t *pair_base;     // [58]
   int32_t n_pair_pairs;          // 556

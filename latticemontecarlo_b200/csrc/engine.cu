@@ -320,9 +320,10 @@ void Engine::upload_geometry_tables() {
   d_enum_of_code = to_device(eoc);
 }
 
-void Engine::load_coefficients(const std::string &json_path) {
+void Engine::load_coefficients(const std::string &json_path, int model) {
   coefficients = parse_coefficients_json(json_path);
-  pair_tables = build_pair_tables(species, coefficients);
+  pair_tables = build_pair_tables(species, coefficients, model);
+  tab.barrier_model = model;
   site_tables = build_site_tables(species, coefficients);
   energy_tables = build_energy_tables(species, coefficients);
   has_coefficients = true;
@@ -483,18 +484,19 @@ void Engine::eval_vacancy_events(int64_t n, const int32_t *walker, const int64_t
   check_event_errors("lmc_eval_vacancy_events");
 }
 
-void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE) {
+void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE, bool first_neighbours_only) {
   require_device();
   require_coefficients();
   if (n <= 0) return;
   const unsigned blocks = static_cast<unsigned>((n + kSwapThreads - 1) / kSwapThreads);
   time_begin();
-  swap_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error);
+  swap_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error,
+                                                      first_neighbours_only ? 1 : 0);
   time_end();
   LMC_CUDA(cudaGetLastError());
 }
 
-void Engine::eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE) {
+void Engine::eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE, bool first_neighbours_only) {
   require_device();
   if (n <= 0) return;
   char *d = static_cast<char *>(scratch(static_cast<size_t>(n) * (8 + 8 + 8 + 4) + 64));
@@ -505,9 +507,9 @@ void Engine::eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, co
   LMC_CUDA(cudaMemcpyAsync(d_a, a, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
   LMC_CUDA(cudaMemcpyAsync(d_b, b, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
   if (walker) LMC_CUDA(cudaMemcpyAsync(d_w, walker, static_cast<size_t>(n) * 4, cudaMemcpyHostToDevice, stream));
-  eval_swap_de_dev(n, walker ? d_w : nullptr, d_a, d_b, d_out);
+  eval_swap_de_dev(n, walker ? d_w : nullptr, d_a, d_b, d_out, first_neighbours_only);
   LMC_CUDA(cudaMemcpyAsync(dE, d_out, static_cast<size_t>(n) * 8, cudaMemcpyDeviceToHost, stream));
-  check_event_errors("lmc_eval_swap_de");
+  check_event_errors(first_neighbours_only ? "lmc_eval_pair_de" : "lmc_eval_swap_de");
 }
 
 void Engine::eval_site_de(int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element, double *dE) {
@@ -1198,6 +1200,13 @@ int lmc_engine_load_coefficients(lmc_engine *engine, const char *json_path) {
     engine->impl->load_coefficients(json_path);
   });
 }
+int lmc_engine_load_coefficients_model(lmc_engine *engine, const char *json_path, int32_t model) {
+  return guard([&] {
+    if (!engine || !json_path) throw std::invalid_argument("null argument");
+    if (model != LMC_BARRIER_QUARTIC && model != LMC_BARRIER_E0) throw std::invalid_argument("unknown barrier model");
+    engine->impl->load_coefficients(json_path, model);
+  });
+}
 int lmc_engine_set_occupancy(lmc_engine *engine, int32_t walker, const uint8_t *occupancy, int64_t n) {
   return guard([&] { engine->impl->set_occupancy(walker, occupancy, n, 1); });
 }
@@ -1225,6 +1234,14 @@ int lmc_eval_barriers_dev(lmc_engine *engine, int64_t n, const int32_t *walker, 
 int lmc_eval_swap_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a, const int64_t *site_b,
                      double *dE) {
   return guard([&] { engine->impl->eval_swap_de(n, walker, site_a, site_b, dE); });
+}
+int lmc_eval_pair_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a, const int64_t *site_b,
+                     double *dE) {
+  return guard([&] { engine->impl->eval_swap_de(n, walker, site_a, site_b, dE, true); });
+}
+int lmc_engine_barrier_model(const lmc_engine *engine) {
+  if (!engine || !engine->impl->has_coefficients || !engine->impl->pair_tables.has_barrier) return -1;
+  return engine->impl->pair_tables.model;
 }
 int lmc_eval_swap_de_dev(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site_a,
                          const int64_t *site_b, double *dE) {

@@ -30,7 +30,7 @@ class Engine {
   Engine(const Engine &) = delete;
   Engine &operator=(const Engine &) = delete;
 
-  void load_coefficients(const std::string &json_path);
+  void load_coefficients(const std::string &json_path, int model = kModelQuartic);
   void set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_t count);
   void get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t count);
   void lattice_jump(int32_t walker, int64_t a, int64_t b);
@@ -39,8 +39,8 @@ class Engine {
                      double *D, double *Ks);
   void eval_barriers_dev(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea,
                          double *dE, double *D, double *Ks);
-  void eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE);
-  void eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE);
+  void eval_swap_de(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE, bool first_neighbours_only = false);
+  void eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE, bool first_neighbours_only = false);
   void eval_site_de(int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element, double *dE);
   double total_energy(int32_t walker, int64_t *counts, int32_t n_types);
   void debug_pair(int32_t walker, int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b, int32_t *sc,

@@ -52,6 +52,13 @@ __device__ __forceinline__ double quartic_barrier_log(double dE, double log_e0) 
   return e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
 }
 
+// Barrier from the folded pair (dE, log E0) for either coefficient model.  model 1 = VacancyMigrationPredictorE0
+// (pred/src/VacancyMigrationPredictorE0.cpp:153-159): Ea = max(0, e0 + dE / 2) with log e0 in the second slot.
+__device__ __forceinline__ double barrier_from_folded(double dE, double log_e0, int model) {
+  if (model == 0) return quartic_barrier_log(dE, log_e0);
+  return fmax(0.0, exp(log_e0) + 0.5 * dE);
+}
+
 // env index of a state-list position (the jump pair sits at positions 21 and 38)
 __host__ __device__ constexpr int env_of_pos(int t) { return t - (t > kFirstPos) - (t > kSecondPos); }
 __device__ __forceinline__ int pos_of_env(int e) { return e + (e >= kFirstPos) + (e >= kSecondPos - 1); }
@@ -227,7 +234,7 @@ barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
         if (!accumulate_pair_tables(tab, static_cast<int>(mig), sol, o, base, drow, acc)) err = kErrExtraVacancy;
         else {
           out_de = acc[0];
-          out_ea = quartic_barrier_log(out_de, acc[2] + 2.0 * acc[1]);
+          out_ea = barrier_from_folded(out_de, acc[2] + 2.0 * acc[1], tab.barrier_model);
           if (D_out) out_d = exp(acc[1]);
           if (Ks_out) out_ks = exp(acc[2]);
         }
@@ -301,7 +308,7 @@ __device__ __forceinline__ double site_energy_change(const DevTables &tab, int x
 // is the same sum over "clusters touching a or b" that the reference recounts on the fly (:96-134).
 __device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, const DevTables &tab, const uint8_t *__restrict__ occ,
                                                      const int32_t *__restrict__ s_delta, int xa, int ya, int za, int xb, int yb,
-                                                     int zb, int *err) {
+                                                     int zb, int *err, bool first_neighbours_only = false) {
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
   (void)vac;
   int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
@@ -314,6 +321,10 @@ __device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, con
   dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
   const int r2 = dx * dx + dy * dy + dz * dz;
   const bool coupled = r2 <= 6;
+  if (first_neighbours_only && r2 != 2) {     // EnergyChangePredictorPair: only first-neighbour pairs have a list (.at throws, :83)
+    *err |= kErrNotNeighbour;
+    return CUDART_NAN;
+  }
   int zpa = za & 1, zpb = zb & 1;
   if (coupled && eb == vac) {   // move the vacancy first so that no intermediate state holds two vacancies
     const int64_t tb = base_a; base_a = base_b; base_b = tb;
@@ -340,7 +351,7 @@ constexpr int kSwapThreads = 128;
 __global__ void __launch_bounds__(kSwapThreads)
 swap_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
                const int32_t *__restrict__ walker, const int64_t *__restrict__ site_a, const int64_t *__restrict__ site_b,
-               double *__restrict__ dE, int *__restrict__ error) {
+               double *__restrict__ dE, int *__restrict__ error, int first_neighbours_only) {
   __shared__ int32_t s_delta[2 * 43];
   for (int q = threadIdx.x; q < 2 * 43; q += blockDim.x) s_delta[q] = tab.site_delta[q];
   __syncthreads();
@@ -356,7 +367,8 @@ swap_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, 
   lat.coords_of_id(a, xa, ya, za);
   lat.coords_of_id(b, xb, yb, zb);
   int err = 0;
-  const double de = swap_energy_change(lat, tab, occ + (walker ? walker[e] : 0) * walker_stride, s_delta, xa, ya, za, xb, yb, zb, &err);
+  const double de = swap_energy_change(lat, tab, occ + (walker ? walker[e] : 0) * walker_stride, s_delta, xa, ya, za, xb, yb, zb, &err,
+                                       first_neighbours_only != 0);
   if (err) atomicOr(error, err);
   dE[e] = de;
 }

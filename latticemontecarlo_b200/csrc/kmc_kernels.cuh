@@ -122,6 +122,7 @@ struct KmcEvalContext {
   const double *C2;                // global: [n][2]
   int b_stride, n_species;
   unsigned solvent, vac_code;
+  int barrier_model;               // DevTables::barrier_model
 };
 
 // The 12 jumps of the vacancy at (X, Y, Z) of occupancy `o`, one jump per lane (lanes 0..11 of a half-warp; all 16 lanes
@@ -149,6 +150,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
   const uint16_t *s_pbase = ctx.s_pbase;
   const double2 *__restrict__ B_all = ctx.B_all;
   const int b_stride = ctx.b_stride;
+  const int barrier_model = ctx.barrier_model;
   {
     // ---- box scan: the non-solvent cells around the vacancy, in cell order
     const int zp = Z & 1;
@@ -257,7 +259,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
         if (!ok) err |= kErrExtraVacancy;
         else {
           de = a0;
-          ea = quartic_barrier_log(de, a1);
+          ea = barrier_from_folded(de, a1, barrier_model);
           rate = exp(-ea * beta);                      // JumpEvent.cpp:13
         }
       }
@@ -318,7 +320,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const double2 *s_A2v = reinterpret_cast<const double2 *>(s_A2);
   const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
   const KmcEvalContext ctx{s_box, s_envpos, s_A2v, s_mask_hi2, s_pbase, B_all, tab.pair_C2,
-                           tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code};
+                           tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code, tab.barrier_model};
   uint32_t *ids = s_ids[wl];
   const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
@@ -452,7 +454,7 @@ vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict_
   const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
   const KmcEvalContext ctx{s_box, s_envpos, reinterpret_cast<const double2 *>(s_A2), reinterpret_cast<const uint2 *>(s_mask_hi), s_pbase,
                            reinterpret_cast<const double2 *>(tab.pair_B2), tab.pair_C2, tab.n_pair_pairs * tab.n_species * tab.n_species,
-                           tab.n_species, solvent, vac_code};
+                           tab.n_species, solvent, vac_code, tab.barrier_model};
   const int64_t slots = static_cast<int64_t>(gridDim.x) * kKmcWalkersPerBlock;
   const int64_t rounds = (n_items + slots - 1) / slots;          // every half-warp runs the same number of rounds (full-mask shuffles)
   for (int64_t r = 0; r < rounds; ++r) {
@@ -548,7 +550,7 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
   const int32_t dmig0 = lat.padded_delta(dxk, dyk, dzk, 0), dmig1 = lat.padded_delta(dxk, dyk, dzk, 1);
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
   const KmcEvalContext ctx{s_box, s_envpos, reinterpret_cast<const double2 *>(s_A2), reinterpret_cast<const uint2 *>(s_mask_hi), s_pbase,
-                           B_all, tab.pair_C2, tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code};
+                           B_all, tab.pair_C2, tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code, tab.barrier_model};
   const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
   int err = 0;
 

@@ -585,23 +585,34 @@ Coefficients parse_coefficients_json(const std::string &path) {
       co.base_theta = to_vector(kv.second.at("theta"));
       continue;
     }
-    // every other top-level key is an element block (VacancyMigrationPredictorQuartic.cpp:44-62); blocks that do
-    // not carry the quartic keys (e.g. files written for the E0 model) are ignored here
-    if (!kv.second.find("mu_x_mmm") || !kv.second.find("U_mm2")) continue;
+    // every other top-level key is an element block.  Quartic files (VacancyMigrationPredictorQuartic.cpp:44-62) carry
+    // the mmm and mm2 blocks with theta_D / theta_Ks, E0 files (VacancyMigrationPredictorE0.cpp:30-37) the mmm block with
+    // theta_e0 / mu_e0 / sigma_e0; a block may carry both.  Blocks with neither are ignored here.
+    if (!kv.second.find("mu_x_mmm") || !kv.second.find("U_mmm")) continue;
+    const bool quartic = kv.second.find("U_mm2") != nullptr, e0 = kv.second.find("theta_e0") != nullptr;
+    if (!quartic && !e0) continue;
     ElementCoefficients ec;
     ec.mu_x_mmm = to_vector(kv.second.at("mu_x_mmm"));
-    ec.mu_x_mm2 = to_vector(kv.second.at("mu_x_mm2"));
     ec.sigma_x_mmm = to_vector(kv.second.at("sigma_x_mmm"));
-    ec.sigma_x_mm2 = to_vector(kv.second.at("sigma_x_mm2"));
     ec.U_mmm = to_matrix(kv.second.at("U_mmm"), &ec.k_mmm);
-    ec.U_mm2 = to_matrix(kv.second.at("U_mm2"), &ec.k_mm2);
-    ec.theta_D = to_vector(kv.second.at("theta_D"));
-    ec.theta_Ks = to_vector(kv.second.at("theta_Ks"));
-    ec.mu_D = to_number(kv.second.at("mu_D"));
-    ec.mu_Ks = to_number(kv.second.at("mu_Ks"));
-    ec.sigma_D = to_number(kv.second.at("sigma_D"));
-    ec.sigma_Ks = to_number(kv.second.at("sigma_Ks"));
-    ec.present = true;
+    if (quartic) {
+      ec.mu_x_mm2 = to_vector(kv.second.at("mu_x_mm2"));
+      ec.sigma_x_mm2 = to_vector(kv.second.at("sigma_x_mm2"));
+      ec.U_mm2 = to_matrix(kv.second.at("U_mm2"), &ec.k_mm2);
+      ec.theta_D = to_vector(kv.second.at("theta_D"));
+      ec.theta_Ks = to_vector(kv.second.at("theta_Ks"));
+      ec.mu_D = to_number(kv.second.at("mu_D"));
+      ec.mu_Ks = to_number(kv.second.at("mu_Ks"));
+      ec.sigma_D = to_number(kv.second.at("sigma_D"));
+      ec.sigma_Ks = to_number(kv.second.at("sigma_Ks"));
+      ec.present = true;
+    }
+    if (e0) {
+      ec.theta_e0 = to_vector(kv.second.at("theta_e0"));
+      ec.mu_e0 = to_number(kv.second.at("mu_e0"));
+      ec.sigma_e0 = to_number(kv.second.at("sigma_e0"));
+      ec.present_e0 = true;
+    }
     co.element[element_enum_from_name(kv.first)] = std::move(ec);
   }
   return co;
@@ -640,7 +651,7 @@ void check_theta(const Species &sp, const Coefficients &co, size_t n_types) {
 }
 }  // namespace
 
-PairTables build_pair_tables(const Species &sp, const Coefficients &co) {
+PairTables build_pair_tables(const Species &sp, const Coefficients &co, int model) {
   const Geometry &g = geometry();
   const int n = sp.n;
   const auto types = cluster_types(sp);
@@ -661,6 +672,8 @@ PairTables build_pair_tables(const Species &sp, const Coefficients &co) {
   };
   PairTables out;
   out.n = n;
+  out.model = model;
+  if (model != kModelQuartic && model != kModelE0) throw std::invalid_argument("unknown barrier model");
   int len_mmm = 0, len_mm2 = 0;
   const auto groups_mmm = group_layout(g, false, n, &len_mmm);
   const auto groups_mm2 = group_layout(g, true, n, &len_mm2);
@@ -704,7 +717,7 @@ PairTables build_pair_tables(const Species &sp, const Coefficients &co) {
     }
     // ---- logD / logKs (GetD :216-246, GetKs :167-215)
     const auto it = co.element.find(sp.enum_of_code[m]);
-    if (it == co.element.end() || !it->second.present) {
+    if (it == co.element.end() || !(model == kModelE0 ? it->second.present_e0 : it->second.present)) {
       C0[m * 3 + 1] = C0[m * 3 + 2] = kNaN;
       continue;
     }
@@ -725,6 +738,34 @@ PairTables build_pair_tables(const Species &sp, const Coefficients &co) {
         c0 -= w[i] * static_cast<ld>(mu_x[i]);
       }
     };
+    if (model == kModelE0) {
+      // log e0 = mu_e0 + sigma_e0 theta_e0^T U_mmm ((x - mu_x) / sigma_x)   (VacancyMigrationPredictorE0.cpp:128-151); it is
+      // stored as quantity 2 with quantity 1 == 0, so that the folded pair (dE, q2 + 2 q1) is (dE, log e0)
+      std::vector<ld> w_e0;
+      ld c_e0;
+      weights(ec.U_mmm, ec.k_mmm, ec.theta_e0, ec.sigma_x_mmm, ec.mu_x_mmm, ec.sigma_e0, ec.mu_e0, len_mmm, w_e0, c_e0, "mmm (E0)");
+      C0[m * 3 + 2] += c_e0;
+      for (const auto &c : g.mmm) {
+        const GroupInfo &gi = groups_mmm[c.group];
+        const ld inv = static_cast<ld>(1) / static_cast<ld>(gi.size);
+        if (c.arity == 1) {
+          const int t = g.env_of_mmm[c.pos[0]];
+          for (int e = 0; e < n; ++e) a_at(m, t, e, 2) += w_e0[gi.offset + e] * inv;
+        } else {
+          int t = g.env_of_mmm[c.pos[0]], u = g.env_of_mmm[c.pos[1]];
+          const bool swapped = t > u;
+          if (swapped) std::swap(t, u);
+          const int p = pair_index[t * kPairEnv + u];
+          if (p < 0) throw std::logic_error("mmm pair over a non-adjacent env pair");
+          for (int e1 = 0; e1 < n; ++e1)
+            for (int e2 = 0; e2 < n; ++e2) {
+              const int slot = gi.symmetric ? tri_index(e1, e2, n) : e1 * n + e2;
+              b_at(m, p, swapped ? e2 : e1, swapped ? e1 : e2, 2) += w_e0[gi.offset + slot] * inv;
+            }
+        }
+      }
+      continue;
+    }
     std::vector<ld> w_d, w_ks;
     ld c_d, c_ks;
     weights(ec.U_mmm, ec.k_mmm, ec.theta_D, ec.sigma_x_mmm, ec.mu_x_mmm, ec.sigma_D, ec.mu_D, len_mmm, w_d, c_d, "mmm");

@@ -132,8 +132,15 @@ struct ElementCoefficients {
   std::vector<double> U_mmm, U_mm2;          // row-major K x L
   int k_mmm{0}, k_mm2{0};
   double mu_D{0}, sigma_D{1}, mu_Ks{0}, sigma_Ks{1};
-  bool present{false};
+  bool present{false};                       // carries the quartic keys (mmm + mm2 blocks, theta_D / theta_Ks, ...)
+  // E0 model (pred/src/VacancyMigrationPredictorE0.cpp:30-37): mmm block + theta_e0 / mu_e0 / sigma_e0
+  std::vector<double> theta_e0;
+  double mu_e0{0}, sigma_e0{1};
+  bool present_e0{false};
 };
+// which closed form turns (dE, environment) into a barrier
+constexpr int kModelQuartic = 0;             // VacancyMigrationPredictorQuartic: Ea(dE, D, Ks)
+constexpr int kModelE0 = 1;                  // VacancyMigrationPredictorE0: Ea = max(0, e0 + dE / 2)
 struct Coefficients {
   std::vector<double> base_theta;
   std::map<int, ElementCoefficients> element;   // key: ElementName enum value
@@ -150,6 +157,7 @@ struct PairTables {
   std::vector<double> A;   // [m][t][e][3]
   std::vector<double> B;   // [m][pair][a][b][3]
   bool has_barrier{false}; // false if the JSON has no per-element blocks (dE only)
+  int model{kModelQuartic}; // kModelE0: quantity 1 is 0 and quantity 2 is log e0
 };
 // Site tables:  H(x, env) = Cs[x] + sum_t As[x][t][e_t] + sum_{(t,u)} Bs[x][(t,u)][e_t][e_u],  codes incl. vacancy;
 // dE(site: old->new) = H(new) - H(old)   (pred/src/EnergyChangePredictorPairSite.cpp:154-192)
@@ -167,7 +175,7 @@ struct EnergyTables {
   std::vector<double> triplet;  // [label-4][c1][c2][c3]
 };
 
-PairTables build_pair_tables(const Species &sp, const Coefficients &co);
+PairTables build_pair_tables(const Species &sp, const Coefficients &co, int model = kModelQuartic);
 SiteTables build_site_tables(const Species &sp, const Coefficients &co);
 EnergyTables build_energy_tables(const Species &sp, const Coefficients &co);
 

@@ -89,8 +89,25 @@ def synthetic_coefficients(seed=20240611, elements=("Al", "Mg", "Zn"), k_mmm=24,
     return out
 
 
-def write_synthetic_json(path, **kw):
-    coeffs = synthetic_coefficients(**kw)
+def synthetic_coefficients_e0(seed=20240612, elements=("Al", "Mg", "Zn"), k_mmm=24, mu_e0=math.log(0.55), sigma_e0=0.2):
+    """Synthetic file for the E0 model; key names as parsed at pred/src/VacancyMigrationPredictorE0.cpp:24-37."""
+    rng = np.random.default_rng(seed)
+    n_types, len_mmm, _ = encode_lengths(len(elements))
+    out = {"Base": {"theta": rng.normal(0.0, 50.0, n_types).tolist()}}
+    for e in elements:
+        out[e] = {
+            "mu_x_mmm": rng.uniform(0.0, 0.5, len_mmm).tolist(),
+            "sigma_x_mmm": rng.uniform(0.5, 1.5, len_mmm).tolist(),
+            "U_mmm": rng.normal(0.0, 1.0 / math.sqrt(len_mmm), (k_mmm, len_mmm)).tolist(),
+            "theta_e0": rng.normal(0.0, 0.3, k_mmm).tolist(),
+            "mu_e0": float(mu_e0),
+            "sigma_e0": float(sigma_e0),
+        }
+    return out
+
+
+def write_synthetic_json(path, model="quartic", **kw):
+    coeffs = synthetic_coefficients_e0(**kw) if model == "e0" else synthetic_coefficients(**kw)
     with open(path, "w") as f:
         json.dump(coeffs, f)
     return coeffs

@@ -728,6 +728,59 @@ class EnergyChangePredictorPairSite:
         return float(self._helper(sc, ec)[0])
 
 
+class VacancyMigrationPredictorE0(VacancyMigrationPredictorQuartic):
+    """pred::VacancyMigrationPredictorE0 (pred/src/VacancyMigrationPredictorE0.cpp): GetDe (:77-125) is the quartic
+    predictor's cluster-count difference with the same normalisers; GetE0 (:127-151) is the mmm one-hot model with
+    theta_e0 / mu_e0 / sigma_e0; Ea = max(0, e0 + dE / 2) (:153-159)."""
+
+    def get_e0(self, cfg, i, j):
+        i = np.atleast_1d(np.asarray(i, dtype=np.int64)); j = np.atleast_1d(np.asarray(j, dtype=np.int64))
+        _, mmm, _ = sorted_lists_of_pairs(cfg, i, j)
+        x_mmm, _, _ = one_hot_encode(self.mapping_mmm, cfg.occ[mmm], self.elements)
+        return np.exp(self._log_model(x_mmm, cfg.occ[j], "mu_x_mmm", "sigma_x_mmm", "U_mmm", "theta_e0", "mu_e0", "sigma_e0"))
+
+    def barrier_and_diff(self, cfg, i, j):
+        de = self.get_de(cfg, i, j)
+        return np.maximum(0.0, self.get_e0(cfg, i, j) + de / 2), de
+
+
+class EnergyChangePredictorPair:
+    """pred::EnergyChangePredictorPair (pred/src/EnergyChangePredictorPair.cpp:69-122): swap dE of a FIRST-NEIGHBOUR pair
+    from the 473 state clusters of the pair (first <- element of second, second <- element of first); equal elements
+    give 0 (:71-75); a pair that is not a first-neighbour pair has no cached list (`.at` throws, :83)."""
+
+    def __init__(self, coefficients, reference_config, element_codes):
+        self.elements = element_set_sorted(element_codes)
+        co = load_coefficients(coefficients)
+        self.mapping_state = mapping_state_pair(reference_config)   # :18
+        self.indexer = ClusterIndexer(self.elements, DE_CLUSTER_COUNTER)
+        self.base_theta = np.asarray(co["Base"]["theta"], dtype=np.float64)
+
+    def de_pair(self, cfg, a, b):
+        a = np.atleast_1d(np.asarray(a, dtype=np.int64)); b = np.atleast_1d(np.asarray(b, dtype=np.int64))
+        if not (cfg.nn[0][a] == b[:, None]).any(axis=1).all():
+            raise IndexError("EnergyChangePredictorPair: not a first-neighbour pair")
+        lo, hi = np.minimum(a, b), np.maximum(a, b)                   # the list of the id-sorted pair is used (:80-83)
+        state, _, _ = sorted_lists_of_pairs(cfg, lo, hi)
+        start = cfg.occ[state].astype(np.int64)
+        end = start.copy()
+        end[state == a[:, None]] = cfg.occ[b]
+        end[state == b[:, None]] = cfg.occ[a]
+        sc = _count_types(self.indexer, self.mapping_state, start)
+        ec = _count_types(self.indexer, self.mapping_state, end)
+        out = _seq_dot(self.base_theta, (ec.astype(np.float64) - sc.astype(np.float64)) / self.indexer.total_bonds)
+        out[cfg.occ[a] == cfg.occ[b]] = 0.0
+        return out
+
+
+class EnergyChangePredictorSite(EnergyChangePredictorPairSite):
+    """pred::EnergyChangePredictorSite (pred/src/EnergyChangePredictorSite.cpp:56-98): the single-site half of the
+    PairSite predictor (per-site cluster lists instead of one translated mapping; same clusters, same counts)."""
+
+    def de_pair(self, cfg, a, b):
+        raise AttributeError("EnergyChangePredictorSite has no pair interface")
+
+
 class EnergyPredictor:
     """pred::EnergyPredictor (pred/src/EnergyPredictor.cpp:40-96,173-177): ordered-tuple counting."""
 

@@ -32,6 +32,10 @@
 #include "EnergyChangePredictorPairSite.h"
 #include "VacancyMigrationPredictorQuartic.h"
 #include "VacancyMigrationPredictorQuarticLru.h"
+#include "VacancyMigrationPredictorE0.h"
+#include "VacancyMigrationPredictorE0Lru.h"
+#include "EnergyChangePredictorPair.h"
+#include "EnergyChangePredictorSite.h"
 #include "TimeTemperatureInterpolator.h"
 #include "RateCorrector.hpp"
 #include "KineticMcFirstOmp.h"
@@ -913,4 +917,71 @@ void ref_rng_uniform_real(uint64_t seed, int64_t n, double *out) {
   for (int64_t k = 0; k < n; ++k) out[k] = d(g);
 }
 
+}  // extern "C"
+
+// ---------------------------------------------------------------- VacancyMigrationPredictorE0[Lru], EnergyChangePredictorPair / Site
+// (the alternative predictors of SURVEY 2b / 8(f)4; no live driver instantiates them)
+namespace {
+struct E0Probe : pred::VacancyMigrationPredictorE0 {   // opens the protected GetE0
+  using pred::VacancyMigrationPredictorE0::VacancyMigrationPredictorE0;
+  using pred::VacancyMigrationPredictorE0::GetE0;
+};
+}  // namespace
+extern "C" {
+void *ref_e0_create(const char *json, void *config_h, const int *codes, int n, int64_t lru_size) {
+  try {
+    ScopedQuietCout quiet;
+    const auto &c = *static_cast<cfg::Config *>(config_h);
+    if (lru_size > 0)
+      return static_cast<pred::VacancyMigrationPredictorE0 *>(
+          new pred::VacancyMigrationPredictorE0Lru(json, c, element_set_from_codes(codes, n), static_cast<size_t>(lru_size)));
+    return static_cast<pred::VacancyMigrationPredictorE0 *>(new E0Probe(json, c, element_set_from_codes(codes, n)));
+  } catch (const std::exception &e) { fail(e); return nullptr; }
+}
+void ref_e0_free(void *h) { delete static_cast<pred::VacancyMigrationPredictorE0 *>(h); }
+// e0 (optional) needs the non-LRU predictor
+int ref_e0_eval(void *h, void *config_h, int64_t n, const int64_t *i, const int64_t *j, double *Ea, double *dE, double *e0) {
+  try {
+    const auto *p = static_cast<pred::VacancyMigrationPredictorE0 *>(h);
+    const auto *probe = dynamic_cast<const E0Probe *>(p);
+    if (e0 && !probe) throw std::runtime_error("e0 output needs the non-LRU predictor");
+    const auto &c = *static_cast<cfg::Config *>(config_h);
+    for (int64_t k = 0; k < n; ++k) {
+      const std::pair<size_t, size_t> pr{static_cast<size_t>(i[k]), static_cast<size_t>(j[k])};
+      const auto r = p->GetBarrierAndDiffFromLatticeIdPair(c, pr);
+      Ea[k] = r.first;
+      dE[k] = r.second;
+      if (e0) e0[k] = probe->GetE0(c, pr);
+    }
+    return 0;
+  } catch (const std::exception &e) { return fail(e); }
+}
+void *ref_pair_create(const char *json, void *config_h, const int *codes, int n) {
+  try {
+    return new pred::EnergyChangePredictorPair(json, *static_cast<cfg::Config *>(config_h), element_set_from_codes(codes, n));
+  } catch (const std::exception &e) { fail(e); return nullptr; }
+}
+void ref_pair_free(void *h) { delete static_cast<pred::EnergyChangePredictorPair *>(h); }
+int ref_pair_de(void *h, void *config_h, int64_t n, const int64_t *a, const int64_t *b, double *out) {
+  try {
+    const auto *p = static_cast<pred::EnergyChangePredictorPair *>(h);
+    const auto &c = *static_cast<cfg::Config *>(config_h);
+    for (int64_t k = 0; k < n; ++k) out[k] = p->GetDeFromLatticeIdPair(c, {static_cast<size_t>(a[k]), static_cast<size_t>(b[k])});
+    return 0;
+  } catch (const std::exception &e) { return fail(e); }
+}
+void *ref_site_create(const char *json, void *config_h, const int *codes, int n) {
+  try {
+    return new pred::EnergyChangePredictorSite(json, *static_cast<cfg::Config *>(config_h), element_set_from_codes(codes, n));
+  } catch (const std::exception &e) { fail(e); return nullptr; }
+}
+void ref_site_free(void *h) { delete static_cast<pred::EnergyChangePredictorSite *>(h); }
+int ref_site_de(void *h, void *config_h, int64_t n, const int64_t *site, const uint8_t *new_code, double *out) {
+  try {
+    const auto *p = static_cast<pred::EnergyChangePredictorSite *>(h);
+    const auto &c = *static_cast<cfg::Config *>(config_h);
+    for (int64_t k = 0; k < n; ++k) out[k] = p->GetDeFromLatticeIdSite(c, static_cast<size_t>(site[k]), element_from_code(new_code[k]));
+    return 0;
+  } catch (const std::exception &e) { return fail(e); }
+}
 }  // extern "C"

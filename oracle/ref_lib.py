@@ -47,7 +47,7 @@ def lib():
         _lib = C.CDLL(_SO)
         _lib.ref_last_error.restype = C.c_char_p
         for name in ("ref_config_create", "ref_config_read", "ref_config_read_map", "ref_config_clone", "ref_quartic_create",
-                     "ref_pairsite_create", "ref_energy_create"):
+                     "ref_pairsite_create", "ref_energy_create", "ref_e0_create", "ref_pair_create", "ref_site_create"):
             getattr(_lib, name).restype = C.c_void_p
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
             getattr(_lib, name).restype = C.c_int64
@@ -290,6 +290,87 @@ class RefPairSite:
             raise RuntimeError(_err())
         return de.value, sc[:n_types].copy(), ec[:n_types].copy()
 
+
+
+class RefE0:
+    """pred::VacancyMigrationPredictorE0 (lru_size=0) or ...E0Lru (lru_size>0)."""
+
+    def __init__(self, json_path, config: RefConfig, elements=("Al", "Mg", "Zn"), lru_size=0):
+        self._codes = _codes(elements)
+        self.lru = lru_size > 0
+        self.h = C.c_void_p(lib().ref_e0_create(str(json_path).encode(), config.h, self._codes[1], self._codes[2], C.c_int64(lru_size)))
+        if not self.h:
+            raise RuntimeError("reference predictor creation failed: " + _err())
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_e0_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def eval(self, config: RefConfig, i, j):
+        """(Ea, dE, e0); e0 is None for the LRU predictor (GetE0 is protected there)."""
+        i = np.ascontiguousarray(i, dtype=np.int64)
+        j = np.ascontiguousarray(j, dtype=np.int64)
+        ea, de = np.empty(len(i)), np.empty(len(i))
+        e0 = None if self.lru else np.empty(len(i))
+        if lib().ref_e0_eval(self.h, config.h, C.c_int64(len(i)), _p(i), _p(j), _p(ea), _p(de), _p(e0)) != 0:
+            raise RuntimeError(_err())
+        return ea, de, e0
+
+
+class RefPair:
+    """pred::EnergyChangePredictorPair (first-neighbour pairs only: anything else throws std::out_of_range)."""
+
+    def __init__(self, json_path, config: RefConfig, elements=("Al", "Mg", "Zn")):
+        self._codes = _codes(elements)
+        self.h = C.c_void_p(lib().ref_pair_create(str(json_path).encode(), config.h, self._codes[1], self._codes[2]))
+        if not self.h:
+            raise RuntimeError("reference predictor creation failed: " + _err())
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_pair_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def de_pair(self, config: RefConfig, a, b):
+        a = np.ascontiguousarray(a, dtype=np.int64)
+        b = np.ascontiguousarray(b, dtype=np.int64)
+        out = np.empty(len(a), dtype=np.float64)
+        if lib().ref_pair_de(self.h, config.h, C.c_int64(len(a)), _p(a), _p(b), _p(out)) != 0:
+            raise RuntimeError(_err())
+        return out
+
+
+class RefSite:
+    """pred::EnergyChangePredictorSite."""
+
+    def __init__(self, json_path, config: RefConfig, elements=("Al", "Mg", "Zn")):
+        self._codes = _codes(elements)
+        self.h = C.c_void_p(lib().ref_site_create(str(json_path).encode(), config.h, self._codes[1], self._codes[2]))
+        if not self.h:
+            raise RuntimeError("reference predictor creation failed: " + _err())
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().ref_site_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def de_site(self, config: RefConfig, site, new_code):
+        site = np.ascontiguousarray(site, dtype=np.int64)
+        new_code = np.ascontiguousarray(new_code, dtype=np.uint8)
+        out = np.empty(len(site), dtype=np.float64)
+        if lib().ref_site_de(self.h, config.h, C.c_int64(len(site)), _p(site), _p(new_code), _p(out)) != 0:
+            raise RuntimeError(_err())
+        return out
 
 class RefEnergy:
     """pred::EnergyPredictor."""

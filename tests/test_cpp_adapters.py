@@ -49,6 +49,37 @@ def test_adapter_demo_matches_c_abi(demo, coef_json):
     assert np.max(np.abs(ea - ea2)) < 1e-11 and np.max(np.abs(de - de2)) < 1e-11
 
 
+@pytest.mark.gpu
+def test_adapter_alternative_predictors(demo, coef_json, tmp_path):
+    """VacancyMigrationPredictorE0Lru / EnergyChangePredictorPair / EnergyChangePredictorSite adapters against the C ABI,
+    sharing one Config with the quartic predictor (model hand-over on the engine)."""
+    from latticemontecarlo_b200 import synth
+    e0_json = str(tmp_path / "e0.json")
+    synth.write_synthetic_json(e0_json, model="e0", k_mmm=6)
+    res = subprocess.run([demo, coef_json, "6", e0_json], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    rows = np.array([[float(v) for v in m] for m in
+                     re.findall(r"E0 model \d+ -> \d+  barrier ([-0-9.e+]+)  change ([-+0-9.e]+)  pair-predictor ([-+0-9.e]+)", res.stdout)])
+    assert rows.shape == (12, 3) and "pair predictor: std::out_of_range" in res.stdout
+    f = 6
+    e = capi.Engine(f, device=0)
+    occ = _mt19937_64_alloy(4 * f ** 3)
+    e.set_occupancy(occ)
+    vac = len(occ) // 2 + 3
+    nb = e.neighbors(1, vac)
+    e.load_coefficients(e0_json, model=capi.BARRIER_E0)
+    ea, de = e.eval_barriers(np.full(12, vac), nb)
+    assert np.max(np.abs(rows[:, 0] - ea)) < 1e-11 and np.max(np.abs(rows[:, 1] - de)) < 1e-11
+    # the engine holds one coefficient file at a time: the pair / site predictors see the E0 file's Base.theta here
+    assert np.max(np.abs(rows[:, 2] - e.eval_pair_de(np.full(12, vac), nb))) < 1e-11
+    m = re.search(r"site \d+ -> Mg: ([-+0-9.e]+)", res.stdout)
+    assert abs(float(m.group(1)) - e.eval_site_de([nb[0]], [2])[0]) < 1e-11
+    e.load_coefficients(coef_json)
+    q = re.search(r"quartic after E0: ([-0-9.e+]+) ([-+0-9.e]+)", res.stdout)
+    ea_q, de_q = e.eval_barriers([vac], [nb[0]])
+    assert abs(float(q.group(1)) - ea_q[0]) < 1e-11 and abs(float(q.group(2)) - de_q[0]) < 1e-11
+
+
 def _mt19937_64_alloy(n):
     """std::mt19937_64(42) + uniform_real_distribution<double>(0,1): one 64-bit draw x, u = double(x) / 2^64
     (libstdc++ generate_canonical)."""
