@@ -450,7 +450,7 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
         temps = np.linspace(600.0, 1000.0, replicas) if replicas > 1 else np.array([800.0])
         eng.set_occupancy_all(pinned.numpy())
         if name == "single_lattice_40x40x40":
-            out["swap_de_eval"] = bench_swap_de_eval(torch, eng, 4 * f ** 3, peak)
+            out["swap_de_eval"] = bench_swap_de_eval(torch, eng, occ[0], peak)
         eng.cmc_reset(*(sa or ()))
         eng.cmc_run(trials // 4, temperatures=temps, seed=5)          # warm-up
         kernel_ms, done = [], []
@@ -485,13 +485,20 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
     return out
 
 
-def bench_swap_de_eval(torch, eng, n_sites, peak, n=1 << 22):
-    """Batched EnergyChangePredictorPairSite::GetDeFromLatticeIdPair with resident inputs: n uniformly random site pairs
-    of the 256k-site lattice (same-species pairs return 0 like the reference; ~42/N of the pairs are coupled)."""
+def bench_swap_de_eval(torch, eng, occ, peak, n=1 << 22):
+    """Batched EnergyChangePredictorPairSite::GetDeFromLatticeIdPair with resident inputs: n random UNLIKE-species site pairs
+    of the 256k-site lattice, drawn like CanonicalMcAbstract::GenerateLatticeIdJumpPair (redraw while the two species are
+    equal, CanonicalMcAbstract.cpp:43-51), so every pair costs two 43-site gathers; ~42/N of the pairs are coupled."""
     rng = np.random.default_rng(11)
+    n_sites = occ.size
+    a = rng.integers(0, n_sites, n)
+    b = rng.integers(0, n_sites, n)
+    same = np.nonzero(occ[a] == occ[b])[0]
+    while same.size:
+        b[same] = rng.integers(0, n_sites, same.size)
+        same = same[occ[a[same]] == occ[b[same]]]
     dev = torch.device("cuda")
-    d_a = torch.from_numpy(rng.integers(0, n_sites, n)).to(dev)
-    d_b = torch.from_numpy(rng.integers(0, n_sites, n)).to(dev)
+    d_a, d_b = torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev)
     d_de = torch.empty(n, dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
     times = []
@@ -501,13 +508,13 @@ def bench_swap_de_eval(torch, eng, n_sites, peak, n=1 << 22):
         if k >= 3:
             times.append(ms)
     ms = sum(times) / len(times)
-    unlike = int((d_de != 0).sum().item())
     achieved = n * BYTES_PER_TRIAL / (ms * 1e-3) / 1e9
-    return {"kernel": "swap_de_kernel", "pairs": n, "unlike_pairs": unlike, "ms": ms, "pairs_per_s": n / (ms * 1e-3),
-            "unlike_pairs_per_s": unlike / (ms * 1e-3), "achieved_gbs": achieved, "frac_of_hbm_peak": achieved / peak,
-            "bytes_per_trial": BYTES_PER_TRIAL, "finite": bool(torch.isfinite(d_de).all().item()),
-            "note": "uniformly random pairs of one 40x40x40 lattice; same-species pairs (dE = 0 without a gather) are counted "
-                    "in pairs_per_s / achieved_gbs, unlike_pairs_per_s counts only the pairs that were evaluated"}
+    check = eng.eval_swap_de(a[:4096], b[:4096])               # the host-buffer entry point on the same pairs
+    return {"kernel": "swap_de_rows_kernel", "pairs": n, "ms": ms, "pairs_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
+            "frac_of_hbm_peak": achieved / peak, "bytes_per_trial": BYTES_PER_TRIAL,
+            "finite": bool(torch.isfinite(d_de).all().item()),
+            "matches_host_entry_point": bool(np.array_equal(check, d_de[:4096].cpu().numpy())),
+            "note": "random unlike-species pairs of one 40x40x40 lattice (every pair is evaluated: 2 x 43-site gathers)"}
 
 
 def bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, json_path):

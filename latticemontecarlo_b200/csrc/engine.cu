@@ -68,6 +68,12 @@ Engine::Engine(const int32_t factors[3], int32_t id_order, const int32_t *elemen
   const Geometry &g = geometry();
   if (g.pair_first_pos != kFirstPos || g.pair_second_pos != kSecondPos || g.site_centre_pos != kCentrePos)
     throw std::logic_error("ordered-neighbourhood structural constants changed");
+  for (int r = 0; r < kSiteRows; ++r)          // the compile-time row table of gather_site_rows against the derived site list
+    for (int k = 0; k < site_row_count(r); ++k) {
+      const int dz = site_row_kind(r) == 0 ? 2 * (k - 1) : (site_row_kind(r) == 1 ? 0 : 2 * k - 1);
+      const Int3 o = g.site_offsets[site_row_pos(r) + k];
+      if (o.x != site_row_dx(r) || o.y != site_row_dy(r) || o.z != dz) throw std::logic_error("site row table does not match the 43-site list");
+    }
   if (device >= 0) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device >= count)
@@ -488,10 +494,25 @@ void Engine::eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a
   require_device();
   require_coefficients();
   if (n <= 0) return;
-  const unsigned blocks = static_cast<unsigned>((n + kSwapThreads - 1) / kSwapThreads);
+  const int64_t want = (n + kSwapThreads - 1) / kSwapThreads;
   time_begin();
-  swap_de_kernel<<<blocks, kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error,
-                                                      first_neighbours_only ? 1 : 0);
+  static const bool force_general = std::getenv("LMC_SWAP_GENERAL_KERNEL") != nullptr;   // A/B switch for tests and profiling
+  if (species.n + 1 <= kSwapMaxM && !force_general) {            // persistent blocks: the walk tables are staged in shared memory once per block
+    static const int occ_variant = std::getenv("LMC_SWAP_OCC") ? std::atoi(std::getenv("LMC_SWAP_OCC")) : 6;     // tuning switch (6 blocks/SM = 80 registers measured best)
+    const size_t smem = swap_rows_smem_bytes(species.n + 1);
+    const int per_sm = occ_variant;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(device_attr(cudaDevAttrMultiProcessorCount)) * per_sm * 3));
+    auto launch = [&](auto kernel) {
+      kernel<<<blocks, kSwapThreads, smem, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error, first_neighbours_only ? 1 : 0);
+    };
+    if (occ_variant >= 8) launch(swap_de_rows_kernel<8>);
+    else if (occ_variant >= 6) launch(swap_de_rows_kernel<6>);
+    else if (occ_variant == 5) launch(swap_de_rows_kernel<5>);
+    else launch(swap_de_rows_kernel<4>);
+  } else {
+    swap_de_kernel<<<static_cast<unsigned>(want), kSwapThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n, walker, a, b, dE, d_error,
+                                                                           first_neighbours_only ? 1 : 0);
+  }
   time_end();
   LMC_CUDA(cudaGetLastError());
 }

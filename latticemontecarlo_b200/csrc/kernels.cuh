@@ -346,7 +346,185 @@ __device__ __forceinline__ double swap_energy_change(const LatticeDesc &lat, con
   return de;
 }
 
+// ----------------------------------------------------------------------------------------------- row-based site gather
+// The 43-site neighbourhood in list order (GetSortedLatticeVectorStateOfSite: lexicographic in (dx, dy, dz)) is 21 rows
+// of constant (dx, dy), each 1-3 consecutive cells of the padded layout (z is the fast axis with the parity squeezed out):
+//   kind 0: dz = -2, 0, +2  -> cells cz-1, cz, cz+1          kind 1: dz = 0 -> cell cz
+//   kind 2: dz = -1, +1     -> cells cz-1, cz (Z even) or cz, cz+1 (Z odd)
+// so ONE load per row (an aligned 8-byte word; a second one only when the 1-3 bytes straddle it) replaces 43 byte loads,
+// and list positions are compile-time constants.  Species codes are kept as 4-bit nibbles in registers (the table walk
+// never goes back to memory), the solute mask is built from the same words.  The row table is verified against the host
+// geometry (site_delta) at engine creation.
+constexpr int kSiteRows = 21;
+__host__ __device__ constexpr int site_row_dx(int r) { return r < 3 ? -2 : (r < 8 ? -1 : (r < 13 ? 0 : (r < 18 ? 1 : 2))); }
+__host__ __device__ constexpr int site_row_dy(int r) { return r < 3 ? r - 1 : (r < 8 ? r - 5 : (r < 13 ? r - 10 : (r < 18 ? r - 15 : r - 19))); }
+__host__ __device__ constexpr int site_row_kind(int r) {
+  const int dx = site_row_dx(r), dy = site_row_dy(r);
+  if ((dx + dy) & 1) return 2;
+  return (dx == 2 || dx == -2 || dy == 2 || dy == -2) ? 1 : 0;
+}
+__host__ __device__ constexpr int site_row_count(int r) { return site_row_kind(r) == 0 ? 3 : (site_row_kind(r) == 1 ? 1 : 2); }
+__host__ __device__ constexpr int site_row_pos(int r) { return r == 0 ? 0 : site_row_pos(r - 1) + site_row_count(r - 1); }
+static_assert(site_row_pos(kSiteRows - 1) + site_row_count(kSiteRows - 1) == 43, "row table must cover the 43-site list");
+static_assert(site_row_pos(10) + 1 == kCentrePos, "centre row");
+
+struct SiteEnvRegs {
+  uint64_t n0, n1, n2; // species code of list position t in nibble t (16 positions per word)
+  uint64_t sol;        // bit e (env index, centre removed) set <=> species != solvent
+  __device__ __forceinline__ unsigned code_at_pos(int t) const {
+    const uint64_t w = t < 16 ? n0 : (t < 32 ? n1 : n2);
+    return static_cast<unsigned>(w >> ((t & 15) * 4)) & 0xFu;
+  }
+  __device__ __forceinline__ unsigned code_at_env(int e) const { return code_at_pos(e + (e >= kCentrePos)); }
+};
+
+// one row (template parameter => every table value is an immediate)
+template <int R>
+__device__ __forceinline__ void gather_site_row(const uint8_t *__restrict__ occ, int64_t base, int zp, int sy, int sx, uint32_t solvent4,
+                                                uint64_t &n0, uint64_t &n1, uint64_t &n2, uint32_t &sol_lo, uint32_t &sol_hi) {
+  constexpr int kind = site_row_kind(R), cnt = site_row_count(R), pos = site_row_pos(R), dx = site_row_dx(R), dy = site_row_dy(R);
+  const int64_t idx = base + dx * sx + dy * sy + (kind == 1 ? 0 : (kind == 0 ? -1 : zp - 1));
+  const uintptr_t addr = reinterpret_cast<uintptr_t>(occ + idx);
+  const uint64_t *p = reinterpret_cast<const uint64_t *>(addr & ~static_cast<uintptr_t>(7));
+  const unsigned b = static_cast<unsigned>(addr & 7u), sh = b * 8u;
+  uint32_t w = static_cast<uint32_t>(*p >> sh);
+  if (cnt > 1 && b + cnt > 8) w |= static_cast<uint32_t>(p[1] << (64u - sh));   // the row's bytes straddle the aligned word
+  uint32_t v = w & 0xFu;                                                        // codes as nibbles
+  if (cnt > 1) v |= (w >> 4) & 0xF0u;
+  if (cnt > 2) v |= (w >> 8) & 0xF00u;
+  constexpr int word = pos >> 4, shift = (pos & 15) * 4;
+  const uint64_t placed = static_cast<uint64_t>(v) << shift;
+  if (word == 0) n0 |= placed; else if (word == 1) n1 |= placed; else n2 |= placed;
+  if ((pos & 15) + cnt > 16) {
+    const uint64_t spill = static_cast<uint64_t>(v) >> (64 - shift);
+    if (word == 0) n1 |= spill; else n2 |= spill;
+  }
+  const uint32_t x = w ^ solvent4;                                              // solute bits
+#pragma unroll
+  for (int k = 0; k < cnt; ++k) {
+    const int t = pos + k;
+    const bool solute = (x & (0xFFu << (8 * k))) != 0;
+    if (t < 32) sol_lo |= solute ? (1u << t) : 0u;
+    else sol_hi |= solute ? (1u << (t - 32)) : 0u;
+  }
+}
+template <int... R>
+__device__ __forceinline__ void gather_site_rows_impl(const uint8_t *__restrict__ occ, int64_t base, int zp, int sy, int sx, uint32_t solvent4,
+                                                      uint64_t &n0, uint64_t &n1, uint64_t &n2, uint32_t &sol_lo, uint32_t &sol_hi) {
+  (gather_site_row<R>(occ, base, zp, sy, sx, solvent4, n0, n1, n2, sol_lo, sol_hi), ...);
+}
+
+__device__ __forceinline__ SiteEnvRegs gather_site_rows(const uint8_t *__restrict__ occ, int64_t base, int zp, int sy, int sx,
+                                                       unsigned solvent) {
+  SiteEnvRegs env;
+  env.n0 = env.n1 = env.n2 = 0;
+  uint32_t sol_lo = 0, sol_hi = 0;                          // over list positions t (centre included), split at 32
+  gather_site_rows_impl<0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20>(occ, base, zp, sy, sx, solvent * 0x01010101u, env.n0,
+                                                                                                  env.n1, env.n2, sol_lo, sol_hi);
+  const uint64_t sol_t = (static_cast<uint64_t>(sol_hi) << 32) | sol_lo;
+  env.sol = (sol_t & ((1ULL << kCentrePos) - 1ULL)) | ((sol_t >> (kCentrePos + 1)) << kCentrePos);
+  return env;
+}
+
+// H(x_new, env) - H(x_old, env) from registers: A / mask / base tables in shared memory, B through the read-only path
+struct SiteWalkTables {
+  const double *s_A;            // [m][42][m]
+  const uint64_t *s_mask_hi;    // [42]
+  const uint16_t *s_base;       // [42]
+  const double *B, *C;          // global
+  int m, n_pairs;
+};
+__device__ __forceinline__ double site_energy_change_regs(const SiteWalkTables &T, int x_old, int x_new, const SiteEnvRegs &env) {
+  const int m = T.m;
+  const int a_stride = kSiteEnvN * m;
+  const size_t b_stride = static_cast<size_t>(T.n_pairs) * m * m;
+  const double *A_new = T.s_A + x_new * a_stride, *A_old = T.s_A + x_old * a_stride;
+  const double *__restrict__ B_new = T.B + x_new * b_stride, *__restrict__ B_old = T.B + x_old * b_stride;
+  double acc = __ldg(T.C + x_new) - __ldg(T.C + x_old);
+  uint64_t sol = env.sol;
+  while (sol) {
+    const int t = __ffsll(static_cast<long long>(sol)) - 1;
+    sol &= sol - 1;
+    const int et = static_cast<int>(env.code_at_env(t));
+    acc += A_new[t * m + et] - A_old[t * m + et];
+    const uint64_t hi = T.s_mask_hi[t];
+    uint64_t partners = hi & sol;
+    if (partners) {
+      const int pbase = T.s_base[t];
+      do {
+        const int u = __ffsll(static_cast<long long>(partners)) - 1;
+        partners &= partners - 1;
+        const int eu = static_cast<int>(env.code_at_env(u));
+        const size_t p = (static_cast<size_t>(pbase + __popcll(hi & ((1ULL << u) - 1ULL))) * m + et) * m + eu;
+        acc += __ldg(B_new + p) - __ldg(B_old + p);
+      } while (partners);
+    }
+  }
+  return acc;
+}
+
 constexpr int kSwapThreads = 128;
+constexpr int kSwapMaxM = 8;     // species incl. vacancy (nibble codes < 16; the element set holds at most 7 species)
+inline size_t swap_rows_smem_bytes(int m) { return static_cast<size_t>(m) * kSiteEnvN * m * 8 + kSiteEnvN * 8 + 2 * 43 * 4 + kSiteEnvN * 2 + 16; }
+
+// Batched swap dE, one thread per pair, persistent blocks (grid-stride) so that the tables are staged once per block.
+// Uncoupled pairs take the row-based register path; the rare coupled pairs (b within the third shell of a, ~42/N of
+// random pairs) and bad ids take swap_energy_change() above.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kSwapThreads, kMinBlocks)
+swap_de_rows_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
+                    const int32_t *__restrict__ walker, const int64_t *__restrict__ site_a, const int64_t *__restrict__ site_b,
+                    double *__restrict__ dE, int *__restrict__ error, int first_neighbours_only) {
+  // dynamic shared memory sized for the actual species count (small footprint => the rest of the 256 KB stays L1)
+  extern __shared__ __align__(16) unsigned char swap_smem[];
+  const int m = tab.n_species + 1;
+  double *s_A = reinterpret_cast<double *>(swap_smem);                                   // [m][42][m]
+  uint64_t *s_mask_hi = reinterpret_cast<uint64_t *>(s_A + m * kSiteEnvN * m);           // [42]
+  int32_t *s_delta = reinterpret_cast<int32_t *>(s_mask_hi + kSiteEnvN);                 // [2][43]
+  uint16_t *s_base = reinterpret_cast<uint16_t *>(s_delta + 2 * 43);                     // [42]
+  for (int q = threadIdx.x; q < m * kSiteEnvN * m; q += blockDim.x) s_A[q] = tab.site_A[q];
+  for (int q = threadIdx.x; q < kSiteEnvN; q += blockDim.x) { s_mask_hi[q] = tab.site_mask_hi[q]; s_base[q] = tab.site_base[q]; }
+  for (int q = threadIdx.x; q < 2 * 43; q += blockDim.x) s_delta[q] = tab.site_delta[q];
+  __syncthreads();
+  const SiteWalkTables T{s_A, s_mask_hi, s_base, tab.site_B, tab.site_C, m, tab.n_site_pairs};
+  const unsigned solvent = static_cast<unsigned>(tab.solvent);
+  const int sy = lat.nz, sx = lat.ny * lat.nz;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t a = site_a[e], b = site_b[e];
+    if (a < 0 || a >= lat.num_sites || b < 0 || b >= lat.num_sites) {
+      atomicOr(error, kErrBadSite);
+      dE[e] = CUDART_NAN;
+      continue;
+    }
+    const uint8_t *o = occ + (walker ? walker[e] : 0) * walker_stride;
+    int xa, ya, za, xb, yb, zb;
+    lat.coords_of_id(a, xa, ya, za);
+    lat.coords_of_id(b, xb, yb, zb);
+    const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
+    const unsigned ea = o[base_a], eb = o[base_b];
+    double de = 0.0;
+    if (ea != eb) {
+      int dx = xb - xa, dy = yb - ya, dz = zb - za;
+      dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
+      dy = dy > py / 2 ? dy - py : (dy < -py / 2 ? dy + py : dy);
+      dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
+      const int r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 <= 6 || first_neighbours_only) {          // coupled (or the first-neighbour-only predictor): general path
+        int err = 0;
+        de = swap_energy_change(lat, tab, o, s_delta, xa, ya, za, xb, yb, zb, &err, first_neighbours_only != 0);
+        if (err) atomicOr(error, err);
+      } else {
+        const SiteEnvRegs env_a = gather_site_rows(o, base_a, za & 1, sy, sx, solvent);
+        de = site_energy_change_regs(T, static_cast<int>(ea), static_cast<int>(eb), env_a);
+        const SiteEnvRegs env_b = gather_site_rows(o, base_b, zb & 1, sy, sx, solvent);
+        de += site_energy_change_regs(T, static_cast<int>(eb), static_cast<int>(ea), env_b);
+        if (de != de) atomicOr(error, kErrExtraVacancy);
+      }
+    }
+    dE[e] = de;
+  }
+}
 
 __global__ void __launch_bounds__(kSwapThreads)
 swap_de_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,

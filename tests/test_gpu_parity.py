@@ -276,3 +276,45 @@ def test_vacancy_event_lists_match_per_event_evaluation(golden, coef_json, tmp_p
     assert np.max(np.abs(ea.reshape(-1) - ea2)) < 1e-12 and np.max(np.abs(de.reshape(-1) - de2)) < 1e-12
     with pytest.raises(capi.LmcOutOfRange):                                                   # not a vacancy there
         e.eval_vacancy_events([int((vac[0] + 1) % (4 * f ** 3))], walker=[0])
+
+
+def test_row_gather_swap_kernel_equals_general_kernel(coef_json, tmp_path):
+    """swap_de_rows_kernel (one aligned load per (dx, dy) row, codes in registers) against the byte-gather kernel it replaced
+    (LMC_SWAP_GENERAL_KERNEL=1 in a second process): 300k random pairs over 3 replicas of a concentrated 9x9x9 alloy with a
+    vacancy each (periodic wrap in every direction, coupled pairs, pairs that involve the vacancy), bit for bit, including
+    the status code and the NaN pattern of pairs the reference has no cluster type for."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "swap_ab.py"
+    script.write_text("""
+import ctypes as C, sys, numpy as np
+sys.path.insert(0, %r)
+from latticemontecarlo_b200 import capi, synth
+f = 9
+e = capi.Engine(f, id_order=capi.ORDER_GENERATE, n_walkers=3, device=0)
+e.load_coefficients(%r)
+occ = np.stack([synth.random_alloy(f, 0.15, 0.2, seed=s) for s in (1, 2, 3)])
+e.set_occupancy_all(occ)
+rng = np.random.default_rng(4)
+n = 300000
+w = rng.integers(0, 3, n).astype(np.int32)
+a = rng.integers(0, e.num_sites, n); b = rng.integers(0, e.num_sites, n)
+vac = np.array([int(np.nonzero(o == 0)[0][0]) for o in occ])
+a[:3000] = vac[w[:3000]]
+out = np.empty(n)
+rc = capi.lib().lmc_eval_swap_de(e.h, C.c_int64(n), capi._p(w), capi._p(a), capi._p(b), capi._p(out))
+np.save(sys.argv[1], np.concatenate([[rc], out]))
+""" % (root, coef_json))
+    outs = []
+    for k, env_extra in enumerate(({}, {"LMC_SWAP_GENERAL_KERNEL": "1"})):
+        out = tmp_path / ("swap_%d.npy" % k)
+        res = subprocess.run([sys.executable, str(script), str(out)], capture_output=True, text=True, env=dict(os.environ, **env_extra))
+        assert res.returncode == 0, res.stderr
+        outs.append(np.load(out))
+    rows, general = outs
+    assert rows[0] == general[0]
+    assert np.array_equal(np.isnan(rows), np.isnan(general))
+    ok = ~np.isnan(rows)
+    assert np.array_equal(rows[ok], general[ok]) and np.count_nonzero(rows[ok]) > 150000
