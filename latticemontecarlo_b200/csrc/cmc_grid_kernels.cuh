@@ -110,9 +110,132 @@ __device__ __forceinline__ void sa_update_batch(SaSchedule &sa, unsigned int n_k
   sa.temperature *= pow(cool, static_cast<double>(n_kept));
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Lane-GROUP evaluation of one swap trial.  The reference's non-interference rule (CanonicalMcOmp.cpp:47-72) caps a batch at
+// about N / 172 trials, so a 40^3 lattice keeps an SM busy with only ~7 kept trials per batch: with one lane per trial
+// side the evaluation is a single-warp latency chain whose length is set by the most solute-rich neighbourhood of the
+// whole batch.  Here a trial owns 2 L lanes (L per side): the 43 cell loads of a side are dealt round-robin to its L lanes,
+// the solute mask and the highest claim mark are combined with warp REDUX over the group, conflicting trials leave before
+// the table walk, and the walk is split by neighbour position (lane `sub` owns the solutes t with t mod L == sub and their
+// partner lists).  Partial sums meet in a fixed XOR tree, so the result depends on nothing but the trial itself.
+// Tables: s_pidx[t * 42 + u] (u > t) is the row of the (t, u) site pair in the B table (mask_hi / base folded into one byte).
+#ifdef LMC_CMC_PROFILE
+__device__ long long g_group_prof[4];     // thread 0 of CTA 0: cycles in {cell loads, mask / mark reduction, walk + tree}, calls
+#define LMC_GROUP_TICK(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long t_now = clock64(); g_group_prof[k] += t_now - t_prev; t_prev = t_now; } } while (0)
+#else
+#define LMC_GROUP_TICK(k) do { } while (0)
+#endif
+template <int L, bool kStagedB>
+__device__ __forceinline__ double swap_energy_change_group(const LatticeDesc &lat, const DevTables &tab, const double *s_C, const double *s_A,
+                                                           const double *Bt, const uint64_t *s_mask, const uint8_t *s_pidx,
+                                                           const unsigned int *cells, const int32_t *__restrict__ s_delta, uint8_t *row,
+                                                           int side, int sub, unsigned trial_mask, unsigned side_mask, int xa, int ya, int za,
+                                                           int xb, int yb, int zb, unsigned my_mark, bool *conflict) {
+#ifdef LMC_CMC_PROFILE
+  long long t_prev = clock64();
+#endif
+  const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
+  int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
+  unsigned ea = cells[base_a] & kCellSpeciesMask, eb = cells[base_b] & kCellSpeciesMask;
+  int dx = xb - xa, dy = yb - ya, dz = zb - za;
+  const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
+  dx = dx > px / 2 ? dx - px : (dx < -px / 2 ? dx + px : dx);
+  dy = dy > py / 2 ? dy - py : (dy < -py / 2 ? dy + py : dy);
+  dz = dz > pz / 2 ? dz - pz : (dz < -pz / 2 ? dz + pz : dz);
+  const bool coupled = dx * dx + dy * dy + dz * dz <= 6;
+  int zpa = za & 1, zpb = zb & 1;
+  if (coupled && eb == vac) {   // move the vacancy first so that no intermediate state holds two vacancies (swap_energy_change)
+    const int64_t tb = base_a; base_a = base_b; base_b = tb;
+    const unsigned te = ea; ea = eb; eb = te;
+    const int tz = zpa; zpa = zpb; zpb = tz;
+    dx = -dx; dy = -dy; dz = -dz;
+  }
+  const int64_t base = side ? base_b : base_a;
+  const int32_t *drow = s_delta + (side ? zpb : zpa) * 43;
+  // side 1 of a coupled pair sees the first site already changed (its halo images are not updated: override by position)
+  const int64_t override_index = (side && coupled) ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
+  constexpr int kPerLane = (43 + L - 1) / L;
+  unsigned cell[kPerLane];
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    const int t = sub + i * L;
+    cell[i] = t < 43 ? cells[base + drow[t]] : 0u;            // plain loads (L1 was invalidated by the barrier's acquire)
+  }
+  unsigned worst = 0, lo = 0, hi = 0;
+#pragma unroll
+  for (int i = 0; i < kPerLane; ++i) {
+    const int t = sub + i * L;
+    if (t < 43 && t != kCentrePos) {
+      const unsigned mk = cell[i] >> 8;
+      worst = mk > worst ? mk : worst;
+      unsigned c = cell[i] & kCellSpeciesMask;
+      if (base + drow[t] == override_index) c = eb;
+      const int e = t - (t > kCentrePos);
+      row[e] = static_cast<uint8_t>(c);
+      const unsigned bit = (c != solvent) ? 1u : 0u;
+      if (e < 32) lo |= bit << e; else hi |= bit << (e - 32);
+    } else if (t == kCentrePos) {
+      const unsigned mk = cell[i] >> 8;
+      worst = mk > worst ? mk : worst;
+    }
+  }
+  LMC_GROUP_TICK(0);
+  // marks of older epochs are numerically smaller than any mark of the current epoch
+  worst = __reduce_max_sync(trial_mask, worst);
+  if (L > 1) {
+    __syncwarp(side_mask);                                  // row[] is complete for every lane of the side
+    lo = __reduce_or_sync(side_mask, lo);
+    hi = __reduce_or_sync(side_mask, hi);
+  }
+  LMC_GROUP_TICK(1);
+  if (worst > my_mark) { *conflict = true; return 0.0; }
+  if (ea == eb) return 0.0;
+  const int m = tab.n_species + 1, mm = m * m;
+  const int x_old = static_cast<int>(side ? eb : ea), x_new = static_cast<int>(side ? ea : eb);
+  const int a_stride = kSiteEnvN * m, b_stride = tab.n_site_pairs * mm;
+  const double *A_new = s_A + x_new * a_stride, *A_old = s_A + x_old * a_stride;
+  const double *B_new = Bt + static_cast<size_t>(x_new) * b_stride, *B_old = Bt + static_cast<size_t>(x_old) * b_stride;
+  double acc = sub == 0 ? s_C[x_new] - s_C[x_old] : 0.0;
+  constexpr unsigned kStripe = L >= 32 ? 1u : 0xFFFFFFFFu / ((1u << (L % 32)) - 1u);   // bits 0, L, 2L, ...
+  auto walk = [&](unsigned mine, int t0) {
+    while (mine) {
+      const int t = t0 + __ffs(static_cast<int>(mine)) - 1;
+      mine &= mine - 1;
+      const int et = row[t];
+      acc += A_new[t * m + et] - A_old[t * m + et];
+      const uint64_t mask = s_mask[t];
+      unsigned plo = static_cast<unsigned>(mask) & lo, phi = static_cast<unsigned>(mask >> 32) & hi;
+      const uint8_t *prow = s_pidx + t * kSiteEnvN;
+      const int col = et * m;
+      while (plo) {
+        const int u = __ffs(static_cast<int>(plo)) - 1;
+        plo &= plo - 1;
+        const int p = prow[u] * mm + col + row[u];
+        acc += kStagedB ? B_new[p] - B_old[p] : __ldg(B_new + p) - __ldg(B_old + p);
+      }
+      while (phi) {
+        const int u = 32 + __ffs(static_cast<int>(phi)) - 1;
+        phi &= phi - 1;
+        const int p = prow[u] * mm + col + row[u];
+        acc += kStagedB ? B_new[p] - B_old[p] : __ldg(B_new + p) - __ldg(B_old + p);
+      }
+    }
+  };
+  walk(lo & (kStripe << sub), 0);
+  walk(hi & (kStripe << sub), 32);          // 32 is a multiple of L: the stripe continues unbroken
+#pragma unroll
+  for (int off = L / 2; off > 0; off >>= 1) acc += __shfl_xor_sync(trial_mask, acc, off);
+  LMC_GROUP_TICK(2);
+#ifdef LMC_CMC_PROFILE
+  if (blockIdx.x == 0 && threadIdx.x == 0) g_group_prof[3] += 1;
+#endif
+  return acc;
+}
+
+template <int L, bool kStagedB>
 __global__ void __launch_bounds__(kCmcMaxThreads)
 cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsigned int *cells, CmcState st, const double *__restrict__ temperatures,
-                uint64_t seed, unsigned long long target_steps, CmcGridParams gp, int stage_b_table) {
+                uint64_t seed, unsigned long long target_steps, CmcGridParams gp) {
   const int n_cta = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   __shared__ int32_t s_delta[2 * 43];
   __shared__ long long s_warp_fixed[kGridMaxWarps];
@@ -124,10 +247,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   __shared__ int s_flag_ok;
   __shared__ long long s_part_e[kGridMaxWorld];
   __shared__ unsigned int s_part_k[kGridMaxWorld], s_part_a[kGridMaxWorld];
-  extern __shared__ double s_dyn[];                // [C: m] [A: m*42*m] [B: m*204*m*m, optional] [mask: 42] [base] [codes]
+  extern __shared__ double s_dyn[];                // [C: m] [A: m*42*m] [B: m*204*m*m, optional] [mask: 42] [base] [pidx: 42*42] [codes]
 
   const int tid = threadIdx.x, B = blockDim.x;
   const int warp = tid >> 5, n_warps = B >> 5;
+  const int stage_b_table = kStagedB ? 1 : 0;
   for (int q = tid; q < 2 * 43; q += B) s_delta[q] = tab.site_delta[q];
   const int m = tab.n_species + 1;
   double *s_C = s_dyn;
@@ -136,12 +260,18 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   double *s_B = s_A + a_len;
   uint64_t *s_mask = reinterpret_cast<uint64_t *>(s_B + (stage_b_table ? b_len : 0));
   uint16_t *s_base = reinterpret_cast<uint16_t *>(s_mask + kSiteEnvN);
-  uint8_t *s_codes = reinterpret_cast<uint8_t *>(s_base + 44);
+  uint8_t *s_pidx = reinterpret_cast<uint8_t *>(s_base + 44);            // [42][42]: B-table row of the site pair (t, u), u > t
+  uint8_t *s_codes = s_pidx + kSiteEnvN * kSiteEnvN + 4;                  // L == 1: one column per thread; L > 1: one 48-byte row per trial side
   for (int q = tid; q < m; q += B) s_C[q] = tab.site_C[q];
   for (int q = tid; q < a_len; q += B) s_A[q] = tab.site_A[q];
   if (stage_b_table)
     for (int q = tid; q < b_len; q += B) s_B[q] = tab.site_B[q];
   for (int q = tid; q < kSiteEnvN; q += B) { s_mask[q] = tab.site_mask_hi[q]; s_base[q] = tab.site_base[q]; }
+  for (int q = tid; q < kSiteEnvN * kSiteEnvN; q += B) {
+    const int t = q / kSiteEnvN, u = q % kSiteEnvN;
+    const uint64_t hi = tab.site_mask_hi[t];
+    s_pidx[q] = static_cast<uint8_t>(tab.site_base[t] + __popcll(hi & ((1ULL << u) - 1ULL)));   // meaningful where bit u of hi is set
+  }
   const SiteTablesView tv{s_A, stage_b_table ? s_B : tab.site_B, s_C, s_mask, s_base, m, tab.n_site_pairs};
   if (tid == 0) {
     s_energy = st.energy[0]; s_steps = st.steps[0]; s_accepted = st.accepted[0]; s_proposals = st.proposals[0];
@@ -152,9 +282,15 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   const uint32_t n_sites = static_cast<uint32_t>(lat.num_sites);
   const double cool = s_sa.enabled ? exp(-3.0 / static_cast<double>(s_sa.maximum_steps > 0 ? s_sa.maximum_steps : 1ULL)) : 1.0;
   const int gtid = cta * B + tid;
-  const int window = B * n_cta;                    // proposals (threads) per batch
-  const int half = B / 2;
-  const int pair_id = tid >> 1, side = tid & 1;
+  constexpr int G = 2 * L;                         // lanes per trial (L per side)
+  const int half = B / G;                          // trials a CTA can evaluate per batch
+  const int n_prop = 2 * half;                     // proposing threads per CTA: twice the capacity (about half survive the draw / claim)
+  const int gprop = cta * n_prop + tid;
+  const int window = n_prop * n_cta;               // proposals per batch
+  const int pair_id = tid / G, side = (tid / L) & 1, sub = tid % L;
+  const unsigned trial_mask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((tid & 31) / G * G);
+  const unsigned side_mask = ((1u << L) - 1u) << ((tid & 31) / L * L);
+  constexpr unsigned kLeaders = G >= 32 ? 1u : 0xFFFFFFFFu / ((1u << (G % 32)) - 1u);      // lane 0 of every trial of a warp
   const int world = gp.world, rank = gp.rank;
   CmcExchange *mine = gp.xchg[rank];
   unsigned long long bar_target = 0;
@@ -178,19 +314,19 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     if (steps0 >= target_steps) break;
     __syncthreads();
     if ((epoch & 0xFFULL) == 0) {                   // 8-bit epoch wrapped: forget all marks (keep the species bytes)
-      for (int64_t q = gtid; q < lat.padded_size; q += window) cells[q] &= kCellSpeciesMask;
+      for (int64_t q = gtid; q < lat.padded_size; q += static_cast<int64_t>(B) * n_cta) cells[q] &= kCellSpeciesMask;
       if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     }
     const unsigned int epoch8 = static_cast<unsigned int>(epoch & 0xFFULL);
     // ---------------- proposals: identical on every rank (same counters), first unlike-species pair of 8 draws
     int32_t a = -1, b = -1;
-    {
+    if (tid < n_prop) {
       uint32_t ida[kCmcDraws], idb[kCmcDraws];
       uint8_t sa_[kCmcDraws], sb_[kCmcDraws];
 #pragma unroll
       for (int d = 0; d < kCmcDraws; d += 2) {
         uint32_t r[4];
-        const unsigned long long g = (prop0 + gtid) * (kCmcDraws / 2) + (d >> 1);
+        const unsigned long long g = (prop0 + gprop) * (kCmcDraws / 2) + (d >> 1);
         philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
         ida[d] = __umulhi(r[0], n_sites); idb[d] = __umulhi(r[1], n_sites);
         ida[d + 1] = __umulhi(r[2], n_sites); idb[d + 1] = __umulhi(r[3], n_sites);
@@ -232,9 +368,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
       a = s_live_a[pair_id]; b = s_live_b[pair_id];
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
-      const int mx = side ? xb : xa, my = side ? yb : ya, mz = side ? zb : za;
-      const unsigned species = cells[lat.padded_index(mx, my, mz)] & kCellSpeciesMask;
-      mark_site(lat, cells, mx, my, mz, (my_mark << 8) | species);
+      if (sub == 0) {
+        const int mx = side ? xb : xa, my = side ? yb : ya, mz = side ? zb : za;
+        const unsigned species = cells[lat.padded_index(mx, my, mz)] & kCellSpeciesMask;
+        mark_site(lat, cells, mx, my, mz, (my_mark << 8) | species);
+      }
     }
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     LMC_GTICK(2);
@@ -245,13 +383,19 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
 #ifdef LMC_CMC_PROFILE
     const long long te0 = clock64();
 #endif
-    if (live && owner) de = swap_side_energy_change_marked(lat, tab, tv, cells, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark,
-                                                           &conflict, &same);
+    if (live && owner) {
+      if constexpr (L == 1)
+        de = swap_side_energy_change_marked(lat, tab, tv, cells, s_delta, s_codes + tid, B, side, xa, ya, za, xb, yb, zb, my_mark, &conflict, &same);
+      else
+        de = swap_energy_change_group<L, kStagedB>(lat, tab, s_C, s_A, kStagedB ? s_B : tab.site_B, s_mask, s_pidx, cells, s_delta,
+                                                   s_codes + (tid / L) * 48, side, sub, trial_mask, side_mask, xa, ya, za, xb, yb, zb, my_mark,
+                                                   &conflict);
+    }
 #ifdef LMC_CMC_PROFILE
     const long long te1 = clock64();
 #endif
-    conflict = __shfl_xor_sync(0xffffffffu, conflict ? 1 : 0, 1) || conflict;
-    de += __shfl_xor_sync(0xffffffffu, de, 1);
+    conflict = __shfl_xor_sync(0xffffffffu, conflict ? 1 : 0, L) || conflict;     // the other side of the trial
+    de += __shfl_xor_sync(0xffffffffu, de, L);
     bool kept = live && owner && !conflict;
     if (kept && de != de) err |= kErrExtraVacancy;
     bool accept = false;
@@ -268,14 +412,14 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     }
     unsigned kept_mask = __ballot_sync(0xffffffffu, kept), acc_mask = __ballot_sync(0xffffffffu, accept);
     {
-      double sum = (accept && side == 0) ? de : 0.0;
+      double sum = (accept && (tid % G) == 0) ? de : 0.0;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xffffffffu, sum, off);
       if ((tid & 31) == 0) {
         s_warp_fixed[warp] = __double2ll_rn(sum * kEnergyFixedScale);   // rounded per warp group = per unit of ownership:
                                                                         // the integer total is the same for every world size
-        s_warp_cnt[warp] = __popc(kept_mask & 0x55555555u);      // one lane per pair
-        s_warp_acc[warp] = __popc(acc_mask & 0x55555555u);
+        s_warp_cnt[warp] = __popc(kept_mask & kLeaders);         // one lane per trial
+        s_warp_acc[warp] = __popc(acc_mask & kLeaders);
       }
       // the owner warp publishes its group's masks in every peer's buffer right away (lane d -> rank d)
       if (world > 1 && owner && (tid & 31) < world && (tid & 31) != rank)
@@ -341,7 +485,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     }
     LMC_GTICK(4);
     // ---------------- apply every accepted swap of this CTA's trials (all ranks alike)
-    if (live && ((acc_mask >> (tid & 31)) & 1u)) {
+    if (live && sub == 0 && ((acc_mask >> (tid & 31)) & 1u)) {
       const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
       const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
       __syncwarp(__activemask());                   // both lanes have read the old species before either writes
@@ -385,6 +529,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     if (any_err) { err |= kErrExtraVacancy; break; }
   }
 #ifdef LMC_CMC_PROFILE
+  if (tid == 0 && cta == 0) {
+    printf("group profile thread 0 (cycles/batch): cell loads %lld reductions %lld walk+tree %lld (walked %lld of %llu batches)\n", g_group_prof[0] / (long long)max(1ULL, n_batches),
+           g_group_prof[1] / (long long)max(1ULL, n_batches), g_group_prof[2] / (long long)max(1LL, g_group_prof[3]), g_group_prof[3], n_batches);
+    g_group_prof[0] = g_group_prof[1] = g_group_prof[2] = g_group_prof[3] = 0;
+  }
   if (tid == 0 && cta == 0)
     printf("grid cmc profile rank %d (cycles/batch): propose %lld compact %lld mark+barrier %lld evaluate %lld exchange %lld apply+barrier %lld reduce %lld | "
            "thread0: dE call %lld accept+reduce %lld | reduce parts: loads %lld shuffles %lld update %lld | batches %llu ctas %d threads %d\n", rank, s_gprof[0] / (long long)max(1ULL, n_batches), s_gprof[1] / (long long)max(1ULL, n_batches),

@@ -843,29 +843,51 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   sms = device_attr(cudaDevAttrMultiProcessorCount);
   int ctas = std::min(sms, kGridMaxCtas);
   if (cmc_grid_ctas > 0) ctas = std::min(ctas, cmc_grid_ctas);
-  // threads per CTA: a trial is one lane pair; about N / 172 trials of a batch can be mutually non-interfering
-  int threads = params.batch_size;
-  if (threads <= 0) {
+  // proposals per CTA and batch (= 2 x the trials a CTA evaluates): about N / 172 trials of a batch can be mutually
+  // non-interfering.  A trial is evaluated by 2 L lanes; small lattices, whose batches leave the SMs almost empty, get
+  // wide groups (L = 8 at 40^3: 32 trials x 16 lanes per CTA)
+  int proposals = params.batch_size;
+  if (proposals <= 0) {
     const int64_t want_pairs = std::max<int64_t>(16, lat.num_sites / 172);
-    threads = 64;
-    while (threads < kCmcMaxThreads && static_cast<int64_t>(threads) / 2 * ctas < want_pairs) threads *= 2;
+    proposals = 64;
+    while (proposals < kCmcMaxThreads / 2 && static_cast<int64_t>(proposals) / 2 * ctas < want_pairs) proposals *= 2;   // <= 256: at least 2 lanes per side
   }
-  if (threads < 32 || threads > kCmcMaxThreads || (threads & (threads - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
-  if (static_cast<int64_t>(ctas) * (threads / 2) > 65535) throw std::invalid_argument("batch too large for 16-bit claim priorities");
+  if (proposals < 32 || proposals > kCmcMaxThreads || (proposals & (proposals - 1))) throw std::invalid_argument("batch_size must be a power of two in 32..512");
+  if (static_cast<int64_t>(ctas) * (proposals / 2) > 65535) throw std::invalid_argument("batch too large for 16-bit claim priorities");
+  int lanes = 8;
+  if (const char *v = std::getenv("LMC_CMC_GRID_LANES")) lanes = std::max(1, std::atoi(v));   // tuning knob: lanes per trial side
+  while (lanes > 1 && proposals * lanes > kCmcMaxThreads) lanes /= 2;
+  if (lanes != 1 && lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16) throw std::invalid_argument("lanes per trial side must be 1, 2, 4, 8 or 16");
+  const int threads = proposals * lanes;            // (proposals / 2) trials x 2 sides x L lanes
   const int m = species.n + 1;
   const size_t a_len = static_cast<size_t>(m) * kSiteEnvN * m, b_len = static_cast<size_t>(m) * tab.n_site_pairs * m * m;
-  const size_t fixed = (m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + static_cast<size_t>(threads) * 86 + 16;
+  const size_t fixed = (m + a_len) * 8 + kSiteEnvN * 8 + 44 * 2 + kSiteEnvN * kSiteEnvN + 4 + static_cast<size_t>(threads) * 43 + 64;
   int max_optin = 0;
   max_optin = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin);
   const int stage_b = (fixed + b_len * 8 + 24 * 1024 <= static_cast<size_t>(max_optin)) ? 1 : 0;
   const size_t smem = fixed + (stage_b ? b_len * 8 : 0);
-  LMC_CUDA(cudaFuncSetAttribute(cmc_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  if (cmc_grid_checked_threads != threads || cmc_grid_checked_smem != smem) {     // once per launch shape
+  using GridKernel = void (*)(LatticeDesc, DevTables, uint8_t *, uint8_t *, unsigned int *, CmcState, const double *, uint64_t, unsigned long long, CmcGridParams);
+  GridKernel kernel = nullptr;
+  switch (lanes * 2 + stage_b) {
+    case 2: kernel = cmc_grid_kernel<1, false>; break;
+    case 3: kernel = cmc_grid_kernel<1, true>; break;
+    case 4: kernel = cmc_grid_kernel<2, false>; break;
+    case 5: kernel = cmc_grid_kernel<2, true>; break;
+    case 8: kernel = cmc_grid_kernel<4, false>; break;
+    case 9: kernel = cmc_grid_kernel<4, true>; break;
+    case 16: kernel = cmc_grid_kernel<8, false>; break;
+    case 17: kernel = cmc_grid_kernel<8, true>; break;
+    case 32: kernel = cmc_grid_kernel<16, false>; break;
+    default: kernel = cmc_grid_kernel<16, true>; break;
+  }
+  if (cmc_grid_checked_threads != threads || cmc_grid_checked_smem != smem || cmc_grid_checked_kernel != reinterpret_cast<const void *>(kernel)) {     // once per launch shape
+    LMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int per_sm = 0;
-    LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cmc_grid_kernel, threads, smem));
+    LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     if (per_sm < 1) throw std::runtime_error("cmc_grid_kernel does not fit on an SM");
     cmc_grid_checked_threads = threads;
     cmc_grid_checked_smem = smem;
+    cmc_grid_checked_kernel = reinterpret_cast<const void *>(kernel);
   }
   CmcGridParams gp{};
   gp.world = cmc_world;
@@ -895,8 +917,8 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   cfg.numAttrs = 1;
   tick("setup");
   time_begin();
-  LMC_CUDA(cudaLaunchKernelEx(&cfg, cmc_grid_kernel, lat, tab, d_occ, d_cmc_mirror, d_cmc_marks, st, static_cast<const double *>(d_cmc_temperature),
-                              static_cast<uint64_t>(params.seed), target, gp, stage_b));
+  LMC_CUDA(cudaLaunchKernelEx(&cfg, kernel, lat, tab, d_occ, d_cmc_mirror, d_cmc_marks, st, static_cast<const double *>(d_cmc_temperature),
+                              static_cast<uint64_t>(params.seed), target, gp));
   time_end();
   tick("launch");
   LMC_CUDA(cudaGetLastError());

@@ -124,6 +124,7 @@ class Engine {
   int cmc_world{1}, cmc_rank{0}, cmc_grid_ctas{0};
   int cmc_grid_checked_threads{0};
   size_t cmc_grid_checked_smem{0};
+  const void *cmc_grid_checked_kernel{nullptr};
   std::map<int, int> attr_cache;
   int device_attr(int attr);
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches
