@@ -244,6 +244,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   __shared__ unsigned long long s_steps, s_accepted, s_proposals, s_epoch, s_sequence;
   __shared__ SaSchedule s_sa;
   __shared__ int32_t s_live_a[kCmcMaxThreads], s_live_b[kCmcMaxThreads];
+  __shared__ uint16_t s_live_sp[kCmcMaxThreads];   // species of the two sites at batch start (a | b << 8), from the proposal's mirror reads
   __shared__ int s_flag_ok;
   __shared__ long long s_part_e[kGridMaxWorld];
   __shared__ unsigned int s_part_k[kGridMaxWorld], s_part_a[kGridMaxWorld];
@@ -284,8 +285,12 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   const int gtid = cta * B + tid;
   constexpr int G = 2 * L;                         // lanes per trial (L per side)
   const int half = B / G;                          // trials a CTA can evaluate per batch
-  const int n_prop = 2 * half;                     // proposing threads per CTA: twice the capacity (about half survive the draw / claim)
-  const int gprop = cta * n_prop + tid;
+  const int n_prop = 2 * half;                     // proposals per CTA and batch: twice the capacity (about half survive the draw / claim)
+  constexpr int S = L >= 4 ? 4 : L;                // lanes that share the kCmcDraws draws of one proposal (n_prop * S <= B)
+  constexpr int kMyDraws = kCmcDraws / S;          // consecutive draws of this lane (one Philox call yields two draws)
+  const int prop_id = tid / S, prop_lane = tid % S;
+  const bool proposer = prop_id < n_prop;
+  const int gprop = cta * n_prop + prop_id;
   const int window = n_prop * n_cta;               // proposals per batch
   const int pair_id = tid / G, side = (tid / L) & 1, sub = tid % L;
   const unsigned trial_mask = (G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << ((tid & 31) / G * G);
@@ -296,6 +301,22 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
   unsigned long long bar_target = 0;
   int err = 0;
   bool healthy = true;
+  // lattice ids of this lane's draws of the coming batch (state-independent: drawn while the previous batch's barrier is pending)
+  uint32_t ida[kMyDraws], idb[kMyDraws];
+  auto draw_ids = [&](unsigned long long prop_base) {
+    if (!proposer) return;
+#pragma unroll
+    for (int d = 0; d < kMyDraws; d += 2) {
+      uint32_t r[4];
+      const unsigned long long g = (prop_base + gprop) * (kCmcDraws / 2) + ((prop_lane * kMyDraws + d) >> 1);
+      philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+      ida[d] = __umulhi(r[0], n_sites); idb[d] = __umulhi(r[1], n_sites);
+      ida[d + 1] = __umulhi(r[2], n_sites); idb[d + 1] = __umulhi(r[3], n_sites);
+    }
+  };
+#pragma unroll
+  for (int d = 0; d < kMyDraws; ++d) { ida[d] = 0; idb[d] = 0; }
+  draw_ids(s_proposals);
 #ifdef LMC_CMC_PROFILE
   __shared__ long long s_gprof[8], s_eprof, s_rprof[3];
   if (tid == 0) { for (int q = 0; q < 8; ++q) s_gprof[q] = 0; s_eprof = 0; s_rprof[0] = s_rprof[1] = s_rprof[2] = 0; }
@@ -318,24 +339,29 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
       if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     }
     const unsigned int epoch8 = static_cast<unsigned int>(epoch & 0xFFULL);
-    // ---------------- proposals: identical on every rank (same counters), first unlike-species pair of 8 draws
+    // ---------------- proposals: identical on every rank (same counters), first unlike-species pair of 8 draws.  The lattice
+    // ids of this batch were drawn (Philox) before the previous batch's closing barrier; S lanes share a proposal.
     int32_t a = -1, b = -1;
-    if (tid < n_prop) {
-      uint32_t ida[kCmcDraws], idb[kCmcDraws];
-      uint8_t sa_[kCmcDraws], sb_[kCmcDraws];
+    unsigned sp = 0;
+    {
+      uint8_t sa_[kMyDraws], sb_[kMyDraws];
 #pragma unroll
-      for (int d = 0; d < kCmcDraws; d += 2) {
-        uint32_t r[4];
-        const unsigned long long g = (prop0 + gprop) * (kCmcDraws / 2) + (d >> 1);
-        philox4x32_10(static_cast<uint32_t>(g), static_cast<uint32_t>(g >> 32), static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
-        ida[d] = __umulhi(r[0], n_sites); idb[d] = __umulhi(r[1], n_sites);
-        ida[d + 1] = __umulhi(r[2], n_sites); idb[d + 1] = __umulhi(r[3], n_sites);
+      for (int d = 0; d < kMyDraws; ++d) {
+        sa_[d] = proposer ? __ldcg(by_id + ida[d]) : 0;
+        sb_[d] = proposer ? __ldcg(by_id + idb[d]) : 0;
       }
+      int first = kCmcDraws;                        // index (over the proposal's 8 draws) of this lane's first unlike pair
 #pragma unroll
-      for (int d = 0; d < kCmcDraws; ++d) { sa_[d] = __ldcg(by_id + ida[d]); sb_[d] = __ldcg(by_id + idb[d]); }
+      for (int d = kMyDraws - 1; d >= 0; --d)
+        if (proposer && sa_[d] != sb_[d]) { first = prop_lane * kMyDraws + d; a = static_cast<int32_t>(ida[d]); b = static_cast<int32_t>(idb[d]); sp = sa_[d] | (sb_[d] << 8); }
+      int best = first;
 #pragma unroll
-      for (int d = kCmcDraws - 1; d >= 0; --d)
-        if (sa_[d] != sb_[d]) { a = static_cast<int32_t>(ida[d]); b = static_cast<int32_t>(idb[d]); }
+      for (int off = S / 2; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, off));
+      const int src = ((tid & 31) / S) * S + (best < kCmcDraws ? best / kMyDraws : 0);
+      a = __shfl_sync(0xffffffffu, a, src);
+      b = __shfl_sync(0xffffffffu, b, src);
+      sp = __shfl_sync(0xffffffffu, sp, src);
+      if (best >= kCmcDraws || prop_lane != 0) a = -1;         // one lane per proposal enters the compaction
     }
     LMC_GTICK(0);
     // ---------------- compaction of this CTA's live trials
@@ -354,6 +380,7 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
         const int slot = my_off + __popc(bal & ((1u << (tid & 31)) - 1u));
         s_live_a[slot] = a;
         s_live_b[slot] = b;
+        s_live_sp[slot] = static_cast<uint16_t>(sp);
       }
     }
     __syncthreads();
@@ -366,12 +393,12 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     const unsigned int my_mark = (epoch8 << 16) | (0xFFFFu - gpair);      // 24 bits
     if (live) {
       a = s_live_a[pair_id]; b = s_live_b[pair_id];
+      sp = s_live_sp[pair_id];
       lat.coords_of_id(a, xa, ya, za);
       lat.coords_of_id(b, xb, yb, zb);
       if (sub == 0) {
         const int mx = side ? xb : xa, my = side ? yb : ya, mz = side ? zb : za;
-        const unsigned species = cells[lat.padded_index(mx, my, mz)] & kCellSpeciesMask;
-        mark_site(lat, cells, mx, my, mz, (my_mark << 8) | species);
+        mark_site(lat, cells, mx, my, mz, (my_mark << 8) | (side ? sp >> 8 : sp & 0xFFu));
       }
     }
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
@@ -431,12 +458,18 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
 #endif
     const int block_err = __syncthreads_or(err != 0);
     LMC_GTICK(3);
-    if (tid < world) {
-      // this CTA's partial sums (own warps only; fixed order).  Thread d ships them to rank d as two lines.
-      long long e = 0;
-      unsigned int n_kept = 0, n_acc = 0;
-      for (int q = 0; q < n_warps; ++q) { e += s_warp_fixed[q]; n_kept += s_warp_cnt[q]; n_acc += s_warp_acc[q]; }
-      if (tid == rank) { s_part_e[rank] = e; s_part_k[rank] = n_kept; s_part_a[rank] = n_acc | (block_err ? 0x80000000u : 0u); }
+    if (warp == 0) {
+      // this CTA's partial sums (own warps only; integer adds: any order).  Thread d ships them to rank d as two lines.
+      long long e = tid < n_warps ? s_warp_fixed[tid] : 0LL;
+      unsigned int n_kept = tid < n_warps ? s_warp_cnt[tid] : 0u, n_acc = tid < n_warps ? s_warp_acc[tid] : 0u;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, off);
+        n_kept += __shfl_xor_sync(0xffffffffu, n_kept, off);
+        n_acc += __shfl_xor_sync(0xffffffffu, n_acc, off);
+      }
+      if (tid >= world) { }
+      else if (tid == rank) { s_part_e[rank] = e; s_part_k[rank] = n_kept; s_part_a[rank] = n_acc | (block_err ? 0x80000000u : 0u); }
       else {
         CmcLine *dst = gp.xchg[tid]->partials[parity][rank][cta];
         const unsigned long long bits = static_cast<unsigned long long>(e);
@@ -486,12 +519,11 @@ cmc_grid_kernel(LatticeDesc lat, DevTables tab, uint8_t *o, uint8_t *by_id, unsi
     LMC_GTICK(4);
     // ---------------- apply every accepted swap of this CTA's trials (all ranks alike)
     if (live && sub == 0 && ((acc_mask >> (tid & 31)) & 1u)) {
-      const int64_t base_a = lat.padded_index(xa, ya, za), base_b = lat.padded_index(xb, yb, zb);
-      const uint8_t ea = __ldcg(o + base_a), eb = __ldcg(o + base_b);
-      __syncwarp(__activemask());                   // both lanes have read the old species before either writes
+      const uint8_t ea = static_cast<uint8_t>(sp & 0xFFu), eb = static_cast<uint8_t>(sp >> 8);   // no kept trial of the batch touched them
       if (side == 0) { store_site(lat, o, xa, ya, za, eb); store_site_cells(lat, cells, xa, ya, za, eb); by_id[a] = eb; }
       else { store_site(lat, o, xb, yb, zb, ea); store_site_cells(lat, cells, xb, yb, zb, ea); by_id[b] = ea; }
     }
+    draw_ids(prop0 + window);                       // the next batch's ids: hidden behind the barrier
     if (!grid_barrier(gp, bar_target, n_cta)) { healthy = false; break; }
     LMC_GTICK(5);
     // ---------------- totals: one 32-byte read per CTA (the accumulators are complete after the grid barrier)
