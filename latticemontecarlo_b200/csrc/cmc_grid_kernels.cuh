@@ -76,15 +76,18 @@ __device__ __forceinline__ bool grid_barrier(const CmcGridParams &gp, unsigned l
   target += n_cta;
   __shared__ int s_ok;
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(gp.barrier_counter, 1ULL);
+    // arrive with release semantics (cumulative over the CTA's writes through the bar.sync above), wait with acquire loads:
+    // one fence less on each side than __threadfence + atomicAdd + volatile spin + __threadfence
+    asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(gp.barrier_counter) : "memory");
     const long long t0 = clock64();
     int ok = 1;
-    while (*reinterpret_cast<volatile unsigned long long *>(gp.barrier_counter) < target) {
+    for (;;) {
+      unsigned long long seen;
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(gp.barrier_counter) : "memory");
+      if (seen >= target) break;
       if (*reinterpret_cast<volatile int *>(gp.abort_flag)) { ok = 0; break; }
       if (clock64() - t0 > gp.spin_limit) { *reinterpret_cast<volatile int *>(gp.abort_flag) = 1; ok = 0; break; }
     }
-    __threadfence();
     s_ok = ok;
   }
   __syncthreads();
