@@ -137,6 +137,33 @@ def test_whole_gpu_single_lattice_driver(coef_json):
         capi.Engine(6, n_walkers=2, device=0).cmc_grid_run(10)       # one lattice only
 
 
+def test_grid_lane_groups_match_lane_pairs(coef_json, monkeypatch):
+    """The lane-GROUP evaluation (2 L lanes per trial: dealt cell loads, REDUX mask / mark reduction, walk split by
+    neighbour position) against the lane-pair evaluation (L = 1) on the same batches: same proposals, same conflict
+    decisions, dE equal to rounding (another summation order) => the same trajectory; energies within 1e-9 eV."""
+    f = 16
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=0)
+    e.load_coefficients(coef_json)
+    occ = synth.random_alloy(f, 0.08, 0.08, seed=77, vacancy_site=None)      # solute-rich: long partner lists
+    ref = None
+    for lanes in (1, 2, 4, 8):
+        monkeypatch.setenv("LMC_CMC_GRID_LANES", str(lanes))
+        e.set_occupancy(occ)
+        e0 = e.total_energy()
+        e.cmc_reset()
+        for n in (4000, 9000):
+            e.cmc_grid_run(n, temperature=650.0, seed=11, batch_size=64)
+        st = e.cmc_state()
+        final = e.get_occupancy(0)
+        assert abs((e.total_energy() - e0) - st["energy"][0]) < 5e-9
+        if ref is None:
+            ref = (st, final)
+            continue
+        assert st["steps"][0] == ref[0]["steps"][0] and st["accepted"][0] == ref[0]["accepted"][0], lanes
+        assert np.array_equal(final, ref[1]), lanes
+        assert abs(st["energy"][0] - ref[0]["energy"][0]) < 1e-9, lanes
+
+
 def test_full_size_lattices_bookkeeping(coef_json):
     """BASELINE configs[1] (40^3, 256k sites) and configs[3] (100^3, 4M sites, simulated annealing) at full size through a
     size-independent identity: the accumulated dE of the accepted swaps equals the total-energy difference, and the
