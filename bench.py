@@ -341,6 +341,21 @@ def bench_barrier_eval(engine, torch, W, peak):
     out = {"kernel": "barrier_kernel", "events": n, "ms": ms, "events_per_s": n / (ms * 1e-3), "achieved_gbs": achieved,
            "frac_of_hbm_peak": achieved / peak, "bytes_per_event": BYTES_PER_EVENT, "finite": bool(torch.isfinite(d_ea).all().item()),
            "note": "arbitrary (vacancy, neighbour) events, one thread per event"}
+    # the same kernel on a batch that fills the device several times over (98k threads are a third of one wave)
+    big = 16
+    d_wb, d_ib, d_jb = d_w.repeat(big), d_i.repeat(big), d_j.repeat(big)
+    d_eab = torch.empty(n * big, dtype=torch.float64, device=dev)
+    d_deb = torch.empty(n * big, dtype=torch.float64, device=dev)
+    times = []
+    for k in range(8):
+        engine.eval_barriers_dev(n * big, d_wb.data_ptr(), d_ib.data_ptr(), d_jb.data_ptr(), d_eab.data_ptr(), d_deb.data_ptr())
+        if k >= 3:
+            times.append(engine.last_kernel_ms())
+    msb = sum(times) / len(times)
+    out["large_batch"] = {"events": n * big, "ms": msb, "events_per_s": n * big / (msb * 1e-3),
+                          "frac_of_hbm_peak": n * big * BYTES_PER_EVENT / (msb * 1e-3) / 1e9 / peak,
+                          "matches_small_batch": bool(torch.equal(d_eab[:n], d_ea) and torch.equal(d_deb[-n:], d_de))}
+    del d_wb, d_ib, d_jb, d_eab, d_deb
     # the event-list form (KineticMcFirstOmp::BuildEventList for a batch of vacancies): one box scan per vacancy.  Every
     # walker holds one vacancy, so a large batch is built by listing each (walker, vacancy) item `reps` times.
     reps = 16
