@@ -328,6 +328,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   double beta = 1.0 / kBoltzmannEv / temperature;
   double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
   double corr_over_prefactor = corr / kPrefactorHz;     // dt = -ln(u1) / total / 1e13 * corr with one division per step
+  double ahead_neg_log_u1 = 0.0, ahead_u2 = 0.0;        // lane l: -ln(u1) and u2 of step (s & ~15) + l
   for (int64_t s = 0; s < n_steps; ++s) {
     // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50): only a T(t) table changes the temperature during a run
     if (prm.n_tt > 0) {
@@ -365,18 +366,26 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     for (int q = 0; q < 12; ++q)
       if (q <= lane) my_cumulative += ord_rate[q];
     // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
-    double u1, u2;
+    double neg_log_u1, u2;
     if (replay_u1) {
-      u1 = replay_u1[static_cast<int64_t>(w) * n_steps + s];
+      neg_log_u1 = -log(replay_u1[static_cast<int64_t>(w) * n_steps + s]);
       u2 = replay_u2[static_cast<int64_t>(w) * n_steps + s];
     } else {
-      uint32_t r[4];
-      philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
-                    static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r);
-      u1 = uniform53(r[0], r[1]) + (1.0 / 9007199254740992.0);   // (0, 1]: -log(u1) is finite
-      u2 = uniform53(r[2], r[3]);
+      // the Philox counter of a step is the walker's step number, so the numbers of the next 16 steps are known in
+      // advance: every 16th step lane l draws (and takes the logarithm) for step s + l, and each step then picks its
+      // pair with two shuffles instead of running Philox + log on all lanes
+      if ((s & 15) == 0) {
+        const int64_t ctr = steps + lane;
+        uint32_t r[4];
+        philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(static_cast<uint64_t>(ctr) >> 32),
+                      static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r);
+        ahead_neg_log_u1 = -log(uniform53(r[0], r[1]) + (1.0 / 9007199254740992.0));   // u1 in (0, 1]: finite
+        ahead_u2 = uniform53(r[2], r[3]);
+      }
+      neg_log_u1 = __shfl_sync(hmask, ahead_neg_log_u1, static_cast<int>(s & 15), 16);
+      u2 = __shfl_sync(hmask, ahead_u2, static_cast<int>(s & 15), 16);
     }
-    const double dt = -log(u1) / total * corr_over_prefactor;
+    const double dt = neg_log_u1 / total * corr_over_prefactor;
     // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
     const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> hshift) & 0xFFFu;
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
