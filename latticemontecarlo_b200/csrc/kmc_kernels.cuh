@@ -270,6 +270,8 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
 // The 12 jumps of one vacancy share a 7 x 7 x 7 half-unit box (196 padded cells).  Per step the half-warp scans the box
 // ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
 // event lane then maps that list into its own symmetry-ordered environment through a constant cell -> env-index table.
+// kInstrumented: replayed uniforms and / or per-step traces (validation runs); the production instantiation carries neither
+template <bool kInstrumented>
 __global__ void __launch_bounds__(kKmcThreads, 8)
 kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
@@ -322,7 +324,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const KmcEvalContext ctx{s_box, s_envpos, s_A2v, s_mask_hi2, s_pbase, B_all, tab.pair_C2,
                            tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code, tab.barrier_model};
   uint32_t *ids = s_ids[wl];
-  const bool tracing = tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature;
+  const bool tracing = kInstrumented && (tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature);
   int err = 0;
 
   double beta = 1.0 / kBoltzmannEv / temperature;
@@ -367,7 +369,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       if (q <= lane) my_cumulative += ord_rate[q];
     // 3./4. random numbers: u1 -> residence time, u2 -> event (CalculateTime then SelectEvent)
     double neg_log_u1, u2;
-    if (replay_u1) {
+    if (kInstrumented && replay_u1) {
       neg_log_u1 = -log(replay_u1[static_cast<int64_t>(w) * n_steps + s]);
       u2 = replay_u2[static_cast<int64_t>(w) * n_steps + s];
     } else {
@@ -394,7 +396,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     const int nx = __shfl_sync(hmask, xj, sel_lane, 16), ny = __shfl_sync(hmask, yj, sel_lane, 16),
               nz = __shfl_sync(hmask, zj, sel_lane, 16);
     const unsigned sel_mig = __shfl_sync(hmask, mig, sel_lane, 16);
-    if (lane == 0 && alive) {
+    if (kInstrumented && lane == 0 && alive) {
       if (tracing) {
         const int64_t at = static_cast<int64_t>(w) * n_steps + s;
         if (tr.from) tr.from[at] = lat.id_of_coords(X, Y, Z);
