@@ -159,7 +159,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
     // each lane reads up to 4 rows of the box (4 consecutive bytes each: one address computation per row); hits are
     // kept as a bit mask + packed codes (index = 4 * iteration + slot) and compacted once at the end
     unsigned hit_mask = 0;
-    unsigned long long hit_codes = 0;           // 4 bits per scanned cell
+    unsigned row_word0 = 0, row_word1 = 0, row_word2 = 0;     // the scanned rows of this lane (kBoxRows / 16 == 3)
     const unsigned solvent4 = solvent * 0x01010101u;
     const int centre_slot = zp ? 1 : 2;
 #pragma unroll
@@ -180,13 +180,12 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
           if (!kHypothetical && ((word >> (8 * centre_slot)) & 0xFFu) != vac_code) err |= kErrNotVacancy;
           word = (word & ~(0xFFu << (8 * centre_slot))) | (solvent << (8 * centre_slot));
         }
-        if (word != solvent4) {                                        // rare: at least one non-solvent cell in this row
-#pragma unroll
-          for (int sl = 0; sl < 4; ++sl) {
-            const unsigned code = (word >> (8 * sl)) & 0xFFu;
-            if (code != solvent) { hit_mask |= 1u << (4 * it + sl); hit_codes |= static_cast<unsigned long long>(code) << (4 * (4 * it + sl)); }
-          }
-        }
+        // non-solvent bytes of the row, branch-free: bit 7 of every byte of `nz` that differs from the solvent code, packed
+        // into 4 mask bits; the row word itself is kept for the (rare) list entries
+        const unsigned diff = word ^ solvent4;
+        const unsigned nz = (diff | ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu)) & 0x80808080u;
+        hit_mask |= ((((nz >> 7) * 0x00204081u) >> 21) & 0xFu) << (4 * it);   // bytes 0..3 -> bits 0..3
+        if (it == 0) row_word0 = word; else if (it == 1) row_word1 = word; else row_word2 = word;
       }
     }
     // exclusive prefix of the per-lane hit counts over the half-warp
@@ -203,7 +202,8 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
       const int it = __ffs(static_cast<int>(hit_mask)) - 1;
       hit_mask &= hit_mask - 1;
       // one 16-bit entry per non-solvent cell: cell index (row * 4 + slot) | species code << 8
-      list[pos] = static_cast<uint16_t>((((it >> 2) * 16 + lane) * 4 + (it & 3)) | (static_cast<unsigned>((hit_codes >> (4 * it)) & 0xFULL) << 8));
+      const unsigned rw = (it >> 2) == 0 ? row_word0 : ((it >> 2) == 1 ? row_word1 : row_word2);
+      list[pos] = static_cast<uint16_t>((((it >> 2) * 16 + lane) * 4 + (it & 3)) | (((rw >> (8 * (it & 3))) & 0xFFu) << 8));
       ++pos;
     }
     __syncwarp(hmask);
@@ -284,7 +284,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   extern __shared__ double s_A2[];                 // [n][58][n][2]: the singlet table of every migrating species
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
-  __shared__ uint32_t s_ids[kKmcWalkersPerBlock][12];
+  __shared__ __align__(16) uint32_t s_ids[kKmcWalkersPerBlock][12];
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
@@ -344,8 +344,14 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     if (active) ids[lane] = id_j;
     __syncwarp(hmask);
     int slot = 0;
+    {
+      const uint4 *idv = reinterpret_cast<const uint4 *>(ids);      // 12 ids = three 16-byte loads
 #pragma unroll
-    for (int q = 0; q < 12; ++q) slot += ids[q] < id_j ? 1 : 0;
+      for (int q = 0; q < 3; ++q) {
+        const uint4 v = idv[q];
+        slot += (v.x < id_j ? 1 : 0) + (v.y < id_j ? 1 : 0) + (v.z < id_j ? 1 : 0) + (v.w < id_j ? 1 : 0);
+      }
+    }
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
     kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list, my_codes, beta, 0, 0u, -1,
@@ -449,7 +455,7 @@ vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict_
   extern __shared__ double s_A2[];
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
-  __shared__ uint32_t s_ids[kKmcWalkersPerBlock][12];
+  __shared__ __align__(16) uint32_t s_ids[kKmcWalkersPerBlock][12];
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
