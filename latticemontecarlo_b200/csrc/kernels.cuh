@@ -51,7 +51,9 @@ __device__ __forceinline__ double quartic_barrier_log(double dE, double log_e0) 
   // almost every warp), and a zero QUOTIENT sends the whole warp through the slow path of the fp64 division (~60
   // instructions): divide a non-zero stand-in and put the zero back
   const bool zero = dE == 0.0;
-  double x = (zero ? 1.0 : 16.0 * dE) / e0;
+  double num = zero ? 1.0 : 16.0 * dE;
+  asm volatile("" : "+d"(num));             // keep the stand-in: the compiler would otherwise divide 16 dE for every lane again
+  double x = num / e0;
   x = zero ? 0.0 : x;
   const double s = 3.0 * x + 4.0;
   return e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
