@@ -354,7 +354,9 @@ def bench_barrier_eval(engine, torch, W, peak):
     msb = sum(times) / len(times)
     out["large_batch"] = {"events": n * big, "ms": msb, "events_per_s": n * big / (msb * 1e-3),
                           "frac_of_hbm_peak": n * big * BYTES_PER_EVENT / (msb * 1e-3) / 1e9 / peak,
-                          "matches_small_batch": bool(torch.equal(d_eab[:n], d_ea) and torch.equal(d_deb[-n:], d_de))}
+                          "matches_small_batch": bool(torch.equal(d_eab[:n], d_ea) and torch.equal(d_deb[-n:], d_de)),
+                          "note": "the same events 16 times over, still grouped by vacancy (12 consecutive threads share one "
+                                  "neighbourhood: L1 hits); events in arbitrary order run at 0.27-0.29 (tools/barrier_probe.py)"}
     del d_wb, d_ib, d_jb, d_eab, d_deb
     # the event-list form (KineticMcFirstOmp::BuildEventList for a batch of vacancies): one box scan per vacancy.  Every
     # walker holds one vacancy, so a large batch is built by listing each (walker, vacancy) item `reps` times.
