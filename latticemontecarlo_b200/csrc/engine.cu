@@ -723,16 +723,15 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
   if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the KMC driver orders events by 32-bit lattice ids (num_sites < 2^31)");
   const size_t kmc_smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
-  const bool instrumented = tracing || d_u1 != nullptr;
-  LMC_CUDA(cudaFuncSetAttribute(instrumented ? kmc_run_kernel<true> : kmc_run_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
+  const bool instrumented = tracing || d_u1 != nullptr;      // the first-order kernel reads its tables through L1: no dynamic shared memory
   time_begin();
   if (second_order) {
     LMC_CUDA(cudaFuncSetAttribute(kmc_chain_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
     kmc_chain_run_kernel<<<static_cast<unsigned>(n_walkers), kChainThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st,
                                                                                                prm, n_steps, d_u2, tr);
   } else {
-    if (instrumented) kmc_run_kernel<true><<<blocks, kKmcThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
-    else kmc_run_kernel<false><<<blocks, kKmcThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+    if (instrumented) kmc_run_kernel<true><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+    else kmc_run_kernel<false><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
   }
   time_end();
   LMC_CUDA(cudaGetLastError());

@@ -134,7 +134,7 @@ struct KmcEvalContext {
 // jumped here from the cell at absolute padded index `hypo_index`: the centre (which really holds the migrated atom) is
 // the vacancy, the cell at hypo_index holds `hypo_code`, and the jump in direction `hypo_dir` (back to where the vacancy
 // came from) moves that atom.  Nothing is written to memory.
-template <bool kHypothetical>
+template <bool kHypothetical, bool kGlobalA = false>
 __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, const KmcEvalContext &ctx, const uint8_t *o, int X, int Y,
                                                       int Z, int lane, bool active, int k, int32_t dmig0, int32_t dmig1,
                                                       uint16_t *list, uint8_t *my_codes, double beta,
@@ -238,7 +238,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
           else { t = 31 + __ffs(static_cast<int>(w_hi)); w_hi &= w_hi - 1; }
           const int et = my_codes[t];
           if (et >= n) { ok = false; continue; }
-          const double2 a = A[t * n + et];
+          const double2 a = kGlobalA ? __ldg(A + t * n + et) : A[t * n + et];
           a0 += a.x; a1 += a.y;
           const uint2 hi = s_mask_hi2[t];
           uint32_t p_lo = hi.x & w_lo, p_hi = hi.y & w_hi;             // partners u > t still to visit
@@ -281,11 +281,9 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
   __shared__ double s_ord_rate[kKmcWalkersPerBlock][12];
   __shared__ uint8_t s_ord_lane[kKmcWalkersPerBlock][12];
-  extern __shared__ double s_A2[];                 // [n][58][n][2]: the singlet table of every migrating species
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
   __shared__ __align__(16) uint32_t s_ids[kKmcWalkersPerBlock][12];
-  for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
   for (int q = threadIdx.x; q < 2 * 12 * kBoxCells; q += blockDim.x) s_envpos[q] = tab.box_envpos[q];
@@ -319,7 +317,10 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   uint16_t *list = s_list[wl];
   uint8_t *my_codes = s_codes[threadIdx.x];
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
-  const double2 *s_A2v = reinterpret_cast<const double2 *>(s_A2);
+  // The singlet table A (8.3 KB for 3 species) is read through L1, not staged: with 8 blocks per SM every staged KB costs
+  // 8 KB of the 256 KB that shared memory and L1 split, and the walkers' boxes only stay L1-resident if L1 gets ~100 KB
+  const double2 *s_A2v = reinterpret_cast<const double2 *>(tab.pair_A2);
+  constexpr bool kGlobalA = true;
   const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
   const KmcEvalContext ctx{s_box, s_envpos, s_A2v, s_mask_hi2, s_pbase, B_all, tab.pair_C2,
                            tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code, tab.barrier_model};
@@ -354,8 +355,8 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     }
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
-    kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list, my_codes, beta, 0, 0u, -1,
-                                 err, ea, de, rate, mig);
+    kmc_scan_and_evaluate<false, kGlobalA>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list, my_codes, beta, 0, 0u, -1,
+                                           err, ea, de, rate, mig);
     if ((__ballot_sync(hmask, err != 0) >> hshift) & 0xFFFFu) alive = false;    // this walker stops; its state is left untouched
     if (!__any_sync(hmask, alive)) break;
     // events in the reference's order through shared memory: s_rate[slot] = rate, s_lane[slot] = lane
