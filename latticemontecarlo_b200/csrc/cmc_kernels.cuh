@@ -230,6 +230,10 @@ __device__ __forceinline__ double swap_side_energy_change_marked(const LatticeDe
   const int zp = side ? zpb : zpa;
   const int64_t override_index = (side && coupled) ? base_b + lat.padded_delta(-dx, -dy, -dz, zpb) : -1;
   const uint64_t sol = gather_site_env_marked(cells, base, s_delta + zp * 43, solvent, codes, stride, override_index, eb, my_mark, conflict);
+  // a trial that lost the claim on either side is dropped by the caller: skip its table walk (both lanes of the pair are here)
+  const unsigned pair_mask = 3u << (threadIdx.x & 30u);
+  const bool lost = __shfl_xor_sync(pair_mask, *conflict ? 1 : 0, 1) || *conflict;
+  if (lost) { *conflict = true; return 0.0; }
   if (ea == eb) return 0.0;
   return site_energy_change_staged(tv, static_cast<int>(side ? eb : ea), static_cast<int>(side ? ea : eb), sol, codes, stride);
 }
