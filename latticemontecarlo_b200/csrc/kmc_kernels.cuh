@@ -271,14 +271,16 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
 // ONCE (13 byte loads per lane instead of 60 per event), compacts the non-solvent cells into a short list, and every
 // event lane then maps that list into its own symmetry-ordered environment through a constant cell -> env-index table.
 // kInstrumented: replayed uniforms and / or per-step traces (validation runs); the production instantiation carries neither
+// 7 blocks per SM: the 8192-walker workload puts at most 7 on an SM (1024 blocks / 148 SMs), and the bound of 8 cost 8
+// registers (spills) and, through the shared-memory carve-out for an 8th block, 32 KB of L1
 template <bool kInstrumented>
-__global__ void __launch_bounds__(kKmcThreads, 8)
+__global__ void __launch_bounds__(kKmcThreads, 7)
 kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
   __shared__ int32_t s_box[2 * kBoxCells];
   __shared__ int8_t s_envpos[2 * 12 * kBoxCells];
   __shared__ uint16_t s_list[kKmcWalkersPerBlock][kBoxCells];
-  __shared__ uint8_t s_codes[kKmcThreads][kEnvN + 2];
+  __shared__ uint8_t s_codes[kKmcWalkersPerBlock * 12][kEnvN + 2];     // one row per EVENT lane (lanes 12..15 of a half-warp have none)
   __shared__ double s_ord_rate[kKmcWalkersPerBlock][12];
   __shared__ uint8_t s_ord_lane[kKmcWalkersPerBlock][12];
   __shared__ uint64_t s_mask_hi[kEnvN];
@@ -315,7 +317,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   double *ord_rate = s_ord_rate[wl];
   uint8_t *ord_lane = s_ord_lane[wl];
   uint16_t *list = s_list[wl];
-  uint8_t *my_codes = s_codes[threadIdx.x];
+  uint8_t *my_codes = s_codes[wl * 12 + k];
   const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
   // The singlet table A (8.3 KB for 3 species) is read through L1, not staged: with 8 blocks per SM every staged KB costs
   // 8 KB of the 256 KB that shared memory and L1 split, and the walkers' boxes only stay L1-resident if L1 gets ~100 KB
