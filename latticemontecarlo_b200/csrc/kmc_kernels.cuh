@@ -396,7 +396,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       neg_log_u1 = __shfl_sync(hmask, ahead_neg_log_u1, static_cast<int>(s & 15), 16);
       u2 = __shfl_sync(hmask, ahead_u2, static_cast<int>(s & 15), 16);
     }
-    const double dt = neg_log_u1 / total * corr_over_prefactor;
+    const double dt = __dmul_rn(neg_log_u1 / total, corr_over_prefactor);   // never contracted into `time += dt`: both instantiations round alike
     // first slot whose cumulative probability is not < u2, else the last one (KineticMcAbstract.cpp:106-116)
     const unsigned hit = (__ballot_sync(hmask, lane < 12 && !(my_cumulative < u2)) >> hshift) & 0xFFFu;
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;

@@ -71,6 +71,31 @@ def test_philox_runs_are_deterministic_and_chunkable(golden, tmp_path):
     assert s1["time"][:16].mean() > s1["time"][-16:].mean()
 
 
+def test_production_and_instrumented_kernels_agree(golden, tmp_path):
+    """kmc_run_kernel<false> (no trace, no replay: the benchmarked instantiation, random numbers drawn 16 steps ahead) and
+    kmc_run_kernel<true> (per-step traces) advance the same Philox trajectories: identical states, and the traced hops
+    lead from the start to the untraced run's final vacancy sites."""
+    e = _engine(golden, "B", tmp_path, n_walkers=48)
+    occ = golden["B_occ"]
+    temps = np.linspace(420.0, 580.0, 48)
+
+    def run(trace):
+        for w in range(48):
+            e.set_occupancy(occ, walker=w)
+        e.kmc_reset()
+        tr = e.kmc_run(37, temperatures=temps, seed=77, trace=trace)          # 37: not a multiple of the 16-step draw-ahead
+        tr2 = e.kmc_run(90, temperatures=temps, seed=77, trace=trace)
+        return e.kmc_state(), e.get_occupancy_all(), tr, tr2
+
+    s0, o0, _, _ = run(False)
+    s1, o1, tr, tr2 = run(True)
+    assert np.array_equal(o0, o1)
+    for key in ("time", "energy", "steps", "vacancy"):
+        assert np.array_equal(s0[key], s1[key]), key
+    assert np.array_equal(tr2["to"][:, -1], s0["vacancy"])
+    assert np.allclose(tr["dt"].sum(axis=1) + tr2["dt"].sum(axis=1), s0["time"], rtol=1e-12)
+
+
 def test_walkers_follow_oracle_with_device_random_numbers(coef_json):
     """Philox mode: recompute each step's decision on the CPU oracle from the traced state (events are a function of
     occupancy only, so the traced (from, to, Ea, dE, total_rate) of every step can be verified independently)."""
