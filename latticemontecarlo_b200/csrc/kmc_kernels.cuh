@@ -625,8 +625,6 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
       const double barrier = ea_ik - de_ik, change = -de_ik;
       s_barrier[rank] = barrier;
       s_de[rank] = change;
-      s_fwd[rank] = exp(-barrier * beta);                      // forward_rate_ (JumpEvent.cpp:13)
-      s_bwd[rank] = exp((change - barrier) * beta);            // GetBackwardRate (:28-30)
       s_total_i[rank] = total_i;
       s_dir[rank] = static_cast<uint8_t>(h);
       s_is_prev[rank] = static_cast<int64_t>(id_i) == previous ? 1 : 0;
@@ -636,6 +634,14 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
     // ---- CalculateTime + SelectEvent (KineticMcChainOmpi.cpp:93-151, KineticMcAbstract.cpp:106-123) in the first
     // half-warp: lane r owns rank r; every sum runs sequentially in rank order like the reference's reductions
     if (threadIdx.x < 16) {
+      // the 12 forward / backward rates of the k -> i events in ONE instruction stream (lane r = rank r) instead of one
+      // lane-0 stream in each of the six warps
+      if (active) {
+        const double barrier = s_barrier[lane], change = s_de[lane];
+        s_fwd[lane] = exp(-barrier * beta);                      // forward_rate_ (JumpEvent.cpp:13)
+        s_bwd[lane] = exp((change - barrier) * beta);            // GetBackwardRate (:28-30)
+      }
+      __syncwarp(0xFFFFu);
       double total_k = 0.0;
 #pragma unroll
       for (int r = 0; r < 12; ++r) total_k += s_fwd[r];
