@@ -208,7 +208,8 @@ typedef struct lmc_cmc_params {
   double temperature;              /* `temperature` (CMC) */
   const double *temperatures;      /* optional per-replica temperatures [n_walkers] */
   uint64_t seed;                   /* Philox4x32-10 key */
-  int32_t batch_size;              /* proposals per batch (power of two, 32..512); 0 = chosen from the lattice size */
+  int32_t batch_size;              /* proposals per thread block and batch (power of two, 32..512; half as many trials
+                                    * are evaluated); 0 = chosen from the lattice size */
 } lmc_cmc_params;
 
 /* reset steps / energy / counters of every replica; with sa_maximum_steps > 0 the SimulatedAnnealing schedule is armed:
@@ -219,7 +220,9 @@ int lmc_cmc_reset(lmc_engine *engine, double sa_initial_temperature, uint64_t sa
 int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
 /* ONE large lattice on the whole GPU, and on several GPUs (BASELINE configs[3]).  Same Markov-chain rules as
  * lmc_cmc_run, but the batch is spread over a persistent cooperative grid (one thread block per SM) instead of one
- * thread-block cluster; requires an engine with n_walkers == 1.
+ * thread-block cluster; requires an engine with n_walkers == 1.  A trial is evaluated by 2 L lanes (L = 8 for small
+ * batches, down to 1 at 512 proposals per block; environment variable LMC_CMC_GRID_LANES overrides it for tuning / A-B runs;
+ * the trajectory does not depend on L up to the rounding of dE).
  *
  * Multi-GPU (one process per GPU, same occupancy / coefficients / seed / reset on every rank): every rank keeps the whole
  * lattice and draws the same proposals; the dE evaluation of a batch is sharded over the ranks, and kept / accept masks
