@@ -337,9 +337,12 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   for (int64_t s = 0; s < n_steps; ++s) {
     // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50): only a T(t) table changes the temperature during a run
     if (prm.n_tt > 0) {
-      temperature = interpolate_temperature(prm, time);
-      beta = 1.0 / kBoltzmannEv / temperature;
-      if (prm.rate_corrector) { corr = rate_correction(c_vac, c_sol, temperature); corr_over_prefactor = corr / kPrefactorHz; }
+      const double t_now = interpolate_temperature(prm, time);
+      if (t_now != temperature) {                   // beyond the ends of the table T(t) is constant: nothing to recompute
+        temperature = t_now;
+        beta = 1.0 / kBoltzmannEv / temperature;
+        if (prm.rate_corrector) { corr = rate_correction(c_vac, c_sol, temperature); corr_over_prefactor = corr / kPrefactorHz; }
+      }
     }
     // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
     const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
@@ -578,9 +581,12 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
   double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
   for (int64_t s = 0; s < n_steps; ++s) {
     if (prm.n_tt > 0) {                            // UpdateTemperature (KineticMcAbstract.cpp:45-50)
-      temperature = interpolate_temperature(prm, time);
-      beta = 1.0 / kBoltzmannEv / temperature;
-      if (prm.rate_corrector) corr = rate_correction(c_vac, c_sol, temperature);
+      const double t_now = interpolate_temperature(prm, time);
+      if (t_now != temperature) {                   // beyond the ends of the table T(t) is constant: nothing to recompute
+        temperature = t_now;
+        beta = 1.0 / kBoltzmannEv / temperature;
+        if (prm.rate_corrector) corr = rate_correction(c_vac, c_sol, temperature);
+      }
     }
     // ---- ranks: the 12 neighbours i of k in ascending lattice-id order
     const int xn = wrap_coord(X + dxk, px), yn = wrap_coord(Y + dyk, py), zn = wrap_coord(Z + dzk, pz);
