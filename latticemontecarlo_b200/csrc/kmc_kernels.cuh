@@ -579,6 +579,7 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
 
   double beta = 1.0 / kBoltzmannEv / temperature;
   double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
+  double ahead_u = 0.0;                            // first half-warp, lane l: the uniform of step (s & ~15) + l
   for (int64_t s = 0; s < n_steps; ++s) {
     if (prm.n_tt > 0) {                            // UpdateTemperature (KineticMcAbstract.cpp:45-50)
       const double t_now = interpolate_temperature(prm, time);
@@ -688,10 +689,15 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
       double u;
       if (replay_u) u = replay_u[static_cast<int64_t>(w) * n_steps + s];
       else {
-        uint32_t r4[4];
-        philox4x32_10(static_cast<uint32_t>(steps), static_cast<uint32_t>(static_cast<uint64_t>(steps) >> 32),
-                      static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r4);
-        u = uniform53(r4[2], r4[3]);
+        // the Philox counter is the step number: lane l draws for step s + l every 16th step (kmc_run_kernel does the same)
+        if ((s & 15) == 0) {
+          const int64_t ctr = steps + lane;
+          uint32_t r4[4];
+          philox4x32_10(static_cast<uint32_t>(ctr), static_cast<uint32_t>(static_cast<uint64_t>(ctr) >> 32),
+                        static_cast<uint32_t>(prm.seed) ^ static_cast<uint32_t>(w), static_cast<uint32_t>(prm.seed >> 32), r4);
+          ahead_u = uniform53(r4[2], r4[3]);
+        }
+        u = __shfl_sync(0xFFFFu, ahead_u, static_cast<int>(s & 15), 16);
       }
       const unsigned hit = __ballot_sync(0xFFFFu, active && !(cumulative < u)) & 0xFFFu;
       const int sel = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
