@@ -496,8 +496,14 @@ vacancy_events_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict_
     if (active) s_ids[wl][lane] = id_j;
     __syncwarp(hmask);
     int slot = 0;
+    {
+      const uint4 *idv = reinterpret_cast<const uint4 *>(s_ids[wl]);    // 12 ids = three 16-byte loads
 #pragma unroll
-    for (int q = 0; q < 12; ++q) slot += s_ids[wl][q] < id_j ? 1 : 0;
+      for (int q = 0; q < 3; ++q) {
+        const uint4 v = idv[q];
+        slot += (v.x < id_j ? 1 : 0) + (v.y < id_j ? 1 : 0) + (v.z < id_j ? 1 : 0) + (v.w < id_j ? 1 : 0);
+      }
+    }
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
     kmc_scan_and_evaluate<false>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, s_list[wl], s_codes[threadIdx.x], 0.0,
@@ -536,7 +542,7 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
   extern __shared__ double s_A2[];
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
-  __shared__ uint32_t s_ids[12][12];
+  __shared__ __align__(16) uint32_t s_ids[12][12];
   // per-rank results in rank (slot) order
   __shared__ double s_fwd[12], s_bwd[12], s_total_i[12], s_barrier[12], s_de[12];
   __shared__ uint8_t s_dir[12], s_is_prev[12], s_mig[12];
@@ -614,8 +620,14 @@ kmc_chain_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walke
     if (active) s_ids[h][lane] = id_l;
     __syncwarp(hmask);
     int slot = 0;
+    {
+      const uint4 *idv = reinterpret_cast<const uint4 *>(s_ids[h]);     // 12 ids = three 16-byte loads
 #pragma unroll
-    for (int q = 0; q < 12; ++q) slot += s_ids[h][q] < id_l ? 1 : 0;
+      for (int q = 0; q < 3; ++q) {
+        const uint4 v = idv[q];
+        slot += (v.x < id_l ? 1 : 0) + (v.y < id_l ? 1 : 0) + (v.z < id_l ? 1 : 0) + (v.w < id_l ? 1 : 0);
+      }
+    }
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
     kmc_scan_and_evaluate<true>(lat, ctx, o, xi, yi, zi, lane, active, k, dmig0, dmig1, s_list[h],
