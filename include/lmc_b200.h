@@ -237,6 +237,40 @@ int lmc_cmc_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_tria
 int lmc_cmc_grid_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n_trials);
 int lmc_cmc_exchange_handle(lmc_engine *engine, void *handle64);
 int lmc_cmc_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles, int32_t grid_ctas);
+/* Domain-decomposed ("sublattice") CMC / SA driver -- BASELINE configs[1] / [3], SURVEY 8(e) "large-lattice CMC / SA".
+ * SEMANTIC CHANGE against mc/src/CanonicalMcAbstract.cpp:43-51 (global random unlike pairs): the periodic lattice is cut
+ * into box-shaped domains of about `domain_edge` half lattice constants per axis whose grid origin moves by a random
+ * vector every sweep; within a sweep a trial swaps two sites drawn uniformly from ONE domain's active core (the domain
+ * minus one plane of sites per face), redrawn while the species are equal as in the reference.  Cores of different
+ * domains are outside each other's 43-site neighbourhoods, so the non-interference rule of CanonicalMcOmp.cpp:47-72 holds
+ * by construction: domains run concurrently (one lane group each, the domain resident in shared memory) with no claims
+ * and one grid barrier per sweep; inside a domain trials are sequential Metropolis steps (CanonicalMcAbstract.cpp:86-101) on
+ * the exact dE of EnergyChangePredictorPairSite::GetDeFromLatticeIdPair.  Proposals are symmetric and every sweep leaves
+ * the canonical distribution invariant; the moving origin makes the chain ergodic (ensemble parity with
+ * mc::CanonicalMcSerial: tests/test_gpu_cmc_stat.py).  Energy / steps / SA schedule are updated once per sweep.
+ * Works for any number of replicas (all replicas sweep in lock step until every one has done n_trials more).
+ *
+ * Multi-GPU (ONE lattice, n_walkers == 1; one process per GPU, same occupancy / coefficients / seed / reset everywhere):
+ * rank r owns a slab of the domain grid along x; at write-back every row goes to the local buffer and, through NVLink
+ * peer mappings, to every rank whose slab or halo holds that plane in the next sweep (halo + migration exchange inside
+ * the persistent kernel); sweep totals travel as flag-carrying lines that double as the inter-GPU barrier.  The
+ * trajectory is identical for every world size.  Set-up, collective over the ranks:
+ *   1. each rank: lmc_cmc_domain_handles(engine, h)       -- three 64-byte CUDA IPC handles (192 bytes)
+ *   2. all-gather the handles
+ *   3. each rank: lmc_cmc_domain_attach_peers(engine, rank, world, handles[world][192])
+ *   4. barrier, then every rank calls lmc_cmc_domain_run with identical arguments. */
+typedef struct lmc_cmc_domain_params {
+  int32_t domain_edge;             /* target domain edge in half lattice constants, 4..48 (0 = 8) */
+  int32_t rounds_per_sweep;        /* Metropolis rounds per domain and sweep (0 = (domain_edge - 2)^3, two per core site) */
+  int32_t tries_per_round;         /* candidate draws per round, each `lanes` pairs (0 = 4); a round without an unlike pair idles */
+  int32_t lanes;                   /* lanes per domain: 2, 4, 8, 16 or 32 (0 = from the number of domains); the random stream,
+                                    * hence the trajectory, depends on it */
+} lmc_cmc_domain_params;
+int lmc_cmc_domain_run(lmc_engine *engine, const lmc_cmc_params *params, const lmc_cmc_domain_params *domain, int64_t n_trials);
+int lmc_cmc_domain_handles(lmc_engine *engine, void *handles192);
+int lmc_cmc_domain_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles);
+/* launch shape of the last lmc_cmc_domain_run: {domain_edge, domains, lanes, threads per block, blocks, rounds per sweep} */
+int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape6);
 /* replay mode on replica `walker`: the n trials (site_a, site_b, u) are applied in the given order with the reference's
  * serial semantics (u is consumed only when dE >= 0).  Outputs (host, [n], optional): dE, energy and temperature before
  * each trial, accept flags. */

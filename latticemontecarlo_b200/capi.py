@@ -134,6 +134,10 @@ class CmcParams(C.Structure):
     _fields_ = [("temperature", C.c_double), ("temperatures", C.c_void_p), ("seed", C.c_uint64), ("batch_size", C.c_int32)]
 
 
+class CmcDomainParams(C.Structure):
+    _fields_ = [("domain_edge", C.c_int32), ("rounds_per_sweep", C.c_int32), ("tries_per_round", C.c_int32), ("lanes", C.c_int32)]
+
+
 class Engine:
     """One lmc_engine (one GPU, or host-only with device=-1)."""
 
@@ -361,6 +365,32 @@ class Engine:
         keep = []
         prm = self._cmc_params(temperature, None, seed, batch_size, keep)
         _check(lib().lmc_cmc_grid_run(self.h, C.byref(prm), C.c_int64(int(n_trials))))
+
+    def cmc_domain_run(self, n_trials, temperature=800.0, temperatures=None, seed=0, domain_edge=0, rounds_per_sweep=0,
+                       tries_per_round=0, lanes=0):
+        """Domain-decomposed ("sublattice") CMC / SA driver: lmc_cmc_domain_run (one lattice or many replicas; after
+        cmc_domain_attach_peers one lattice over several GPUs)."""
+        keep = []
+        prm = self._cmc_params(temperature, temperatures, seed, 0, keep)
+        dom = CmcDomainParams(int(domain_edge), int(rounds_per_sweep), int(tries_per_round), int(lanes))
+        _check(lib().lmc_cmc_domain_run(self.h, C.byref(prm), C.byref(dom), C.c_int64(int(n_trials))))
+
+    def cmc_domain_last_shape(self):
+        out = (C.c_int32 * 6)()
+        _check(lib().lmc_cmc_domain_last_shape(self.h, out))
+        return dict(zip(("domain_edge", "domains", "lanes", "threads", "blocks", "rounds_per_sweep"), (int(v) for v in out)))
+
+    def cmc_domain_handles(self):
+        """192 bytes: CUDA IPC handles of the two occupancy buffers and the line buffer (to be all-gathered over the ranks)."""
+        buf = C.create_string_buffer(192)
+        _check(lib().lmc_cmc_domain_handles(self.h, buf))
+        return buf.raw
+
+    def cmc_domain_attach_peers(self, rank, world, handles):
+        """handles: list of `world` 192-byte blobs in rank order (entry `rank` is ignored)."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 192 * world
+        _check(lib().lmc_cmc_domain_attach_peers(self.h, int(rank), int(world), blob))
 
     def cmc_exchange_handle(self):
         """64-byte CUDA IPC handle of this engine's exchange buffer (to be all-gathered over the ranks)."""

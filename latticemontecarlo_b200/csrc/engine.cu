@@ -18,6 +18,7 @@
 #include "kmc_kernels.cuh"
 #include "cmc_kernels.cuh"
 #include "cmc_grid_kernels.cuh"
+#include "cmc_domain_kernels.cuh"
 #include "tables.h"
 
 namespace lmc {
@@ -94,8 +95,15 @@ Engine::~Engine() {
     cudaSetDevice(device);
     for (int r = 0; r < 8; ++r)
       if (cmc_peer_xchg[r] && cmc_peer_xchg[r] != d_cmc_xchg) cudaIpcCloseMemHandle(cmc_peer_xchg[r]);
+    for (int r = 0; r < 8; ++r) {
+      if (r == dom_rank) continue;
+      for (int b = 0; b < 2; ++b)
+        if (dom_peer_occ[b][r]) cudaIpcCloseMemHandle(dom_peer_occ[b][r]);
+      if (dom_peer_lines[r]) cudaIpcCloseMemHandle(dom_peer_lines[r]);
+    }
     for (void *p : device_allocs) cudaFree(p);
-    cudaFree(d_occ);
+    if (d_occ_buf[1]) { cudaFree(d_occ_buf[0]); cudaFree(d_occ_buf[1]); }
+    else cudaFree(d_occ);
     cudaFree(d_error);
     cudaFree(d_scratch);
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -831,6 +839,7 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   require_coefficients();
   if (n_walkers != 1) throw std::invalid_argument("lmc_cmc_grid_run drives ONE lattice with the whole GPU (n_walkers == 1)");
   if (!cmc_ready) cmc_reset(0.0, 0);
+  if (cmc_cells_stale) cmc_sync_cells();
   cmc_grid_prepare();
   if (n_trials <= 0) return;
   const double temp = params.temperatures ? params.temperatures[0] : params.temperature;
@@ -939,6 +948,244 @@ void Engine::cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ domain-decomposed CMC / SA
+void Engine::cmc_domain_prepare() {
+  require_device();
+  if (d_occ_buf[1]) return;
+  const size_t bytes = static_cast<size_t>(n_walkers) * lat.padded_size + 16;
+  d_occ_buf[0] = d_occ;
+  LMC_CUDA(cudaMalloc(&d_occ_buf[1], bytes));
+  occ_cur = 0;
+  d_dom_state = dev_alloc<DomState>(2 * static_cast<size_t>(n_walkers));
+  d_dom_accum = dev_alloc<unsigned long long>(3 * static_cast<size_t>(n_walkers) * 4);
+  d_dom_lines = dev_alloc<DomLine>(2 * kGridMaxWorld);
+  d_dom_counters = dev_alloc<unsigned long long>(4);   // [0] grid barrier, [1] inter-GPU line sequence, [2] sweeps done
+  d_dom_abort = dev_alloc<int>(1);
+  for (void *p : {d_dom_state, static_cast<void *>(d_dom_accum), d_dom_lines, static_cast<void *>(d_dom_counters), static_cast<void *>(d_dom_abort)})
+    device_allocs.push_back(p);
+  LMC_CUDA(cudaMemsetAsync(d_occ_buf[1], 0, bytes, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_lines, 0, sizeof(DomLine) * 2 * kGridMaxWorld, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 32, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  for (int b = 0; b < 2; ++b) dom_peer_occ[b][0] = d_occ_buf[b];
+  dom_peer_lines[0] = d_dom_lines;
+}
+
+void Engine::cmc_domain_handles(void *handles192) {
+  if (!handles192) throw std::invalid_argument("null handle buffer");
+  cmc_domain_prepare();
+  cudaIpcMemHandle_t h[3];
+  LMC_CUDA(cudaIpcGetMemHandle(&h[0], d_occ_buf[0]));
+  LMC_CUDA(cudaIpcGetMemHandle(&h[1], d_occ_buf[1]));
+  LMC_CUDA(cudaIpcGetMemHandle(&h[2], d_dom_lines));
+  std::memcpy(handles192, h, 192);
+}
+
+void Engine::cmc_domain_attach_peers(int32_t rank, int32_t world, const void *handles) {
+  cmc_domain_prepare();
+  if (world < 1 || world > kGridMaxWorld || rank < 0 || rank >= world) throw std::invalid_argument("rank / world out of range (world <= 8)");
+  if (world > 1 && !handles) throw std::invalid_argument("null handles");
+  if (n_walkers != 1) throw std::invalid_argument("the multi-GPU domain driver runs ONE lattice (n_walkers == 1)");
+  for (int r = 0; r < 8; ++r) {
+    if (r != dom_rank) {
+      for (int b = 0; b < 2; ++b)
+        if (dom_peer_occ[b][r]) cudaIpcCloseMemHandle(dom_peer_occ[b][r]);
+      if (dom_peer_lines[r]) cudaIpcCloseMemHandle(dom_peer_lines[r]);
+    }
+    dom_peer_occ[0][r] = dom_peer_occ[1][r] = nullptr;
+    dom_peer_lines[r] = nullptr;
+  }
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) {
+      dom_peer_occ[0][r] = d_occ_buf[0]; dom_peer_occ[1][r] = d_occ_buf[1]; dom_peer_lines[r] = d_dom_lines;
+      continue;
+    }
+    cudaIpcMemHandle_t h[3];
+    std::memcpy(h, static_cast<const char *>(handles) + 192 * r, 192);
+    void *mapped[3] = {nullptr, nullptr, nullptr};
+    for (int q = 0; q < 3; ++q) LMC_CUDA(cudaIpcOpenMemHandle(&mapped[q], h[q], cudaIpcMemLazyEnablePeerAccess));
+    dom_peer_occ[0][r] = static_cast<uint8_t *>(mapped[0]);
+    dom_peer_occ[1][r] = static_cast<uint8_t *>(mapped[1]);
+    dom_peer_lines[r] = mapped[2];
+  }
+  dom_world = world;
+  dom_rank = rank;
+  // a fresh world starts a fresh line sequence (collective: every rank attaches before any rank runs)
+  LMC_CUDA(cudaMemsetAsync(d_dom_lines, 0, sizeof(DomLine) * 2 * kGridMaxWorld, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 16, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::cmc_sync_cells() {
+  const unsigned blocks = static_cast<unsigned>((lat.num_sites + 255) / 256);
+  for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
+    const unsigned ny = static_cast<unsigned>(std::min(32768, n_walkers - w0));
+    cmc_mirror_kernel<<<dim3(blocks, ny), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(w0) * lat.padded_size,
+                                                            d_cmc_mirror + static_cast<int64_t>(w0) * lat.num_sites);
+    ++launch_count;
+  }
+  // claim marks cleared, species bytes copied: the packed cell array of the batched CMC kernels
+  const int64_t n_cells = static_cast<int64_t>(n_walkers) * lat.padded_size;
+  cmc_cells_init_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, stream>>>(n_cells, d_occ, d_cmc_marks);
+  ++launch_count;
+  LMC_CUDA(cudaGetLastError());
+  LMC_CUDA(cudaMemsetAsync(d_cmc_epoch, 0, static_cast<size_t>(n_walkers) * 8, stream));   // the marks were cleared: epochs may restart
+  cmc_cells_stale = false;
+}
+
+void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_params *dom, int64_t n_trials) {
+  require_device();
+  require_coefficients();
+  if (n_walkers > kDomMaxWalkers) throw std::invalid_argument("lmc_cmc_domain_run drives at most 2048 replicas per engine");
+  if (!cmc_ready) cmc_reset(0.0, 0);
+  cmc_domain_prepare();
+  if (dom_world > 1 && n_walkers != 1) throw std::invalid_argument("the multi-GPU domain driver runs ONE lattice (n_walkers == 1)");
+  if (n_trials <= 0) return;
+  const size_t nw = static_cast<size_t>(n_walkers);
+  std::vector<double> temps(nw, params.temperature);
+  if (params.temperatures) std::copy(params.temperatures, params.temperatures + nw, temps.begin());
+  LMC_CUDA(cudaMemcpyAsync(d_cmc_temperature, temps.data(), nw * 8, cudaMemcpyHostToDevice, stream));
+  std::vector<unsigned long long> steps(nw);
+  unsigned long long sweep0 = 0;
+  LMC_CUDA(cudaMemcpyAsync(steps.data(), d_cmc_steps, nw * 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(&sweep0, d_dom_counters + 2, 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long target = *std::min_element(steps.begin(), steps.end()) + static_cast<unsigned long long>(n_trials);
+  // ---- decomposition
+  const int edge = dom && dom->domain_edge > 0 ? dom->domain_edge : 8;
+  if (edge < 4 || edge > 48) throw std::invalid_argument("domain_edge must be in 4..48 half lattice constants");
+  const int px = 2 * lat.fx, py = 2 * lat.fy;
+  CmcDomainParams dp{};
+  dp.ndx = std::max(1, px / edge); dp.ndy = std::max(1, py / edge); dp.ndz = std::max(1, (2 * lat.fz) / edge);
+  auto max_size = [](int period, int nd) { return (period + nd - 1) / nd; };
+  const int dx_max = max_size(px, dp.ndx), dy_max = max_size(py, dp.ndy), dz_max = 2 * max_size(lat.fz, dp.ndz);
+  const int dz_min = 2 * (lat.fz / dp.ndz);
+  if (px / dp.ndx < 4 || py / dp.ndy < 4 || dz_min < 4) throw std::invalid_argument("domains must span at least 4 half lattice constants per axis");
+  if (static_cast<long long>(dx_max - 2) * (dy_max - 2) * (dz_max - 2) / 2 > 65535) throw std::invalid_argument("domain core too large (<= 65535 sites)");
+  dp.tile_y = dy_max + 2;
+  dp.tile_zh = (dz_max + 2) / 2;
+  const int tile_cells = (dx_max + 2) * dp.tile_y * dp.tile_zh;
+  if (2 * dp.tile_y * dp.tile_zh + 2 * dp.tile_zh + 2 > 32767) throw std::invalid_argument("domain tile too large for 16-bit offsets");
+  dp.tile_cells = (tile_cells + 15) & ~15;
+  dp.max_core = (dx_max - 2) * (dy_max - 2) * (dz_max - 2) / 2;
+  dp.tile_bytes = dp.tile_cells + 96 + ((2 * dp.max_core + 15) & ~15);
+  dp.rounds = dom && dom->rounds_per_sweep > 0 ? dom->rounds_per_sweep : (edge - 2) * (edge - 2) * (edge - 2);
+  dp.tries = dom && dom->tries_per_round > 0 ? dom->tries_per_round : 4;
+  dp.n_walkers = n_walkers;
+  dp.world = dom_world; dp.rank = dom_rank;
+  // ---- launch shape: one lane group per domain; wide groups while the domains of the whole job leave the SMs empty
+  const int sms = device_attr(cudaDevAttrMultiProcessorCount);
+  const long long items_total = static_cast<long long>(n_walkers) * dp.ndx * dp.ndy * dp.ndz;
+  const int slab = domain_slab_begin(dp.ndx, dom_world, dom_rank + 1) - domain_slab_begin(dp.ndx, dom_world, dom_rank);
+  const long long items_rank = static_cast<long long>(n_walkers) * slab * dp.ndy * dp.ndz;
+  int lanes = dom ? dom->lanes : 0;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_LANES")) lanes = std::atoi(v);        // tuning knob
+  if (lanes <= 0) lanes = items_total <= static_cast<long long>(sms) * dom_world * 16 ? 32 : (items_total <= static_cast<long long>(sms) * dom_world * 48 ? 16 : 8);
+  if (lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per domain must be 2, 4, 8, 16 or 32");
+  const int m = species.n + 1;
+  const size_t b_bytes = static_cast<size_t>(m) * tab.n_site_pairs * m * m * 8;
+  size_t fixed = (static_cast<size_t>(m) + static_cast<size_t>(m) * kSiteEnvN * m) * 8 + kSiteEnvN * 8 + nw * 8 + kDomPidxBytes + 2 * 44 * 2;
+  const int max_optin = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin) - 1024;     // static shared memory of the kernel
+  int max_threads = kDomMaxThreads;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_THREADS")) max_threads = std::max(32, std::min(kDomMaxThreads, std::atoi(v) / 32 * 32));
+  int groups = static_cast<int>(std::min<long long>(max_threads / lanes, std::max<long long>(1, (items_rank + sms - 1) / sms)));
+  // the pair table B is staged in shared memory when it fits next to the tiles of a single pass
+  int stage_b = fixed + b_bytes + static_cast<size_t>(groups) * dp.tile_bytes <= static_cast<size_t>(max_optin) ? 1 : 0;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_STAGE_B")) stage_b = std::atoi(v) && fixed + b_bytes + dp.tile_bytes <= static_cast<size_t>(max_optin);
+  if (stage_b) fixed += b_bytes;
+  while (groups > 1 && fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) --groups;
+  if (fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) throw std::invalid_argument("domain tile does not fit in shared memory");
+  int threads = (groups * lanes + 31) / 32 * 32;
+  groups = threads / lanes;
+  while (fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) { threads -= 32; groups = threads / lanes; }
+  const size_t smem = fixed + static_cast<size_t>(groups) * dp.tile_bytes;
+  const int ctas = static_cast<int>(std::max<long long>(1, std::min<long long>(sms, (items_rank + groups - 1) / groups)));
+  using DomKernel = void (*)(LatticeDesc, DevTables, CmcDomainParams, CmcState, uint64_t, unsigned long long);
+  DomKernel kernel = nullptr;
+  switch (lanes * 2 + stage_b) {
+    case 4: kernel = cmc_domain_kernel<1, false>; break;
+    case 5: kernel = cmc_domain_kernel<1, true>; break;
+    case 8: kernel = cmc_domain_kernel<2, false>; break;
+    case 9: kernel = cmc_domain_kernel<2, true>; break;
+    case 16: kernel = cmc_domain_kernel<4, false>; break;
+    case 17: kernel = cmc_domain_kernel<4, true>; break;
+    case 32: kernel = cmc_domain_kernel<8, false>; break;
+    case 33: kernel = cmc_domain_kernel<8, true>; break;
+    case 64: kernel = cmc_domain_kernel<16, false>; break;
+    default: kernel = cmc_domain_kernel<16, true>; break;
+  }
+  LMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int per_sm = 0;
+  LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) throw std::runtime_error("cmc_domain_kernel does not fit on an SM");
+  // ---- buffers: the sweep with index s reads occ[s & 1]; the data of sweep0 sits in d_occ_buf[occ_cur]
+  const int phase = (occ_cur - static_cast<int>(sweep0 & 1ULL)) & 1;
+  for (int i = 0; i < 2; ++i) {
+    dp.occ[i] = d_occ_buf[(i + phase) & 1];
+    for (int r = 0; r < kGridMaxWorld; ++r) dp.peer_occ[i][r] = dom_peer_occ[(i + phase) & 1][r];
+  }
+  for (int r = 0; r < kGridMaxWorld; ++r) dp.peer_lines[r] = static_cast<DomLine *>(dom_peer_lines[r]);
+  dp.lines = static_cast<DomLine *>(d_dom_lines);
+  dp.state = static_cast<DomState *>(d_dom_state);
+  dp.accum = d_dom_accum;
+  dp.barrier_counter = d_dom_counters;
+  dp.line_seq = d_dom_counters + 1;
+  dp.abort_flag = d_dom_abort;
+  dp.sweep = d_dom_counters + 2;
+  dp.spin_limit = static_cast<long long>(device_attr(cudaDevAttrClockRate)) * 1000LL * 5LL;   // ~5 s
+  LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_abort, 0, 4, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_accum, 0, 3 * nw * 4 * 8, stream));
+  CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
+  dom_state_init_kernel<<<static_cast<unsigned>((nw + 127) / 128), 128, 0, stream>>>(n_walkers, st, d_cmc_temperature,
+                                                                                    static_cast<DomState *>(d_dom_state) + ((sweep0 + 1) & 1ULL) * nw);
+  ++launch_count;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+  cfg.blockDim = dim3(static_cast<unsigned>(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;      // co-residency of all CTAs: the per-sweep grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  dom_last_lanes = lanes; dom_last_threads = threads; dom_last_ctas = ctas; dom_last_domains = static_cast<int>(items_total);
+  dom_last_rounds = dp.rounds; dom_last_edge = edge;
+  time_begin();
+  LMC_CUDA(cudaLaunchKernelEx(&cfg, kernel, lat, tab, dp, st, static_cast<uint64_t>(params.seed), target));
+  time_end();
+  LMC_CUDA(cudaGetLastError());
+  int32_t err = 0;
+  int aborted = 0;
+  unsigned long long sweep_end = 0;
+  LMC_CUDA(cudaMemcpyAsync(&err, d_cmc_error, 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(&aborted, d_dom_abort, 4, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaMemcpyAsync(&sweep_end, d_dom_counters + 2, 8, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  if (aborted) {
+    cmc_ready = false;
+    throw std::runtime_error("CMC domain run: barrier / peer exchange timed out (a peer rank is missing or out of step)");
+  }
+  if (err) {
+    cmc_ready = false;
+    throw std::out_of_range("CMC: Cluster not found in ClusterIndexer (two vacancies within interaction range)");
+  }
+  // the occupancy now lives in the buffer the next sweep would read; its periodic halo images are refreshed for the other kernels
+  occ_cur = (static_cast<int>(sweep_end & 1ULL) + phase) & 1;
+  d_occ = d_occ_buf[occ_cur];
+  {
+    const unsigned blocks = static_cast<unsigned>((lat.padded_size + 255) / 256);
+    for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
+      const unsigned ny = static_cast<unsigned>(std::min(32768, n_walkers - w0));
+      dom_refresh_halo_kernel<<<dim3(blocks, ny), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(w0) * lat.padded_size);
+      ++launch_count;
+    }
+    LMC_CUDA(cudaGetLastError());
+  }
+  cmc_cells_stale = true;
+}
+
 // ------------------------------------------------------------------------------------------------ CMC / SA driver
 void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps) {
   require_device();
@@ -960,22 +1207,10 @@ void Engine::cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps)
   LMC_CUDA(cudaMemsetAsync(d_cmc_steps, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_accepted, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_proposals, 0, nw * 8, stream));
+  if (d_dom_counters) LMC_CUDA(cudaMemsetAsync(d_dom_counters + 2, 0, 8, stream));   // sweep counter of the domain driver
   LMC_CUDA(cudaMemsetAsync(d_cmc_epoch, 0, nw * 8, stream));
   LMC_CUDA(cudaMemsetAsync(d_cmc_error, 0, nw * 4, stream));
-  {
-    const unsigned blocks = static_cast<unsigned>((lat.num_sites + 255) / 256);
-    for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
-      const unsigned ny = static_cast<unsigned>(std::min(32768, n_walkers - w0));
-      cmc_mirror_kernel<<<dim3(blocks, ny), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(w0) * lat.padded_size,
-                                                              d_cmc_mirror + static_cast<int64_t>(w0) * lat.num_sites);
-      ++launch_count;
-    }
-    // claim marks cleared, species bytes copied: the packed cell array of the CMC kernels
-    const int64_t n_cells = static_cast<int64_t>(n_walkers) * lat.padded_size;
-    cmc_cells_init_kernel<<<static_cast<unsigned>((n_cells + 255) / 256), 256, 0, stream>>>(n_cells, d_occ, d_cmc_marks);
-    ++launch_count;
-    LMC_CUDA(cudaGetLastError());
-  }
+  cmc_sync_cells();
   // SimulatedAnnealing constructor (mc/src/SimulatedAnnealing.cpp:53-56; ratios mc/include/SimulatedAnnealing.h:45-57)
   SaSchedule sa{};
   sa.enabled = sa_maximum_steps > 0 ? 1 : 0;
@@ -1002,6 +1237,7 @@ void Engine::cmc_run(const lmc_cmc_params &params, int64_t n_trials, int32_t rep
     return;
   }
   if (!cmc_ready) cmc_reset(0.0, 0);
+  if (cmc_cells_stale) cmc_sync_cells();
   const size_t nw = static_cast<size_t>(n_walkers);
   std::vector<double> temps(nw, params.temperature);
   if (params.temperatures) std::copy(params.temperatures, params.temperatures + nw, temps.begin());
@@ -1359,6 +1595,25 @@ int lmc_cmc_grid_run(lmc_engine *engine, const lmc_cmc_params *params, int64_t n
     if (!params) throw std::invalid_argument("null params");
     engine->impl->cmc_grid_run(*params, n_trials);
   });
+}
+int lmc_cmc_domain_run(lmc_engine *engine, const lmc_cmc_params *params, const lmc_cmc_domain_params *domain, int64_t n_trials) {
+  return guard([&] {
+    if (!params) throw std::invalid_argument("null params");
+    engine->impl->cmc_domain_run(*params, domain, n_trials);
+  });
+}
+int lmc_cmc_domain_handles(lmc_engine *engine, void *handles192) {
+  return guard([&] { engine->impl->cmc_domain_handles(handles192); });
+}
+int lmc_cmc_domain_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles) {
+  return guard([&] { engine->impl->cmc_domain_attach_peers(rank, world, handles); });
+}
+int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape6) {
+  if (!engine || !shape6) return LMC_ERR_INVALID_ARGUMENT;
+  const auto &e = *engine->impl;
+  shape6[0] = e.dom_last_edge; shape6[1] = e.dom_last_domains; shape6[2] = e.dom_last_lanes; shape6[3] = e.dom_last_threads;
+  shape6[4] = e.dom_last_ctas; shape6[5] = e.dom_last_rounds;
+  return LMC_OK;
 }
 int lmc_cmc_exchange_handle(lmc_engine *engine, void *handle64) {
   return guard([&] { engine->impl->cmc_exchange_handle(handle64); });

@@ -16,6 +16,7 @@
 struct lmc_kmc_params;
 struct lmc_kmc_trace;
 struct lmc_cmc_params;
+struct lmc_cmc_domain_params;
 
 namespace lmc {
 
@@ -64,6 +65,12 @@ class Engine {
   void cmc_exchange_handle(void *handle64);
   void cmc_attach_peers(int32_t rank, int32_t world, const void *handles, int32_t grid_ctas);
   void cmc_grid_run(const lmc_cmc_params &params, int64_t n_trials);
+  // domain-decomposed ("sublattice") driver (cmc_domain_kernels.cuh)
+  void cmc_domain_prepare();
+  void cmc_domain_handles(void *handles192);
+  void cmc_domain_attach_peers(int32_t rank, int32_t world, const void *handles);
+  void cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_params *dom, int64_t n_trials);
+  void cmc_sync_cells();                           // rebuild the batched drivers' mirror / cell arrays after the occupancy changed under them
 
   // host-side geometry (no device needed)
   void neighbors(int32_t shell, int64_t site, int64_t *out) const;
@@ -125,6 +132,19 @@ class Engine {
   int cmc_grid_checked_threads{0};
   size_t cmc_grid_checked_smem{0};
   const void *cmc_grid_checked_kernel{nullptr};
+  // domain-decomposed driver: second occupancy buffer, sweep-parity state, totals, inter-GPU lines
+  uint8_t *d_occ_buf[2]{nullptr, nullptr};         // d_occ is always d_occ_buf[occ_cur] once the driver has been prepared
+  int occ_cur{0};
+  void *d_dom_state{nullptr};                      // DomState[2][n_walkers]
+  unsigned long long *d_dom_accum{nullptr};        // [3][n_walkers][4]
+  void *d_dom_lines{nullptr};                      // DomLine[2][8] (IPC-shareable)
+  unsigned long long *d_dom_counters{nullptr};     // [0] grid barrier counter, [1] inter-GPU line sequence
+  int *d_dom_abort{nullptr};
+  uint8_t *dom_peer_occ[2][8]{};                   // peer mappings of both occupancy buffers ([.][rank] = own)
+  void *dom_peer_lines[8]{};
+  int dom_world{1}, dom_rank{0};
+  bool cmc_cells_stale{false};
+  int dom_last_lanes{0}, dom_last_threads{0}, dom_last_ctas{0}, dom_last_domains{0}, dom_last_rounds{0}, dom_last_edge{0};
   std::map<int, int> attr_cache;
   int device_attr(int attr);
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches

@@ -88,3 +88,25 @@ def attach_cmc_peers(engine, rank: int, world: int, sm_count: int | None = None)
     engine.cmc_attach_peers(rank, world, [g[0] for g in gathered], grid_ctas)
     dist.barrier()
     return grid_ctas
+
+
+def domain_slab(n_domains_x: int, rank: int, world: int):
+    """(first, count) of the x slab of the domain grid owned by `rank` in the domain-decomposed CMC / SA driver
+    (cmc_domain_kernels.cuh: `domain_slab_begin(ndx, world, r) = ndx * r / world`)."""
+    first = (int(n_domains_x) * int(rank)) // int(world)
+    return first, (int(n_domains_x) * (int(rank) + 1)) // int(world) - first
+
+
+def attach_cmc_domain_peers(engine, rank: int, world: int):
+    """Collective set-up of the multi-GPU domain-decomposed CMC / SA driver (include/lmc_b200.h,
+    lmc_cmc_domain_attach_peers): all-gather the 192-byte CUDA IPC handle blobs (two occupancy buffers + line buffer),
+    attach, barrier."""
+    import torch.distributed as dist
+    blob = engine.cmc_domain_handles()
+    if world == 1 or not (dist.is_available() and dist.is_initialized()):
+        engine.cmc_domain_attach_peers(0, 1, [blob])
+        return
+    gathered = [None] * world
+    dist.all_gather_object(gathered, bytes(blob))
+    engine.cmc_domain_attach_peers(rank, world, gathered)
+    dist.barrier()

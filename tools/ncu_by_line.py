@@ -33,6 +33,7 @@ def line_table(kernel):
 def main():
     rep, kernel = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    by_source_order = len(sys.argv) > 4            # 4th argument: divisor (e.g. warp-rounds) -> listing in source order, counts / divisor
     raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[1]
@@ -50,6 +51,19 @@ def main():
         total += n
     tot_s = sum(samples.values())
     print("total warp instructions %d, samples %d" % (total, tot_s))
+    if by_source_order:
+        div = float(sys.argv[4])
+        for loc, n in sorted(per_line.items(), key=lambda kv: kv[0] or ("", 0)):
+            if n / div < 1.0:
+                continue
+            src = ""
+            if loc:
+                try:
+                    src = open(os.path.join(ROOT, "latticemontecarlo_b200", "csrc", loc[0])).read().splitlines()[loc[1] - 1].strip()
+                except Exception:
+                    pass
+            print("%8.1f inst %6.2f%% samp  %s:%s  %s" % (n / div, 100.0 * samples[loc] / max(tot_s, 1), loc[0] if loc else "?", loc[1] if loc else "?", src[:110]))
+        return
     for loc, n in per_line.most_common(top):
         src = ""
         if loc:
@@ -60,4 +74,5 @@ def main():
         print("%6.2f%% inst %6.2f%% samp  %s:%s  %s" % (100.0 * n / total, 100.0 * samples[loc] / max(tot_s, 1), loc[0] if loc else "?", loc[1] if loc else "?", src[:110]))
 
 
-main()
+if __name__ == "__main__":
+    main()
