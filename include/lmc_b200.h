@@ -262,15 +262,21 @@ int lmc_cmc_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const 
 typedef struct lmc_cmc_domain_params {
   int32_t domain_edge;             /* target domain edge in half lattice constants, 4..48 (0 = 8) */
   int32_t rounds_per_sweep;        /* Metropolis rounds per domain and sweep (0 = (domain_edge - 2)^3, two per core site) */
-  int32_t tries_per_round;         /* candidate draws per round, each `lanes` pairs (0 = 4); a round without an unlike pair idles */
-  int32_t lanes;                   /* lanes per domain: 2, 4, 8, 16 or 32 (0 = from the number of domains); the random stream,
-                                    * hence the trajectory, depends on it */
+  int32_t speculate;               /* rounds of one domain evaluated at once on the current state and committed up to the first
+                                    * accepted one: 1, 2 (with 8 or 16 lanes) or 4 (with 8 lanes); 0 = 32 / lanes when the lattice
+                                    * has fewer domains than the GPU has warp slots, else 1.  Exactly the sequential chain */
+  int32_t lanes;                   /* lanes per trial: 2, 4, 8, 16 or 32 (0 = from the number of domains).  Launch shape only:
+                                    * the random stream is keyed by (seed, sweep, domain, round), the trajectory does not
+                                    * depend on it (up to the rounding of dE in the last bit) */
+  double passes;                   /* domains per lane group and sweep, handed out dynamically (0 = 1; > 1 trades resident
+                                    * groups for load balance when the domains differ in cost).  Launch shape only */
 } lmc_cmc_domain_params;
 int lmc_cmc_domain_run(lmc_engine *engine, const lmc_cmc_params *params, const lmc_cmc_domain_params *domain, int64_t n_trials);
 int lmc_cmc_domain_handles(lmc_engine *engine, void *handles192);
 int lmc_cmc_domain_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles);
-/* launch shape of the last lmc_cmc_domain_run: {domain_edge, domains, lanes, threads per block, blocks, rounds per sweep} */
-int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape6);
+/* launch shape of the last lmc_cmc_domain_run: {domain_edge, domains, lanes, threads per block, blocks, rounds per sweep,
+ * speculate} */
+int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape7);
 /* replay mode on replica `walker`: the n trials (site_a, site_b, u) are applied in the given order with the reference's
  * serial semantics (u is consumed only when dE >= 0).  Outputs (host, [n], optional): dE, energy and temperature before
  * each trial, accept flags. */

@@ -13,11 +13,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "liblmc_b200.so")
-SOURCES = ["engine.cu", "tables.cpp"]
+SOURCES = ["engine.cu", "cmc_domain.cu", "tables.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "lmc_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function", "-ccbin", "/usr/bin/g++", "--expt-relaxed-constexpr"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 CLI_SRC = os.path.join(CSRC, "host", "lmc_cli.cpp")
@@ -44,17 +45,41 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """One object per source (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
     if not force and not needs_build():
         build_cli()
         return OUT
+    from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get("LMC_NVCC_EXTRA", "").split()          # e.g. -DLMC_CMC_PROFILE for the clock64 phase profile
-    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    newest_header = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    stamp = os.path.join(OBJ_DIR, "flags.txt")
+    flags_text = " ".join(FLAGS + extra)
+    same_flags = os.path.exists(stamp) and open(stamp).read() == flags_text
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC, src)
+        if not force and same_flags and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), newest_header):
+            return obj, ""
+        cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed compiling " + src)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    with open(stamp, "w") as f:
+        f.write(flags_text)
+    if verbose:
+        for _, err in results:
+            sys.stderr.write(err)
+    res = subprocess.run([NVCC, "--shared", "-ccbin", "/usr/bin/g++"] + [o for o, _ in results] + ["-o", OUT], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building liblmc_b200.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc failed linking liblmc_b200.so")
     build_cli(force=True)
     return OUT
 

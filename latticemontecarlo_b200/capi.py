@@ -135,7 +135,8 @@ class CmcParams(C.Structure):
 
 
 class CmcDomainParams(C.Structure):
-    _fields_ = [("domain_edge", C.c_int32), ("rounds_per_sweep", C.c_int32), ("tries_per_round", C.c_int32), ("lanes", C.c_int32)]
+    _fields_ = [("domain_edge", C.c_int32), ("rounds_per_sweep", C.c_int32), ("speculate", C.c_int32), ("lanes", C.c_int32),
+                ("passes", C.c_double)]
 
 
 class Engine:
@@ -367,18 +368,18 @@ class Engine:
         _check(lib().lmc_cmc_grid_run(self.h, C.byref(prm), C.c_int64(int(n_trials))))
 
     def cmc_domain_run(self, n_trials, temperature=800.0, temperatures=None, seed=0, domain_edge=0, rounds_per_sweep=0,
-                       tries_per_round=0, lanes=0):
+                       speculate=0, lanes=0, passes=0.0):
         """Domain-decomposed ("sublattice") CMC / SA driver: lmc_cmc_domain_run (one lattice or many replicas; after
         cmc_domain_attach_peers one lattice over several GPUs)."""
         keep = []
         prm = self._cmc_params(temperature, temperatures, seed, 0, keep)
-        dom = CmcDomainParams(int(domain_edge), int(rounds_per_sweep), int(tries_per_round), int(lanes))
+        dom = CmcDomainParams(int(domain_edge), int(rounds_per_sweep), int(speculate), int(lanes), float(passes))
         _check(lib().lmc_cmc_domain_run(self.h, C.byref(prm), C.byref(dom), C.c_int64(int(n_trials))))
 
     def cmc_domain_last_shape(self):
-        out = (C.c_int32 * 6)()
+        out = (C.c_int32 * 7)()
         _check(lib().lmc_cmc_domain_last_shape(self.h, out))
-        return dict(zip(("domain_edge", "domains", "lanes", "threads", "blocks", "rounds_per_sweep"), (int(v) for v in out)))
+        return dict(zip(("domain_edge", "domains", "lanes", "threads", "blocks", "rounds_per_sweep", "speculate"), (int(v) for v in out)))
 
     def cmc_domain_handles(self):
         """192 bytes: CUDA IPC handles of the two occupancy buffers and the line buffer (to be all-gathered over the ranks)."""

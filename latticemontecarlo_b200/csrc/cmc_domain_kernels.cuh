@@ -30,44 +30,12 @@
 // travel as flag-in-data lines (cmc_grid_kernels.cuh), which double as the inter-GPU barrier.  All decisions are keyed by
 // (seed, sweep, domain), so the trajectory is identical for every world size.
 #pragma once
-#include "cmc_grid_kernels.cuh"
+#include <cuda_runtime.h>
+
+#include "cmc_domain.h"
+#include "device_common.h"
 
 namespace lmc {
-
-constexpr int kDomMaxWalkers = 2048;     // replicas one launch can drive (per-replica temperature lives in shared memory)
-constexpr int kDomMaxThreads = 1024;
-constexpr int kDomPidxBytes = (kSiteEnvN * kSiteEnvN + 15) & ~15;
-
-struct DomState {                        // per-replica chain state between sweeps
-  double energy;
-  unsigned long long steps, accepted;
-  double temperature;                    // fixed temperature (CMC) or the schedule's current one (SA)
-  SaSchedule sa;
-};
-
-struct DomLine { unsigned long long v[4]; unsigned long long flag; unsigned long long pad[3]; };   // 64 bytes
-
-struct CmcDomainParams {
-  int ndx, ndy, ndz;                     // domains per axis
-  int tile_y, tile_zh;                   // tile strides: index = (tx * tile_y + ty) * tile_zh + (tz >> 1)
-  int tile_cells;                        // bytes of the tile proper (multiple of 16)
-  int tile_bytes;                        // shared memory per lane group: tile + 2 species rows (96 B) + solute list (2 B per core site)
-  int max_core;                          // largest core of any domain (sites)
-  int rounds, tries;                     // Metropolis rounds per domain and sweep; candidate draws per round
-  int n_walkers;
-  int world, rank;
-  uint8_t *occ[2];                       // double-buffered occupancy, padded layout, [walker][padded_size]
-  uint8_t *peer_occ[2][kGridMaxWorld];   // the same buffers of every rank (peer mappings; [.][rank] = own)
-  DomState *state;                       // [2][n_walkers]
-  unsigned long long *accum;             // [3][n_walkers][4]: sum dE (2^-44 eV fixed point), trials, accepted, errors
-  DomLine *lines;                        // [2][world] sweep totals of every rank (multi-GPU; written by the peers)
-  DomLine *peer_lines[kGridMaxWorld];
-  unsigned long long *barrier_counter;
-  int *abort_flag;
-  long long spin_limit;
-  unsigned long long *sweep;             // sweeps done so far (persists over launches; Philox counter)
-  unsigned long long *line_seq;          // inter-GPU line sequence (never reset while the peers are attached)
-};
 
 // ---- Philox4x32-10 with a full 128-bit counter
 __device__ __forceinline__ void philox4x32_10_c4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
@@ -93,12 +61,6 @@ __device__ __forceinline__ void domain_shift(uint64_t seed, unsigned long long s
   sy = static_cast<int>(__umulhi(r[1], static_cast<uint32_t>(py)));
   sz = static_cast<int>(__umulhi(r[2], static_cast<uint32_t>(pz)));
 }
-
-// first x index (inclusive) of rank r's slab of the domain grid
-__host__ __device__ __forceinline__ int domain_slab_begin(int ndx, int world, int r) { return static_cast<int>((static_cast<long long>(ndx) * r) / world); }
-// lower bound (inclusive) of domain i along an axis of `period` half-units cut into nd parts (z: even bounds, see below)
-__host__ __device__ __forceinline__ int domain_lo(int i, int period, int nd) { return static_cast<int>((static_cast<long long>(i) * period) / nd); }
-__host__ __device__ __forceinline__ int domain_lo_z(int i, int fz, int nd) { return 2 * static_cast<int>((static_cast<long long>(i) * fz) / nd); }
 
 __device__ __forceinline__ bool dom_grid_barrier(const CmcDomainParams &dp, unsigned long long &target, unsigned n_cta) {
   __syncthreads();
@@ -192,7 +154,7 @@ __device__ __forceinline__ bool dom_intergpu_sum(const CmcDomainParams &dp, unsi
   const int parity = static_cast<int>(seq & 1ULL);
   if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < dp.world) {
     const ulonglong2 v0 = __ldcg(reinterpret_cast<const ulonglong2 *>(mine)), v1 = __ldcg(reinterpret_cast<const ulonglong2 *>(mine) + 1);
-    DomLine *dst = dp.peer_lines[threadIdx.x] + parity * kGridMaxWorld + dp.rank;
+    DomLine *dst = dp.peer_lines[threadIdx.x] + parity * kDomWorldMax + dp.rank;
     dst->v[0] = v0.x; dst->v[1] = v0.y; dst->v[2] = v1.x; dst->v[3] = v1.y;
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&dst->flag), "l"(seq) : "memory");
@@ -202,7 +164,7 @@ __device__ __forceinline__ bool dom_intergpu_sum(const CmcDomainParams &dp, unsi
     int ok = 1;
     const long long t0 = clock64();
     for (int p = 0; p < dp.world && ok; ++p) {
-      const DomLine *src = dp.lines + parity * kGridMaxWorld + p;
+      const DomLine *src = dp.lines + parity * kDomWorldMax + p;
       for (;;) {
         unsigned long long f;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(f) : "l"(&src->flag) : "memory");
@@ -220,29 +182,47 @@ __device__ __forceinline__ bool dom_intergpu_sum(const CmcDomainParams &dp, unsi
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// The sweep kernel.  L lanes per trial side, G = 2 L lanes per domain; kStagedB: pair table B staged in shared memory.
+// The sweep kernel.  L lanes per trial side, G = 2 L lanes per trial, S trials of one domain in flight (a TEAM of
+// T = S G <= 32 lanes owns a domain).
+//
+// Speculation (S > 1).  A domain's rounds form one sequential Markov chain, so a lattice with few domains (40^3: 1000) runs
+// at the latency of ONE dependent round per domain.  But only ~10 % of the trials are accepted, and a rejected trial leaves
+// the state untouched: the S groups of a team evaluate rounds r0 .. r0 + S - 1 at once, all on the current state, and the
+// team commits them up to and including the first accepted one; later rounds of the batch are discarded and drawn again
+// (their random numbers are a function of the round index, so the redo sees the same draws).  This is exactly the
+// sequential chain -- the trajectory does not depend on S.
+//
+// kTab == 1: DIFFERENCE tables in shared memory.  Both sites of a swap change between the same two species x_lo < x_hi, one
+// in each direction, so the walk needs D = T[x_hi] - T[x_lo] only (one lookup and one add per term instead of two; the
+// direction is a sign).  In the delta form solvent sites never enter a walk, so D is stored for non-solvent environment
+// species only: m (m - 1) / 2 species pairs x (1 + 42 (m - 1) + 204 (m - 1)^2) doubles -- 94 KB for a ternary alloy with
+// vacancy, less than the pair table itself.  The sums are the same terms in the same order (negation is exact), so both
+// table forms give bit-identical dE.  kTab == 0: A staged, B through the read-only path (more species than fit).
 //
 // Proposal.  The reference draws two uniform sites until their species differ (CanonicalMcAbstract.cpp:43-51), i.e. every
 // unordered unlike pair is equally likely.  In a dilute alloy 92 % of such draws are solvent-solvent, so the same
 // distribution is sampled from the other end: every unlike pair holds at least one NON-SOLVENT site, hence
-//     a uniform from the domain's list of non-solvent core sites (built at tile load, updated on accepted swaps),
+//     a from the domain's list of non-solvent core sites (built at tile load, updated on accepted swaps),
 //     b uniform from all core sites, redrawn while species(a) == species(b),
 //     and a pair of two (different) non-solvent species -- which can be drawn from either end -- kept with probability 1/2
-// gives every unordered unlike pair of the core the same probability 1 / (S * ncore) per draw.  One Philox call per
+// gives every unordered unlike pair of the core the same probability 1 / (S_list * ncore) per draw.  One Philox call per
 // draw, keyed by (seed, sweep, domain, round, try): the random stream does not depend on the launch shape.
-template <int L, bool kStagedB>
-__global__ void __launch_bounds__(kDomMaxThreads, 1)
+constexpr int kDomTries = 4;
+template <int L, int kTab, int kMaxThreads, int S>
+__global__ void __launch_bounds__(kMaxThreads, 1)
 cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState st, uint64_t seed, unsigned long long target_steps) {
-  constexpr int G = 2 * L;
-  constexpr unsigned kGroupBits = G >= 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+  constexpr int G = 2 * L, T = S * G;
+  static_assert(T <= 32 && (32 % T) == 0, "a team is a power-of-two slice of a warp");
+  constexpr unsigned kTeamBits = T >= 32 ? 0xFFFFFFFFu : ((1u << T) - 1u);
   constexpr unsigned kSideBits = (1u << L) - 1u;
+  constexpr unsigned kLeaders = G >= 32 ? 1u : 0xFFFFFFFFu / ((1u << (G % 32)) - 1u);     // lane 0 of every group of a warp
   const int n_cta = static_cast<int>(gridDim.x), cta = static_cast<int>(blockIdx.x);
   const int tid = threadIdx.x, B = blockDim.x, lane = tid & 31;
-  const int gl = lane % G, gb = lane - gl;                 // lane within the group, first lane of the group
+  const int tl = lane % T, tb = lane - tl;                 // lane within the team, first lane of the team
+  const int grp = tl / G, gl = tl % G;                     // speculative slot of this lane's group, lane within the group
   const int side = gl / L, sub = gl % L;
-  const unsigned group_mask = kGroupBits << gb;
-  const int side_shift = gb + side * L;
-  const int groups_per_cta = B / G, group_in_cta = tid / G;
+  const int side_shift = tb + grp * G + side * L;
+  const int team_in_cta = tid / T;
   const int nw = dp.n_walkers;
   const int m = tab.n_species + 1, mm = m * m;
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac = static_cast<unsigned>(tab.n_species);
@@ -251,26 +231,58 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
   __shared__ unsigned long long s_tot[4];
   __shared__ int s_done, s_fail, s_ok2;
   __shared__ unsigned long long s_sum[4];
-  // dynamic shared memory, fixed-size tables first (constant offsets): [mask 42 x 8] [pidx 42 x 42] [tdelta 2 x 44 x 2] [C: m] [A: m*42*m]
-  // [B: m*204*m*m, optional] [temperature: nw] [group tiles: tile | species rows 2 x 48 | solute list]
+  // dynamic shared memory, fixed-size tables first (constant offsets): [mask 42 x 8] [pidx 42 x 42] [tdelta 2 x 44 x 2] [sp: 64]
+  // then kTab == 0: [C: m] [A: m*42*m]   kTab == 1: [dC: n_sp] [DA: n_sp*42*ns] [DB: n_sp*204*ns*ns]
+  // then [temperature: nw] [team tiles: tile | species rows S x 2 x 48 | solute list]
   extern __shared__ double s_dyn[];
   uint64_t *s_mask = reinterpret_cast<uint64_t *>(s_dyn);
   uint8_t *s_pidx = reinterpret_cast<uint8_t *>(s_mask + kSiteEnvN);
   int16_t *s_tdelta = reinterpret_cast<int16_t *>(s_pidx + kDomPidxBytes);
-  double *s_C = reinterpret_cast<double *>(s_tdelta + 2 * 44);
-  double *s_A = s_C + m;
-  const int a_len = m * kSiteEnvN * m, b_len = m * tab.n_site_pairs * mm;
+  uint8_t *s_sp = reinterpret_cast<uint8_t *>(s_tdelta + 2 * 44);   // [x_old * m + x_new] -> species-pair index | 0x80 if x_old > x_new
+  double *s_C = reinterpret_cast<double *>(s_sp + 64);
+  const int ns = m - 1, ns2 = ns * ns, n_sp = m * (m - 1) / 2;
+  const int a_len = kTab ? n_sp * kSiteEnvN * ns : m * kSiteEnvN * m, b_len = kTab ? n_sp * tab.n_site_pairs * ns2 : 0;
+  const int c_len = kTab ? n_sp : m;
+  double *s_A = s_C + c_len;
   double *s_B = s_A + a_len;
-  double *s_temp = s_B + (kStagedB ? b_len : 0);
+  double *s_temp = s_B + b_len;
   uint8_t *s_tiles = reinterpret_cast<uint8_t *>(s_temp + nw);
-  uint8_t *tile = s_tiles + static_cast<size_t>(group_in_cta) * dp.tile_bytes;
-  uint8_t *row = tile + dp.tile_cells + side * 48;        // species of this side's 42 environment sites
-  uint16_t *list = reinterpret_cast<uint16_t *>(tile + dp.tile_cells + 96);   // core indices of the non-solvent core sites
+  uint8_t *tile = s_tiles + static_cast<size_t>(team_in_cta) * dp.tile_bytes;
+  uint8_t *row = tile + dp.tile_cells + (grp * 2 + side) * 48;   // species of this side's 42 environment sites
+  uint16_t *list = reinterpret_cast<uint16_t *>(tile + dp.tile_cells + S * 96);   // core indices of the non-solvent core sites
 
-  for (int q = tid; q < m; q += B) s_C[q] = tab.site_C[q];
-  for (int q = tid; q < a_len; q += B) s_A[q] = tab.site_A[q];
-  if (kStagedB)
-    for (int q = tid; q < b_len; q += B) s_B[q] = tab.site_B[q];
+  for (int q = tid; q < m * m; q += B) {
+    const int xo = q / m, xn = q % m, lo = xo < xn ? xo : xn, hi = xo < xn ? xn : xo;
+    s_sp[q] = static_cast<uint8_t>((lo * m - lo * (lo + 1) / 2 + (hi - lo - 1)) | (xo > xn ? 0x80 : 0));
+  }
+  if (kTab) {
+    // species pair sp = (lo < hi); non-solvent species index e' = e - (e > solvent)
+    for (int q = tid; q < n_sp + a_len + b_len; q += B) {
+      int r = q, which = 0;
+      if (r >= n_sp) { r -= n_sp; which = 1; }
+      if (which == 1 && r >= a_len) { r -= a_len; which = 2; }
+      const int per_sp = which == 0 ? 1 : (which == 1 ? kSiteEnvN * ns : tab.n_site_pairs * ns2);
+      const int sp = r / per_sp, rest = r - sp * per_sp;
+      int lo = 0, acc = 0;
+      while (acc + (m - 1 - lo) <= sp) { acc += m - 1 - lo; ++lo; }
+      const int hi = lo + 1 + (sp - acc);
+      double v;
+      if (which == 0) v = tab.site_C[hi] - tab.site_C[lo];
+      else if (which == 1) {
+        const int t = rest / ns, e1 = rest % ns, e = e1 + (e1 >= static_cast<int>(solvent));
+        v = tab.site_A[(hi * kSiteEnvN + t) * m + e] - tab.site_A[(lo * kSiteEnvN + t) * m + e];
+      } else {
+        const int pr = rest / ns2, e12 = rest % ns2, e1 = e12 / ns, e2_ = e12 % ns;
+        const int ea_ = e1 + (e1 >= static_cast<int>(solvent)), eb_ = e2_ + (e2_ >= static_cast<int>(solvent));
+        const size_t b_stride = static_cast<size_t>(tab.n_site_pairs) * mm;
+        v = tab.site_B[hi * b_stride + (pr * m + ea_) * m + eb_] - tab.site_B[lo * b_stride + (pr * m + ea_) * m + eb_];
+      }
+      s_C[q] = v;      // dC, DA, DB are contiguous
+    }
+  } else {
+    for (int q = tid; q < m; q += B) s_C[q] = tab.site_C[q];
+    for (int q = tid; q < a_len; q += B) s_A[q] = tab.site_A[q];
+  }
   for (int q = tid; q < kSiteEnvN; q += B) s_mask[q] = tab.site_mask_hi[q];
   for (int q = tid; q < kSiteEnvN * kSiteEnvN; q += B) {
     const int t = q / kSiteEnvN, u = q % kSiteEnvN;
@@ -283,15 +295,14 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
     const int dx = tab.site_off[4 * t], dy = tab.site_off[4 * t + 1], dz = tab.site_off[4 * t + 2];
     s_tdelta[zp * 44 + t] = static_cast<int16_t>((dx * TY + dy) * TZH + (((zp + dz + 8) >> 1) - ((zp + 8) >> 1)));
   }
-  const double *Bt = kStagedB ? s_B : tab.site_B;
+  const unsigned own_lo = static_cast<unsigned>(dp.own_mask[sub]), own_hi = static_cast<unsigned>(dp.own_mask[sub] >> 32);
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
   const int world = dp.world, rank = dp.rank;
   const int ix_lo = domain_slab_begin(dp.ndx, world, rank), ix_hi = domain_slab_begin(dp.ndx, world, rank + 1);
   const int nd_yz = dp.ndy * dp.ndz, nd_rank = (ix_hi - ix_lo) * nd_yz, nd_total = dp.ndx * nd_yz;
   const int n_items = nw * nd_rank;
-  const int groups_total = n_cta * groups_per_cta;
-  const int gid = cta * groups_per_cta + group_in_cta;
-  const int safe_idx = (2 * TY + 2) * TZH + 1;            // a core cell of every tile: gather base of lane groups without a trial
+  const int safe_idx = (2 * TY + 2) * TZH + 1;            // a core cell of every tile: gather base of groups without a trial
+  const int rounds = dp.rounds;
   unsigned long long sweep = *dp.sweep;
   unsigned long long line_seq = world > 1 ? *dp.line_seq : 0ULL;
   unsigned long long bar_target = 0;
@@ -351,10 +362,11 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       }
       break;
     }
-    // the totals buffer of the sweep after this one was last read in the previous prologue: clear it now
+    // the totals buffer (and the domain queue) of the sweep after this one were last used one sweep ago: clear them now
     if (cta == 0) {
       unsigned long long *acc_clear = dp.accum + static_cast<size_t>((sweep + 1) % 3ULL) * nw * 4;
       for (int q = tid; q < nw * 4; q += B) acc_clear[q] = 0ULL;
+      if (tid == 0) dp.queue[(sweep + 1) % 3ULL] = 0u;
     }
     unsigned long long *acc_now = dp.accum + static_cast<size_t>(sweep % 3ULL) * nw * 4;
     const uint8_t *src_occ = dp.occ[sweep & 1ULL];
@@ -365,11 +377,16 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
     if (world > 1) domain_shift(seed, sweep + 1, px, py, pz, nsx, nsy, nsz);
     (void)nsy; (void)nsz;
 
-    long long my_fixed = 0;                     // group leader: totals of this group's domains (n_walkers == 1: summed per CTA)
+    long long my_fixed = 0;                     // team leader: totals of this team's domains (n_walkers == 1: summed per CTA)
     unsigned int my_kept = 0, my_acc = 0;
-    for (int item0 = 0; item0 < n_items; item0 += groups_total) {
-      const int item = item0 + gid;
+    unsigned int *queue = dp.queue + sweep % 3ULL;
+    for (;;) {
+      // next domain of the sweep: handed out dynamically (teams that drew cheap domains take more)
+      int item = 0;
+      if (tl == 0) item = static_cast<int>(atomicAdd(queue, 1u));
+      item = __shfl_sync(0xffffffffu, item, tb);
       const bool has_item = item < n_items;
+      if (!__any_sync(0xffffffffu, has_item)) break;
       int w = 0, ix = 0, iy = 0, iz = 0;
       if (has_item) {
         w = item / nd_rank;
@@ -386,7 +403,7 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       // ---- load the tile: (Dx + 2) x (Dy + 2) rows of (Dz + 2) / 2 sites
       if (has_item) {
         const int n_rows = (Dx + 2) * (Dy + 2), nk = (Dz + 2) >> 1;
-        for (int r = gl; r < n_rows; r += G) {
+        for (int r = tl; r < n_rows; r += T) {
           const int tx = r / (Dy + 2), ty = r - tx * (Dy + 2);
           int X = gx0 + tx; X -= X >= px ? px : 0; X -= X >= px ? px : 0;
           int Y = gy0 + ty; Y -= Y >= py ? py : 0; Y -= Y >= py ? py : 0;
@@ -416,12 +433,12 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       };
       // ---- the non-solvent sites of the core, in core-index order
       uint32_t n_sol = 0;
-      for (uint32_t i0 = 0; i0 < static_cast<uint32_t>(dp.max_core); i0 += G) {
-        const uint32_t i = i0 + gl;
+      for (uint32_t i0 = 0; i0 < static_cast<uint32_t>(dp.max_core); i0 += T) {
+        const uint32_t i = i0 + tl;
         bool sol = false;
         if (i < ncore) sol = tile[tile_index(decode(i))] != solvent;
-        const unsigned bal = (__ballot_sync(0xffffffffu, sol) >> gb) & kGroupBits;
-        if (sol) list[n_sol + __popc(bal & ((1u << gl) - 1u))] = static_cast<uint16_t>(i);
+        const unsigned bal = (__ballot_sync(0xffffffffu, sol) >> tb) & kTeamBits;
+        if (sol) list[n_sol + __popc(bal & ((1u << tl) - 1u))] = static_cast<uint16_t>(i);
         n_sol += __popc(bal);
       }
       __syncwarp();
@@ -431,26 +448,54 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       long long fixed = 0;
       unsigned int kept = 0, acc = 0;
       const bool can_draw = n_sol > 0u && ncore > 1u;
-      for (int round = 0; round < dp.rounds; ++round) {
-        // -- draw (identical in every lane of the group: no communication)
+      // The first draw of a round is state independent up to the list lookup: lane j of the team draws for round blk + j,
+      // T rounds at a time (one Philox call per lane and T rounds), and a round's values are broadcast when it comes up.
+      uint32_t pre_kb = 0, pre_ulo = 0, pre_uhi = 0;
+      int r0 = can_draw ? 0 : rounds, blk = -T;              // next round to commit; first round of the drawn block
+      while (__any_sync(0xffffffffu, r0 < rounds)) {
+        if (r0 < rounds && r0 >= blk + T) {
+          blk += T;
+          uint32_t r[4];
+          philox4x32_10_c4(static_cast<uint32_t>((blk + tl) * kDomTries), item_global, static_cast<uint32_t>(sweep), static_cast<uint32_t>(sweep >> 32),
+                           static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
+          pre_kb = __umulhi(r[0], n_sol) | (__umulhi(r[1], ncore) << 16);     // list slot | core index of b
+          pre_ulo = r[2]; pre_uhi = r[3];
+        }
+        // this group's round of the batch; a batch does not run past the drawn block
+        const int my_round = r0 + grp;
+        const int limit = min(rounds, blk + T);
+        const bool active = my_round < limit;
+        // -- draw (identical in every lane of the group)
         bool found = false;
         uint32_t pa = 0, pb = 0, slot = 0, core_b = 0, u_lo = 0, u_hi = 0;
         unsigned ea = solvent, eb = solvent;
-        for (int tr = 0; tr < dp.tries; ++tr) {
-          if (can_draw && !found) {
+        {
+          const int src = active ? tb + (my_round - blk) : lane;
+          const uint32_t kb = __shfl_sync(0xffffffffu, pre_kb, src), w2 = __shfl_sync(0xffffffffu, pre_ulo, src), w3 = __shfl_sync(0xffffffffu, pre_uhi, src);
+          if (active) {
+            const uint32_t k = kb & 0xFFFFu, ib = kb >> 16;
+            const uint32_t qa_ = decode(list[k]), qb_ = decode(ib);
+            const unsigned ca = tile[tile_index(qa_)], cb = tile[tile_index(qb_)];
+            // unlike species; a pair of two non-solvent species is reachable from both ends: keep it with probability 1/2
+            // (bit 0 of the low word is below the 53 bits the uniform uses)
+            if (ca != cb && (cb == solvent || (w2 & 1u))) {
+              found = true; pa = qa_; pb = qb_; slot = k; core_b = ib; ea = ca; eb = cb; u_lo = w2; u_hi = w3;
+            }
+          }
+        }
+        for (int tr = 1; tr < kDomTries; ++tr) {    // redraws (like species, or a thinned non-solvent pair)
+          if (__all_sync(0xffffffffu, found || !active)) break;
+          if (active && !found) {
             uint32_t r[4];
-            philox4x32_10_c4(static_cast<uint32_t>(round * dp.tries + tr), item_global, static_cast<uint32_t>(sweep), static_cast<uint32_t>(sweep >> 32),
+            philox4x32_10_c4(static_cast<uint32_t>(my_round * kDomTries + tr), item_global, static_cast<uint32_t>(sweep), static_cast<uint32_t>(sweep >> 32),
                              static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32), r);
             const uint32_t k = __umulhi(r[0], n_sol), ib = __umulhi(r[1], ncore);
             const uint32_t qa_ = decode(list[k]), qb_ = decode(ib);
             const unsigned ca = tile[tile_index(qa_)], cb = tile[tile_index(qb_)];
-            // unlike species; a pair of two non-solvent species is reachable from both ends: keep it with probability 1/2
-            // (bit 0 of r[2] is below the 53 bits the uniform uses)
             if (ca != cb && (cb == solvent || (r[2] & 1u))) {
               found = true; pa = qa_; pb = qb_; slot = k; core_b = ib; ea = ca; eb = cb; u_lo = r[2]; u_hi = r[3];
             }
           }
-          if (__all_sync(0xffffffffu, found || !can_draw)) break;
         }
         // -- evaluate: EnergyChangePredictorPairSite::GetDeFromLatticeIdPair on the tile (L lanes per site).  Warp-uniform
         // control flow: groups without a trial gather around a dummy cell and discard the result.
@@ -480,7 +525,7 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
             const int at = base + drow[t];
             c = tile[at];
             if (at == override_index) c = e2;
-            if (t != kCentrePos) row[t - (t > kCentrePos)] = static_cast<uint8_t>(c);
+            if (t != kCentrePos) row[t - (t > kCentrePos)] = static_cast<uint8_t>(kTab ? c - (c > solvent) : c);
             else c = solvent;
           }
           const unsigned bits = (__ballot_sync(0xffffffffu, c != solvent) >> side_shift) & kSideBits;   // positions i L .. i L + L - 1
@@ -491,49 +536,64 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
         const uint64_t env = (m43 & 0x1FFFFFULL) | ((m43 >> 22) << 21);
         const unsigned lo = static_cast<unsigned>(env), hi = static_cast<unsigned>(env >> 32);
         __syncwarp();
-        const int x_old = static_cast<int>(side ? e2 : e1), x_new = static_cast<int>(side ? e1 : e2);
-        const int a_stride = kSiteEnvN * m, b_stride = tab.n_site_pairs * mm;
-        const double *A_new = s_A + x_new * a_stride, *A_old = s_A + x_old * a_stride;
-        const double *B_new = Bt + x_new * b_stride, *B_old = Bt + x_old * b_stride;
-        double de = sub == 0 ? s_C[x_new] - s_C[x_old] : 0.0;
-        constexpr unsigned kStripe = L >= 32 ? 1u : 0xFFFFFFFFu / ((1u << (L % 32)) - 1u);   // bits 0, L, 2L, ...
-        auto walk = [&](unsigned mine, int t0) {
-          while (mine) {
-            const int t = t0 + __ffs(static_cast<int>(mine)) - 1;
-            mine &= mine - 1;
-            const int et = row[t];
-            de += A_new[t * m + et] - A_old[t * m + et];
-            const uint64_t mask = s_mask[t];
-            unsigned plo = static_cast<unsigned>(mask) & lo, phi = static_cast<unsigned>(mask >> 32) & hi;
-            const uint8_t *prow = s_pidx + t * kSiteEnvN;
-            const int col = et * m;
-            while (plo) {
-              const int u = __ffs(static_cast<int>(plo)) - 1;
-              plo &= plo - 1;
-              const int p = prow[u] * mm + col + row[u];
-              de += kStagedB ? B_new[p] - B_old[p] : __ldg(B_new + p) - __ldg(B_old + p);
+        // Table walk over this lane's share of the non-solvent positions (tried and dropped: four partners at a time with
+        // predication and two accumulators -- more instructions than latency saved: -10 % at 40^3, -17 % at 100^3).
+        double de = 0.0;
+        auto walk_all = [&](auto single, auto pair) {
+          auto walk = [&](unsigned mine, int t0) {
+            while (mine) {
+              const int t = t0 + __ffs(static_cast<int>(mine)) - 1;
+              mine &= mine - 1;
+              const int et = row[t];
+              de += single(t, et);
+              const uint64_t mask = s_mask[t];
+              const uint8_t *prow = s_pidx + t * kSiteEnvN;
+              unsigned plo = static_cast<unsigned>(mask) & lo, phi = static_cast<unsigned>(mask >> 32) & hi;
+              while (plo) {
+                const int u = __ffs(static_cast<int>(plo)) - 1;
+                plo &= plo - 1;
+                de += pair(prow[u], et, row[u]);
+              }
+              while (phi) {
+                const int u = 32 + __ffs(static_cast<int>(phi)) - 1;
+                phi &= phi - 1;
+                de += pair(prow[u], et, row[u]);
+              }
             }
-            while (phi) {
-              const int u = 32 + __ffs(static_cast<int>(phi)) - 1;
-              phi &= phi - 1;
-              const int p = prow[u] * mm + col + row[u];
-              de += kStagedB ? B_new[p] - B_old[p] : __ldg(B_new + p) - __ldg(B_old + p);
-            }
-          }
+          };
+          walk(lo & own_lo, 0);
+          walk(hi & own_hi, 32);
         };
-        if (found) {
-          walk(lo & (kStripe << sub), 0);
-          walk(hi & (kStripe << sub), 32);
+        if (kTab) {
+          // difference tables: the species pair of the swap, the direction as a sign (side 1 changes the other way)
+          const unsigned spw = s_sp[e1 * m + e2];
+          const int sp = spw & 0x7F;
+          const double *DA = s_A + sp * (kSiteEnvN * ns), *DB = s_B + sp * (tab.n_site_pairs * ns2);
+          if (sub == 0) de = s_C[sp];
+          if (found)
+            walk_all([&](int t, int et) { return DA[t * ns + et]; },
+                     [&](int p, int et, int eu) { return DB[(p * ns + et) * ns + eu]; });
+          if (((spw >> 7) ^ static_cast<unsigned>(side)) & 1u) de = -de;
+        } else {
+          const int x_old = static_cast<int>(side ? e2 : e1), x_new = static_cast<int>(side ? e1 : e2);
+          const int a_stride = kSiteEnvN * m, b_stride = tab.n_site_pairs * mm;
+          const double *A_new = s_A + x_new * a_stride, *A_old = s_A + x_old * a_stride;
+          const double *B_new = tab.site_B + x_new * b_stride, *B_old = tab.site_B + x_old * b_stride;
+          if (sub == 0) de = s_C[x_new] - s_C[x_old];
+          if (found)
+            walk_all([&](int t, int et) { return A_new[t * m + et] - A_old[t * m + et]; },
+                     [&](int p, int et, int eu) { const int q = (p * m + et) * m + eu; return __ldg(B_new + q) - __ldg(B_old + q); });
         }
         __syncwarp();
 #pragma unroll
         for (int off = G / 2; off > 0; off >>= 1) de += __shfl_xor_sync(0xffffffffu, de, off);
+        bool accept = false;
         if (found) {
           if (de != de) err |= kErrExtraVacancy;
           // CanonicalMcAbstract::SelectEvent (:86-101): dE < 0 accepts, else u < exp(-dE beta).  The exponential is bracketed in
           // single precision first; the double-precision call only decides the (rare) draws inside the bracket, so the
           // decisions are those of the double-precision test
-          bool accept = de < 0.0;
+          accept = de < 0.0;
           if (!accept) {
             const double x = -de * beta, u = uniform53(u_lo, u_hi);
             const float ef = __expf(static_cast<float>(x));
@@ -541,15 +601,24 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
             accept = u < e_lo;
             if (!accept && !(u > e_hi)) accept = u < exp(x);
           }
-          ++kept;
-          if (accept) {
-            ++acc;
-            fixed += __double2ll_rn(de * kEnergyFixedScale);
-            if (gl == 0) {
-              tile[idx_a0] = static_cast<uint8_t>(eb); tile[idx_b0] = static_cast<uint8_t>(ea);
-              if (eb == solvent) list[slot] = static_cast<uint16_t>(core_b);     // the non-solvent atom now sits at b
-            }
+        }
+        // -- commit the batch up to and including its first accepted round
+        {
+          const unsigned acc_team = (__ballot_sync(0xffffffffu, accept) >> tb) & kTeamBits;
+          const unsigned found_team = (__ballot_sync(0xffffffffu, found) >> tb) & kTeamBits & kLeaders;
+          const int first = acc_team ? (__ffs(static_cast<int>(acc_team)) - 1) / G : S;      // slot of the first accepted round
+          const int n_active = max(0, min(S, limit - r0));
+          const int committed = min(first + 1, n_active);
+          kept += __popc(found_team & (committed * G >= 32 ? 0xFFFFFFFFu : ((1u << (committed * G)) - 1u)));
+          if (S > 1) {
+            const double de_first = __shfl_sync(0xffffffffu, de, tb + (first < S ? first : 0) * G);
+            if (first < S) { ++acc; fixed += __double2ll_rn(de_first * kEnergyFixedScale); }
+          } else if (first < S) { ++acc; fixed += __double2ll_rn(de * kEnergyFixedScale); }
+          if (grp == first && gl == 0) {
+            tile[idx_a0] = static_cast<uint8_t>(eb); tile[idx_b0] = static_cast<uint8_t>(ea);
+            if (eb == solvent) list[slot] = static_cast<uint16_t>(core_b);     // the non-solvent atom now sits at b
           }
+          if (r0 < rounds) r0 += committed;
         }
         __syncwarp();
       }
@@ -557,7 +626,7 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       if (has_item) {
         const int nk = Dz >> 1;
         const int n_rows = Dx * Dy;
-        for (int r = gl; r < n_rows; r += G) {
+        for (int r = tl; r < n_rows; r += T) {
           const int tx = r / Dy + 1, ty = r - (tx - 1) * Dy + 1;
           int X = gx0 + tx; X -= X >= px ? px : 0; X -= X >= px ? px : 0;
           int Y = gy0 + ty; Y -= Y >= py ? py : 0; Y -= Y >= py ? py : 0;
@@ -591,7 +660,7 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
             Z += 2; Z -= Z >= pz ? pz : 0;
           }
         }
-        if (gl == 0) {
+        if (tl == 0) {
           if (nw > 1) {
             if (fixed) atomicAdd(acc_now + 4 * w, static_cast<unsigned long long>(fixed));
             if (kept) atomicAdd(acc_now + 4 * w + 1, static_cast<unsigned long long>(kept));
@@ -605,8 +674,8 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
     }
     if (nw == 1) {
       // one lattice: totals per CTA through shared memory, then one set of global atomics
-      long long f = gl == 0 ? my_fixed : 0LL;
-      unsigned int k = gl == 0 ? my_kept : 0u, a = gl == 0 ? my_acc : 0u;
+      long long f = tl == 0 ? my_fixed : 0LL;
+      unsigned int k = tl == 0 ? my_kept : 0u, a = tl == 0 ? my_acc : 0u;
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         f += __shfl_xor_sync(0xffffffffu, f, off);

@@ -56,9 +56,6 @@ __device__ __forceinline__ bool line_wait(const CmcLine *src, unsigned flag, uns
   }
 }
 
-// batch energy totals are accumulated in 2^-44 eV fixed point: integer adds commute, so the total does not depend on the
-// order in which thread blocks (or GPUs) contribute -- every rank gets the bit-identical energy (resolution 5.7e-14 eV)
-constexpr double kEnergyFixedScale = 17592186044416.0;   // 2^44
 
 struct CmcGridParams {
   int world, rank;

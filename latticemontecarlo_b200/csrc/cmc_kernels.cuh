@@ -23,28 +23,10 @@
 #include <cstdio>
 #include <cooperative_groups.h>
 #include "kmc_kernels.cuh"
+#include "cmc_state.h"
 
 namespace lmc {
 namespace cg = cooperative_groups;
-
-struct SaSchedule {             // SimulatedAnnealing members (mc/include/SimulatedAnnealing.h:33-68)
-  double temperature;
-  double recent_best_energy;
-  unsigned long long last_improvement_step, last_reheat_step;
-  unsigned long long maximum_steps, reheat_trigger_steps, reheat_cooldown_steps, window_size;
-  unsigned int window_trials, window_accepts, reheats_done;
-  int enabled;
-};
-
-struct CmcState {               // per-replica arrays
-  double *energy;               // energy_ (relative to the start, like McAbstract::energy_ with restart_energy 0)
-  unsigned long long *steps;    // effective trials so far (steps_)
-  unsigned long long *accepted;
-  unsigned long long *proposals;   // Philox counter: proposals drawn so far
-  unsigned long long *epoch;    // batch counter for the claim tags
-  SaSchedule *sa;
-  int32_t *error;
-};
 
 struct CmcReplay {              // host-ordered trial stream for replica 0 (device copies)
   const int64_t *a, *b;
@@ -53,7 +35,6 @@ struct CmcReplay {              // host-ordered trial stream for replica 0 (devi
   uint8_t *accepted;
 };
 
-constexpr double kSaEpsilon = 1e-4;   // kEpsilon (cfg/include/VectorMatrix.hpp:65) used by SimulatedAnnealing.cpp:85,104
 
 // SimulatedAnnealing::UpdateTemperature (mc/src/SimulatedAnnealing.cpp:99-139), one trial
 __device__ __forceinline__ void sa_update(SaSchedule &s, bool accepted, double energy, unsigned long long step, double cool_factor) {

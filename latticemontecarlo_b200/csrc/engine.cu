@@ -18,7 +18,7 @@
 #include "kmc_kernels.cuh"
 #include "cmc_kernels.cuh"
 #include "cmc_grid_kernels.cuh"
-#include "cmc_domain_kernels.cuh"
+#include "cmc_domain.h"
 #include "tables.h"
 
 namespace lmc {
@@ -959,13 +959,13 @@ void Engine::cmc_domain_prepare() {
   d_dom_state = dev_alloc<DomState>(2 * static_cast<size_t>(n_walkers));
   d_dom_accum = dev_alloc<unsigned long long>(3 * static_cast<size_t>(n_walkers) * 4);
   d_dom_lines = dev_alloc<DomLine>(2 * kGridMaxWorld);
-  d_dom_counters = dev_alloc<unsigned long long>(4);   // [0] grid barrier, [1] inter-GPU line sequence, [2] sweeps done
+  d_dom_counters = dev_alloc<unsigned long long>(8);   // [0] grid barrier, [1] inter-GPU line sequence, [2] sweeps done, [4..5] domain queues (3 x u32)
   d_dom_abort = dev_alloc<int>(1);
   for (void *p : {d_dom_state, static_cast<void *>(d_dom_accum), d_dom_lines, static_cast<void *>(d_dom_counters), static_cast<void *>(d_dom_abort)})
     device_allocs.push_back(p);
   LMC_CUDA(cudaMemsetAsync(d_occ_buf[1], 0, bytes, stream));
   LMC_CUDA(cudaMemsetAsync(d_dom_lines, 0, sizeof(DomLine) * 2 * kGridMaxWorld, stream));
-  LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 32, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 64, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
   for (int b = 0; b < 2; ++b) dom_peer_occ[b][0] = d_occ_buf[b];
   dom_peer_lines[0] = d_dom_lines;
@@ -1068,9 +1068,8 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   if (2 * dp.tile_y * dp.tile_zh + 2 * dp.tile_zh + 2 > 32767) throw std::invalid_argument("domain tile too large for 16-bit offsets");
   dp.tile_cells = (tile_cells + 15) & ~15;
   dp.max_core = (dx_max - 2) * (dy_max - 2) * (dz_max - 2) / 2;
-  dp.tile_bytes = dp.tile_cells + 96 + ((2 * dp.max_core + 15) & ~15);
   dp.rounds = dom && dom->rounds_per_sweep > 0 ? dom->rounds_per_sweep : (edge - 2) * (edge - 2) * (edge - 2);
-  dp.tries = dom && dom->tries_per_round > 0 ? dom->tries_per_round : 4;
+  const double dom_passes = dom ? dom->passes : 0.0;
   dp.n_walkers = n_walkers;
   dp.world = dom_world; dp.rank = dom_rank;
   // ---- launch shape: one lane group per domain; wide groups while the domains of the whole job leave the SMs empty
@@ -1078,42 +1077,64 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   const long long items_total = static_cast<long long>(n_walkers) * dp.ndx * dp.ndy * dp.ndz;
   const int slab = domain_slab_begin(dp.ndx, dom_world, dom_rank + 1) - domain_slab_begin(dp.ndx, dom_world, dom_rank);
   const long long items_rank = static_cast<long long>(n_walkers) * slab * dp.ndy * dp.ndz;
-  int lanes = dom ? dom->lanes : 0;
-  if (const char *v = std::getenv("LMC_CMC_DOMAIN_LANES")) lanes = std::atoi(v);        // tuning knob
-  if (lanes <= 0) lanes = items_total <= static_cast<long long>(sms) * dom_world * 16 ? 32 : (items_total <= static_cast<long long>(sms) * dom_world * 48 ? 16 : 8);
-  if (lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per domain must be 2, 4, 8, 16 or 32");
+  // lanes per trial (G) and trials of a domain in flight (S): few domains -> a whole warp per domain, as S speculative
+  // trials of 32 / S lanes each; many domains -> 8 lanes per domain, four domains per warp, no speculation
+  int lanes = dom ? dom->lanes : 0, spec = dom ? dom->speculate : 0;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_LANES")) lanes = std::atoi(v);        // tuning knobs
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_SPECULATE")) spec = std::atoi(v);
+  const bool few = items_total <= static_cast<long long>(sms) * dom_world * 16;
+  if (lanes <= 0) lanes = few ? (spec == 1 ? 32 : (spec == 2 ? 16 : 8)) : (items_total <= static_cast<long long>(sms) * dom_world * 48 ? 16 : 8);
+  if (spec <= 0) spec = few ? (lanes == 8 ? 4 : (lanes == 16 ? 2 : 1)) : 1;
+  if (lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per trial must be 2, 4, 8, 16 or 32");
+  if (!((spec == 1) || (spec == 2 && (lanes == 8 || lanes == 16)) || (spec == 4 && lanes == 8)))
+    throw std::invalid_argument("speculate must be 1, 2 (8 or 16 lanes) or 4 (8 lanes)");
+  const int team = lanes * spec;                      // lanes per domain
+  dp.tile_bytes = dp.tile_cells + spec * 96 + ((2 * dp.max_core + 15) & ~15);
   const int m = species.n + 1;
-  const size_t b_bytes = static_cast<size_t>(m) * tab.n_site_pairs * m * m * 8;
-  size_t fixed = (static_cast<size_t>(m) + static_cast<size_t>(m) * kSiteEnvN * m) * 8 + kSiteEnvN * 8 + nw * 8 + kDomPidxBytes + 2 * 44 * 2;
+  // shared memory: fixed tables, then the coefficient tables -- difference tables per species pair (kTab 1) when they fit
+  const int ns = m - 1, n_sp = m * (m - 1) / 2;
+  const size_t base_bytes = kSiteEnvN * 8 + kDomPidxBytes + 2 * 44 * 2 + 64 + nw * 8;
+  const size_t tab0_bytes = (static_cast<size_t>(m) + static_cast<size_t>(m) * kSiteEnvN * m) * 8;
+  const size_t tab1_bytes = static_cast<size_t>(n_sp) * (1 + kSiteEnvN * ns + static_cast<size_t>(tab.n_site_pairs) * ns * ns) * 8;
   const int max_optin = device_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin) - 1024;     // static shared memory of the kernel
   int max_threads = kDomMaxThreads;
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_THREADS")) max_threads = std::max(32, std::min(kDomMaxThreads, std::atoi(v) / 32 * 32));
-  int groups = static_cast<int>(std::min<long long>(max_threads / lanes, std::max<long long>(1, (items_rank + sms - 1) / sms)));
-  // the pair table B is staged in shared memory when it fits next to the tiles of a single pass
-  int stage_b = fixed + b_bytes + static_cast<size_t>(groups) * dp.tile_bytes <= static_cast<size_t>(max_optin) ? 1 : 0;
-  if (const char *v = std::getenv("LMC_CMC_DOMAIN_STAGE_B")) stage_b = std::atoi(v) && fixed + b_bytes + dp.tile_bytes <= static_cast<size_t>(max_optin);
-  if (stage_b) fixed += b_bytes;
+  // lane groups per block: the domains of a sweep are handed out dynamically; `passes` domains per group on average
+  double passes = dom_passes > 0.0 ? dom_passes : 1.0;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_PASSES")) passes = std::max(1.0, std::atof(v));
+  if (spec > 1) max_threads = std::min(max_threads, 512);       // speculative instantiations exist for small blocks only
+  int groups = static_cast<int>(std::min<long long>(max_threads / team, std::max<long long>(1, static_cast<long long>(std::ceil(static_cast<double>(items_rank) / (sms * passes))))));
+  int k_tab = (m <= 8 && base_bytes + tab1_bytes + static_cast<size_t>(std::min(groups, 8)) * dp.tile_bytes <= static_cast<size_t>(max_optin)) ? 1 : 0;
+  if (const char *v = std::getenv("LMC_CMC_DOMAIN_TABLES")) k_tab = std::atoi(v) ? k_tab : 0;      // A/B switch: 0 forces the A + B form
+  const size_t fixed = base_bytes + (k_tab ? tab1_bytes : tab0_bytes);
+  if (fixed + dp.tile_bytes > static_cast<size_t>(max_optin)) throw std::invalid_argument("domain tile does not fit in shared memory");
   while (groups > 1 && fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) --groups;
-  if (fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) throw std::invalid_argument("domain tile does not fit in shared memory");
-  int threads = (groups * lanes + 31) / 32 * 32;
-  groups = threads / lanes;
-  while (fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) { threads -= 32; groups = threads / lanes; }
+  int threads = (groups * team + 31) / 32 * 32;
+  groups = threads / team;
+  while (fixed + static_cast<size_t>(groups) * dp.tile_bytes > static_cast<size_t>(max_optin)) { threads -= 32; groups = threads / team; }
   const size_t smem = fixed + static_cast<size_t>(groups) * dp.tile_bytes;
   const int ctas = static_cast<int>(std::max<long long>(1, std::min<long long>(sms, (items_rank + groups - 1) / groups)));
-  using DomKernel = void (*)(LatticeDesc, DevTables, CmcDomainParams, CmcState, uint64_t, unsigned long long);
-  DomKernel kernel = nullptr;
-  switch (lanes * 2 + stage_b) {
-    case 4: kernel = cmc_domain_kernel<1, false>; break;
-    case 5: kernel = cmc_domain_kernel<1, true>; break;
-    case 8: kernel = cmc_domain_kernel<2, false>; break;
-    case 9: kernel = cmc_domain_kernel<2, true>; break;
-    case 16: kernel = cmc_domain_kernel<4, false>; break;
-    case 17: kernel = cmc_domain_kernel<4, true>; break;
-    case 32: kernel = cmc_domain_kernel<8, false>; break;
-    case 33: kernel = cmc_domain_kernel<8, true>; break;
-    case 64: kernel = cmc_domain_kernel<16, false>; break;
-    default: kernel = cmc_domain_kernel<16, true>; break;
+  // table-walk ownership: environment positions dealt to the L lanes of a side by longest-processing-time-first on the
+  // number of pair partners above each position (the stripe t mod L leaves the busiest lane 1.2 - 1.65 x the mean)
+  {
+    const Geometry &g = geometry();
+    const int L = lanes / 2;
+    std::vector<int> order(kSiteEnvN), load(L, 0);
+    for (int t = 0; t < kSiteEnvN; ++t) order[t] = t;
+    auto weight = [&](int t) { return 2 + __builtin_popcountll(g.site_pair_mask_hi[t]); };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight(a) > weight(b); });
+    for (int q = 0; q < 16; ++q) dp.own_mask[q] = 0ULL;
+    for (int t : order) {
+      const int best = static_cast<int>(std::min_element(load.begin(), load.end()) - load.begin());
+      load[best] += weight(t);
+      dp.own_mask[best] |= 1ULL << t;
+    }
   }
+  const void *kernel = nullptr;
+  // blocks of at most 512 threads get the 128-register instantiation (no spills in the round loop)
+  const bool small = threads <= 512 && !std::getenv("LMC_CMC_DOMAIN_64REG");
+  kernel = cmc_domain_kernel_for(lanes, k_tab, spec, small);
+  if (!kernel) throw std::logic_error("no cmc_domain_kernel instantiation for this launch shape");
   LMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
   LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
@@ -1130,15 +1151,16 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   dp.accum = d_dom_accum;
   dp.barrier_counter = d_dom_counters;
   dp.line_seq = d_dom_counters + 1;
+  dp.queue = reinterpret_cast<unsigned int *>(d_dom_counters + 4);
   dp.abort_flag = d_dom_abort;
   dp.sweep = d_dom_counters + 2;
   dp.spin_limit = static_cast<long long>(device_attr(cudaDevAttrClockRate)) * 1000LL * 5LL;   // ~5 s
   LMC_CUDA(cudaMemsetAsync(d_dom_counters, 0, 8, stream));
+  LMC_CUDA(cudaMemsetAsync(d_dom_counters + 4, 0, 16, stream));
   LMC_CUDA(cudaMemsetAsync(d_dom_abort, 0, 4, stream));
   LMC_CUDA(cudaMemsetAsync(d_dom_accum, 0, 3 * nw * 4 * 8, stream));
   CmcState st{d_cmc_energy, d_cmc_steps, d_cmc_accepted, d_cmc_proposals, d_cmc_epoch, static_cast<SaSchedule *>(d_cmc_sa), d_cmc_error};
-  dom_state_init_kernel<<<static_cast<unsigned>((nw + 127) / 128), 128, 0, stream>>>(n_walkers, st, d_cmc_temperature,
-                                                                                    static_cast<DomState *>(d_dom_state) + ((sweep0 + 1) & 1ULL) * nw);
+  cmc_domain_state_init(n_walkers, st, d_cmc_temperature, static_cast<DomState *>(d_dom_state) + ((sweep0 + 1) & 1ULL) * nw, stream);
   ++launch_count;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(static_cast<unsigned>(ctas));
@@ -1150,10 +1172,13 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  dom_last_lanes = lanes; dom_last_threads = threads; dom_last_ctas = ctas; dom_last_domains = static_cast<int>(items_total);
+  dom_last_lanes = lanes; dom_last_spec = spec; dom_last_threads = threads; dom_last_ctas = ctas; dom_last_domains = static_cast<int>(items_total);
   dom_last_rounds = dp.rounds; dom_last_edge = edge;
   time_begin();
-  LMC_CUDA(cudaLaunchKernelEx(&cfg, kernel, lat, tab, dp, st, static_cast<uint64_t>(params.seed), target));
+  uint64_t seed_arg = static_cast<uint64_t>(params.seed);
+  unsigned long long target_arg = target;
+  void *args[] = {&lat, &tab, &dp, &st, &seed_arg, &target_arg};
+  LMC_CUDA(cudaLaunchKernelExC(&cfg, kernel, args));
   time_end();
   LMC_CUDA(cudaGetLastError());
   int32_t err = 0;
@@ -1174,15 +1199,9 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   // the occupancy now lives in the buffer the next sweep would read; its periodic halo images are refreshed for the other kernels
   occ_cur = (static_cast<int>(sweep_end & 1ULL) + phase) & 1;
   d_occ = d_occ_buf[occ_cur];
-  {
-    const unsigned blocks = static_cast<unsigned>((lat.padded_size + 255) / 256);
-    for (int w0 = 0; w0 < n_walkers; w0 += 32768) {
-      const unsigned ny = static_cast<unsigned>(std::min(32768, n_walkers - w0));
-      dom_refresh_halo_kernel<<<dim3(blocks, ny), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(w0) * lat.padded_size);
-      ++launch_count;
-    }
-    LMC_CUDA(cudaGetLastError());
-  }
+  cmc_domain_refresh_halo(lat, d_occ, n_walkers, stream);
+  launch_count += (n_walkers + 32767) / 32768;
+  LMC_CUDA(cudaGetLastError());
   cmc_cells_stale = true;
 }
 
@@ -1608,11 +1627,11 @@ int lmc_cmc_domain_handles(lmc_engine *engine, void *handles192) {
 int lmc_cmc_domain_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const void *handles) {
   return guard([&] { engine->impl->cmc_domain_attach_peers(rank, world, handles); });
 }
-int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape6) {
+int lmc_cmc_domain_last_shape(const lmc_engine *engine, int32_t *shape6) {     // seven entries
   if (!engine || !shape6) return LMC_ERR_INVALID_ARGUMENT;
   const auto &e = *engine->impl;
   shape6[0] = e.dom_last_edge; shape6[1] = e.dom_last_domains; shape6[2] = e.dom_last_lanes; shape6[3] = e.dom_last_threads;
-  shape6[4] = e.dom_last_ctas; shape6[5] = e.dom_last_rounds;
+  shape6[4] = e.dom_last_ctas; shape6[5] = e.dom_last_rounds; shape6[6] = e.dom_last_spec;
   return LMC_OK;
 }
 int lmc_cmc_exchange_handle(lmc_engine *engine, void *handle64) {

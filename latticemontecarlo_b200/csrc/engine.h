@@ -144,7 +144,7 @@ class Engine {
   void *dom_peer_lines[8]{};
   int dom_world{1}, dom_rank{0};
   bool cmc_cells_stale{false};
-  int dom_last_lanes{0}, dom_last_threads{0}, dom_last_ctas{0}, dom_last_domains{0}, dom_last_rounds{0}, dom_last_edge{0};
+  int dom_last_spec{0}, dom_last_lanes{0}, dom_last_threads{0}, dom_last_ctas{0}, dom_last_domains{0}, dom_last_rounds{0}, dom_last_edge{0};
   std::map<int, int> attr_cache;
   int device_attr(int attr);
   // measurement: CUDA events around the last hot kernel on the engine stream, and a count of our kernel launches

@@ -11,19 +11,17 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include "device_common.h"
 #include "device_tables.h"
 
 namespace lmc {
 
 // structural constants of the ordered neighbourhoods (verified against tables.cpp at engine creation)
-constexpr int kFirstPos = 21, kSecondPos = 38, kCentrePos = 21;
-constexpr int kEnvN = 58, kSiteEnvN = 42;
 constexpr int kBoxRows = 48;            // KMC box scan: (dx, dy) rows of the 7 x 7 box around a vacancy that hold a neighbourhood site of
                                         // some jump (the 4 corner rows hold none: 45 rows, padded to 3 x 16 for the half-warp scan)
 constexpr int kBoxCells = kBoxRows * 4; // 4 consecutive z slots (cells of the padded layout) per row
 constexpr int kBoxCentreRow = 22;       // position of the vacancy's own row (dx = dy = 0) among the kept rows
 
-enum EventError : int { kErrNotNeighbour = 1, kErrNotVacancy = 2, kErrExtraVacancy = 4, kErrBadSite = 8 };
 
 // The environment of an event is summarised by ONE bit mask over the env index: bit t set <=> the species at env
 // site t differs from the solvent.  Only those sites contribute to the contracted (delta-form) tables, and their

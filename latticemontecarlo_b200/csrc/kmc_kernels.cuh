@@ -13,7 +13,6 @@
 
 namespace lmc {
 
-constexpr double kBoltzmannEv = 8.617333262145e-5;   // cfg/include/Constants.hpp:31
 constexpr double kPrefactorHz = 1e13;                // Constants.hpp:32
 
 struct KmcState {            // per-walker arrays in device memory
@@ -52,11 +51,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     k1 += 0xBB67AE85u;
   }
   out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-}
-// 53-bit uniforms like libstdc++'s generate_canonical<double,53> on a 64-bit engine: floor(x / 2^11) * 2^-53
-__device__ __forceinline__ double uniform53(uint32_t lo, uint32_t hi) {
-  const uint64_t x = (static_cast<uint64_t>(hi) << 32) | lo;
-  return static_cast<double>(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
 // pred::TimeTemperatureInterpolator::GetTemperature (pred/src/TimeTemperatureInterpolator.cpp:43-65)

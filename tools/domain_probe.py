@@ -26,6 +26,19 @@ def check(f, replicas, trials, **kw):
     cons = all(np.array_equal(np.sort(fin[w]), np.sort(occ[w])) for w in range(replicas))
     print("f=%d replicas=%d %s: steps %s acc ratio %.3f  |dE bookkeeping| %.2e  conserved %s  shape %s" % (
         f, replicas, kw, st["steps"][:3], st["accepted"].sum() / max(1, st["steps"].sum()), ok_e, cons, e.cmc_domain_last_shape()), flush=True)
+    # the A + B table form (LMC_CMC_DOMAIN_TABLES=0) and another lane count must give the same trajectory
+    ref_state = (fin.copy(), st["energy"].copy(), st["steps"].copy())
+    for env, extra in (({"LMC_CMC_DOMAIN_TABLES": "0"}, {}), ({}, {"lanes": 8, "speculate": 1}), ({}, {"lanes": 8, "speculate": 4}), ({}, {"lanes": 16, "speculate": 2}),
+                       ({}, {"lanes": 32, "speculate": 1}), ({"LMC_CMC_DOMAIN_PASSES": "3"}, {"lanes": 8, "speculate": 2})):
+        os.environ.update(env)
+        e.set_occupancy_all(occ); e.cmc_reset()
+        kw2 = dict(kw); kw2.update(extra)
+        e.cmc_domain_run(trials, temperature=800.0, temperatures=temps, seed=3, **kw2)
+        e.cmc_domain_run(trials, temperature=800.0, temperatures=temps, seed=3, **kw2)
+        for k in env: del os.environ[k]
+        st3 = e.cmc_state(); fin3 = e.get_occupancy_all()
+        print("   variant %s %s: same occupancy %s, same steps %s, max |dE_total diff| %.2e" % (env, extra, np.array_equal(fin3, ref_state[0]),
+              np.array_equal(st3["steps"], ref_state[2]), np.max(np.abs(st3["energy"] - ref_state[1]))), flush=True)
     # the batched driver keeps working on the result
     e.cmc_run(2000, temperature=800.0, temperatures=temps, seed=1)
     e2 = np.array([e.total_energy(w) for w in range(replicas)])
@@ -36,6 +49,8 @@ def check(f, replicas, trials, **kw):
 
 def rate(f, replicas, trials, p=0.02, sa=None, **kw):
     js = "/tmp/coef_probe.json"
+    if not os.path.exists(js):
+        synth.write_synthetic_json(js)
     e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=replicas, device=0)
     e.load_coefficients(js)
     occ = np.stack([synth.random_alloy(f, p, p, seed=1000 + r, vacancy_site=None) for r in range(replicas)])
@@ -68,13 +83,12 @@ if __name__ == "__main__":
         check(24, 1, 200000)
         check(24, 1, 200000, lanes=2)
     if mode in ("all", "rate"):
-        for lanes in (32, 16, 8):
-            rate(40, 1, 20000000, lanes=lanes)
-        rate(40, 1, 20000000, domain_edge=10)
-        rate(40, 1, 20000000, domain_edge=6)
-        for lanes in (16, 8, 4, 2):
-            rate(100, 1, 200000000, lanes=lanes)
-        rate(100, 1, 200000000, sa=(900.0, 4000000000), lanes=8)
-        rate(20, 148, 200000, lanes=8)
-        rate(20, 148, 200000, lanes=16)
-        rate(40, 1, 20000000, p=0.10)
+        for lanes, spec in ((32, 1), (16, 2), (8, 4), (8, 2)):
+            rate(40, 1, 20000000, lanes=lanes, speculate=spec)
+        rate(40, 1, 20000000, domain_edge=6, rounds_per_sweep=216, lanes=8, speculate=4)
+        rate(40, 1, 20000000, domain_edge=6, rounds_per_sweep=216, lanes=16, speculate=2)
+        rate(100, 1, 200000000, lanes=8, speculate=1)
+        rate(20, 148, 200000, lanes=8, speculate=1)
+        rate(40, 1, 2000000)
+        rate(40, 1, 2000000, domain_edge=6, rounds_per_sweep=216)
+        rate(100, 1, 20000000)
