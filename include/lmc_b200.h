@@ -265,7 +265,7 @@ typedef struct lmc_cmc_domain_params {
   int32_t speculate;               /* rounds of one domain evaluated at once on the current state and committed up to the first
                                     * accepted one: 1, 2 (with 8 or 16 lanes) or 4 (with 8 lanes); 0 = 32 / lanes when the lattice
                                     * has fewer domains than the GPU has warp slots, else 1.  Exactly the sequential chain */
-  int32_t lanes;                   /* lanes per trial: 2, 4, 8, 16 or 32 (0 = from the number of domains).  Launch shape only:
+  int32_t lanes;                   /* lanes per trial: 8, 16 or 32 (0 = from the number of domains).  Launch shape only:
                                     * the random stream is keyed by (seed, sweep, domain, round), the trajectory does not
                                     * depend on it (up to the rounding of dE in the last bit) */
   double passes;                   /* domains per lane group and sweep, handed out dynamically (0 = 1; > 1 trades resident

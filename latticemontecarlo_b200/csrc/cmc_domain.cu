@@ -6,32 +6,24 @@
 namespace lmc {
 
 const void *cmc_domain_kernel_for(int lanes, int k_tab, int speculate, bool small_block) {
-#define LMC_DOM_PICK(LL, TT) (small_block ? reinterpret_cast<const void *>(cmc_domain_kernel<LL, TT, 512, 1>) \
-                                          : reinterpret_cast<const void *>(cmc_domain_kernel<LL, TT, kDomMaxThreads, 1>))
-  switch ((lanes * 2 + (k_tab ? 1 : 0)) * 8 + speculate) {
-    case (4 + 0) * 8 + 1: return LMC_DOM_PICK(1, 0);
-    case (4 + 1) * 8 + 1: return LMC_DOM_PICK(1, 1);
-    case (8 + 0) * 8 + 1: return LMC_DOM_PICK(2, 0);
-    case (8 + 1) * 8 + 1: return LMC_DOM_PICK(2, 1);
-    case (16 + 0) * 8 + 1: return LMC_DOM_PICK(4, 0);
-    case (16 + 1) * 8 + 1: return LMC_DOM_PICK(4, 1);
-    case (32 + 0) * 8 + 1: return LMC_DOM_PICK(8, 0);
-    case (32 + 1) * 8 + 1: return LMC_DOM_PICK(8, 1);
-    case (64 + 0) * 8 + 1: return LMC_DOM_PICK(16, 0);
-    case (64 + 1) * 8 + 1: return LMC_DOM_PICK(16, 1);
-    default: break;
-  }
-#undef LMC_DOM_PICK
-  if (!small_block) return nullptr;                 // speculative instantiations exist for blocks of <= 512 threads only
-  switch ((lanes * 2 + (k_tab ? 1 : 0)) * 8 + speculate) {
-    case (16 + 0) * 8 + 2: return reinterpret_cast<const void *>(cmc_domain_kernel<4, 0, 512, 2>);
-    case (16 + 1) * 8 + 2: return reinterpret_cast<const void *>(cmc_domain_kernel<4, 1, 512, 2>);
-    case (16 + 0) * 8 + 4: return reinterpret_cast<const void *>(cmc_domain_kernel<4, 0, 512, 4>);
-    case (16 + 1) * 8 + 4: return reinterpret_cast<const void *>(cmc_domain_kernel<4, 1, 512, 4>);
-    case (32 + 0) * 8 + 2: return reinterpret_cast<const void *>(cmc_domain_kernel<8, 0, 512, 2>);
-    case (32 + 1) * 8 + 2: return reinterpret_cast<const void *>(cmc_domain_kernel<8, 1, 512, 2>);
-    default: return nullptr;
-  }
+  // instantiations: 8 / 16 / 32 lanes per trial (fewer lanes were slower everywhere: 22 or 43 loads per lane), blocks of
+  // <= 512 threads (128 registers) or <= 1024 (64 registers)
+#define LMC_DOM_CASE(LANES, TAB, SPEC, LL)                                                                      \
+  if (lanes == LANES && (k_tab ? 1 : 0) == TAB && speculate == SPEC)                                            \
+    return small_block ? reinterpret_cast<const void *>(cmc_domain_kernel<LL, TAB, 512, SPEC>)                  \
+                       : reinterpret_cast<const void *>(cmc_domain_kernel<LL, TAB, kDomMaxThreads, SPEC>);
+#define LMC_DOM_CASE_SMALL(LANES, TAB, SPEC, LL)                                                                \
+  if (lanes == LANES && (k_tab ? 1 : 0) == TAB && speculate == SPEC)                                            \
+    return small_block ? reinterpret_cast<const void *>(cmc_domain_kernel<LL, TAB, 512, SPEC>) : nullptr;
+  LMC_DOM_CASE(8, 0, 1, 4) LMC_DOM_CASE(8, 1, 1, 4)
+  LMC_DOM_CASE(8, 0, 2, 4) LMC_DOM_CASE(8, 1, 2, 4)
+  LMC_DOM_CASE(8, 0, 4, 4) LMC_DOM_CASE(8, 1, 4, 4)
+  LMC_DOM_CASE(16, 0, 1, 8) LMC_DOM_CASE(16, 1, 1, 8)
+  LMC_DOM_CASE_SMALL(16, 0, 2, 8) LMC_DOM_CASE_SMALL(16, 1, 2, 8)
+  LMC_DOM_CASE(32, 0, 1, 16) LMC_DOM_CASE(32, 1, 1, 16)
+#undef LMC_DOM_CASE
+#undef LMC_DOM_CASE_SMALL
+  return nullptr;
 }
 
 void cmc_domain_state_init(int n_walkers, const CmcState &st, const double *temperatures, DomState *dst, cudaStream_t stream) {

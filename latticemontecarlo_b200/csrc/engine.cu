@@ -1077,15 +1077,16 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   const long long items_total = static_cast<long long>(n_walkers) * dp.ndx * dp.ndy * dp.ndz;
   const int slab = domain_slab_begin(dp.ndx, dom_world, dom_rank + 1) - domain_slab_begin(dp.ndx, dom_world, dom_rank);
   const long long items_rank = static_cast<long long>(n_walkers) * slab * dp.ndy * dp.ndz;
-  // lanes per trial (G) and trials of a domain in flight (S): few domains -> a whole warp per domain, as S speculative
-  // trials of 32 / S lanes each; many domains -> 8 lanes per domain, four domains per warp, no speculation
+  // lanes per trial (G) and trials of a domain in flight (S), from the domains this rank holds per SM: few domains -> a
+  // whole warp per domain as four speculative trials of 8 lanes; many -> 8 lanes per domain, four domains per warp, no
+  // speculation.  Launch shape only: the trajectory does not depend on it.
   int lanes = dom ? dom->lanes : 0, spec = dom ? dom->speculate : 0;
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_LANES")) lanes = std::atoi(v);        // tuning knobs
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_SPECULATE")) spec = std::atoi(v);
-  const bool few = items_total <= static_cast<long long>(sms) * dom_world * 16;
-  if (lanes <= 0) lanes = few ? (spec == 1 ? 32 : (spec == 2 ? 16 : 8)) : (items_total <= static_cast<long long>(sms) * dom_world * 48 ? 16 : 8);
-  if (spec <= 0) spec = few ? (lanes == 8 ? 4 : (lanes == 16 ? 2 : 1)) : 1;
-  if (lanes != 2 && lanes != 4 && lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per trial must be 2, 4, 8, 16 or 32");
+  const double dom_per_sm = static_cast<double>(items_rank) / sms;
+  if (lanes <= 0) lanes = spec == 1 && dom_per_sm <= 8.0 ? 32 : 8;
+  if (spec <= 0) spec = lanes == 8 ? (dom_per_sm <= 16.0 ? 4 : (dom_per_sm <= 32.0 ? 2 : 1)) : (lanes == 16 && dom_per_sm <= 16.0 ? 2 : 1);
+  if (lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per trial must be 8, 16 or 32");
   if (!((spec == 1) || (spec == 2 && (lanes == 8 || lanes == 16)) || (spec == 4 && lanes == 8)))
     throw std::invalid_argument("speculate must be 1, 2 (8 or 16 lanes) or 4 (8 lanes)");
   const int team = lanes * spec;                      // lanes per domain
@@ -1102,7 +1103,7 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   // lane groups per block: the domains of a sweep are handed out dynamically; `passes` domains per group on average
   double passes = dom_passes > 0.0 ? dom_passes : 1.0;
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_PASSES")) passes = std::max(1.0, std::atof(v));
-  if (spec > 1) max_threads = std::min(max_threads, 512);       // speculative instantiations exist for small blocks only
+  if (spec > 1 && lanes == 16) max_threads = std::min(max_threads, 512);       // no 1024-thread instantiation of (16 lanes, 2 trials)
   int groups = static_cast<int>(std::min<long long>(max_threads / team, std::max<long long>(1, static_cast<long long>(std::ceil(static_cast<double>(items_rank) / (sms * passes))))));
   int k_tab = (m <= 8 && base_bytes + tab1_bytes + static_cast<size_t>(std::min(groups, 8)) * dp.tile_bytes <= static_cast<size_t>(max_optin)) ? 1 : 0;
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_TABLES")) k_tab = std::atoi(v) ? k_tab : 0;      // A/B switch: 0 forces the A + B form
