@@ -9,8 +9,9 @@ Metric (BASELINE.json): KMC vacancy hops/s (primary, walker-sharded, weak scalin
 
 One "step" = one pass of the hot path over one batch: every walker of the rank advances `--hops` KMC steps
 (12 candidate barriers + Arrhenius rates + event select + residence time + jump per hop) in ONE kernel launch.
-Workload = BASELINE configs[2] shape: independent single-vacancy Al-2%Mg-2%Zn walkers on 8x8x8 FCC cells
-(2048 sites), T_w = 400..600 K, synthetic JSON coefficients; 8192 walkers per GPU.
+Workload = BASELINE configs[2] as written: 8192 independent single-vacancy Al-2%Mg-2%Zn walkers on 8x8x8 FCC cells
+(2048 sites), T_w = 400..600 K, synthetic JSON coefficients, walker w on GPU w mod N -- STRONG scaling
+(the headline at N > 1); the weak-scaling line (8192 walkers on every GPU) is reported next to it as `weak_scaling`.
 """
 from __future__ import annotations
 
@@ -57,16 +58,16 @@ def recorded_traffic(kernel, **shape):
     return None
 
 
-def walker_occupancy(first_walker, n_walkers, factor=FACTOR):
-    """Random Al-Mg-Zn alloy per walker (seed 42 + global walker index), one vacancy each, REASSIGNED id order."""
+def walker_occupancy(first_walker, n_walkers, factor=FACTOR, stride=1, p_mg=P_MG, p_zn=P_ZN):
+    """Random Al-Mg-Zn alloy per walker (seed 42 + global walker index first + stride * i), one vacancy each, REASSIGNED id order."""
     n = 4 * factor ** 3
     out = np.empty((n_walkers, n), dtype=np.uint8)
     for w in range(n_walkers):
-        u = np.random.default_rng(42 + first_walker + w).random(n)
+        u = np.random.default_rng(42 + first_walker + stride * w).random(n)
         row = out[w]
         row[:] = 1
-        row[u < P_MG + P_ZN] = 3
-        row[u < P_MG] = 2
+        row[u < p_mg + p_zn] = 3
+        row[u < p_mg] = 2
         row[n // 2 + 3] = 0
     return out
 
@@ -153,6 +154,7 @@ def run_reference(args):
     if not R.build():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/liblmc_ref.so missing and /root/reference absent"}))
         return 0
+    R.lib()                                   # mapped in this process too (the trajectories run in forked workers that inherit it)
     cores = host_cores()
     with tempfile.TemporaryDirectory() as d:
         js = os.path.join(d, "quartic_coefficients.json")
@@ -181,11 +183,11 @@ def run_reference(args):
 
 
 def workload_config(args, n_gpus):
-    return {"workload": "BASELINE configs[2]: batched KMC, independent single-vacancy Al-2%Mg-2%Zn walkers on 8x8x8 FCC "
-                        "(2048 sites), T=400..600 K, walker-sharded, synthetic JSON coefficients (K=24/32)",
-            "walkers_per_gpu": args.walkers, "walkers_total": args.walkers * n_gpus, "hops_per_walker_per_step": args.hops,
+    return {"workload": "BASELINE configs[2]: batched KMC, %d independent single-vacancy Al-2%%Mg-2%%Zn walkers on 8x8x8 FCC "
+                        "(2048 sites), T=400..600 K, walker w on GPU w mod %d, synthetic JSON coefficients (K=24/32)" % (args.walkers, n_gpus),
+            "walkers_total": args.walkers, "walkers_per_gpu": -(-args.walkers // n_gpus), "hops_per_walker_per_step": args.hops,
             "sites_per_walker": 4 * FACTOR ** 3, "l2": "flushed between timed steps (256 MiB write)",
-            "parallelism": "walker-sharded x%d, no data-path collective" % n_gpus}
+            "parallelism": "walker-sharded x%d (w mod N), no data-path collective" % n_gpus}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -203,20 +205,11 @@ def run_ours(args):
     if capi.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     n_gpus = world
-    W, H = args.walkers, args.hops
+    H = args.hops
     n_sites = 4 * FACTOR ** 3
     tmp = tempfile.TemporaryDirectory()
     js = os.path.join(tmp.name, "quartic_coefficients.json")
     synth.write_synthetic_json(js)
-    engine = capi.Engine(FACTOR, id_order=capi.ORDER_REASSIGNED, n_walkers=W, device=local_rank)
-    engine.load_coefficients(js)
-    occ_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
-    occ_np = occ_pinned.numpy()
-    first_walker, _ = sharding.shard_range(W * n_gpus, rank, n_gpus)        # weak scaling: W walkers on every rank
-    occ_np[:] = walker_occupancy(first_walker, W)
-    out_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
-    temps = sharding.walker_temperatures(first_walker, W, W * n_gpus)
-    stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local_rank)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -225,77 +218,126 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    engine.set_occupancy_all(occ_np)
-    engine.kmc_reset()
-
-    def step_resident():
-        flush.fill_(1)                       # evict the walkers' occupancy from L2 between timed steps
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            engine.kmc_run(H, temperatures=temps, seed=20260101)
-            e1.record(stream)
-        e1.synchronize()
-        return e0.elapsed_time(e1), engine.last_kernel_ms()
-
-    for _ in range(max(3, args.warmup)):
-        step_resident()
-    launches0 = engine.launch_count()
-    barrier()
-    with ClockSampler(local_rank) as clocks:
-        wall0 = time.perf_counter()
-        timings = [step_resident() for _ in range(args.steps)]
-        barrier()
-        wall = time.perf_counter() - wall0
-    launches = engine.launch_count() - launches0
-    step_ms = sum(t[0] for t in timings)
-    kernel_ms = sum(t[1] for t in timings)
-    step_ms, kernel_ms = sharding.max_over_ranks([step_ms, kernel_ms], device="cuda")      # slowest rank defines the step
-    hops_total = float(W) * H * args.steps * n_gpus
-    value = hops_total / (step_ms * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers: H2D occupancy, reset, run, D2H state + occupancy
-    def step_e2e():
-        t0 = time.perf_counter()
+    def measure_kmc(first_walker, stride, W, walkers_total, steps, p_mg=P_MG, p_zn=P_ZN, with_e2e=True, sample_clocks=False):
+        """KMC throughput of this rank's W walkers (global indices first_walker + stride * i): resident (CUDA events on the
+        engine stream, L2 flushed between steps) and end to end through the C ABI with pinned host buffers."""
+        engine = capi.Engine(FACTOR, id_order=capi.ORDER_REASSIGNED, n_walkers=W, device=local_rank)
+        engine.load_coefficients(js)
+        occ_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
+        occ_np = occ_pinned.numpy()
+        occ_np[:] = walker_occupancy(first_walker, W, stride=stride, p_mg=p_mg, p_zn=p_zn)
+        out_pinned = torch.empty((W, n_sites), dtype=torch.uint8, pin_memory=True)
+        temps = 400.0 + 200.0 * (first_walker + stride * np.arange(W)) / max(1, walkers_total - 1)
+        stream = torch.cuda.ExternalStream(engine.cuda_stream(), device=local_rank)
         engine.set_occupancy_all(occ_np)
         engine.kmc_reset()
-        engine.kmc_run(H, temperatures=temps, seed=20260101)
+
+        def step_resident():
+            flush.fill_(1)                       # evict the walkers' occupancy from L2 between timed steps
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                engine.kmc_run(H, temperatures=temps, seed=20260101)
+                e1.record(stream)
+            e1.synchronize()
+            return e0.elapsed_time(e1), engine.last_kernel_ms()
+
+        for _ in range(max(3, args.warmup)):
+            step_resident()
+        steps_before = engine.kmc_state()["steps"].copy()
+        launches0 = engine.launch_count()
+        barrier()
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        wall0 = time.perf_counter()
+        timings = [step_resident() for _ in range(steps)]
+        barrier()
+        wall = time.perf_counter() - wall0
+        if sampler:
+            sampler.__exit__(None, None, None)
+        launches = engine.launch_count() - launches0
         st = engine.kmc_state()
-        capi._check(capi.lib().lmc_engine_get_occupancy_all(engine.h, out_pinned.numpy().ctypes.data_as(capi.C.c_void_p),
-                                                            capi.C.c_int64(W * n_sites)))
-        return time.perf_counter() - t0, st
+        advanced = st["steps"] - steps_before
+        step_ms, kernel_ms = sharding.max_over_ranks([sum(t[0] for t in timings), sum(t[1] for t in timings)], device="cuda")
+        res = {"engine": engine, "occ_pinned": occ_pinned, "temps": temps, "step_ms": step_ms, "kernel_ms": kernel_ms,
+               "local_kernel_ms": sum(t[1] for t in timings), "wall": wall, "launches": launches, "clocks": sampler,
+               "walkers_advanced_all_steps": int(np.count_nonzero(advanced == H * steps)), "min_steps_advanced": int(advanced.min()),
+               "age_hops": [int(steps_before.min()), int(st["steps"].max())]}
+        if with_e2e:
+            # ---- end to end through the C ABI with host buffers: H2D occupancy, reset, run, D2H state + occupancy
+            def step_e2e():
+                t0 = time.perf_counter()
+                engine.set_occupancy_all(occ_np)
+                engine.kmc_reset()
+                engine.kmc_run(H, temperatures=temps, seed=20260101)
+                engine.kmc_state()
+                capi._check(capi.lib().lmc_engine_get_occupancy_all(engine.h, out_pinned.numpy().ctypes.data_as(capi.C.c_void_p),
+                                                                    capi.C.c_int64(W * n_sites)))
+                return time.perf_counter() - t0
 
-    for _ in range(2):
-        step_e2e()
-    barrier()
-    e2e_s = sum(step_e2e()[0] for _ in range(args.steps))
-    barrier()
-    e2e_s = sharding.max_over_ranks([e2e_s], device="cuda")[0]
-    e2e_value = hops_total / e2e_s
+            for _ in range(2):
+                step_e2e()
+            barrier()
+            e2e_s = sum(step_e2e() for _ in range(steps))
+            barrier()
+            res["e2e_s"] = sharding.max_over_ranks([e2e_s], device="cuda")[0]
+        return res
 
+    # ---- headline: BASELINE configs[2] as written -- args.walkers walkers in total, walker w on GPU w mod N (strong scaling)
+    W_total = args.walkers
+    W = len(sharding.interleaved_walkers(W_total, rank, n_gpus))          # walker w on GPU w mod N
+    head = measure_kmc(rank, n_gpus, W, W_total, args.steps, sample_clocks=True)
+    engine, occ_pinned, temps = head["engine"], head["occ_pinned"], head["temps"]
+    hops_total = float(W_total) * H * args.steps
+    value = hops_total / (head["step_ms"] * 1e-3)
+    e2e_value = hops_total / head["e2e_s"]
+    advanced_all = sharding.sum_over_ranks([head["walkers_advanced_all_steps"]], device="cuda")[0]
     peak, peak_kind = measured_peaks()
-    achieved = (float(W) * H * args.steps * BYTES_PER_KMC_STEP) / (kernel_ms * 1e-3) / 1e9     # per GPU, dominant kernel
+    achieved = (float(W) * H * args.steps * BYTES_PER_KMC_STEP) / (head["local_kernel_ms"] * 1e-3) / 1e9     # this GPU, dominant kernel
     line = {
         "metric": "kmc_vacancy_hops_per_s", "value": value, "unit": "hops/s", "n_gpus": n_gpus, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": max(3, args.warmup), "ms_per_step": head["step_ms"] / args.steps, "higher_is_better": True,
+        "scaling": "strong" if n_gpus > 1 else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, n_gpus),
         "e2e": {"value": e2e_value, "unit": "hops/s", "h2d_bytes_per_step": int(W * n_sites + W * 8),
                 "d2h_bytes_per_step": int(W * n_sites + W * 44)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(head["launches"]),
+        "walkers_advanced_all_steps": int(advanced_all), "walkers_total": W_total,
+        "walker_age_hops_during_timed_region": head["age_hops"],
         "roofline": {"kernel": "kmc_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": int(W * H * BYTES_PER_KMC_STEP),
                      "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
                              "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"},
-        "wall_s_timed_region": wall,
+        "wall_s_timed_region": head["wall"],
     }
+    clocks = head["clocks"]
+    if n_gpus > 1:
+        # weak-scaling extra: args.walkers walkers on EVERY GPU (the round-1 headline), same w mod N dealing of seeds / temperatures
+        weak = measure_kmc(rank, n_gpus, W_total, W_total * n_gpus, max(3, args.steps // 2), with_e2e=False)
+        wsteps = max(3, args.steps // 2)
+        line["weak_scaling"] = {"value": float(W_total) * n_gpus * H * wsteps / (weak["step_ms"] * 1e-3), "unit": "hops/s", "scaling": "weak",
+                                "walkers_per_gpu": W_total, "walkers_total": W_total * n_gpus, "ms_per_step": weak["step_ms"] / wsteps,
+                                "roofline_frac_this_gpu": float(W_total) * H * wsteps * BYTES_PER_KMC_STEP / (weak["local_kernel_ms"] * 1e-3) / 1e9 / peak}
+        weak["engine"].close()
+    if rank == 0:
+        line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)          # on the walkers as the timed region left them
+    if rank == 0 and not args.no_age:
+        line["value_vs_age"] = bench_value_vs_age(engine, occ_pinned, W, H, temps)
+        rich = measure_kmc(0, 1, W_total if n_gpus == 1 else W, W_total, 3, p_mg=0.10, p_zn=0.10, with_e2e=False) if n_gpus == 1 else None
+        if rich:
+            wr = W_total
+            line["alloy_10Mg_10Zn"] = {"value": float(wr) * H * 3 / (rich["step_ms"] * 1e-3), "unit": "hops/s", "walkers": wr,
+                                       "walkers_advanced_all_steps": rich["walkers_advanced_all_steps"],
+                                       "note": "same driver on Al-10%Mg-10%Zn walkers: the table walk is O(non-solvent sites + their pairs)"}
+            rich["engine"].close()
     cmc_multi = None
     if world > 1 and not args.no_cmc:
         cmc_multi = bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, js)      # collective: every rank takes part
     if rank == 0:
         line["clocks"] = clocks.summary()
-        line["barrier_eval"] = bench_barrier_eval(engine, torch, W, peak)
         if n_gpus == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(js)
         if not args.no_chain:
@@ -304,12 +346,31 @@ def run_ours(args):
         if not args.no_cmc:
             line["cmc"] = bench_cmc(torch, local_rank, js, peak, n_gpus == 1 and not args.no_cpu_baseline)
             if cmc_multi is not None:
-                line["cmc"]["multi_gpu_single_lattice_100x100x100_sa"] = cmc_multi
+                line["cmc"]["multi_gpu"] = cmc_multi
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def bench_value_vs_age(engine, occ_pinned, W, H, temps):
+    """The rate as the walkers age (trajectories find solute: longer table walks): kernel rate of one launch of H hops at
+    walker ages of about 0, 20k and 200k hops."""
+    out = []
+    engine.set_occupancy_all(occ_pinned.numpy())
+    engine.kmc_reset()
+    target, done = [0, 20000, 200000], 0
+    for age in target:
+        while done < age:
+            n = min(8192, age - done)
+            engine.kmc_run(n, temperatures=temps, seed=20260101)
+            done += n
+        engine.kmc_run(H, temperatures=temps, seed=20260101)
+        ms = engine.last_kernel_ms()
+        done += H
+        out.append({"age_hops": age, "value": W * H / (ms * 1e-3), "kernel_ms": ms})
+    return out
 
 
 def bench_barrier_eval(engine, torch, W, peak):
@@ -450,15 +511,22 @@ def bench_chain(engine, W, temps, occ_pinned, peak, json_path, with_cpu):
 
 
 def bench_cmc(torch, device, json_path, peak, with_cpu):
-    """Secondary metric: CMC swap trials/s.  (a) BASELINE configs[1]: one 40x40x40 (256k sites) Al-2%Mg-2%Zn lattice at
-    800 K, batches of mutually non-interfering trials in ONE persistent kernel launch per step; (b) the same driver over
-    148 independent replicas (one thread block each) -- temperatures shard with no communication."""
+    """Secondary metric: CMC swap trials/s on BASELINE configs[1] (one 40x40x40 Al-2%Mg-2%Zn lattice, 800 K), configs[3]
+    (SimulatedAnnealing on 100x100x100 = 4M sites) and 148 independent 20^3 replicas at 600..1000 K, with both drivers:
+      `domain`  lmc_cmc_domain_run -- spatial domains, pairs drawn inside a domain core, one grid barrier per sweep (the
+                north_star's decomposition; semantic change stated in include/lmc_b200.h; ensemble parity with
+                mc::CanonicalMcSerial in tests/test_gpu_cmc_stat.py)
+      `global_pairs`  lmc_cmc_run -- the reference's global pair draw, batches of mutually non-interfering trials.
+    Rates are kernel rates (CUDA events on the engine stream); `fresh` = the first trials from the random alloy, `aged` =
+    after about 300 trials per site at 800 K (solute has clustered: longer table walks); `e2e` includes H2D occupancy,
+    reset, run and D2H occupancy through the C ABI."""
     from latticemontecarlo_b200 import capi, synth
     out = {"metric": "cmc_swap_trials_per_s", "unit": "trials/s", "bytes_per_trial": BYTES_PER_TRIAL}
-    cases = (("single_lattice_40x40x40", 40, 1, 200000, None),                        # BASELINE configs[1]
-             ("single_lattice_100x100x100_sa", 100, 1, 2000000, (900.0, 40000000)),    # configs[3]: SimulatedAnnealing, 4M sites
-             ("replicas_148x_20x20x20", 20, 148, 20000, None))
-    for name, f, replicas, trials, sa in cases:
+    cases = (("single_lattice_40x40x40", 40, 1, None, 8),                              # BASELINE configs[1]
+             ("single_lattice_100x100x100_sa", 100, 1, (900.0, 40000000000), 8),       # configs[3]: SimulatedAnnealing, 4M sites
+             ("replicas_148x_20x20x20", 20, 148, None, 8))
+    for name, f, replicas, sa, trials_per_site in cases:
+        n_sites = 4 * f ** 3 * replicas
         eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=replicas, device=device)
         eng.load_coefficients(json_path)
         occ = np.stack([synth.random_alloy(f, P_MG, P_ZN, seed=1000 + r, vacancy_site=None) for r in range(replicas)])
@@ -468,33 +536,59 @@ def bench_cmc(torch, device, json_path, peak, with_cpu):
         eng.set_occupancy_all(pinned.numpy())
         if name == "single_lattice_40x40x40":
             out["swap_de_eval"] = bench_swap_de_eval(torch, eng, occ[0], peak)
+        entry = {"replicas": replicas, "sites": 4 * f ** 3, "driver": "SimulatedAnnealing schedule" if sa else "CanonicalMc at fixed temperature"}
+
+        def timed(run, per_launch, launches):
+            kernel_ms, done = [], []
+            for _ in range(launches):
+                s0 = eng.cmc_state()["steps"].sum()
+                run(per_launch)
+                kernel_ms.append(eng.last_kernel_ms())
+                done.append(int(eng.cmc_state()["steps"].sum() - s0))
+            return sum(done) / (sum(kernel_ms) * 1e-3), float(np.mean(kernel_ms)), int(np.mean(done))
+
+        # ---- domain driver
+        per_launch = trials_per_site * 4 * f ** 3                    # per replica
+        run_dom = lambda n: eng.cmc_domain_run(n, temperatures=temps, seed=5)
         eng.cmc_reset(*(sa or ()))
-        eng.cmc_run(trials // 4, temperatures=temps, seed=5)          # warm-up
-        kernel_ms, done = [], []
-        for _ in range(5):
-            s0 = eng.cmc_state()["steps"].sum()
-            eng.cmc_run(trials, temperatures=temps, seed=5)
-            kernel_ms.append(eng.last_kernel_ms())
-            done.append(int(eng.cmc_state()["steps"].sum() - s0))
-        rate = sum(done) / (sum(kernel_ms) * 1e-3)
+        run_dom(per_launch // 4)                                      # warm-up
+        eng.set_occupancy_all(pinned.numpy()); eng.cmc_reset(*(sa or ()))
+        fresh, fresh_ms, fresh_n = timed(run_dom, per_launch, 3)
+        run_dom(300 * 4 * f ** 3 - 3 * per_launch)                    # age the alloy
+        aged, aged_ms, aged_n = timed(run_dom, per_launch, 3)
+        st = eng.cmc_state()
         t0 = time.perf_counter()
         n_e2e = 0
         for _ in range(3):
             eng.set_occupancy_all(pinned.numpy())
             eng.cmc_reset(*(sa or ()))
-            eng.cmc_run(trials, temperatures=temps, seed=5)
-            st = eng.cmc_state()
+            run_dom(per_launch)
+            n_e2e += int(eng.cmc_state()["steps"].sum())
             eng.get_occupancy_all()
-            n_e2e += int(st["steps"].sum())
         e2e = n_e2e / (time.perf_counter() - t0)
-        achieved = rate * BYTES_PER_TRIAL / 1e9
+        entry["domain"] = {"value": fresh, "aged": aged, "e2e": e2e, "kernel_ms": fresh_ms, "aged_kernel_ms": aged_ms, "trials_per_launch": fresh_n,
+                           "accept_ratio_aged": float(st["accepted"].sum() / max(1, st["steps"].sum())), "shape": eng.cmc_domain_last_shape(),
+                           "roofline": {"kernel": "cmc_domain_kernel", "bound": "hbm", "achieved": fresh * BYTES_PER_TRIAL / 1e9, "peak": peak, "unit": "GB/s",
+                                        "frac": fresh * BYTES_PER_TRIAL / 1e9 / peak, "frac_aged": aged * BYTES_PER_TRIAL / 1e9 / peak,
+                                        "traffic": recorded_traffic("cmc_domain_kernel", replicas=replicas, factor=f),
+                                        "note": "effective bandwidth (440 algorithmic B per trial, SURVEY 8(d)); a domain lives in shared memory for "
+                                                "a whole sweep, so the physical traffic is one read + one write of the occupancy per sweep"}}
+        # ---- global-pair driver (the reference's proposal)
+        trials = 200000 if f == 40 else (2000000 if f == 100 else 20000)
+        sa_g = (sa[0], 40000000) if sa else ()
+        run_glob = lambda n: eng.cmc_run(n, temperatures=temps, seed=5)
+        eng.set_occupancy_all(pinned.numpy()); eng.cmc_reset(*sa_g)
+        run_glob(trials // 4)
+        g_rate, g_ms, g_n = timed(run_glob, trials, 5)
+        st = eng.cmc_state()
         kernel = "cmc_grid_kernel" if replicas == 1 else "cmc_run_kernel"     # one lattice: whole-GPU cooperative kernel
-        out[name] = {"value": rate, "e2e": e2e, "replicas": replicas, "sites": 4 * f ** 3, "trials_per_launch": int(np.mean(done)),
-                     "kernel_ms": float(np.mean(kernel_ms)), "accept_ratio": float(st["accepted"].sum() / max(1, st["steps"].sum())),
-                     "driver": "SimulatedAnnealing schedule" if sa else "CanonicalMc at fixed temperature",
-                     "roofline": {"kernel": kernel, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                                  "frac": achieved / peak,
-                                  "traffic": recorded_traffic(kernel, replicas=replicas, factor=f, trials=trials)}}
+        entry["global_pairs"] = {"value": g_rate, "kernel_ms": g_ms, "trials_per_launch": g_n,
+                                 "accept_ratio": float(st["accepted"].sum() / max(1, st["steps"].sum())),
+                                 "roofline": {"kernel": kernel, "bound": "hbm", "achieved": g_rate * BYTES_PER_TRIAL / 1e9, "peak": peak, "unit": "GB/s",
+                                              "frac": g_rate * BYTES_PER_TRIAL / 1e9 / peak,
+                                              "traffic": recorded_traffic(kernel, replicas=replicas, factor=f, trials=trials)}}
+        entry["value"] = fresh
+        out[name] = entry
         eng.close()
     out["value"] = out["single_lattice_40x40x40"]["value"]
     if with_cpu:
@@ -535,36 +629,58 @@ def bench_swap_de_eval(torch, eng, occ, peak, n=1 << 22):
 
 
 def bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, json_path):
-    """BASELINE configs[3] over all GPUs of the job: ONE 4M-site lattice annealed by `world` ranks (replicated occupancy,
-    sharded dE evaluation, in-kernel peer-memory exchange: include/lmc_b200.h, lmc_cmc_attach_peers).  Every rank takes
-    part; the rate uses the slowest rank's kernel time; the ranks' final states must be identical."""
+    """BASELINE configs[3] / [1] over all GPUs of the job: ONE lattice annealed by `world` ranks with the domain driver
+    (x slabs of the domain grid, halo / migration rows written into peer memory inside the persistent kernel:
+    include/lmc_b200.h, lmc_cmc_domain_attach_peers).  Every rank takes part; the rate uses the slowest rank's kernel time;
+    all ranks must end identical AND equal to the single-GPU run of the same seed, which rank 0 computes in the same job."""
     import hashlib
     from latticemontecarlo_b200 import capi, sharding, synth
-    f, trials = 100, 2000000
-    eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=local_rank)
-    eng.load_coefficients(json_path)
-    occ = synth.random_alloy(f, P_MG, P_ZN, seed=1000, vacancy_site=None)
-    eng.set_occupancy(occ)
-    sharding.attach_cmc_peers(eng, rank, world)
-    eng.cmc_reset(900.0, 40000000)
-    dist.barrier(); torch.cuda.synchronize()
-    eng.cmc_grid_run(trials // 4, seed=5)
-    ms, done = [], []
-    for _ in range(5):
+    out = {}
+    for name, f, sa, trials in (("single_lattice_100x100x100_sa", 100, (900.0, 40000000000), 8 * 4000000), ("single_lattice_40x40x40", 40, (), 8 * 256000)):
+        occ = synth.random_alloy(f, P_MG, P_ZN, seed=1000, vacancy_site=None)
+
+        def digest(e):
+            st = e.cmc_state()
+            return hashlib.sha256(e.get_occupancy(0).tobytes()).hexdigest() + "%.17g %d %d %.17g" % (st["energy"][0], st["steps"][0], st["accepted"][0], st["temperature"][0])
+
+        def run(e, collective):
+            e.set_occupancy(occ)
+            e.cmc_reset(*sa)
+            e.cmc_domain_run(trials // 4, seed=5)
+            ms, done = [], []
+            for _ in range(3):
+                if collective:
+                    dist.barrier(); torch.cuda.synchronize()
+                s0 = int(e.cmc_state()["steps"][0])
+                e.cmc_domain_run(trials, seed=5)
+                ms.append(sharding.max_over_ranks([e.last_kernel_ms()], device="cuda")[0] if collective else e.last_kernel_ms())
+                done.append(int(e.cmc_state()["steps"][0]) - s0)
+            return sum(done) / (sum(ms) * 1e-3), float(np.mean(ms)), int(np.mean(done)), digest(e)
+
+        eng = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=local_rank)
+        eng.load_coefficients(json_path)
+        sharding.attach_cmc_domain_peers(eng, rank, world)
         dist.barrier(); torch.cuda.synchronize()
-        s0 = int(eng.cmc_state()["steps"][0])
-        eng.cmc_grid_run(trials, seed=5)
-        ms.append(sharding.max_over_ranks([eng.last_kernel_ms()], device="cuda")[0])
-        done.append(int(eng.cmc_state()["steps"][0]) - s0)
-    st = eng.cmc_state()
-    digest = hashlib.sha256(eng.get_occupancy(0).tobytes()).hexdigest() + "%.17g" % st["energy"][0]
-    digests = [None] * world
-    dist.all_gather_object(digests, digest)
-    eng.close()
-    return {"value": sum(done) / (sum(ms) * 1e-3), "unit": "trials/s", "n_gpus": world, "sites": 4 * f ** 3, "scaling": "strong",
-            "driver": "SimulatedAnnealing schedule", "trials_per_launch": int(np.mean(done)), "kernel_ms": float(np.mean(ms)),
-            "ranks_identical": len(set(digests)) == 1,
-            "exchange": "kept/accept masks + partial sums as 16-byte flag-in-data lines written into peer memory inside cmc_grid_kernel"}
+        rate, ms, done, dg = run(eng, True)
+        shape = eng.cmc_domain_last_shape()
+        digests = [None] * world
+        dist.all_gather_object(digests, dg)
+        eng.close()
+        single = None
+        if rank == 0:
+            ref = capi.Engine(f, id_order=capi.ORDER_REASSIGNED, n_walkers=1, device=local_rank)
+            ref.load_coefficients(json_path)
+            r1, ms1, _, dg1 = run(ref, False)
+            ref.close()
+            single = {"value": r1, "kernel_ms": ms1, "equals_multi_gpu_run": dg1 == dg}
+        out[name] = {"value": rate, "unit": "trials/s", "n_gpus": world, "sites": 4 * f ** 3, "scaling": "strong",
+                     "driver": "SimulatedAnnealing schedule" if sa else "CanonicalMc at fixed temperature", "trials_per_launch": done, "kernel_ms": ms,
+                     "shape": shape, "ranks_identical": len(set(digests)) == 1, "single_gpu_same_job": single,
+                     "speedup_vs_single_gpu_same_job": rate / single["value"] if single else None,
+                     "exchange": "domain rows written into the next sweep's holders through NVLink peer mappings inside cmc_domain_kernel; "
+                                 "sweep totals as flag-carrying lines (inter-GPU barrier); no NCCL call on the data path"}
+        dist.barrier()
+    return out
 
 
 def cpu_baseline_cmc(json_path):
@@ -610,11 +726,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--walkers", type=int, default=8192, help="walkers per GPU")
+    ap.add_argument("--walkers", type=int, default=8192, help="walkers of the job (strong scaling: w mod N); also walkers per GPU of the weak-scaling extra")
     ap.add_argument("--hops", type=int, default=2048, help="KMC steps per walker per bench step")
-    ap.add_argument("--ref-hops", type=int, default=4000, help="reference arm: hops per trajectory per step")
+    ap.add_argument("--ref-hops", type=int, default=20000, help="reference arm: hops per trajectory per step (same length as cpu_baseline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cmc", action="store_true", help="skip the secondary CMC measurement")
+    ap.add_argument("--no-age", action="store_true", help="skip the value-vs-walker-age and rich-alloy extras")
     ap.add_argument("--no-chain", action="store_true", help="skip the secondary second-order KMC measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -18,6 +18,20 @@ def shard_range(total: int, rank: int, world: int):
     return first, base + (1 if rank < extra else 0)
 
 
+def interleaved_walkers(total: int, rank: int, world: int):
+    """Global indices of the walkers owned by `rank` when walker w lives on GPU w mod world: neighbouring
+    walkers -- neighbouring temperatures, hence similar cost -- are dealt to different ranks, so every rank gets the same
+    mix and no rank is the slow one."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return np.arange(int(rank), int(total), int(world), dtype=np.int64)
+
+
+def temperatures_of(walkers, total: int, t_lo: float = 400.0, t_hi: float = 600.0):
+    """T_w = t_lo + (t_hi - t_lo) * w / (total - 1) for global walker indices."""
+    return t_lo + (t_hi - t_lo) * np.asarray(walkers, dtype=np.float64) / max(1, int(total) - 1)
+
+
 def walker_temperatures(first: int, count: int, total: int, t_lo: float = 400.0, t_hi: float = 600.0):
     """T_w = t_lo + (t_hi - t_lo) * w / (total - 1) for the global walker indices of this shard."""
     w = first + np.arange(count)

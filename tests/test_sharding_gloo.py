@@ -56,3 +56,24 @@ def test_evaluation_owner_partitions_the_warp_groups():
         assert all(0 <= o < world for o in owners)
         counts = [owners.count(r) for r in range(world)]
         assert max(counts) - min(counts) <= 1
+
+
+def test_interleaved_walkers_and_domain_slabs_partition_their_units():
+    """bench.py's strong-scaling KMC deals walker w to rank w mod N; the multi-GPU domain CMC driver gives rank r the x slab
+    [ndx r / N, ndx (r + 1) / N) of the domain grid (cmc_domain.h: domain_slab_begin)."""
+    for total in (1, 7, 8192, 8193):
+        for world in (1, 2, 3, 8):
+            parts = [sharding.interleaved_walkers(total, r, world) for r in range(world)]
+            assert np.array_equal(np.sort(np.concatenate(parts)), np.arange(total))
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+            t = np.concatenate([sharding.temperatures_of(p, total) for p in parts])
+            assert np.allclose(np.sort(t), 400.0 + 200.0 * np.arange(total) / max(1, total - 1))
+            # every rank sees the whole temperature range (that is the point of dealing w mod N)
+            if total >= 64:
+                assert all(sharding.temperatures_of(p, total).max() - sharding.temperatures_of(p, total).min() > 190.0 for p in parts)
+    for ndx in (1, 5, 10, 25):
+        for world in (1, 2, 4, 8):
+            slabs = [sharding.domain_slab(ndx, r, world) for r in range(world)]
+            assert slabs[0][0] == 0 and sum(c for _, c in slabs) == ndx
+            for (f0, c0), (f1, _) in zip(slabs, slabs[1:]):
+                assert f0 + c0 == f1
