@@ -192,6 +192,13 @@ int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_step
  * the meaning of lmc_kmc_run's (Ea / dE of the chosen k -> i event, total_rate = total_rate_k_). */
 int lmc_kmc_chain_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u,
                       const lmc_kmc_trace *trace);
+/* Restart (McAbstract constructor, mc/src/McAbstract.cpp:24-30: steps_ = restart_steps, energy_ = restart_energy, time_ =
+ * restart_time): overwrite the per-walker clocks after lmc_kmc_reset (host arrays [n_walkers], any may be NULL).  The time
+ * feeds T(t) and the rate corrector; the step number is the Philox counter, so a restarted run continues the random stream
+ * of the run it resumes instead of repeating its first uniforms.
+ * Note: lmc_engine_set_occupancy / lmc_engine_lattice_jump and any KMC error invalidate the KMC state -- the next run
+ * starts from lmc_kmc_reset (clocks at zero) unless this call follows the reset. */
+int lmc_kmc_set_state(lmc_engine *engine, const double *time, const double *energy, const int64_t *steps);
 /* per-walker state after the last run (host arrays [n_walkers], any may be NULL): McAbstract::time_, energy_, steps_ */
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy,
                       double *temperature);

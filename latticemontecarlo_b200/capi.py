@@ -334,6 +334,13 @@ class Engine:
         """mc::KineticMcChainOmpi::Simulate over all walkers (lmc_kmc_chain_run)."""
         return self.kmc_run(n_steps, replay_u2=replay_u, second_order=True, **kw)
 
+    def kmc_set_state(self, time=None, energy=None, steps=None):
+        """Restart: overwrite the per-walker clocks after kmc_reset (lmc_kmc_set_state)."""
+        t = None if time is None else np.ascontiguousarray(np.broadcast_to(time, self.n_walkers), dtype=np.float64)
+        e = None if energy is None else np.ascontiguousarray(np.broadcast_to(energy, self.n_walkers), dtype=np.float64)
+        s = None if steps is None else np.ascontiguousarray(np.broadcast_to(steps, self.n_walkers), dtype=np.int64)
+        _check(lib().lmc_kmc_set_state(self.h, _p(t), _p(e), _p(s)))
+
     def kmc_state(self):
         n = self.n_walkers
         out = dict(time=np.empty(n), energy=np.empty(n), steps=np.empty(n, np.int64), vacancy=np.empty(n, np.int64),

@@ -385,6 +385,7 @@ void Engine::set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_
   if (walker < 0 || count < 1 || walker + count > n_walkers) throw std::invalid_argument("walker index out of range");
   if (n != lat.num_sites * count) throw std::invalid_argument("occupancy length must be num_sites per walker");
   cmc_ready = false;                       // the CMC mirror / cell arrays are rebuilt by the next lmc_cmc_reset (or run)
+  kmc_ready = false;                       // vacancy position, concentrations and clocks belong to the old configuration
   uint8_t *d_in = static_cast<uint8_t *>(scratch(static_cast<size_t>(n)));
   LMC_CUDA(cudaMemcpyAsync(d_in, occ, static_cast<size_t>(n), cudaMemcpyHostToDevice, stream));
   const int threads = 256;
@@ -423,6 +424,7 @@ void Engine::lattice_jump(int32_t walker, int64_t a, int64_t b) {
   if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
   if (a < 0 || b < 0 || a >= lat.num_sites || b >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
   cmc_ready = false;
+  kmc_ready = false;                       // the vacancy may have moved: the next KMC run locates it again (clocks restart)
   lattice_jump_kernel<<<1, 32, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker) * lat.padded_size, a, b);
   LMC_CUDA(cudaGetLastError());
   LMC_CUDA(cudaStreamSynchronize(stream));
@@ -761,6 +763,19 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     }
 }
 
+void Engine::kmc_set_state(const double *time, const double *energy, const int64_t *steps) {
+  require_device();
+  if (!kmc_ready) kmc_reset();
+  const size_t nw = static_cast<size_t>(n_walkers);
+  if (steps)
+    for (size_t w = 0; w < nw; ++w)
+      if (steps[w] < 0) throw std::invalid_argument("steps must be >= 0");
+  if (time) LMC_CUDA(cudaMemcpyAsync(d_kmc_time, time, nw * 8, cudaMemcpyHostToDevice, stream));
+  if (energy) LMC_CUDA(cudaMemcpyAsync(d_kmc_energy, energy, nw * 8, cudaMemcpyHostToDevice, stream));
+  if (steps) LMC_CUDA(cudaMemcpyAsync(d_kmc_steps, steps, nw * 8, cudaMemcpyHostToDevice, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
 void Engine::kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {
   require_device();
   if (!d_kmc_vacancy) throw std::invalid_argument("lmc_kmc_reset has not been called");
@@ -1077,15 +1092,16 @@ void Engine::cmc_domain_run(const lmc_cmc_params &params, const lmc_cmc_domain_p
   const long long items_total = static_cast<long long>(n_walkers) * dp.ndx * dp.ndy * dp.ndz;
   const int slab = domain_slab_begin(dp.ndx, dom_world, dom_rank + 1) - domain_slab_begin(dp.ndx, dom_world, dom_rank);
   const long long items_rank = static_cast<long long>(n_walkers) * slab * dp.ndy * dp.ndz;
-  // lanes per trial (G) and trials of a domain in flight (S), from the domains this rank holds per SM: few domains -> a
-  // whole warp per domain as four speculative trials of 8 lanes; many -> 8 lanes per domain, four domains per warp, no
-  // speculation.  Launch shape only: the trajectory does not depend on it.
+  // lanes per trial (G) and trials of a domain in flight (S).  Measured on B200 (tools/domain_probe.py): 8 lanes per trial and
+  // four speculative trials per domain -- a whole warp per domain -- win at every load from 7 to 125 domains per SM (when the
+  // domains outnumber the 32 warps of a block they are handed out dynamically over several passes: the domains of a sweep
+  // differ in cost by 2x, and a domain that runs four trials at a time leaves less of a tail).  Launch shape only: the
+  // trajectory does not depend on it.
   int lanes = dom ? dom->lanes : 0, spec = dom ? dom->speculate : 0;
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_LANES")) lanes = std::atoi(v);        // tuning knobs
   if (const char *v = std::getenv("LMC_CMC_DOMAIN_SPECULATE")) spec = std::atoi(v);
-  const double dom_per_sm = static_cast<double>(items_rank) / sms;
-  if (lanes <= 0) lanes = spec == 1 && dom_per_sm <= 8.0 ? 32 : 8;
-  if (spec <= 0) spec = lanes == 8 ? (dom_per_sm <= 16.0 ? 4 : (dom_per_sm <= 32.0 ? 2 : 1)) : (lanes == 16 && dom_per_sm <= 16.0 ? 2 : 1);
+  if (lanes <= 0) lanes = spec == 1 ? 8 : (spec == 2 ? 16 : 8);
+  if (spec <= 0) spec = lanes == 8 ? 4 : (lanes == 16 ? 2 : 1);
   if (lanes != 8 && lanes != 16 && lanes != 32) throw std::invalid_argument("lanes per trial must be 8, 16 or 32");
   if (!((spec == 1) || (spec == 2 && (lanes == 8 || lanes == 16)) || (spec == 4 && lanes == 8)))
     throw std::invalid_argument("speculate must be 1, 2 (8 or 16 lanes) or 4 (8 lanes)");
@@ -1597,6 +1613,9 @@ int lmc_kmc_chain_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t 
     if (!params) throw std::invalid_argument("null params");
     engine->impl->kmc_run(*params, n_steps, nullptr, replay_u, trace, true);
   });
+}
+int lmc_kmc_set_state(lmc_engine *engine, const double *time, const double *energy, const int64_t *steps) {
+  return guard([&] { engine->impl->kmc_set_state(time, energy, steps); });
 }
 int lmc_kmc_get_state(lmc_engine *engine, double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature) {
   return guard([&] { engine->impl->kmc_get_state(time, energy, steps, vacancy, temperature); });

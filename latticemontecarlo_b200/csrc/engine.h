@@ -54,6 +54,7 @@ class Engine {
   void kmc_reset();
   void kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace,
                bool second_order);
+  void kmc_set_state(const double *time, const double *energy, const int64_t *steps);
   void kmc_get_state(double *time, double *energy, int64_t *steps, int64_t *vacancy, double *temperature);
 
   void cmc_reset(double sa_initial_temperature, uint64_t sa_maximum_steps);

@@ -512,6 +512,13 @@ void run_kmc(const Parameter &p, bool second_order) {
   const auto occ = config.occupancy();
   check(lmc_engine_set_occupancy(eng.e, 0, occ.data(), static_cast<int64_t>(occ.size())));
   check(lmc_kmc_reset(eng.e));
+  if (p.restart_steps > 0) {
+    // McAbstract.cpp:24-30: a restarted run resumes the clocks; on the device the time feeds T(t) / the rate corrector and
+    // the step number is the Philox counter (the resumed run continues the random stream instead of repeating it)
+    const double t0 = p.restart_time, e0 = p.restart_energy;
+    const int64_t s0 = static_cast<int64_t>(p.restart_steps);
+    check(lmc_kmc_set_state(eng.e, &t0, &e0, &s0));
+  }
   double absolute_energy = 0;
   check(lmc_total_energy(eng.e, 0, &absolute_energy, nullptr, 0));   // McAbstract.cpp:26
   const auto tt = read_time_temperature(p.time_temperature_filename);
@@ -586,20 +593,22 @@ void run_kmc(const Parameter &p, bool second_order) {
           escaped = true;
         }
       }
-      // Dump (:59-104)
+      // Dump (:59-104).  IsEscaped has already set steps_ = maximum_steps_ + 1 when the vacancy escaped (:219), so the dump of the
+      // escape step is taken with that step number
+      const unsigned long long dump_steps = escaped ? p.maximum_steps + 1 : steps;
       if (skip_first_dump) {
         skip_first_dump = false;
       } else {
-        if (steps == 0) {
+        if (dump_steps == 0) {
           log << "steps\ttime\ttemperature\tenergy\tEa\tdE\tselected\tvac1\tvac2\tvac3";
           if (p.solute_disp) log << "\tsolute_com1\tsolute_com2\tsolute_com3";
           log << std::endl;
         }
-        if (p.config_dump_steps && steps % p.config_dump_steps == 0) config.write(std::to_string(steps) + ".cfg.gz");
-        if (steps == p.maximum_steps) config.write("end.cfg.gz");
-        if (log_this_step(steps, p.log_dump_steps)) {
+        if (p.config_dump_steps && dump_steps % p.config_dump_steps == 0) config.write(std::to_string(dump_steps) + ".cfg.gz");
+        if (dump_steps == p.maximum_steps) config.write("end.cfg.gz");
+        if (log_this_step(dump_steps, p.log_dump_steps)) {
           const Vec3 v = config.unwrapped_position_of_lattice(vacancy);
-          log << steps << '\t' << time << '\t' << temperature << '\t' << energy << '\t' << Ea[s] << '\t' << dE[s] << '\t'
+          log << dump_steps << '\t' << time << '\t' << temperature << '\t' << energy << '\t' << Ea[s] << '\t' << dE[s] << '\t'
               << config.lattice_to_atom[static_cast<size_t>(to[s])] << '\t';
           log << std::fixed << v[0] << ' ' << v[1] << ' ' << v[2];   // operator<<(Vector_d) switches the stream to fixed for good
           if (p.solute_disp) log << '\t' << solute_com[0] << ' ' << solute_com[1] << ' ' << solute_com[2];

@@ -41,7 +41,13 @@
 #include "KineticMcFirstOmp.h"
 #include "KineticMcChainOmpi.h"
 #include "CanonicalMcSerial.h"
+// CanonicalMcOmp keeps its batch (event_vector_, BuildEventVector) private and offers no hook between the batch build and
+// the per-event accept loop; the traced driver below re-runs CanonicalMcOmp::Simulate's loop with the class's own
+// building blocks, which needs access to them.  Access specifiers do not change the layout, and every header
+// CanonicalMcOmp.h pulls in is already included (guarded) above, so the redefinition touches that one class only.
+#define private public
 #include "CanonicalMcOmp.h"
+#undef private
 #include "SimulatedAnnealing.h"
 
 namespace {
@@ -320,6 +326,51 @@ class QuietCmcOmp : public mc::CanonicalMcOmp {
 
  protected:
   void Dump() const override {}
+};
+
+// mc::CanonicalMcOmp::Simulate (mc/src/CanonicalMcOmp.cpp:80-92) with one trace record per event: the batch is built by the
+// reference's own BuildEventVector (greedy serial pass with the unavailable_position_ rule, dE evaluated for the whole batch
+// on the batch-start configuration), then the events are accepted / rejected in order.
+class TracedCmcOmp : public mc::CanonicalMcOmp {
+ public:
+  using mc::CanonicalMcOmp::CanonicalMcOmp;
+  void Reseed(uint64_t seed) { generator_.seed(seed); }
+  void SetTrace(SwapTrace *t, int64_t *batch_of) { trace_ = t; batch_of_ = batch_of; }
+  const cfg::Config &config() const { return config_; }
+  double energy() const { return energy_; }
+  unsigned long long steps() const { return steps_; }
+  void SimulateTraced() {
+    int64_t batch = 0;
+    while (steps_ <= maximum_steps_) {
+      BuildEventVector();
+      for (auto [pair, dE] : event_vector_) {
+        thermodynamic_averaging_.AddEnergy(energy_);
+        if (trace_ && trace_->n < trace_->cap) {
+          const int64_t k = trace_->n++;
+          trace_->a[k] = static_cast<int64_t>(pair.first);
+          trace_->b[k] = static_cast<int64_t>(pair.second);
+          trace_->energy_before[k] = energy_;
+          trace_->temperature[k] = dE;
+          if (batch_of_) batch_of_[k] = batch;
+          if (trace_->u) {
+            auto g = generator_;
+            std::uniform_real_distribution<double> d(0.0, 1.0);
+            trace_->u[k] = d(g);  // SelectEvent consumes it iff dE >= 0
+          }
+        }
+        SelectEvent(pair, dE);
+        ++steps_;
+      }
+      ++batch;
+    }
+  }
+
+ protected:
+  void Dump() const override {}
+
+ private:
+  SwapTrace *trace_{nullptr};
+  int64_t *batch_of_{nullptr};
 };
 
 class TracedSa : public mc::SimulatedAnnealing {
@@ -794,6 +845,31 @@ double ref_cmc_omp(void *config_h, const char *json, const int *codes, int ncode
     cmc.Reseed(seed);
     const double t0 = now_s();
     cmc.Simulate();
+    const double t1 = now_s();
+    copy_occupancy(cmc.config(), final_occ);
+    if (final_energy) *final_energy = cmc.energy();
+    if (steps_done) *steps_done = cmc.steps();
+    return t1 - t0;
+  } catch (const std::exception &e) { fail(e); return -1.0; }
+}
+
+// mc::CanonicalMcOmp with a trace (pair, dE, energy before, the uniform SelectEvent would draw, batch number per event).
+double ref_cmc_omp_traced(void *config_h, const char *json, const int *codes, int ncodes, double temperature,
+                          uint64_t maximum_steps, uint64_t seed, int threads, const char *workdir, int64_t trace_cap, int64_t *a,
+                          int64_t *b, double *dE, double *energy_before, double *u, int64_t *batch_of, uint8_t *final_occ,
+                          double *final_energy, uint64_t *steps_done) {
+  try {
+    ScopedChdir cd(workdir);
+    ScopedQuietCout quiet;
+    if (threads > 0) omp_set_num_threads(threads);
+    TracedCmcOmp cmc(*static_cast<cfg::Config *>(config_h), 1ULL << 62, 1ULL << 62, maximum_steps, 0, 0, 0.0, temperature,
+                     element_set_from_codes(codes, ncodes), json);
+    cmc.Reseed(seed);
+    SwapTrace tr;
+    tr.cap = trace_cap; tr.a = a; tr.b = b; tr.temperature = dE; tr.energy_before = energy_before; tr.u = u;
+    cmc.SetTrace(&tr, batch_of);
+    const double t0 = now_s();
+    cmc.SimulateTraced();
     const double t1 = now_s();
     copy_occupancy(cmc.config(), final_occ);
     if (final_energy) *final_energy = cmc.energy();

@@ -24,9 +24,12 @@ ELEMENT_CODES = {"X": 0, "Al": 1, "Mg": 2, "Zn": 3, "Cu": 4, "Sn": 5}
 
 def build(force: bool = False) -> bool:
     """Compile oracle/_ref/liblmc_ref.so if the reference sources are present. Returns availability."""
-    if os.path.exists(_SO) and not force:
+    have_ref = os.path.isdir(os.path.join(REFERENCE_ROOT, "lmc"))
+    stale = have_ref and os.path.exists(_SO) and os.path.getmtime(_SO) < max(
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("ref_harness.cpp", "Makefile"))      # the harness grew an entry point
+    if os.path.exists(_SO) and not force and not stale:
         return True
-    if not os.path.isdir(os.path.join(REFERENCE_ROOT, "lmc")):
+    if not have_ref:
         return os.path.exists(_SO)
     subprocess.run(["make", "-C", _HERE, "-j8", "all"], check=True, stdout=subprocess.DEVNULL)
     return os.path.exists(_SO)
@@ -51,7 +54,7 @@ def lib():
             getattr(_lib, name).restype = C.c_void_p
         for name in ("ref_config_num_sites", "ref_mapping", "ref_config_vacancy"):
             getattr(_lib, name).restype = C.c_int64
-        for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_sa", "ref_rate_correction",
+        for name in ("ref_kmc_first_omp", "ref_cmc_serial", "ref_cmc_omp", "ref_cmc_omp_traced", "ref_sa", "ref_rate_correction",
                      "ref_kmc_first_omp_with_logs", "ref_cmc_serial_with_logs", "ref_kmc_chain_ompi", "ref_kmc_chain_ompi_with_logs"):
             getattr(_lib, name).restype = C.c_double
     return _lib
@@ -491,6 +494,24 @@ def cmc_omp(config: RefConfig, json_path, elements=("Al", "Mg", "Zn"), temperatu
     if sec < 0:
         raise RuntimeError(_err())
     return dict(seconds=sec, final_occ=occ, final_energy=fe.value, steps=int(steps.value))
+
+
+def cmc_omp_traced(config: RefConfig, json_path, elements=("Al", "Mg", "Zn"), temperature=800.0, maximum_steps=100, seed=1, threads=4):
+    """mc::CanonicalMcOmp with `threads` OMP threads (= batch size) and one trace record per event."""
+    _, p, n = _codes(elements)
+    cap = int(maximum_steps) + 2 * int(threads) + 2            # the last batch may run past maximum_steps
+    a = np.zeros(cap, dtype=np.int64); b = np.zeros(cap, dtype=np.int64); batch = np.zeros(cap, dtype=np.int64)
+    de = np.zeros(cap, dtype=np.float64); eb = np.zeros(cap, dtype=np.float64); u = np.zeros(cap, dtype=np.float64)
+    occ = np.empty(config.num_sites, dtype=np.uint8)
+    fe = C.c_double(); steps = C.c_uint64()
+    with tempfile.TemporaryDirectory() as d:
+        sec = lib().ref_cmc_omp_traced(config.h, str(json_path).encode(), p, n, C.c_double(temperature), C.c_uint64(int(maximum_steps)),
+                                       C.c_uint64(int(seed)), int(threads), d.encode(), C.c_int64(cap), _p(a), _p(b), _p(de), _p(eb), _p(u),
+                                       _p(batch), _p(occ), C.byref(fe), C.byref(steps))
+    if sec < 0:
+        raise RuntimeError(_err())
+    k = int(steps.value)
+    return dict(seconds=sec, a=a[:k], b=b[:k], dE=de[:k], energy_before=eb[:k], u=u[:k], batch=batch[:k], final_occ=occ, final_energy=fe.value, steps=k)
 
 
 def simulated_annealing(factor, solvent, solute_counts: dict, occ, json_path, initial_temperature=700.0,

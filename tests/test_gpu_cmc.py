@@ -37,6 +37,25 @@ def test_cmc_replay_reproduces_reference_chain(golden, tag, tmp_path):
     assert abs(st["energy"][1] - (g("energy_before")[-1] + (g("dE")[-1] if out["accepted"][-1] else 0.0))) < 1e-9
 
 
+@pytest.mark.parametrize("tag", ["P", "Q"])
+def test_cmc_replay_reproduces_reference_omp_chain(golden, tag, tmp_path):
+    """The trace of mc::CanonicalMcOmp (batches of non-interfering trials, dE on the batch-start configuration:
+    mc/src/CanonicalMcOmp.cpp:40-92; tests/golden/make_golden_omp.py) replayed through lmc_cmc_replay."""
+    import os
+    omp = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_omp_v1.npz"), allow_pickle=False)
+    g = lambda k: omp["%s_%s" % (tag, k)]
+    f, reassign, _, temperature, _ = g("params")
+    e = capi.Engine(int(f), id_order=capi.ORDER_REASSIGNED if int(reassign) else capi.ORDER_GENERATE, device=0)
+    e.load_coefficients(H.golden_json(golden, tmp_path))
+    e.set_occupancy(g("occ"))
+    e.cmc_reset()
+    out = e.cmc_replay(g("a"), g("b"), g("u"), temperature=float(temperature))
+    assert np.max(np.abs(out["dE"] - g("dE"))) < TOL
+    assert np.max(np.abs(out["energy_before"] - g("energy_before"))) < 1e-9
+    assert np.array_equal(e.get_occupancy(0), g("final_occ"))
+    assert abs(e.cmc_state()["energy"][0] - g("final_energy")[0]) < 1e-9
+
+
 def test_simulated_annealing_replay_reproduces_reference_schedule(golden, tmp_path):
     f, t0, steps = golden["SA_params"]
     e = capi.Engine(int(f), id_order=capi.ORDER_GENERATE, device=0)

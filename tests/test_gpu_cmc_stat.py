@@ -1,0 +1,136 @@
+"""GPU suite: STATISTICAL parity of every CMC / SA chain that is not a replay of the reference's random stream.
+
+The batched drivers (lmc_cmc_run: priority-claim batches; lmc_cmc_grid_run: whole-GPU batches) keep the reference's global
+pair draw but compose their batches differently, and the domain driver (lmc_cmc_domain_run) draws its pairs inside spatial
+domains.  All are Metropolis chains on the same energy model, so their stationary distribution must be the canonical one
+that mc::CanonicalMcSerial samples.  Reference ensembles come from the unmodified reference (oracle/_ref):
+  tests/golden/golden_cmc_stat_v1.npz   CanonicalMcSerial, 6x6x6 Al-6%Mg-6%Zn, 1500 K, 16 seeds x 2e6 trials
+                                        (tests/golden/make_golden_cmc_stat.py)
+  tests/golden/golden_sa_stat_v1.npz    SimulatedAnnealing, same cell, T0 = 1500 K, 16 seeds x 3e5 trials
+                                        (tests/golden/make_golden_sa_stat.py)
+Compared per driver: mean energy, energy variance and the first-neighbour Warren-Cowley parameters of Mg-Mg, Zn-Zn and
+Mg-Zn pairs -- ensemble means within 3 standard errors (of the difference of the two ensemble means).  The acceptance
+ratio is printed but not compared: it is a property of the proposal, not of the stationary distribution (on this 864-site
+cell a trial blocks a tenth of the lattice for the rest of its batch, so batches keep isolated trials more often than
+trials in solute-rich regions; the domain driver proposes pairs inside one core)."""
+import os
+
+import numpy as np
+import pytest
+
+from latticemontecarlo_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+Z_MAX = 3.0
+
+
+def _warren_cowley(occ, nn1):
+    out = []
+    for i, j in ((2, 2), (3, 3), (2, 3)):
+        sites = np.nonzero(occ == i)[0]
+        out.append(1.0 - np.mean(occ[nn1[sites]] == j) / np.mean(occ == j))
+    return out
+
+
+def _setup(tmp_path, n_walkers):
+    ref = np.load(os.path.join(GOLD, "golden_cmc_stat_v1.npz"), allow_pickle=False)
+    factor, p_mg, p_zn, occ_seed, temperature, _, _, _, burn_in, json_seed = ref["params"]
+    js = str(tmp_path / "coef_stat.json")
+    synth.write_synthetic_json(js, seed=int(json_seed))
+    occ = synth.random_alloy(int(factor), float(p_mg), float(p_zn), seed=int(occ_seed), vacancy_site=None)
+    e = capi.Engine(int(factor), id_order=capi.ORDER_GENERATE, n_walkers=n_walkers, device=0)
+    e.load_coefficients(js)
+    nn1 = np.stack([e.neighbors(1, s) for s in range(occ.size)])
+    return ref, e, occ, nn1, float(temperature), int(burn_in)
+
+
+def _ensemble(e, occ, nn1, run, n_trials, burn_in, sample_every=5000, sro_every=10):
+    """Per-replica (mean energy, energy variance, acceptance ratio, SRO x 3) after the burn-in; energies are sampled every
+    `sample_every` trials (relative to the common initial configuration, like the reference's energy_)."""
+    nw = e.n_walkers
+    e.set_occupancy_all(np.tile(occ, (nw, 1)))
+    e.cmc_reset()
+    samples, sro, st_burn = [], [], None
+    k = 0
+    while True:
+        run(sample_every)
+        st = e.cmc_state()
+        if st["steps"].min() < burn_in:
+            continue
+        if st_burn is None:
+            st_burn = {q: st[q].copy() for q in ("steps", "accepted")}
+        samples.append(st["energy"].copy())
+        k += 1
+        if k % sro_every == 0:
+            final = e.get_occupancy_all()
+            sro.append([_warren_cowley(final[w], nn1) for w in range(nw)])
+        if st["steps"].min() >= n_trials:
+            break
+    samples = np.array(samples)                                   # [sample][replica]
+    acc = (st["accepted"] - st_burn["accepted"]) / np.maximum(1, st["steps"] - st_burn["steps"])
+    return {"mean_energy": samples.mean(axis=0), "var_energy": samples.var(axis=0), "accept_ratio": acc, "sro": np.mean(np.array(sro), axis=0)}
+
+
+def _compare(name, ours, ref, keys=("mean_energy", "var_energy", "sro")):
+    if "accept_ratio" in ours:
+        print("%-28s accept_ratio  ours %.4f  reference %.4f (not compared)" % (name, np.mean(ours["accept_ratio"]), np.mean(ref["accept_ratio"])))
+    worst = []
+    for key in keys:
+        a, b = np.asarray(ours[key], dtype=np.float64), np.asarray(ref[key], dtype=np.float64)
+        se = np.sqrt(a.var(axis=0, ddof=1) / a.shape[0] + b.var(axis=0, ddof=1) / b.shape[0])
+        z = np.abs(a.mean(axis=0) - b.mean(axis=0)) / se
+        print("%-28s %-13s ours %s  reference %s  z %s" % (name, key, np.round(a.mean(axis=0), 4), np.round(b.mean(axis=0), 4), np.round(z, 2)))
+        worst.append((float(np.max(z)), key))
+    assert max(worst)[0] < Z_MAX, (name, worst)
+
+
+def test_global_pair_batches_sample_the_canonical_ensemble(tmp_path):
+    ref, e, occ, nn1, temperature, burn_in = _setup(tmp_path, 16)
+    ours = _ensemble(e, occ, nn1, lambda n: e.cmc_run(n, temperature=temperature, seed=101), 2000000, burn_in)
+    _compare("lmc_cmc_run (16 replicas)", ours, ref)
+
+
+@pytest.mark.parametrize("edge", [0, 6])
+def test_domain_driver_samples_the_canonical_ensemble(tmp_path, edge):
+    """edge 0: one domain per replica (core = the cell minus two frozen planes per axis, moving every sweep);
+    edge 6: 2 x 2 x 2 domains of 32 core sites each."""
+    ref, e, occ, nn1, temperature, burn_in = _setup(tmp_path, 16)
+    ours = _ensemble(e, occ, nn1, lambda n: e.cmc_domain_run(n, temperature=temperature, seed=202, domain_edge=edge), 2000000, burn_in)
+    _compare("lmc_cmc_domain_run edge %d" % edge, ours, ref)
+
+
+def test_whole_gpu_batches_sample_the_canonical_ensemble(tmp_path):
+    """lmc_cmc_grid_run drives one lattice per engine: 8 seeds x 6e5 trials."""
+    ref, e, occ, nn1, temperature, burn_in = _setup(tmp_path, 1)
+    parts = []
+    for seed in range(8):
+        parts.append(_ensemble(e, occ, nn1, lambda n: e.cmc_grid_run(n, temperature=temperature, seed=300 + seed, batch_size=32), 600000, burn_in))
+    ours = {k: np.concatenate([p[k] if p[k].ndim == 1 else p[k] for p in parts]) for k in parts[0]}
+    _compare("lmc_cmc_grid_run (8 seeds)", ours, ref)
+
+
+@pytest.mark.parametrize("driver", ["batched", "domain"])
+def test_batched_simulated_annealing_final_state_distribution(tmp_path, driver):
+    """mc::SimulatedAnnealing applies its schedule per trial, the batched drivers per batch / per sweep (stated
+    approximation): the distribution of the final energy and of the final short-range order over 16 seeds must agree."""
+    ref = np.load(os.path.join(GOLD, "golden_sa_stat_v1.npz"), allow_pickle=False)
+    factor, p_mg, p_zn, occ_seed, t0, max_steps, n_seeds, json_seed = ref["params"]
+    js = str(tmp_path / "coef_stat.json")
+    synth.write_synthetic_json(js, seed=int(json_seed))
+    occ = synth.random_alloy(int(factor), float(p_mg), float(p_zn), seed=int(occ_seed), vacancy_site=None)
+    nw = int(n_seeds)
+    e = capi.Engine(int(factor), id_order=capi.ORDER_GENERATE, n_walkers=nw, device=0)
+    e.load_coefficients(js)
+    nn1 = np.stack([e.neighbors(1, s) for s in range(occ.size)])
+    e.set_occupancy_all(np.tile(occ, (nw, 1)))
+    e.cmc_reset(float(t0), int(max_steps))
+    if driver == "batched":
+        e.cmc_run(int(max_steps), seed=77)
+    else:
+        e.cmc_domain_run(int(max_steps), seed=77, rounds_per_sweep=64)      # short sweeps: the schedule is applied per sweep
+    st = e.cmc_state()
+    final = e.get_occupancy_all()
+    ours = {"final_energy": st["energy"], "sro": np.array([_warren_cowley(final[w], nn1) for w in range(nw)])}
+    assert np.all(st["steps"] >= max_steps) and np.all(st["steps"] < 1.02 * max_steps)
+    _compare("SimulatedAnnealing (%s)" % driver, ours, ref, keys=("final_energy", "sro"))

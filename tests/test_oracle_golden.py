@@ -176,6 +176,38 @@ def test_cmc_replay(golden, tag):
     assert 0.05 < tr["accepted"].mean() < 0.95
 
 
+@pytest.mark.parametrize("tag", ["P", "Q"])
+def test_cmc_omp_batches(golden, tag):
+    """mc::CanonicalMcOmp (mc/src/CanonicalMcOmp.cpp:40-92), golden_omp_v1.npz: every batch holds at most `threads` trials,
+    no trial site lies within the 43-site neighbourhoods of an earlier trial of its batch (the unavailable_position_ rule),
+    the dE the reference evaluated on the batch-START configuration equals the dE the serial chain sees, and the serial
+    replay of the stream reproduces its energies and final occupancy."""
+    import os
+    omp = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_omp_v1.npz"), allow_pickle=False)
+    g = lambda k: omp["%s_%s" % (tag, k)]
+    f, reassign, threads, temperature, _ = g("params")
+    co = H.golden_coefficients(golden)
+    cfg = O.Config.generate_fcc(int(f), None)
+    if int(reassign):
+        cfg.reassign_lattice_vector()
+    cfg.occ[:] = g("occ")
+    pred = O.EnergyChangePredictorPairSite(co, cfg, H.CODES)
+    a, b, batch = g("a"), g("b"), g("batch")
+    for q in range(int(batch[-1]) + 1):
+        idx = np.nonzero(batch == q)[0]
+        assert 1 <= len(idx) <= int(threads)
+        taken = set()
+        for i in idx:
+            assert int(a[i]) not in taken and int(b[i]) not in taken
+            for s in (int(a[i]), int(b[i])):
+                taken.update(int(x) for x in cfg.neighbors_set_of_site(s))
+                taken.add(s)
+    tr = O.metropolis_trials(cfg, pred, a, b, g("u"), temperature=float(temperature))
+    assert np.max(np.abs(tr["dE"] - g("dE"))) < TOL
+    assert np.max(np.abs(tr["energy_before"] - g("energy_before"))) < 1e-9
+    assert np.array_equal(cfg.occ, g("final_occ"))
+
+
 def test_simulated_annealing_replay(golden):
     co = H.golden_coefficients(golden)
     f, t0, steps = golden["SA_params"]

@@ -83,12 +83,14 @@ if __name__ == "__main__":
         check(24, 1, 200000)
         check(24, 1, 200000, lanes=2)
     if mode in ("all", "rate"):
-        for lanes, spec in ((32, 1), (16, 2), (8, 4), (8, 2)):
-            rate(40, 1, 20000000, lanes=lanes, speculate=spec)
-        rate(40, 1, 20000000, domain_edge=6, rounds_per_sweep=216, lanes=8, speculate=4)
-        rate(40, 1, 20000000, domain_edge=6, rounds_per_sweep=216, lanes=16, speculate=2)
-        rate(100, 1, 200000000, lanes=8, speculate=1)
-        rate(20, 148, 200000, lanes=8, speculate=1)
-        rate(40, 1, 2000000)
-        rate(40, 1, 2000000, domain_edge=6, rounds_per_sweep=216)
-        rate(100, 1, 20000000)
+        for lanes, spec in ((8, 1), (8, 2), (8, 4)):
+            rate(100, 1, 8 * 4 * 100 ** 3, lanes=lanes, speculate=spec)
+        os.environ["LMC_CMC_DOMAIN_THREADS"] = "512"
+        for lanes, spec in ((8, 1), (8, 2), (8, 4)):
+            rate(100, 1, 8 * 4 * 100 ** 3, lanes=lanes, speculate=spec)
+        rate(20, 148, 8 * 32000, lanes=8, speculate=4)
+        rate(20, 148, 8 * 32000, lanes=8, speculate=2)
+        del os.environ["LMC_CMC_DOMAIN_THREADS"]
+        rate(20, 148, 8 * 32000, lanes=8, speculate=4)
+        rate(20, 148, 8 * 32000, lanes=8, speculate=2)
+        rate(20, 148, 8 * 32000, lanes=8, speculate=1)
