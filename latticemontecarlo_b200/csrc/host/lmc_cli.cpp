@@ -69,6 +69,7 @@ struct Parameter {
   unsigned long long seed{0};
   bool seed_given{false};
   std::string replay_uniforms_filename;   // validation: "u1 u2" per KMC step instead of the device RNG
+  std::string replay_trials_filename;     // validation: "site_a site_b u" per CMC trial (the reference's serial stream)
   int device{0};
 
   static std::vector<std::string> split(const std::string &s) {
@@ -116,6 +117,7 @@ struct Parameter {
         for (size_t i = 1; i < segs.size(); ++i) solute_number_set.push_back(std::stoul(segs[i]));
       } else if (k == "seed") { seed = std::stoull(v); seed_given = true; }
       else if (k == "replay_uniforms_filename") replay_uniforms_filename = v;
+      else if (k == "replay_trials_filename") replay_trials_filename = v;
       else if (k == "device") device = std::stoi(v);
     }
   }
@@ -756,6 +758,50 @@ void run_swap_driver(const Parameter &p, bool annealing) {
           << absolute_energy0 + (energy - energy0) << std::endl;
     }
   };
+  if (!annealing && !p.replay_trials_filename.empty()) {
+    // Replay of the reference's serial trial stream (CanonicalMcSerial::Simulate, mc/src/CanonicalMcSerial.cpp:40-51): per
+    // step AddEnergy(energy_), Dump(), then the trial -- so the sliding window of ThermodynamicAveraging holds consecutive
+    // steps, the log rows and the .cfg dumps (atom identities through Config::LatticeJump) are the reference's own.
+    std::vector<int64_t> ta, tb;
+    std::vector<double> tu;
+    {
+      std::ifstream ifs(p.replay_trials_filename);
+      if (!ifs) throw std::runtime_error("Cannot open " + p.replay_trials_filename);
+      long long a, b;
+      for (double u; ifs >> a >> b >> u;) { ta.push_back(a); tb.push_back(b); tu.push_back(u); }
+    }
+    const unsigned long long n_total = p.maximum_steps >= start_steps ? p.maximum_steps - start_steps + 1 : 0;
+    if (ta.size() < n_total) throw std::runtime_error("replay_trials_filename holds too few rows");
+    bool skip_first_dump = restarted;
+    unsigned long long steps_r = start_steps;
+    double absolute_energy = absolute_energy0;
+    std::vector<double> dE(4096), e_before(4096), t_before(4096);
+    std::vector<uint8_t> accepted(4096);
+    for (unsigned long long done = 0; done < n_total;) {
+      const size_t chunk = static_cast<size_t>(std::min<unsigned long long>(4096, n_total - done));
+      check(lmc_cmc_replay(eng.e, 0, &prm, static_cast<int64_t>(chunk), ta.data() + done, tb.data() + done, tu.data() + done, dE.data(),
+                           e_before.data(), t_before.data(), accepted.data()));
+      for (size_t s = 0; s < chunk; ++s, ++steps_r) {
+        const double energy_now = energy0 + e_before[s];
+        averaging.AddEnergy(energy_now);
+        if (skip_first_dump) skip_first_dump = false;
+        else {                                                  // CanonicalMcAbstract::Dump (mc/src/CanonicalMcAbstract.cpp:53-84)
+          if (steps_r == 0) log << "steps\ttemperature\tenergy\taverage_energy\tabsolute_energy" << std::endl;
+          if (p.config_dump_steps && steps_r % p.config_dump_steps == 0) config.write(std::to_string(steps_r) + ".cfg.gz");
+          if (steps_r == p.maximum_steps) config.write("end.cfg.gz");
+          if (log_this_step(steps_r, p.log_dump_steps))
+            log << steps_r << '\t' << p.temperature << '\t' << energy_now << '\t' << averaging.GetThermodynamicAverage(1.0 / kBoltzmann / p.temperature)
+                << '\t' << absolute_energy << std::endl;
+        }
+        if (accepted[s]) {
+          config.lattice_jump(ta[done + s], tb[done + s]);
+          absolute_energy += dE[s];
+        }
+      }
+      done += chunk;
+    }
+    return;
+  }
   double energy, temperature;
   unsigned long long steps;
   read_state(energy, steps, temperature);

@@ -48,6 +48,35 @@ def main():
     print(sorted(os.listdir(out)))
     chain(golden, js, tt)
     from_map(js, tt)
+    cmc(js)
+
+
+def cmc(js):
+    """mc::CanonicalMcSerial as shipped (cmc_log.txt with the thermodynamic average over a 50-step window, 0 / 100 / 200 /
+    300.cfg.gz, end.cfg.gz) on a vacancy-free 5x5x5 cell, together with the trial stream (site_a, site_b, u) its
+    std::mt19937_64 delivered -> tests/golden/cli_cmc_v1/."""
+    out = os.path.join(ROOT, "tests", "golden", "cli_cmc_v1")
+    os.makedirs(out, exist_ok=True)
+    work = tempfile.mkdtemp()
+    steps, seed, f = 300, 33, 5
+    occ = synth.random_alloy(f, 0.08, 0.08, seed=105, vacancy_site=None)
+    R.RefConfig.fcc(f, occ, reassign=False).write(os.path.join(work, "start.cfg"))
+    cfg = R.RefConfig.read(os.path.join(work, "start.cfg"), reassign=True)
+    trace = R.cmc_serial(cfg, js, temperature=800.0, maximum_steps=steps, seed=seed)
+    R.cmc_serial_with_logs(cfg, js, work, temperature=800.0, maximum_steps=steps, log_dump_steps=10, config_dump_steps=100,
+                           thermodynamic_averaging_steps=50, seed=seed)
+    with open(os.path.join(out, "trials.txt"), "w") as fh:
+        for a, b, u in zip(trace["a"], trace["b"], trace["u"]):
+            fh.write("%d %d %.17g\n" % (a, b, u))
+    for name in ("start.cfg", "cmc_log.txt", "0.cfg.gz", "100.cfg.gz", "300.cfg.gz", "end.cfg.gz"):
+        shutil.copy(os.path.join(work, name), os.path.join(out, name.replace(".cfg.gz", ".cfg.txt")))
+    with open(os.path.join(out, "cmc_param.txt"), "w") as fh:
+        fh.write("simulation_method CanonicalMcSerial\njson_coefficients_filename coefficients.json\nconfig_filename start.cfg\n"
+                 "log_dump_steps 10\nconfig_dump_steps 100\nmaximum_steps %d\nthermodynamic_averaging_steps 50\ntemperature 800\n"
+                 "element_set Al Mg Zn\nrestart_steps 0\nrestart_energy 0\n# extension of lmc_b200 (ignored by the reference):\n"
+                 "replay_trials_filename trials.txt\n" % steps)
+    print(open(os.path.join(out, "cmc_log.txt")).read()[:500])
+    print(sorted(os.listdir(out)))
 
 
 def from_map(js, tt):

@@ -191,3 +191,67 @@ def test_cmc_and_sa_cli_run_and_log(exe, golden, coef_json, tmp_path):
     final = occupancy_of(tmp_path / "end.cfg.gz")
     assert (final == 2).sum() == 12 and (final == 3).sum() == 15
     assert os.path.exists(tmp_path / "lowest_energy.cfg.gz")
+
+
+@pytest.mark.gpu
+def test_cmc_cli_replay_reproduces_reference_log_average_energy_and_dumps(exe, golden, tmp_path):
+    """simulation_method CanonicalMcSerial with the reference's trial stream (replay_trials_filename): cmc_log.txt incl. the
+    `average_energy` column -- mc::ThermodynamicAveraging over a 50-step sliding window, fed every step
+    (mc/src/ThermodynamicAveraging.cpp:5-39, CanonicalMcSerial.cpp:40-51) -- and the .cfg dumps (atom identities through
+    Config::LatticeJump) against what the reference wrote (tests/golden/cli_cmc_v1, make_golden_cli.cmc)."""
+    gold = os.path.join(ROOT, "tests", "golden", "cli_cmc_v1")
+    for name in ("start.cfg", "cmc_param.txt", "trials.txt"):
+        shutil.copy(os.path.join(gold, name), tmp_path / name)
+    shutil.copy(H.golden_json(golden, tmp_path), tmp_path / "coefficients.json")
+    res = subprocess.run([exe, "-p", "cmc_param.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 0, res.stderr
+    head, mine = _rows((tmp_path / "cmc_log.txt").read_text())
+    head_ref, ref = _rows(open(os.path.join(gold, "cmc_log.txt")).read())
+    assert head == head_ref and len(mine) == len(ref) and len(ref) > 30
+    for a, b in zip(mine, ref):
+        assert a[0] == b[0] and float(a[1]) == float(b[1])                     # steps, temperature
+        va, vb = np.array([float(x) for x in a[2:]]), np.array([float(x) for x in b[2:]])
+        assert np.max(np.abs(va - vb)) < 1e-9, (a, b)                          # energy, average_energy, absolute_energy (eV)
+    assert any(abs(float(r[2]) - float(r[3])) > 1e-3 for r in ref[5:])        # the window average is not just the energy
+    for name in ("0", "100", "300", "end"):
+        got = gzip.open(tmp_path / (name + ".cfg.gz"), "rt").read()
+        assert got == open(os.path.join(gold, name + ".cfg.txt")).read(), name
+
+
+@pytest.mark.gpu
+def test_kmc_cli_restart_continues_the_run(exe, golden, tmp_path):
+    """Restart (mc/src/McAbstract.cpp:24-34, script/restart.py:51-105): a run resumed from the 30-step dump with
+    restart_steps / restart_energy / restart_time taken from the log must continue exactly where the uninterrupted run
+    went -- same T(t) (the clock resumes at restart_time), same random stream (the Philox counter is the step number),
+    appended log, identical end.cfg.gz."""
+    full, part = tmp_path / "full", tmp_path / "part"
+    for d in (full, part):
+        d.mkdir()
+        for name in ("start.cfg", "time_temperature.dat"):
+            shutil.copy(os.path.join(GOLD, name), d / name)
+        shutil.copy(H.golden_json(golden, tmp_path), d / "coefficients.json")
+    base = ("simulation_method KineticMcFirstOmp\njson_coefficients_filename coefficients.json\ntime_temperature_filename time_temperature.dat\n"
+            "log_dump_steps 1\nconfig_dump_steps 30\nthermodynamic_averaging_steps 0\ntemperature 500\nelement_set Al Mg Zn\n"
+            "rate_corrector true\nearly_stop false\nsolute_disp false\nseed 1234\n")
+    (full / "p.txt").write_text(base + "config_filename start.cfg\nmaximum_steps 60\nrestart_steps 0\nrestart_energy 0\nrestart_time 0\n")
+    assert subprocess.run([exe, "-p", "p.txt"], capture_output=True, text=True, cwd=full).returncode == 0
+    (part / "p.txt").write_text(base + "config_filename start.cfg\nmaximum_steps 30\nrestart_steps 0\nrestart_energy 0\nrestart_time 0\n")
+    assert subprocess.run([exe, "-p", "p.txt"], capture_output=True, text=True, cwd=part).returncode == 0
+    _, rows = _rows((part / "kmc_log.txt").read_text())
+    last = rows[-1]
+    assert last[0] == "30"
+    with gzip.open(part / "30.cfg.gz", "rt") as fh:
+        (part / "restart.cfg").write_text(fh.read())
+    (part / "p2.txt").write_text(base + "config_filename restart.cfg\nmaximum_steps 60\nrestart_steps 30\nrestart_energy %s\nrestart_time %s\n" % (last[3], last[1]))
+    res = subprocess.run([exe, "-p", "p2.txt"], capture_output=True, text=True, cwd=part)
+    assert res.returncode == 0, res.stderr
+    _, a = _rows((full / "kmc_log.txt").read_text())
+    _, b = _rows((part / "kmc_log.txt").read_text())
+    assert [r[0] for r in a] == [r[0] for r in b] == [str(s) for s in range(61)]          # the restarted run appends rows 31..60
+    for ra, rb in zip(a, b):
+        va, vb = np.array([float(x) for x in ra]), np.array([float(x) for x in rb])
+        # (the log prints times in fixed notation with 16 decimals: ~12 significant digits at 3e-5 s)
+        assert ra[6] == rb[6] and np.allclose(va[[1, 2]], vb[[1, 2]], rtol=1e-9, atol=0), (ra, rb)     # atom, time, temperature
+        assert np.max(np.abs(va[3:6] - vb[3:6])) < 1e-9 and np.max(np.abs(va[7:10] - vb[7:10])) < 1e-9
+    assert float(a[45][2]) != float(a[0][2])                                   # the temperature ramp is live in the resumed half
+    assert gzip.open(full / "end.cfg.gz", "rt").read() == gzip.open(part / "end.cfg.gz", "rt").read()
