@@ -136,9 +136,32 @@ int lmc_eval_pair_de(lmc_engine *engine, int64_t n, const int32_t *walker, const
  * (pred/src/EnergyChangePredictorSite.cpp:56-98): species at `site` replaced by new_element */
 int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *site,
                      const uint8_t *new_element, double *dE);
+/* Config::GetElementAtLatticeId (cfg/src/Config.cpp:132-135) for a list of sites: ElementName codes */
+int lmc_engine_get_elements(lmc_engine *engine, int32_t walker, int64_t n, const int64_t *lattice_ids, uint8_t *elements);
+/* Config::GetVacancyLatticeId (cfg/src/Config.cpp:296-310) generalised: the lowest lattice id that holds `element` (-1 if
+ * none; values below -1000 are error codes - 1000); *count (optional) receives the number of such sites */
+int64_t lmc_engine_find_element(lmc_engine *engine, int32_t walker, int32_t element, int64_t *count);
+/* path of the coefficient file whose tables are on the engine ("" if none): lets several predictor objects that share an
+ * engine notice that another file has been loaded since */
+const char *lmc_engine_coefficients_path(const lmc_engine *engine);
 /* EnergyPredictor::GetEnergy / GetEncode (pred/src/EnergyPredictor.cpp:40-96,173-177) of one replica.
  * counts (optional, n_types int64) receives the exact integer cluster counts of GetEncode before normalisation. */
 int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t *counts, int32_t n_types);
+/* EnergyPredictor::GetEnergyOfCluster / GetEncodeOfCluster (pred/src/EnergyPredictor.cpp:97-172,178-184): the energy of the
+ * clusters that lie entirely inside the site set { listed sites and their first- to third-neighbour shells }.  The sites
+ * are LATTICE ids (the reference takes atom ids and maps them with Config::GetLatticeIdFromAtomId; the adapters do that).
+ * n == 0 gives 0.  counts as in lmc_total_energy. */
+int lmc_energy_of_cluster(lmc_engine *engine, int32_t walker, const int64_t *lattice_ids, int64_t n, double *energy, int64_t *counts,
+                          int32_t n_types);
+/* EnergyPredictor::GetEncode (lattice_ids == NULL and n < 0: the whole configuration) / GetEncodeOfCluster: the cluster counts
+ * divided by the per-label normalisers {256, 3072, 1536, 6144, 12288, 6144, 12288, 6144, ...} (EnergyPredictor.cpp:8), in
+ * ClusterIndexer order (n_types doubles) -- the vector the reference dots with Base.theta. */
+int lmc_energy_encode(lmc_engine *engine, int32_t walker, const int64_t *lattice_ids, int64_t n, double *encode, int32_t n_types);
+/* EnergyPredictor::GetChemicalPotential(solvent) (pred/src/EnergyPredictor.cpp:196-214): for every element of the set and the
+ * vacancy X, E(15 x 15 x 15 solvent cell with atom 0 replaced by the element) - E(pure solvent cell); 0 for the solvent.
+ * Entries in element-name order (std::map<Element, double>: Element::operator< compares names).  Returns the number of
+ * entries (call with elements == NULL for the length), negative on error. */
+int32_t lmc_chemical_potential(lmc_engine *engine, int32_t solvent_element, int32_t *elements, double *mu, int32_t capacity);
 
 /* ------------------------------------------------------------------------------------------------ measurement
  * the engine's cudaStream_t (all engine work is enqueued on it; e.g. to record CUDA events around calls) */
@@ -332,6 +355,7 @@ int32_t lmc_tables_group_sizes(int32_t which, int32_t n_elements, int32_t *sizes
 /* Introspection of the contracted coefficient tables (host copies; engine must have coefficients loaded).
  * which: 0 pair_C [m][3], 1 pair_A [m][58][n][3], 2 pair_B [m][556][n][n][3]   (jump tables: dE, logD, logKs)
  *        3 site_C [x],    4 site_A [x][42][n+1],  5 site_B [x][204][n+1][n+1]  (single-site tables, codes incl. vacancy)
+ *        6 "Base".theta as read (one entry per cluster type in ClusterIndexer order)
  * Species codes are positions in the element set sorted by name; the vacancy is code n.  Returns the length. */
 int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *out, int64_t capacity);
 /* environment pairs (t,u), t<u, as indices into the environment (ordered state list without the centre site(s)):

@@ -19,6 +19,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <map>
 #include <memory>
 #include <set>
 #include <stdexcept>
@@ -45,41 +46,110 @@ inline void check(int rc) {
 
 namespace cfg {
 // Device-resident counterpart of cfg::Config (lmc/cfg/include/Config.h:14-112) for FCC supercells.
+//
+// COPY SEMANTICS differ from the reference: copies of a Config share ONE engine (device occupancy) and one atom <-> lattice
+// map, so a driver constructed from a Config (mc::KineticMcFirstOmp takes it by value, like the reference) advances the
+// caller's object too.  Clone() makes the deep copy the reference's copy constructor would.
 class Config {
  public:
   Config(const std::array<size_t, 3> &factors, lmc_id_order order, const std::set<ElementName> &element_set, ElementName solvent,
-         int n_walkers = 1, int device = 0) {
+         int n_walkers = 1, int device = 0)
+      : state_(std::make_shared<State>()) {
     const int32_t f[3] = {static_cast<int32_t>(factors[0]), static_cast<int32_t>(factors[1]), static_cast<int32_t>(factors[2])};
-    std::vector<int32_t> es;
-    for (auto e : element_set) es.push_back(static_cast<int32_t>(e));
+    for (auto e : element_set) state_->elements.push_back(static_cast<int32_t>(e));
+    state_->factors = {f[0], f[1], f[2]};
+    state_->order = order; state_->solvent = static_cast<int32_t>(solvent); state_->n_walkers = n_walkers; state_->device = device;
     lmc_engine *raw = nullptr;
-    check(lmc_engine_create(&raw, f, order, es.data(), static_cast<int32_t>(es.size()), static_cast<int32_t>(solvent), n_walkers, device));
-    engine_.reset(raw, lmc_engine_destroy);
+    check(lmc_engine_create(&raw, f, order, state_->elements.data(), static_cast<int32_t>(state_->elements.size()), static_cast<int32_t>(solvent),
+                            n_walkers, device));
+    state_->engine.reset(raw, lmc_engine_destroy);
   }
-  [[nodiscard]] size_t GetNumAtoms() const { return static_cast<size_t>(lmc_engine_num_sites(engine_.get())); }
+  // deep copy: own engine with the same occupancy, coefficient file and atom <-> lattice maps
+  [[nodiscard]] Config Clone() const {
+    std::set<ElementName> es;
+    for (auto e : state_->elements) es.insert(static_cast<ElementName>(e));
+    Config out({static_cast<size_t>(state_->factors[0]), static_cast<size_t>(state_->factors[1]), static_cast<size_t>(state_->factors[2])},
+               state_->order, es, static_cast<ElementName>(state_->solvent), state_->n_walkers, state_->device);
+    for (int w = 0; w < state_->n_walkers; ++w) out.SetOccupancy(GetOccupancy(w), w);
+    const std::string path = lmc_engine_coefficients_path(engine());
+    if (!path.empty()) {
+      const int model = lmc_engine_barrier_model(engine());
+      check(lmc_engine_load_coefficients_model(out.engine(), path.c_str(), model == LMC_BARRIER_E0 ? LMC_BARRIER_E0 : LMC_BARRIER_QUARTIC));
+    }
+    out.state_->maps = state_->maps;
+    return out;
+  }
+  [[nodiscard]] size_t GetNumAtoms() const { return static_cast<size_t>(lmc_engine_num_sites(engine())); }
   void SetOccupancy(const std::vector<uint8_t> &element_by_lattice_id, int walker = 0) {
-    check(lmc_engine_set_occupancy(engine_.get(), walker, element_by_lattice_id.data(), static_cast<int64_t>(element_by_lattice_id.size())));
+    check(lmc_engine_set_occupancy(engine(), walker, element_by_lattice_id.data(), static_cast<int64_t>(element_by_lattice_id.size())));
   }
   [[nodiscard]] std::vector<uint8_t> GetOccupancy(int walker = 0) const {
     std::vector<uint8_t> out(GetNumAtoms());
-    check(lmc_engine_get_occupancy(engine_.get(), walker, out.data(), static_cast<int64_t>(out.size())));
+    check(lmc_engine_get_occupancy(engine(), walker, out.data(), static_cast<int64_t>(out.size())));
     return out;
   }
   // Config::GetFirst/Second/ThirdNeighborsAdjacencyList()[lattice_id] (ascending ids)
   [[nodiscard]] std::vector<size_t> GetNeighbors(int shell, size_t lattice_id) const {
     int64_t buf[24];
-    check(lmc_engine_neighbors(engine_.get(), shell, static_cast<int64_t>(lattice_id), buf));
+    check(lmc_engine_neighbors(engine(), shell, static_cast<int64_t>(lattice_id), buf));
     const int n = shell == 1 ? 12 : (shell == 2 ? 6 : 24);
     return std::vector<size_t>(buf, buf + n);
   }
-  void LatticeJump(const std::pair<size_t, size_t> &lattice_id_jump_pair, int walker = 0) {   // Config.cpp:431-456
-    check(lmc_engine_lattice_jump(engine_.get(), walker, static_cast<int64_t>(lattice_id_jump_pair.first),
-                                  static_cast<int64_t>(lattice_id_jump_pair.second)));
+  // Config::GetElementAtLatticeId / GetElementAtAtomId (cfg/src/Config.cpp:128-135)
+  [[nodiscard]] ElementName GetElementAtLatticeId(size_t lattice_id, int walker = 0) const {
+    const int64_t id = static_cast<int64_t>(lattice_id);
+    uint8_t e = 0;
+    check(lmc_engine_get_elements(engine(), walker, 1, &id, &e));
+    return static_cast<ElementName>(e);
   }
-  [[nodiscard]] lmc_engine *engine() const { return engine_.get(); }
+  [[nodiscard]] ElementName GetElementAtAtomId(size_t atom_id, int walker = 0) const { return GetElementAtLatticeId(GetLatticeIdFromAtomId(atom_id, walker), walker); }
+  // Config::GetVacancyLatticeId / GetVacancyAtomId (cfg/src/Config.cpp:296-310): the first vacancy by lattice id
+  [[nodiscard]] size_t GetVacancyLatticeId(int walker = 0) const {
+    const int64_t id = lmc_engine_find_element(engine(), walker, 0, nullptr);
+    if (id < -1) check(static_cast<int>(id + 1000));
+    if (id < 0) throw std::runtime_error("vacancy not found");
+    return static_cast<size_t>(id);
+  }
+  [[nodiscard]] size_t GetVacancyAtomId(int walker = 0) const { return GetAtomIdFromLatticeId(GetVacancyLatticeId(walker), walker); }
+  // atom <-> lattice maps (cfg/src/Config.cpp:115-127): the identity until LatticeJump moves atoms
+  [[nodiscard]] size_t GetLatticeIdFromAtomId(size_t atom_id, int walker = 0) const {
+    const auto it = state_->maps.find(walker);
+    return it == state_->maps.end() ? atom_id : it->second.atom_to_lattice.at(atom_id);
+  }
+  [[nodiscard]] size_t GetAtomIdFromLatticeId(size_t lattice_id, int walker = 0) const {
+    const auto it = state_->maps.find(walker);
+    return it == state_->maps.end() ? lattice_id : it->second.lattice_to_atom.at(lattice_id);
+  }
+  void LatticeJump(const std::pair<size_t, size_t> &lattice_id_jump_pair, int walker = 0) {   // Config.cpp:431-456
+    check(lmc_engine_lattice_jump(engine(), walker, static_cast<int64_t>(lattice_id_jump_pair.first),
+                                  static_cast<int64_t>(lattice_id_jump_pair.second)));
+    auto &m = state_->maps[walker];
+    if (m.atom_to_lattice.empty()) {
+      m.atom_to_lattice.resize(GetNumAtoms());
+      m.lattice_to_atom.resize(GetNumAtoms());
+      for (size_t q = 0; q < m.atom_to_lattice.size(); ++q) m.atom_to_lattice[q] = m.lattice_to_atom[q] = q;
+    }
+    const size_t a = m.lattice_to_atom[lattice_id_jump_pair.first], b = m.lattice_to_atom[lattice_id_jump_pair.second];
+    m.atom_to_lattice[a] = lattice_id_jump_pair.second; m.atom_to_lattice[b] = lattice_id_jump_pair.first;
+    m.lattice_to_atom[lattice_id_jump_pair.first] = b; m.lattice_to_atom[lattice_id_jump_pair.second] = a;
+  }
+  void AtomJump(const std::pair<size_t, size_t> &atom_id_jump_pair, int walker = 0) {          // Config.cpp:458-462
+    LatticeJump({GetLatticeIdFromAtomId(atom_id_jump_pair.first, walker), GetLatticeIdFromAtomId(atom_id_jump_pair.second, walker)}, walker);
+  }
+  [[nodiscard]] lmc_engine *engine() const { return state_->engine.get(); }
 
  private:
-  std::shared_ptr<lmc_engine> engine_;
+  struct Maps { std::vector<size_t> atom_to_lattice, lattice_to_atom; };
+  struct State {
+    std::shared_ptr<lmc_engine> engine;
+    std::map<int, Maps> maps;                       // per walker, allocated by its first jump
+    std::vector<int32_t> elements;
+    std::array<int32_t, 3> factors{};
+    lmc_id_order order{};
+    int32_t solvent{0};
+    int n_walkers{1}, device{0};
+  };
+  std::shared_ptr<State> state_;
 };
 }  // namespace cfg
 
@@ -92,7 +162,15 @@ inline void LoadCoefficients(const cfg::Config &reference_config, const std::str
 // An engine holds the barrier tables of ONE model at a time.  A barrier predictor re-loads its file if another predictor
 // object has put a different model (or none) on the shared engine since, so two predictor objects on one Config stay correct.
 inline void EnsureBarrierModel(const cfg::Config &config, const std::string &predictor_filename, lmc_barrier_model model) {
-  if (lmc_engine_barrier_model(config.engine()) != static_cast<int>(model)) LoadCoefficients(config, predictor_filename, model);
+  if (lmc_engine_barrier_model(config.engine()) != static_cast<int>(model) || predictor_filename != lmc_engine_coefficients_path(config.engine()))
+    LoadCoefficients(config, predictor_filename, model);
+}
+// The dE / energy predictors read only "Base".theta: they re-load when another FILE has been put on the shared engine since
+// (keeping whatever barrier model is there if the file carries its blocks).
+inline void EnsureCoefficientFile(const cfg::Config &config, const std::string &predictor_filename) {
+  if (predictor_filename == lmc_engine_coefficients_path(config.engine())) return;
+  const int model = lmc_engine_barrier_model(config.engine());
+  LoadCoefficients(config, predictor_filename, model == LMC_BARRIER_E0 ? LMC_BARRIER_E0 : LMC_BARRIER_QUARTIC);
 }
 
 class VacancyMigrationPredictorQuartic {
@@ -110,6 +188,13 @@ class VacancyMigrationPredictorQuartic {
     double ea = 0, de = 0;
     check(lmc_eval_barriers(config.engine(), 1, &w, &i, &j, &ea, &de, nullptr, nullptr));
     return {ea, de};
+  }
+  // pred/include/VacancyMigrationPredictorQuartic.h:22-24
+  [[nodiscard]] virtual std::pair<double, double> GetBarrierAndDiffFromAtomIdPair(const cfg::Config &config,
+                                                                                   const std::pair<size_t, size_t> &atom_id_jump_pair,
+                                                                                   int walker = 0) const {
+    return GetBarrierAndDiffFromLatticeIdPair(config, {config.GetLatticeIdFromAtomId(atom_id_jump_pair.first, walker),
+                                                       config.GetLatticeIdFromAtomId(atom_id_jump_pair.second, walker)}, walker);
   }
   // batch form: all candidate events of a step (or of many walkers) in one launch
   void GetBarrierAndDiffFromLatticeIdPairs(const cfg::Config &config, const std::vector<int32_t> &walker, const std::vector<int64_t> &first,
@@ -173,11 +258,21 @@ class VacancyMigrationPredictorE0Lru : public VacancyMigrationPredictorE0 {     
 class EnergyChangePredictorPairSite {
  public:
   EnergyChangePredictorPairSite(const std::string &predictor_filename, const cfg::Config &reference_config,
-                                const std::set<ElementName> &) {
-    LoadCoefficients(reference_config, predictor_filename);
+                                const std::set<ElementName> &)
+      : filename_(predictor_filename) {
+    EnsureCoefficientFile(reference_config, predictor_filename);
+  }
+  // pred/include/EnergyChangePredictorPairSite.h:20-25
+  [[nodiscard]] double GetDeFromAtomIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &atom_id_jump_pair, int walker = 0) const {
+    return GetDeFromLatticeIdPair(config, {config.GetLatticeIdFromAtomId(atom_id_jump_pair.first, walker),
+                                           config.GetLatticeIdFromAtomId(atom_id_jump_pair.second, walker)}, walker);
+  }
+  [[nodiscard]] double GetDeFromAtomIdSite(const cfg::Config &config, size_t atom_id, ElementName new_element, int walker = 0) const {
+    return GetDeFromLatticeIdSite(config, config.GetLatticeIdFromAtomId(atom_id, walker), new_element, walker);
   }
   [[nodiscard]] double GetDeFromLatticeIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair,
                                               int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
     const int64_t a = static_cast<int64_t>(lattice_id_jump_pair.first), b = static_cast<int64_t>(lattice_id_jump_pair.second);
     const int32_t w = walker;
     double de = 0;
@@ -185,6 +280,7 @@ class EnergyChangePredictorPairSite {
     return de;
   }
   [[nodiscard]] double GetDeFromLatticeIdSite(const cfg::Config &config, size_t lattice_id, ElementName new_element, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
     const int64_t s = static_cast<int64_t>(lattice_id);
     const uint8_t e = static_cast<uint8_t>(new_element);
     const int32_t w = walker;
@@ -192,6 +288,9 @@ class EnergyChangePredictorPairSite {
     check(lmc_eval_site_de(config.engine(), 1, &w, &s, &e, &de));
     return de;
   }
+
+ private:
+  std::string filename_;
 };
 
 // pred::EnergyChangePredictorPair (pred/src/EnergyChangePredictorPair.cpp:69-122): exchange energy of a FIRST-NEIGHBOUR pair;
@@ -199,25 +298,39 @@ class EnergyChangePredictorPairSite {
 // NB these dE predictors read only "Base".theta; they re-use whatever barrier model is on the engine.
 class EnergyChangePredictorPair {
  public:
-  EnergyChangePredictorPair(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &) {
-    if (lmc_engine_barrier_model(reference_config.engine()) < 0) LoadCoefficients(reference_config, predictor_filename);
+  EnergyChangePredictorPair(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &)
+      : filename_(predictor_filename) {
+    EnsureCoefficientFile(reference_config, predictor_filename);
+  }
+  [[nodiscard]] double GetDeFromAtomIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &atom_id_jump_pair, int walker = 0) const {
+    return GetDeFromLatticeIdPair(config, {config.GetLatticeIdFromAtomId(atom_id_jump_pair.first, walker),
+                                           config.GetLatticeIdFromAtomId(atom_id_jump_pair.second, walker)}, walker);
   }
   [[nodiscard]] double GetDeFromLatticeIdPair(const cfg::Config &config, const std::pair<size_t, size_t> &lattice_id_jump_pair,
                                               int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
     const int64_t a = static_cast<int64_t>(lattice_id_jump_pair.first), b = static_cast<int64_t>(lattice_id_jump_pair.second);
     const int32_t w = walker;
     double de = 0;
     check(lmc_eval_pair_de(config.engine(), 1, &w, &a, &b, &de));
     return de;
   }
+
+ private:
+  std::string filename_;
 };
 // pred::EnergyChangePredictorSite (pred/src/EnergyChangePredictorSite.cpp:56-98)
 class EnergyChangePredictorSite {
  public:
-  EnergyChangePredictorSite(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &) {
-    if (lmc_engine_barrier_model(reference_config.engine()) < 0) LoadCoefficients(reference_config, predictor_filename);
+  EnergyChangePredictorSite(const std::string &predictor_filename, const cfg::Config &reference_config, const std::set<ElementName> &)
+      : filename_(predictor_filename) {
+    EnsureCoefficientFile(reference_config, predictor_filename);
+  }
+  [[nodiscard]] double GetDeFromAtomIdSite(const cfg::Config &config, size_t atom_id, ElementName new_element, int walker = 0) const {
+    return GetDeFromLatticeIdSite(config, config.GetLatticeIdFromAtomId(atom_id, walker), new_element, walker);
   }
   [[nodiscard]] double GetDeFromLatticeIdSite(const cfg::Config &config, size_t lattice_id, ElementName new_element, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
     const int64_t s = static_cast<int64_t>(lattice_id);
     const uint8_t e = static_cast<uint8_t>(new_element);
     const int32_t w = walker;
@@ -225,18 +338,67 @@ class EnergyChangePredictorSite {
     check(lmc_eval_site_de(config.engine(), 1, &w, &s, &e, &de));
     return de;
   }
+
+ private:
+  std::string filename_;
 };
 
-class EnergyPredictor {
+class EnergyPredictor {      // pred/include/EnergyPredictor.h:14-30
  public:
-  EnergyPredictor(const std::string &predictor_filename, const cfg::Config &reference_config) {
-    LoadCoefficients(reference_config, predictor_filename);
+  EnergyPredictor(const std::string &predictor_filename, const cfg::Config &reference_config) : filename_(predictor_filename) {
+    EnsureCoefficientFile(reference_config, predictor_filename);
   }
   [[nodiscard]] double GetEnergy(const cfg::Config &config, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
     double e = 0;
     check(lmc_total_energy(config.engine(), walker, &e, nullptr, 0));
     return e;
   }
+  // energy of the clusters inside { the listed atoms and their 1-3NN shells } (pred/src/EnergyPredictor.cpp:97-184)
+  [[nodiscard]] double GetEnergyOfCluster(const cfg::Config &config, const std::vector<size_t> &atom_id_list, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
+    const auto ids = LatticeIds(config, atom_id_list, walker);
+    double e = 0;
+    check(lmc_energy_of_cluster(config.engine(), walker, ids.data(), static_cast<int64_t>(ids.size()), &e, nullptr, 0));
+    return e;
+  }
+  [[nodiscard]] std::vector<double> GetEncode(const cfg::Config &config, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
+    std::vector<double> out(static_cast<size_t>(NumTypes(config)));
+    check(lmc_energy_encode(config.engine(), walker, nullptr, -1, out.data(), static_cast<int32_t>(out.size())));
+    return out;
+  }
+  [[nodiscard]] std::vector<double> GetEncodeOfCluster(const cfg::Config &config, const std::vector<size_t> &atom_id_list, int walker = 0) const {
+    EnsureCoefficientFile(config, filename_);
+    const auto ids = LatticeIds(config, atom_id_list, walker);
+    std::vector<double> out(static_cast<size_t>(NumTypes(config)));
+    check(lmc_energy_encode(config.engine(), walker, ids.data(), static_cast<int64_t>(ids.size()), out.data(), static_cast<int32_t>(out.size())));
+    return out;
+  }
+  // pred/src/EnergyPredictor.cpp:196-214; needs a Config for the engine that holds the coefficient file
+  [[nodiscard]] std::map<ElementName, double> GetChemicalPotential(const cfg::Config &config, ElementName solvent_element) const {
+    EnsureCoefficientFile(config, filename_);
+    int32_t el[16];
+    double mu[16];
+    const int32_t n = lmc_chemical_potential(config.engine(), static_cast<int32_t>(solvent_element), el, mu, 16);
+    check(n);
+    std::map<ElementName, double> out;
+    for (int32_t q = 0; q < n; ++q) out[static_cast<ElementName>(el[q])] = mu[q];
+    return out;
+  }
+
+ private:
+  static std::vector<int64_t> LatticeIds(const cfg::Config &config, const std::vector<size_t> &atom_id_list, int walker) {
+    std::vector<int64_t> ids;
+    for (auto a : atom_id_list) ids.push_back(static_cast<int64_t>(config.GetLatticeIdFromAtomId(a, walker)));
+    return ids;
+  }
+  static int32_t NumTypes(const cfg::Config &config) {     // Base.theta has one entry per cluster type of the element set (+ X)
+    const int64_t n = lmc_engine_get_tables(config.engine(), 6, nullptr, 0);
+    check(static_cast<int>(n < 0 ? n : 0));
+    return static_cast<int32_t>(n);
+  }
+  std::string filename_;
 };
 }  // namespace pred
 

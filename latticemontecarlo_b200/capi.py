@@ -59,6 +59,8 @@ def lib():
         _lib.lmc_engine_last_kernel_ms.restype = C.c_double
         _lib.lmc_engine_launch_count.restype = C.c_int64
         _lib.lmc_engine_get_tables.restype = C.c_int64
+        _lib.lmc_engine_find_element.restype = C.c_int64
+        _lib.lmc_engine_coefficients_path.restype = C.c_char_p
     return _lib
 
 
@@ -268,6 +270,46 @@ class Engine:
         return (e.value, counts) if want_counts else e.value
 
     # ---- measurement
+    def get_elements(self, lattice_ids, walker=0):
+        ids = _i64(lattice_ids)
+        out = np.empty(len(ids), np.uint8)
+        _check(lib().lmc_engine_get_elements(self.h, int(walker), C.c_int64(len(ids)), _p(ids), _p(out)))
+        return out
+
+    def find_element(self, element, walker=0):
+        """(lowest lattice id holding `element` or -1, number of such sites)."""
+        cnt = C.c_int64()
+        first = lib().lmc_engine_find_element(self.h, int(walker), int(element), C.byref(cnt))
+        if first < -1:
+            _check(int(first) + 1000)
+        return int(first), int(cnt.value)
+
+    def energy_of_cluster(self, lattice_ids, walker=0, want_counts=False):
+        """EnergyPredictor::GetEnergyOfCluster on lattice ids (lmc_energy_of_cluster)."""
+        ids = _i64(lattice_ids)
+        e = C.c_double()
+        counts = np.zeros(self.n_types, np.int64) if want_counts else None
+        _check(lib().lmc_energy_of_cluster(self.h, int(walker), _p(ids) if len(ids) else None, C.c_int64(len(ids)), C.byref(e), _p(counts),
+                                           self.n_types if want_counts else 0))
+        return (e.value, counts) if want_counts else e.value
+
+    def energy_encode(self, lattice_ids=None, walker=0):
+        """EnergyPredictor::GetEncode (lattice_ids None) / GetEncodeOfCluster."""
+        out = np.empty(self.n_types, np.float64)
+        if lattice_ids is None:
+            _check(lib().lmc_energy_encode(self.h, int(walker), None, C.c_int64(-1), _p(out), self.n_types))
+        else:
+            ids = _i64(lattice_ids)
+            _check(lib().lmc_energy_encode(self.h, int(walker), _p(ids) if len(ids) else None, C.c_int64(len(ids)), _p(out), self.n_types))
+        return out
+
+    def chemical_potential(self, solvent=1):
+        """EnergyPredictor::GetChemicalPotential(solvent): {element enum: mu} incl. the vacancy X (0)."""
+        n = _check(lib().lmc_chemical_potential(self.h, int(solvent), None, None, 0))
+        el = np.zeros(n, np.int32); mu = np.zeros(n, np.float64)
+        _check(lib().lmc_chemical_potential(self.h, int(solvent), _p(el), _p(mu), n))
+        return {int(a): float(b) for a, b in zip(el, mu)}
+
     def cuda_stream(self):
         return int(lib().lmc_engine_cuda_stream(self.h) or 0)
 

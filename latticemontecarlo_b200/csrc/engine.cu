@@ -335,7 +335,12 @@ void Engine::upload_geometry_tables() {
 }
 
 void Engine::load_coefficients(const std::string &json_path, int model) {
-  coefficients = parse_coefficients_json(json_path);
+  load_coefficients(parse_coefficients_json(json_path), model);
+  coefficients_path = json_path;
+}
+
+void Engine::load_coefficients(const Coefficients &co, int model) {
+  coefficients = co;
   pair_tables = build_pair_tables(species, coefficients, model);
   tab.barrier_model = model;
   site_tables = build_site_tables(species, coefficients);
@@ -417,6 +422,41 @@ void Engine::get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t coun
   LMC_CUDA(cudaGetLastError());
   LMC_CUDA(cudaMemcpyAsync(occ, d_out, static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
+}
+
+void Engine::get_elements(int32_t walker, int64_t n, const int64_t *sites, uint8_t *out) {
+  require_device();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  if (n <= 0) return;
+  if (!sites || !out) throw std::invalid_argument("null buffer");
+  char *d = static_cast<char *>(scratch(static_cast<size_t>(n) * 9 + 64));
+  int64_t *d_sites = reinterpret_cast<int64_t *>(d);
+  uint8_t *d_out = reinterpret_cast<uint8_t *>(d_sites + n);
+  LMC_CUDA(cudaMemcpyAsync(d_sites, sites, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+  gather_sites_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker) * lat.padded_size, d_sites, n,
+                                                                                 d_enum_of_code, d_out, d_error);
+  ++launch_count;
+  LMC_CUDA(cudaGetLastError());
+  LMC_CUDA(cudaMemcpyAsync(out, d_out, static_cast<size_t>(n), cudaMemcpyDeviceToHost, stream));
+  check_event_errors("lmc_engine_get_elements");
+}
+
+int64_t Engine::find_element(int32_t walker, int32_t element, int64_t *count) {
+  require_device();
+  if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
+  const int code = element >= 0 && element < 16 ? species.code_of_enum[static_cast<size_t>(element)] : -1;
+  if (code < 0) throw std::invalid_argument("element is not in the element set");
+  unsigned long long *d = static_cast<unsigned long long *>(scratch(64));
+  const unsigned long long init[2] = {~0ULL, 0ULL};
+  LMC_CUDA(cudaMemcpyAsync(d, init, 16, cudaMemcpyHostToDevice, stream));
+  find_element_kernel<<<static_cast<unsigned>((lat.num_sites + 255) / 256), 256, 0, stream>>>(lat, d_occ + static_cast<int64_t>(walker) * lat.padded_size, code, d, d + 1);
+  ++launch_count;
+  LMC_CUDA(cudaGetLastError());
+  unsigned long long res[2];
+  LMC_CUDA(cudaMemcpyAsync(res, d, 16, cudaMemcpyDeviceToHost, stream));
+  LMC_CUDA(cudaStreamSynchronize(stream));
+  if (count) *count = static_cast<int64_t>(res[1]);
+  return res[1] ? static_cast<int64_t>(res[0]) : -1;
 }
 
 void Engine::lattice_jump(int32_t walker, int64_t a, int64_t b) {
@@ -568,21 +608,39 @@ void Engine::eval_site_de(int64_t n, const int32_t *walker, const int64_t *site,
   check_event_errors("lmc_eval_site_de");
 }
 
-double Engine::total_energy(int32_t walker, int64_t *counts, int32_t n_types) {
+double Engine::total_energy(int32_t walker, int64_t *counts, int32_t n_types) { return cluster_energy(walker, nullptr, -1, counts, n_types); }
+
+// EnergyPredictor::GetEnergy (sites == nullptr) / GetEnergyOfCluster (pred/src/EnergyPredictor.cpp:97-184): n listed lattice
+// sites; the site set is the listed sites plus their 1-3NN shells
+double Engine::cluster_energy(int32_t walker, const int64_t *sites, int64_t n, int64_t *counts, int32_t n_types) {
   require_device();
   require_coefficients();
   if (walker < 0 || walker >= n_walkers) throw std::invalid_argument("walker index out of range");
   if (counts && n_types != tab.n_types) throw std::invalid_argument("counts buffer must hold n_types entries");
+  if (sites == nullptr && n >= 0) throw std::invalid_argument("null site list");
   const unsigned blocks = static_cast<unsigned>((lat.num_sites + kEnergyThreads - 1) / kEnergyThreads);
   const int m = species.n + 1;
-  char *d = static_cast<char *>(scratch(static_cast<size_t>(blocks) * 8 + static_cast<size_t>(tab.n_types) * 8 + 64));
+  const size_t member_bytes = sites ? static_cast<size_t>(lat.padded_size) + 16 : 0, list_bytes = sites ? static_cast<size_t>(std::max<int64_t>(n, 1)) * 8 : 0;
+  char *d = static_cast<char *>(scratch(static_cast<size_t>(blocks) * 8 + static_cast<size_t>(tab.n_types) * 8 + 64 + list_bytes + member_bytes));
   double *d_sums = reinterpret_cast<double *>(d);
   unsigned long long *d_counts = reinterpret_cast<unsigned long long *>(d_sums + blocks);
+  int64_t *d_sites = reinterpret_cast<int64_t *>(d_counts + tab.n_types + 8);
+  uint8_t *d_member = sites ? reinterpret_cast<uint8_t *>(d_sites) + list_bytes : nullptr;
   LMC_CUDA(cudaMemsetAsync(d_counts, 0, static_cast<size_t>(tab.n_types) * 8, stream));
+  if (sites) {
+    LMC_CUDA(cudaMemsetAsync(d_member, 0, member_bytes, stream));
+    if (n > 0) {
+      LMC_CUDA(cudaMemcpyAsync(d_sites, sites, static_cast<size_t>(n) * 8, cudaMemcpyHostToDevice, stream));
+      mark_cluster_sites_kernel<<<static_cast<unsigned>((n * 43 + 127) / 128), 128, 0, stream>>>(lat, tab, d_sites, n, d_member, d_error);
+      ++launch_count;
+      LMC_CUDA(cudaGetLastError());
+    }
+  }
   const size_t smem = sizeof(double) * (m + 3 * m * m + 4 * m * m * m) + sizeof(int32_t) * 2 * 43 + sizeof(unsigned) * tab.n_types;
   energy_kernel<<<blocks, kEnergyThreads, smem, stream>>>(lat, tab, d_occ + static_cast<int64_t>(walker) * lat.padded_size, d_sums,
-                                                         counts ? d_counts : nullptr);
+                                                         counts ? d_counts : nullptr, d_member);
   LMC_CUDA(cudaGetLastError());
+  if (sites) check_event_errors("lmc_energy_of_cluster");
   std::vector<double> sums(blocks);
   LMC_CUDA(cudaMemcpyAsync(sums.data(), d_sums, static_cast<size_t>(blocks) * 8, cudaMemcpyDeviceToHost, stream));
   if (counts) LMC_CUDA(cudaMemcpyAsync(counts, d_counts, static_cast<size_t>(tab.n_types) * 8, cudaMemcpyDeviceToHost, stream));
@@ -1567,6 +1625,68 @@ int lmc_eval_site_de(lmc_engine *engine, int64_t n, const int32_t *walker, const
                      double *dE) {
   return guard([&] { engine->impl->eval_site_de(n, walker, site, new_element, dE); });
 }
+int lmc_engine_get_elements(lmc_engine *engine, int32_t walker, int64_t n, const int64_t *lattice_ids, uint8_t *elements) {
+  return guard([&] { engine->impl->get_elements(walker, n, lattice_ids, elements); });
+}
+int64_t lmc_engine_find_element(lmc_engine *engine, int32_t walker, int32_t element, int64_t *count) {
+  int64_t first = -1;
+  const int rc = guard([&] { first = engine->impl->find_element(walker, element, count); });
+  return rc == LMC_OK ? first : rc - 1000;       // errors as values below -1 (-1 = no such site)
+}
+const char *lmc_engine_coefficients_path(const lmc_engine *engine) { return engine ? engine->impl->coefficients_path.c_str() : ""; }
+int lmc_energy_of_cluster(lmc_engine *engine, int32_t walker, const int64_t *lattice_ids, int64_t n, double *energy, int64_t *counts,
+                          int32_t n_types) {
+  return guard([&] {
+    if (n < 0 || (n > 0 && !lattice_ids)) throw std::invalid_argument("bad site list");
+    static const int64_t none = 0;
+    const double e = engine->impl->cluster_energy(walker, n > 0 ? lattice_ids : &none, n, counts, n_types);
+    if (energy) *energy = e;
+  });
+}
+int lmc_energy_encode(lmc_engine *engine, int32_t walker, const int64_t *lattice_ids, int64_t n, double *encode, int32_t n_types) {
+  return guard([&] {
+    auto &impl = *engine->impl;
+    if (!encode || n_types != impl.tab.n_types) throw std::invalid_argument("encode buffer must hold n_types entries");
+    std::vector<int64_t> counts(static_cast<size_t>(n_types));
+    static const int64_t none = 0;
+    if (lattice_ids || n == 0) impl.cluster_energy(walker, n > 0 ? lattice_ids : &none, n, counts.data(), n_types);
+    else impl.cluster_energy(walker, nullptr, -1, counts.data(), n_types);
+    const auto types = lmc::cluster_types(impl.species);
+    for (int32_t q = 0; q < n_types; ++q) encode[q] = static_cast<double>(counts[static_cast<size_t>(q)]) / lmc::energy_cluster_counter(types[static_cast<size_t>(q)].label);
+  });
+}
+int32_t lmc_chemical_potential(lmc_engine *engine, int32_t solvent_element, int32_t *elements, double *mu, int32_t capacity) {
+  int32_t count = -1;
+  const int rc = guard([&] {
+    auto &impl = *engine->impl;
+    impl.require_device();
+    impl.require_coefficients();
+    // pred/src/EnergyPredictor.cpp:196-214: 15 x 15 x 15 cells of pure solvent, atom 0 replaced by each other element (and X)
+    std::vector<int32_t> set;
+    for (int c = 0; c < impl.species.n; ++c) set.push_back(impl.species.enum_of_code[static_cast<size_t>(c)]);
+    if (std::find(set.begin(), set.end(), solvent_element) == set.end()) throw std::invalid_argument("solvent element is not in the element set");
+    const int32_t f15[3] = {15, 15, 15};
+    lmc::Engine ref(f15, LMC_ID_ORDER_GENERATE, set.data(), static_cast<int32_t>(set.size()), solvent_element, 1, impl.device);
+    ref.load_coefficients(impl.coefficients, impl.pair_tables.model);
+    std::vector<uint8_t> occ(static_cast<size_t>(ref.lat.num_sites), static_cast<uint8_t>(solvent_element));
+    ref.set_occupancy(0, occ.data(), static_cast<int64_t>(occ.size()), 1);
+    const double e_solvent = ref.total_energy(0, nullptr, 0);
+    std::vector<int32_t> all(set);
+    all.push_back(0);                                      // ElementName::X
+    std::sort(all.begin(), all.end(), [](int a, int b) { return std::string(lmc::element_name(a)) < std::string(lmc::element_name(b)); });
+    count = static_cast<int32_t>(all.size());
+    if (!elements || !mu || capacity < count) return;      // query of the length
+    for (int32_t q = 0; q < count; ++q) {
+      elements[q] = all[static_cast<size_t>(q)];
+      if (all[static_cast<size_t>(q)] == solvent_element) { mu[q] = 0.0; continue; }
+      occ[0] = static_cast<uint8_t>(all[static_cast<size_t>(q)]);
+      ref.set_occupancy(0, occ.data(), static_cast<int64_t>(occ.size()), 1);
+      mu[q] = ref.total_energy(0, nullptr, 0) - e_solvent;
+      occ[0] = static_cast<uint8_t>(solvent_element);
+    }
+  });
+  return rc == LMC_OK ? count : rc;
+}
 int lmc_total_energy(lmc_engine *engine, int32_t walker, double *energy, int64_t *counts, int32_t n_types) {
   return guard([&] {
     const double e = engine->impl->total_energy(walker, counts, n_types);
@@ -1787,7 +1907,8 @@ int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *o
       case 3: v = &e.site_tables.C; break;
       case 4: v = &e.site_tables.A; break;
       case 5: v = &e.site_tables.B; break;
-      default: throw std::invalid_argument("which must be 0..5");
+      case 6: v = &e.coefficients.base_theta; break;
+      default: throw std::invalid_argument("which must be 0..6");
     }
     len = static_cast<int64_t>(v->size());
     if (out) std::copy(v->begin(), v->begin() + std::min<int64_t>(len, capacity), out);

@@ -32,9 +32,12 @@ class Engine {
   Engine &operator=(const Engine &) = delete;
 
   void load_coefficients(const std::string &json_path, int model = kModelQuartic);
+  void load_coefficients(const Coefficients &co, int model);
   void set_occupancy(int32_t walker, const uint8_t *occ, int64_t n, int32_t count);
   void get_occupancy(int32_t walker, uint8_t *occ, int64_t n, int32_t count);
   void lattice_jump(int32_t walker, int64_t a, int64_t b);
+  void get_elements(int32_t walker, int64_t n, const int64_t *sites, uint8_t *out);
+  int64_t find_element(int32_t walker, int32_t element, int64_t *count);
 
   void eval_barriers(int64_t n, const int32_t *walker, const int64_t *site_i, const int64_t *site_j, double *Ea, double *dE,
                      double *D, double *Ks);
@@ -44,6 +47,7 @@ class Engine {
   void eval_swap_de_dev(int64_t n, const int32_t *walker, const int64_t *a, const int64_t *b, double *dE, bool first_neighbours_only = false);
   void eval_site_de(int64_t n, const int32_t *walker, const int64_t *site, const uint8_t *new_element, double *dE);
   double total_energy(int32_t walker, int64_t *counts, int32_t n_types);
+  double cluster_energy(int32_t walker, const int64_t *sites, int64_t n, int64_t *counts, int32_t n_types);
   void debug_pair(int32_t walker, int64_t i, int64_t j, int64_t *state, int64_t *mmm, int64_t *mm2, int64_t *mm2b, int32_t *sc,
                   int32_t *ec, int32_t *enc_mmm, int32_t *enc_f, int32_t *enc_b);
   void debug_site(int32_t walker, int64_t site, int32_t new_element, int64_t *state43, int32_t *sc, int32_t *ec);
@@ -96,6 +100,7 @@ class Engine {
   int32_t device{-1};
   bool has_coefficients{false};
   Coefficients coefficients;
+  std::string coefficients_path;
   PairTables pair_tables;
   SiteTables site_tables;
   EnergyTables energy_tables;

@@ -593,7 +593,9 @@ constexpr int kEnergyThreads = 128;
 
 __global__ void __launch_bounds__(kEnergyThreads)
 energy_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, double *__restrict__ block_sums,
-              unsigned long long *__restrict__ counts) {
+              unsigned long long *__restrict__ counts, const uint8_t *__restrict__ member) {
+  // member != nullptr: EnergyPredictor::GetEncodeOfCluster (pred/src/EnergyPredictor.cpp:97-172) -- only clusters whose
+  // sites all lie in the marked set (the listed atoms and their 1-3NN shells) are counted
   extern __shared__ unsigned char smem_raw[];
   const int m = tab.n_species + 1;
   double *s_single = reinterpret_cast<double *>(smem_raw);
@@ -617,22 +619,32 @@ energy_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, d
     const int64_t base = lat.padded_index(x, y, z);
     const int32_t *drow = s_delta + (z & 1) * 43;
     unsigned char code[43];
+    unsigned long long in_set = ~0ULL;                       // bit t: list position t belongs to the cluster's site set
 #pragma unroll
     for (int t = 0; t < 43; ++t) code[t] = occ[base + drow[t]];
-    const int c1 = code[kCentrePos];
-    acc += s_single[c1];
-    if (counts) atomicAdd(&s_counts[tab.type_lut[c1 * m * m]], 1u);
-    for (int q = 0; q < 42; ++q) {
-      const int pos = tab.e_shell_pos[2 * q], shell = tab.e_shell_pos[2 * q + 1];
-      const int c2 = code[pos];
-      acc += s_pair[((shell - 1) * m + c1) * m + c2];
-      if (counts) atomicAdd(&s_counts[tab.type_lut[((shell * m + c1) * m + c2) * m]], 1u);
+    if (member) {
+      in_set = 0ULL;
+#pragma unroll
+      for (int t = 0; t < 43; ++t) in_set |= static_cast<unsigned long long>(member[base + drow[t]] != 0) << t;
     }
-    for (int q = 0; q < tab.n_e_walk; ++q) {
-      const int p2 = tab.e_walk[4 * q], p3 = tab.e_walk[4 * q + 1], label = tab.e_walk[4 * q + 2];
-      const int c2 = code[p2], c3 = code[p3];
-      acc += s_trip[(((label - 4) * m + c1) * m + c2) * m + c3];
-      if (counts) atomicAdd(&s_counts[tab.type_lut[((label * m + c1) * m + c2) * m + c3]], 1u);
+    if ((in_set >> kCentrePos) & 1ULL) {
+      const int c1 = code[kCentrePos];
+      acc += s_single[c1];
+      if (counts) atomicAdd(&s_counts[tab.type_lut[c1 * m * m]], 1u);
+      for (int q = 0; q < 42; ++q) {
+        const int pos = tab.e_shell_pos[2 * q], shell = tab.e_shell_pos[2 * q + 1];
+        if (!((in_set >> pos) & 1ULL)) continue;
+        const int c2 = code[pos];
+        acc += s_pair[((shell - 1) * m + c1) * m + c2];
+        if (counts) atomicAdd(&s_counts[tab.type_lut[((shell * m + c1) * m + c2) * m]], 1u);
+      }
+      for (int q = 0; q < tab.n_e_walk; ++q) {
+        const int p2 = tab.e_walk[4 * q], p3 = tab.e_walk[4 * q + 1], label = tab.e_walk[4 * q + 2];
+        if (!((in_set >> p2) & (in_set >> p3) & 1ULL)) continue;
+        const int c2 = code[p2], c3 = code[p3];
+        acc += s_trip[(((label - 4) * m + c1) * m + c2) * m + c3];
+        if (counts) atomicAdd(&s_counts[tab.type_lut[((label * m + c1) * m + c2) * m + c3]], 1u);
+      }
     }
   }
   // block reduction in a fixed order
@@ -649,6 +661,39 @@ energy_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, d
     for (int q = threadIdx.x; q < tab.n_types; q += blockDim.x)
       if (s_counts[q]) atomicAdd(&counts[q], static_cast<unsigned long long>(s_counts[q]));
   }
+}
+
+// Config::GetElementAtLatticeId for a list of sites (element enum codes)
+__global__ void gather_sites_kernel(LatticeDesc lat, const uint8_t *__restrict__ padded, const int64_t *__restrict__ sites, int64_t n,
+                                    const uint8_t *__restrict__ enum_of_code, uint8_t *__restrict__ out, int *error) {
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q >= n) return;
+  const int64_t id = sites[q];
+  if (id < 0 || id >= lat.num_sites) { atomicOr(error, kErrBadSite); out[q] = 0; return; }
+  out[q] = enum_of_code[padded[lat.padded_index_of_id(id)]];
+}
+// Config::GetVacancyLatticeId generalised: the lowest lattice id holding compact code `code` (-1 if none), and the count
+__global__ void find_element_kernel(LatticeDesc lat, const uint8_t *__restrict__ padded, int code, unsigned long long *first, unsigned long long *count) {
+  const int64_t id = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const bool hit = id < lat.num_sites && padded[lat.padded_index_of_id(id)] == code;
+  const unsigned bal = __ballot_sync(0xffffffffu, hit);
+  if (bal && (threadIdx.x & 31) == 0) {
+    atomicMin(first, static_cast<unsigned long long>(id + __ffs(static_cast<int>(bal)) - 1));
+    atomicAdd(count, static_cast<unsigned long long>(__popc(bal)));
+  }
+}
+
+// site set of GetEncodeOfCluster: every listed site and its 42 first- to third-neighbours, marked in a padded-layout byte
+// array (halo images included, like the occupancy)
+__global__ void mark_cluster_sites_kernel(LatticeDesc lat, DevTables tab, const int64_t *__restrict__ sites, int64_t n, uint8_t *member, int *error) {
+  const int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q >= n * 43) return;
+  const int64_t id = sites[q / 43];
+  if (id < 0 || id >= lat.num_sites) { atomicOr(error, kErrBadSite); return; }
+  int x, y, z;
+  lat.coords_of_id(id, x, y, z);
+  const int8_t *o = tab.site_off + 4 * (q % 43);
+  store_site(lat, member, wrap_coord(x + o[0], 2 * lat.fx), wrap_coord(y + o[1], 2 * lat.fy), wrap_coord(z + o[2], 2 * lat.fz), 1);
 }
 
 // ----------------------------------------------------------------------------------------------- debug taps

@@ -877,6 +877,8 @@ SiteTables build_site_tables(const Species &sp, const Coefficients &co) {
   return out;
 }
 
+double energy_cluster_counter(int label) { return kEnergyClusterCounter[label]; }
+
 EnergyTables build_energy_tables(const Species &sp, const Coefficients &co) {
   const int m = sp.n + 1;
   const auto types = cluster_types(sp);

@@ -178,5 +178,6 @@ struct EnergyTables {
 PairTables build_pair_tables(const Species &sp, const Coefficients &co, int model = kModelQuartic);
 SiteTables build_site_tables(const Species &sp, const Coefficients &co);
 EnergyTables build_energy_tables(const Species &sp, const Coefficients &co);
+double energy_cluster_counter(int label);   // normaliser of EnergyPredictor::GetEncode by cluster label (pred/src/EnergyPredictor.cpp:8)
 
 }  // namespace lmc

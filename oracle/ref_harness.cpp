@@ -709,6 +709,34 @@ int ref_energy_get(void *h, void *config_h, double *energy, double *encode, int 
   } catch (const std::exception &e) { return fail(e); }
 }
 
+// EnergyPredictor::GetEnergyOfCluster / GetEncodeOfCluster (pred/src/EnergyPredictor.cpp:97-184) on a list of ATOM ids
+int ref_energy_of_cluster(void *h, void *config_h, const int64_t *atom_ids, int64_t n, double *energy, double *encode, int cap) {
+  try {
+    const auto *p = static_cast<pred::EnergyPredictor *>(h);
+    const auto &c = *static_cast<cfg::Config *>(config_h);
+    std::vector<size_t> ids(atom_ids, atom_ids + n);
+    if (encode) {
+      const auto enc = p->GetEncodeOfCluster(c, ids);
+      for (size_t q = 0; q < enc.size() && q < static_cast<size_t>(cap); ++q) encode[q] = enc[q];
+    }
+    if (energy) *energy = p->GetEnergyOfCluster(c, ids);
+    return 0;
+  } catch (const std::exception &e) { return fail(e); }
+}
+// EnergyPredictor::GetChemicalPotential (pred/src/EnergyPredictor.cpp:196-214): entries in std::map order
+int ref_chemical_potential(void *h, int solvent_code, int *codes_out, double *mu_out, int cap) {
+  try {
+    const auto *p = static_cast<pred::EnergyPredictor *>(h);
+    const auto mu = p->GetChemicalPotential(Element(static_cast<ElementName>(solvent_code)));
+    int k = 0;
+    for (const auto &[el, v] : mu) {
+      if (k < cap) { codes_out[k] = static_cast<int>(static_cast<ElementName>(el)); mu_out[k] = v; }
+      ++k;
+    }
+    return k;
+  } catch (const std::exception &e) { fail(e); return -1; }
+}
+
 // ---------------------------------------------------------------- helpers (pred/include/RateCorrector.hpp, TimeTemperatureInterpolator)
 double ref_rate_correction(double c_vac, double c_solute, double temperature) {
   return pred::RateCorrector(c_vac, c_solute).GetTimeCorrectionFactor(temperature);

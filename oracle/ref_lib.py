@@ -400,6 +400,22 @@ class RefEnergy:
         return e.value, enc[:n_types].copy()
 
 
+    def energy_of_cluster(self, config: RefConfig, atom_ids, n_types=95):
+        ids = np.ascontiguousarray(atom_ids, dtype=np.int64)
+        e = C.c_double()
+        enc = np.zeros(512, dtype=np.float64)
+        if lib().ref_energy_of_cluster(self.h, config.h, _p(ids), C.c_int64(len(ids)), C.byref(e), _p(enc), 512) != 0:
+            raise RuntimeError(_err())
+        return e.value, enc[:n_types].copy()
+
+    def chemical_potential(self, solvent="Al"):
+        codes = np.zeros(16, dtype=np.int32); mu = np.zeros(16, dtype=np.float64)
+        k = lib().ref_chemical_potential(self.h, ELEMENT_CODES[solvent], _p(codes), _p(mu), 16)
+        if k < 0:
+            raise RuntimeError(_err())
+        return {int(c): float(v) for c, v in zip(codes[:k], mu[:k])}
+
+
 def rate_correction(c_vac, c_solute, temperature):
     return float(lib().ref_rate_correction(C.c_double(c_vac), C.c_double(c_solute), C.c_double(temperature)))
 

@@ -105,3 +105,64 @@ def _mt19937_64_alloy(n):
         occ[k] = 2 if u < 0.02 else (3 if u < 0.04 else 1)
     occ[n // 2 + 3] = 0
     return occ
+
+
+@pytest.fixture(scope="module")
+def energy_demo(tmp_path_factory):
+    _build.build()
+    exe = str(tmp_path_factory.mktemp("demo2") / "adapter_energy_demo")
+    libdir = os.path.join(ROOT, "latticemontecarlo_b200")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "adapter_energy_demo.cpp"), "-L" + libdir, "-llmc_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                   check=True)
+    return exe
+
+
+def test_energy_demo_compiles_and_fails_loudly_without_gpu(energy_demo, coef_json, tmp_path):
+    if capi.device_count() > 0:
+        pytest.skip("a GPU is present")
+    (tmp_path / "occ.bin").write_bytes(bytes([1] * 256))
+    res = subprocess.run([energy_demo, coef_json, str(tmp_path / "occ.bin"), "4", "0"], capture_output=True, text=True)
+    assert res.returncode == 1 and "not available" in res.stderr
+
+
+@pytest.mark.gpu
+def test_atom_id_entry_points_and_energy_predictor_surface(energy_demo, golden, tmp_path):
+    """GetBarrierAndDiffFromAtomIdPair, GetDeFromAtomIdPair / Site, Config read accessors, EnergyPredictor::GetEnergyOfCluster /
+    GetEncode / GetChemicalPotential through the C++ adapters, against the reference's own values
+    (tests/golden/golden_energy_v1.npz, make_golden_energy.py) and the C ABI."""
+    from tests import helpers as H
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_energy_v1.npz"), allow_pickle=False)
+    js = H.golden_json(golden, tmp_path)
+    f, reassign = (int(v) for v in g["B_params"])
+    occ = g["B_occ"]
+    (tmp_path / "occ.bin").write_bytes(occ.tobytes())
+    res = subprocess.run([energy_demo, js, str(tmp_path / "occ.bin"), str(f), str(reassign)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    out = res.stdout
+    val = lambda pat: float(re.search(pat, out).group(1))
+    assert abs(val(r"E = ([-0-9.e+]+)") - g["B_energy"][0]) < 1e-9
+    assert abs(val(r"encode n = 95 sum = ([-0-9.e+]+)") - g["B_encode"].sum()) < 1e-9
+    mu = {int(a): float(b) for a, b in re.findall(r"mu\[(\d+)\] = ([-0-9.e+]+)", out)}
+    assert set(mu) == set(int(v) for v in g["mu_elements"])
+    for el, v in zip(g["mu_elements"], g["mu_values"]):
+        assert abs(mu[int(el)] - v) < 1e-9
+    assert "(same atom: 1)" in out and "clone independent: 1" in out
+    assert abs(val(r"dE check ([-0-9.e+]+)")) < 1e-9
+    m = re.search(r"swap dE by atom ids ([-+0-9.e]+) by lattice ids ([-+0-9.e]+)", out)
+    assert m.group(1) == m.group(2)
+    # the same calls through the C ABI (atom id == lattice id before the jump in GenerateFCC order)
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED if reassign else capi.ORDER_GENERATE, device=0)
+    e.load_coefficients(js)
+    e.set_occupancy(occ)
+    vac, n_vac = e.find_element(0)
+    assert n_vac == 1 and re.search(r"vacancy lattice %d atom %d element 0" % (vac, vac), out)
+    assert abs(val(r"E_cluster = ([-0-9.e+]+)") - e.energy_of_cluster([3, 17, 40, vac])) < 1e-11
+    j = int(e.neighbors(1, vac)[4])
+    ea, de = e.eval_barriers([vac], [j])
+    m = re.search(r"jump by atom ids: Ea = ([-0-9.e+]+) dE = ([-+0-9.e]+)", out)
+    assert abs(float(m.group(1)) - ea[0]) < 1e-11 and abs(float(m.group(2)) - de[0]) < 1e-11
+    e.lattice_jump(vac, j)
+    # after the jump the vacancy ATOM sits on lattice site j, the moved atom on the old vacancy site
+    assert abs(val(r"E_cluster after jump = ([-0-9.e+]+)") - e.energy_of_cluster([3, 17, 40, j])) < 1e-11
+    assert abs(val(r"site dE by atom id ([-+0-9.e]+)") - e.eval_site_de([vac], [3])[0]) < 1e-11

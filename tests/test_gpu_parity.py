@@ -318,3 +318,37 @@ np.save(sys.argv[1], np.concatenate([[rc], out]))
     assert np.array_equal(np.isnan(rows), np.isnan(general))
     ok = ~np.isnan(rows)
     assert np.array_equal(rows[ok], general[ok]) and np.count_nonzero(rows[ok]) > 150000
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_energy_predictor_encode_cluster_energy_and_chemical_potential(golden, tag, tmp_path):
+    """EnergyPredictor::GetEncode, GetEnergyOfCluster / GetEncodeOfCluster and GetChemicalPotential(Al)
+    (pred/src/EnergyPredictor.cpp:40-214) against the reference's own outputs (tests/golden/golden_energy_v1.npz)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_energy_v1.npz"), allow_pickle=False)
+    f, reassign = (int(v) for v in g[tag + "_params"])
+    e = capi.Engine(f, id_order=capi.ORDER_REASSIGNED if reassign else capi.ORDER_GENERATE, device=0)
+    e.load_coefficients(H.golden_json(golden, tmp_path))
+    occ = g[tag + "_occ"]
+    e.set_occupancy(occ)
+    assert abs(e.total_energy() - g[tag + "_energy"][0]) < TOL
+    assert np.max(np.abs(e.energy_encode() - g[tag + "_encode"])) < 1e-15          # integer counts / fixed normalisers
+    lattice_of_atom = g[tag + "_lattice_of_atom"]
+    for k in range(int(g[tag + "_n_lists"][0])):
+        ids = lattice_of_atom[g["%s_list%d" % (tag, k)]]
+        assert abs(e.energy_of_cluster(ids) - g["%s_cluster_energy%d" % (tag, k)][0]) < TOL, k
+        assert np.max(np.abs(e.energy_encode(ids) - g["%s_cluster_encode%d" % (tag, k)])) < 1e-15, k
+    assert e.energy_of_cluster([]) == 0.0
+    # the full list is the whole configuration
+    assert abs(e.energy_of_cluster(np.arange(occ.size)) - e.total_energy()) < 1e-9
+    mu = e.chemical_potential(1)
+    assert list(mu) == [int(v) for v in g["mu_elements"]]                          # std::map order: by element name
+    assert np.max(np.abs(np.array(list(mu.values())) - g["mu_values"])) < TOL
+    # Config read accessors
+    sites = np.array([0, 5, occ.size - 1, occ.size // 2])
+    assert np.array_equal(e.get_elements(sites), occ[sites])
+    first, count = e.find_element(0)
+    assert count == np.count_nonzero(occ == 0) and first == int(np.nonzero(occ == 0)[0][0])
+    assert e.find_element(2)[1] == np.count_nonzero(occ == 2)
+    with pytest.raises(capi.LmcInvalidArgument):
+        e.get_elements([occ.size])
