@@ -706,22 +706,15 @@ void run_swap_driver(const Parameter &p, bool annealing) {
   if (annealing) {
     // energy_ = [E(config) - E(pure solvent)] - sum_e mu_e * count_e with mu from 15^3 reference cells
     // (SimulatedAnnealing.cpp:58-70, EnergyPredictor::GetChemicalPotential :196-214)
-    const int32_t f15[3] = {15, 15, 15};
-    EngineHandle ref;
-    check(lmc_engine_create(&ref.e, f15, LMC_ID_ORDER_REASSIGNED, elements.data(), static_cast<int32_t>(elements.size()), solvent, 1, p.device));
-    check(lmc_engine_load_coefficients(ref.e, p.json_coefficients_filename.c_str()));
-    std::vector<uint8_t> pure(4 * 15 * 15 * 15, static_cast<uint8_t>(solvent));
-    double e_pure15 = 0, e_pure = 0;
-    check(lmc_engine_set_occupancy(ref.e, 0, pure.data(), static_cast<int64_t>(pure.size())));
-    check(lmc_total_energy(ref.e, 0, &e_pure15, nullptr, 0));
-    double solution = 0;
+    int32_t mu_el[16];
+    double mu[16];
+    const int32_t n_mu = lmc_chemical_potential(eng.e, solvent, mu_el, mu, 16);
+    check(n_mu);
+    double solution = 0, e_pure = 0;
     for (size_t k = 0; k < p.solute_element_set.size() && k < p.solute_number_set.size(); ++k) {
-      pure[0] = static_cast<uint8_t>(element_from_string(p.solute_element_set[k]));
-      double e1 = 0;
-      check(lmc_engine_set_occupancy(ref.e, 0, pure.data(), static_cast<int64_t>(pure.size())));
-      check(lmc_total_energy(ref.e, 0, &e1, nullptr, 0));
-      solution += (e1 - e_pure15) * static_cast<double>(p.solute_number_set[k]);
-      pure[0] = static_cast<uint8_t>(solvent);
+      const int el = element_from_string(p.solute_element_set[k]);
+      for (int32_t q = 0; q < n_mu; ++q)
+        if (mu_el[q] == el) solution += mu[q] * static_cast<double>(p.solute_number_set[k]);
     }
     std::vector<uint8_t> all_solvent(config.n(), static_cast<uint8_t>(solvent));
     check(lmc_engine_set_occupancy(eng.e, 0, all_solvent.data(), static_cast<int64_t>(all_solvent.size())));

@@ -40,6 +40,14 @@ def main():
                 out["%s_list%d" % (tag, k)] = ids.astype(np.int64)
                 out["%s_cluster_energy%d" % (tag, k)] = np.array([e])
                 out["%s_cluster_encode%d" % (tag, k)] = enc
+        # SimulatedAnnealing's reference energy (mc/src/SimulatedAnnealing.cpp:58-70): energy_ at construction for the
+        # occupancy of golden_v1's SA case = [E(config) - E(pure solvent)] - sum_e mu_e * count_e
+        occ_sa = golden["SA_occ"]
+        f_sa = int(golden["SA_params"][0])
+        cnt = {"Mg": int((occ_sa == 2).sum()), "Zn": int((occ_sa == 3).sum())}
+        tr = R.simulated_annealing(f_sa, "Al", cnt, occ_sa, js, initial_temperature=700.0, maximum_steps=1, seed=9, trace=False)
+        out["SA_initial_energy"] = np.array([tr["energy0"]])
+        print("SA initial_energy", tr["energy0"])
         mu = pred.chemical_potential("Al")
         out["mu_elements"] = np.array(list(mu.keys()), dtype=np.int32)
         out["mu_values"] = np.array(list(mu.values()))

@@ -344,6 +344,16 @@ def test_energy_predictor_encode_cluster_energy_and_chemical_potential(golden, t
     mu = e.chemical_potential(1)
     assert list(mu) == [int(v) for v in g["mu_elements"]]                          # std::map order: by element name
     assert np.max(np.abs(np.array(list(mu.values())) - g["mu_values"])) < TOL
+    # SimulatedAnnealing's reference energy (mc/src/SimulatedAnnealing.cpp:58-70): [E(config) - E(pure solvent)] - sum mu_e n_e
+    # vanishes for isolated solutes -- the reference's constructor value for one Mg + one Zn placed >= 4NN apart is stored
+    pure = np.ones_like(occ)
+    iso = pure.copy()
+    iso[0], iso[occ.size // 2 + 1] = 2, 3
+    e.set_occupancy(pure); e_pure = e.total_energy()
+    e.set_occupancy(iso); e_iso = e.total_energy()
+    initial_energy = (e_iso - e_pure) - mu[2] - mu[3]
+    assert abs(initial_energy) < 1e-9 and abs(initial_energy - g["SA_initial_energy"][0]) < 1e-9
+    e.set_occupancy(occ)
     # Config read accessors
     sites = np.array([0, 5, occ.size - 1, occ.size // 2])
     assert np.array_equal(e.get_elements(sites), occ[sites])
