@@ -52,10 +52,10 @@ struct CmcDomainParams {
 };
 
 // first x index (inclusive) of rank r's slab of the domain grid
-LMC_HD int domain_slab_begin(int ndx, int world, int r) { return static_cast<int>((static_cast<long long>(ndx) * r) / world); }
+LMC_HD int domain_slab_begin(int ndx, int world, int r) { return static_cast<int>((static_cast<unsigned>(ndx) * static_cast<unsigned>(r)) / static_cast<unsigned>(world)); }
 // lower bound (inclusive) of domain i along an axis of `period` half-units cut into nd parts (z: even bounds, see below)
-LMC_HD int domain_lo(int i, int period, int nd) { return static_cast<int>((static_cast<long long>(i) * period) / nd); }
-LMC_HD int domain_lo_z(int i, int fz, int nd) { return 2 * static_cast<int>((static_cast<long long>(i) * fz) / nd); }
+LMC_HD int domain_lo(int i, int period, int nd) { return static_cast<int>((static_cast<unsigned>(i) * static_cast<unsigned>(period)) / static_cast<unsigned>(nd)); }   // i <= nd, period < 2^15: 32 bits
+LMC_HD int domain_lo_z(int i, int fz, int nd) { return 2 * static_cast<int>((static_cast<unsigned>(i) * static_cast<unsigned>(fz)) / static_cast<unsigned>(nd)); }
 
 
 // entry points of cmc_domain.cu

@@ -241,18 +241,7 @@ struct HostConfig {
       fis.ignore(std::numeric_limits<std::streamsize>::max(), '\n');
     }
     // FCC supercell detection: factors from the basis lengths and the site count, sites on the half-unit grid
-    double len[3], volume_cells = static_cast<double>(num_atoms) / 4.0, prod = 1.0;
-    for (int d = 0; d < 3; ++d) {
-      len[d] = std::sqrt(c.basis[d][0] * c.basis[d][0] + c.basis[d][1] * c.basis[d][1] + c.basis[d][2] * c.basis[d][2]);
-      prod *= len[d];
-    }
-    const double scale = std::cbrt(volume_cells / prod);
-    size_t check_sites = 4;
-    for (int d = 0; d < 3; ++d) {
-      c.factors[d] = static_cast<int32_t>(std::lround(len[d] * scale));
-      check_sites *= static_cast<size_t>(c.factors[d]);
-    }
-    if (check_sites != num_atoms) throw std::runtime_error(filename + ": not an FCC supercell (site count does not match the basis)");
+    c.detect_factors(num_atoms, filename);
     c.atom_to_lattice.assign(num_atoms, -1);
     c.lattice_to_atom.assign(num_atoms, -1);
     c.rel_of_lattice.resize(num_atoms);
@@ -362,6 +351,21 @@ struct HostConfig {
       check_sites *= static_cast<size_t>(factors[d]);
     }
     if (check_sites != num_atoms) throw std::runtime_error(filename + ": not an FCC supercell (site count does not match the basis)");
+    // What the engine's integer geometry assumes -- checked, not assumed: an orthogonal cell whose axes are the cubic axes
+    // (the reference would accept any basis and find whatever neighbours its distance cutoffs give), and a lattice
+    // constant for which the reference's cutoffs 3.5 / 4.8 / 5.3 A (cfg/include/Constants.hpp:6-10) select exactly the first,
+    // second and third FCC shells: r1 = a / sqrt 2, r2 = a, r3 = a sqrt(3/2), r4 = a sqrt 2  =>  3.92 A < a <= 4.32 A.
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        if (i != j && std::abs(basis[i][j]) > 1e-6 * len[i])
+          throw std::runtime_error(filename + ": the cell must be orthogonal with its axes along the cubic axes (off-diagonal basis entries found)");
+    for (int d = 0; d < 3; ++d) {
+      const double a = len[d] / factors[d];
+      if (!(a * std::sqrt(1.5) <= 5.3 && a * std::sqrt(2.0) > 5.3 && a > 4.8 / std::sqrt(1.5)))
+        throw std::runtime_error(filename + ": lattice constant " + std::to_string(a) + " A along axis " + std::to_string(d) +
+                                 " is outside the range (3.92, 4.32] A in which the reference's neighbour cutoffs give the FCC 1-3NN shells");
+      if (factors[d] < 4) throw std::runtime_error(filename + ": the supercell needs at least 4 conventional cells per axis");
+    }
   }
   // half-unit grid coordinates of a relative position
   std::array<int, 3> grid_coordinates(const Vec3 &rel, const std::string &filename) const {

@@ -255,3 +255,20 @@ def test_kmc_cli_restart_continues_the_run(exe, golden, tmp_path):
         assert np.max(np.abs(va[3:6] - vb[3:6])) < 1e-9 and np.max(np.abs(va[7:10] - vb[7:10])) < 1e-9
     assert float(a[45][2]) != float(a[0][2])                                   # the temperature ramp is live in the resumed half
     assert gzip.open(full / "end.cfg.gz", "rt").read() == gzip.open(part / "end.cfg.gz", "rt").read()
+
+
+def test_cli_rejects_cells_outside_the_engine_geometry(exe, tmp_path):
+    """The integer FCC geometry needs an orthogonal cubic-axes cell whose lattice constant keeps the reference's distance
+    cutoffs (3.5 / 4.8 / 5.3 A) on the first three FCC shells: anything else is an error, not a silent assumption."""
+    text = open(os.path.join(GOLD, "start.cfg")).read()
+    base = "simulation_method KineticMcFirstOmp\njson_coefficients_filename none.json\nconfig_filename %s\nelement_set Al Mg Zn\nmaximum_steps 1\n"
+    (tmp_path / "sheared.cfg").write_text(text.replace("H0(1,2) = 0 A", "H0(1,2) = 1.5 A"))
+    (tmp_path / "p1.txt").write_text(base % "sheared.cfg")
+    res = subprocess.run([exe, "-p", "p1.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 1 and "must be orthogonal" in res.stderr, res.stderr
+    import re
+    stretched = re.sub(r"H0\((\d),\1\) = ([0-9.]+) A", lambda m: "H0(%s,%s) = %.6f A" % (m.group(1), m.group(1), float(m.group(2)) * 1.1), text)
+    (tmp_path / "stretched.cfg").write_text(stretched)
+    (tmp_path / "p2.txt").write_text(base % "stretched.cfg")
+    res = subprocess.run([exe, "-p", "p2.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 1 and "lattice constant" in res.stderr, res.stderr

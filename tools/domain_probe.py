@@ -83,14 +83,6 @@ if __name__ == "__main__":
         check(24, 1, 200000)
         check(24, 1, 200000, lanes=2)
     if mode in ("all", "rate"):
-        for lanes, spec in ((8, 1), (8, 2), (8, 4)):
-            rate(100, 1, 8 * 4 * 100 ** 3, lanes=lanes, speculate=spec)
-        os.environ["LMC_CMC_DOMAIN_THREADS"] = "512"
-        for lanes, spec in ((8, 1), (8, 2), (8, 4)):
-            rate(100, 1, 8 * 4 * 100 ** 3, lanes=lanes, speculate=spec)
-        rate(20, 148, 8 * 32000, lanes=8, speculate=4)
-        rate(20, 148, 8 * 32000, lanes=8, speculate=2)
-        del os.environ["LMC_CMC_DOMAIN_THREADS"]
-        rate(20, 148, 8 * 32000, lanes=8, speculate=4)
-        rate(20, 148, 8 * 32000, lanes=8, speculate=2)
-        rate(20, 148, 8 * 32000, lanes=8, speculate=1)
+        for f in (100, 50, 40):
+            for edge, rounds in ((8, 0), (6, 0), (6, 128), (6, 216), (10, 0)):
+                rate(f, 1, 8 * 4 * f ** 3, domain_edge=edge, rounds_per_sweep=rounds)

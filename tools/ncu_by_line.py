@@ -11,8 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def line_table(kernel):
     d = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "latticemontecarlo_b200", "liblmc_b200.so")], cwd=d, capture_output=True)
-    cub = [f for f in os.listdir(d) if f.startswith("engine.") and f.endswith(".cubin")][0]
-    sass = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout.splitlines()
+    sass = []
+    for cub in sorted(f for f in os.listdir(d) if f.endswith(".cubin")):       # one cubin per translation unit
+        text = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(d, cub)], capture_output=True, text=True).stdout
+        if kernel in text:
+            sass = text.splitlines()
+            break
     table, cur, inside = {}, None, False
     for ln in sass:
         if ln.startswith("\t.section\t.text."):
