@@ -290,8 +290,8 @@ int lmc_cmc_attach_peers(lmc_engine *engine, int32_t rank, int32_t world, const 
  *   3. each rank: lmc_cmc_domain_attach_peers(engine, rank, world, handles[world][192])
  *   4. barrier, then every rank calls lmc_cmc_domain_run with identical arguments. */
 typedef struct lmc_cmc_domain_params {
-  int32_t domain_edge;             /* target domain edge in half lattice constants, 4..48 (0 = 8) */
-  int32_t rounds_per_sweep;        /* Metropolis rounds per domain and sweep (0 = (domain_edge - 2)^3, two per core site) */
+  int32_t domain_edge;             /* target domain edge in half lattice constants, 4..48 (0 = 6: cores of 32 sites) */
+  int32_t rounds_per_sweep;        /* Metropolis rounds per domain and sweep (0 = 216) */
   int32_t speculate;               /* rounds of one domain evaluated at once on the current state and committed up to the first
                                     * accepted one: 1, 2 (with 8 or 16 lanes) or 4 (with 8 lanes); 0 = 32 / lanes when the lattice
                                     * has fewer domains than the GPU has warp slots, else 1.  Exactly the sequential chain */
