@@ -1,6 +1,9 @@
 // cmc_domain.cu -- translation unit of the domain-decomposed CMC / SA driver: the instantiations of the sweep kernel
 // (cmc_domain_kernels.cuh) and the two small kernels around it.  Kept apart from engine.cu so that the two dozen
 // instantiations compile in parallel with the rest of the library.
+#ifdef LMC_DOM_PROFILE
+#include <cstdio>
+#endif
 #include "cmc_domain_kernels.cuh"
 
 namespace lmc {

@@ -208,6 +208,9 @@ __device__ __forceinline__ bool dom_intergpu_sum(const CmcDomainParams &dp, unsi
 // gives every unordered unlike pair of the core the same probability 1 / (S_list * ncore) per draw.  One Philox call per
 // draw, keyed by (seed, sweep, domain, round, try): the random stream does not depend on the launch shape.
 constexpr int kDomTries = 4;
+#ifdef LMC_DOM_PROFILE
+__device__ unsigned long long g_dom_hist[6][64];
+#endif
 template <int L, int kTab, int kMaxThreads, int S>
 __global__ void __launch_bounds__(kMaxThreads, 1)
 cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState st, uint64_t seed, unsigned long long target_steps) {
@@ -452,6 +455,10 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
       // T rounds at a time (one Philox call per lane and T rounds), and a round's values are broadcast when it comes up.
       uint32_t pre_kb = 0, pre_ulo = 0, pre_uhi = 0;
       int r0 = can_draw ? 0 : rounds, blk = -T;              // next round to commit; first round of the drawn block
+#ifdef LMC_DOM_PROFILE
+      const long long tp0 = clock64();
+      int tp_steps = 0;
+#endif
       while (__any_sync(0xffffffffu, r0 < rounds)) {
         if (r0 < rounds && r0 >= blk + T) {
           blk += T;
@@ -619,9 +626,23 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
             if (eb == solvent) list[slot] = static_cast<uint16_t>(core_b);     // the non-solvent atom now sits at b
           }
           if (r0 < rounds) r0 += committed;
+#ifdef LMC_DOM_PROFILE
+          if (n_active > 0) ++tp_steps;
+#endif
         }
         __syncwarp();
       }
+#ifdef LMC_DOM_PROFILE
+      if (tl == 0 && has_item) {
+        const long long cyc = clock64() - tp0;
+        atomicAdd(&g_dom_hist[0][min(63, tp_steps / 4)], 1ULL);                 // speculative batches per domain-sweep
+        atomicAdd(&g_dom_hist[1][min(63, static_cast<int>(cyc >> 15))], 1ULL);  // cycles per domain-sweep (2^15 per bin)
+        atomicAdd(&g_dom_hist[2][min(63, static_cast<int>(n_sol))], 1ULL);      // non-solvent core sites
+        atomicAdd(&g_dom_hist[3][min(63, static_cast<int>(acc))], 1ULL);        // accepted trials
+        atomicAdd(&g_dom_hist[4][min(63, static_cast<int>(n_sol))], static_cast<unsigned long long>(cyc));   // cycles by n_sol
+        atomicAdd(&g_dom_hist[5][min(63, static_cast<int>(n_sol))], static_cast<unsigned long long>(tp_steps));
+      }
+#endif
       // ---- write the domain back (canonical cells only) -- locally and to the ranks that will hold these planes next sweep
       if (has_item) {
         const int nk = Dz >> 1;
@@ -710,6 +731,20 @@ cmc_domain_kernel(LatticeDesc lat, DevTables tab, CmcDomainParams dp, CmcState s
     }
     ++sweep;
   }
+#ifdef LMC_DOM_PROFILE
+  __syncthreads();
+  if (cta == 0 && tid == 0) {
+    const char *names[4] = {"batches/4", "cycles>>15", "n_sol", "accepted"};
+    for (int h = 0; h < 4; ++h) {
+      printf("hist %s:", names[h]);
+      for (int q = 0; q < 64; ++q) if (g_dom_hist[h][q]) printf(" %d:%llu", q, g_dom_hist[h][q]);
+      printf("\n");
+    }
+    printf("mean cycles / batches by n_sol:");
+    for (int q = 0; q < 64; ++q) if (g_dom_hist[2][q]) printf(" %d:%llu/%llu", q, g_dom_hist[4][q] / g_dom_hist[2][q], g_dom_hist[5][q] / g_dom_hist[2][q]);
+    printf("\n");
+  }
+#endif
   __syncthreads();
   if (cta == 0) {
     // leaving through the "done" test: the prologue has just written the final state into the parity buffer of `sweep`
