@@ -71,6 +71,27 @@ int main(int argc, char **argv) {
     chain.Simulate();
     check(lmc_kmc_get_state(chain.GetConfig().engine(), &t, &e, &steps, nullptr, nullptr));
     std::printf("chain KMC: %lld steps, time %.6e s, energy %+.9f eV\n", static_cast<long long>(steps), t, e);
+    {
+      // canonical MC on a vacancy-free deep copy: global pairs (the reference's proposal), then the domain-decomposed driver
+      cfg::Config cmc_config = config.Clone();
+      occ[vacancy] = static_cast<uint8_t>(ElementName::Al);
+      cmc_config.SetOccupancy(occ);
+      const double e_start = energy.GetEnergy(cmc_config);
+      mc::CanonicalMcOmp cmc(cmc_config, 1999, 800.0, argv[1], 7);
+      cmc.Simulate();
+      double de_sum = 0, temperature = 0;
+      int64_t trials = 0, accepted = 0;
+      cmc.GetState(&de_sum, &trials, &accepted, &temperature);
+      std::printf("CMC: %lld trials, %lld accepted, energy drift %.3e eV\n", static_cast<long long>(trials), static_cast<long long>(accepted),
+                  std::abs(energy.GetEnergy(cmc.GetConfig()) - (e_start + de_sum)));
+      mc::CanonicalMcOmp domain_cmc(cmc_config, 1999, 800.0, argv[1], 7);     // continues on the same engine state
+      domain_cmc.SetDomainDecomposition(6, 64);
+      const double e_mid = energy.GetEnergy(cmc_config);
+      domain_cmc.Simulate();
+      domain_cmc.GetState(&de_sum, &trials, &accepted, &temperature);
+      std::printf("domain CMC: %lld trials, %lld accepted, energy drift %.3e eV\n", static_cast<long long>(trials),
+                  static_cast<long long>(accepted), std::abs(energy.GetEnergy(domain_cmc.GetConfig()) - (e_mid + de_sum)));
+    }
   } catch (const std::exception &e) {
     std::fprintf(stderr, "error: %s\n", e.what());
     return 1;

@@ -466,11 +466,26 @@ class CanonicalMcOmp {
     pred::LoadCoefficients(config_, json_coefficients_filename);
     check(lmc_cmc_reset(config_.engine(), simulated_annealing ? temperature : 0.0, simulated_annealing ? maximum_steps : 0));
   }
+  // Extension (no reference counterpart): swap partners are drawn inside box domains of `domain_edge` half lattice constants
+  // whose grid is shifted at random before every sweep of `rounds_per_sweep` trials per domain (0 = engine defaults: 6 / 216).
+  // Same Metropolis rule and equilibrium distribution as the global-pair driver (tests/test_gpu_cmc_stat.py), 5-10x the
+  // trial rate; trials advance in whole sweeps, so Simulate() may overshoot maximum_steps by less than one sweep.
+  void SetDomainDecomposition(int domain_edge = 0, int rounds_per_sweep = 0) {
+    domain_ = true;
+    domain_params_ = lmc_cmc_domain_params{};
+    domain_params_.domain_edge = domain_edge;
+    domain_params_.rounds_per_sweep = rounds_per_sweep;
+  }
   void Simulate() {
     lmc_cmc_params prm{};
     prm.temperature = temperature_;
     prm.seed = seed_;
-    check(lmc_cmc_run(config_.engine(), &prm, static_cast<int64_t>(maximum_steps_ + 1)));
+    if (domain_) check(lmc_cmc_domain_run(config_.engine(), &prm, &domain_params_, static_cast<int64_t>(maximum_steps_ + 1)));
+    else check(lmc_cmc_run(config_.engine(), &prm, static_cast<int64_t>(maximum_steps_ + 1)));
+  }
+  // energy relative to the start, trials done, trials accepted, current temperature (the SA schedule moves it)
+  void GetState(double *energy, int64_t *steps, int64_t *accepted, double *temperature) const {
+    check(lmc_cmc_get_state(config_.engine(), energy, steps, accepted, temperature));
   }
   [[nodiscard]] const cfg::Config &GetConfig() const { return config_; }
 
@@ -479,6 +494,8 @@ class CanonicalMcOmp {
   unsigned long long maximum_steps_;
   double temperature_;
   uint64_t seed_;
+  bool domain_{false};
+  lmc_cmc_domain_params domain_params_{};
 };
 }  // namespace mc
 

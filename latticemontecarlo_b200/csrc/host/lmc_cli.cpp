@@ -70,6 +70,8 @@ struct Parameter {
   bool seed_given{false};
   std::string replay_uniforms_filename;   // validation: "u1 u2" per KMC step instead of the device RNG
   std::string replay_trials_filename;     // validation: "site_a site_b u" per CMC trial (the reference's serial stream)
+  int domain_edge{0};                     // extension: > 0 runs CMC / SA with the domain-decomposed driver (lmc_cmc_domain_run)
+  int rounds_per_sweep{0};
   int device{0};
 
   static std::vector<std::string> split(const std::string &s) {
@@ -118,6 +120,8 @@ struct Parameter {
       } else if (k == "seed") { seed = std::stoull(v); seed_given = true; }
       else if (k == "replay_uniforms_filename") replay_uniforms_filename = v;
       else if (k == "replay_trials_filename") replay_trials_filename = v;
+      else if (k == "domain_edge") domain_edge = std::stoi(v);
+      else if (k == "rounds_per_sweep") rounds_per_sweep = std::stoi(v);
       else if (k == "device") device = std::stoi(v);
     }
   }
@@ -813,7 +817,16 @@ void run_swap_driver(const Parameter &p, bool annealing) {
     // run to the next step the reference would log (its cadence is log-spaced up to 10 * log_dump_steps)
     unsigned long long target = steps + 1;
     while (target <= last && !log_this_step(target, p.log_dump_steps) && !(annealing && target % std::max(1ULL, p.log_dump_steps) == 0)) ++target;
-    check(lmc_cmc_run(eng.e, &prm, static_cast<int64_t>(target - steps)));
+    if (p.domain_edge > 0) {
+      // swap partners drawn inside randomly shifted box domains; advances in whole sweeps (domains x rounds_per_sweep trials),
+      // which is then the granularity of the log rows
+      lmc_cmc_domain_params dom{};
+      dom.domain_edge = p.domain_edge;
+      dom.rounds_per_sweep = p.rounds_per_sweep;
+      check(lmc_cmc_domain_run(eng.e, &prm, &dom, static_cast<int64_t>(target - steps)));
+    } else {
+      check(lmc_cmc_run(eng.e, &prm, static_cast<int64_t>(target - steps)));
+    }
     read_state(energy, steps, temperature);
     averaging.AddEnergy(energy);
     if (annealing && energy < lowest_energy - kEpsilon) {

@@ -4,10 +4,13 @@
 //
 // One half-warp owns one walker for the whole launch: lanes 0..11 evaluate the 12 candidate jumps of the walker's
 // vacancy (barrier kernel body), the 12 events are put in the reference's order (ascending neighbour lattice id),
-// Arrhenius rates, the cumulative-probability select and the residence-time update are done with half-warp
-// shuffles in exactly the reference's (sequential) floating point order, and the jump is written back to the
-// walker's occupancy.  Random numbers come from Philox4x32-10 (key = seed ^ walker, counter = step) or, in replay
-// mode, from host-supplied (u1, u2) streams so that the reference's event sequence can be reproduced.
+// the total rate and the cumulative probabilities of the select are accumulated in the reference's (sequential) order,
+// and the jump is written back to the walker's occupancy.  The residence time is (-ln u1 / total) * (corr / 1e13) -- one
+// division per step; the reference divides by 1e13 first and multiplies by corr afterwards, so the two agree to the
+// last bit or one ulp per step (the tests bound the accumulated time at 1e-9 relative).  Random numbers come from
+// Philox4x32-10 (key = seed ^ walker, counter = step; u1 is shifted to (0, 1] so that the logarithm stays finite, the
+// reference's generate_canonical delivers [0, 1)) or, in replay mode, from host-supplied (u1, u2) streams so that the
+// reference's event sequence can be reproduced.
 #pragma once
 #include "kernels.cuh"
 

@@ -179,6 +179,20 @@ def test_cmc_and_sa_cli_run_and_log(exe, golden, coef_json, tmp_path):
     assert np.array_equal(np.sort(final), np.sort(occ))
     e.set_occupancy(final)
     assert abs(e.total_energy() - float(rows[-1][4])) < 1e-6
+    # the same run with the domain-decomposed driver (extension keys): whole sweeps, same bookkeeping
+    os.rename(tmp_path / "cmc_log.txt", tmp_path / "cmc_log_global.txt")
+    (tmp_path / "cmc_dom.txt").write_text((tmp_path / "cmc.txt").read_text() + "domain_edge 6\nrounds_per_sweep 32\n")
+    res = subprocess.run([exe, "-p", "cmc_dom.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 0, res.stderr
+    head, rows = _rows((tmp_path / "cmc_log.txt").read_text())
+    steps = [int(r[0]) for r in rows]
+    assert steps[0] == 0 and steps == sorted(steps) and steps[-1] == 3000
+    offs = [float(r[4]) - float(r[2]) for r in rows]
+    assert max(offs) - min(offs) < 1e-8
+    final = occupancy_of(tmp_path / "end.cfg.gz")
+    assert np.array_equal(np.sort(final), np.sort(occ)) and not np.array_equal(final, occ)
+    e.set_occupancy(final)
+    assert abs(e.total_energy() - float(rows[-1][4])) < 1e-6
     (tmp_path / "sa.txt").write_text("simulation_method SimulatedAnnealing\njson_coefficients_filename c.json\nfactor 6\nsolvent_element Al\n"
                                      "solute_element_set Mg Zn\nsolute_number_set 12 15\nlog_dump_steps 1000\nconfig_dump_steps 100000\n"
                                      "maximum_steps 6000\ninitial_temperature 700\nseed 9\n")

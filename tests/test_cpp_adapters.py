@@ -38,6 +38,11 @@ def test_adapter_demo_matches_c_abi(demo, coef_json):
     de = np.array([float(m) for m in re.findall(r"dE = ([-+0-9.e]+) eV", res.stdout)])
     assert len(ea) == 12 and "std::out_of_range as in the reference" in res.stdout and "KMC: 1000 steps" in res.stdout
     assert "chain KMC: 500 steps" in res.stdout
+    # CanonicalMcOmp adapter, global pairs and domain decomposition: the accumulated dE equals the change of the total energy
+    m = re.search(r"^CMC: (\d+) trials, (\d+) accepted, energy drift ([-0-9.e+]+) eV", res.stdout, re.M)
+    assert m and int(m.group(1)) >= 2000 and int(m.group(2)) > 0 and float(m.group(3)) < 1e-8
+    m = re.search(r"^domain CMC: (\d+) trials, (\d+) accepted, energy drift ([-0-9.e+]+) eV", res.stdout, re.M)
+    assert m and int(m.group(1)) >= 2000 and int(m.group(2)) > 0 and float(m.group(3)) < 1e-8
     # the same occupancy through the Python binding: the demo draws it with std::mt19937_64(42), re-created here
     f = 6
     e = capi.Engine(f, device=0)
