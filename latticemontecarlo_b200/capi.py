@@ -47,10 +47,11 @@ def declared_symbols():
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("LMC_B200_LIB", LIB_PATH)      # A/B runs of two builds (tools/ab.sh); the default is the in-tree library
+        if not os.path.exists(path):
             raise RuntimeError("liblmc_b200.so not built: run `python -m latticemontecarlo_b200.build` "
                                "(there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(path)
         _lib.lmc_last_error.restype = C.c_char_p
         _lib.lmc_engine_num_sites.restype = C.c_int64
         _lib.lmc_tables_mapping.restype = C.c_int64

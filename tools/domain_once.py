@@ -15,4 +15,8 @@ if warm:
     e.cmc_domain_run(warm, temperature=800.0, seed=5, lanes=lanes, domain_edge=edge)
 e.cmc_domain_run(trials, temperature=800.0, seed=5, lanes=lanes, domain_edge=edge)
 st = e.cmc_state()
-print(st["steps"].sum(), e.last_kernel_ms(), e.cmc_domain_last_shape())
+import hashlib
+ms = e.last_kernel_ms()
+digest = hashlib.sha1(np.ascontiguousarray(e.get_occupancy_all()).tobytes()).hexdigest()[:16]
+print(st["steps"].sum(), ms, e.cmc_domain_last_shape())
+print("digest", digest, "energy %.12f" % float(np.sum(st["energy"])), "accepted", int(np.sum(st["accepted"])))
