@@ -205,6 +205,16 @@ def test_cmc_and_sa_cli_run_and_log(exe, golden, coef_json, tmp_path):
     final = occupancy_of(tmp_path / "end.cfg.gz")
     assert (final == 2).sum() == 12 and (final == 3).sum() == 15
     assert os.path.exists(tmp_path / "lowest_energy.cfg.gz")
+    # simulated annealing with the domain-decomposed driver: same log format, schedule evaluated per sweep
+    (tmp_path / "sa_dom.txt").write_text((tmp_path / "sa.txt").read_text() + "domain_edge 6\nrounds_per_sweep 16\n")
+    res = subprocess.run([exe, "-p", "sa_dom.txt"], capture_output=True, text=True, cwd=tmp_path)
+    assert res.returncode == 0 and "initial_energy = " in res.stdout, res.stderr
+    head, rows = _rows((tmp_path / "sa_log.txt").read_text())
+    temps = [float(r[1]) for r in rows]
+    assert temps[0] == 700.0 and temps[-1] < 0.2 * temps[0] and int(rows[-1][0]) == 6000
+    assert float(rows[-1][3]) <= float(rows[0][2]) + 1e-9                        # lowest_energy never above the start
+    final = occupancy_of(tmp_path / "end.cfg.gz")
+    assert (final == 2).sum() == 12 and (final == 3).sum() == 15
 
 
 @pytest.mark.gpu
