@@ -52,7 +52,7 @@ def test_domain_driver_bookkeeping_conservation_and_temperature_order(coef_json)
     assert np.max(np.abs((e_after - e_start) - st3["energy"])) < 5e-9
 
 
-@pytest.mark.parametrize("f,edge", [(4, 0), (6, 12), (10, 7), (16, 8), (16, 10)])
+@pytest.mark.parametrize("f,edge", [(4, 0), (6, 12), (10, 7), (16, 8), (16, 10), ((5, 9, 14), 6), ((12, 4, 7), 0)])
 def test_trajectory_does_not_depend_on_the_launch_shape(coef_json, monkeypatch, f, edge):
     """Same seed => same occupancy, steps and accepted counts for every (lanes, speculative rounds), for the A + B table
     form against the difference tables, and for several domains per lane group; energies equal to the rounding of dE
