@@ -182,6 +182,11 @@ def run_reference(args):
     return 0
 
 
+def kmc_kernel_name(lanes):
+    """The first-order kernel the library chose: thousands of walkers -> half-warp per walker; a few per SM -> block per walker."""
+    return "kmc_run_kernel" if lanes == 0 else "kmc_team_run_kernel<%d>" % lanes
+
+
 def workload_config(args, n_gpus):
     return {"workload": "BASELINE configs[2]: batched KMC, %d independent single-vacancy Al-2%%Mg-2%%Zn walkers on 8x8x8 FCC "
                         "(2048 sites), T=400..600 K, walker w on GPU w mod %d, synthetic JSON coefficients (K=24/32)" % (args.walkers, n_gpus),
@@ -264,7 +269,7 @@ def run_ours(args):
         res = {"engine": engine, "occ_pinned": occ_pinned, "temps": temps, "step_ms": step_ms, "kernel_ms": kernel_ms,
                "local_kernel_ms": sum(t[1] for t in timings), "wall": wall, "launches": launches, "clocks": sampler,
                "walkers_advanced_all_steps": int(np.count_nonzero(advanced == H * steps)), "min_steps_advanced": int(advanced.min()),
-               "age_hops": [int(steps_before.min()), int(st["steps"].max())]}
+               "age_hops": [int(steps_before.min()), int(st["steps"].max())], "lanes": engine.kmc_last_launch_lanes()}
         if with_e2e:
             # ---- end to end through the C ABI with host buffers: H2D occupancy, reset, run, D2H state + occupancy
             def step_e2e():
@@ -306,8 +311,8 @@ def run_ours(args):
         "gpu_launches": int(head["launches"]),
         "walkers_advanced_all_steps": int(advanced_all), "walkers_total": W_total,
         "walker_age_hops_during_timed_region": head["age_hops"],
-        "roofline": {"kernel": "kmc_run_kernel", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H), "peak_kind": peak_kind,
+        "roofline": {"kernel": kmc_kernel_name(head["lanes"]), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H) if head["lanes"] == 0 else None, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": int(W * H * BYTES_PER_KMC_STEP),
                      "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
                              "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"},
@@ -333,6 +338,8 @@ def run_ours(args):
                                        "walkers_advanced_all_steps": rich["walkers_advanced_all_steps"],
                                        "note": "same driver on Al-10%Mg-10%Zn walkers: the table walk is O(non-solvent sites + their pairs)"}
             rich["engine"].close()
+    if rank == 0 and n_gpus == 1 and not args.no_age:
+        line["low_occupancy"] = bench_low_occupancy(local_rank, js, max(1, W_total // 8), H)
     cmc_multi = None
     if world > 1 and not args.no_cmc:
         cmc_multi = bench_cmc_multi_gpu(torch, dist, local_rank, rank, world, js)      # collective: every rank takes part
@@ -444,6 +451,44 @@ def bench_barrier_eval(engine, torch, W, peak):
     return out
 
 
+def bench_low_occupancy(device, json_path, walkers, hops):
+    """One GPU's share of the job when it is spread over 8 GPUs (1024 of 8192 walkers: 7 per SM).  A KMC step is a serial
+    dependency, so this is a latency measurement: the half-warp kernel against the block-per-walker kernel the library
+    picks at this occupancy (LMC_KMC_TEAM_LANES is read at every launch)."""
+    from latticemontecarlo_b200 import capi
+    eng = capi.Engine(FACTOR, id_order=capi.ORDER_REASSIGNED, n_walkers=walkers, device=device)
+    eng.load_coefficients(json_path)
+    occ = walker_occupancy(0, walkers, stride=8)
+    temps = 400.0 + 200.0 * (8 * np.arange(walkers)) / max(1, 8 * walkers - 1)
+    out = {"walkers": walkers, "hops_per_launch": hops, "unit": "hops/s"}
+    saved = os.environ.get("LMC_KMC_TEAM_LANES")
+    try:
+        for name, forced in (("half_warp_kernel", "0"), ("library_choice", None)):
+            if forced is None:
+                os.environ.pop("LMC_KMC_TEAM_LANES", None)
+            else:
+                os.environ["LMC_KMC_TEAM_LANES"] = forced
+            eng.set_occupancy_all(occ)
+            eng.kmc_reset()
+            eng.kmc_run(hops, temperatures=temps, seed=20260101)
+            ms = []
+            for _ in range(3):
+                eng.kmc_run(hops, temperatures=temps, seed=20260101)
+                ms.append(eng.last_kernel_ms())
+            st = eng.kmc_state()
+            out[name] = {"kernel": kmc_kernel_name(eng.kmc_last_launch_lanes()), "value": walkers * hops / (min(ms) * 1e-3), "kernel_ms": min(ms),
+                         "us_per_step": min(ms) * 1e3 / hops, "walkers_advanced_all_steps": int(np.count_nonzero(st["steps"] == 4 * hops)),
+                         "vacancy_digest": int(np.bitwise_xor.reduce(st["vacancy"] * (np.arange(walkers) + 1)))}
+    finally:
+        if saved is None:
+            os.environ.pop("LMC_KMC_TEAM_LANES", None)
+        else:
+            os.environ["LMC_KMC_TEAM_LANES"] = saved
+    out["same_trajectories"] = out["half_warp_kernel"]["vacancy_digest"] == out["library_choice"]["vacancy_digest"]
+    eng.close()
+    return out
+
+
 def bench_single_trajectory(device, json_path):
     """BASELINE configs[0] / configs[4]: ONE vacancy trajectory (a step is a serial dependency, so this is a latency
     number): 10^6-site Al-2%Mg-2%Zn supercell (f = 63), time-temperature ramp + rate corrector, first- and second-order KMC."""
@@ -465,6 +510,7 @@ def bench_single_trajectory(device, json_path):
             ms.append(eng.last_kernel_ms())
         st = eng.kmc_state()
         out[name] = {"value": steps / (min(ms) * 1e-3), "kernel_ms": min(ms), "us_per_step": min(ms) * 1e3 / steps,
+                     "kernel": "kmc_chain_run_kernel" if second_order else kmc_kernel_name(eng.kmc_last_launch_lanes()),
                      "time_reached_s": float(st["time"][0]), "temperature_reached_K": float(st["temperature"][0])}
     eng.close()
     return out

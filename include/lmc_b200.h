@@ -204,6 +204,10 @@ int lmc_kmc_reset(lmc_engine *engine);
  * Philox stream by caller-supplied uniforms: u1 -> residence time, u2 -> event selection, in the reference's draw order. */
 int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_steps, const double *replay_u1,
                 const double *replay_u2, const lmc_kmc_trace *trace);
+/* launch shape of the most recent lmc_kmc_run: 0 = throughput kernel (half-warp per walker, kmc_run_kernel); 8 / 16 / 32 =
+ * latency kernel (thread block per walker, that many lanes per candidate jump, kmc_team_run_kernel), which the library
+ * picks when the engine holds only a few walkers per SM.  Both walk the same Philox trajectories. */
+int lmc_kmc_last_launch_lanes(const lmc_engine *engine);
 /* Second-order ("chain") KMC: mc::KineticMcChainOmpi::Simulate (mc/src/KineticMcChainOmpi.cpp:56-152,
  * mc/include/KineticMcAbstract.h:65-143; the method script/kmc_param.txt:1 selects).  Per step and walker, for each of
  * the 12 neighbours i of the vacancy site k (the reference's 12 MPI ranks, ascending lattice id): the 12 jumps i -> l in

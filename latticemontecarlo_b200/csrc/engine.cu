@@ -16,6 +16,7 @@
 #include "engine.h"
 #include "kernels.cuh"
 #include "kmc_kernels.cuh"
+#include "kmc_team_kernels.cuh"
 #include "cmc_kernels.cuh"
 #include "cmc_grid_kernels.cuh"
 #include "cmc_domain.h"
@@ -739,6 +740,40 @@ void Engine::kmc_reset() {
   kmc_ready = true;
 }
 
+// The launch shape of a first-order KMC run.  A block per walker with 8 / 16 / 32 lanes per candidate jump is used when
+// every walker's block is resident at once (a second wave would double the run time) -- the widest group that fits;
+// thousands of walkers go to the half-warp kernel.  LMC_KMC_TEAM_LANES = 0 / 8 / 16 / 32 overrides the choice (A/B runs).
+const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t smem, int *lanes_out) {
+  const int forced = std::getenv("LMC_KMC_TEAM_LANES") ? std::atoi(std::getenv("LMC_KMC_TEAM_LANES")) : -1;
+  const int max_per_sm = std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM") ? std::atoi(std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM")) : 7;
+  if (forced == 0) return nullptr;
+  auto kernel_for = [&](int lanes) -> const void * {
+    switch (lanes) {
+      case 8: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<8, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<8, false>);
+      case 16: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<16, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<16, false>);
+      case 32: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<32, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<32, false>);
+    }
+    return nullptr;
+  };
+  int sms = 0, dev = 0;
+  LMC_CUDA(cudaGetDevice(&dev));
+  LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  for (int lanes : {32, 16, 8}) {
+    if (forced > 0 && lanes != forced) continue;
+    const void *kernel = kernel_for(lanes);
+    LMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int per_sm = 0;
+    LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 12 * lanes + 32, smem));
+    const int64_t resident = static_cast<int64_t>(per_sm) * sms;
+    // measured on B200 (tools/kmc_team_sweep.sh, profiles/r2_k_team_sweep.txt): 16 lanes per jump up to ~3 walkers per SM, 8 lanes
+    // up to 7; 32 lanes are within 3 % of 16 where they win (1 walker per SM) and are only chosen by the override
+    const double per_sm_limit = lanes == 32 ? 0.0 : (lanes == 16 ? 3.0 : static_cast<double>(max_per_sm));
+    if (forced > 0 || (n_walkers <= resident && n_walkers <= per_sm_limit * sms)) { *lanes_out = lanes; return kernel; }
+  }
+  if (forced > 0) throw std::invalid_argument("LMC_KMC_TEAM_LANES must be 0, 8, 16 or 32");
+  return nullptr;
+}
+
 void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double *u1, const double *u2, const lmc_kmc_trace *trace,
                      bool second_order) {
   require_device();
@@ -797,7 +832,12 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     LMC_CUDA(cudaFuncSetAttribute(kmc_chain_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
     kmc_chain_run_kernel<<<static_cast<unsigned>(n_walkers), kChainThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st,
                                                                                                prm, n_steps, d_u2, tr);
+  } else if (const void *team = kmc_team_kernel_choice(instrumented, kmc_smem, &kmc_team_lanes)) {
+    // few walkers: a thread block per walker (kmc_team_kernels.cuh) -- the step is latency-bound, not throughput-bound
+    void *args[] = {&lat, &tab, &d_occ, const_cast<int64_t *>(&lat.padded_size), &n_walkers, &st, &prm, &n_steps, &d_u1, &d_u2, &tr};
+    LMC_CUDA(cudaLaunchKernel(team, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * kmc_team_lanes + 32)), args, kmc_smem, stream));
   } else {
+    kmc_team_lanes = 0;
     if (instrumented) kmc_run_kernel<true><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
     else kmc_run_kernel<false><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
   }
@@ -1709,6 +1749,7 @@ double lmc_engine_last_kernel_ms(lmc_engine *engine) {
   return ms;
 }
 int64_t lmc_engine_launch_count(const lmc_engine *engine) { return engine ? engine->impl->launch_count : 0; }
+int lmc_kmc_last_launch_lanes(const lmc_engine *engine) { return engine ? engine->impl->kmc_team_lanes : 0; }
 int lmc_eval_vacancy_events(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site, int64_t *neighbour_site,
                             double *Ea, double *dE) {
   return guard([&] { engine->impl->eval_vacancy_events(n, walker, vacancy_site, neighbour_site, Ea, dE); });

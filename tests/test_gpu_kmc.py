@@ -12,6 +12,15 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
+@pytest.fixture(autouse=True, params=["0", "8", "16", "32"], ids=lambda v: "halfwarp" if v == "0" else "team%s" % v)
+def kmc_launch_shape(request, monkeypatch):
+    """Every test of this module runs on the throughput kernel (half-warp per walker, kmc_run_kernel) and on the three
+    instantiations of the latency kernel (block per walker with 8 / 16 / 32 lanes per candidate jump,
+    kmc_team_run_kernel); the library reads the switch at every launch.  The second-order driver ignores it."""
+    monkeypatch.setenv("LMC_KMC_TEAM_LANES", request.param)
+    return request.param
+
+
 def _engine(golden, tag, tmp_path, n_walkers=1):
     order = capi.ORDER_REASSIGNED if int(golden[tag + "_factor"][1]) else capi.ORDER_GENERATE
     e = capi.Engine(int(golden[tag + "_factor"][0]), id_order=order, n_walkers=n_walkers, device=0)
@@ -222,3 +231,34 @@ def test_chain_runs_are_chunkable_and_suppress_flicker(golden, tmp_path):
     _, _, tf = run([120], second_order=False)
     back = lambda t: float(np.mean(t["to"][:, 1:] == t["from"][:, :-1]))
     assert back(t1) < back(tf)
+
+
+def test_latency_kernel_walks_the_throughput_kernels_trajectories(golden, tmp_path, monkeypatch):
+    """kmc_team_run_kernel adds the contracted table terms in a different order (tree over lanes) than kmc_run_kernel,
+    so dE / Ea agree to rounding, not bit for bit; the Philox stream and the select arithmetic are the same, so the
+    walkers must visit the same sites.  Also the automatic choice (few walkers -> a block per walker)."""
+    e = _engine(golden, "B", tmp_path, n_walkers=40)
+    occ = golden["B_occ"]
+    temps = np.linspace(420.0, 580.0, 40)
+
+    def run(shape):
+        if shape is None:
+            monkeypatch.delenv("LMC_KMC_TEAM_LANES", raising=False)
+        else:
+            monkeypatch.setenv("LMC_KMC_TEAM_LANES", shape)
+        for w in range(40):
+            e.set_occupancy(occ, walker=w)
+        e.kmc_reset()
+        tr = e.kmc_run(300, temperatures=temps, seed=2024, trace=True)
+        e.kmc_run(211, temperatures=temps, seed=2024)
+        return e.kmc_state(), e.get_occupancy_all(), tr
+
+    s0, o0, t0 = run("0")
+    for shape in ("8", "16", "32", None):
+        s1, o1, t1 = run(shape)
+        assert np.array_equal(o0, o1), shape
+        assert np.array_equal(s0["vacancy"], s1["vacancy"]) and np.array_equal(s0["steps"], s1["steps"])
+        assert np.array_equal(t0["to"], t1["to"]) and np.array_equal(t0["slot"], t1["slot"])
+        assert np.max(np.abs(t0["Ea"] - t1["Ea"])) < 1e-12 and np.max(np.abs(t0["dE"] - t1["dE"])) < 1e-12
+        assert np.allclose(s0["time"], s1["time"], rtol=1e-12, atol=0)
+        assert np.max(np.abs(s0["energy"] - s1["energy"])) < 1e-10
