@@ -115,6 +115,12 @@ class Engine {
   void *d_scratch{nullptr};
   void *h_pinned{nullptr};
   size_t scratch_bytes{0};
+  // request grouping (grouping.h): own workspace (the staging scratch above holds the caller's arrays meanwhile)
+  void *d_group{nullptr};
+  size_t group_bytes{0};
+  unsigned int *h_group_local{nullptr};
+  bool last_grouped{false};
+  const uint32_t *group_if_scattered(int64_t n, const int32_t *walker, const int64_t *site);
   // KMC per-walker state (device)
   int64_t *d_kmc_vacancy{nullptr}, *d_kmc_steps{nullptr};
   double *d_kmc_time{nullptr}, *d_kmc_energy{nullptr}, *d_kmc_temperature{nullptr}, *d_kmc_cvac{nullptr}, *d_kmc_csol{nullptr};

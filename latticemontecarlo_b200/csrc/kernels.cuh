@@ -206,12 +206,13 @@ __global__ void __launch_bounds__(kBarrierThreads)
 barrier_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
                const int32_t *__restrict__ walker, const int64_t *__restrict__ site_i, const int64_t *__restrict__ site_j,
                double *__restrict__ Ea, double *__restrict__ dE, double *__restrict__ D_out, double *__restrict__ Ks_out,
-               int *__restrict__ error) {
+               int *__restrict__ error, const uint32_t *__restrict__ perm) {
   __shared__ int32_t s_delta[24 * kPairDeltaStride];
   for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
   __syncthreads();
-  const int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (e >= n) return;
+  const int64_t q_thread = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (q_thread >= n) return;
+  const int64_t e = perm ? static_cast<int64_t>(perm[q_thread]) : q_thread;      // grouped by lattice region (grouping.h); results in caller order
   const int64_t i = site_i[e], j = site_j[e];
   const int w = walker ? walker[e] : 0;
   const double nan = CUDART_NAN;
@@ -479,7 +480,7 @@ template <int kMinBlocks>
 __global__ void __launch_bounds__(kSwapThreads, kMinBlocks)
 swap_de_rows_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ occ, int64_t walker_stride, int64_t n,
                     const int32_t *__restrict__ walker, const int64_t *__restrict__ site_a, const int64_t *__restrict__ site_b,
-                    double *__restrict__ dE, int *__restrict__ error, int first_neighbours_only) {
+                    double *__restrict__ dE, int *__restrict__ error, int first_neighbours_only, const uint32_t *__restrict__ perm) {
   // dynamic shared memory sized for the actual species count (small footprint => the rest of the 256 KB stays L1)
   extern __shared__ __align__(16) unsigned char swap_smem[];
   const int m = tab.n_species + 1;
@@ -495,7 +496,8 @@ swap_de_rows_kernel(LatticeDesc lat, DevTables tab, const uint8_t *__restrict__ 
   const unsigned solvent = static_cast<unsigned>(tab.solvent);
   const int sy = lat.nz, sx = lat.ny * lat.nz;
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
-  for (int64_t e = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; e < n; e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  for (int64_t q = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; q < n; q += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t e = perm ? static_cast<int64_t>(perm[q]) : q;      // grouped by the region of site a (grouping.h); results in caller order
     const int64_t a = site_a[e], b = site_b[e];
     if (a < 0 || a >= lat.num_sites || b < 0 || b >= lat.num_sites) {
       atomicOr(error, kErrBadSite);

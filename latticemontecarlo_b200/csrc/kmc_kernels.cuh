@@ -18,6 +18,12 @@ namespace lmc {
 
 constexpr double kPrefactorHz = 1e13;                // Constants.hpp:32
 
+// pair-table loads of the walk in flight together (same summation order as one at a time: bit-identical results).
+// Measured on B200, 8192 walkers x 2048 hops x 8 launches: 1 -> 128.0 ms, 2 -> 125.6 ms, 3 -> 129.6 ms
+#ifndef LMC_KMC_BATCH_B
+#define LMC_KMC_BATCH_B 2
+#endif
+
 struct KmcState {            // per-walker arrays in device memory
   int64_t *vacancy;          // lattice id of the vacancy
   double *time, *energy;     // time_ / energy_ of McAbstract
@@ -241,6 +247,25 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
           uint32_t p_lo = hi.x & w_lo, p_hi = hi.y & w_hi;             // partners u > t still to visit
           if ((p_lo | p_hi) == 0) continue;
           const int row = (s_pbase[t] * n + et) * n;
+#if LMC_KMC_BATCH_B > 1
+          do {                                       // LMC_KMC_BATCH_B partners per pass: their table loads are in flight together
+            double2 b[LMC_KMC_BATCH_B];
+#pragma unroll
+            for (int q = 0; q < LMC_KMC_BATCH_B; ++q) {
+              b[q] = make_double2(0.0, 0.0);
+              if ((p_lo | p_hi) == 0) continue;
+              int u;
+              if (p_lo) { u = __ffs(static_cast<int>(p_lo)) - 1; p_lo &= p_lo - 1; }
+              else { u = 31 + __ffs(static_cast<int>(p_hi)); p_hi &= p_hi - 1; }
+              const int eu = my_codes[u];
+              if (eu >= n) { ok = false; continue; }
+              const int rank = u < 32 ? __popc(hi.x & ((1u << u) - 1u)) : __popc(hi.x) + __popc(hi.y & ((1u << (u - 32)) - 1u));
+              b[q] = __ldg(B + row + rank * (n * n) + eu);
+            }
+#pragma unroll
+            for (int q = 0; q < LMC_KMC_BATCH_B; ++q) { a0 += b[q].x; a1 += b[q].y; }
+          } while (p_lo | p_hi);
+#else
           do {
             int u;
             if (p_lo) { u = __ffs(static_cast<int>(p_lo)) - 1; p_lo &= p_lo - 1; }
@@ -252,6 +277,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
             const double2 b = __ldg(B + row + rank * (n * n) + eu);
             a0 += b.x; a1 += b.y;
           } while (p_lo | p_hi);
+#endif
         }
         if (!ok) err |= kErrExtraVacancy;
         else {

@@ -362,3 +362,54 @@ def test_energy_predictor_encode_cluster_energy_and_chemical_potential(golden, t
     assert e.find_element(2)[1] == np.count_nonzero(occ == 2)
     with pytest.raises(capi.LmcInvalidArgument):
         e.get_elements([occ.size])
+
+
+def test_grouped_requests_give_the_callers_order_bit_for_bit(coef_json, monkeypatch):
+    """Device-side grouping of scattered requests (grouping.cu: requests ordered by the lattice region of their first
+    site, kernels run over the permutation) must not change a single bit of any result nor their order; the automatic
+    choice (barrier events only; swaps are grouped only on request) leaves an already local request order alone."""
+    f, W = 8, 24
+    e = capi.Engine(f, n_walkers=W, device=0)
+    e.load_coefficients(coef_json)
+    vac = np.empty(W, dtype=np.int64)
+    occs = []
+    for w in range(W):
+        occ = synth.random_alloy(f, 0.05, 0.05, seed=900 + w)
+        e.set_occupancy(occ, walker=w)
+        occs.append(occ)
+        vac[w] = int(np.nonzero(occ == 0)[0][0])
+    nb = np.stack([e.neighbors(1, int(v)) for v in vac])
+    rng = np.random.default_rng(5)
+    n_ev = W * 12 * 40
+    perm = rng.permutation(n_ev)
+    w_ev = np.tile(np.repeat(np.arange(W, dtype=np.int32), 12), 40)[perm]
+    i_ev = np.tile(np.repeat(vac, 12), 40)[perm]
+    j_ev = np.tile(nb.reshape(-1), 40)[perm]
+    n_sw = 20000
+    w_sw = rng.integers(0, W, n_sw).astype(np.int32)
+    a_sw = rng.integers(0, e.num_sites, n_sw)
+    b_sw = rng.integers(0, e.num_sites, n_sw)
+    vac_hit = (a_sw == vac[w_sw]) | (b_sw == vac[w_sw])             # keep the vacancy out of the swaps
+    a_sw[vac_hit] = (vac[w_sw[vac_hit]] + 7) % e.num_sites
+    b_sw[vac_hit] = (vac[w_sw[vac_hit]] + 11) % e.num_sites
+
+    def run(mode):
+        if mode is None:
+            monkeypatch.delenv("LMC_GROUP_REQUESTS", raising=False)
+            monkeypatch.setenv("LMC_GROUP_MIN", "1000")
+        else:
+            monkeypatch.setenv("LMC_GROUP_REQUESTS", mode)
+        ea, de, d, ks = e.eval_barriers(i_ev, j_ev, walker=w_ev, want_parts=True)
+        return ea, de, d, ks, e.eval_swap_de(a_sw, b_sw, walker=w_sw)
+
+    plain, grouped, auto = run("0"), run("1"), run(None)
+    for k in range(5):
+        assert np.array_equal(plain[k], grouped[k]), k
+        assert np.array_equal(plain[k], auto[k]), k
+    assert np.all(np.isfinite(plain[0])) and np.all(np.isfinite(plain[4]))
+    # requests that are already grouped by vacancy are left in place by the automatic choice (and give the same numbers)
+    monkeypatch.delenv("LMC_GROUP_REQUESTS", raising=False)
+    monkeypatch.setenv("LMC_GROUP_MIN", "100")
+    ea_g, de_g = e.eval_barriers(np.repeat(vac, 12), nb.reshape(-1), walker=np.repeat(np.arange(W, dtype=np.int32), 12))
+    back = np.argsort(perm)[: W * 12]                                 # where the first copy of every event went
+    assert np.array_equal(ea_g, plain[0][back]) and np.array_equal(de_g, plain[1][back])

@@ -19,6 +19,8 @@ for f in [int(v) for v in sys.argv[1:]] or [40]:
     while same.size:
         b[same] = rng.integers(0, occ.size, same.size)
         same = same[occ[a[same]] == occ[b[same]]]
+    if os.environ.get("PROBE_PRESORT"):                       # the order grouping would produce, made on the host (no sort, no indirection)
+        order = np.argsort(a, kind="stable"); a, b = a[order], b[order]
     d_a, d_b = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
     d_de = torch.empty(n, dtype=torch.float64, device="cuda")
     ms = []
