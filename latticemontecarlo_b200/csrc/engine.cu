@@ -814,9 +814,10 @@ const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t smem, int *
     int per_sm = 0;
     LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 12 * lanes + 32, smem));
     const int64_t resident = static_cast<int64_t>(per_sm) * sms;
-    // measured on B200 (tools/kmc_team_sweep.sh, profiles/r2_k_team_sweep.txt): 16 lanes per jump up to ~3 walkers per SM, 8 lanes
-    // up to 7; 32 lanes are within 3 % of 16 where they win (1 walker per SM) and are only chosen by the override
-    const double per_sm_limit = lanes == 32 ? 0.0 : (lanes == 16 ? 3.0 : static_cast<double>(max_per_sm));
+    // measured on B200 (tools/kmc_team_sweep.sh, profiles/r2_k_team_sweep.txt): 32 lanes per jump win by ~5 % around one
+    // walker per SM, 16 lanes up to ~3 walkers per SM (and for a handful of walkers), 8 lanes up to 7
+    if (forced <= 0 && lanes == 32 && n_walkers < 64) continue;
+    const double per_sm_limit = lanes == 32 ? 1.0 : (lanes == 16 ? 3.0 : static_cast<double>(max_per_sm));
     if (forced > 0 || (n_walkers <= resident && n_walkers <= per_sm_limit * sms)) { *lanes_out = lanes; return kernel; }
   }
   if (forced > 0) throw std::invalid_argument("LMC_KMC_TEAM_LANES must be 0, 8, 16 or 32");

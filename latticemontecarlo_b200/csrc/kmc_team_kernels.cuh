@@ -10,11 +10,11 @@
 //    lane and pass -- no box scan, no compaction, no cell -> env mapping loop), the non-solvent mask comes from ballots,
 //    every lane contracts the table terms of the sites it loaded itself (A term + its pairs with higher partners, the
 //    table loads of up to four partners in flight together), and a shuffle tree adds the partial sums.  The first lane
-//    of each group evaluates the closed form and files (Ea, dE) in the reference's event order (slot = rank of the
-//    neighbour's lattice id, found by the group's lanes while the gather is in flight).
+//    of each group files (dE, log E0) in the reference's event order (slot = rank of the neighbour's lattice id, a table
+//    lookup by the vacancy's boundary / parity class).
 //  * one more warp, the SELECTOR, owns the walker's clock: while the event threads work it prepares the step's
-//    uniforms and store addresses; when the events have arrived (named barrier A: the events only ARRIVE) it turns the
-//    12 barriers into rates in one instruction stream, runs the reference's sequential total / division / running sum /
+//    uniforms; when the events have arrived (named barrier A: the events only ARRIVE) it evaluates the 12 closed forms
+//    and rates in one instruction stream, runs the reference's sequential total / division / running sum /
 //    select, writes the jump, publishes the new vacancy site and arrives at barrier B, on which the event threads wait.
 //    The residence time, the clock, T(t) and the rate corrector are updated after that, off the critical path.
 //
@@ -37,8 +37,12 @@ namespace lmc {
 __device__ __forceinline__ void team_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void team_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// boundary / parity class of a half-unit coordinate (periods are even and >= 8): 0 = coordinate 0, 3 = period - 1, else 1 + parity
+__device__ __forceinline__ int coord_class(int v, int period) { return v == 0 ? 0 : (v == period - 1 ? 3 : 1 + (v & 1)); }
+__device__ __forceinline__ int class_representative(int c, int period) { return c == 0 ? 0 : (c == 3 ? period - 1 : 1 + c); }
+
 template <int G, bool kInstrumented>
-__global__ void __launch_bounds__(12 * G + 32)
+__global__ void __launch_bounds__(12 * G + 32, G == 8 ? 7 : (G == 16 ? 3 : 1))     // resident blocks per SM the dispatch counts on
 kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                     int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
   static_assert(G == 8 || G == 16 || G == 32, "lanes per candidate jump");
@@ -51,15 +55,33 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
   __shared__ uint8_t s_codes[12][64];             // species by env index, per candidate jump (non-solvent sites only)
-  __shared__ double s_ea[12], s_de[12];           // in event (slot) order
+  __shared__ double s_de[12], s_le[12];           // (dE, log E0) in event (slot) order
   __shared__ __align__(16) double s_p[12];
   __shared__ uint8_t s_dir[12], s_mig[12];
   __shared__ int s_sel_x, s_sel_y, s_sel_z;       // the new vacancy site
   __shared__ int s_err, s_stop;
+  // The event order of the 12 jumps (ascending lattice id of the neighbour) depends on the vacancy site only through, per
+  // axis, whether a neighbour wraps around the period (coordinate 0 or period - 1) and the coordinate's parity: 4 classes
+  // per axis.  Slot of jump k for every class, ranked once per block on a representative site of the class.
+  __shared__ uint8_t s_slot[64][12];
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
   if (threadIdx.x == 0) { s_err = 0; s_stop = 0; }
+  {
+    const int px_ = 2 * lat.fx, py_ = 2 * lat.fy, pz_ = 2 * lat.fz;
+    for (int q = threadIdx.x; q < 64 * 12; q += blockDim.x) {
+      const int cls = q / 12, kk = q % 12;
+      const int RX = class_representative(cls >> 4, px_), RY = class_representative((cls >> 2) & 3, py_), RZ = class_representative(cls & 3, pz_);
+      int rank = 0;
+      if (((RX + RY + RZ) & 1) == 0) {             // classes of the other parity hold no site
+        const int64_t id_k = lat.id_of_coords(wrap_coord(RX + tab.nn1[4 * kk], px_), wrap_coord(RY + tab.nn1[4 * kk + 1], py_), wrap_coord(RZ + tab.nn1[4 * kk + 2], pz_));
+        for (int o2 = 0; o2 < 12; ++o2)
+          rank += lat.id_of_coords(wrap_coord(RX + tab.nn1[4 * o2], px_), wrap_coord(RY + tab.nn1[4 * o2 + 1], py_), wrap_coord(RZ + tab.nn1[4 * o2 + 2], pz_)) < id_k;
+      }
+      s_slot[cls][kk] = static_cast<uint8_t>(rank);
+    }
+  }
   __syncthreads();
   const int w = blockIdx.x;
   if (w >= n_walkers || st.error[w] != 0 || st.vacancy[w] < 0) return;     // uniform over the block
@@ -77,16 +99,10 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
     const int sub = threadIdx.x % G;
     const int gshift = lane & ~(G - 1);              // position of the group inside its warp
     const unsigned gmask = G == 32 ? full : ((1u << G) - 1u);
-    const int dxk = tab.nn1[4 * k], dyk = tab.nn1[4 * k + 1], dzk = tab.nn1[4 * k + 2];
-    // the directions whose neighbour ids this lane ranks against the group's own (sub, and sub + 8 for 8-lane groups)
-    const int q0 = sub < 12 ? sub : 0, q1 = (G == 8 && sub + 8 < 12) ? sub + 8 : 0;
-    const int dx0 = tab.nn1[4 * q0], dy0 = tab.nn1[4 * q0 + 1], dz0 = tab.nn1[4 * q0 + 2];
-    const int dx1 = tab.nn1[4 * q1], dy1 = tab.nn1[4 * q1 + 1], dz1 = tab.nn1[4 * q1 + 2];
     const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
     const double2 *A_all = reinterpret_cast<const double2 *>(s_A2);
     const uint2 *mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
     const int b_stride = tab.n_pair_pairs * n * n;
-    const int barrier_model = tab.barrier_model;
     uint8_t *codes = s_codes[k];
 #ifdef LMC_KMC_TEAM_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tick = clock64();
@@ -102,19 +118,9 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
         const int t = sub + G * j;
         c[j] = t < 60 ? static_cast<unsigned>(o[base + drow[t]]) : solvent;
       }
-      // ---- event order (KineticMcFirstOmp.cpp:52-68): slot = rank of this jump's neighbour id among the 12 neighbour ids
-      int slot;
-      {
-        const uint32_t id_k = static_cast<uint32_t>(lat.id_of_coords(wrap_coord(X + dxk, px), wrap_coord(Y + dyk, py), wrap_coord(Z + dzk, pz)));
-        const uint32_t id_0 = static_cast<uint32_t>(lat.id_of_coords(wrap_coord(X + dx0, px), wrap_coord(Y + dy0, py), wrap_coord(Z + dz0, pz)));
-        unsigned less = __ballot_sync(full, sub < 12 && id_0 < id_k);
-        slot = __popc((less >> gshift) & gmask);
-        if (G == 8) {
-          const uint32_t id_1 = static_cast<uint32_t>(lat.id_of_coords(wrap_coord(X + dx1, px), wrap_coord(Y + dy1, py), wrap_coord(Z + dz1, pz)));
-          less = __ballot_sync(full, sub + 8 < 12 && id_1 < id_k);
-          slot += __popc((less >> gshift) & gmask);
-        }
-      }
+      // ---- event order (KineticMcFirstOmp.cpp:52-68): slot = rank of this jump's neighbour id among the 12 neighbour ids,
+      // a function of the vacancy's boundary / parity class only (table built at block start)
+      const int slot = s_slot[(coord_class(X, px) * 4 + coord_class(Y, py)) * 4 + coord_class(Z, pz)][k];
       // ---- non-solvent mask over the env index, species of the two pair sites
       uint64_t pm = 0;                               // by state position
 #pragma unroll
@@ -192,14 +198,14 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
       }
       LMC_TEAM_TICK(2);                              // shuffle tree
       if (err) atomicOr(&s_err, err);
-      else if (sub == 0) {
+      else if (sub == 0) {                           // (dE, log E0) of this jump; the selector evaluates the 12 closed forms in one stream
         s_de[slot] = a0;
-        s_ea[slot] = barrier_from_folded(a0, a1, barrier_model);
+        s_le[slot] = a1;
         s_dir[slot] = static_cast<uint8_t>(k);
         s_mig[slot] = static_cast<uint8_t>(mig);
       }
       __syncwarp(full);
-      LMC_TEAM_TICK(3);                              // closed form
+      LMC_TEAM_TICK(3);                              // filing
       team_bar_arrive(kBarA, kThreads);              // the 12 events of this step are filed
       team_bar_sync(kBarB, kThreads);                // the selector has jumped (or stopped the walker)
       if (*static_cast<volatile int *>(&s_stop)) break;
@@ -219,6 +225,7 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   int64_t steps = st.steps[w];
   const double c_vac = st.c_vacancy[w], c_sol = st.c_solute[w];
   const int ql = lane < 12 ? lane : 0;             // lane q < 12 keeps direction q (the jump) and owns slot q (the select)
+  const int barrier_model = tab.barrier_model;
   const int dxl = tab.nn1[4 * ql], dyl = tab.nn1[4 * ql + 1], dzl = tab.nn1[4 * ql + 2];
   const bool tracing = kInstrumented && (tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature);
   double beta = 1.0 / kBoltzmannEv / temperature;
@@ -267,7 +274,8 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
     }
     LMC_TEAM_TICK(1);                              // wait for the events (the flag load cannot pass the barrier)
     // CalculateTime + SelectEvent (KineticMcFirstOmp.cpp:55-77, KineticMcAbstract.cpp:106-116): lane q < 12 owns slot q
-    const double my_ea = s_ea[ql], my_de = s_de[ql];
+    const double my_de = s_de[ql];
+    const double my_ea = barrier_from_folded(my_de, s_le[ql], barrier_model);      // 12 closed forms in one instruction stream
     const int my_dir = s_dir[ql];
     const unsigned my_mig = s_mig[ql];
     const double rate = lane < 12 ? exp(-my_ea * beta) : 0.0;            // JumpEvent.cpp:13
