@@ -208,6 +208,9 @@ int lmc_kmc_run(lmc_engine *engine, const lmc_kmc_params *params, int64_t n_step
  * latency kernel (thread block per walker, that many lanes per candidate jump, kmc_team_run_kernel), which the library
  * picks when the engine holds only a few walkers per SM.  Both walk the same Philox trajectories. */
 int lmc_kmc_last_launch_lanes(const lmc_engine *engine);
+/* 1 if that launch was a latency-kernel launch that kept every walker's occupancy in shared memory (cells up to 48 KB
+ * padded, e.g. the 8 x 8 x 8 cell of the batched workload: 5.8 KB; LMC_KMC_TEAM_SMEM=0 switches it off), else 0. */
+int lmc_kmc_last_launch_resident_occupancy(const lmc_engine *engine);
 /* Second-order ("chain") KMC: mc::KineticMcChainOmpi::Simulate (mc/src/KineticMcChainOmpi.cpp:56-152,
  * mc/include/KineticMcAbstract.h:65-143; the method script/kmc_param.txt:1 selects).  Per step and walker, for each of
  * the 12 neighbours i of the vacancy site k (the reference's 12 MPI ranks, ascending lattice id): the 12 jumps i -> l in

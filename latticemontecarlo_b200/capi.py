@@ -327,6 +327,10 @@ class Engine:
         """0: half-warp-per-walker kernel; 8 / 16 / 32: block-per-walker latency kernel with that many lanes per jump."""
         return int(lib().lmc_kmc_last_launch_lanes(self.h))
 
+    def kmc_last_launch_resident_occupancy(self):
+        """True if the last first-order launch was a latency-kernel launch with the walkers' occupancy in shared memory."""
+        return bool(lib().lmc_kmc_last_launch_resident_occupancy(self.h))
+
     # ---- device-resident batches (inputs already in HBM): pointers are raw device addresses (e.g. tensor.data_ptr())
     def eval_barriers_dev(self, n, walker_ptr, i_ptr, j_ptr, ea_ptr, de_ptr):
         _check(lib().lmc_eval_barriers_dev(self.h, C.c_int64(int(n)), C.c_void_p(walker_ptr or None), C.c_void_p(i_ptr), C.c_void_p(j_ptr),

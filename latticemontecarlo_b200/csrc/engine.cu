@@ -792,16 +792,23 @@ void Engine::kmc_reset() {
 // The launch shape of a first-order KMC run.  A block per walker with 8 / 16 / 32 lanes per candidate jump is used when
 // every walker's block is resident at once (a second wave would double the run time) -- the widest group that fits;
 // thousands of walkers go to the half-warp kernel.  LMC_KMC_TEAM_LANES = 0 / 8 / 16 / 32 overrides the choice (A/B runs).
-const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t smem, int *lanes_out) {
+const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out) {
   const int forced = std::getenv("LMC_KMC_TEAM_LANES") ? std::atoi(std::getenv("LMC_KMC_TEAM_LANES")) : -1;
   const int max_per_sm = std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM") ? std::atoi(std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM")) : 7;
   if (forced == 0) return nullptr;
-  auto kernel_for = [&](int lanes) -> const void * {
+  // small cells: the walker's occupancy resident in shared memory (LMC_KMC_TEAM_SMEM=0 switches it off for A/B runs)
+  const bool smem_env = !(std::getenv("LMC_KMC_TEAM_SMEM") && std::atoi(std::getenv("LMC_KMC_TEAM_SMEM")) == 0);
+  const size_t occ_smem = static_cast<size_t>(lat.padded_size) + 16;
+  auto kernel_for = [&](int lanes, bool resident_occ) -> const void * {
+#define LMC_TEAM_CASE(G) \
+    case G: return resident_occ ? (instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<G, true, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<G, false, true>)) \
+                                : (instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<G, true, false>) : reinterpret_cast<const void *>(kmc_team_run_kernel<G, false, false>));
     switch (lanes) {
-      case 8: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<8, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<8, false>);
-      case 16: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<16, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<16, false>);
-      case 32: return instrumented ? reinterpret_cast<const void *>(kmc_team_run_kernel<32, true>) : reinterpret_cast<const void *>(kmc_team_run_kernel<32, false>);
+      LMC_TEAM_CASE(8)
+      LMC_TEAM_CASE(16)
+      LMC_TEAM_CASE(32)
     }
+#undef LMC_TEAM_CASE
     return nullptr;
   };
   int sms = 0, dev = 0;
@@ -809,16 +816,24 @@ const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t smem, int *
   LMC_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   for (int lanes : {32, 16, 8}) {
     if (forced > 0 && lanes != forced) continue;
-    const void *kernel = kernel_for(lanes);
-    LMC_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    int per_sm = 0;
-    LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 12 * lanes + 32, smem));
-    const int64_t resident = static_cast<int64_t>(per_sm) * sms;
     // measured on B200 (tools/kmc_team_sweep.sh, profiles/r2_k_team_sweep.txt): 32 lanes per jump win by ~5 % around one
     // walker per SM, 16 lanes up to ~3 walkers per SM (and for a handful of walkers), 8 lanes up to 7
     if (forced <= 0 && lanes == 32 && n_walkers < 64) continue;
     const double per_sm_limit = lanes == 32 ? 1.0 : (lanes == 16 ? 3.0 : static_cast<double>(max_per_sm));
-    if (forced > 0 || (n_walkers <= resident && n_walkers <= per_sm_limit * sms)) { *lanes_out = lanes; return kernel; }
+    for (int resident_occ = (smem_env && occ_smem <= (48u << 10)) ? 1 : 0; resident_occ >= 0; --resident_occ) {
+      const void *kernel = kernel_for(lanes, resident_occ != 0);
+      const size_t smem = table_smem + (resident_occ ? occ_smem : 0);
+      if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess) { cudaGetLastError(); continue; }
+      int per_sm = 0;
+      LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 12 * lanes + 32, smem));
+      const int64_t resident = static_cast<int64_t>(per_sm) * sms;
+      if (per_sm > 0 && ((forced > 0 && (n_walkers <= resident || !resident_occ)) || (n_walkers <= resident && n_walkers <= per_sm_limit * sms))) {
+        *lanes_out = lanes;
+        *smem_out = smem;
+        kmc_team_resident_occ = resident_occ != 0;
+        return kernel;
+      }
+    }
   }
   if (forced > 0) throw std::invalid_argument("LMC_KMC_TEAM_LANES must be 0, 8, 16 or 32");
   return nullptr;
@@ -871,21 +886,24 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     tr.slot = trace->slot ? reinterpret_cast<int32_t *>(cursor) : nullptr;
   }
   KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error, d_kmc_previous};
-  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed};
+  // LMC_KMC_SELECT_MARGIN (tests; read at every launch): a value > 1 sends every first-order step through the sequential select
+  const double select_margin = std::getenv("LMC_KMC_SELECT_MARGIN") ? std::atof(std::getenv("LMC_KMC_SELECT_MARGIN")) : kSelectMargin;
+  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, std::max(select_margin, kSelectMargin)};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
   if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the KMC driver orders events by 32-bit lattice ids (num_sites < 2^31)");
   const size_t kmc_smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
   const bool instrumented = tracing || d_u1 != nullptr;      // the first-order kernel reads its tables through L1: no dynamic shared memory
+  size_t team_smem = kmc_smem;
   time_begin();
   if (second_order) {
     LMC_CUDA(cudaFuncSetAttribute(kmc_chain_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
     kmc_chain_run_kernel<<<static_cast<unsigned>(n_walkers), kChainThreads, kmc_smem, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st,
                                                                                                prm, n_steps, d_u2, tr);
-  } else if (const void *team = kmc_team_kernel_choice(instrumented, kmc_smem, &kmc_team_lanes)) {
+  } else if (const void *team = kmc_team_kernel_choice(instrumented, kmc_smem, &kmc_team_lanes, &team_smem)) {
     // few walkers: a thread block per walker (kmc_team_kernels.cuh) -- the step is latency-bound, not throughput-bound
     void *args[] = {&lat, &tab, &d_occ, const_cast<int64_t *>(&lat.padded_size), &n_walkers, &st, &prm, &n_steps, &d_u1, &d_u2, &tr};
-    LMC_CUDA(cudaLaunchKernel(team, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * kmc_team_lanes + 32)), args, kmc_smem, stream));
+    LMC_CUDA(cudaLaunchKernel(team, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * kmc_team_lanes + 32)), args, team_smem, stream));
   } else {
     kmc_team_lanes = 0;
     if (instrumented) kmc_run_kernel<true><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
@@ -1800,6 +1818,9 @@ double lmc_engine_last_kernel_ms(lmc_engine *engine) {
 }
 int64_t lmc_engine_launch_count(const lmc_engine *engine) { return engine ? engine->impl->launch_count : 0; }
 int lmc_kmc_last_launch_lanes(const lmc_engine *engine) { return engine ? engine->impl->kmc_team_lanes : 0; }
+int lmc_kmc_last_launch_resident_occupancy(const lmc_engine *engine) {
+  return engine && engine->impl->kmc_team_lanes > 0 && engine->impl->kmc_team_resident_occ ? 1 : 0;
+}
 int lmc_eval_vacancy_events(lmc_engine *engine, int64_t n, const int32_t *walker, const int64_t *vacancy_site, int64_t *neighbour_site,
                             double *Ea, double *dE) {
   return guard([&] { engine->impl->eval_vacancy_events(n, walker, vacancy_site, neighbour_site, Ea, dE); });

@@ -128,7 +128,8 @@ class Engine {
   int64_t *d_kmc_previous{nullptr};
   bool kmc_ready{false};
   int kmc_team_lanes{0};       // lanes per candidate jump of the last first-order KMC launch (0: half-warp kernel)
-  const void *kmc_team_kernel_choice(bool instrumented, size_t smem, int *lanes_out);
+  bool kmc_team_resident_occ{false};   // ... and whether that launch kept the walkers' occupancy in shared memory
+  const void *kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out);
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};
   unsigned long long *d_cmc_steps{nullptr}, *d_cmc_accepted{nullptr}, *d_cmc_proposals{nullptr}, *d_cmc_epoch{nullptr};

@@ -39,7 +39,56 @@ struct KmcParams {
   const double *tt_time, *tt_temp;
   int32_t rate_corrector;
   uint64_t seed;
+  double select_margin;      // latency kernel: rounding margin of its one-pass event selection (select_event_fast); > 1 = always the sequential form
 };
+
+// One-pass event selection of the latency kernel (kmc_team_kernels.cuh).
+// SelectEvent (KineticMcAbstract.cpp:106-116) picks the first slot whose running sum of p_q = rate_q / total is not below
+// u2, with `total` and the running sum accumulated one after the other: three dependent passes over the 12 events.
+// The same slot follows from ONE pass whenever u2 is not within rounding distance of a boundary.  With the exact
+// partial sums S_i of the (non-negative) rates and S = S_11, the reference's running sum c_i equals S_i / S up to a
+// relative error below 24 ulp (11 additions in `total`, one division, 11 additions in the sum), i.e. |c_i - S_i / S| <
+// 3e-15.  Here lane i adds the rates of slots 0..i as a tree, P_i (relative error <= 4 ulp), T = P_11, and compares
+// P_i with u2 T (one more rounding): |(P_i - u2 T) / T - (S_i / S - u2)| < 2e-15.  If |P_i - u2 T| > margin T with
+// margin = 1e-12 for every slot, both forms order every c_i and u2 alike and select the same slot.  Otherwise (about
+// 2e-11 of the steps, or a total that is zero, infinite or NaN) the caller runs the reference's sequential form.
+// Returns whether `below` (this lane's "c_i < u2") is decided; the caller votes over the lanes that own a slot.
+constexpr double kSelectMargin = 1e-12;
+// kWidth = 0: every lane adds T itself (a latency-bound caller); 16 / 32: T is shuffled from lane 11 of each kWidth-lane group
+template <int kWidth>
+__device__ __forceinline__ bool select_event_fast(const double (&r)[12], int lane, double u2, double margin, bool &below) {
+  double m[12];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) m[q] = q <= lane ? r[q] : 0.0;
+  const double P = ((m[0] + m[1]) + (m[2] + m[3])) + ((m[4] + m[5]) + (m[6] + m[7])) + ((m[8] + m[9]) + (m[10] + m[11]));
+  double T;
+  if (kWidth == 0) T = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7])) + ((r[8] + r[9]) + (r[10] + r[11]));
+  else T = __shfl_sync(0xFFFFFFFFu, P, 11, kWidth == 0 ? 32 : kWidth);
+  const double d = fma(-u2, T, P);
+  below = d < 0.0;
+  return fabs(d) > margin * T;                                             // false for NaN and for T = 0 or infinity
+}
+
+// The reference's form (KineticMcFirstOmp.cpp:55-77, KineticMcAbstract.cpp:106-116): total, p_q = rate_q / total and the
+// running sum, each accumulated in slot order.  `rates` (shared memory: the 12 rates of this lane group in slot order) is
+// overwritten with the probabilities.  Called by all lanes of a warp together; out of line, because it runs about once
+// in 1e10 steps and must not cost the callers registers.  Returns this lane's "c_lane < u2".
+__device__ __noinline__ bool select_event_sequential(double *rates, int lane, bool owns_slot, double u2, double *total_out) {
+  double total = 0.0;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) total += rates[q];
+  const double mine = rates[owns_slot ? lane : 0];
+  __syncwarp(0xFFFFFFFFu);
+  if (owns_slot) rates[lane] = mine / total;
+  __syncwarp(0xFFFFFFFFu);
+  double cumulative = 0.0;                      // ((p0 + p1) + p2) + ... + p_lane
+#pragma unroll
+  for (int q = 0; q < 12; ++q)
+    if (q <= lane) cumulative += rates[q];
+  __syncwarp(0xFFFFFFFFu);
+  *total_out = total;
+  return cumulative < u2;
+}
 
 struct KmcTraceDev {         // optional per-step records, [walker][n_steps]; any pointer may be null
   int64_t *from, *to;

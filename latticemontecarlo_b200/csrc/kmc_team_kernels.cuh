@@ -41,7 +41,52 @@ __device__ __forceinline__ void team_bar_arrive(int id, int count) { asm volatil
 __device__ __forceinline__ int coord_class(int v, int period) { return v == 0 ? 0 : (v == period - 1 ? 3 : 1 + (v & 1)); }
 __device__ __forceinline__ int class_representative(int c, int period) { return c == 0 ? 0 : (c == 3 ? period - 1 : 1 + c); }
 
-template <int G, bool kInstrumented>
+// exp(x) for the selector's dependent chain: k = round(x / ln 2), r = x - k ln 2 (two-constant Cody-Waite), a degree-13
+// Taylor polynomial in Estrin form (4 dependent FMA levels; truncation 4e-18 for |r| <= 0.347, rounding <= 2 ulp), 2^k
+// added to the exponent field.  Branch-free, about 25 instructions, 11 of them on the dependent path (the library's
+// exp: 47 and two branches).  Valid for |x| < 700 only: the caller checks the arguments once and otherwise takes the
+// library functions.
+__device__ __forceinline__ double exp_chain(double x) {
+  constexpr double kMagic = 6755399441055744.0;                        // 1.5 * 2^52: the add rounds to the nearest integer
+  const double t = fma(x, 1.4426950408889634074, kMagic);
+  const int k = __double2loint(t);
+  const double kf = t - kMagic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = fma(r, 1.0, 1.0), a1 = fma(r, 1.0 / 6.0, 0.5), a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0), a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0),
+               a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0), a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0),
+               a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+  const double p = fma(d1, r8, d0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// (Ea, rate) of a jump from the folded pair (dE, log E0): barrier_from_folded (kernels.cuh) and JumpEvent.cpp:13 as one
+// dependent chain.  The division of the quartic form, x = 16 dE / E0, becomes a second exponential that runs beside the
+// first (x = 16 dE exp(-log E0)); one range check at the end covers the three exponentials.  Agrees with
+// barrier_from_folded / exp to a few ulp.
+__device__ __forceinline__ void barrier_and_rate_chain(double dE, double log_e0, int model, double beta, double &ea_out, double &rate_out) {
+  const double e0 = exp_chain(log_e0), inv_e0 = exp_chain(-log_e0);
+  const double x = 16.0 * dE * inv_e0;
+  const double s = 3.0 * x + 4.0;
+  double ea = e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
+  if (model != 0) ea = fmax(0.0, e0 + 0.5 * dE);
+  const double arg = -ea * beta;
+  double rate = exp_chain(arg);
+  if (!(fabs(log_e0) < 700.0 && fabs(arg) < 700.0)) {          // barriers of tens of eV, NaN: the library functions
+    ea = barrier_from_folded(dE, log_e0, model);
+    rate = exp(-ea * beta);
+  }
+  ea_out = ea;
+  rate_out = rate;
+}
+
+// kSmemOcc: the walker's whole (padded) occupancy lives in shared memory for the launch -- small cells only (the 8 x 8 x 8
+// cell of the batched workload is 5.8 KB).  The gather then never leaves the SM (shared-memory latency instead of L1 hits
+// plus two L2 round trips for the lines the previous jump has just written); the selector writes each jump to both copies.
+template <int G, bool kInstrumented, bool kSmemOcc>
 __global__ void __launch_bounds__(12 * G + 32, G == 8 ? 7 : (G == 16 ? 3 : 1))     // resident blocks per SM the dispatch counts on
 kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                     int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
@@ -51,7 +96,7 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   constexpr int kBarA = 1, kBarB = 2;
   constexpr unsigned full = 0xFFFFFFFFu;
   __shared__ int32_t s_delta[24 * kPairDeltaStride + 4];
-  extern __shared__ double s_A2[];                // [n][58][n][2]: (dE, log E0) singlet terms
+  extern __shared__ double s_A2[];                // [n][58][n][2]: (dE, log E0) singlet terms; kSmemOcc: followed by the occupancy
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
   __shared__ uint8_t s_codes[12][64];             // species by env index, per candidate jump (non-solvent sites only)
@@ -86,6 +131,11 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   const int w = blockIdx.x;
   if (w >= n_walkers || st.error[w] != 0 || st.vacancy[w] < 0) return;     // uniform over the block
   uint8_t *o = occ + w * walker_stride;
+  uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_A2 + tab.n_species * kEnvN * tab.n_species * 2);
+  if (kSmemOcc) {
+    for (int q = threadIdx.x; q < static_cast<int>(lat.padded_size); q += blockDim.x) s_occ[q] = o[q];
+    __syncthreads();
+  }
   int X, Y, Z;
   lat.coords_of_id(st.vacancy[w], X, Y, Z);
   const unsigned solvent = static_cast<unsigned>(tab.solvent), vac_code = static_cast<unsigned>(tab.n_species);
@@ -116,7 +166,8 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
 #pragma unroll
       for (int j = 0; j < NJ; ++j) {
         const int t = sub + G * j;
-        c[j] = t < 60 ? static_cast<unsigned>(o[base + drow[t]]) : solvent;
+        if (kSmemOcc) c[j] = t < 60 ? static_cast<unsigned>(s_occ[static_cast<int>(base) + drow[t]]) : solvent;
+        else c[j] = t < 60 ? static_cast<unsigned>(o[base + drow[t]]) : solvent;
       }
       // ---- event order (KineticMcFirstOmp.cpp:52-68): slot = rank of this jump's neighbour id among the 12 neighbour ids,
       // a function of the vacancy's boundary / parity class only (table built at block start)
@@ -275,54 +326,54 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
     LMC_TEAM_TICK(1);                              // wait for the events (the flag load cannot pass the barrier)
     // CalculateTime + SelectEvent (KineticMcFirstOmp.cpp:55-77, KineticMcAbstract.cpp:106-116): lane q < 12 owns slot q
     const double my_de = s_de[ql];
-    const double my_ea = barrier_from_folded(my_de, s_le[ql], barrier_model);      // 12 closed forms in one instruction stream
+    double my_ea, rate;                            // 12 closed forms and rates in one instruction stream (lanes >= 12 shadow slot 0)
+    barrier_and_rate_chain(my_de, s_le[ql], barrier_model, beta, my_ea, rate);
     const int my_dir = s_dir[ql];
     const unsigned my_mig = s_mig[ql];
-    const double rate = lane < 12 ? exp(-my_ea * beta) : 0.0;            // JumpEvent.cpp:13
     // the neighbour site of the jump in slot q, while the exponential is in flight
     const int xs = __shfl_sync(full, xq, my_dir), ys = __shfl_sync(full, yq, my_dir), zs = __shfl_sync(full, zq, my_dir);
     if (lane < 12) s_p[lane] = rate;
     __syncwarp(full);
     LMC_TEAM_TICK(4);                              // rates
     const double2 *p2 = reinterpret_cast<const double2 *>(s_p);
-    double total = 0.0;                            // sequential, in slot order
-    {
-      double2 r[6];
+    double r_ord[12];                              // the 12 rates in slot order
 #pragma unroll
-      for (int q = 0; q < 6; ++q) r[q] = p2[q];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) { total += r[q].x; total += r[q].y; }
+    for (int q = 0; q < 6; ++q) { const double2 v = p2[q]; r_ord[2 * q] = v.x; r_ord[2 * q + 1] = v.y; }
+    // one-pass select (select_event_fast, kmc_kernels.cuh): the same slot as the reference's total / division / running sum
+    // unless u2 lies within rounding distance of a boundary -- then (and only then) the sequential form runs
+    bool below;
+    double total = 0.0;
+    bool have_total = false;
+    const bool sure = select_event_fast<0>(r_ord, lane, u2, prm.select_margin, below);
+    const unsigned unsure = __ballot_sync(full, lane < 12 && !sure);           // the two votes go out back to back
+    unsigned hit = __ballot_sync(full, lane < 12 && !below) & 0xFFFu;
+    if (unsure) {
+      below = select_event_sequential(s_p, lane, lane < 12, u2, &total);
+      have_total = true;
+      hit = __ballot_sync(full, lane < 12 && !below) & 0xFFFu;
     }
-    __syncwarp(full);
-    LMC_TEAM_TICK(5);                              // total
-    if (lane < 12) s_p[lane] = rate / total;
-    __syncwarp(full);
-    LMC_TEAM_TICK(6);                              // division
-    double my_cumulative = 0.0;                    // ((p0 + p1) + p2) + ... + p_lane   (+ 0.0 beyond the lane's slot: exact)
-    {
-      double2 r[6];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) r[q] = p2[q];
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        my_cumulative += 2 * q <= lane ? r[q].x : 0.0;
-        my_cumulative += 2 * q + 1 <= lane ? r[q].y : 0.0;
-      }
-    }
-    LMC_TEAM_TICK(7);                              // running sum
-    const unsigned hit = __ballot_sync(full, lane < 12 && !(my_cumulative < u2)) & 0xFFFu;
+    LMC_TEAM_TICK(7);                              // select
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
     const unsigned sel_mig = __shfl_sync(full, my_mig, sel_slot);
     const int nx = __shfl_sync(full, xs, sel_slot), ny = __shfl_sync(full, ys, sel_slot), nz = __shfl_sync(full, zs, sel_slot);
     // Config::LatticeJump: lanes 0-7 write the images of the old vacancy site, lanes 8-15 those of the new one
-    if (lane < 16)
+    if (lane < 16) {
+      if (kSmemOcc) store_site_image(lat, s_occ, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7, static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
       store_site_image(lat, o, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7, static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
+    }
     if (lane == 0) { s_sel_x = nx; s_sel_y = ny; s_sel_z = nz; }
     __syncwarp(full);
     team_bar_arrive(kBarB, kThreads);              // ---- the jump is visible: the event threads start the next step
     LMC_TEAM_TICK(2);                              // select + jump
     const double sel_de = __shfl_sync(full, my_de, sel_slot), sel_ea = __shfl_sync(full, my_ea, sel_slot);
-    // ---- off the critical path: residence time, clock, energy, trace
+    // ---- off the critical path: total rate in slot order (sequential, KineticMcFirstOmp.cpp:55-77), residence time, clock, energy, trace
+    if (!have_total) {                             // s_p still holds the rates (re-read: nothing stays live across the select)
+      double2 v[6];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) v[q] = p2[q];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) { total += v[q].x; total += v[q].y; }
+    }
     const double dt = __dmul_rn(neg_log_u1 / total, corr_over_prefactor);
     if (kInstrumented && tracing && lane == 0) {
       const int64_t at = static_cast<int64_t>(w) * n_steps + s;
@@ -343,8 +394,8 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   }
 #ifdef LMC_KMC_TEAM_PROFILE
   if (blockIdx.x == 0 && lane == 0)
-    printf("team profile G=%d selector, cycles per step: preparation %lld wait for events %lld rates %lld total %lld division %lld running sum %lld pick + jump %lld clock %lld\n", G, prof[0] / n_steps,
-           prof[1] / n_steps, prof[4] / n_steps, prof[5] / n_steps, prof[6] / n_steps, prof[7] / n_steps, prof[2] / n_steps, prof[3] / n_steps);
+    printf("team profile G=%d selector, cycles per step: preparation %lld wait for events %lld rates %lld select %lld pick + jump %lld clock %lld\n", G, prof[0] / n_steps,
+           prof[1] / n_steps, prof[4] / n_steps, prof[7] / n_steps, prof[2] / n_steps, prof[3] / n_steps);
 #endif
   if (lane == 0) {
     const int err = *static_cast<volatile int *>(&s_err);

@@ -262,3 +262,32 @@ def test_latency_kernel_walks_the_throughput_kernels_trajectories(golden, tmp_pa
         assert np.max(np.abs(t0["Ea"] - t1["Ea"])) < 1e-12 and np.max(np.abs(t0["dE"] - t1["dE"])) < 1e-12
         assert np.allclose(s0["time"], s1["time"], rtol=1e-12, atol=0)
         assert np.max(np.abs(s0["energy"] - s1["energy"])) < 1e-10
+
+
+def test_one_pass_select_equals_the_sequential_select(golden, tmp_path, monkeypatch):
+    """select_event_fast (one pass over the 12 rates, guarded by a rounding margin) must pick the slot the reference's
+    total / division / running-sum form picks: LMC_KMC_SELECT_MARGIN=2 sends every step through the sequential form
+    (select_event_sequential); trajectories, clocks and energies must be bit-identical on every launch shape."""
+    e = _engine(golden, "B", tmp_path, n_walkers=40)
+    occ = golden["B_occ"]
+    temps = np.linspace(420.0, 580.0, 40)
+
+    def run(margin):
+        if margin is None:
+            monkeypatch.delenv("LMC_KMC_SELECT_MARGIN", raising=False)
+        else:
+            monkeypatch.setenv("LMC_KMC_SELECT_MARGIN", margin)
+        for w in range(40):
+            e.set_occupancy(occ, walker=w)
+        e.kmc_reset()
+        tr = e.kmc_run(400, temperatures=temps, seed=77, trace=True)
+        e.kmc_run(333, temperatures=temps, seed=77)
+        return e.kmc_state(), e.get_occupancy_all(), tr
+
+    s0, o0, t0 = run(None)
+    s1, o1, t1 = run("2")
+    assert np.array_equal(o0, o1)
+    for key in ("vacancy", "steps", "time", "energy"):
+        assert np.array_equal(s0[key], s1[key]), key
+    for key in ("from", "to", "slot", "dt", "Ea", "dE", "total_rate"):
+        assert np.array_equal(t0[key], t1[key]), key
