@@ -888,7 +888,13 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   KmcState st{d_kmc_vacancy, d_kmc_time, d_kmc_energy, d_kmc_steps, d_kmc_temperature, d_kmc_cvac, d_kmc_csol, d_kmc_error, d_kmc_previous};
   // LMC_KMC_SELECT_MARGIN (tests; read at every launch): a value > 1 sends every first-order step through the sequential select
   const double select_margin = std::getenv("LMC_KMC_SELECT_MARGIN") ? std::atof(std::getenv("LMC_KMC_SELECT_MARGIN")) : kSelectMargin;
-  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, std::max(select_margin, kSelectMargin)};
+  // LMC_KMC_FINISH_TIMES=1 (diagnostics): when each walker's half-warp left kmc_run_kernel, as deciles of the launch
+  unsigned long long *d_finish = nullptr;
+  if (std::getenv("LMC_KMC_FINISH_TIMES") && !second_order) {
+    LMC_CUDA(cudaMalloc(&d_finish, nw * 8));
+    LMC_CUDA(cudaMemsetAsync(d_finish, 0, nw * 8, stream));
+  }
+  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, d_finish, std::max(select_margin, kSelectMargin)};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
   if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the KMC driver orders events by 32-bit lattice ids (num_sites < 2^31)");
@@ -922,6 +928,21 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   std::vector<int32_t> err(nw);
   LMC_CUDA(cudaMemcpyAsync(err.data(), d_kmc_error, nw * 4, cudaMemcpyDeviceToHost, stream));
   LMC_CUDA(cudaStreamSynchronize(stream));
+  if (d_finish) {
+    std::vector<unsigned long long> fin(nw);
+    LMC_CUDA(cudaMemcpy(fin.data(), d_finish, nw * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_finish);
+    std::vector<unsigned long long> t;
+    for (unsigned long long v : fin) if (v) t.push_back(v);
+    if (!t.empty()) {
+      std::sort(t.begin(), t.end());
+      const double kernel_ns = last_kernel_ms() * 1e6;      // the last walker leaves at the end of the kernel
+      std::fprintf(stderr, "kmc finish times (%zu walkers, kernel %.3f ms), fraction of the kernel time at which the given fraction of walkers had finished:", t.size(), kernel_ns * 1e-6);
+      for (double q : {0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.98, 0.99, 0.995, 0.999})
+        std::fprintf(stderr, " q%.3g=%.3f", q, 1.0 - static_cast<double>(t.back() - t[static_cast<size_t>(q * (t.size() - 1))]) / kernel_ns);
+      std::fprintf(stderr, "\n");
+    }
+  }
   for (size_t w = 0; w < nw; ++w)
     if (err[w]) {
       kmc_ready = false;

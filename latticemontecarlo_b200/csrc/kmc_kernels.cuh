@@ -39,6 +39,7 @@ struct KmcParams {
   const double *tt_time, *tt_temp;
   int32_t rate_corrector;
   uint64_t seed;
+  unsigned long long *finish_ns;   // diagnostics (LMC_KMC_FINISH_TIMES=1): %globaltimer when a walker's half-warp leaves kmc_run_kernel; else null
   double select_margin;      // latency kernel: rounding margin of its one-pass event selection (select_event_fast); > 1 = always the sequential form
 };
 
@@ -504,6 +505,11 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
       X = nx; Y = ny; Z = nz;
     }
     __syncwarp(hmask);
+  }
+  if (prm.finish_ns && lane == 0 && w_raw < n_walkers) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    prm.finish_ns[w] = now;
   }
   if (lane == 0 && w_raw < n_walkers && (alive || err == 0) && st.error[w] == 0) {
     st.vacancy[w] = lat.id_of_coords(X, Y, Z);

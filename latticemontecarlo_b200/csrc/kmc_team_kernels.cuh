@@ -103,8 +103,8 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   __shared__ double s_de[12], s_le[12];           // (dE, log E0) in event (slot) order
   __shared__ __align__(16) double s_p[12];
   __shared__ uint8_t s_dir[12], s_mig[12];
-  __shared__ int s_sel_x, s_sel_y, s_sel_z;       // the new vacancy site
-  __shared__ int s_err, s_stop;
+  __shared__ __align__(16) int s_sel[4];          // the new vacancy site (x, y, z) and the stop flag: one 16-byte load per event thread
+  __shared__ int s_err;
   // The event order of the 12 jumps (ascending lattice id of the neighbour) depends on the vacancy site only through, per
   // axis, whether a neighbour wraps around the period (coordinate 0 or period - 1) and the coordinate's parity: 4 classes
   // per axis.  Slot of jump k for every class, ranked once per block on a representative site of the class.
@@ -112,7 +112,7 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
-  if (threadIdx.x == 0) { s_err = 0; s_stop = 0; }
+  if (threadIdx.x == 0) s_err = 0;
   {
     const int px_ = 2 * lat.fx, py_ = 2 * lat.fy, pz_ = 2 * lat.fz;
     for (int q = threadIdx.x; q < 64 * 12; q += blockDim.x) {
@@ -142,11 +142,14 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   const int n = tab.n_species;
   const int px = 2 * lat.fx, py = 2 * lat.fy, pz = 2 * lat.fz;
   const int lane = threadIdx.x & 31;
+  // (Rotating the roles over the warps of a block from walker to walker, so that the selector warps of an SM do not all
+  // sit at the same warp index, was measured at 7 walkers per SM: 2.771 vs 2.774 us per step -- no effect, not kept.)
+  const int vtid = static_cast<int>(threadIdx.x);
 
-  if (threadIdx.x < kEventThreads) {
+  if (vtid < kEventThreads) {
     // ================================================================================================ event threads
-    const int k = threadIdx.x / G;                   // candidate jump (first-neighbour direction) of this lane group
-    const int sub = threadIdx.x % G;
+    const int k = vtid / G;                          // candidate jump (first-neighbour direction) of this lane group
+    const int sub = vtid % G;
     const int gshift = lane & ~(G - 1);              // position of the group inside its warp
     const unsigned gmask = G == 32 ? full : ((1u << G) - 1u);
     const double2 *__restrict__ B_all = reinterpret_cast<const double2 *>(tab.pair_B2);
@@ -259,12 +262,13 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
       LMC_TEAM_TICK(3);                              // filing
       team_bar_arrive(kBarA, kThreads);              // the 12 events of this step are filed
       team_bar_sync(kBarB, kThreads);                // the selector has jumped (or stopped the walker)
-      if (*static_cast<volatile int *>(&s_stop)) break;
-      LMC_TEAM_TICK(4);                              // wait for the selector (the flag load cannot pass the barrier)
-      X = s_sel_x; Y = s_sel_y; Z = s_sel_z;
+      const int4 sel = *reinterpret_cast<const int4 *>(s_sel);   // after the barrier (a memory clobber): re-read every step
+      if (sel.w) break;
+      LMC_TEAM_TICK(4);                              // wait for the selector (the load cannot pass the barrier)
+      X = sel.x; Y = sel.y; Z = sel.z;
     }
 #ifdef LMC_KMC_TEAM_PROFILE
-    if (blockIdx.x == 0 && threadIdx.x == 0)
+    if (blockIdx.x == 0 && vtid == 0)
       printf("team profile G=%d event thread 0, cycles per step: gather %lld walk %lld tree %lld closed form %lld wait for selector %lld\n", G,
              prof[0] / n_steps, prof[1] / n_steps, prof[2] / n_steps, prof[3] / n_steps, prof[4] / n_steps);
 #endif
@@ -316,14 +320,10 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
     const int xq = wrap_coord(X + dxl, px), yq = wrap_coord(Y + dyl, py), zq = wrap_coord(Z + dzl, pz);   // lane q < 12: the neighbour in direction q
     LMC_TEAM_TICK(0);                              // preparation
     team_bar_sync(kBarA, kThreads);                // ---- the 12 (Ea, dE) of this step are in shared memory, in event order
-    if (*static_cast<volatile int *>(&s_err) != 0) {
-      failed = true;                               // the walker stops; its state is left as it was before this step
-      if (lane == 0) s_stop = 1;
-      __syncwarp(full);
-      team_bar_arrive(kBarB, kThreads);
-      break;
-    }
-    LMC_TEAM_TICK(1);                              // wait for the events (the flag load cannot pass the barrier)
+    // an event group that found an error has filed nothing (its slot holds the previous step's pair): the flag is loaded
+    // here and looked at just before the jump is written, so that the load does not sit in front of the rate chain
+    const int step_err = *static_cast<volatile int *>(&s_err);
+    LMC_TEAM_TICK(1);                              // wait for the events
     // CalculateTime + SelectEvent (KineticMcFirstOmp.cpp:55-77, KineticMcAbstract.cpp:106-116): lane q < 12 owns slot q
     const double my_de = s_de[ql];
     double my_ea, rate;                            // 12 closed forms and rates in one instruction stream (lanes >= 12 shadow slot 0)
@@ -353,6 +353,13 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
       hit = __ballot_sync(full, lane < 12 && !below) & 0xFFFu;
     }
     LMC_TEAM_TICK(7);                              // select
+    if (step_err != 0) {
+      failed = true;                               // the walker stops; its state is left as it was before this step
+      if (lane == 0) *reinterpret_cast<int4 *>(s_sel) = make_int4(X, Y, Z, 1);
+      __syncwarp(full);
+      team_bar_arrive(kBarB, kThreads);
+      break;
+    }
     const int sel_slot = hit ? (__ffs(static_cast<int>(hit)) - 1) : 11;
     const unsigned sel_mig = __shfl_sync(full, my_mig, sel_slot);
     const int nx = __shfl_sync(full, xs, sel_slot), ny = __shfl_sync(full, ys, sel_slot), nz = __shfl_sync(full, zs, sel_slot);
@@ -361,7 +368,7 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
       if (kSmemOcc) store_site_image(lat, s_occ, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7, static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
       store_site_image(lat, o, lane < 8 ? X : nx, lane < 8 ? Y : ny, lane < 8 ? Z : nz, lane & 7, static_cast<uint8_t>(lane < 8 ? sel_mig : vac_code));
     }
-    if (lane == 0) { s_sel_x = nx; s_sel_y = ny; s_sel_z = nz; }
+    if (lane == 0) *reinterpret_cast<int4 *>(s_sel) = make_int4(nx, ny, nz, 0);
     __syncwarp(full);
     team_bar_arrive(kBarB, kThreads);              // ---- the jump is visible: the event threads start the next step
     LMC_TEAM_TICK(2);                              // select + jump
