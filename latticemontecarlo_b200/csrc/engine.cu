@@ -352,7 +352,14 @@ void Engine::load_coefficients(const Coefficients &co, int model) {
   has_coefficients = true;
   if (device >= 0) {
     cudaSetDevice(device);
-    auto fold = [](const std::vector<double> &v) {      // [..][3] = (dE, logD, logKs)  ->  [..][2] = (dE, logKs + 2 logD)
+    // [..][3] = (dE, logD, logKs)  ->  [..][2] = (dE, logKs + 2 logD) for the KMC kernels.  The folded tables are put on a
+    // common binary grid: every entry is rounded to a multiple of 2^-q, q per component chosen so that the largest
+    // possible sum |C| + sum_t max|A_t| + sum_pairs max|B| stays below 2^(51-q).  Then every partial sum any kernel can
+    // form is a multiple of 2^-q below 2^52 of them, i.e. EXACT in double: the contracted sums do not depend on the
+    // order of the additions, and the launch shapes of the KMC driver (half-warp per walker: sequential; block per walker:
+    // tree over lanes) deliver bit-identical (dE, log E0).  Cost: <= 2^-(q+1) per entry (q = 44..48 for eV-sized
+    // coefficients: ~1e-14 eV), against a parity tolerance of 1e-9 eV.
+    auto fold = [](const std::vector<double> &v) {
       std::vector<double> out(v.size() / 3 * 2);
       for (size_t i = 0; i < v.size() / 3; ++i) {
         out[2 * i] = v[3 * i];
@@ -360,9 +367,37 @@ void Engine::load_coefficients(const Coefficients &co, int model) {
       }
       return out;
     };
-    tab.pair_C2 = to_device(fold(pair_tables.C));
-    tab.pair_A2 = to_device(fold(pair_tables.A));
-    tab.pair_B2 = to_device(fold(pair_tables.B));
+    std::vector<double> C2 = fold(pair_tables.C), A2 = fold(pair_tables.A), B2 = fold(pair_tables.B);
+    {
+      const size_t n = static_cast<size_t>(species.n), n_pairs = static_cast<size_t>(tab.n_pair_pairs);
+      for (int c = 0; c < 2; ++c) {
+        double bound = 0.0;
+        for (size_t m = 0; m < n; ++m) {
+          double b = std::fabs(C2[m * 2 + c]);
+          for (size_t t = 0; t < static_cast<size_t>(kEnvN); ++t) {
+            double mx = 0.0;
+            for (size_t e = 0; e < n; ++e) mx = std::max(mx, std::fabs(A2[((m * kEnvN + t) * n + e) * 2 + c]));
+            b += mx;
+          }
+          for (size_t pq = 0; pq < n_pairs; ++pq) {
+            double mx = 0.0;
+            for (size_t e = 0; e < n * n; ++e) mx = std::max(mx, std::fabs(B2[((m * n_pairs + pq) * n * n + e) * 2 + c]));
+            b += mx;
+          }
+          bound = std::max(bound, b);
+        }
+        int exp2 = 0;
+        std::frexp(std::max(bound, 1e-300), &exp2);            // bound < 2^exp2
+        const int q = std::min(60, 51 - exp2);
+        pair_grid_bits[c] = q;
+        const double up = std::ldexp(1.0, q), down = std::ldexp(1.0, -q);
+        for (std::vector<double> *tabv : {&C2, &A2, &B2})
+          for (size_t i = static_cast<size_t>(c); i < tabv->size(); i += 2) (*tabv)[i] = std::nearbyint((*tabv)[i] * up) * down;
+      }
+    }
+    tab.pair_C2 = to_device(C2);
+    tab.pair_A2 = to_device(A2);
+    tab.pair_B2 = to_device(B2);
     tab.pair_C = to_device(pair_tables.C);
     tab.pair_A = to_device(pair_tables.A);
     tab.pair_B = to_device(pair_tables.B);
