@@ -327,6 +327,10 @@ class Engine:
         """0: half-warp-per-walker kernel; 8 / 16 / 32: block-per-walker latency kernel with that many lanes per jump."""
         return int(lib().lmc_kmc_last_launch_lanes(self.h))
 
+    def kmc_last_launch_handoff(self):
+        """True if the last first-order launch ran the half-warp kernel and handed its tail to the latency kernel."""
+        return bool(lib().lmc_kmc_last_launch_handoff(self.h))
+
     def kmc_last_launch_resident_occupancy(self):
         """True if the last first-order launch was a latency-kernel launch with the walkers' occupancy in shared memory."""
         return bool(lib().lmc_kmc_last_launch_resident_occupancy(self.h))

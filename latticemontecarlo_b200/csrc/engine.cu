@@ -789,6 +789,10 @@ void Engine::debug_site(int32_t walker, int64_t site, int32_t new_element, int64
 }
 
 // ------------------------------------------------------------------------------------------------ KMC driver
+__global__ void kmc_target_kernel(const int64_t *__restrict__ steps, int64_t *__restrict__ target, int n, int64_t n_steps) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n) target[w] = steps[w] + n_steps;
+}
 namespace {
 template <class T>
 T *dev_alloc(size_t n) {
@@ -807,6 +811,8 @@ void Engine::kmc_reset() {
     d_kmc_time = dev_alloc<double>(n); d_kmc_energy = dev_alloc<double>(n); d_kmc_temperature = dev_alloc<double>(n);
     d_kmc_cvac = dev_alloc<double>(n); d_kmc_csol = dev_alloc<double>(n); d_kmc_error = dev_alloc<int32_t>(n);
     d_kmc_previous = dev_alloc<int64_t>(n);
+    d_kmc_target = dev_alloc<int64_t>(n); d_kmc_done = dev_alloc<int>(1);
+    device_allocs.push_back(d_kmc_target); device_allocs.push_back(d_kmc_done);
     for (void *p : {static_cast<void *>(d_kmc_vacancy), static_cast<void *>(d_kmc_steps), static_cast<void *>(d_kmc_time),
                     static_cast<void *>(d_kmc_energy), static_cast<void *>(d_kmc_temperature), static_cast<void *>(d_kmc_cvac),
                     static_cast<void *>(d_kmc_csol), static_cast<void *>(d_kmc_error), static_cast<void *>(d_kmc_previous)})
@@ -827,8 +833,9 @@ void Engine::kmc_reset() {
 // The launch shape of a first-order KMC run.  A block per walker with 8 / 16 / 32 lanes per candidate jump is used when
 // every walker's block is resident at once (a second wave would double the run time) -- the widest group that fits;
 // thousands of walkers go to the half-warp kernel.  LMC_KMC_TEAM_LANES = 0 / 8 / 16 / 32 overrides the choice (A/B runs).
-const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out) {
-  const int forced = std::getenv("LMC_KMC_TEAM_LANES") ? std::atoi(std::getenv("LMC_KMC_TEAM_LANES")) : -1;
+const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out, bool for_tail) {
+  // for_tail: the 8-lane instantiation for the tail of a hybrid launch (any number of blocks; most leave at once)
+  const int forced = for_tail ? 8 : (std::getenv("LMC_KMC_TEAM_LANES") ? std::atoi(std::getenv("LMC_KMC_TEAM_LANES")) : -1);
   const int max_per_sm = std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM") ? std::atoi(std::getenv("LMC_KMC_TEAM_WALKERS_PER_SM")) : 7;
   if (forced == 0) return nullptr;
   // small cells: the walker's occupancy resident in shared memory (LMC_KMC_TEAM_SMEM=0 switches it off for A/B runs)
@@ -862,7 +869,7 @@ const void *Engine::kmc_team_kernel_choice(bool instrumented, size_t table_smem,
       int per_sm = 0;
       LMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 12 * lanes + 32, smem));
       const int64_t resident = static_cast<int64_t>(per_sm) * sms;
-      if (per_sm > 0 && ((forced > 0 && (n_walkers <= resident || !resident_occ)) || (n_walkers <= resident && n_walkers <= per_sm_limit * sms))) {
+      if (per_sm > 0 && ((forced > 0 && (n_walkers <= resident || !resident_occ || (for_tail && per_sm >= 7))) || (n_walkers <= resident && n_walkers <= per_sm_limit * sms))) {
         *lanes_out = lanes;
         *smem_out = smem;
         kmc_team_resident_occ = resident_occ != 0;
@@ -929,7 +936,8 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     LMC_CUDA(cudaMalloc(&d_finish, nw * 8));
     LMC_CUDA(cudaMemsetAsync(d_finish, 0, nw * 8, stream));
   }
-  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, d_finish, std::max(select_margin, kSelectMargin)};
+  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, nullptr, 0, nullptr, d_finish,
+                std::max(select_margin, kSelectMargin)};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
   if (lat.num_sites >= (1LL << 31)) throw std::invalid_argument("the KMC driver orders events by 32-bit lattice ids (num_sites < 2^31)");
@@ -947,8 +955,35 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     LMC_CUDA(cudaLaunchKernel(team, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * kmc_team_lanes + 32)), args, team_smem, stream));
   } else {
     kmc_team_lanes = 0;
+    // Tail hand-off.  A launch of thousands of walkers lasts as long as its most expensive walker (the first half-warp
+    // is through at ~0.4 of the kernel time, the median at 0.7: profiles/r2_m_kmc_finish_times.txt).  Once all but
+    // `keep` walkers are through, the half-warps still running stop at a 16-step boundary and the latency kernel takes
+    // each of those walkers from where it stopped to its target -- a block per walker runs such a step 2-3 x faster.
+    // Every launch shape computes bit-identical (dE, log E0, rate) (tables on a binary grid, one rate chain), so the
+    // result does not depend on when the hand-off happens.  LMC_KMC_HANDOFF=0 switches it off, a value in (0, 1) sets
+    // the fraction of the walkers handed over.
+    double keep_fraction = 0.2;
+    if (const char *v = std::getenv("LMC_KMC_HANDOFF")) keep_fraction = std::atof(v);
+    const bool handoff = !instrumented && keep_fraction > 0.0 && keep_fraction < 1.0 && n_walkers >= 2048 && n_steps >= 128;
+    kmc_handoff = handoff;
+    if (handoff) {
+      kmc_target_kernel<<<static_cast<unsigned>((n_walkers + 255) / 256), 256, 0, stream>>>(d_kmc_steps, d_kmc_target, n_walkers, n_steps);
+      LMC_CUDA(cudaMemsetAsync(d_kmc_done, 0, sizeof(int), stream));
+      prm.handoff_done = d_kmc_done;
+      prm.handoff_threshold = n_walkers - std::max(1, static_cast<int>(keep_fraction * n_walkers));
+    }
     if (instrumented) kmc_run_kernel<true><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
     else kmc_run_kernel<false><<<blocks, kKmcThreads, 0, stream>>>(lat, tab, d_occ, lat.padded_size, n_walkers, st, prm, n_steps, d_u1, d_u2, tr);
+    if (handoff) {
+      LMC_CUDA(cudaGetLastError());
+      int lanes = 0;
+      const void *tail = kmc_team_kernel_choice(false, kmc_smem, &lanes, &team_smem, true);
+      prm.handoff_done = nullptr;
+      prm.steps_target = d_kmc_target;
+      void *args[] = {&lat, &tab, &d_occ, const_cast<int64_t *>(&lat.padded_size), &n_walkers, &st, &prm, &n_steps, &d_u1, &d_u2, &tr};
+      LMC_CUDA(cudaLaunchKernel(tail, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * lanes + 32)), args, team_smem, stream));
+      ++launch_count;
+    }
   }
   time_end();
   LMC_CUDA(cudaGetLastError());
@@ -1874,6 +1909,7 @@ double lmc_engine_last_kernel_ms(lmc_engine *engine) {
 }
 int64_t lmc_engine_launch_count(const lmc_engine *engine) { return engine ? engine->impl->launch_count : 0; }
 int lmc_kmc_last_launch_lanes(const lmc_engine *engine) { return engine ? engine->impl->kmc_team_lanes : 0; }
+int lmc_kmc_last_launch_handoff(const lmc_engine *engine) { return engine && engine->impl->kmc_team_lanes == 0 && engine->impl->kmc_handoff ? 1 : 0; }
 int lmc_kmc_last_launch_resident_occupancy(const lmc_engine *engine) {
   return engine && engine->impl->kmc_team_lanes > 0 && engine->impl->kmc_team_resident_occ ? 1 : 0;
 }

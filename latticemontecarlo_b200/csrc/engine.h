@@ -130,7 +130,10 @@ class Engine {
   int kmc_team_lanes{0};       // lanes per candidate jump of the last first-order KMC launch (0: half-warp kernel)
   int pair_grid_bits[2]{0, 0};         // the folded KMC tables are multiples of 2^-bits (dE, log E0): exact sums in any order
   bool kmc_team_resident_occ{false};   // ... and whether that launch kept the walkers' occupancy in shared memory
-  const void *kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out);
+  bool kmc_handoff{false};             // the last half-warp launch handed its tail to the latency kernel
+  int64_t *d_kmc_target{nullptr};      // hybrid launch: the step number every walker has to reach
+  int *d_kmc_done{nullptr};            // hybrid launch: walkers that are through
+  const void *kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out, bool for_tail = false);
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};
   unsigned long long *d_cmc_steps{nullptr}, *d_cmc_accepted{nullptr}, *d_cmc_proposals{nullptr}, *d_cmc_epoch{nullptr};

@@ -39,6 +39,12 @@ struct KmcParams {
   const double *tt_time, *tt_temp;
   int32_t rate_corrector;
   uint64_t seed;
+  // Tail hand-off (Engine::kmc_run): kmc_run_kernel counts the walkers that have done all their steps in *handoff_done
+  // and, once handoff_threshold of them are through, the half-warps still running stop at the next 16-step boundary and
+  // save their state; kmc_team_run_kernel then takes every walker from st.steps[w] to steps_target[w].  All null / 0 = off.
+  int *handoff_done;
+  int32_t handoff_threshold;
+  const int64_t *steps_target;
   unsigned long long *finish_ns;   // diagnostics (LMC_KMC_FINISH_TIMES=1): %globaltimer when a walker's half-warp leaves kmc_run_kernel; else null
   double select_margin;      // latency kernel: rounding margin of its one-pass event selection (select_event_fast); > 1 = always the sequential form
 };
@@ -89,6 +95,49 @@ __device__ __noinline__ bool select_event_sequential(double *rates, int lane, bo
   __syncwarp(0xFFFFFFFFu);
   *total_out = total;
   return cumulative < u2;
+}
+
+// exp(x) for the dependent chain of a KMC step (all first- and second-order KMC kernels use it, so that every launch
+// shape computes bit-identical rates): k = round(x / ln 2), r = x - k ln 2 (two-constant Cody-Waite), a degree-13
+// Taylor polynomial in Estrin form (4 dependent FMA levels; truncation 4e-18 for |r| <= 0.347, rounding <= 2 ulp), 2^k
+// added to the exponent field.  Branch-free, about 25 instructions, 11 of them on the dependent path (the library's
+// exp: 47 and two branches).  Valid for |x| < 700 only: the caller checks the arguments once and otherwise takes the
+// library functions.
+__device__ __forceinline__ double exp_chain(double x) {
+  constexpr double kMagic = 6755399441055744.0;                        // 1.5 * 2^52: the add rounds to the nearest integer
+  const double t = fma(x, 1.4426950408889634074, kMagic);
+  const int k = __double2loint(t);
+  const double kf = t - kMagic;
+  double r = fma(kf, -6.93147180369123816490e-01, x);
+  r = fma(kf, -1.90821492927058770002e-10, r);
+  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+  const double a0 = fma(r, 1.0, 1.0), a1 = fma(r, 1.0 / 6.0, 0.5), a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0), a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0),
+               a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0), a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0),
+               a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
+  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+  const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+  const double p = fma(d1, r8, d0);
+  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
+// (Ea, rate) of a jump from the folded pair (dE, log E0): barrier_from_folded (kernels.cuh) and JumpEvent.cpp:13 as one
+// dependent chain.  The division of the quartic form, x = 16 dE / E0, becomes a second exponential that runs beside the
+// first (x = 16 dE exp(-log E0)); one range check at the end covers the three exponentials.  Agrees with
+// barrier_from_folded / exp to a few ulp.
+__device__ __forceinline__ void barrier_and_rate_chain(double dE, double log_e0, int model, double beta, double &ea_out, double &rate_out) {
+  const double e0 = exp_chain(log_e0), inv_e0 = exp_chain(-log_e0);
+  const double x = 16.0 * dE * inv_e0;
+  const double s = 3.0 * x + 4.0;
+  double ea = e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
+  if (model != 0) ea = fmax(0.0, e0 + 0.5 * dE);
+  const double arg = -ea * beta;
+  double rate = exp_chain(arg);
+  if (!(fabs(log_e0) < 700.0 && fabs(arg) < 700.0)) {          // barriers of tens of eV, NaN: the library functions
+    ea = barrier_from_folded(dE, log_e0, model);
+    rate = exp(-ea * beta);
+  }
+  ea_out = ea;
+  rate_out = rate;
 }
 
 struct KmcTraceDev {         // optional per-step records, [walker][n_steps]; any pointer may be null
@@ -332,8 +381,7 @@ __device__ __forceinline__ void kmc_scan_and_evaluate(const LatticeDesc &lat, co
         if (!ok) err |= kErrExtraVacancy;
         else {
           de = a0;
-          ea = barrier_from_folded(de, a1, barrier_model);
-          rate = exp(-ea * beta);                      // JumpEvent.cpp:13
+          barrier_and_rate_chain(de, a1, barrier_model, beta, ea, rate);    // closed form + JumpEvent.cpp:13
         }
       }
     }
@@ -407,7 +455,14 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   double corr = prm.rate_corrector ? rate_correction(c_vac, c_sol, temperature) : 1.0;
   double corr_over_prefactor = corr / kPrefactorHz;     // dt = -ln(u1) / total / 1e13 * corr with one division per step
   double ahead_neg_log_u1 = 0.0, ahead_u2 = 0.0;        // lane l: -ln(u1) and u2 of step (s & ~15) + l
+  bool handed_off = false;
   for (int64_t s = 0; s < n_steps; ++s) {
+    if (prm.handoff_done && (s & 15) == 0 && s > 0) {      // one L2 read per warp and 16 steps; the value is warp-uniform
+      int through = 0;
+      if ((threadIdx.x & 31) == 0) through = *static_cast<volatile int *>(prm.handoff_done);
+      through = __shfl_sync(hmask, through, 0);
+      if (through >= prm.handoff_threshold) { handed_off = true; break; }
+    }
     // 1. UpdateTemperature (KineticMcAbstract.cpp:45-50): only a T(t) table changes the temperature during a run
     if (prm.n_tt > 0) {
       const double t_now = interpolate_temperature(prm, time);
@@ -506,6 +561,7 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
     }
     __syncwarp(hmask);
   }
+  if (prm.handoff_done && !handed_off && lane == 0 && w_raw < n_walkers) atomicAdd(prm.handoff_done, 1);   // through (or stopped by an error)
   if (prm.finish_ns && lane == 0 && w_raw < n_walkers) {
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));

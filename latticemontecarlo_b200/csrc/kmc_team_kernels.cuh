@@ -41,55 +41,20 @@ __device__ __forceinline__ void team_bar_arrive(int id, int count) { asm volatil
 __device__ __forceinline__ int coord_class(int v, int period) { return v == 0 ? 0 : (v == period - 1 ? 3 : 1 + (v & 1)); }
 __device__ __forceinline__ int class_representative(int c, int period) { return c == 0 ? 0 : (c == 3 ? period - 1 : 1 + c); }
 
-// exp(x) for the selector's dependent chain: k = round(x / ln 2), r = x - k ln 2 (two-constant Cody-Waite), a degree-13
-// Taylor polynomial in Estrin form (4 dependent FMA levels; truncation 4e-18 for |r| <= 0.347, rounding <= 2 ulp), 2^k
-// added to the exponent field.  Branch-free, about 25 instructions, 11 of them on the dependent path (the library's
-// exp: 47 and two branches).  Valid for |x| < 700 only: the caller checks the arguments once and otherwise takes the
-// library functions.
-__device__ __forceinline__ double exp_chain(double x) {
-  constexpr double kMagic = 6755399441055744.0;                        // 1.5 * 2^52: the add rounds to the nearest integer
-  const double t = fma(x, 1.4426950408889634074, kMagic);
-  const int k = __double2loint(t);
-  const double kf = t - kMagic;
-  double r = fma(kf, -6.93147180369123816490e-01, x);
-  r = fma(kf, -1.90821492927058770002e-10, r);
-  const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-  const double a0 = fma(r, 1.0, 1.0), a1 = fma(r, 1.0 / 6.0, 0.5), a2 = fma(r, 1.0 / 120.0, 1.0 / 24.0), a3 = fma(r, 1.0 / 5040.0, 1.0 / 720.0),
-               a4 = fma(r, 1.0 / 362880.0, 1.0 / 40320.0), a5 = fma(r, 1.0 / 39916800.0, 1.0 / 3628800.0),
-               a6 = fma(r, 1.0 / 6227020800.0, 1.0 / 479001600.0);
-  const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
-  const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
-  const double p = fma(d1, r8, d0);
-  return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-
-// (Ea, rate) of a jump from the folded pair (dE, log E0): barrier_from_folded (kernels.cuh) and JumpEvent.cpp:13 as one
-// dependent chain.  The division of the quartic form, x = 16 dE / E0, becomes a second exponential that runs beside the
-// first (x = 16 dE exp(-log E0)); one range check at the end covers the three exponentials.  Agrees with
-// barrier_from_folded / exp to a few ulp.
-__device__ __forceinline__ void barrier_and_rate_chain(double dE, double log_e0, int model, double beta, double &ea_out, double &rate_out) {
-  const double e0 = exp_chain(log_e0), inv_e0 = exp_chain(-log_e0);
-  const double x = 16.0 * dE * inv_e0;
-  const double s = 3.0 * x + 4.0;
-  double ea = e0 * (s * s) * (8.0 + 4.0 * x - 1.5 * (x * x)) * (1.0 / 8192.0);
-  if (model != 0) ea = fmax(0.0, e0 + 0.5 * dE);
-  const double arg = -ea * beta;
-  double rate = exp_chain(arg);
-  if (!(fabs(log_e0) < 700.0 && fabs(arg) < 700.0)) {          // barriers of tens of eV, NaN: the library functions
-    ea = barrier_from_folded(dE, log_e0, model);
-    rate = exp(-ea * beta);
-  }
-  ea_out = ea;
-  rate_out = rate;
-}
-
 // kSmemOcc: the walker's whole (padded) occupancy lives in shared memory for the launch -- small cells only (the 8 x 8 x 8
 // cell of the batched workload is 5.8 KB).  The gather then never leaves the SM (shared-memory latency instead of L1 hits
 // plus two L2 round trips for the lines the previous jump has just written); the selector writes each jump to both copies.
 template <int G, bool kInstrumented, bool kSmemOcc>
 __global__ void __launch_bounds__(12 * G + 32, G == 8 ? 7 : (G == 16 ? 3 : 1))     // resident blocks per SM the dispatch counts on
 kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
-                    int64_t n_steps, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
+                    int64_t n_steps_all, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
+  // tail of a hybrid launch (prm.steps_target): this walker's remaining steps; most blocks have none and leave at once
+  int64_t n_steps = n_steps_all;
+  if (prm.steps_target) {
+    if (static_cast<int>(blockIdx.x) >= n_walkers) return;
+    n_steps = prm.steps_target[blockIdx.x] - st.steps[blockIdx.x];
+    if (n_steps <= 0) return;
+  }
   static_assert(G == 8 || G == 16 || G == 32, "lanes per candidate jump");
   constexpr int NJ = (60 + G - 1) / G;            // gather passes: lane `sub` loads the state positions sub, sub + G, ...
   constexpr int kEventThreads = 12 * G, kThreads = kEventThreads + 32;

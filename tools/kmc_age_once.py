@@ -15,4 +15,7 @@ for _ in range(L):
     e.kmc_run(H, temperatures=sharding.walker_temperatures(0, W, W), seed=20260101)
     ms.append(e.last_kernel_ms())
 st = e.kmc_state()
-print(os.environ.get("LMC_B200_LIB", "in-tree"), " ".join("%.3f" % m for m in ms), "sum %.3f ms" % sum(ms), "vacancy xor", int((st["vacancy"] * 7919 % 1000003).sum()))
+import hashlib
+digest = hashlib.sha1(st["time"].tobytes() + st["energy"].tobytes() + st["vacancy"].tobytes() + st["steps"].tobytes()).hexdigest()[:12]
+print(os.environ.get("LMC_B200_LIB", "in-tree"), "handoff", os.environ.get("LMC_KMC_HANDOFF", "default"), " ".join("%.3f" % m for m in ms), "sum %.3f ms" % sum(ms),
+      "vacancy xor", int((st["vacancy"] * 7919 % 1000003).sum()), "state sha1", digest, "hybrid" if e.kmc_last_launch_handoff() else "plain")
