@@ -182,11 +182,12 @@ def run_reference(args):
     return 0
 
 
-def kmc_kernel_name(lanes, resident_occupancy=False):
-    """The first-order kernel the library chose: thousands of walkers -> half-warp per walker; a few per SM -> block per walker
-    (small cells: with the walker's occupancy resident in shared memory)."""
+def kmc_kernel_name(lanes, resident_occupancy=False, handoff=False):
+    """The first-order kernel the library chose: thousands of walkers -> half-warp per walker (with the tail of the launch
+    handed to the block-per-walker kernel); a few per SM -> block per walker (small cells: with the walker's occupancy
+    resident in shared memory)."""
     if lanes == 0:
-        return "kmc_run_kernel"
+        return "kmc_run_kernel + kmc_team_run_kernel<8> for the tail of the launch" if handoff else "kmc_run_kernel"
     return "kmc_team_run_kernel<%d%s>" % (lanes, ", occupancy in shared memory" if resident_occupancy else "")
 
 
@@ -273,7 +274,7 @@ def run_ours(args):
                "local_kernel_ms": sum(t[1] for t in timings), "wall": wall, "launches": launches, "clocks": sampler,
                "walkers_advanced_all_steps": int(np.count_nonzero(advanced == H * steps)), "min_steps_advanced": int(advanced.min()),
                "age_hops": [int(steps_before.min()), int(st["steps"].max())], "lanes": engine.kmc_last_launch_lanes(),
-               "resident_occupancy": engine.kmc_last_launch_resident_occupancy()}
+               "resident_occupancy": engine.kmc_last_launch_resident_occupancy(), "handoff": engine.kmc_last_launch_handoff()}
         if with_e2e:
             # ---- end to end through the C ABI with host buffers: H2D occupancy, reset, run, D2H state + occupancy
             def step_e2e():
@@ -315,11 +316,13 @@ def run_ours(args):
         "gpu_launches": int(head["launches"]),
         "walkers_advanced_all_steps": int(advanced_all), "walkers_total": W_total,
         "walker_age_hops_during_timed_region": head["age_hops"],
-        "roofline": {"kernel": kmc_kernel_name(head["lanes"], head["resident_occupancy"]), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": kmc_kernel_name(head["lanes"], head["resident_occupancy"], head["handoff"]), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H) if head["lanes"] == 0 else recorded_traffic("kmc_team_run_kernel", walkers=W, hops=H, lanes=head["lanes"]), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": int(W * H * BYTES_PER_KMC_STEP),
                      "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
-                             "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"},
+                             "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"
+                             + ("; the launch duration covers the throughput kernel, the latency kernel that finishes the walkers still "
+                                "running when 65 % were through, and the two one-block helper kernels between them" if head["handoff"] else "")},
         "wall_s_timed_region": head["wall"],
     }
     clocks = head["clocks"]
@@ -480,7 +483,7 @@ def bench_low_occupancy(device, json_path, walkers, hops):
                 eng.kmc_run(hops, temperatures=temps, seed=20260101)
                 ms.append(eng.last_kernel_ms())
             st = eng.kmc_state()
-            out[name] = {"kernel": kmc_kernel_name(eng.kmc_last_launch_lanes(), eng.kmc_last_launch_resident_occupancy()), "value": walkers * hops / (min(ms) * 1e-3), "kernel_ms": min(ms),
+            out[name] = {"kernel": kmc_kernel_name(eng.kmc_last_launch_lanes(), eng.kmc_last_launch_resident_occupancy(), eng.kmc_last_launch_handoff()), "value": walkers * hops / (min(ms) * 1e-3), "kernel_ms": min(ms),
                          "us_per_step": min(ms) * 1e3 / hops, "walkers_advanced_all_steps": int(np.count_nonzero(st["steps"] == 4 * hops)),
                          "vacancy_digest": int(np.bitwise_xor.reduce(st["vacancy"] * (np.arange(walkers) + 1)))}
     finally:
@@ -514,7 +517,7 @@ def bench_single_trajectory(device, json_path):
             ms.append(eng.last_kernel_ms())
         st = eng.kmc_state()
         out[name] = {"value": steps / (min(ms) * 1e-3), "kernel_ms": min(ms), "us_per_step": min(ms) * 1e3 / steps,
-                     "kernel": "kmc_chain_run_kernel" if second_order else kmc_kernel_name(eng.kmc_last_launch_lanes(), eng.kmc_last_launch_resident_occupancy()),
+                     "kernel": "kmc_chain_run_kernel" if second_order else kmc_kernel_name(eng.kmc_last_launch_lanes(), eng.kmc_last_launch_resident_occupancy(), eng.kmc_last_launch_handoff()),
                      "time_reached_s": float(st["time"][0]), "temperature_reached_K": float(st["temperature"][0])}
     eng.close()
     return out

@@ -811,8 +811,8 @@ void Engine::kmc_reset() {
     d_kmc_time = dev_alloc<double>(n); d_kmc_energy = dev_alloc<double>(n); d_kmc_temperature = dev_alloc<double>(n);
     d_kmc_cvac = dev_alloc<double>(n); d_kmc_csol = dev_alloc<double>(n); d_kmc_error = dev_alloc<int32_t>(n);
     d_kmc_previous = dev_alloc<int64_t>(n);
-    d_kmc_target = dev_alloc<int64_t>(n); d_kmc_done = dev_alloc<int>(1);
-    device_allocs.push_back(d_kmc_target); device_allocs.push_back(d_kmc_done);
+    d_kmc_target = dev_alloc<int64_t>(n); d_kmc_done = dev_alloc<int>(2); d_kmc_tail_order = dev_alloc<int32_t>(n);
+    device_allocs.push_back(d_kmc_target); device_allocs.push_back(d_kmc_done); device_allocs.push_back(d_kmc_tail_order);
     for (void *p : {static_cast<void *>(d_kmc_vacancy), static_cast<void *>(d_kmc_steps), static_cast<void *>(d_kmc_time),
                     static_cast<void *>(d_kmc_energy), static_cast<void *>(d_kmc_temperature), static_cast<void *>(d_kmc_cvac),
                     static_cast<void *>(d_kmc_csol), static_cast<void *>(d_kmc_error), static_cast<void *>(d_kmc_previous)})
@@ -936,7 +936,7 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     LMC_CUDA(cudaMalloc(&d_finish, nw * 8));
     LMC_CUDA(cudaMemsetAsync(d_finish, 0, nw * 8, stream));
   }
-  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, nullptr, 0, nullptr, d_finish,
+  KmcParams prm{static_cast<int32_t>(n_tt), d_tt_time, d_tt_temp, params.rate_corrector, params.seed, nullptr, 0, nullptr, nullptr, nullptr, d_finish,
                 std::max(select_margin, kSelectMargin)};
   const int walkers_per_block = kKmcThreads / 16;
   const unsigned blocks = static_cast<unsigned>((n_walkers + walkers_per_block - 1) / walkers_per_block);
@@ -962,7 +962,7 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     // Every launch shape computes bit-identical (dE, log E0, rate) (tables on a binary grid, one rate chain), so the
     // result does not depend on when the hand-off happens.  LMC_KMC_HANDOFF=0 switches it off, a value in (0, 1) sets
     // the fraction of the walkers handed over.
-    double keep_fraction = 0.2;
+    double keep_fraction = 0.35;     // measured optimum at the bench shape (profiles/r2_n_handoff_sweep*.txt): 0.25-0.4 within 1 %
     if (const char *v = std::getenv("LMC_KMC_HANDOFF")) keep_fraction = std::atof(v);
     const bool handoff = !instrumented && keep_fraction > 0.0 && keep_fraction < 1.0 && n_walkers >= 2048 && n_steps >= 128;
     kmc_handoff = handoff;
@@ -980,9 +980,13 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
       const void *tail = kmc_team_kernel_choice(false, kmc_smem, &lanes, &team_smem, true);
       prm.handoff_done = nullptr;
       prm.steps_target = d_kmc_target;
+      prm.tail_order = d_kmc_tail_order;
+      prm.tail_count = d_kmc_done + 1;
+      kmc_tail_order_kernel<<<1, 1024, 0, stream>>>(d_kmc_steps, d_kmc_target, d_kmc_error, n_walkers, n_steps, d_kmc_tail_order, d_kmc_done + 1);
+      // (fewer resident blocks per SM for the tail -- 5, 4, 3 instead of 7 -- measured: no gain, profiles/r2_n_tail_sweep.txt)
       void *args[] = {&lat, &tab, &d_occ, const_cast<int64_t *>(&lat.padded_size), &n_walkers, &st, &prm, &n_steps, &d_u1, &d_u2, &tr};
       LMC_CUDA(cudaLaunchKernel(tail, dim3(static_cast<unsigned>(n_walkers)), dim3(static_cast<unsigned>(12 * lanes + 32)), args, team_smem, stream));
-      ++launch_count;
+      launch_count += 3;            // kmc_target_kernel, kmc_tail_order_kernel and the tail kernel, besides kmc_run_kernel (time_end)
     }
   }
   time_end();

@@ -132,7 +132,8 @@ class Engine {
   bool kmc_team_resident_occ{false};   // ... and whether that launch kept the walkers' occupancy in shared memory
   bool kmc_handoff{false};             // the last half-warp launch handed its tail to the latency kernel
   int64_t *d_kmc_target{nullptr};      // hybrid launch: the step number every walker has to reach
-  int *d_kmc_done{nullptr};            // hybrid launch: walkers that are through
+  int *d_kmc_done{nullptr};            // hybrid launch: [0] walkers that are through, [1] walkers in the tail
+  int32_t *d_kmc_tail_order{nullptr};  // hybrid launch: the tail's walkers, most steps left first
   const void *kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out, bool for_tail = false);
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};

@@ -45,6 +45,7 @@ struct KmcParams {
   int *handoff_done;
   int32_t handoff_threshold;
   const int64_t *steps_target;
+  const int32_t *tail_order, *tail_count;   // tail: block b takes walker tail_order[b] (most steps left first), b < *tail_count
   unsigned long long *finish_ns;   // diagnostics (LMC_KMC_FINISH_TIMES=1): %globaltimer when a walker's half-warp leaves kmc_run_kernel; else null
   double select_margin;      // latency kernel: rounding margin of its one-pass event selection (select_event_fast); > 1 = always the sequential form
 };
@@ -138,6 +139,36 @@ __device__ __forceinline__ void barrier_and_rate_chain(double dE, double log_e0,
   }
   ea_out = ea;
   rate_out = rate;
+}
+
+// Hybrid launch, between the two kernels: the walkers that still have steps to do, those with the most steps left first
+// (64 classes; the latency kernel's blocks start in this order, so the longest remainder is not left for last).  One block.
+__global__ void kmc_tail_order_kernel(const int64_t *__restrict__ steps, const int64_t *__restrict__ target, const int32_t *__restrict__ error, int n,
+                                      int64_t n_steps, int32_t *__restrict__ order, int32_t *__restrict__ count) {
+  __shared__ int s_hist[64], s_start[64];
+  for (int q = threadIdx.x; q < 64; q += blockDim.x) s_hist[q] = 0;
+  __syncthreads();
+  auto cls = [&](int w) -> int {             // 0 = most steps left; -1 = nothing to do
+    const int64_t left = error[w] ? 0 : target[w] - steps[w];
+    if (left <= 0) return -1;
+    const int64_t c = 63 - (left * 63) / (n_steps > 0 ? n_steps : 1);
+    return static_cast<int>(c < 0 ? 0 : (c > 63 ? 63 : c));
+  };
+  for (int w = threadIdx.x; w < n; w += blockDim.x) {
+    const int c = cls(w);
+    if (c >= 0) atomicAdd(&s_hist[c], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int at = 0;
+    for (int q = 0; q < 64; ++q) { s_start[q] = at; at += s_hist[q]; }
+    *count = at;
+  }
+  __syncthreads();
+  for (int w = threadIdx.x; w < n; w += blockDim.x) {
+    const int c = cls(w);
+    if (c >= 0) order[atomicAdd(&s_start[c], 1)] = w;
+  }
 }
 
 struct KmcTraceDev {         // optional per-step records, [walker][n_steps]; any pointer may be null

@@ -48,11 +48,14 @@ template <int G, bool kInstrumented, bool kSmemOcc>
 __global__ void __launch_bounds__(12 * G + 32, G == 8 ? 7 : (G == 16 ? 3 : 1))     // resident blocks per SM the dispatch counts on
 kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stride, int n_walkers, KmcState st, KmcParams prm,
                     int64_t n_steps_all, const double *__restrict__ replay_u1, const double *__restrict__ replay_u2, KmcTraceDev tr) {
-  // tail of a hybrid launch (prm.steps_target): this walker's remaining steps; most blocks have none and leave at once
+  // tail of a hybrid launch (prm.steps_target): block b takes the walker with the b-th most steps left, for exactly those
+  // steps; the blocks beyond the list leave at once
   int64_t n_steps = n_steps_all;
+  int w = blockIdx.x;
   if (prm.steps_target) {
-    if (static_cast<int>(blockIdx.x) >= n_walkers) return;
-    n_steps = prm.steps_target[blockIdx.x] - st.steps[blockIdx.x];
+    if (static_cast<int>(blockIdx.x) >= *prm.tail_count) return;
+    w = prm.tail_order[blockIdx.x];
+    n_steps = prm.steps_target[w] - st.steps[w];
     if (n_steps <= 0) return;
   }
   static_assert(G == 8 || G == 16 || G == 32, "lanes per candidate jump");
@@ -93,7 +96,6 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
     }
   }
   __syncthreads();
-  const int w = blockIdx.x;
   if (w >= n_walkers || st.error[w] != 0 || st.vacancy[w] < 0) return;     // uniform over the block
   uint8_t *o = occ + w * walker_stride;
   uint8_t *s_occ = reinterpret_cast<uint8_t *>(s_A2 + tab.n_species * kEnvN * tab.n_species * 2);
