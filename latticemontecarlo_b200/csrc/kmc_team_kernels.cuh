@@ -18,9 +18,11 @@
 //    select, writes the jump, publishes the new vacancy site and arrives at barrier B, on which the event threads wait.
 //    The residence time, the clock, T(t) and the rate corrector are updated after that, off the critical path.
 //
-// Same Philox stream (key = seed ^ walker, counter = step number) and same select arithmetic as kmc_run_kernel; the
-// contracted sums are added in a different order (tree over lanes), i.e. (dE, Ea) agree to ~1e-16 relative and the
-// trajectories agree unless a cumulative probability falls within that distance of the drawn uniform.
+// Same Philox stream (key = seed ^ walker, counter = step number), same (Ea, rate) chain and same select as kmc_run_kernel.
+// The contracted sums are added in a different order (tree over lanes), but the folded tables sit on a binary grid
+// (Engine::load_coefficients) on which every partial sum is exact, so (dE, log E0) -- and with them rates, clocks,
+// energies and trajectories -- are bit-identical to kmc_run_kernel's.  That is what lets Engine::kmc_run hand the tail of
+// a large launch from that kernel to this one (prm.steps_target / tail_order) without the result depending on when.
 #pragma once
 #include "kmc_kernels.cuh"
 #ifdef LMC_KMC_TEAM_PROFILE

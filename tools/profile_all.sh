@@ -14,6 +14,7 @@ cap() {
   python tools/ncu_by_line.py /tmp/${tag}_$name.ncu-rep $kern 25 > gpurun_out/${tag}_${name}_lines.txt 2>&1
 }
 cap kmc_run_kernel 'kmc_run_kernel' 0 python tools/kmc_once.py 8192 2048
+cap kmc_tail 'kmc_team_run_kernel' 0 python tools/kmc_once.py 8192 2048
 cap kmc_team_1024 'kmc_team_run_kernel' 1 python tools/kmc_team_probe.py 1024 2048 8
 cap kmc_team_single 'kmc_team_run_kernel' 1 python tools/kmc_team_probe.py 1 20000 40
 cap kmc_chain_run_kernel 'kmc_chain_run_kernel' 0 python tools/chain_once.py 8192 256
