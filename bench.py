@@ -317,7 +317,7 @@ def run_ours(args):
         "walkers_advanced_all_steps": int(advanced_all), "walkers_total": W_total,
         "walker_age_hops_during_timed_region": head["age_hops"],
         "roofline": {"kernel": kmc_kernel_name(head["lanes"], head["resident_occupancy"], head["handoff"]), "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H) if head["lanes"] == 0 else recorded_traffic("kmc_team_run_kernel", walkers=W, hops=H, lanes=head["lanes"]), "peak_kind": peak_kind,
+                     "frac": achieved / peak, "traffic": recorded_traffic("kmc_run_kernel", walkers=W, hops=H, handoff=bool(head["handoff"])) if head["lanes"] == 0 else recorded_traffic("kmc_team_run_kernel", walkers=W, hops=H, lanes=head["lanes"]), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": int(W * H * BYTES_PER_KMC_STEP),
                      "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
                              "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"

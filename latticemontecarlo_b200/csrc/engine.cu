@@ -1014,6 +1014,20 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
       std::fprintf(stderr, "kmc finish times (%zu walkers, kernel %.3f ms), fraction of the kernel time at which the given fraction of walkers had finished:", t.size(), kernel_ns * 1e-6);
       for (double q : {0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 0.95, 0.98, 0.99, 0.995, 0.999})
         std::fprintf(stderr, " q%.3g=%.3f", q, 1.0 - static_cast<double>(t.back() - t[static_cast<size_t>(q * (t.size() - 1))]) / kernel_ns);
+      // persistence of a walker's cost from launch to launch (decides whether the previous launch can order the next one)
+      static std::vector<unsigned long long> previous;
+      if (previous.size() == fin.size()) {
+        double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+        const double n = static_cast<double>(fin.size());
+        for (size_t w = 0; w < fin.size(); ++w) {
+          const double x = static_cast<double>(previous[w]), y = static_cast<double>(fin[w] - t.front());
+          sx += x; sy += y; sxx += x * x; syy += y * y; sxy += x * y;
+        }
+        const double cov = sxy - sx * sy / n, vx = sxx - sx * sx / n, vy = syy - sy * sy / n;
+        std::fprintf(stderr, " | correlation with the previous launch's finish times %.3f", cov / std::sqrt(vx * vy));
+      }
+      previous.resize(fin.size());
+      for (size_t w = 0; w < fin.size(); ++w) previous[w] = fin[w] - t.front();
       std::fprintf(stderr, "\n");
     }
   }
