@@ -322,7 +322,7 @@ def run_ours(args):
                      "note": "effective bandwidth: 3810 algorithmic B per KMC step (SURVEY 8(d)); geometry comes from constant "
                              "offset tables and walkers are L2-resident, so physical DRAM traffic is far below this"
                              + ("; the launch duration covers the throughput kernel, the latency kernel that finishes the walkers still "
-                                "running when 65 % were through, and the two one-block helper kernels between them" if head["handoff"] else "")},
+                                "running when all but ~19 per SM were through, and the two one-block helper kernels between them" if head["handoff"] else "")},
         "wall_s_timed_region": head["wall"],
     }
     clocks = head["clocks"]

@@ -211,9 +211,10 @@ int lmc_kmc_last_launch_lanes(const lmc_engine *engine);
 /* 1 if that launch was a latency-kernel launch that kept every walker's occupancy in shared memory (cells up to 48 KB
  * padded, e.g. the 8 x 8 x 8 cell of the batched workload: 5.8 KB; LMC_KMC_TEAM_SMEM=0 switches it off), else 0. */
 int lmc_kmc_last_launch_resident_occupancy(const lmc_engine *engine);
-/* 1 if that launch was a throughput-kernel launch whose tail -- the walkers still running when 65 % were through -- was
- * handed to the latency kernel (>= 2048 walkers, >= 128 steps, no trace / replay; LMC_KMC_HANDOFF=0 switches it off,
- * a value in (0, 1) sets the fraction handed over).  Results are bit-identical with and without the hand-off. */
+/* 1 if that launch was a throughput-kernel launch whose tail -- the walkers still running when all but ~19 per SM (at most
+ * 80 % of the launch) were through -- was handed to the latency kernel (>= 128 steps, no trace / replay;
+ * LMC_KMC_HANDOFF=0 switches it off, a value in (0, 1) sets the fraction handed over).  Results are bit-identical with and
+ * without the hand-off. */
 int lmc_kmc_last_launch_handoff(const lmc_engine *engine);
 /* Second-order ("chain") KMC: mc::KineticMcChainOmpi::Simulate (mc/src/KineticMcChainOmpi.cpp:56-152,
  * mc/include/KineticMcAbstract.h:65-143; the method script/kmc_param.txt:1 selects).  Per step and walker, for each of

@@ -961,10 +961,19 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
     // each of those walkers from where it stopped to its target -- a block per walker runs such a step 2-3 x faster.
     // Every launch shape computes bit-identical (dE, log E0, rate) (tables on a binary grid, one rate chain), so the
     // result does not depend on when the hand-off happens.  LMC_KMC_HANDOFF=0 switches it off, a value in (0, 1) sets
-    // the fraction of the walkers handed over.
-    double keep_fraction = 0.35;     // measured optimum at the bench shape (profiles/r2_n_handoff_sweep*.txt): 0.25-0.4 within 1 %
+    // the fraction of the walkers handed over.  Applies whenever this kernel is chosen (more walkers than the latency
+    // kernel can hold at once) and the launch is long enough to have a tail (>= 128 steps).
+    // How many walkers to hand over (measured on B200, ms per 2048-hop launch, profiles/r2_n_handoff_sweep*.txt and
+    // r2_p_handoff_by_walkers.txt): 8192 walkers -- 35 % is the optimum (14.1; none 16.0, 50 % 14.6); 4096 -- 65 % (9.65; none
+    // 11.5, 35 % 9.9); 2048 and 1536 -- 80 % (8.3; none 10.3, 35 % 8.7).  In walkers that is ~19 per SM (2.7 rounds of the
+    // 7 blocks an SM holds) wherever that is less than 80 % of the launch.
+    int sm_count = 0, cur_dev = 0;
+    LMC_CUDA(cudaGetDevice(&cur_dev));
+    LMC_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, cur_dev));
+    double keep_fraction = std::min(0.8, 19.0 * sm_count / std::max(1, n_walkers));
     if (const char *v = std::getenv("LMC_KMC_HANDOFF")) keep_fraction = std::atof(v);
-    const bool handoff = !instrumented && keep_fraction > 0.0 && keep_fraction < 1.0 && n_walkers >= 2048 && n_steps >= 128;
+    static const int handoff_min_walkers = std::getenv("LMC_KMC_HANDOFF_MIN_WALKERS") ? std::atoi(std::getenv("LMC_KMC_HANDOFF_MIN_WALKERS")) : 256;
+    const bool handoff = !instrumented && keep_fraction > 0.0 && keep_fraction < 1.0 && n_walkers >= handoff_min_walkers && n_steps >= 128;
     kmc_handoff = handoff;
     if (handoff) {
       kmc_target_kernel<<<static_cast<unsigned>((n_walkers + 255) / 256), 256, 0, stream>>>(d_kmc_steps, d_kmc_target, n_walkers, n_steps);
