@@ -296,7 +296,8 @@ def test_one_pass_select_equals_the_sequential_select(golden, tmp_path, monkeypa
         assert np.array_equal(t0[key], t1[key]), key
 
 
-def test_tail_handoff_is_bit_identical(coef_json, monkeypatch, kmc_launch_shape):
+@pytest.mark.parametrize("ramp", [False, True], ids=["constant_T", "T_of_t_and_corrector"])
+def test_tail_handoff_is_bit_identical(coef_json, monkeypatch, kmc_launch_shape, ramp):
     """Thousands of walkers: once most are through, kmc_run_kernel hands the walkers still running to the latency kernel
     (Engine::kmc_run).  Every launch shape computes bit-identical (dE, log E0, rate) -- the folded tables sit on a binary
     grid, so the sums are exact in any order -- hence clocks, energies, sites and occupancies must not depend on whether,
@@ -310,13 +311,18 @@ def test_tail_handoff_is_bit_identical(coef_json, monkeypatch, kmc_launch_shape)
     occ = np.stack([synth.random_alloy(8, 0.03, 0.03, seed=900 + w % 37) for w in range(nw)])
     temps = np.linspace(400.0, 600.0, nw)
 
+    # a T(t) ramp that is log-spaced over eight decades of time, so that the walkers' clocks are on it whatever their scale,
+    # + the rate corrector
+    ramp_table = np.column_stack([np.concatenate([[0.0], np.logspace(-6, 2, 32)]), np.linspace(450.0, 600.0, 33)])
+    kw = dict(time_temperature=ramp_table, rate_corrector=True) if ramp else {}
+
     def run(setting):
         monkeypatch.setenv("LMC_KMC_HANDOFF", setting)
         e.set_occupancy_all(occ)
         e.kmc_reset()
-        e.kmc_run(160, temperatures=temps, seed=5)
+        e.kmc_run(160, temperatures=temps, seed=5, **kw)
         used = e.kmc_last_launch_handoff()
-        e.kmc_run(200, temperatures=temps, seed=5)
+        e.kmc_run(200, temperatures=temps, seed=5, **kw)
         return e.kmc_state(), e.get_occupancy_all(), used
 
     s0, o0, used0 = run("0")
@@ -328,3 +334,5 @@ def test_tail_handoff_is_bit_identical(coef_json, monkeypatch, kmc_launch_shape)
         for key in ("vacancy", "steps", "time", "energy"):
             assert np.array_equal(s0[key], s1[key]), (setting, key)
     assert np.all(s0["steps"] == 360)
+    if ramp:
+        assert len(np.unique(s0["temperature"])) > 16          # the walkers sit at different points of the ramp
