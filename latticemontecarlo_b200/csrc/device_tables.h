@@ -14,6 +14,7 @@ struct DevTables {
   const int32_t *site_delta;     // [2][43]     same for the 43-site neighbourhood, row = zpar
   const int8_t *dir_lut;         // [27]        (dx+1)*9 + (dy+1)*3 + (dz+1) -> direction k, -1 if not a first neighbour
   const int8_t *nn1;             // [12][4]     first-neighbour vectors (x,y,z,0)
+  const uint8_t *kmc_slot;       // [64][12]    event order (rank of the neighbour's lattice id) of jump k by the vacancy's boundary / parity class
   const int8_t *frame_p;         // [12][4]     canonical perpendicular first neighbour of each direction
   const int8_t *pair_off;        // [12][2][60][4] lattice offsets of the ordered pair neighbourhood (debug taps)
   const int8_t *site_off;        // [43][4]

@@ -249,6 +249,28 @@ void Engine::upload_geometry_tables() {
   tab.site_delta = to_device(site_delta);
   tab.dir_lut = to_device(dir_lut);
   tab.nn1 = to_device(nn1);
+  {
+    // Event order of the 12 jumps of a vacancy (KineticMcFirstOmp.cpp:52-68: ascending lattice id of the neighbour).  It
+    // depends on the vacancy site only through, per axis, whether a neighbour wraps around the period (coordinate 0 or
+    // period - 1) and the coordinate's parity: 4 classes per axis.  slot[class][k] = rank of jump k's neighbour id,
+    // ranked here once on a representative site of each class (periods are even and >= 8: factors >= 4).
+    std::vector<uint8_t> slot(64 * 12, 0);
+    const int period[3] = {2 * lat.fx, 2 * lat.fy, 2 * lat.fz};
+    auto representative = [&](int c, int axis) { return c == 0 ? 0 : (c == 3 ? period[axis] - 1 : 1 + c); };
+    for (int cls = 0; cls < 64; ++cls) {
+      const int R[3] = {representative(cls >> 4, 0), representative((cls >> 2) & 3, 1), representative(cls & 3, 2)};
+      if ((R[0] + R[1] + R[2]) & 1) continue;                  // classes of the other parity hold no site
+      int64_t id[12];
+      for (int k = 0; k < 12; ++k)
+        id[k] = lat.id_of_coords(wrap_coord(R[0] + g.nn1[k].x, period[0]), wrap_coord(R[1] + g.nn1[k].y, period[1]), wrap_coord(R[2] + g.nn1[k].z, period[2]));
+      for (int k = 0; k < 12; ++k) {
+        int rank = 0;
+        for (int o2 = 0; o2 < 12; ++o2) rank += id[o2] < id[k];
+        slot[cls * 12 + k] = static_cast<uint8_t>(rank);
+      }
+    }
+    tab.kmc_slot = to_device(slot);
+  }
   tab.frame_p = to_device(frame_p);
   tab.pair_off = to_device(pair_off);
   tab.site_off = to_device(site_off);

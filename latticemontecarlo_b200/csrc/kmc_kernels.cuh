@@ -171,6 +171,9 @@ __global__ void kmc_tail_order_kernel(const int64_t *__restrict__ steps, const i
   }
 }
 
+// boundary / parity class of a half-unit coordinate (periods are even and >= 8): 0 = coordinate 0, 3 = period - 1, else 1 + parity
+__device__ __forceinline__ int coord_class(int v, int period) { return v == 0 ? 0 : (v == period - 1 ? 3 : 1 + (v & 1)); }
+
 struct KmcTraceDev {         // optional per-step records, [walker][n_steps]; any pointer may be null
   int64_t *from, *to;
   int32_t *slot;
@@ -437,7 +440,8 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   __shared__ uint8_t s_ord_lane[kKmcWalkersPerBlock][12];
   __shared__ uint64_t s_mask_hi[kEnvN];
   __shared__ uint16_t s_pbase[kEnvN];
-  __shared__ __align__(16) uint32_t s_ids[kKmcWalkersPerBlock][12];
+  __shared__ uint8_t s_slot[64][12];               // event order by the vacancy's boundary / parity class (DevTables::kmc_slot)
+  for (int q = threadIdx.x; q < 64 * 12; q += blockDim.x) (&s_slot[0][0])[q] = tab.kmc_slot[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 2 * kBoxCells; q += blockDim.x) s_box[q] = tab.box_delta[q];
   for (int q = threadIdx.x; q < 2 * 12 * kBoxCells; q += blockDim.x) s_envpos[q] = tab.box_envpos[q];
@@ -478,7 +482,6 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
   const uint2 *s_mask_hi2 = reinterpret_cast<const uint2 *>(s_mask_hi);
   const KmcEvalContext ctx{s_box, s_envpos, s_A2v, s_mask_hi2, s_pbase, B_all, tab.pair_C2,
                            tab.n_pair_pairs * tab.n_species * tab.n_species, n_species, solvent, vac_code, tab.barrier_model};
-  uint32_t *ids = s_ids[wl];
   const bool tracing = kInstrumented && (tr.from || tr.to || tr.slot || tr.dt || tr.Ea || tr.dE || tr.total_rate || tr.temperature);
   int err = 0;
 
@@ -503,20 +506,10 @@ kmc_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker_stri
         if (prm.rate_corrector) { corr = rate_correction(c_vac, c_sol, temperature); corr_over_prefactor = corr / kPrefactorHz; }
       }
     }
-    // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted)
+    // 2. BuildEventList: event order = ascending lattice id of the neighbour (adjacency lists are sorted) -- a function of the
+    // vacancy's boundary / parity class only (table ranked by the host)
     const int xj = wrap_coord(X + dxk, px), yj = wrap_coord(Y + dyk, py), zj = wrap_coord(Z + dzk, pz);
-    const uint32_t id_j = static_cast<uint32_t>(lat.id_of_coords(xj, yj, zj));       // num_sites < 2^31 (checked by the host)
-    if (active) ids[lane] = id_j;
-    __syncwarp(hmask);
-    int slot = 0;
-    {
-      const uint4 *idv = reinterpret_cast<const uint4 *>(ids);      // 12 ids = three 16-byte loads
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const uint4 v = idv[q];
-        slot += (v.x < id_j ? 1 : 0) + (v.y < id_j ? 1 : 0) + (v.z < id_j ? 1 : 0) + (v.w < id_j ? 1 : 0);
-      }
-    }
+    const int slot = s_slot[(coord_class(X, px) * 4 + coord_class(Y, py)) * 4 + coord_class(Z, pz)][k];
     double ea = 0.0, de = 0.0, rate = 0.0;
     unsigned mig = 0;
     kmc_scan_and_evaluate<false, kGlobalA>(lat, ctx, o, X, Y, Z, lane, active, k, dmig0, dmig1, list, my_codes, beta, 0, 0u, -1,

@@ -39,10 +39,6 @@ namespace lmc {
 __device__ __forceinline__ void team_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void team_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-// boundary / parity class of a half-unit coordinate (periods are even and >= 8): 0 = coordinate 0, 3 = period - 1, else 1 + parity
-__device__ __forceinline__ int coord_class(int v, int period) { return v == 0 ? 0 : (v == period - 1 ? 3 : 1 + (v & 1)); }
-__device__ __forceinline__ int class_representative(int c, int period) { return c == 0 ? 0 : (c == 3 ? period - 1 : 1 + c); }
-
 // kSmemOcc: the walker's whole (padded) occupancy lives in shared memory for the launch -- small cells only (the 8 x 8 x 8
 // cell of the batched workload is 5.8 KB).  The gather then never leaves the SM (shared-memory latency instead of L1 hits
 // plus two L2 round trips for the lines the previous jump has just written); the selector writes each jump to both copies.
@@ -77,26 +73,13 @@ kmc_team_run_kernel(LatticeDesc lat, DevTables tab, uint8_t *occ, int64_t walker
   __shared__ int s_err;
   // The event order of the 12 jumps (ascending lattice id of the neighbour) depends on the vacancy site only through, per
   // axis, whether a neighbour wraps around the period (coordinate 0 or period - 1) and the coordinate's parity: 4 classes
-  // per axis.  Slot of jump k for every class, ranked once per block on a representative site of the class.
+  // per axis.  Slot of jump k for every class: DevTables::kmc_slot, ranked on the host on a representative site of the class.
   __shared__ uint8_t s_slot[64][12];
   for (int q = threadIdx.x; q < tab.n_species * kEnvN * tab.n_species * 2; q += blockDim.x) s_A2[q] = tab.pair_A2[q];
   for (int q = threadIdx.x; q < kEnvN; q += blockDim.x) { s_mask_hi[q] = tab.pair_mask_hi[q]; s_pbase[q] = tab.pair_base[q]; }
   for (int q = threadIdx.x; q < 24 * kPairDeltaStride; q += blockDim.x) s_delta[q] = tab.pair_delta[q];
   if (threadIdx.x == 0) s_err = 0;
-  {
-    const int px_ = 2 * lat.fx, py_ = 2 * lat.fy, pz_ = 2 * lat.fz;
-    for (int q = threadIdx.x; q < 64 * 12; q += blockDim.x) {
-      const int cls = q / 12, kk = q % 12;
-      const int RX = class_representative(cls >> 4, px_), RY = class_representative((cls >> 2) & 3, py_), RZ = class_representative(cls & 3, pz_);
-      int rank = 0;
-      if (((RX + RY + RZ) & 1) == 0) {             // classes of the other parity hold no site
-        const int64_t id_k = lat.id_of_coords(wrap_coord(RX + tab.nn1[4 * kk], px_), wrap_coord(RY + tab.nn1[4 * kk + 1], py_), wrap_coord(RZ + tab.nn1[4 * kk + 2], pz_));
-        for (int o2 = 0; o2 < 12; ++o2)
-          rank += lat.id_of_coords(wrap_coord(RX + tab.nn1[4 * o2], px_), wrap_coord(RY + tab.nn1[4 * o2 + 1], py_), wrap_coord(RZ + tab.nn1[4 * o2 + 2], pz_)) < id_k;
-      }
-      s_slot[cls][kk] = static_cast<uint8_t>(rank);
-    }
-  }
+  for (int q = threadIdx.x; q < 64 * 12; q += blockDim.x) (&s_slot[0][0])[q] = tab.kmc_slot[q];
   __syncthreads();
   if (w >= n_walkers || st.error[w] != 0 || st.vacancy[w] < 0) return;     // uniform over the block
   uint8_t *o = occ + w * walker_stride;
