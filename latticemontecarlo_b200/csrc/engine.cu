@@ -966,6 +966,7 @@ void Engine::kmc_run(const lmc_kmc_params &params, int64_t n_steps, const double
   const size_t kmc_smem = static_cast<size_t>(species.n) * kEnvN * species.n * 2 * sizeof(double);
   const bool instrumented = tracing || d_u1 != nullptr;      // the first-order kernel reads its tables through L1: no dynamic shared memory
   size_t team_smem = kmc_smem;
+  kmc_handoff = false;
   time_begin();
   if (second_order) {
     LMC_CUDA(cudaFuncSetAttribute(kmc_chain_run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kmc_smem)));
