@@ -349,6 +349,10 @@ int lmc_debug_site(lmc_engine *engine, int32_t walker, int64_t site, int32_t new
 /* ------------------------------------------------------------------------------------------------ host-side tables
  * (no device needed).  Neighbour lists in ascending lattice id like Config::Get{First,Second,Third}NeighborsAdjacencyList. */
 int lmc_engine_neighbors(const lmc_engine *engine, int32_t shell, int64_t site, int64_t *out);
+/* the 12 first neighbours of `site` in the order the first-order KMC kernels file their events (a 64 x 12 table by the
+ * site's boundary / parity class, ranked on the host): must equal lmc_engine_neighbors(1, site), i.e. the event order of
+ * KineticMcFirstOmp::BuildEventList (mc/src/KineticMcFirstOmp.cpp:52-68), for every site.  Host side; used by the tests. */
+int lmc_engine_kmc_event_order(const lmc_engine *engine, int64_t site, int64_t *out12);
 int lmc_engine_site_coords(const lmc_engine *engine, int64_t site, int32_t xyz_half_units[3]);
 /* host evaluation of the ordered id lists (same definition as lmc_debug_pair / lmc_debug_site) */
 int lmc_engine_pair_lists(const lmc_engine *engine, int64_t site_i, int64_t site_j, int64_t *state60, int64_t *mmm58,

@@ -511,6 +511,12 @@ class Engine:
         _check(lib().lmc_engine_neighbors(self.h, int(shell), C.c_int64(int(site)), _p(out)))
         return out
 
+    def kmc_event_order(self, site):
+        """The 12 first neighbours of `site` in the KMC kernels' event order (class table); equals neighbors(1, site)."""
+        out = np.empty(12, dtype=np.int64)
+        _check(lib().lmc_engine_kmc_event_order(self.h, C.c_int64(int(site)), _p(out)))
+        return out
+
     def site_coords(self, site):
         out = (C.c_int32 * 3)()
         _check(lib().lmc_engine_site_coords(self.h, C.c_int64(int(site)), out))

@@ -174,6 +174,46 @@ void *Engine::scratch(size_t bytes) {
   return d_scratch;
 }
 
+// Event order of the 12 jumps of a vacancy (KineticMcFirstOmp.cpp:52-68: ascending lattice id of the neighbour).  It
+// depends on the vacancy site only through, per axis, whether a neighbour wraps around the period (coordinate 0 or
+// period - 1) and the coordinate's parity: 4 classes per axis.  slot[class][k] = rank of jump k's neighbour id, ranked
+// once on a representative site of each class (periods are even and >= 8: factors >= 4).  Host only.
+std::vector<uint8_t> Engine::kmc_event_order_table() const {
+  const Geometry &g = geometry();
+  std::vector<uint8_t> slot(64 * 12, 0);
+  const int period[3] = {2 * lat.fx, 2 * lat.fy, 2 * lat.fz};
+  auto representative = [&](int c, int axis) { return c == 0 ? 0 : (c == 3 ? period[axis] - 1 : 1 + c); };
+  for (int cls = 0; cls < 64; ++cls) {
+    const int R[3] = {representative(cls >> 4, 0), representative((cls >> 2) & 3, 1), representative(cls & 3, 2)};
+    if ((R[0] + R[1] + R[2]) & 1) continue;                  // classes of the other parity hold no site
+    int64_t id[12];
+    for (int k = 0; k < 12; ++k)
+      id[k] = lat.id_of_coords(wrap_coord(R[0] + g.nn1[k].x, period[0]), wrap_coord(R[1] + g.nn1[k].y, period[1]), wrap_coord(R[2] + g.nn1[k].z, period[2]));
+    for (int k = 0; k < 12; ++k) {
+      int rank = 0;
+      for (int o2 = 0; o2 < 12; ++o2) rank += id[o2] < id[k];
+      slot[cls * 12 + k] = static_cast<uint8_t>(rank);
+    }
+  }
+  return slot;
+}
+
+// The 12 first neighbours of `site` in the order the KMC kernels file their events: neighbour of direction k goes to slot
+// table[class(site)][k].  Must equal the ascending-id list of Config::GetFirstNeighborsAdjacencyList for every site.
+void Engine::kmc_event_order(int64_t site, int64_t *neighbours_in_slot_order) const {
+  if (site < 0 || site >= lat.num_sites) throw std::invalid_argument("lattice id out of range");
+  const Geometry &g = geometry();
+  const std::vector<uint8_t> table = kmc_event_order_table();
+  const int period[3] = {2 * lat.fx, 2 * lat.fy, 2 * lat.fz};
+  int X, Y, Z;
+  lat.coords_of_id(site, X, Y, Z);
+  auto cls1 = [](int v, int p) { return v == 0 ? 0 : (v == p - 1 ? 3 : 1 + (v & 1)); };      // coord_class of the kernels
+  const int cls = (cls1(X, period[0]) * 4 + cls1(Y, period[1])) * 4 + cls1(Z, period[2]);
+  for (int k = 0; k < 12; ++k)
+    neighbours_in_slot_order[table[cls * 12 + k]] =
+        lat.id_of_coords(wrap_coord(X + g.nn1[k].x, period[0]), wrap_coord(Y + g.nn1[k].y, period[1]), wrap_coord(Z + g.nn1[k].z, period[2]));
+}
+
 void Engine::upload_geometry_tables() {
   const Geometry &g = geometry();
   std::vector<int32_t> pair_delta(24 * kPairDeltaStride, 0), site_delta(2 * 43);
@@ -249,28 +289,7 @@ void Engine::upload_geometry_tables() {
   tab.site_delta = to_device(site_delta);
   tab.dir_lut = to_device(dir_lut);
   tab.nn1 = to_device(nn1);
-  {
-    // Event order of the 12 jumps of a vacancy (KineticMcFirstOmp.cpp:52-68: ascending lattice id of the neighbour).  It
-    // depends on the vacancy site only through, per axis, whether a neighbour wraps around the period (coordinate 0 or
-    // period - 1) and the coordinate's parity: 4 classes per axis.  slot[class][k] = rank of jump k's neighbour id,
-    // ranked here once on a representative site of each class (periods are even and >= 8: factors >= 4).
-    std::vector<uint8_t> slot(64 * 12, 0);
-    const int period[3] = {2 * lat.fx, 2 * lat.fy, 2 * lat.fz};
-    auto representative = [&](int c, int axis) { return c == 0 ? 0 : (c == 3 ? period[axis] - 1 : 1 + c); };
-    for (int cls = 0; cls < 64; ++cls) {
-      const int R[3] = {representative(cls >> 4, 0), representative((cls >> 2) & 3, 1), representative(cls & 3, 2)};
-      if ((R[0] + R[1] + R[2]) & 1) continue;                  // classes of the other parity hold no site
-      int64_t id[12];
-      for (int k = 0; k < 12; ++k)
-        id[k] = lat.id_of_coords(wrap_coord(R[0] + g.nn1[k].x, period[0]), wrap_coord(R[1] + g.nn1[k].y, period[1]), wrap_coord(R[2] + g.nn1[k].z, period[2]));
-      for (int k = 0; k < 12; ++k) {
-        int rank = 0;
-        for (int o2 = 0; o2 < 12; ++o2) rank += id[o2] < id[k];
-        slot[cls * 12 + k] = static_cast<uint8_t>(rank);
-      }
-    }
-    tab.kmc_slot = to_device(slot);
-  }
+  tab.kmc_slot = to_device(kmc_event_order_table());
   tab.frame_p = to_device(frame_p);
   tab.pair_off = to_device(pair_off);
   tab.site_off = to_device(site_off);
@@ -2064,6 +2083,9 @@ int lmc_debug_site(lmc_engine *engine, int32_t walker, int64_t site, int32_t new
 
 int lmc_engine_neighbors(const lmc_engine *engine, int32_t shell, int64_t site, int64_t *out) {
   return guard([&] { engine->impl->neighbors(shell, site, out); });
+}
+int lmc_engine_kmc_event_order(const lmc_engine *engine, int64_t site, int64_t *out) {
+  return guard([&] { engine->impl->kmc_event_order(site, out); });
 }
 int lmc_engine_site_coords(const lmc_engine *engine, int64_t site, int32_t xyz[3]) {
   return guard([&] {

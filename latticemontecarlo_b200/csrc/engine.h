@@ -134,6 +134,8 @@ class Engine {
   int64_t *d_kmc_target{nullptr};      // hybrid launch: the step number every walker has to reach
   int *d_kmc_done{nullptr};            // hybrid launch: [0] walkers that are through, [1] walkers in the tail
   int32_t *d_kmc_tail_order{nullptr};  // hybrid launch: the tail's walkers, most steps left first
+  std::vector<uint8_t> kmc_event_order_table() const;                        // [64][12], see engine.cu
+  void kmc_event_order(int64_t site, int64_t *neighbours_in_slot_order) const;
   const void *kmc_team_kernel_choice(bool instrumented, size_t table_smem, int *lanes_out, size_t *smem_out, bool for_tail = false);
   // CMC / SA per-replica state (device)
   double *d_cmc_energy{nullptr};

@@ -190,3 +190,16 @@ def test_synthetic_inputs_are_reference_compatible(coef_json):
     e = capi.Engine(4, device=-1)
     e.load_coefficients(coef_json)
     assert e.get_tables()["pair_B"].shape == (3, 556, 3, 3, 3)
+
+
+@pytest.mark.parametrize("factors", [(4, 4, 4), (4, 5, 6), (6, 4, 5), (8, 8, 8)])
+@pytest.mark.parametrize("order", [capi.ORDER_GENERATE, capi.ORDER_REASSIGNED])
+def test_kmc_event_order_table_equals_sorted_neighbour_ids(factors, order):
+    """The first-order KMC kernels take the event order of the 12 jumps (KineticMcFirstOmp::BuildEventList: ascending
+    lattice id of the neighbour) from a 64 x 12 table by the vacancy's boundary / parity class instead of ranking ids per
+    step.  The table must reproduce the sorted first-neighbour list for EVERY site: all boundary classes, non-cubic
+    cells, both id orders."""
+    e = capi.Engine(factors, id_order=order, device=-1)
+    n = 4 * factors[0] * factors[1] * factors[2]
+    for site in range(n):
+        assert np.array_equal(e.kmc_event_order(site), e.neighbors(1, site)), site
