@@ -372,8 +372,13 @@ int32_t lmc_tables_group_sizes(int32_t which, int32_t n_elements, int32_t *sizes
  * which: 0 pair_C [m][3], 1 pair_A [m][58][n][3], 2 pair_B [m][556][n][n][3]   (jump tables: dE, logD, logKs)
  *        3 site_C [x],    4 site_A [x][42][n+1],  5 site_B [x][204][n+1][n+1]  (single-site tables, codes incl. vacancy)
  *        6 "Base".theta as read (one entry per cluster type in ClusterIndexer order)
+ *        7 / 8 / 9 the folded tables the KMC kernels walk: [..][2] = (dE, log E0 = logKs + 2 logD) of pair_C / pair_A / pair_B,
+ *        every entry rounded to a multiple of 2^-bits (lmc_engine_kmc_table_grid_bits) so that sums are exact in any order
  * Species codes are positions in the element set sorted by name; the vacancy is code n.  Returns the length. */
 int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *out, int64_t capacity);
+/* binary grid of the folded KMC tables: bits[c] for component c (0: dE, 1: log E0); chosen so that the largest sum any
+ * environment can produce, |C| + sum_t max|A_t| + sum_pairs max|B|, stays below 2^(51 - bits[c]) */
+int lmc_engine_kmc_table_grid_bits(const lmc_engine *engine, int32_t bits[2]);
 /* environment pairs (t,u), t<u, as indices into the environment (ordered state list without the centre site(s)):
  * which 0: the 556 pairs of the jump environment, 1: the 204 pairs of the site environment. Returns the pair count. */
 int32_t lmc_tables_env_pairs(int32_t which, int16_t *pairs, int32_t capacity_pairs);

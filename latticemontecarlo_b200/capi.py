@@ -200,6 +200,20 @@ class Engine:
     def lattice_jump(self, a, b, walker=0):
         _check(lib().lmc_engine_lattice_jump(self.h, int(walker), C.c_int64(int(a)), C.c_int64(int(b))))
 
+    def kmc_folded_tables(self):
+        """The (dE, log E0) tables the KMC kernels walk, on their binary grid, and the grid bits per component."""
+        lib().lmc_engine_get_tables.restype = C.c_int64
+        raw = []
+        for which in (7, 8, 9):
+            n = _check(lib().lmc_engine_get_tables(self.h, which, None, C.c_int64(0)))
+            buf = np.empty(n, dtype=np.float64)
+            _check(lib().lmc_engine_get_tables(self.h, which, _p(buf), C.c_int64(n)))
+            raw.append(buf)
+        bits = (C.c_int32 * 2)()
+        _check(lib().lmc_engine_kmc_table_grid_bits(self.h, bits))
+        n = len(self.element_set)
+        return dict(C=raw[0].reshape(n, 2), A=raw[1].reshape(n, 58, n, 2), B=raw[2].reshape(n, -1, n, n, 2), bits=(int(bits[0]), int(bits[1])))
+
     def get_tables(self):
         """Host copies of the contracted coefficient tables, reshaped (see lmc_engine_get_tables)."""
         lib().lmc_engine_get_tables.restype = C.c_int64

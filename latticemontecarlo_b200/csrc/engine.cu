@@ -391,54 +391,55 @@ void Engine::load_coefficients(const Coefficients &co, int model) {
   site_tables = build_site_tables(species, coefficients);
   energy_tables = build_energy_tables(species, coefficients);
   has_coefficients = true;
+  // [..][3] = (dE, logD, logKs)  ->  [..][2] = (dE, logKs + 2 logD) for the KMC kernels.  The folded tables are put on a
+  // common binary grid: every entry is rounded to a multiple of 2^-q, q per component chosen so that the largest
+  // possible sum |C| + sum_t max|A_t| + sum_pairs max|B| stays below 2^(51-q).  Then every partial sum any kernel can
+  // form is a multiple of 2^-q below 2^52 of them, i.e. EXACT in double: the contracted sums do not depend on the
+  // order of the additions, and the launch shapes of the KMC driver (half-warp per walker: sequential; block per walker:
+  // tree over lanes) deliver bit-identical (dE, log E0).  Cost: <= 2^-(q+1) per entry (q = 44..48 for eV-sized
+  // coefficients: ~1e-14 eV), against a parity tolerance of 1e-9 eV.
+  auto fold = [](const std::vector<double> &v) {
+    std::vector<double> out(v.size() / 3 * 2);
+    for (size_t i = 0; i < v.size() / 3; ++i) {
+      out[2 * i] = v[3 * i];
+      out[2 * i + 1] = v[3 * i + 2] + 2.0 * v[3 * i + 1];
+    }
+    return out;
+  };
+  std::vector<double> &C2 = folded_C, &A2 = folded_A, &B2 = folded_B;
+  C2 = fold(pair_tables.C); A2 = fold(pair_tables.A); B2 = fold(pair_tables.B);
+  {
+    const size_t n = static_cast<size_t>(species.n), n_pairs = geometry().env_pairs.size();
+    for (int c = 0; c < 2; ++c) {
+      double bound = 0.0;
+      for (size_t m = 0; m < n; ++m) {
+        double b = std::fabs(C2[m * 2 + c]);
+        for (size_t t = 0; t < static_cast<size_t>(kEnvN); ++t) {
+          double mx = 0.0;
+          for (size_t e = 0; e < n; ++e) mx = std::max(mx, std::fabs(A2[((m * kEnvN + t) * n + e) * 2 + c]));
+          b += mx;
+        }
+        for (size_t pq = 0; pq < n_pairs; ++pq) {
+          double mx = 0.0;
+          for (size_t e = 0; e < n * n; ++e) mx = std::max(mx, std::fabs(B2[((m * n_pairs + pq) * n * n + e) * 2 + c]));
+          b += mx;
+        }
+        bound = std::max(bound, b);
+      }
+      int exp2 = 0;
+      std::frexp(std::max(bound, 1e-300), &exp2);            // bound < 2^exp2
+      const int q = std::min(60, 51 - exp2);
+      pair_grid_bits[c] = q;
+      const double up = std::ldexp(1.0, q), down = std::ldexp(1.0, -q);
+      for (std::vector<double> *tabv : {&C2, &A2, &B2})
+        for (size_t i = static_cast<size_t>(c); i < tabv->size(); i += 2) (*tabv)[i] = std::nearbyint((*tabv)[i] * up) * down;
+    }
+  }
   if (device >= 0) {
     cudaSetDevice(device);
-    // [..][3] = (dE, logD, logKs)  ->  [..][2] = (dE, logKs + 2 logD) for the KMC kernels.  The folded tables are put on a
-    // common binary grid: every entry is rounded to a multiple of 2^-q, q per component chosen so that the largest
-    // possible sum |C| + sum_t max|A_t| + sum_pairs max|B| stays below 2^(51-q).  Then every partial sum any kernel can
-    // form is a multiple of 2^-q below 2^52 of them, i.e. EXACT in double: the contracted sums do not depend on the
-    // order of the additions, and the launch shapes of the KMC driver (half-warp per walker: sequential; block per walker:
-    // tree over lanes) deliver bit-identical (dE, log E0).  Cost: <= 2^-(q+1) per entry (q = 44..48 for eV-sized
-    // coefficients: ~1e-14 eV), against a parity tolerance of 1e-9 eV.
-    auto fold = [](const std::vector<double> &v) {
-      std::vector<double> out(v.size() / 3 * 2);
-      for (size_t i = 0; i < v.size() / 3; ++i) {
-        out[2 * i] = v[3 * i];
-        out[2 * i + 1] = v[3 * i + 2] + 2.0 * v[3 * i + 1];
-      }
-      return out;
-    };
-    std::vector<double> C2 = fold(pair_tables.C), A2 = fold(pair_tables.A), B2 = fold(pair_tables.B);
-    {
-      const size_t n = static_cast<size_t>(species.n), n_pairs = static_cast<size_t>(tab.n_pair_pairs);
-      for (int c = 0; c < 2; ++c) {
-        double bound = 0.0;
-        for (size_t m = 0; m < n; ++m) {
-          double b = std::fabs(C2[m * 2 + c]);
-          for (size_t t = 0; t < static_cast<size_t>(kEnvN); ++t) {
-            double mx = 0.0;
-            for (size_t e = 0; e < n; ++e) mx = std::max(mx, std::fabs(A2[((m * kEnvN + t) * n + e) * 2 + c]));
-            b += mx;
-          }
-          for (size_t pq = 0; pq < n_pairs; ++pq) {
-            double mx = 0.0;
-            for (size_t e = 0; e < n * n; ++e) mx = std::max(mx, std::fabs(B2[((m * n_pairs + pq) * n * n + e) * 2 + c]));
-            b += mx;
-          }
-          bound = std::max(bound, b);
-        }
-        int exp2 = 0;
-        std::frexp(std::max(bound, 1e-300), &exp2);            // bound < 2^exp2
-        const int q = std::min(60, 51 - exp2);
-        pair_grid_bits[c] = q;
-        const double up = std::ldexp(1.0, q), down = std::ldexp(1.0, -q);
-        for (std::vector<double> *tabv : {&C2, &A2, &B2})
-          for (size_t i = static_cast<size_t>(c); i < tabv->size(); i += 2) (*tabv)[i] = std::nearbyint((*tabv)[i] * up) * down;
-      }
-    }
-    tab.pair_C2 = to_device(C2);
-    tab.pair_A2 = to_device(A2);
-    tab.pair_B2 = to_device(B2);
+    tab.pair_C2 = to_device(folded_C);
+    tab.pair_A2 = to_device(folded_A);
+    tab.pair_B2 = to_device(folded_B);
     tab.pair_C = to_device(pair_tables.C);
     tab.pair_A = to_device(pair_tables.A);
     tab.pair_B = to_device(pair_tables.B);
@@ -2084,6 +2085,13 @@ int lmc_debug_site(lmc_engine *engine, int32_t walker, int64_t site, int32_t new
 int lmc_engine_neighbors(const lmc_engine *engine, int32_t shell, int64_t site, int64_t *out) {
   return guard([&] { engine->impl->neighbors(shell, site, out); });
 }
+int lmc_engine_kmc_table_grid_bits(const lmc_engine *engine, int32_t bits[2]) {
+  return guard([&] {
+    engine->impl->require_coefficients();
+    bits[0] = engine->impl->pair_grid_bits[0];
+    bits[1] = engine->impl->pair_grid_bits[1];
+  });
+}
 int lmc_engine_kmc_event_order(const lmc_engine *engine, int64_t site, int64_t *out) {
   return guard([&] { engine->impl->kmc_event_order(site, out); });
 }
@@ -2187,7 +2195,10 @@ int64_t lmc_engine_get_tables(const lmc_engine *engine, int32_t which, double *o
       case 4: v = &e.site_tables.A; break;
       case 5: v = &e.site_tables.B; break;
       case 6: v = &e.coefficients.base_theta; break;
-      default: throw std::invalid_argument("which must be 0..6");
+      case 7: v = &e.folded_C; break;
+      case 8: v = &e.folded_A; break;
+      case 9: v = &e.folded_B; break;
+      default: throw std::invalid_argument("which must be 0..9");
     }
     len = static_cast<int64_t>(v->size());
     if (out) std::copy(v->begin(), v->begin() + std::min<int64_t>(len, capacity), out);

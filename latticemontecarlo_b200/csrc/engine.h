@@ -128,6 +128,7 @@ class Engine {
   int64_t *d_kmc_previous{nullptr};
   bool kmc_ready{false};
   int kmc_team_lanes{0};       // lanes per candidate jump of the last first-order KMC launch (0: half-warp kernel)
+  std::vector<double> folded_C, folded_A, folded_B;   // the KMC kernels' tables: (dE, log E0) per entry, on the binary grid (host copies)
   int pair_grid_bits[2]{0, 0};         // the folded KMC tables are multiples of 2^-bits (dE, log E0): exact sums in any order
   bool kmc_team_resident_occ{false};   // ... and whether that launch kept the walkers' occupancy in shared memory
   bool kmc_handoff{false};             // the last half-warp launch handed its tail to the latency kernel

@@ -203,3 +203,54 @@ def test_kmc_event_order_table_equals_sorted_neighbour_ids(factors, order):
     n = 4 * factors[0] * factors[1] * factors[2]
     for site in range(n):
         assert np.array_equal(e.kmc_event_order(site), e.neighbors(1, site)), site
+
+
+@pytest.mark.parametrize("source", ["golden", "synthetic"])
+def test_folded_kmc_tables_sit_on_a_binary_grid_with_exact_sums(golden, coef_json, tmp_path, source):
+    """The (dE, log E0) tables of the KMC kernels are rounded to multiples of 2^-bits with the largest possible sum below
+    2^(51 - bits): then every partial sum is exact in double, so the sequential sums of the half-warp kernel and the tree
+    sums of the block-per-walker kernel are the same numbers (which is what makes the tail hand-off deterministic).
+    Checks: grid membership, the bound, the rounding error against the unrounded fold, and order independence of random
+    environment sums evaluated sequentially, in reverse and as a tree -- in float64, on the host."""
+    e = capi.Engine(4, device=-1)
+    e.load_coefficients(H.golden_json(golden, tmp_path) if source == "golden" else coef_json)
+    F, T = e.kmc_folded_tables(), e.get_tables()
+    n = F["C"].shape[0]
+    for c, bits in enumerate(F["bits"]):
+        scale = 2.0 ** bits
+        unrounded = {"C": T["pair_C"][..., 0] if c == 0 else T["pair_C"][..., 2] + 2.0 * T["pair_C"][..., 1],
+                     "A": T["pair_A"][..., 0] if c == 0 else T["pair_A"][..., 2] + 2.0 * T["pair_A"][..., 1],
+                     "B": T["pair_B"][..., 0] if c == 0 else T["pair_B"][..., 2] + 2.0 * T["pair_B"][..., 1]}
+        bound = 0.0
+        for m in range(n):
+            bound = max(bound, abs(F["C"][m, c]) + np.abs(F["A"][m, :, :, c]).max(axis=1).sum() + np.abs(F["B"][m, :, :, :, c]).max(axis=(1, 2)).sum())
+        assert bound < 2.0 ** (52 - bits)                                    # sums of grid points stay exactly representable
+        for key in ("C", "A", "B"):
+            v = F[key][..., c]
+            assert np.array_equal(v * scale, np.rint(v * scale))             # every entry is a multiple of 2^-bits
+            assert np.max(np.abs(v - unrounded[key])) <= 0.5 / scale         # and the nearest one
+        assert 0.5 / scale < 1e-12                                           # far inside the 1e-9 eV parity tolerance
+    # order independence on random environments: species e_t per site, the pair terms of all 556 pairs
+    pairs = capi.tables_env_pairs("pair")
+    rng = np.random.default_rng(5)
+    for trial in range(20):
+        m = int(rng.integers(0, n))
+        env = rng.integers(0, n, 58)
+        for c in range(2):
+            terms = [F["C"][m, c]] + [F["A"][m, t, env[t], c] for t in range(58)] + [F["B"][m, p, env[t], env[u], c] for p, (t, u) in enumerate(pairs)]
+            terms = np.array(terms)
+            forward = 0.0
+            for x in terms:
+                forward += x
+            backward = 0.0
+            for x in terms[::-1]:
+                backward += x
+            tree = terms.copy()
+            while len(tree) > 1:
+                if len(tree) % 2:
+                    tree = np.append(tree, 0.0)
+                tree = tree[0::2] + tree[1::2]
+            shuffled = 0.0
+            for x in rng.permutation(terms):
+                shuffled += x
+            assert forward == backward == tree[0] == shuffled
